@@ -1,0 +1,176 @@
+/*
+ * gridworld_b200.h -- C-ABI of the B200-native batched grid-world step / FeAR /
+ * observation-render path (libgridworld_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of Henweiz/MARL-Responsible-Nav
+ * (reference files are cited as <file>:<line>, relative to the reference root):
+ *
+ *   gw_reset          <- CustomMAEnv.reset / setup_env     custom/ma_customenv.py:169-215, :338-429
+ *                        CustomEnv.reset                   custom/customenv.py:186-356
+ *   gw_step           <- CustomMAEnv.step  / setup_step    custom/ma_customenv.py:217-334, :432-452
+ *                        CustomEnv.step                    custom/customenv.py:78-183
+ *                        (GWorld.UpdateGWorld              custom/grid_world.py:424-563,
+ *                         Responsibility.FeAR_4_one_actor  custom/Responsibility.py:135-210,
+ *                         get_action_mask                  custom/ma_customenv.py:467-506,
+ *                         obs flatten + reward shaping     maddpg/agent.py:89,128-131,160)
+ *   gw_update_world   <- GWorld.UpdateGWorld (operator level, arbitrary positions/actions)
+ *   gw_fear_one_actor <- Responsibility.FeAR_4_one_actor (operator level, arbitrary close list)
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary; every entry returns gw_status
+ *     (0 = OK) and gw_last_error() gives the message;
+ *   - all array arguments are DEVICE pointers owned by the caller (PyTorch
+ *     tensors: tensor.data_ptr()); the handle owns only the packed per-env
+ *     state, its lookup tables and the statistics accumulators;
+ *   - calls are asynchronous and ordered on the caller's CUDA stream
+ *     (`stream` is a cudaStream_t passed as void*; NULL = legacy default stream);
+ *     nothing in gw_step / gw_reset synchronises or allocates, so both are
+ *     CUDA-graph capturable;
+ *   - there is NO CPU implementation behind this interface: without a CUDA
+ *     device gw_create fails with GW_ENODEV.
+ *   - cells are (row, col) with row-major flat index row*W+col; W must be 16
+ *     and H <= 16 in this version (all shipped scenarios are 10x16).
+ */
+#ifndef GRIDWORLD_B200_H
+#define GRIDWORLD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GW_ABI_VERSION 1
+#define GW_MAX_AGENTS 4
+#define GW_MAX_LEARNERS 2
+#define GW_N_ACTIONS 9        /* custom/custom_agent.py:140-150 */
+#define GW_MAX_POLICIES 16
+#define GW_MAX_H 16
+#define GW_W 16
+
+typedef enum gw_status {
+  GW_OK = 0,
+  GW_EINVAL = -1,   /* bad config / argument / alignment */
+  GW_ENOMEM = -2,
+  GW_ECUDA = -3,    /* CUDA runtime error (message has the cudaError string) */
+  GW_ENODEV = -4,   /* no CUDA device: there is no CPU fallback */
+  GW_ESTATE = -5    /* call order (step before reset) */
+} gw_status;
+
+typedef enum gw_env_kind {
+  GW_ENV_MULTI = 0,   /* custom/ma_customenv.py: learners 0..n_learners-1, one apple each, int rewards */
+  GW_ENV_SINGLE = 1   /* custom/customenv.py: learner 0, one apple, +0.1 shaping, raw-id observation */
+} gw_env_kind;
+
+typedef enum gw_obs_dtype { GW_OBS_F32 = 0, GW_OBS_BF16 = 1 } gw_obs_dtype;
+
+/* Plain-old-data environment description (what the reference keeps in
+ * Scenarios.json + module constants + configs/custom*.yaml). */
+typedef struct gw_config {
+  int32_t struct_size;                 /* = sizeof(gw_config) */
+  int32_t abi_version;                 /* = GW_ABI_VERSION */
+  int32_t height, width;               /* Scenario['Map']['Region'] shape */
+  uint16_t map_rows[GW_MAX_H];         /* bit c of map_rows[r] = Region[r][c] == 1 */
+  int32_t n_agents;                    /* Scenario['N_Agents'] (2..4) */
+  int32_t n_learners;                  /* N_INTELLIGENT_AGENTS (1..2), ma_customenv.py:19 */
+  int32_t env_kind;                    /* gw_env_kind */
+  int8_t apple_row[GW_MAX_LEARNERS];   /* ma_customenv.py:422 / customenv.py:334; -1 = none */
+  int8_t apple_col[GW_MAX_LEARNERS];
+  uint8_t policy_map[GW_MAX_H * GW_W]; /* policy-region index per cell, ma_customenv.py:346-354 */
+  uint8_t mdr_map[GW_MAX_H * GW_W];    /* MdR ACTION id per cell (mdrs[key]['mdr']), :357-365,:445-447 */
+  int32_t n_policies;
+  float step_weights[GW_MAX_POLICIES][3];   /* Policies[key]['stepWeights'] */
+  float dir_weights[GW_MAX_POLICIES][4];    /* Policies[key]['directionWeights'] (Up,Down,Left,Right) */
+  double perturb_prob;                 /* 0.25, ma_customenv.py:441 */
+  int32_t fear;                        /* compute FeAR (WITH_FEAR / fear=True) */
+  int32_t fear_radius;                 /* 5, ma_customenv.py:249 */
+  double fear_weight;                  /* FeAR_weight, maddpg/agent.py:128-130 (shaped_reward output) */
+  int32_t max_steps;                   /* TRAIN_STEPS episode cap used by auto-reset, 0 = none */
+  int32_t auto_reset;                  /* re-spawn finished envs inside gw_step */
+  int32_t obs_dtype;                   /* gw_obs_dtype */
+  int32_t device;                      /* CUDA device ordinal */
+  int64_t num_envs;                    /* E on this handle */
+  int64_t env_id_base;                 /* global id of env 0 (sharding: results do not depend on the split) */
+  uint64_t seed;                       /* device RNG key (Philox4x32-10) */
+} gw_config;
+
+/* Device pointers for one gw_reset / gw_step call.  NULL = not wanted / not given. */
+typedef struct gw_io {
+  /* inputs */
+  const int8_t* learner_actions; /* [E, n_learners]   required by gw_step */
+  const int8_t* npc_actions;     /* [E, n_agents]     replay mode: SelectActionsForAll's draw for every agent
+                                                      (learner columns ignored); NULL = device RNG */
+  const int8_t* spawn;           /* [E, n_agents, 2]  replay mode: (row, col) spawn cells, used whenever an env
+                                                      (re)spawns in this call; NULL = device RNG */
+  /* outputs */
+  void* obs;                     /* [E, n_learners, H*W] f32 or bf16: next policy input (reset obs after an auto-reset) */
+  void* final_obs;               /* [E, n_learners, H*W] written ONLY for envs whose episode ended in this call */
+  float* reward;                 /* [E, n_learners] env reward */
+  float* shaped_reward;          /* [E, n_learners] fear_weight*fear + reward, fp64 math rounded once */
+  double* fear;                  /* [E, n_learners] info["fear"] */
+  uint8_t* terminated;           /* [E, n_learners] */
+  uint8_t* truncated;            /* [E, n_learners] */
+  uint8_t* ended;                /* [E] episode boundary: all-truncated (multi) / terminated|truncated (single) / max_steps */
+  int8_t* action_mask;           /* [E, n_learners, 9] */
+  int8_t* positions;             /* [E, n_agents, 2] agent cells after the step (before any auto-reset) */
+  uint32_t* info;                /* [E] bits 0-3 crash, 4-7 restricted, 8-9 learner crashes, 10-11 apples rewarded,
+                                        12 ended, 13 unresolved collisions (reference prints a warning),
+                                        14-15 distance-shaping reward fired for learner 0/1 */
+} gw_io;
+
+typedef struct gw_stats {          /* sums since gw_create / gw_reset_stats, this handle only */
+  uint64_t env_steps;
+  uint64_t agent_steps;            /* env_steps * n_learners */
+  uint64_t episodes;
+  uint64_t episode_len_sum;
+  uint64_t crashes;                /* learner crashes */
+  uint64_t apples;                 /* apples rewarded */
+  uint64_t unresolved;
+  uint64_t fear_nonzero;           /* learner-steps with fear != 0 */
+  double return_sum;               /* sum of env rewards over finished episodes (all learners) */
+  double fear_sum;
+} gw_stats;
+
+typedef struct gw_handle gw_handle;
+
+int gw_abi_version(void);
+const char* gw_build_info(void);              /* arch, nvcc version */
+int gw_default_config(gw_config* cfg);        /* zero + struct_size/abi_version + reference constants */
+int gw_create(const gw_config* cfg, gw_handle** out);
+int gw_destroy(gw_handle* h);
+const char* gw_last_error(const gw_handle* h); /* h may be NULL (errors from gw_create) */
+
+/* reset envs with reset_mask[e] != 0 (device uint8 [E]); NULL = all */
+int gw_reset(gw_handle* h, const uint8_t* reset_mask, const gw_io* io, void* stream);
+int gw_step(gw_handle* h, const gw_io* io, void* stream);
+int gw_sync(gw_handle* h, void* stream);       /* cudaStreamSynchronize + surface async faults */
+
+/* packed env state (16 bytes/env) for checkpoint / resume; device or host destination */
+size_t gw_state_bytes(const gw_handle* h);
+int gw_get_state(gw_handle* h, void* dst, int dst_is_device, void* stream);
+int gw_set_state(gw_handle* h, const void* src, int src_is_device, void* stream);
+
+int gw_get_stats(gw_handle* h, gw_stats* host_out, void* stream);   /* synchronises the stream */
+int gw_reset_stats(gw_handle* h, void* stream);
+int gw_launch_count(const gw_handle* h, uint64_t* kernels_launched); /* kernels launched by this handle so far */
+
+/* Operator level: C independent world updates (GWorld.UpdateGWorld with explicit actions).
+ * n_agents_per_case NULL = cfg.n_agents everywhere.  apples: [C,2,2] (row,col), row<0 = absent, NULL = no apples;
+ * eaters are agents 0..min(2,n)-1.  Outputs: new_positions [C,4,2], crash/restricted [C,4] (0/1),
+ * caught [C,2,2] = times eater i stood on apple k over the 4 sub-steps. */
+int gw_update_world(gw_handle* h, int64_t n_cases, const int8_t* n_agents_per_case, const int8_t* positions,
+                    const int8_t* actions, const int8_t* apples, int8_t* new_positions, uint8_t* crash,
+                    uint8_t* restricted, int8_t* caught, void* stream);
+
+/* Operator level: C independent FeAR_4_one_actor evaluations.  in_list [C,4] marks the agents present in
+ * ActionID4Agents (the actor's entry is forced on).  Outputs resp [C,4] fp64 (row `actor` of the matrix),
+ * n_mdr / n_act [C,4] valid-move counts. */
+int gw_fear_one_actor(gw_handle* h, int64_t n_cases, const int8_t* n_agents_per_case, const int8_t* positions,
+                      const int8_t* actions, const int8_t* mdr, const int8_t* actor, const uint8_t* in_list,
+                      double* resp, int8_t* n_mdr, int8_t* n_act, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRIDWORLD_B200_H */

@@ -1,0 +1,129 @@
+"""ctypes binding of libgridworld_b200.so (include/gridworld_b200.h).  Fails loudly: there is no fallback."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libgridworld_b200.so")
+
+GW_MAX_AGENTS, GW_MAX_LEARNERS, GW_N_ACTIONS, GW_MAX_POLICIES, GW_MAX_H, GW_W = 4, 2, 9, 16, 16, 16
+GW_OK, GW_EINVAL, GW_ENOMEM, GW_ECUDA, GW_ENODEV, GW_ESTATE = 0, -1, -2, -3, -4, -5
+GW_ENV_MULTI, GW_ENV_SINGLE = 0, 1
+GW_OBS_F32, GW_OBS_BF16 = 0, 1
+
+EXPORTS = ["gw_abi_version", "gw_build_info", "gw_default_config", "gw_create", "gw_destroy", "gw_last_error",
+           "gw_reset", "gw_step", "gw_sync", "gw_state_bytes", "gw_get_state", "gw_set_state", "gw_get_stats",
+           "gw_reset_stats", "gw_launch_count", "gw_update_world", "gw_fear_one_actor"]
+
+
+class GwConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("abi_version", C.c_int32),
+        ("height", C.c_int32), ("width", C.c_int32),
+        ("map_rows", C.c_uint16 * GW_MAX_H),
+        ("n_agents", C.c_int32), ("n_learners", C.c_int32), ("env_kind", C.c_int32),
+        ("apple_row", C.c_int8 * GW_MAX_LEARNERS), ("apple_col", C.c_int8 * GW_MAX_LEARNERS),
+        ("policy_map", C.c_uint8 * (GW_MAX_H * GW_W)), ("mdr_map", C.c_uint8 * (GW_MAX_H * GW_W)),
+        ("n_policies", C.c_int32),
+        ("step_weights", (C.c_float * 3) * GW_MAX_POLICIES), ("dir_weights", (C.c_float * 4) * GW_MAX_POLICIES),
+        ("perturb_prob", C.c_double),
+        ("fear", C.c_int32), ("fear_radius", C.c_int32), ("fear_weight", C.c_double),
+        ("max_steps", C.c_int32), ("auto_reset", C.c_int32), ("obs_dtype", C.c_int32), ("device", C.c_int32),
+        ("num_envs", C.c_int64), ("env_id_base", C.c_int64), ("seed", C.c_uint64),
+    ]
+
+
+class GwIO(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name in (
+        "learner_actions", "npc_actions", "spawn", "obs", "final_obs", "reward", "shaped_reward", "fear",
+        "terminated", "truncated", "ended", "action_mask", "positions", "info")]
+
+
+class GwStats(C.Structure):
+    _fields_ = [("env_steps", C.c_uint64), ("agent_steps", C.c_uint64), ("episodes", C.c_uint64),
+                ("episode_len_sum", C.c_uint64), ("crashes", C.c_uint64), ("apples", C.c_uint64),
+                ("unresolved", C.c_uint64), ("fear_nonzero", C.c_uint64), ("return_sum", C.c_double),
+                ("fear_sum", C.c_double)]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library once.  Raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m marl_responsible_nav_b200.build` "
+            "(or __graft_entry__.build()).  This package has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i64 = C.c_void_p, C.c_int64
+    lib.gw_abi_version.restype = C.c_int
+    lib.gw_build_info.restype = C.c_char_p
+    lib.gw_default_config.argtypes = [C.POINTER(GwConfig)]
+    lib.gw_create.argtypes = [C.POINTER(GwConfig), C.POINTER(vp)]
+    lib.gw_destroy.argtypes = [vp]
+    lib.gw_last_error.argtypes = [vp]
+    lib.gw_last_error.restype = C.c_char_p
+    lib.gw_reset.argtypes = [vp, vp, C.POINTER(GwIO), vp]
+    lib.gw_step.argtypes = [vp, C.POINTER(GwIO), vp]
+    lib.gw_sync.argtypes = [vp, vp]
+    lib.gw_state_bytes.argtypes = [vp]
+    lib.gw_state_bytes.restype = C.c_size_t
+    lib.gw_get_state.argtypes = [vp, vp, C.c_int, vp]
+    lib.gw_set_state.argtypes = [vp, vp, C.c_int, vp]
+    lib.gw_get_stats.argtypes = [vp, C.POINTER(GwStats), vp]
+    lib.gw_reset_stats.argtypes = [vp, vp]
+    lib.gw_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.gw_update_world.argtypes = [vp, i64] + [vp] * 8 + [vp]
+    lib.gw_fear_one_actor.argtypes = [vp, i64] + [vp] * 9 + [vp]
+    if lib.gw_abi_version() != 1:
+        raise RuntimeError("libgridworld_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc, handle=None, what=""):
+    if rc == GW_OK:
+        return
+    msg = load().gw_last_error(handle)
+    raise RuntimeError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def build_config(scenario, num_envs=1, env_kind="multi", fear=True, fear_weight=0.0, fear_radius=5, n_agents=None,
+                 n_learners=None, apples=None, max_steps=150, auto_reset=True, obs_bf16=False, seed=0, env_id_base=0,
+                 perturb_prob=0.25, device=0) -> GwConfig:
+    """Fill a gw_config from a Scenario (host only; no library call, no GPU needed)."""
+    kind = {"multi": GW_ENV_MULTI, "single": GW_ENV_SINGLE}[env_kind]
+    H, W = scenario.shape
+    n_agents = int(n_agents if n_agents is not None else scenario.n_agents)
+    n_learners = int(n_learners if n_learners is not None else (2 if env_kind == "multi" else 1))
+    if apples is None:
+        apples = ((9, 0), (5, 10))[:n_learners] if env_kind == "multi" else ((9, 15),)   # ma_customenv.py:422 / customenv.py:334
+    cfg = GwConfig()
+    cfg.struct_size, cfg.abi_version = C.sizeof(GwConfig), 1
+    cfg.height, cfg.width = H, W
+    for r, bits in enumerate(scenario.map_rows()):
+        cfg.map_rows[r] = bits
+    cfg.n_agents, cfg.n_learners, cfg.env_kind = n_agents, n_learners, kind
+    for k in range(GW_MAX_LEARNERS):
+        a = apples[k] if k < len(apples) else None
+        cfg.apple_row[k], cfg.apple_col[k] = (int(a[0]), int(a[1])) if a is not None else (-1, -1)
+    for r in range(H):
+        for c in range(W):
+            cfg.policy_map[r * GW_W + c] = int(scenario.policy_index[r, c])
+            cfg.mdr_map[r * GW_W + c] = int(scenario.mdr_action[r, c])
+    cfg.n_policies = len(scenario.policies)
+    for i, (sw, dw) in enumerate(scenario.policies):
+        for s_ in range(3):
+            cfg.step_weights[i][s_] = float(sw[s_])
+        for d in range(4):
+            cfg.dir_weights[i][d] = float(dw[d])
+    cfg.perturb_prob = float(perturb_prob)
+    cfg.fear, cfg.fear_radius, cfg.fear_weight = int(bool(fear)), int(fear_radius), float(fear_weight)
+    cfg.max_steps, cfg.auto_reset = int(max_steps), int(bool(auto_reset))
+    cfg.obs_dtype = GW_OBS_BF16 if obs_bf16 else GW_OBS_F32
+    cfg.device = int(device)
+    cfg.num_envs, cfg.env_id_base, cfg.seed = int(num_envs), int(env_id_base), int(seed) & (2 ** 64 - 1)
+    return cfg

@@ -1,0 +1,254 @@
+"""BatchedGridWorld: E independent grid worlds advanced per kernel launch (tensor API).
+
+Host side is PyTorch only for device memory and streams; every computation happens in
+csrc/libgridworld_b200.so through the C-ABI of include/gridworld_b200.h.  No CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .scenarios import Scenario, builtin_scenario
+
+MA_APPLES = ((9, 0), (5, 10))        # custom/ma_customenv.py:422
+SINGLE_APPLE = ((9, 15),)            # custom/customenv.py:334
+
+
+@dataclass
+class StepOutput:
+    """Device tensors written by one gw_reset / gw_step call (views of the env's own buffers unless
+    the caller passed its own)."""
+    obs: torch.Tensor                       # [E, n_learners, H*W] (mlp) or [E, n_learners, 1, H, W] (cnn)
+    action_mask: torch.Tensor               # int8 [E, n_learners, 9]
+    positions: torch.Tensor                 # int8 [E, n_agents, 2]
+    reward: Optional[torch.Tensor] = None        # f32 [E, n_learners]
+    shaped_reward: Optional[torch.Tensor] = None  # f32 [E, n_learners]  FeAR_weight*fear + reward
+    fear: Optional[torch.Tensor] = None          # f64 [E, n_learners]
+    terminated: Optional[torch.Tensor] = None    # u8 [E, n_learners]
+    truncated: Optional[torch.Tensor] = None     # u8 [E, n_learners]
+    ended: Optional[torch.Tensor] = None         # u8 [E]
+    info: Optional[torch.Tensor] = None          # int32 [E] packed (see gridworld_b200.h)
+    final_obs: Optional[torch.Tensor] = None     # like obs; rows valid where ended != 0
+
+
+def _check(t: Optional[torch.Tensor], name, dtype, shape, device):
+    if t is None:
+        return None
+    if t.device != device or t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+        raise ValueError(f"{name}: expected contiguous {dtype} tensor of shape {tuple(shape)} on {device}, "
+                         f"got {t.dtype} {tuple(t.shape)} on {t.device}")
+    return t
+
+
+class BatchedGridWorld:
+    def __init__(self, scenario: Union[str, Scenario] = "Level 3", num_envs: int = 1, device="cuda",
+                 env_kind: str = "multi", fear: bool = True, fear_weight: float = 0.0, fear_radius: int = 5,
+                 n_agents: Optional[int] = None, n_learners: Optional[int] = None,
+                 apples: Optional[Sequence[Tuple[int, int]]] = None, max_steps: int = 150,
+                 auto_reset: bool = True, obs_dtype: torch.dtype = torch.float32, obs_layout: str = "mlp",
+                 seed: int = 0, env_id_base: int = 0, perturb_prob: float = 0.25):
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedGridWorld needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = N.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("BatchedGridWorld runs on CUDA devices only")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.scenario = builtin_scenario(scenario) if isinstance(scenario, str) else scenario
+        sc = self.scenario
+        self.kind = {"multi": N.GW_ENV_MULTI, "single": N.GW_ENV_SINGLE}[env_kind]
+        self.n_agents = int(n_agents if n_agents is not None else sc.n_agents)
+        self.n_learners = int(n_learners if n_learners is not None else (2 if env_kind == "multi" else 1))
+        self.num_envs = int(num_envs)
+        self.H, self.W = sc.shape
+        self.obs_len = self.H * self.W
+        if obs_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("obs_dtype must be torch.float32 or torch.bfloat16")
+        if obs_layout not in ("mlp", "cnn"):
+            raise ValueError("obs_layout must be 'mlp' ([E,L,H*W]) or 'cnn' ([E,L,1,H,W])")
+        self.obs_dtype, self.obs_layout = obs_dtype, obs_layout
+        if apples is None:
+            apples = MA_APPLES[:self.n_learners] if env_kind == "multi" else SINGLE_APPLE
+        self.apples = tuple(tuple(a) if a is not None else None for a in apples)
+
+        cfg = N.build_config(sc, num_envs=self.num_envs, env_kind=env_kind, fear=fear, fear_weight=fear_weight,
+                             fear_radius=fear_radius, n_agents=self.n_agents, n_learners=self.n_learners,
+                             apples=self.apples, max_steps=max_steps, auto_reset=auto_reset,
+                             obs_bf16=(obs_dtype == torch.bfloat16), seed=seed, env_id_base=env_id_base,
+                             perturb_prob=perturb_prob, device=self.device.index)
+        probe = N.GwConfig()
+        N.check(self.lib.gw_default_config(C.byref(probe)), None, "gw_default_config")
+        if probe.struct_size != C.sizeof(N.GwConfig):
+            raise RuntimeError("gw_config layout mismatch between ctypes and the library")
+        self.cfg = cfg
+        self.fear, self.fear_weight, self.auto_reset, self.max_steps = bool(fear), float(fear_weight), bool(auto_reset), int(max_steps)
+        h = C.c_void_p()
+        N.check(self.lib.gw_create(C.byref(cfg), C.byref(h)), None, "gw_create")
+        self._h = h
+
+        E, L, A, dev = self.num_envs, self.n_learners, self.n_agents, self.device
+        self._obs_shape = (E, L, self.obs_len)
+        self.buf = StepOutput(
+            obs=torch.empty(self._obs_shape, dtype=obs_dtype, device=dev),
+            action_mask=torch.empty((E, L, N.GW_N_ACTIONS), dtype=torch.int8, device=dev),
+            positions=torch.empty((E, A, 2), dtype=torch.int8, device=dev),
+            reward=torch.zeros((E, L), dtype=torch.float32, device=dev),
+            shaped_reward=torch.zeros((E, L), dtype=torch.float32, device=dev),
+            fear=torch.zeros((E, L), dtype=torch.float64, device=dev),
+            terminated=torch.zeros((E, L), dtype=torch.uint8, device=dev),
+            truncated=torch.zeros((E, L), dtype=torch.uint8, device=dev),
+            ended=torch.zeros((E,), dtype=torch.uint8, device=dev),
+            info=torch.zeros((E,), dtype=torch.int32, device=dev),
+            final_obs=None)
+
+    # ------------------------------------------------------------------ helpers
+    def close(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._h = None
+            self.lib.gw_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _view(self, obs: torch.Tensor) -> torch.Tensor:
+        if self.obs_layout == "cnn":
+            return obs.view(self.num_envs, self.n_learners, 1, self.H, self.W)
+        return obs
+
+    def _io(self, obs, final_obs, actions=None, npc_actions=None, spawn=None, outputs=True) -> N.GwIO:
+        E, L, A, dev = self.num_envs, self.n_learners, self.n_agents, self.device
+        io = N.GwIO()
+        b = self.buf
+        io.learner_actions = _check(actions, "actions", torch.int8, (E, L), dev).data_ptr() if actions is not None else None
+        io.npc_actions = _check(npc_actions, "npc_actions", torch.int8, (E, A), dev).data_ptr() if npc_actions is not None else None
+        io.spawn = _check(spawn, "spawn", torch.int8, (E, A, 2), dev).data_ptr() if spawn is not None else None
+        io.obs = obs.data_ptr()
+        io.final_obs = final_obs.data_ptr() if final_obs is not None else None
+        io.action_mask, io.positions = b.action_mask.data_ptr(), b.positions.data_ptr()
+        if outputs:
+            io.reward, io.shaped_reward, io.fear = b.reward.data_ptr(), b.shaped_reward.data_ptr(), b.fear.data_ptr()
+            io.terminated, io.truncated, io.ended = b.terminated.data_ptr(), b.truncated.data_ptr(), b.ended.data_ptr()
+            io.info = b.info.data_ptr()
+        return io
+
+    def _obs_arg(self, t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+        if t is None:
+            return None
+        if t.dtype != self.obs_dtype or t.device != self.device or not t.is_contiguous() or t.numel() != self.num_envs * self.n_learners * self.obs_len:
+            raise ValueError(f"{name}: need a contiguous {self.obs_dtype} tensor with {self._obs_shape} elements on {self.device}")
+        if t.data_ptr() % 16:
+            raise ValueError(f"{name}: must be 16-byte aligned")
+        return t
+
+    @staticmethod
+    def _as_i8(x, device) -> Optional[torch.Tensor]:
+        if x is None:
+            return None
+        if not isinstance(x, torch.Tensor):
+            x = torch.as_tensor(np.asarray(x))
+        return x.to(device=device, dtype=torch.int8).contiguous()
+
+    # ------------------------------------------------------------------ API
+    def reset(self, mask: Optional[torch.Tensor] = None, spawn=None, obs_out: Optional[torch.Tensor] = None) -> StepOutput:
+        """CustomMAEnv.reset for every env (or those with mask != 0).  `spawn` [E, n_agents, 2] replays recorded
+        spawn cells (sorted row-major like the reference); None draws them on the device."""
+        spawn = self._as_i8(spawn, self.device)
+        obs = self._obs_arg(obs_out, "obs_out") if obs_out is not None else self.buf.obs
+        io = self._io(obs, None, None, None, spawn, outputs=False)
+        mptr = None
+        if mask is not None:
+            mask = _check(mask.to(torch.uint8) if mask.dtype == torch.bool else mask, "mask", torch.uint8, (self.num_envs,), self.device)
+            mptr = mask.data_ptr()
+        N.check(self.lib.gw_reset(self._h, mptr, C.byref(io), self._stream()), self._h, "gw_reset")
+        return StepOutput(obs=self._view(obs), action_mask=self.buf.action_mask, positions=self.buf.positions)
+
+    def step(self, actions, npc_actions=None, spawn=None, obs_out: Optional[torch.Tensor] = None,
+             final_obs_out: Optional[torch.Tensor] = None) -> StepOutput:
+        """One env.step for all envs.  actions: int8 [E, n_learners].  `npc_actions` [E, n_agents] / `spawn`
+        replay recorded NPC draws / respawn cells; None = device RNG."""
+        actions = self._as_i8(actions, self.device)
+        npc_actions = self._as_i8(npc_actions, self.device)
+        spawn = self._as_i8(spawn, self.device)
+        obs = self._obs_arg(obs_out, "obs_out") if obs_out is not None else self.buf.obs
+        fin = self._obs_arg(final_obs_out, "final_obs_out")
+        io = self._io(obs, fin, actions, npc_actions, spawn)
+        N.check(self.lib.gw_step(self._h, C.byref(io), self._stream()), self._h, "gw_step")
+        b = self.buf
+        return StepOutput(obs=self._view(obs), action_mask=b.action_mask, positions=b.positions, reward=b.reward,
+                          shaped_reward=b.shaped_reward, fear=b.fear, terminated=b.terminated, truncated=b.truncated,
+                          ended=b.ended, info=b.info, final_obs=self._view(fin) if fin is not None else None)
+
+    def sync(self):
+        N.check(self.lib.gw_sync(self._h, self._stream()), self._h, "gw_sync")
+
+    def stats(self) -> Dict[str, float]:
+        s = N.GwStats()
+        N.check(self.lib.gw_get_stats(self._h, C.byref(s), self._stream()), self._h, "gw_get_stats")
+        return {name: getattr(s, name) for name, _ in N.GwStats._fields_}
+
+    def reset_stats(self):
+        N.check(self.lib.gw_reset_stats(self._h, self._stream()), self._h, "gw_reset_stats")
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        N.check(self.lib.gw_launch_count(self._h, C.byref(n)), self._h, "gw_launch_count")
+        return int(n.value)
+
+    def state_dict(self) -> torch.Tensor:
+        """Packed per-env state (16 B/env) as a uint8 CPU tensor (checkpoint / resume)."""
+        nbytes = int(self.lib.gw_state_bytes(self._h))
+        out = torch.empty(nbytes, dtype=torch.uint8)
+        N.check(self.lib.gw_get_state(self._h, C.c_void_p(out.data_ptr()), 0, self._stream()), self._h, "gw_get_state")
+        return out
+
+    def load_state_dict(self, state: torch.Tensor):
+        nbytes = int(self.lib.gw_state_bytes(self._h))
+        state = state.contiguous()
+        if state.dtype != torch.uint8 or state.numel() != nbytes:
+            raise ValueError(f"state must be a uint8 tensor of {nbytes} bytes")
+        N.check(self.lib.gw_set_state(self._h, C.c_void_p(state.data_ptr()), int(state.is_cuda), self._stream()),
+                self._h, "gw_set_state")
+
+    # ------------------------------------------------------------------ operator-level entry points
+    def update_world(self, positions, actions, n_agents=None, apples=None):
+        """GWorld.UpdateGWorld for C independent cases.  positions [C,4,2], actions [C,4] (int8, padded)."""
+        dev = self.device
+        pos, act = self._as_i8(positions, dev), self._as_i8(actions, dev)
+        Cn = pos.shape[0]
+        nper, app = self._as_i8(n_agents, dev), self._as_i8(apples, dev)
+        new_pos = torch.empty((Cn, 4, 2), dtype=torch.int8, device=dev)
+        crash = torch.empty((Cn, 4), dtype=torch.uint8, device=dev)
+        restr = torch.empty((Cn, 4), dtype=torch.uint8, device=dev)
+        caught = torch.zeros((Cn, 2, 2), dtype=torch.int8, device=dev)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        N.check(self.lib.gw_update_world(self._h, Cn, p(nper), p(pos), p(act), p(app), p(new_pos), p(crash), p(restr),
+                                         p(caught), self._stream()), self._h, "gw_update_world")
+        return new_pos, crash, restr, caught
+
+    def fear_one_actor(self, positions, actions, mdr, actor, in_list=None, n_agents=None):
+        """Responsibility.FeAR_4_one_actor for C independent cases -> (resp f64 [C,4], n_mdr, n_act int8 [C,4])."""
+        dev = self.device
+        pos, act, md, ac = (self._as_i8(x, dev) for x in (positions, actions, mdr, actor))
+        Cn = pos.shape[0]
+        nper = self._as_i8(n_agents, dev)
+        il = None if in_list is None else torch.as_tensor(np.asarray(in_list)).to(device=dev, dtype=torch.uint8).contiguous()
+        resp = torch.empty((Cn, 4), dtype=torch.float64, device=dev)
+        n_mdr = torch.empty((Cn, 4), dtype=torch.int8, device=dev)
+        n_act = torch.empty((Cn, 4), dtype=torch.int8, device=dev)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        N.check(self.lib.gw_fear_one_actor(self._h, Cn, p(nper), p(pos), p(act), p(md), p(ac), p(il), p(resp), p(n_mdr),
+                                           p(n_act), self._stream()), self._h, "gw_fear_one_actor")
+        return resp, n_mdr, n_act

@@ -1,0 +1,212 @@
+"""GPU (-m gpu): the CUDA library, called through its C-ABI, vs the golden vectors recorded from the reference
+and vs the C oracle on seeded device-RNG rollouts at the BASELINE.json batch sizes.
+
+Bar: bit-exact for positions, crash/restricted flags, done flags, integer rewards, observations, masks and the
+packed env state; FeAR and the single-env float reward are compared with == as well (north_star allows 1e-6 rel)."""
+import numpy as np
+import pytest
+
+import c_oracle
+import replay_checks as RC
+
+pytestmark = pytest.mark.gpu
+
+
+def make(**kw):
+    return RC.GpuBackend("Level 3", **kw)
+
+
+def test_update_cases_golden():
+    assert RC.check_update_cases(make) > 6000
+
+
+def test_fear_cases_golden():
+    assert RC.check_fear_cases(make) == 500
+
+
+def test_ma_episodes_golden():
+    assert RC.check_ma_episodes(make) > 1500
+
+
+def test_ma_episodes_golden_bf16():
+    assert RC.check_ma_episodes(make, obs_bf16=True) > 1500
+
+
+def test_ma_sessions_autoreset_golden():
+    assert RC.check_ma_sessions_autoreset(make) > 1500
+
+
+def test_single_episodes_golden():
+    assert RC.check_single_episodes(make) > 1000
+
+
+def _rollout_vs_oracle(E, steps, seed, scenario="Level 3", threads=8, masked=False, **kw):
+    g = RC.GpuBackend(scenario, num_envs=E, seed=seed, **kw)
+    o = c_oracle.COracle(scenario, num_envs=E, seed=seed, threads=threads, **kw)
+    g.reset(); o.reset()
+    assert np.array_equal(g.positions, o.positions)
+    assert np.array_equal(g.obs, o.obs) and np.array_equal(g.action_mask, o.action_mask)
+    rng = np.random.default_rng(seed + 1)
+    L = o.L
+    n_end = 0
+    for t in range(steps):
+        if masked:      # masked-uniform learner actions: fewer restricted moves, different crash rate
+            u = rng.random((E, L, 9)) * o.action_mask
+            la = u.argmax(-1).astype(np.int8)
+        else:
+            la = rng.integers(0, 9, size=(E, L)).astype(np.int8)
+        g.step(la); o.step(la)
+        for name in ("positions", "reward", "shaped_reward", "fear", "terminated", "truncated", "ended", "info",
+                     "action_mask", "obs"):
+            a, b = getattr(g, name), getattr(o, name)
+            assert np.array_equal(a, b), (name, t, np.flatnonzero((a != b).reshape(E, -1).any(1))[:5])
+        ended = o.ended.astype(bool)
+        if ended.any() and kw.get("auto_reset", True):
+            assert np.array_equal(g.final_obs[ended], o.final_obs[ended]), t
+        n_end += int(ended.sum())
+    assert np.array_equal(g.state(), o.state())
+    sg, so = g.stats(), o.stats()
+    for k in ("env_steps", "agent_steps", "episodes", "episode_len_sum", "crashes", "apples", "unresolved", "fear_nonzero"):
+        assert sg[k] == so[k], (k, sg[k], so[k])
+    assert abs(sg["return_sum"] - so["return_sum"]) < 1e-6
+    assert abs(sg["fear_sum"] - so["fear_sum"]) <= 1e-9 * max(1.0, abs(so["fear_sum"]))
+    return n_end, so
+
+
+def test_rollout_config2_fear_4096():
+    """BASELINE config[1]: custom_fear_5.yaml, 4096 envs, FeAR on, fp32 MLP obs, device RNG + auto-reset."""
+    n_end, st = _rollout_vs_oracle(4096, 40, seed=42, fear=True, fear_weight=-5.0, auto_reset=True, max_steps=150)
+    assert n_end > 4096 and st["fear_nonzero"] > 1000
+
+
+def test_rollout_config3_cnn_16384_bf16():
+    """BASELINE config[2]: 16384 envs, obs rendered in the CNN actor's input layout (same bytes), bf16."""
+    n_end, _ = _rollout_vs_oracle(16384, 12, seed=66, fear=False, obs_bf16=True, auto_reset=True, max_steps=150)
+    assert n_end > 4096
+
+
+def test_rollout_masked_actions_and_time_limit():
+    n_end, st = _rollout_vs_oracle(2048, 60, seed=0, fear=True, masked=True, auto_reset=True, max_steps=20)
+    assert st["episodes"] > 2048
+
+
+def test_rollout_level5_three_agents():
+    _rollout_vs_oracle(2048, 25, seed=3, scenario="Level 5", fear=True, auto_reset=True, max_steps=150)
+
+
+def test_rollout_gamemap_four_agents():
+    _rollout_vs_oracle(2048, 25, seed=4, scenario="GameMap", n_agents=4, fear=True, auto_reset=True, max_steps=150)
+
+
+def test_rollout_single_env_kind():
+    _rollout_vs_oracle(4096, 40, seed=5, env_kind="single", fear=True, auto_reset=True, max_steps=150)
+
+
+def test_rollout_no_autoreset_sticky_flags():
+    _rollout_vs_oracle(1024, 30, seed=6, fear=False, auto_reset=False, max_steps=0)
+
+
+def test_large_batch_properties_1m():
+    """Config[3] size (1M envs): size-independent properties instead of an oracle diff --
+    agents stay on active cells and distinct, crashed agents do not move, masks match positions,
+    sharding invariance: the same global env ids on two handles give the same trajectories."""
+    import torch
+    from marl_responsible_nav_b200 import BatchedGridWorld, builtin_scenario
+    E = 1 << 20
+    sc = builtin_scenario("Level 3")
+    region = torch.as_tensor(sc.region, device="cuda").bool()
+    env = BatchedGridWorld("Level 3", num_envs=E, fear=True, auto_reset=True, seed=9)
+    half = BatchedGridWorld("Level 3", num_envs=E // 2, fear=True, auto_reset=True, seed=9, env_id_base=E // 2)
+    out = env.reset(); outh = half.reset()
+    assert torch.equal(out.positions[E // 2:], outh.positions)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(5):
+        prev = out.positions.clone().long()
+        la = torch.randint(0, 9, (E, 2), generator=gen, device="cuda", dtype=torch.int8)
+        out = env.step(la); outh = half.step(la[E // 2:].contiguous())
+        pos = out.positions.long()
+        assert region[pos[..., 0], pos[..., 1]].all()
+        flat = pos[..., 0] * 16 + pos[..., 1]
+        srt = flat.sort(dim=1).values
+        assert (srt[:, 1:] != srt[:, :-1]).all()
+        crash = torch.stack([(out.info >> i) & 1 for i in range(4)], 1).bool()
+        assert torch.equal(pos[crash], prev[crash])
+        assert torch.equal(out.positions[E // 2:], outh.positions)
+        assert torch.equal(out.fear[E // 2:], outh.fear) and torch.equal(out.obs[E // 2:], outh.obs)
+        assert ((out.info >> 13) & 1).sum().item() == 0          # collision fix-point always resolves
+
+
+def test_state_checkpoint_roundtrip():
+    import torch
+    from marl_responsible_nav_b200 import BatchedGridWorld
+    a = BatchedGridWorld("Level 3", num_envs=512, fear=True, seed=11)
+    a.reset()
+    la = torch.randint(0, 9, (512, 2), device="cuda", dtype=torch.int8)
+    for _ in range(5):
+        a.step(la)
+    snap = a.state_dict()
+    b = BatchedGridWorld("Level 3", num_envs=512, fear=True, seed=11)
+    b.load_state_dict(snap)
+    for _ in range(5):
+        oa, ob = a.step(la), b.step(la)
+        assert torch.equal(oa.obs, ob.obs) and torch.equal(oa.positions, ob.positions) and torch.equal(oa.fear, ob.fear)
+
+
+def test_compat_envs_match_reference_trace_under_seeds():
+    """CustomMAEnv / CustomEnv with the reference's own seeding (ctor seed + random.seed + np.random.seed):
+    identical trajectories to the traces recorded from the reference."""
+    import random
+    from marl_responsible_nav_b200 import CustomMAEnv, CustomEnv
+    g = RC.npz("ma_episodes.npz")
+    for sess in np.unique(g["ep_session"]):
+        eps = np.flatnonzero(g["ep_session"] == sess)
+        seed, fear = int(g["ep_seed"][eps[0]]), bool(g["ep_fear"][eps[0]])
+        env = CustomMAEnv(render=False, fear=fear, seed=seed)
+        random.seed(seed); np.random.seed(seed)
+        for ep in eps[:6]:
+            obs, info = env.reset()
+            assert np.array_equal(np.stack([obs[a] for a in env.possible_agents]).astype(np.float32), g["ep_reset_obs"][ep])
+            assert obs["agent_0"].dtype == np.float64 and obs["agent_0"].shape == (10, 16)
+            assert info["fear"] == 0.0
+            for t in range(int(g["ep_n_steps"][ep])):
+                s = int(g["ep_first_step"][ep]) + t
+                obs, rew, term, trunc, info = env.step(tuple(int(a) for a in g["learner_act"][s]))
+                assert [rew[a] for a in env.possible_agents] == list(g["reward"][s])
+                assert [term[a] for a in env.possible_agents] == list(g["term"][s])
+                assert [trunc[a] for a in env.possible_agents] == list(g["trunc"][s])
+                assert [float(info["fear"][a]) for a in env.possible_agents] == list(g["fear"][s])
+                assert info["agent_crashes"] == g["crash_count"][s] and info["apples_caught"] == g["apples_caught"][s]
+                assert np.array_equal(np.stack([obs[a] for a in env.possible_agents]).astype(np.float32), g["obs"][s])
+                assert np.array_equal(np.stack([info[a]["action_mask"] for a in env.possible_agents]), g["mask"][s])
+        assert env.step(()) == ({}, {}, {}, {}, {})
+        assert env.num_agents == 2 and env.action_space.n == 9
+    gs = RC.npz("single_episodes.npz")
+    for sess in np.unique(gs["ep_session"]):
+        eps = np.flatnonzero(gs["ep_session"] == sess)
+        seed, fear = int(gs["ep_seed"][eps[0]]), bool(gs["ep_fear"][eps[0]])
+        CustomEnv.rng = np.random.default_rng(seed)
+        env = CustomEnv(render=False, fear=fear)
+        random.seed(seed); np.random.seed(seed)
+        for ep in eps[:6]:
+            obs, _ = env.reset()
+            assert np.array_equal(obs.astype(np.float32), gs["ep_reset_obs"][ep])
+            for t in range(int(gs["ep_n_steps"][ep])):
+                s = int(gs["ep_first_step"][ep]) + t
+                obs, rew, term, trunc, info = env.step([int(gs["action"][s])])
+                assert rew[0] == gs["reward"][s] and term[0] == gs["term"][s] and trunc == gs["trunc"][s]
+                assert float(info["fear"]) == gs["fear"][s] and info["restricted"] == gs["restricted"][s]
+                assert info["episode"]["r"] == gs["ep_r"][s] and info["episode"]["l"] == gs["ep_l"][s]
+                assert np.array_equal(obs.astype(np.float32), gs["obs"][s])
+
+
+def test_errors_are_loud():
+    import torch
+    from marl_responsible_nav_b200 import BatchedGridWorld
+    env = BatchedGridWorld("Level 3", num_envs=8)
+    with pytest.raises(RuntimeError, match="gw_reset first"):
+        env.step(torch.zeros((8, 2), dtype=torch.int8, device="cuda"))
+    env.reset()
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((7, 2), dtype=torch.int8, device="cuda"))
+    with pytest.raises(RuntimeError, match="n_agents"):
+        BatchedGridWorld("Level 3", num_envs=8, n_agents=7)
