@@ -120,6 +120,7 @@ def test_large_batch_properties_1m():
     out = env.reset(); outh = half.reset()
     assert torch.equal(out.positions[E // 2:], outh.positions)
     gen = torch.Generator(device="cuda").manual_seed(1)
+    fresh = torch.zeros(E, dtype=torch.bool, device="cuda")    # env respawned after `positions` was written
     for t in range(5):
         prev = out.positions.clone().long()
         la = torch.randint(0, 9, (E, 2), generator=gen, device="cuda", dtype=torch.int8)
@@ -129,8 +130,9 @@ def test_large_batch_properties_1m():
         flat = pos[..., 0] * 16 + pos[..., 1]
         srt = flat.sort(dim=1).values
         assert (srt[:, 1:] != srt[:, :-1]).all()
-        crash = torch.stack([(out.info >> i) & 1 for i in range(4)], 1).bool()
+        crash = torch.stack([(out.info >> i) & 1 for i in range(4)], 1).bool() & ~fresh[:, None]
         assert torch.equal(pos[crash], prev[crash])
+        fresh = out.ended.bool()
         assert torch.equal(out.positions[E // 2:], outh.positions)
         assert torch.equal(out.fear[E // 2:], outh.fear) and torch.equal(out.obs[E // 2:], outh.obs)
         assert ((out.info >> 13) & 1).sum().item() == 0          # collision fix-point always resolves
