@@ -1,14 +1,21 @@
 // Device-side building blocks of the batched grid world (sm_100a).
 //
-// Formulation.  The reference grows a Python list of cells per agent and per
-// sub-step (custom/grid_world.py:458-518) and re-derives floor/ceil positions
-// from it in every collision pass (:255-264).  Here an agent's whole nominal
-// trajectory is three packed cells (p0 start, p1 after move 1, p2 after move 2):
-// a crash reverts every later path entry to p0 (:200-208), so at any sub-step an
-// agent is either on its nominal trajectory or "reverted" (A = B = p0).  The
-// fix-point of :247-405 then runs on a 4-bit crashed mask.  A cell is one byte:
-// (row << 4) | col  (W = 16), so cell equality / direction equality are integer
-// compares.  tests/ diff this against the literal restatement in oracle/.
+// Formulation (differs from the reference's on purpose; tests/ diff it against the literal
+// restatement in oracle/):
+//   * A cell is one byte (row << 4) | col (W = 16).
+//   * The reference grows a list of cells per agent and sub-step (custom/grid_world.py:458-518).
+//     Here an agent's nominal trajectory is three cells p0, p1, p2 read from a next-cell table, and
+//     is classified into one of 13 "effective trajectories" (eff): 0 stationary, 1-4 one step in
+//     direction d, 5-8 two steps, 9-12 two-step action whose second move is blocked.  Blocked and
+//     Stay moves are the same trajectory, and so is a crashed agent: the revert of :200-208 puts
+//     every later path entry back on p0, i.e. a crashed agent is a stationary one.
+//   * The five-rule pair test (:276-390) only compares cells of the two agents, so it is translation
+//     invariant: for a pair it depends on (p0_j - p0_i, eff_i, eff_j) and on nothing else.  gw_create
+//     evaluates the literal rules (pair_hit below) once for every |delta|_1 <= 4 and every eff pair
+//     into a 13.7 KB table of 4-bit masks (bit s = the pair collides at sub-step s).  Agents further
+//     apart than 4 can never share or swap a cell within one step.
+//   * The fix-point of :247-405 then runs on bit vectors: three 24-bit words hold the masks of the six
+//     pairs for (both nominal / second crashed / first crashed); one pass is a handful of logic ops.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -17,29 +24,49 @@
 
 namespace gw {
 
+constexpr int N_EFF = 13;
+constexpr int LUT_DELTAS = 81;                      // (dr + 4) * 9 + (dc + 4)
+constexpr int LUT_BYTES = LUT_DELTAS * N_EFF * N_EFF;   // 13689
+
 struct Tables {                         // device-global, read-only, built by gw_create
-  uint16_t map_rows[GW_MAX_H];
+  uint8_t pair_lut[LUT_BYTES + 7];      // [delta][eff_i][eff_j] -> 4-bit sub-step hit mask
+  uint8_t next_cell[GW_MAX_H * GW_W * 4];       // [cell][dir Up,Down,Left,Right] -> cell after the move (same cell if blocked)
   uint8_t mdr_map[GW_MAX_H * GW_W];
   uint8_t policy_map[GW_MAX_H * GW_W];
   uint32_t policy_thr[GW_MAX_POLICIES][2][8];   // 31-bit cdf thresholds, [policy][perturbed][k]
   uint8_t active_cell[GW_MAX_H * GW_W];         // row-major list of active cells (np.where order)
+  uint16_t map_rows[GW_MAX_H];
   int32_t n_active;
   int32_t pad_;
   double resp_lut[10][10];                      // clip((m-a)/(m+1e-6),-1,1), Responsibility.py:194-198
 };
 
 // ---------------------------------------------------------------- Philox4x32-10
-__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+__host__ __device__ __forceinline__ void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * c[0];
+    const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
   }
-  return ctr;
+}
+
+// ---------------------------------------------------------------- the literal pair test (LUT builder)
+// custom/grid_world.py:276-390, first match wins.  q = (step+1)*len in quarter sub-steps,
+// f = floor(q/4), c = ceil(q/4); A = path[f], B = path[c]; P = start cell.
+__host__ __device__ __forceinline__ bool pair_hit(int Ai, int Bi, int Pi, int qi, int fi, int ci,
+                                                  int Aj, int Bj, int Pj, int qj, int fj, int cj) {
+  if (Ai == Aj || Bi == Bj) return true;                                   // :276-278
+  if (Ai == Bj && Bi == Aj) return true;                                   // :291-294
+  const bool same_dir = (Bi - Ai) == (Bj - Aj);                            // :314-318 (cell codes: unique per direction)
+  if (Ai == Bj) return !(((4 * ci - qi) + (qj - 4 * fj) <= 4) && same_dir);   // :307-326
+  if (Bi == Aj) return !(((4 * cj - qj) + (qi - 4 * fi) <= 4) && same_dir);   // :339-357
+  return (Ai == Pj && Pi == Aj) || (Bi == Pj && Pi == Bj) ||               // :371-378
+         (Ai == Pj && Pi == Bj) || (Bi == Pj && Pi == Aj);
 }
 
 // ---------------------------------------------------------------- geometry
@@ -47,186 +74,225 @@ __device__ __forceinline__ int manhattan(uint32_t a, uint32_t b) {
   return abs((int)(a >> 4) - (int)(b >> 4)) + abs((int)(a & 15) - (int)(b & 15));
 }
 
-__device__ __forceinline__ bool cell_ok(const uint16_t* rows, int H, int r, int c) {
-  return (unsigned)r < (unsigned)H && (unsigned)c < (unsigned)GW_W && ((rows[r] >> c) & 1);
-}
+// Trajectory of one agent for action a (custom/custom_agent.py:140-150 + grid_world.py:481-518):
+// off-grid (clip) or inactive target => the agent stays and the move is "restricted".
+struct Traj {
+  uint32_t p1, p2, eff;
+  uint32_t r1, r2;          // first / second move restricted
+  uint32_t two;             // two-step action
+};
 
-// Action table custom/custom_agent.py:140-150: 0 Stay, 1 Up, 2 Down, 3 Left, 4 Right, 5-8 the same twice.
-__device__ __forceinline__ void action_delta(int a, int& dr, int& dc, int& len) {
-  len = a >= 5 ? 2 : 1;
-  const int d = (a == 0) ? -1 : ((a - 1) & 3);
-  dr = (d == 0) ? -1 : (d == 1) ? 1 : 0;
-  dc = (d == 2) ? -1 : (d == 3) ? 1 : 0;
-}
-
-// One move of grid_world.py:481-518: off-grid (clip) or inactive target => stay + restricted.
-__device__ __forceinline__ uint32_t try_move(const uint16_t* rows, int H, uint32_t p, int dr, int dc, bool& blocked) {
-  const int r = (int)(p >> 4) + dr, c = (int)(p & 15) + dc;
-  const bool ok = cell_ok(rows, H, r, c);
-  blocked = !ok;
-  return ok ? (uint32_t)((r << 4) | c) : p;
+__device__ __forceinline__ Traj make_traj(const uint8_t* __restrict__ s_next, uint32_t p0, uint32_t a) {
+  Traj t;
+  t.p1 = t.p2 = p0;
+  t.eff = t.r1 = t.r2 = 0;
+  t.two = a >= 5 ? 1u : 0u;
+  if (a != 0) {
+    const uint32_t d = (a - 1) & 3u;
+    t.p1 = s_next[p0 * 4 + d];
+    if (t.p1 == p0) {
+      t.r1 = 1;                                   // a blocked first move of a two-step action is blocked twice
+    } else if (!t.two) {
+      t.eff = 1 + d;
+    } else {
+      t.p2 = s_next[t.p1 * 4 + d];
+      t.r2 = (t.p2 == t.p1) ? 1u : 0u;
+      t.eff = (t.r2 ? 9u : 5u) + d;
+    }
+    if (!t.two) t.p2 = t.p1;
+  }
+  return t;
 }
 
 // get_action_mask, custom/ma_customenv.py:467-506: only the TARGET cell is tested.
 __device__ __forceinline__ uint32_t action_mask_bits(const uint16_t* rows, int H, uint32_t p) {
   uint32_t m = 1u;
+  const int r = (int)(p >> 4), c = (int)(p & 15);
 #pragma unroll
   for (int a = 1; a < GW_N_ACTIONS; ++a) {
-    int dr, dc, len;
-    action_delta(a, dr, dc, len);
-    if (cell_ok(rows, H, (int)(p >> 4) + dr * len, (int)(p & 15) + dc * len)) m |= 1u << a;
+    const int len = a >= 5 ? 2 : 1, d = (a - 1) & 3;
+    const int tr = r + (d == 0 ? -len : d == 1 ? len : 0), tc = c + (d == 2 ? -len : d == 3 ? len : 0);
+    if ((unsigned)tr < (unsigned)H && (unsigned)tc < (unsigned)GW_W && ((rows[tr] >> tc) & 1)) m |= 1u << a;
   }
   return m;
 }
 
-// ---------------------------------------------------------------- pair test
-// custom/grid_world.py:276-390, first match wins.  q = (step+1)*len in quarter
-// sub-steps, f = floor(q/4), c = ceil(q/4); A = path[f], B = path[c].
-__device__ __forceinline__ bool pair_hit(uint32_t Ai, uint32_t Bi, uint32_t Pi, int qi, int fi, int ci,
-                                         uint32_t Aj, uint32_t Bj, uint32_t Pj, int qj, int fj, int cj) {
-  if (Ai == Aj || Bi == Bj) return true;                                   // :276-278
-  if (Ai == Bj && Bi == Aj) return true;                                   // :291-294
-  const bool same_dir = ((int)Bi - (int)Ai) == ((int)Bj - (int)Aj);        // :314-318 (cell codes: unique per direction)
-  if (Ai == Bj) return !(((4 * ci - qi) + (qj - 4 * fj) <= 4) && same_dir);   // :307-326
-  if (Bi == Aj) return !(((4 * cj - qj) + (qi - 4 * fi) <= 4) && same_dir);   // :339-357
-  return (Ai == Pj && Pi == Aj) || (Bi == Pj && Pi == Bj) ||               // :371-378
-         (Ai == Pj && Pi == Bj) || (Bi == Pj && Pi == Aj);
+// ---------------------------------------------------------------- pair geometry of one env
+// near6: bit p = pair p (01,02,03,12,13,23) within Manhattan distance 4; didx: 7-bit delta index per pair.
+struct PairGeom {
+  uint32_t near6;
+  uint32_t didx_lo;     // pairs 0..3, 8 bits each
+  uint32_t didx_hi;     // pairs 4..5
+};
+
+__device__ __forceinline__ PairGeom pair_geometry(int n, uint32_t cells) {
+  PairGeom g;
+  g.near6 = g.didx_lo = g.didx_hi = 0;
+  int p = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = i + 1; j < 4; ++j, ++p) {
+      if (j < n) {
+        const uint32_t a = (cells >> (8 * i)) & 0xFFu, b = (cells >> (8 * j)) & 0xFFu;
+        const int dr = (int)(b >> 4) - (int)(a >> 4), dc = (int)(b & 15) - (int)(a & 15);
+        if (abs(dr) + abs(dc) <= 4) {
+          g.near6 |= 1u << p;
+          const uint32_t di = (uint32_t)((dr + 4) * 9 + (dc + 4));
+          if (p < 4) g.didx_lo |= di << (8 * p); else g.didx_hi |= di << (8 * (p - 4));
+        }
+      }
+    }
+  }
+  return g;
 }
 
-struct SimResult {
+__device__ __forceinline__ uint32_t geom_didx(const PairGeom& g, int p) {
+  return p < 4 ? (g.didx_lo >> (8 * p)) & 0xFFu : (g.didx_hi >> (8 * (p - 4))) & 0xFFu;
+}
+
+// agents connected to x through chains of near pairs (only they can influence x's crash outcome)
+__device__ __forceinline__ uint32_t reach_mask(uint32_t near6, int x) {
+  uint32_t adj = 0;                                   // 4 nibbles: adjacency row per agent
+  if (near6 & 1u) adj |= (2u << 0) | (1u << 4);       // (0,1)
+  if (near6 & 2u) adj |= (4u << 0) | (1u << 8);       // (0,2)
+  if (near6 & 4u) adj |= (8u << 0) | (1u << 12);      // (0,3)
+  if (near6 & 8u) adj |= (4u << 4) | (2u << 8);       // (1,2)
+  if (near6 & 16u) adj |= (8u << 4) | (2u << 12);     // (1,3)
+  if (near6 & 32u) adj |= (8u << 8) | (4u << 12);     // (2,3)
+  uint32_t r = 1u << x;
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    uint32_t nr = r;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      if ((r >> a) & 1u) nr |= (adj >> (4 * a)) & 0xFu;
+    r = nr;
+  }
+  return r;
+}
+
+// ---------------------------------------------------------------- collision fix-point on bit vectors
+// Returns the crashed mask after each of the four sub-steps, 4 bits each (bits 12-15 = final AgentCrash).
+// custom/grid_world.py:247-405: within a pass the paths are frozen (hits are evaluated on the crashed mask
+// of the pass start), crashed agents revert after the pass, passes repeat while something was hit.  Every
+// pass with a hit crashes at least one more agent, so the reference's 2N-pass cap can never bind.
+__device__ __forceinline__ uint32_t collide(const uint8_t* __restrict__ s_lut, const PairGeom& g, const uint32_t eff[4]) {
+  if (g.near6 == 0) return 0;
+  uint32_t NNw = 0;
+  {
+    int p = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = i + 1; j < 4; ++j, ++p)
+        if ((g.near6 >> p) & 1u)
+          NNw |= (uint32_t)s_lut[geom_didx(g, p) * (N_EFF * N_EFF) + eff[i] * N_EFF + eff[j]] << (4 * p);
+  }
+  if (NNw == 0) return 0;                             // nobody collides while everyone is on course
+  uint32_t NRw = 0, RNw = 0;                          // second agent crashed (stationary) / first agent crashed
+  {
+    int p = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = i + 1; j < 4; ++j, ++p)
+        if ((g.near6 >> p) & 1u) {
+          const uint32_t base = geom_didx(g, p) * (N_EFF * N_EFF);
+          NRw |= (uint32_t)s_lut[base + eff[i] * N_EFF] << (4 * p);
+          RNw |= (uint32_t)s_lut[base + eff[j]] << (4 * p);
+        }
+  }
+  uint32_t crashed = 0, out = 0;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    while (true) {
+      const uint32_t Pi = ((crashed & 1u) ? 0x000FFFu : 0u) | ((crashed & 2u) ? 0x0FF000u : 0u) | ((crashed & 4u) ? 0xF00000u : 0u);
+      const uint32_t Pj = ((crashed & 2u) ? 0x00000Fu : 0u) | ((crashed & 4u) ? 0x00F0F0u : 0u) | ((crashed & 8u) ? 0xFF0F00u : 0u);
+      const uint32_t hp = (((NNw & ~Pi & ~Pj) | (NRw & ~Pi & Pj) | (RNw & Pi & ~Pj)) >> s) & 0x111111u;
+      if (hp == 0) break;
+      crashed |= ((hp & 0x000111u) ? 1u : 0u) | ((hp & 0x011001u) ? 2u : 0u) | ((hp & 0x101010u) ? 4u : 0u) |
+                 ((hp & 0x110100u) ? 8u : 0u);
+    }
+    out |= crashed << (4 * s);
+  }
+  return out;
+}
+
+// cell of agent at the end of sub-step s (grid_world.py:259-264 floor index; crashed => start cell)
+__device__ __forceinline__ uint32_t cell_at(uint32_t p0, const Traj& t, uint32_t crashed_s, int s) {
+  if (crashed_s) return p0;
+  if (t.two) return s == 0 ? p0 : (s == 3 ? t.p2 : t.p1);
+  return s == 3 ? t.p1 : p0;
+}
+
+struct StepResult {
   uint32_t cells;       // 4 x 8-bit final cells
   uint32_t crash;       // bit i
   uint32_t restr;       // bit i
   uint32_t caught;      // 3-bit counters, field (eater*2 + apple)
-  uint32_t unresolved;
 };
 
 // GWorld.UpdateGWorld with explicit actions for all n agents (custom/grid_world.py:424-563).
-// cells: 4 x 8-bit start cells; acts: 4 x 4-bit action ids.
-template <bool APPLES>
-__device__ __forceinline__ SimResult simulate(const uint16_t* rows, int H, int n, uint32_t cells, uint32_t acts,
-                                              uint32_t apple_cells = 0, uint32_t apple_on = 0, int n_eaters = 0) {
-  uint32_t p0[4], p1[4], p2[4];
-  int len[4];
-  uint32_t r1 = 0, r2 = 0;
+__device__ __forceinline__ StepResult world_update(const uint8_t* __restrict__ s_lut, const uint8_t* __restrict__ s_next,
+                                                   int n, uint32_t cells, uint32_t acts, const PairGeom& g,
+                                                   uint32_t apple_cells, uint32_t apple_on, int n_eaters) {
+  Traj t[4];
+  uint32_t eff[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    p0[i] = (cells >> (8 * i)) & 0xFFu;
-    p1[i] = p2[i] = p0[i];
-    len[i] = 1;
-    if (i < n) {
-      const int a = (acts >> (4 * i)) & 0xF;
-      int dr, dc;
-      action_delta(a, dr, dc, len[i]);
-      bool b1 = false, b2 = false;
-      p1[i] = try_move(rows, H, p0[i], dr, dc, b1);
-      p2[i] = p1[i];
-      if (len[i] == 2) p2[i] = try_move(rows, H, p1[i], dr, dc, b2);
-      if (a != 0 && b1) r1 |= 1u << i;
-      if (b2) r2 |= 1u << i;
-    }
+    t[i] = make_traj(s_next, (cells >> (8 * i)) & 0xFFu, i < n ? (acts >> (4 * i)) & 0xFu : 0u);
+    eff[i] = t[i].eff;
   }
-  uint32_t crashed = 0, crashed_after0 = 0, caught = 0, unresolved = 0;
-  uint32_t A[4], B[4];
+  const uint32_t cm = (n >= 2) ? collide(s_lut, g, eff) : 0u;
+  StepResult r;
+  r.crash = (cm >> 12) & 0xFu;
+  r.cells = 0;
+  r.restr = 0;
+  r.caught = 0;
 #pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    int q[4], f[4], c[4];
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t p0 = (cells >> (8 * i)) & 0xFFu;
+    // a lone agent never moves (the floor positions are only assigned inside the pair loops, :259/:264)
+    const uint32_t fin = (n >= 2) ? cell_at(p0, t[i], (r.crash >> i) & 1u, 3) : p0;
+    r.cells |= fin << (8 * i);
+    // the second move is attempted only if the agent did not crash during sub-step 0 (:464)
+    if (i < n && (t[i].r1 | (t[i].r2 & ~(cm >> i) & 1u))) r.restr |= 1u << i;
+  }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      q[i] = (s + 1) * len[i];
-      f[i] = q[i] >> 2;
-      c[i] = (q[i] + 3) >> 2;
-      const uint32_t pf = f[i] == 0 ? p0[i] : (f[i] == 1 ? p1[i] : p2[i]);
-      const uint32_t pc = c[i] == 1 ? p1[i] : p2[i];
-      const bool rev = (crashed >> i) & 1;
-      A[i] = rev ? p0[i] : pf;
-      B[i] = rev ? p0[i] : pc;
-    }
-    if (n >= 2) {
-      int loops = 0;
-      while (true) {                                                       // :250-405
-        ++loops;
-        uint32_t hits = 0;
+  for (int e = 0; e < 2; ++e) {                                            // :531-540, every sub-step
+    if (e < n_eaters) {
+      const uint32_t p0 = (cells >> (8 * e)) & 0xFFu;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+      for (int s = 0; s < 4; ++s) {
+        const uint32_t cur = (n >= 2) ? cell_at(p0, t[e], (cm >> (4 * s + e)) & 1u, s) : p0;
 #pragma unroll
-          for (int j = i + 1; j < 4; ++j) {
-            if (j < n && pair_hit(A[i], B[i], p0[i], q[i], f[i], c[i], A[j], B[j], p0[j], q[j], f[j], c[j]))
-              hits |= (1u << i) | (1u << j);
-          }
-        }
-        crashed |= hits;                                                   // record_collision :407-412
-#pragma unroll
-        for (int i = 0; i < 4; ++i)                                        // revertStepsWithCollisions :190-209
-          if ((crashed >> i) & 1) A[i] = B[i] = p0[i];
-        if (hits == 0) break;
-        if (loops >= 2 * n) { unresolved = 1; break; }                     // 'Collisions Not Resolved' :400-402
-      }
-    }
-    if (s == 0) crashed_after0 = crashed;
-    if (APPLES) {                                                          // :531-540, every sub-step
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const uint32_t cur = (n >= 2) ? A[e] : p0[e];
-          if (e < n_eaters && ((apple_on >> k) & 1) && cur == ((apple_cells >> (8 * k)) & 0xFFu))
-            caught += 1u << (3 * (e * 2 + k));
-        }
+        for (int k = 0; k < 2; ++k)
+          if (((apple_on >> k) & 1u) && cur == ((apple_cells >> (8 * k)) & 0xFFu)) r.caught += 1u << (3 * (e * 2 + k));
       }
     }
   }
-  SimResult out;
-  out.cells = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) out.cells |= ((n >= 2) ? A[i] : p0[i]) << (8 * i);   // :213-231 (a lone agent never moves)
-  out.crash = crashed;
-  out.restr = r1 | (r2 & ~crashed_after0);          // the 2nd move is attempted only if not crashed in sub-step 0 (:464)
-  out.caught = caught;
-  out.unresolved = unresolved;
-  return out;
+  return r;
 }
 
-// ---------------------------------------------------------------- FeAR (one warp)
-// FeAR_4_one_actor (custom/Responsibility.py:135-210) for actor x on one warp: lanes 0..26 are
-// (affected slot, affected action); two rounds (actor plays MdR / actor plays its action);
-// counts by ballot + popc.  `in_list` = agents present in ActionID4Agents (others Stay, :43).
-// Returns the per-slot counts packed 4 bits each: bits [4*js .. ] n_mdr, bits [16 + 4*js ..] n_act.
-__device__ __forceinline__ uint32_t fear_counts_warp(const uint16_t* rows, int H, int n, uint32_t cells, uint32_t acts,
-                                                     uint32_t in_list, int x, int mdr_x, int lane) {
-  uint32_t base = 0;
+// One counterfactual of CountValidMovesOfAffected (custom/Responsibility.py:32-48): is the affected agent j
+// neither restricted nor crashed when the listed agents play `acts` (already swapped) and the others Stay?
+__device__ __forceinline__ bool counterfactual_valid(const uint8_t* __restrict__ s_lut, const uint8_t* __restrict__ s_next,
+                                                     int n, uint32_t cells, uint32_t acts, const PairGeom& g, int j) {
+  const Traj tj = make_traj(s_next, (cells >> (8 * j)) & 0xFFu, (acts >> (4 * j)) & 0xFu);
+  if (tj.r1 | tj.r2) return false;          // restricted, or crashed before the blocked second move: invalid either way
+  uint32_t eff[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if ((in_list >> k) & 1) base |= ((acts >> (4 * k)) & 0xFu) << (4 * k);
-  const int js = lane / 9, ap = lane - js * 9;
-  const int j = js + (js >= x ? 1 : 0);
-  const bool lane_on = lane < 27 && j < n;
-  uint32_t packed = 0;
-#pragma unroll
-  for (int v = 0; v < 2; ++v) {
-    const uint32_t av = v == 0 ? (uint32_t)mdr_x : ((acts >> (4 * x)) & 0xFu);
-    uint32_t a4 = (base & ~(0xFu << (4 * x))) | (av << (4 * x));
-    bool valid = false;
-    if (lane_on) {
-      if ((in_list >> j) & 1) a4 = (a4 & ~(0xFu << (4 * j))) | ((uint32_t)ap << (4 * j));   // SwapActionIDs4Agents
-      const SimResult r = simulate<false>(rows, H, n, cells, a4);
-      valid = (((r.crash | r.restr) >> j) & 1) == 0;                        // Responsibility.py:46
-    }
-    const uint32_t b = __ballot_sync(0xFFFFFFFFu, valid);
-#pragma unroll
-    for (int s = 0; s < 3; ++s) packed |= (uint32_t)__popc(b & (0x1FFu << (9 * s))) << (16 * v + 4 * s);
-  }
-  return packed;
+  for (int i = 0; i < 4; ++i)
+    eff[i] = (i < n) ? make_traj(s_next, (cells >> (8 * i)) & 0xFFu, (acts >> (4 * i)) & 0xFu).eff : 0u;
+  const uint32_t cm = collide(s_lut, g, eff);
+  return ((cm >> (12 + j)) & 1u) == 0;
 }
 
 // np.sum over the Resp matrix (one non-zero row): numpy's 8-lane pairwise reduction adds the row as
-// first + (second + third) for n = 4, first + second for n = 3 (checked in tests).
-__device__ __forceinline__ double fear_sum_from_counts(const Tables* T, int n, uint32_t packed) {
-  double r[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-  for (int s = 0; s < 3; ++s)
-    if (s < n - 1) r[s] = T->resp_lut[(packed >> (4 * s)) & 0xF][(packed >> (16 + 4 * s)) & 0xF];
-  return n == 4 ? r[0] + (r[1] + r[2]) : (n == 3 ? r[0] + r[1] : r[0]);
+// first + (second + third) for n = 4, first + second for n = 3 (checked in tests/test_c_oracle.py).
+__device__ __forceinline__ double fear_sum3(int n, double r0, double r1, double r2) {
+  return n == 4 ? r0 + (r1 + r2) : (n == 3 ? r0 + r1 : r0);
 }
 
 }  // namespace gw

@@ -1,11 +1,16 @@
 // libgridworld_b200.so -- kernels + C-ABI (include/gridworld_b200.h).  sm_100a only.
 //
-// v1 layout: ONE WARP PER ENVIRONMENT.
-//   state  : uint4 per env {cells 4x8b, meta, rng tick, episode return 2xi16}, 16 B, L2-resident
-//   step   : every lane holds the env's scalars (broadcast load); lanes 0..n-1 fetch / draw the
-//            agents' actions; FeAR = 27 lanes x 4 rounds of counterfactual sims, ballot+popc counts;
-//            the real step is evaluated redundantly by all lanes (no shuffles needed afterwards);
-//            observations leave as 128-bit coalesced stores, 32 lanes x 16 B per instruction.
+// Kernel layout (v2).  A CTA owns a tile of TILE consecutive environments and runs four phases:
+//   P1  thread per env   : load the 16-byte packed state (coalesced), fetch/draw actions, advance the world with the
+//                          pair-mask table (gw_device.cuh), rewards / done flags / auto-reset, scalar outputs,
+//                          enqueue the FeAR tasks (actor x, affected j) that can be non-zero
+//   P2  thread per sim   : the CTA drains the task queue, one counterfactual per thread (18 per task), counts land in
+//                          4-bit fields of a shared-memory word per (env, actor) via atomicAdd
+//   P3  thread per env   : counts -> Resp LUT -> fear, shaped reward, episode statistics (warp-reduced atomics)
+//   P4  CTA cooperative  : observations: every thread streams 16-byte copies of the constant map row-template
+//                          (full 512 B per warp instruction, coalesced), then the <= 5 special cells per observation
+//                          are patched with 4-byte stores that hit the lines just written (they merge in L2)
+// State is 16 B/env and lives in HBM/L2 between launches; nothing else is kept by the library.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,80 +49,207 @@ struct StepParams {
 constexpr int STAT_SLOTS = 1024;
 enum { ST_EPISODES = 0, ST_LEN, ST_CRASH, ST_APPLES, ST_UNRES, ST_FEAR_NZ, ST_RETURN_MILLI, ST_FEAR_BITS };
 
-// ------------------------------------------------------------------ observation render
-// value of one cell for learner k.  custom/ma_customenv.py:303-322 (step) / :198-209 (reset),
-// custom/customenv.py:161-163 / :341-344 (single env: raw ids, every remaining apple).
-__device__ __forceinline__ float obs_value(const uint16_t* rows, int n, int kind, uint32_t cells, uint32_t apples_left,
-                                           uint32_t apple_cells, bool fresh, int k, uint32_t cell) {
-  float v = ((rows[cell >> 4] >> (cell & 15)) & 1) ? 0.0f : -1.0f;
-  int who = -1;
+// render record per env (shared memory): what P4 needs
+constexpr uint32_t R_FRESH = 1u << 2, R_FINAL = 1u << 3, R_SKIP = 1u << 6;   // bits 0-1 apples shown in obs, 4-5 apples at final
+
+template <int TILE>
+struct Smem {
+  alignas(16) uint8_t lut[(LUT_BYTES + 15) / 16 * 16];
+  alignas(16) uint8_t next[GW_MAX_H * GW_W * 4];
+  alignas(16) uint4 tmpl[64];
+  uint16_t rows[GW_MAX_H];
+  uint32_t cells_old[TILE], acts[TILE], geom_lo[TILE], geom_hi[TILE], close[TILE];
+  uint32_t cnt[TILE * 2];
+  uint32_t cells_new[TILE], cells_fin[TILE], rinfo[TILE];
+  uint16_t queue[TILE * 6];
+  uint32_t qn;
+  alignas(16) uint8_t mask[TILE * GW_MAX_LEARNERS * GW_N_ACTIONS + 16];
+};
+
+template <int THREADS, int TILE, int OBS>
+__device__ __forceinline__ void load_tables(Smem<TILE>& s, const Tables* __restrict__ T, int H, bool need_lut) {
+  const int tid = threadIdx.x;
+  if (need_lut) {
+    const uint4* src = reinterpret_cast<const uint4*>(T->pair_lut);
+    uint4* dst = reinterpret_cast<uint4*>(s.lut);
+    for (int i = tid; i < (LUT_BYTES + 15) / 16; i += THREADS) dst[i] = __ldg(src + i);
+    const uint4* nsrc = reinterpret_cast<const uint4*>(T->next_cell);
+    uint4* ndst = reinterpret_cast<uint4*>(s.next);
+    for (int i = tid; i < GW_MAX_H * GW_W * 4 / 16; i += THREADS) ndst[i] = __ldg(nsrc + i);
+  }
+  if (tid < GW_MAX_H) s.rows[tid] = T->map_rows[tid];
+  // constant observation template: -1 inactive / 0 active (WorldState reset, grid_world.py:433-434)
+  const int Q = (OBS == GW_OBS_F32) ? H * 4 : H * 2;
+  for (int q = tid; q < Q; q += THREADS) {
+    uint32_t w[4];
+    if (OBS == GW_OBS_F32) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    if (i < n && ((cells >> (8 * i)) & 0xFFu) == cell) who = i;           // WorldState[loc] = idx+1 in agent order
-  bool apple_here;
-  if (kind == GW_ENV_MULTI)
-    apple_here = ((apples_left >> k) & 1) && ((apple_cells >> (8 * k)) & 0xFFu) == cell;   // own apple only
-  else
-    apple_here = (apples_left & 1) && (apple_cells & 0xFFu) == cell;
+      for (int c = 0; c < 4; ++c) {
+        const int cell = q * 4 + c;
+        w[c] = ((T->map_rows[cell >> 4] >> (cell & 15)) & 1) ? 0u : 0xBF800000u;          // 0.0f / -1.0f
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int c0 = q * 8 + 2 * c, c1 = c0 + 1;
+        const uint32_t lo = ((T->map_rows[c0 >> 4] >> (c0 & 15)) & 1) ? 0u : 0xBF80u;      // bf16 0 / -1
+        const uint32_t hi = ((T->map_rows[c1 >> 4] >> (c1 & 15)) & 1) ? 0u : 0xBF80u;
+        w[c] = lo | (hi << 16);
+      }
+    }
+    s.tmpl[q] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  if (tid == 0) s.qn = 0;
+}
+
+// value of an agent / apple cell.  custom/ma_customenv.py:303-322 (step) / :198-209 (reset),
+// custom/customenv.py:161-163 / :341-344 (single env: raw ids, every remaining apple).
+__device__ __forceinline__ float special_value(int kind, bool fresh, int who, int k, bool apple_here) {
+  float v = 0.0f;
   if (who >= 0) {
     if (fresh) v = 0.5f;                                                   // AddAgent marker, grid_world.py:140
-    else if (apple_here || kind == GW_ENV_SINGLE) v = (float)(who + 1);    // id+9 is not remapped (A.7)
+    else if (apple_here || kind == GW_ENV_SINGLE) v = (float)(who + 1);    // id+9 is never remapped
     else v = (who == k) ? 1.0f : 5.0f;
   }
-  if (apple_here) v += 9.0f;
-  return v;
+  return apple_here ? v + 9.0f : v;
 }
 
 template <int OBS>
-__device__ __forceinline__ void render_obs(void* dst_base, long long e, const uint16_t* rows, int H, int n, int nl,
-                                           int kind, uint32_t cells, uint32_t apples_left, uint32_t apple_cells,
-                                           bool fresh, int lane) {
-  const int cells_per_obs = H * GW_W;
-  if (OBS == GW_OBS_F32) {
-    float4* dst = reinterpret_cast<float4*>(dst_base) + e * (long long)(nl * cells_per_obs / 4);
-    const int quads = nl * cells_per_obs / 4;
-    for (int q = lane; q < quads; q += 32) {
-      const int k = q / (cells_per_obs / 4);
-      const uint32_t c0 = (uint32_t)(q - k * (cells_per_obs / 4)) * 4;
-      float4 v;
-      v.x = obs_value(rows, n, kind, cells, apples_left, apple_cells, fresh, k, c0 + 0);
-      v.y = obs_value(rows, n, kind, cells, apples_left, apple_cells, fresh, k, c0 + 1);
-      v.z = obs_value(rows, n, kind, cells, apples_left, apple_cells, fresh, k, c0 + 2);
-      v.w = obs_value(rows, n, kind, cells, apples_left, apple_cells, fresh, k, c0 + 3);
-      __stcs(dst + q, v);                                                  // streaming: never re-read by this kernel
-    }
-  } else {
-    uint4* dst = reinterpret_cast<uint4*>(dst_base) + e * (long long)(nl * cells_per_obs / 8);
-    const int octs = nl * cells_per_obs / 8;
-    for (int q = lane; q < octs; q += 32) {
-      const int k = q / (cells_per_obs / 8);
-      const uint32_t c0 = (uint32_t)(q - k * (cells_per_obs / 8)) * 8;
-      uint32_t w[4];
+__device__ __forceinline__ void store_cell(void* obs_base, long long elem, float v) {
+  if (OBS == GW_OBS_F32) reinterpret_cast<float*>(obs_base)[elem] = v;
+  else reinterpret_cast<__nv_bfloat16*>(obs_base)[elem] = __float2bfloat16(v);
+}
+
+// patch the special cells of one env's observations (thread per env)
+template <int OBS>
+__device__ __forceinline__ void patch_env(void* obs_base, long long e, int cells_per_obs, int n, int nl, int kind,
+                                          uint32_t cells, uint32_t apples_left, uint32_t apple_cells, bool fresh) {
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const __nv_bfloat16 lo = __float2bfloat16(obs_value(rows, n, kind, cells, apples_left, apple_cells, fresh, k, c0 + 2 * h));
-        const __nv_bfloat16 hi = __float2bfloat16(obs_value(rows, n, kind, cells, apples_left, apple_cells, fresh, k, c0 + 2 * h + 1));
-        w[h] = (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
-      }
-      __stcs(dst + q, make_uint4(w[0], w[1], w[2], w[3]));
+  for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
+    if (k >= nl) break;
+    const long long base = (e * nl + k) * (long long)cells_per_obs;
+    const bool apple_on = (kind == GW_ENV_MULTI) ? ((apples_left >> k) & 1u) : (apples_left & 1u);
+    const uint32_t apple = (kind == GW_ENV_MULTI) ? (apple_cells >> (8 * k)) & 0xFFu : apple_cells & 0xFFu;
+    bool apple_covered = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i >= n) break;
+      const uint32_t c = (cells >> (8 * i)) & 0xFFu;
+      const bool here = apple_on && c == apple;
+      apple_covered |= here;
+      store_cell<OBS>(obs_base, base + c, special_value(kind, fresh, i, k, here));
     }
+    if (apple_on && !apple_covered) store_cell<OBS>(obs_base, base + apple, 9.0f);
   }
 }
 
-__device__ __forceinline__ void write_masks(int8_t* dst, long long e, const uint16_t* rows, int H, int nl, uint32_t cells,
-                                            int lane) {
-  if (dst == nullptr) return;
-  if (lane < nl * GW_N_ACTIONS) {
-    const int k = lane / GW_N_ACTIONS, a = lane - k * GW_N_ACTIONS;
-    const uint32_t m = action_mask_bits(rows, H, (cells >> (8 * k)) & 0xFFu);
-    dst[e * (nl * GW_N_ACTIONS) + lane] = (int8_t)((m >> a) & 1);
+// whole observation of one env written by one warp with the special cells patched in registers
+// (used for final_obs, which only the few envs that ended in this step need)
+template <int OBS, int TILE>
+__device__ __forceinline__ void render_env_warp(const Smem<TILE>& s, void* obs_base, long long e, int H, int n, int nl,
+                                                int kind, uint32_t cells, uint32_t apples_left, uint32_t apple_cells,
+                                                bool fresh, int lane) {
+  const int cpo = H * GW_W;
+  const int per_vec = (OBS == GW_OBS_F32) ? 4 : 8;
+  const int Q = cpo / per_vec;
+  uint4* dst = reinterpret_cast<uint4*>(obs_base) + e * (long long)(nl * Q);
+  for (int g = lane; g < nl * Q; g += 32) {
+    const int k = g / Q, q = g - k * Q;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c >= per_vec) break;
+      const uint32_t cell = (uint32_t)(q * per_vec + c);
+      int who = -1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < n && ((cells >> (8 * i)) & 0xFFu) == cell) who = i;
+      const bool apple_on = (kind == GW_ENV_MULTI) ? ((apples_left >> k) & 1u) : (apples_left & 1u);
+      const uint32_t apple = (kind == GW_ENV_MULTI) ? (apple_cells >> (8 * k)) & 0xFFu : apple_cells & 0xFFu;
+      const bool here = apple_on && apple == cell;
+      const float base = ((s.rows[cell >> 4] >> (cell & 15)) & 1) ? 0.0f : -1.0f;
+      v[c] = (who >= 0 || here) ? special_value(kind, fresh, who, k, here) : base;
+    }
+    uint4 o;
+    if (OBS == GW_OBS_F32) {
+      o = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+    } else {
+      uint32_t w[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h)
+        w[h] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(v[2 * h])) |
+               ((uint32_t)__bfloat16_as_ushort(__float2bfloat16(v[2 * h + 1])) << 16);
+      o = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    dst[g] = o;
+  }
+}
+
+// P4: observations + action masks of the tile
+template <int THREADS, int TILE, int OBS>
+__device__ __forceinline__ void render_tile(Smem<TILE>& s, const StepParams& p, long long tile_base, int tile_envs) {
+  const int tid = threadIdx.x;
+  const int cpo = p.H * GW_W;
+  const int Q = (OBS == GW_OBS_F32) ? cpo / 4 : cpo / 8;
+  if (p.io.obs != nullptr) {
+    // bulk: the constant template, 16 B per thread, consecutive threads -> consecutive addresses
+    uint4* dst = reinterpret_cast<uint4*>(p.io.obs) + tile_base * (long long)(p.nl * Q);
+    const int V = tile_envs * p.nl * Q;
+    int q = tid % Q;
+    const int qstep = THREADS % Q;
+    const bool partial = p.reset_mask != nullptr;          // masked reset: untouched envs keep their observation
+    for (int g = tid; g < V; g += THREADS) {
+      if (!partial || !(s.rinfo[g / (p.nl * Q)] & R_SKIP)) __stcs(dst + g, s.tmpl[q]);
+      q += qstep;
+      if (q >= Q) q -= Q;
+    }
+  }
+  __syncthreads();                                           // patches must land after the template
+  if (tid < tile_envs) {
+    const uint32_t ri = s.rinfo[tid];
+    if (p.io.obs != nullptr && !(ri & R_SKIP))
+      patch_env<OBS>(p.io.obs, tile_base + tid, cpo, p.n, p.nl, p.kind, s.cells_new[tid], ri & 3u, p.apple_cells,
+                     (ri & R_FRESH) != 0);
+    if (p.io.action_mask != nullptr && !(ri & R_SKIP)) {
+#pragma unroll
+      for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
+        if (k >= p.nl) break;
+        const uint32_t m = action_mask_bits(s.rows, p.H, (s.cells_new[tid] >> (8 * k)) & 0xFFu);
+#pragma unroll
+        for (int a = 0; a < GW_N_ACTIONS; ++a) s.mask[(tid * p.nl + k) * GW_N_ACTIONS + a] = (uint8_t)((m >> a) & 1u);
+      }
+    }
+  }
+  // final observations of the envs that ended (rare): one warp per such env
+  if (p.io.final_obs != nullptr) {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int el = warp; el < tile_envs; el += THREADS / 32) {
+      const uint32_t ri = s.rinfo[el];
+      if (ri & R_FINAL)
+        render_env_warp<OBS, TILE>(s, p.io.final_obs, tile_base + el, p.H, p.n, p.nl, p.kind, s.cells_fin[el],
+                                   (ri >> 4) & 3u, p.apple_cells, false, lane);
+    }
+  }
+  if (p.io.action_mask != nullptr) {
+    __syncthreads();
+    const int bytes = tile_envs * p.nl * GW_N_ACTIONS;
+    int8_t* dst = p.io.action_mask + tile_base * (long long)(p.nl * GW_N_ACTIONS);
+    const bool partial = p.reset_mask != nullptr;
+    if (!partial && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      const int vecs = bytes / 16;
+      for (int i = tid; i < vecs; i += THREADS) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(s.mask)[i];
+      for (int i = vecs * 16 + tid; i < bytes; i += THREADS) dst[i] = (int8_t)s.mask[i];
+    } else {
+      for (int i = tid; i < bytes; i += THREADS)
+        if (!partial || !(s.rinfo[i / (p.nl * GW_N_ACTIONS)] & R_SKIP)) dst[i] = (int8_t)s.mask[i];
+    }
   }
 }
 
 // ------------------------------------------------------------------ spawn
 // setup_env, custom/ma_customenv.py:372-380: a sorted n-subset of the active cells (row-major order).
 // Replay mode reads the recorded cells; native mode draws them from Philox (uniform over subsets).
-__device__ __forceinline__ uint32_t spawn_cells(const StepParams& p, long long e, uint32_t tick, int lane) {
+__device__ __forceinline__ uint32_t spawn_cells(const StepParams& p, long long e, uint32_t tick) {
   uint32_t cells = 0;
   if (p.io.spawn != nullptr) {
     for (int i = 0; i < p.n; ++i) {
@@ -127,20 +259,24 @@ __device__ __forceinline__ uint32_t spawn_cells(const StepParams& p, long long e
     return cells;
   }
   const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
-  const uint4 w = philox4x32(make_uint4((uint32_t)gid, (uint32_t)(gid >> 32), tick, 0x100u),
-                             make_uint2(p.seed_lo, p.seed_hi));
-  const uint32_t words[4] = {w.x, w.y, w.z, w.w};
-  int chosen[4] = {0, 0, 0, 0};
+  uint32_t w[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), tick, 0x100u};
+  philox4x32(w, p.seed_lo, p.seed_hi);
+  uint32_t chosen = 0;                       // up to 4 sorted indices, 8 bits each
   const int na = p.tables->n_active;
-  for (int k = 0; k < p.n; ++k) {
-    int d = (int)__umulhi(words[k], (uint32_t)(na - k));                   // k-th draw among the remaining cells
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k >= p.n) break;
+    uint32_t d = __umulhi(w[k], (uint32_t)(na - k));                      // k-th draw among the remaining cells
     int pos = 0;
-    for (int t = 0; t < k; ++t)                                            // chosen[] ascending
-      if (d >= chosen[t]) { ++d; pos = t + 1; }
-    for (int t = k; t > pos; --t) chosen[t] = chosen[t - 1];
-    chosen[pos] = d;
+#pragma unroll
+    for (int t = 0; t < 3; ++t)                                           // chosen ascending
+      if (t < k && d >= ((chosen >> (8 * t)) & 0xFFu)) { ++d; pos = t + 1; }
+    const uint32_t lowmask = (pos == 0) ? 0u : (0xFFFFFFFFu >> (32 - 8 * pos));
+    chosen = (chosen & lowmask) | (d << (8 * pos)) | ((chosen & ~lowmask) << 8);
   }
-  for (int i = 0; i < p.n; ++i) cells |= (uint32_t)p.tables->active_cell[chosen[i]] << (8 * i);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < p.n) cells |= (uint32_t)__ldg(&p.tables->active_cell[(chosen >> (8 * i)) & 0xFFu]) << (8 * i);
   return cells;
 }
 
@@ -153,249 +289,393 @@ __device__ __forceinline__ uint32_t fresh_meta(const StepParams& p, uint32_t cel
   return meta;                                                             // multi: prev_distance = None (:212)
 }
 
-__device__ __forceinline__ void stat_add(unsigned long long* stats, int slot, int which, unsigned long long v) {
-  atomicAdd(&stats[slot * 8 + which], v);
+__device__ __forceinline__ void write_positions(int8_t* dst, long long e, int n, uint32_t cells) {
+  if (dst == nullptr) return;
+  if (n == 4) {
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t c = (cells >> (8 * i)) & 0xFFu, d = (cells >> (8 * (i + 2))) & 0xFFu;
+      lo |= ((c >> 4) | ((c & 15u) << 8)) << (16 * i);
+      hi |= ((d >> 4) | ((d & 15u) << 8)) << (16 * i);
+    }
+    reinterpret_cast<uint2*>(dst)[e] = make_uint2(lo, hi);
+  } else {
+    for (int i = 0; i < n; ++i) {
+      const uint32_t c = (cells >> (8 * i)) & 0xFFu;
+      dst[(e * n + i) * 2] = (int8_t)(c >> 4);
+      dst[(e * n + i) * 2 + 1] = (int8_t)(c & 15u);
+    }
+  }
 }
 
 // ------------------------------------------------------------------ reset kernel
-template <int OBS>
-__global__ void __launch_bounds__(128) gw_reset_kernel(StepParams p) {
-  __shared__ uint16_t s_rows[GW_MAX_H];
-  if (threadIdx.x < GW_MAX_H) s_rows[threadIdx.x] = p.tables->map_rows[threadIdx.x];
+template <int THREADS, int TILE, int OBS>
+__global__ void __launch_bounds__(THREADS) gw_reset_kernel(StepParams p) {
+  __shared__ Smem<TILE> s;
+  load_tables<THREADS, TILE, OBS>(s, p.tables, p.H, false);
   __syncthreads();
-  const long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (e >= p.E) return;
-  if (p.reset_mask != nullptr && p.reset_mask[e] == 0) return;
-  uint4 st = p.state[e];
-  const uint32_t cells = spawn_cells(p, e, st.z, lane);
-  const uint32_t meta = fresh_meta(p, cells);
-  if (p.io.obs) render_obs<OBS>(p.io.obs, e, s_rows, p.H, p.n, p.nl, p.kind, cells, meta & M_APPLES, p.apple_cells, true, lane);
-  write_masks(p.io.action_mask, e, s_rows, p.H, p.nl, cells, lane);
-  if (lane < p.n * 2 && p.io.positions) {
-    const uint32_t c = (cells >> (8 * (lane >> 1))) & 0xFFu;
-    p.io.positions[e * p.n * 2 + lane] = (int8_t)((lane & 1) ? (c & 15) : (c >> 4));
+  const long long tile_base = (long long)blockIdx.x * TILE;
+  const int tile_envs = (int)min((long long)TILE, p.E - tile_base);
+  const int tid = threadIdx.x;
+  if (tid < tile_envs) {
+    const long long e = tile_base + tid;
+    if (p.reset_mask != nullptr && p.reset_mask[e] == 0) {
+      s.rinfo[tid] = R_SKIP;
+      s.cells_new[tid] = 0;
+    } else {
+      const uint4 st = p.state[e];
+      const uint32_t cells = spawn_cells(p, e, st.z);
+      const uint32_t meta = fresh_meta(p, cells);
+      s.cells_new[tid] = cells;
+      s.rinfo[tid] = (meta & M_APPLES) | R_FRESH;
+      write_positions(p.io.positions, e, p.n, cells);
+      p.state[e] = make_uint4(cells, meta, st.z + 1, 0u);
+    }
   }
-  if (lane == 0) p.state[e] = make_uint4(cells, meta, st.z + 1, 0u);
+  __syncthreads();
+  render_tile<THREADS, TILE, OBS>(s, p, tile_base, tile_envs);
 }
 
 // ------------------------------------------------------------------ step kernel
-template <bool FEAR, int OBS>
-__global__ void __launch_bounds__(128) gw_step_kernel(StepParams p) {
-  __shared__ uint16_t s_rows[GW_MAX_H];
-  if (threadIdx.x < GW_MAX_H) s_rows[threadIdx.x] = p.tables->map_rows[threadIdx.x];
+template <int THREADS, int TILE, bool FEAR, int OBS>
+__global__ void __launch_bounds__(THREADS) gw_step_kernel(StepParams p) {
+  __shared__ Smem<TILE> s;
+  load_tables<THREADS, TILE, OBS>(s, p.tables, p.H, true);
   __syncthreads();
-  const long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (e >= p.E) return;
-  const Tables* T = p.tables;
+  const Tables* __restrict__ T = p.tables;
+  const long long tile_base = (long long)blockIdx.x * TILE;
+  const int tile_envs = (int)min((long long)TILE, p.E - tile_base);
+  const int tid = threadIdx.x;
   const int n = p.n, nl = p.nl;
+  const long long e = tile_base + tid;
+  const bool own = tid < tile_envs;
 
-  const uint4 st = p.state[e];                                             // same address on all lanes: one broadcast load
-  const uint32_t cells = st.x;
-  uint32_t meta = st.y;
-  const uint32_t tick = st.z;
+  // per-env registers that live across the phases
+  uint32_t task_bits = 0;            // bit (x*4 + j): (x, j) is an enqueued FeAR task
+  double reward[GW_MAX_LEARNERS] = {0.0, 0.0};
+  uint32_t fear_stat_ended = 0, steps_now = 0;
+  int ret0 = 0, ret1 = 0;
 
-  // ---- setup_step (ma_customenv.py:432-452): lane i < n owns agent i's action and MdR
-  int my_act = 0, my_mdr = 0;
-  if (lane < n) {
-    const uint32_t c = (cells >> (8 * lane)) & 0xFFu;
-    my_mdr = T->mdr_map[c];
-    if (lane < nl) {
-      my_act = p.io.learner_actions[e * nl + lane];                        // :239-242
-    } else if (p.io.npc_actions != nullptr) {
-      my_act = p.io.npc_actions[e * n + lane];
+  // ================================================================= P1
+  if (own) {
+    const uint4 st = p.state[e];
+    const uint32_t cells = st.x;
+    uint32_t meta = st.y;
+    const uint32_t tick = st.z;
+
+    // ---- setup_step (ma_customenv.py:432-452)
+    uint32_t acts = 0, mdrs = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < n) mdrs |= (uint32_t)__ldg(&T->mdr_map[(cells >> (8 * i)) & 0xFFu]) << (4 * i);   // :445-447
+#pragma unroll
+    for (int k = 0; k < GW_MAX_LEARNERS; ++k)
+      if (k < nl) acts |= (uint32_t)min(max((int)p.io.learner_actions[e * nl + k], 0), 8) << (4 * k);   // :239-242
+    if (p.io.npc_actions != nullptr) {
+#pragma unroll
+      for (int i = 1; i < 4; ++i)
+        if (i >= nl && i < n) acts |= (uint32_t)min(max((int)p.io.npc_actions[e * n + i], 0), 8) << (4 * i);
     } else {
       const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
-      const uint4 w = philox4x32(make_uint4((uint32_t)gid, (uint32_t)(gid >> 32), tick, (uint32_t)lane),
-                                 make_uint2(p.seed_lo, p.seed_hi));
-      const int pert = w.x < p.perturb_thr ? 1 : 0;                        // random.random() < 0.25 (:441)
-      const uint32_t* thr = T->policy_thr[T->policy_map[c]][pert];
-      const uint32_t u = w.y >> 1;
-      int a = 0;
+      uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a += (u >= thr[k]) ? 1 : 0;              // np.random.choice(9, p) (custom_agent.py:31)
-      my_act = a;
-    }
-    my_act = min(max(my_act, 0), GW_N_ACTIONS - 1);
-  }
-  uint32_t acts = 0, mdrs = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    acts |= ((uint32_t)__shfl_sync(0xFFFFFFFFu, my_act, i) & 0xFu) << (4 * i);
-    mdrs |= ((uint32_t)__shfl_sync(0xFFFFFFFFu, my_mdr, i) & 0xFu) << (4 * i);
-  }
-
-  // ---- FeAR on the pre-step positions (ma_customenv.py:245-252 / customenv.py:113-120)
-  double fear[GW_MAX_LEARNERS] = {0.0, 0.0};
-  if (FEAR) {
-    for (int x = 0; x < nl; ++x) {
-      uint32_t close = 0;                                                  // close_agents :456-464
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (k < n && (k == x || manhattan((cells >> (8 * x)) & 0xFFu, (cells >> (8 * k)) & 0xFFu) <= p.fear_radius))
-          close |= 1u << k;
-      const uint32_t packed = fear_counts_warp(s_rows, p.H, n, cells, acts, close, x, (mdrs >> (4 * x)) & 0xF, lane);
-      fear[x] = fear_sum_from_counts(T, n, packed);
-    }
-  }
-
-  // ---- the real update (:254), evaluated identically on every lane
-  const uint32_t apples_before = meta & M_APPLES;
-  const SimResult r = simulate<true>(s_rows, p.H, n, cells, acts, p.apple_cells, apples_before, nl);
-  const uint32_t cells_new = r.cells;
-
-  double reward[GW_MAX_LEARNERS] = {0.0, 0.0};
-  uint32_t apples_left = apples_before;
-  uint32_t term_now = 0, trunc_now = 0, apples_rewarded = 0, crash_count = 0, shaped = 0;
-  if (p.kind == GW_ENV_MULTI) {
-    uint32_t term = (meta >> M_TERM_SH) & 3u, trunc = (meta & M_TRUNC) ? 1u : 0u;
-    int ri[GW_MAX_LEARNERS] = {0, 0};
-#pragma unroll
-    for (int k = 0; k < GW_MAX_LEARNERS; ++k)                              // own apple only (:258-271)
-      if (k < nl && ((apples_left >> k) & 1) && ((r.caught >> (3 * (k * 2 + k))) & 7u)) {
-        apples_left &= ~(1u << k);
-        ri[k] += 20;
-        ++apples_rewarded;
+      for (int i = 1; i < 4; ++i) {
+        if (i < nl || i >= n) continue;
+        const int m = i - nl;                                              // NPC index: Philox call m/2, words 2(m%2), 2(m%2)+1
+        if ((m & 1) == 0) {
+          w[0] = (uint32_t)gid; w[1] = (uint32_t)(gid >> 32); w[2] = tick; w[3] = (uint32_t)(m >> 1);
+          philox4x32(w, p.seed_lo, p.seed_hi);
+        }
+        const uint32_t wa = (m & 1) ? w[2] : w[0], wb = (m & 1) ? w[3] : w[1];
+        const int pert = wa < p.perturb_thr ? 1 : 0;                       // random.random() < 0.25 (:441)
+        const uint32_t c = (cells >> (8 * i)) & 0xFFu;
+        const uint4* thr4 = reinterpret_cast<const uint4*>(T->policy_thr[__ldg(&T->policy_map[c])][pert]);
+        const uint4 t0 = __ldg(thr4), t1 = __ldg(thr4 + 1);
+        const uint32_t u = wb >> 1;
+        const uint32_t a = (u >= t0.x) + (u >= t0.y) + (u >= t0.z) + (u >= t0.w) + (u >= t1.x) + (u >= t1.y) +
+                           (u >= t1.z) + (u >= t1.w);                      // np.random.choice(9, p) (custom_agent.py:31)
+        acts |= a << (4 * i);
       }
-    if (apples_rewarded && apples_left == 0) {                             // last apple: +20 to all, truncate (:272-275)
-#pragma unroll
-      for (int k = 0; k < GW_MAX_LEARNERS; ++k) if (k < nl) ri[k] += 20;
-      trunc = 1;
     }
-    uint32_t pdv = 0, pd[2] = {0, 0};
+    const PairGeom g = pair_geometry(n, cells);
+
+    // ---- FeAR tasks on the pre-step positions (ma_customenv.py:245-252 / customenv.py:113-120)
+    if (FEAR) {
+      s.cells_old[tid] = cells;
+      s.acts[tid] = acts | (mdrs << 16);
+      s.geom_lo[tid] = g.didx_lo;
+      s.geom_hi[tid] = g.didx_hi | (g.near6 << 16);
+      s.cnt[tid * 2] = 0;
+      s.cnt[tid * 2 + 1] = 0;
+      uint32_t closew = 0;
 #pragma unroll
-    for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
-      if (k >= nl) continue;
-      if ((r.crash >> k) & 1) {                                            // :281-285
-        ri[k] -= 10;
-        ++crash_count;
+      for (int x = 0; x < GW_MAX_LEARNERS; ++x) {
+        if (x >= nl) break;
+        uint32_t close = 0;                                                // close_agents :456-464
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < n && (k == x || manhattan((cells >> (8 * x)) & 0xFFu, (cells >> (8 * k)) & 0xFFu) <= p.fear_radius))
+            close |= 1u << k;
+        closew |= close << (4 * x);
+        // action == MdR: both counts are equal -> Resp = 0 exactly.  Agents that no chain of near pairs links to the
+        // actor cannot be influenced by its move -> equal counts -> 0 as well.
+        if (((acts >> (4 * x)) & 0xFu) != ((mdrs >> (4 * x)) & 0xFu)) {
+          const uint32_t js = reach_mask(g.near6, x) & ~(1u << x) & ((1u << n) - 1u);
+          if (js) {
+            const uint32_t slot = atomicAdd(&s.qn, (uint32_t)__popc(js));
+            uint32_t k2 = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if ((js >> j) & 1u) {
+                s.queue[slot + k2] = (uint16_t)(tid | (x << 8) | (j << 9) | (((close >> j) & 1u) << 11));
+                ++k2;
+              }
+            task_bits |= js << (4 * x);
+          }
+        }
+      }
+      s.close[tid] = closew;
+    }
+
+    // ---- the real update (:254)
+    const uint32_t apples_before = meta & M_APPLES;
+    const StepResult r = world_update(s.lut, s.next, n, cells, acts, g, p.apple_cells, apples_before, nl);
+    const uint32_t cells_new = r.cells;
+
+    uint32_t apples_left = apples_before;
+    uint32_t term_now = 0, trunc_now = 0, apples_rewarded = 0, crash_count = 0, shaped = 0;
+    if (p.kind == GW_ENV_MULTI) {
+      uint32_t term = (meta >> M_TERM_SH) & 3u, trunc = (meta & M_TRUNC) ? 1u : 0u;
+      int ri[GW_MAX_LEARNERS] = {0, 0};
+#pragma unroll
+      for (int k = 0; k < GW_MAX_LEARNERS; ++k)                            // own apple only (:258-271)
+        if (k < nl && ((apples_left >> k) & 1u) && ((r.caught >> (3 * (k * 2 + k))) & 7u)) {
+          apples_left &= ~(1u << k);
+          ri[k] += 20;
+          ++apples_rewarded;
+        }
+      if (apples_rewarded && apples_left == 0) {                           // last apple: +20 to all, truncate (:272-275)
+#pragma unroll
+        for (int k = 0; k < GW_MAX_LEARNERS; ++k) if (k < nl) ri[k] += 20;
         trunc = 1;
-        term |= 1u << k;
       }
-      if ((apples_left >> k) & 1) {                                        // :287-300
-        const uint32_t d = (uint32_t)manhattan((cells_new >> (8 * k)) & 0xFFu, (p.apple_cells >> (8 * k)) & 0xFFu);
-        const uint32_t prev_valid = (meta >> (M_PDV_SH + k)) & 1u;
-        const uint32_t prev = (meta >> (k == 0 ? M_PD0_SH : M_PD1_SH)) & 31u;
-        if (prev_valid && prev > d) { ri[k] += 1; shaped |= 1u << k; }
-        pdv |= 1u << k;
-        pd[k] = d;
+      uint32_t pdv = 0, pd[2] = {0, 0};
+#pragma unroll
+      for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
+        if (k >= nl) continue;
+        if ((r.crash >> k) & 1u) {                                         // :281-285
+          ri[k] -= 10;
+          ++crash_count;
+          trunc = 1;
+          term |= 1u << k;
+        }
+        if ((apples_left >> k) & 1u) {                                     // :287-300
+          const uint32_t d = (uint32_t)manhattan((cells_new >> (8 * k)) & 0xFFu, (p.apple_cells >> (8 * k)) & 0xFFu);
+          const uint32_t prev_valid = (meta >> (M_PDV_SH + k)) & 1u;
+          const uint32_t prev = (meta >> (k == 0 ? M_PD0_SH : M_PD1_SH)) & 31u;
+          if (prev_valid && prev > d) { ri[k] += 1; shaped |= 1u << k; }
+          pdv |= 1u << k;
+          pd[k] = d;
+        }
+        reward[k] = (double)ri[k];
       }
-      reward[k] = (double)ri[k];
+      term_now = term;
+      trunc_now = trunc ? ((1u << nl) - 1u) : 0u;
+      const uint32_t steps = min(((meta >> M_STEPS_SH) & M_STEPS_MASK) + 1u, M_STEPS_MASK);
+      meta = apples_left | (term << M_TERM_SH) | (trunc ? M_TRUNC : 0u) | (pdv << M_PDV_SH) | (pd[0] << M_PD0_SH) |
+             (pd[1] << M_PD1_SH) | (steps << M_STEPS_SH);
+    } else {                                                               // customenv.py:126-158
+      double rew = 0.0;
+      const uint32_t apple = p.apple_cells & 0xFFu;
+      const uint32_t d = (uint32_t)manhattan(cells_new & 0xFFu, apple);
+      if (r.crash & 1u) { rew -= 10.0; term_now = 1; crash_count = 1; }
+      if ((apples_left & 1u) && (r.caught & 7u) == 1u) {                   // len(apples_caught) == 1 (:143)
+        apples_left &= ~1u;
+        rew += 20.0;
+        trunc_now = 1;
+        apples_rewarded = 1;
+      }
+      const uint32_t prev = (meta >> M_PD0_SH) & 31u;
+      if (d < prev) { rew += 0.1; shaped = 1; }                            // :157-158
+      reward[0] = rew;
+      const uint32_t steps = min(((meta >> M_STEPS_SH) & M_STEPS_MASK) + 1u, M_STEPS_MASK);
+      meta = apples_left | (1u << M_PDV_SH) | (d << M_PD0_SH) | (steps << M_STEPS_SH);
     }
-    term_now = term;
-    trunc_now = trunc ? ((1u << nl) - 1u) : 0u;
-    const uint32_t steps = min(((meta >> M_STEPS_SH) & M_STEPS_MASK) + 1u, M_STEPS_MASK);
-    meta = apples_left | (term << M_TERM_SH) | (trunc ? M_TRUNC : 0u) | (pdv << M_PDV_SH) | (pd[0] << M_PD0_SH) |
-           (pd[1] << M_PD1_SH) | (steps << M_STEPS_SH);
-  } else {                                                                 // customenv.py:126-158
-    double rew = 0.0;
-    const uint32_t apple = p.apple_cells & 0xFFu;
-    const uint32_t d = (uint32_t)manhattan(cells_new & 0xFFu, apple);
-    if (r.crash & 1u) { rew -= 10.0; term_now = 1; crash_count = 1; }
-    if ((apples_left & 1u) && (r.caught & 7u) == 1u) {                     // len(apples_caught) == 1 (:143)
-      apples_left &= ~1u;
-      rew += 20.0;
-      trunc_now = 1;
-      apples_rewarded = 1;
-    }
-    const uint32_t prev = (meta >> M_PD0_SH) & 31u;
-    if (d < prev) { rew += 0.1; shaped = 1; }                              // :157-158
-    reward[0] = rew;
-    const uint32_t steps = min(((meta >> M_STEPS_SH) & M_STEPS_MASK) + 1u, M_STEPS_MASK);
-    meta = apples_left | (1u << M_PDV_SH) | (d << M_PD0_SH) | (steps << M_STEPS_SH);
-  }
-  const uint32_t steps_now = (meta >> M_STEPS_SH) & M_STEPS_MASK;
-  const bool episode_over = (p.kind == GW_ENV_MULTI) ? (trunc_now != 0) : ((term_now | trunc_now) != 0);
-  const bool ended = episode_over || (p.max_steps > 0 && (int)steps_now >= p.max_steps);
+    steps_now = (meta >> M_STEPS_SH) & M_STEPS_MASK;
+    const bool episode_over = (p.kind == GW_ENV_MULTI) ? (trunc_now != 0) : ((term_now | trunc_now) != 0);
+    const bool ended = episode_over || (p.max_steps > 0 && (int)steps_now >= p.max_steps);
 
-  // ---- scalar outputs
-  if (lane < nl) {
-    const long long o = e * nl + lane;
-    const double f = fear[lane == 0 ? 0 : 1], rw = reward[lane == 0 ? 0 : 1];
-    if (p.io.reward) p.io.reward[o] = (float)rw;
-    if (p.io.fear) p.io.fear[o] = f;
-    if (p.io.shaped_reward) p.io.shaped_reward[o] = (float)(p.fear_weight * f + rw);   // maddpg/agent.py:130
-    if (p.io.terminated) p.io.terminated[o] = (uint8_t)((term_now >> lane) & 1u);
-    if (p.io.truncated) p.io.truncated[o] = (uint8_t)((trunc_now >> lane) & 1u);
-  }
-  if (lane < n * 2 && p.io.positions) {
-    const uint32_t c = (cells_new >> (8 * (lane >> 1))) & 0xFFu;
-    p.io.positions[e * n * 2 + lane] = (int8_t)((lane & 1) ? (c & 15) : (c >> 4));
-  }
-  if (lane == 0) {
+    // ---- scalar outputs (one thread per env: each array is written with unit stride across the warp)
+    if (nl == 2) {
+      if (p.io.reward) reinterpret_cast<float2*>(p.io.reward)[e] = make_float2((float)reward[0], (float)reward[1]);
+      if (p.io.terminated) reinterpret_cast<uchar2*>(p.io.terminated)[e] = make_uchar2(term_now & 1u, (term_now >> 1) & 1u);
+      if (p.io.truncated) reinterpret_cast<uchar2*>(p.io.truncated)[e] = make_uchar2(trunc_now & 1u, (trunc_now >> 1) & 1u);
+    } else {
+      if (p.io.reward) p.io.reward[e] = (float)reward[0];
+      if (p.io.terminated) p.io.terminated[e] = (uint8_t)(term_now & 1u);
+      if (p.io.truncated) p.io.truncated[e] = (uint8_t)(trunc_now & 1u);
+    }
+    write_positions(p.io.positions, e, n, cells_new);
     if (p.io.ended) p.io.ended[e] = ended ? 1 : 0;
     if (p.io.info)
       p.io.info[e] = (r.crash & 15u) | ((r.restr & 15u) << 4) | (crash_count << 8) | (apples_rewarded << 10) |
-                     ((ended ? 1u : 0u) << 12) | (r.unresolved << 13) | (shaped << 14);
+                     ((ended ? 1u : 0u) << 12) | (shaped << 14);
+
+    // ---- episode return (reward units: 1 multi, 0.1 single), state for the next step, render record
+    ret0 = (int)(short)(st.w & 0xFFFFu);
+    ret1 = (int)(short)(st.w >> 16);
+    const double unit = (p.kind == GW_ENV_MULTI) ? 1.0 : 10.0;
+    ret0 += (int)lrint(reward[0] * unit);
+    ret1 += (int)lrint(reward[1] * unit);
+    fear_stat_ended = (ended ? 1u : 0u) | (crash_count << 1) | (apples_rewarded << 3);
+    if (ended && p.auto_reset) {
+      const uint32_t cells_sp = spawn_cells(p, e, tick);
+      const uint32_t meta_sp = fresh_meta(p, cells_sp);
+      s.cells_new[tid] = cells_sp;
+      s.cells_fin[tid] = cells_new;
+      s.rinfo[tid] = (meta_sp & M_APPLES) | R_FRESH | R_FINAL | (apples_left << 4);
+      p.state[e] = make_uint4(cells_sp, meta_sp, tick + 1, 0u);
+    } else {
+      s.cells_new[tid] = cells_new;
+      s.rinfo[tid] = apples_left;
+      p.state[e] = make_uint4(cells_new, meta, tick + 1, ((uint32_t)ret0 & 0xFFFFu) | ((uint32_t)ret1 << 16));
+    }
   }
 
-  // ---- episode return (reward units: 1 multi, 0.1 single) and statistics
-  int ret0 = (int)(short)(st.w & 0xFFFFu), ret1 = (int)(short)(st.w >> 16);
-  const double unit = (p.kind == GW_ENV_MULTI) ? 1.0 : 10.0;
-  ret0 += (int)lrint(reward[0] * unit);
-  ret1 += (int)lrint(reward[1] * unit);
-  if (lane == 0) {
-    const int slot = (int)(e & (STAT_SLOTS - 1));
-    if (ended) {
-      stat_add(p.stats, slot, ST_EPISODES, 1);
-      stat_add(p.stats, slot, ST_LEN, steps_now);
-      stat_add(p.stats, slot, ST_RETURN_MILLI, (unsigned long long)(long long)llrint((ret0 + ret1) * (1000.0 / unit)));
-    }
-    if (crash_count) stat_add(p.stats, slot, ST_CRASH, crash_count);
-    if (apples_rewarded) stat_add(p.stats, slot, ST_APPLES, apples_rewarded);
-    if (r.unresolved) stat_add(p.stats, slot, ST_UNRES, 1);
-    if (FEAR) {
-      const int nz = (fear[0] != 0.0) + (fear[1] != 0.0);
-      if (nz) {
-        stat_add(p.stats, slot, ST_FEAR_NZ, nz);
-        atomicAdd(reinterpret_cast<double*>(&p.stats[slot * 8 + ST_FEAR_BITS]), fear[0] + fear[1]);
+  // ================================================================= P2: counterfactual sims (Responsibility.py:20-54)
+  if (FEAR) {
+    __syncthreads();
+    const uint32_t n_work = s.qn * 18u;
+    for (uint32_t w = tid; w < n_work; w += THREADS) {
+      const uint32_t tk = s.queue[w / 18u], rr = w % 18u;
+      const uint32_t v = rr / 9u, ap = rr - v * 9u;
+      const uint32_t el = tk & 0xFFu, x = (tk >> 8) & 1u, j = (tk >> 9) & 3u, jc = (tk >> 11) & 1u;
+      if (!jc && ap != 0) continue;                      // affected not in the list: it Stays in all nine sims (:43)
+      const uint32_t cells = s.cells_old[el], aw = s.acts[el];
+      const uint32_t close = (s.close[el] >> (4 * x)) & 0xFu;
+      const uint32_t keep = ((close & 1u) ? 0xFu : 0u) | ((close & 2u) ? 0xF0u : 0u) | ((close & 4u) ? 0xF00u : 0u) |
+                            ((close & 8u) ? 0xF000u : 0u);
+      uint32_t a4 = aw & keep;                           // agents outside the close list Stay (defaultAction='stay')
+      if (v == 0) a4 = (a4 & ~(0xFu << (4 * x))) | (((aw >> (16 + 4 * x)) & 0xFu) << (4 * x));   // actor plays its MdR (:169-172)
+      if (jc) a4 = (a4 & ~(0xFu << (4 * j))) | (ap << (4 * j));                                  // affected tries action ap (:34-39)
+      PairGeom g;
+      g.didx_lo = s.geom_lo[el];
+      g.didx_hi = s.geom_hi[el] & 0xFFFFu;
+      g.near6 = s.geom_hi[el] >> 16;
+      if (counterfactual_valid(s.lut, s.next, n, cells, a4, g, (int)j)) {
+        const uint32_t jslot = j - (j > x ? 1u : 0u);
+        atomicAdd(&s.cnt[el * 2 + x], (jc ? 1u : 9u) << (4 * (jslot * 2 + v)));
       }
     }
+    __syncthreads();
   }
 
-  // ---- observations, masks, auto-reset
-  uint32_t cells_out = cells_new, meta_out = meta, tick_out = tick + 1, ret_out;
-  if (ended && p.auto_reset) {
-    if (p.io.final_obs)
-      render_obs<OBS>(p.io.final_obs, e, s_rows, p.H, n, nl, p.kind, cells_new, apples_left, p.apple_cells, false, lane);
-    cells_out = spawn_cells(p, e, tick, lane);
-    meta_out = fresh_meta(p, cells_out);
-    ret_out = 0;
-    if (p.io.obs)
-      render_obs<OBS>(p.io.obs, e, s_rows, p.H, n, nl, p.kind, cells_out, meta_out & M_APPLES, p.apple_cells, true, lane);
-  } else {
-    ret_out = ((uint32_t)ret0 & 0xFFFFu) | ((uint32_t)ret1 << 16);
-    if (p.io.obs)
-      render_obs<OBS>(p.io.obs, e, s_rows, p.H, n, nl, p.kind, cells_new, apples_left, p.apple_cells, false, lane);
+  // ================================================================= P3: fear, shaped reward, statistics
+  if (own) {
+    double fear[GW_MAX_LEARNERS] = {0.0, 0.0};
+    if (FEAR) {
+#pragma unroll
+      for (int x = 0; x < GW_MAX_LEARNERS; ++x) {
+        if (x >= nl) break;
+        const uint32_t tb = (task_bits >> (4 * x)) & 0xFu;
+        if (tb == 0) continue;
+        const uint32_t c = s.cnt[tid * 2 + x];
+        double rs[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int js = 0; js < 3; ++js) {
+          const int j = js + (js >= x ? 1 : 0);
+          if ((tb >> j) & 1u) rs[js] = T->resp_lut[(c >> (8 * js)) & 0xFu][(c >> (8 * js + 4)) & 0xFu];
+        }
+        fear[x] = fear_sum3(n, rs[0], rs[1], rs[2]);
+      }
+    }
+    if (nl == 2) {
+      if (p.io.fear) reinterpret_cast<double2*>(p.io.fear)[e] = make_double2(fear[0], fear[1]);
+      if (p.io.shaped_reward)
+        reinterpret_cast<float2*>(p.io.shaped_reward)[e] =
+            make_float2((float)(p.fear_weight * fear[0] + reward[0]), (float)(p.fear_weight * fear[1] + reward[1]));   // maddpg/agent.py:130
+    } else {
+      if (p.io.fear) p.io.fear[e] = fear[0];
+      if (p.io.shaped_reward) p.io.shaped_reward[e] = (float)(p.fear_weight * fear[0] + reward[0]);
+    }
+    // statistics: most lanes contribute nothing, so reduce over the warp first
+    const uint32_t ended = fear_stat_ended & 1u, crashes = (fear_stat_ended >> 1) & 3u, apples = (fear_stat_ended >> 3) & 3u;
+    const int nz = FEAR ? ((fear[0] != 0.0) + (fear[1] != 0.0)) : 0;
+    const unsigned act = __activemask();
+    const unsigned any = __ballot_sync(act, ended | crashes | apples | (uint32_t)nz);
+    if (any) {
+      const double unit = (p.kind == GW_ENV_MULTI) ? 1.0 : 10.0;
+      const int slot = (int)((e >> 5) & (STAT_SLOTS - 1));
+      const int lane = tid & 31;
+      const int leader = __ffs(act) - 1;
+      const unsigned w_end = __reduce_add_sync(act, ended), w_len = __reduce_add_sync(act, ended ? steps_now : 0u);
+      const unsigned w_cr = __reduce_add_sync(act, crashes), w_ap = __reduce_add_sync(act, apples);
+      const unsigned w_nz = __reduce_add_sync(act, (unsigned)nz);
+      const int w_ret = __reduce_add_sync(act, ended ? (ret0 + ret1) : 0);
+      if (lane == leader) {
+        if (w_end) {
+          atomicAdd(&p.stats[slot * 8 + ST_EPISODES], (unsigned long long)w_end);
+          atomicAdd(&p.stats[slot * 8 + ST_LEN], (unsigned long long)w_len);
+          atomicAdd(&p.stats[slot * 8 + ST_RETURN_MILLI], (unsigned long long)(long long)llrint(w_ret * (1000.0 / unit)));
+        }
+        if (w_cr) atomicAdd(&p.stats[slot * 8 + ST_CRASH], (unsigned long long)w_cr);
+        if (w_ap) atomicAdd(&p.stats[slot * 8 + ST_APPLES], (unsigned long long)w_ap);
+        if (w_nz) atomicAdd(&p.stats[slot * 8 + ST_FEAR_NZ], (unsigned long long)w_nz);
+      }
+      if (nz) atomicAdd(reinterpret_cast<double*>(&p.stats[slot * 8 + ST_FEAR_BITS]), fear[0] + fear[1]);
+    }
   }
-  write_masks(p.io.action_mask, e, s_rows, p.H, nl, cells_out, lane);
-  if (lane == 0) p.state[e] = make_uint4(cells_out, meta_out, tick_out, ret_out);
+
+  // ================================================================= P4
+  __syncthreads();
+  render_tile<THREADS, TILE, OBS>(s, p, tile_base, tile_envs);
 }
 
 // ------------------------------------------------------------------ operator-level kernels
-__global__ void __launch_bounds__(128) gw_update_world_kernel(const Tables* T, int H, int n_default, long long C,
+struct OpSmem {
+  alignas(16) uint8_t lut[(LUT_BYTES + 15) / 16 * 16];
+  alignas(16) uint8_t next[GW_MAX_H * GW_W * 4];
+};
+
+__device__ __forceinline__ void load_op_tables(OpSmem& s, const Tables* __restrict__ T) {
+  const uint4* src = reinterpret_cast<const uint4*>(T->pair_lut);
+  uint4* dst = reinterpret_cast<uint4*>(s.lut);
+  for (int i = threadIdx.x; i < (LUT_BYTES + 15) / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+  const uint4* nsrc = reinterpret_cast<const uint4*>(T->next_cell);
+  uint4* ndst = reinterpret_cast<uint4*>(s.next);
+  for (int i = threadIdx.x; i < GW_MAX_H * GW_W * 4 / 16; i += blockDim.x) ndst[i] = __ldg(nsrc + i);
+  __syncthreads();
+}
+
+__device__ __forceinline__ void load_case(long long c, int n, const int8_t* pos, const int8_t* act, uint32_t& cells,
+                                          uint32_t& acts) {
+  cells = acts = 0;
+  for (int i = 0; i < n; ++i) {
+    cells |= (uint32_t)(((pos[(c * 4 + i) * 2] & 15) << 4) | (pos[(c * 4 + i) * 2 + 1] & 15)) << (8 * i);
+    acts |= (uint32_t)min(max((int)act[c * 4 + i], 0), 8) << (4 * i);
+  }
+}
+
+__global__ void __launch_bounds__(128) gw_update_world_kernel(const Tables* T, int n_default, long long C,
                                                               const int8_t* n_per, const int8_t* pos, const int8_t* act,
                                                               const int8_t* apples, int8_t* new_pos, uint8_t* crash,
                                                               uint8_t* restr, int8_t* caught) {
-  __shared__ uint16_t s_rows[GW_MAX_H];
-  if (threadIdx.x < GW_MAX_H) s_rows[threadIdx.x] = T->map_rows[threadIdx.x];
-  __syncthreads();
+  __shared__ OpSmem s;
+  load_op_tables(s, T);
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const int n = n_per ? n_per[c] : n_default;
-  uint32_t cells = 0, acts = 0, apple_cells = 0, apple_on = 0;
-  for (int i = 0; i < n; ++i) {
-    cells |= (uint32_t)(((pos[(c * 4 + i) * 2] & 15) << 4) | (pos[(c * 4 + i) * 2 + 1] & 15)) << (8 * i);
-    acts |= ((uint32_t)act[c * 4 + i] & 0xFu) << (4 * i);
-  }
+  uint32_t cells, acts, apple_cells = 0, apple_on = 0;
+  load_case(c, n, pos, act, cells, acts);
   if (apples)
     for (int k = 0; k < 2; ++k)
       if (apples[(c * 2 + k) * 2] >= 0) {
         apple_on |= 1u << k;
         apple_cells |= (uint32_t)(((apples[(c * 2 + k) * 2] & 15) << 4) | (apples[(c * 2 + k) * 2 + 1] & 15)) << (8 * k);
       }
-  const SimResult r = simulate<true>(s_rows, H, n, cells, acts, apple_cells, apple_on, min(2, n));
+  const PairGeom g = pair_geometry(n, cells);
+  const StepResult r = world_update(s.lut, s.next, n, cells, acts, g, apple_cells, apple_on, min(2, n));
   for (int i = 0; i < 4; ++i) {
     const uint32_t cc = (r.cells >> (8 * i)) & 0xFFu;
     new_pos[(c * 4 + i) * 2] = i < n ? (int8_t)(cc >> 4) : (int8_t)-1;
@@ -407,32 +687,51 @@ __global__ void __launch_bounds__(128) gw_update_world_kernel(const Tables* T, i
     for (int f = 0; f < 4; ++f) caught[c * 4 + f] = (int8_t)((r.caught >> (3 * f)) & 7u);
 }
 
-__global__ void __launch_bounds__(128) gw_fear_kernel(const Tables* T, int H, int n_default, long long C,
-                                                      const int8_t* n_per, const int8_t* pos, const int8_t* act,
-                                                      const int8_t* mdr, const int8_t* actor, const uint8_t* in_list,
-                                                      double* resp, int8_t* n_mdr, int8_t* n_act) {
-  __shared__ uint16_t s_rows[GW_MAX_H];
-  if (threadIdx.x < GW_MAX_H) s_rows[threadIdx.x] = T->map_rows[threadIdx.x];
-  __syncthreads();
+// one warp per case: lanes 0..26 = (affected slot, affected action), two rounds (actor plays MdR / its action)
+__global__ void __launch_bounds__(128) gw_fear_kernel(const Tables* T, int n_default, long long C, const int8_t* n_per,
+                                                      const int8_t* pos, const int8_t* act, const int8_t* mdr,
+                                                      const int8_t* actor, const uint8_t* in_list, double* resp,
+                                                      int8_t* n_mdr, int8_t* n_act) {
+  __shared__ OpSmem s;
+  load_op_tables(s, T);
   const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (c >= C) return;
   const int n = n_per ? n_per[c] : n_default;
   const int x = actor[c];
-  uint32_t cells = 0, acts = 0, lst = 1u << x;
-  for (int i = 0; i < n; ++i) {
-    cells |= (uint32_t)(((pos[(c * 4 + i) * 2] & 15) << 4) | (pos[(c * 4 + i) * 2 + 1] & 15)) << (8 * i);
-    acts |= ((uint32_t)act[c * 4 + i] & 0xFu) << (4 * i);
+  uint32_t cells, acts, lst = 1u << x;
+  load_case(c, n, pos, act, cells, acts);
+  for (int i = 0; i < n; ++i)
     if (in_list == nullptr || in_list[c * 4 + i]) lst |= 1u << i;
+  const PairGeom g = pair_geometry(n, cells);
+  uint32_t base = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if ((lst >> k) & 1u) base |= ((acts >> (4 * k)) & 0xFu) << (4 * k);
+  const int js = lane / 9, ap = lane - js * 9;
+  const int j = js + (js >= x ? 1 : 0);
+  const bool lane_on = lane < 27 && j < n;
+  uint32_t packed = 0;
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    const uint32_t av = v == 0 ? (uint32_t)min(max((int)mdr[c * 4 + x], 0), 8) : ((acts >> (4 * x)) & 0xFu);
+    uint32_t a4 = (base & ~(0xFu << (4 * x))) | (av << (4 * x));
+    bool valid = false;
+    if (lane_on) {
+      if ((lst >> j) & 1u) a4 = (a4 & ~(0xFu << (4 * j))) | ((uint32_t)ap << (4 * j));   // SwapActionIDs4Agents
+      valid = counterfactual_valid(s.lut, s.next, n, cells, a4, g, j);
+    }
+    const uint32_t b = __ballot_sync(0xFFFFFFFFu, valid);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) packed |= (uint32_t)__popc(b & (0x1FFu << (9 * q))) << (16 * v + 4 * q);
   }
-  const uint32_t packed = fear_counts_warp(s_rows, H, n, cells, acts, lst, x, mdr[c * 4 + x], lane);
   if (lane < 4) {
     double rv = 0.0;
     int8_t m = 0, a = 0;
     if (lane < n && lane != x) {
-      const int js = lane - (lane > x ? 1 : 0);
-      m = (int8_t)((packed >> (4 * js)) & 0xF);
-      a = (int8_t)((packed >> (16 + 4 * js)) & 0xF);
+      const int q = lane - (lane > x ? 1 : 0);
+      m = (int8_t)((packed >> (4 * q)) & 0xF);
+      a = (int8_t)((packed >> (16 + 4 * q)) & 0xF);
       rv = T->resp_lut[m][a];
     }
     resp[c * 4 + lane] = rv;
@@ -569,6 +868,55 @@ static void policy_thresholds(const float sw[3], const float dw_in[4], bool pert
   for (int k = last; k < 8; ++k) thr[k] = 0x80000000u;
 }
 
+// next-cell table: one move of grid_world.py:481-518 (off-grid clip or inactive target => stay)
+static void build_next_cell(const gw_config* c, uint8_t* next) {
+  static const int DR[4] = {-1, 1, 0, 0}, DC[4] = {0, 0, -1, 1};     // Up, Down, Left, Right (custom_agent.py:140-150)
+  for (int r = 0; r < GW_MAX_H; ++r)
+    for (int col = 0; col < GW_W; ++col)
+      for (int d = 0; d < 4; ++d) {
+        const int tr = r + DR[d], tc = col + DC[d];
+        const bool ok = tr >= 0 && tr < c->height && tc >= 0 && tc < c->width && ((c->map_rows[tr] >> tc) & 1);
+        next[((r << 4) | col) * 4 + d] = (uint8_t)(ok ? ((tr << 4) | tc) : ((r << 4) | col));
+      }
+}
+
+// pair-mask table: the literal five-rule test (gw::pair_hit) for every relative start offset within Manhattan
+// distance 4 and every pair of effective trajectories, bit s = collision at sub-step s (both agents on course).
+static void build_pair_lut(uint8_t* lut) {
+  static const int DR[4] = {-1, 1, 0, 0}, DC[4] = {0, 0, -1, 1};
+  std::memset(lut, 0, gw::LUT_BYTES);
+  auto traj = [&](int p0, int eff, int& p1, int& p2, int& len) {
+    p1 = p2 = p0;
+    len = 1;
+    if (eff == 0) return;
+    const int d = (eff - 1) & 3, step = DR[d] * 64 + DC[d];            // virtual 64-wide grid: no wrap-around
+    p1 = p0 + step;
+    if (eff <= 4) { p2 = p1; len = 1; }
+    else if (eff <= 8) { p2 = p1 + step; len = 2; }
+    else { p2 = p1; len = 2; }                                         // second move blocked
+  };
+  for (int dr = -4; dr <= 4; ++dr)
+    for (int dc = -4; dc <= 4; ++dc) {
+      if (std::abs(dr) + std::abs(dc) > 4 || (dr == 0 && dc == 0)) continue;
+      const int Pi = 16 * 64 + 16, Pj = Pi + dr * 64 + dc;
+      for (int ei = 0; ei < gw::N_EFF; ++ei)
+        for (int ej = 0; ej < gw::N_EFF; ++ej) {
+          int i1, i2, li, j1, j2, lj;
+          traj(Pi, ei, i1, i2, li);
+          traj(Pj, ej, j1, j2, lj);
+          uint8_t mask = 0;
+          for (int s = 0; s < 4; ++s) {
+            const int qi = (s + 1) * li, fi = qi >> 2, ci = (qi + 3) >> 2;
+            const int qj = (s + 1) * lj, fj = qj >> 2, cj = (qj + 3) >> 2;
+            const int Ai = fi == 0 ? Pi : (fi == 1 ? i1 : i2), Bi = ci == 1 ? i1 : i2;
+            const int Aj = fj == 0 ? Pj : (fj == 1 ? j1 : j2), Bj = cj == 1 ? j1 : j2;
+            if (gw::pair_hit(Ai, Bi, Pi, qi, fi, ci, Aj, Bj, Pj, qj, fj, cj)) mask |= (uint8_t)(1u << s);
+          }
+          lut[((dr + 4) * 9 + (dc + 4)) * (gw::N_EFF * gw::N_EFF) + ei * gw::N_EFF + ej] = mask;
+        }
+    }
+}
+
 int gw_create(const gw_config* cfg, gw_handle** out) {
   if (!cfg || !out) return fail(nullptr, GW_EINVAL, "gw_create: null argument");
   *out = nullptr;
@@ -604,6 +952,8 @@ int gw_create(const gw_config* cfg, gw_handle** out) {
     for (int c = 0; c < cfg->width; ++c)
       if ((cfg->map_rows[r] >> c) & 1) t->active_cell[na++] = (uint8_t)((r << 4) | c);
   t->n_active = na;
+  build_next_cell(cfg, t->next_cell);
+  build_pair_lut(t->pair_lut);
   for (int m = 0; m < 10; ++m)
     for (int a = 0; a < 10; ++a) {
       volatile double v = ((double)m - (double)a) / ((double)m + 0.000001);   // Responsibility.py:194-195, EPS :12
@@ -662,10 +1012,45 @@ static int check_io(gw_handle* h, const gw_io* io, bool step) {
   if (!io) return fail(h, GW_EINVAL, "null gw_io");
   if (step && !io->learner_actions) return fail(h, GW_EINVAL, "gw_step: learner_actions is required");
   if (misaligned(io->obs, 16) || misaligned(io->final_obs, 16)) return fail(h, GW_EINVAL, "obs/final_obs must be 16-byte aligned");
-  if (misaligned(io->reward, 4) || misaligned(io->shaped_reward, 4) || misaligned(io->fear, 8) || misaligned(io->info, 4))
-    return fail(h, GW_EINVAL, "misaligned output pointer");
+  if (misaligned(io->reward, 8) || misaligned(io->shaped_reward, 8) || misaligned(io->fear, 16) || misaligned(io->info, 4) ||
+      misaligned(io->positions, 8) || misaligned(io->terminated, 2) || misaligned(io->truncated, 2))
+    return fail(h, GW_EINVAL, "misaligned output pointer (reward/shaped_reward/positions 8 B, fear 16 B, info 4 B)");
   return GW_OK;
 }
+
+}  // extern "C" (templates below need C++ linkage)
+
+// Tile selection: small batches use 32-env tiles so that every SM gets work (E = 4096 -> 128 CTAs); large batches use
+// 256-env tiles so that the per-CTA table load is amortised.  GW_TILE=32|128|256 overrides (experiments).
+static int pick_tile(long long E) {
+  if (const char* s = std::getenv("GW_TILE")) {
+    const int v = std::atoi(s);
+    if (v == 32 || v == 128 || v == 256) return v;
+  }
+  if (E <= 32LL * 148 * 3) return 32;
+  if (E <= 128LL * 148 * 6) return 128;
+  return 256;
+}
+
+template <int THREADS, int TILE>
+static void launch_step_t(const gw_config& c, const gw::StepParams& p, unsigned blocks, cudaStream_t s) {
+  const bool f32 = c.obs_dtype == GW_OBS_F32;
+  if (c.fear) {
+    if (f32) gw::gw_step_kernel<THREADS, TILE, true, GW_OBS_F32><<<blocks, THREADS, 0, s>>>(p);
+    else gw::gw_step_kernel<THREADS, TILE, true, GW_OBS_BF16><<<blocks, THREADS, 0, s>>>(p);
+  } else {
+    if (f32) gw::gw_step_kernel<THREADS, TILE, false, GW_OBS_F32><<<blocks, THREADS, 0, s>>>(p);
+    else gw::gw_step_kernel<THREADS, TILE, false, GW_OBS_BF16><<<blocks, THREADS, 0, s>>>(p);
+  }
+}
+
+template <int THREADS, int TILE>
+static void launch_reset_t(const gw_config& c, const gw::StepParams& p, unsigned blocks, cudaStream_t s) {
+  if (c.obs_dtype == GW_OBS_F32) gw::gw_reset_kernel<THREADS, TILE, GW_OBS_F32><<<blocks, THREADS, 0, s>>>(p);
+  else gw::gw_reset_kernel<THREADS, TILE, GW_OBS_BF16><<<blocks, THREADS, 0, s>>>(p);
+}
+
+extern "C" {
 
 int gw_reset(gw_handle* h, const uint8_t* reset_mask, const gw_io* io, void* stream) {
   if (!h) return GW_EINVAL;
@@ -674,11 +1059,12 @@ int gw_reset(gw_handle* h, const uint8_t* reset_mask, const gw_io* io, void* str
   GW_CUDA(h, cudaSetDevice(h->cfg.device));
   gw::StepParams p = make_params(h, io);
   p.reset_mask = reset_mask;
-  const int threads = 128;
-  const long long blocks = (h->cfg.num_envs * 32 + threads - 1) / threads;
+  const int tile = pick_tile(h->cfg.num_envs);
+  const unsigned blocks = (unsigned)((h->cfg.num_envs + tile - 1) / tile);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (h->cfg.obs_dtype == GW_OBS_F32) gw::gw_reset_kernel<GW_OBS_F32><<<(unsigned)blocks, threads, 0, s>>>(p);
-  else gw::gw_reset_kernel<GW_OBS_BF16><<<(unsigned)blocks, threads, 0, s>>>(p);
+  if (tile == 32) launch_reset_t<128, 32>(h->cfg, p, blocks, s);
+  else if (tile == 128) launch_reset_t<128, 128>(h->cfg, p, blocks, s);
+  else launch_reset_t<256, 256>(h->cfg, p, blocks, s);
   GW_CUDA(h, cudaGetLastError());
   h->reset_done = true;
   h->launches += 1;
@@ -691,17 +1077,12 @@ int gw_step(gw_handle* h, const gw_io* io, void* stream) {
   if (!h->reset_done) return fail(h, GW_ESTATE, "gw_step: call gw_reset first");
   GW_CUDA(h, cudaSetDevice(h->cfg.device));
   gw::StepParams p = make_params(h, io);
-  const int threads = 128;
-  const long long blocks = (h->cfg.num_envs * 32 + threads - 1) / threads;
+  const int tile = pick_tile(h->cfg.num_envs);
+  const unsigned blocks = (unsigned)((h->cfg.num_envs + tile - 1) / tile);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const bool f32 = h->cfg.obs_dtype == GW_OBS_F32;
-  if (h->cfg.fear) {
-    if (f32) gw::gw_step_kernel<true, GW_OBS_F32><<<(unsigned)blocks, threads, 0, s>>>(p);
-    else gw::gw_step_kernel<true, GW_OBS_BF16><<<(unsigned)blocks, threads, 0, s>>>(p);
-  } else {
-    if (f32) gw::gw_step_kernel<false, GW_OBS_F32><<<(unsigned)blocks, threads, 0, s>>>(p);
-    else gw::gw_step_kernel<false, GW_OBS_BF16><<<(unsigned)blocks, threads, 0, s>>>(p);
-  }
+  if (tile == 32) launch_step_t<128, 32>(h->cfg, p, blocks, s);
+  else if (tile == 128) launch_step_t<128, 128>(h->cfg, p, blocks, s);
+  else launch_step_t<256, 256>(h->cfg, p, blocks, s);
   GW_CUDA(h, cudaGetLastError());
   h->launches += 1;
   h->env_steps += (uint64_t)h->cfg.num_envs;
@@ -796,8 +1177,7 @@ int gw_update_world(gw_handle* h, int64_t n_cases, const int8_t* n_per, const in
   const int threads = 128;
   const long long blocks = (n_cases + threads - 1) / threads;
   gw::gw_update_world_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      h->d_tables, h->cfg.height, h->cfg.n_agents, n_cases, n_per, positions, actions, apples, new_positions, crash,
-      restricted, caught);
+      h->d_tables, h->cfg.n_agents, n_cases, n_per, positions, actions, apples, new_positions, crash, restricted, caught);
   GW_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return GW_OK;
@@ -814,8 +1194,7 @@ int gw_fear_one_actor(gw_handle* h, int64_t n_cases, const int8_t* n_per, const 
   const int threads = 128;
   const long long blocks = (n_cases * 32 + threads - 1) / threads;
   gw::gw_fear_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      h->d_tables, h->cfg.height, h->cfg.n_agents, n_cases, n_per, positions, actions, mdr, actor, in_list, resp, n_mdr,
-      n_act);
+      h->d_tables, h->cfg.n_agents, n_cases, n_per, positions, actions, mdr, actor, in_list, resp, n_mdr, n_act);
   GW_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return GW_OK;

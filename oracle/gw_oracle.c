@@ -399,12 +399,15 @@ static void step_range(gwo_handle* h, const gw_io* io, int64_t lo, int64_t hi, s
       if (i < nl) act[i] = io->learner_actions[e * nl + i];
       else if (io->npc_actions) act[i] = io->npc_actions[e * n + i];
       else {
+        /* RNG spec: NPC number m = i - n_learners uses Philox call m/2 (counter = global env id, tick,
+         * call index; key = seed), words 2(m%2) [perturbation] and 2(m%2)+1 [action draw] */
         const uint64_t gid = (uint64_t)(c->env_id_base + e);
-        uint32_t w[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), s->tick, (uint32_t)i};
+        const int m = i - nl;
+        uint32_t w[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), s->tick, (uint32_t)(m >> 1)};
         philox4x32(w, (uint32_t)c->seed, (uint32_t)(c->seed >> 32));
-        const int pert = w[0] < perturb_thr;
+        const int pert = w[2 * (m & 1)] < perturb_thr;
         const uint32_t* thr = h->thr[c->policy_map[s->loc[i].r * GW_W + s->loc[i].c]][pert];
-        const uint32_t u = w[1] >> 1;
+        const uint32_t u = w[2 * (m & 1) + 1] >> 1;
         int a = 0;
         for (int k = 0; k < 8; ++k) a += (u >= thr[k]);
         act[i] = a;
