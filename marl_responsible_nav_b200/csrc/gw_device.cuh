@@ -290,7 +290,7 @@ __device__ __forceinline__ bool counterfactual_valid(const uint8_t* __restrict__
 }
 
 // np.sum over the Resp matrix (one non-zero row): numpy's 8-lane pairwise reduction adds the row as
-// first + (second + third) for n = 4, first + second for n = 3 (checked in tests/test_c_oracle.py).
+// first + (second + third) for n = 4, first + second for n = 3 (numpy association checked in tests/).
 __device__ __forceinline__ double fear_sum3(int n, double r0, double r1, double r2) {
   return n == 4 ? r0 + (r1 + r2) : (n == 3 ? r0 + r1 : r0);
 }
