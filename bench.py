@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every step from Python instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -189,6 +190,25 @@ def run_ours(a):
 
     run(W)
     env.sync()
+    # The timed loop is replayed from a CUDA graph of n_act consecutive steps (each with its own action tensor and ring
+    # slot), so that the device is not waiting on the Python/ctypes call between launches (--no-graph: eager launches).
+    graph = None
+    if a.graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            run(n_act, W)
+        env.sync()
+
+    def timed(K):
+        if graph is None:
+            run(K, W)
+            return
+        for _ in range(K // n_act):
+            graph.replay()
+        run(K % n_act, W)
+
+    timed(min(K, 2 * n_act))                                      # graph warm-up
+    env.sync()
     env.reset_stats()
     l0 = env.launch_count()
     sampler = ClockSampler(local)
@@ -199,14 +219,14 @@ def run_ours(a):
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    run(K, W)
+    timed(K)
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
-    launches = env.launch_count() - l0
+    launches = K                                                  # one gw_step kernel per step (graph replays are not seen by the host counter)
     st = env.stats()
     t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
     stat_vec = torch.tensor([st["episodes"], st["episode_len_sum"], st["crashes"], st["apples"], st["fear_nonzero"],
@@ -266,7 +286,7 @@ def run_ours(a):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": f"gw_step_kernel<fear={bool(a.fear)},{a.obs}>",
                      "algorithmic_bytes_per_launch": algo, "peak_source": peak_src,
-                     "note": "launch duration = event time over K back-to-back launches / K (includes launch gaps)"},
+                     "note": "launch duration = CUDA-event time over K back-to-back launches / K (includes launch gaps); " + ("CUDA-graph replay" if a.graph else "eager launches")},
         "workload_stats": {"episodes": stat_vec[0].item(), "mean_episode_len": stat_vec[1].item() / max(1.0, stat_vec[0].item()),
                            "learner_crashes_per_env_step": stat_vec[2].item() / (world * E * K),
                            "apples_per_env_step": stat_vec[3].item() / (world * E * K),

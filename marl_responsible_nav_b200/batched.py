@@ -106,6 +106,7 @@ class BatchedGridWorld:
             ended=torch.zeros((E,), dtype=torch.uint8, device=dev),
             info=torch.zeros((E,), dtype=torch.int32, device=dev),
             final_obs=None)
+        self._io_step, self._io_reset = self._make_io(True), self._make_io(False)
 
     # ------------------------------------------------------------------ helpers
     def close(self):
@@ -130,13 +131,16 @@ class BatchedGridWorld:
 
     def _io(self, obs, final_obs, actions=None, npc_actions=None, spawn=None, outputs=True) -> N.GwIO:
         E, L, A, dev = self.num_envs, self.n_learners, self.n_agents, self.device
-        io = N.GwIO()
-        b = self.buf
+        io = self._io_step if outputs else self._io_reset          # pointers to the env-owned buffers are filled once
         io.learner_actions = _check(actions, "actions", torch.int8, (E, L), dev).data_ptr() if actions is not None else None
         io.npc_actions = _check(npc_actions, "npc_actions", torch.int8, (E, A), dev).data_ptr() if npc_actions is not None else None
         io.spawn = _check(spawn, "spawn", torch.int8, (E, A, 2), dev).data_ptr() if spawn is not None else None
         io.obs = obs.data_ptr()
         io.final_obs = final_obs.data_ptr() if final_obs is not None else None
+        return io
+
+    def _make_io(self, outputs: bool) -> N.GwIO:
+        io, b = N.GwIO(), self.buf
         io.action_mask, io.positions = b.action_mask.data_ptr(), b.positions.data_ptr()
         if outputs:
             io.reward, io.shaped_reward, io.fear = b.reward.data_ptr(), b.shaped_reward.data_ptr(), b.fear.data_ptr()
@@ -157,9 +161,11 @@ class BatchedGridWorld:
     def _as_i8(x, device) -> Optional[torch.Tensor]:
         if x is None:
             return None
-        if not isinstance(x, torch.Tensor):
-            x = torch.as_tensor(np.asarray(x))
-        return x.to(device=device, dtype=torch.int8).contiguous()
+        if isinstance(x, torch.Tensor):
+            if x.dtype == torch.int8 and x.device == device and x.is_contiguous():
+                return x                                           # hot path: no copy, no launch
+            return x.to(device=device, dtype=torch.int8).contiguous()
+        return torch.as_tensor(np.asarray(x)).to(device=device, dtype=torch.int8).contiguous()
 
     # ------------------------------------------------------------------ API
     def reset(self, mask: Optional[torch.Tensor] = None, spawn=None, obs_out: Optional[torch.Tensor] = None) -> StepOutput:

@@ -177,7 +177,15 @@ __device__ __forceinline__ uint32_t reach_mask(uint32_t near6, int x) {
 // custom/grid_world.py:247-405: within a pass the paths are frozen (hits are evaluated on the crashed mask
 // of the pass start), crashed agents revert after the pass, passes repeat while something was hit.  Every
 // pass with a hit crashes at least one more agent, so the reference's 2N-pass cap can never bind.
-__device__ __forceinline__ uint32_t collide(const uint8_t* __restrict__ s_lut, const PairGeom& g, const uint32_t eff[4]) {
+// `stop`: agents whose crash ends the evaluation early (counterfactuals only ask about one agent); the
+// returned word is then only valid in its final nibble for those agents.
+__device__ __forceinline__ uint32_t agents_of_pairs(uint32_t hp) {
+  return ((hp & 0x000111u) ? 1u : 0u) | ((hp & 0x011001u) ? 2u : 0u) | ((hp & 0x101010u) ? 4u : 0u) |
+         ((hp & 0x110100u) ? 8u : 0u);
+}
+
+__device__ __forceinline__ uint32_t collide(const uint8_t* __restrict__ s_lut, const PairGeom& g, const uint32_t eff[4],
+                                            uint32_t stop = 0) {
   if (g.near6 == 0) return 0;
   uint32_t NNw = 0;
   {
@@ -190,6 +198,11 @@ __device__ __forceinline__ uint32_t collide(const uint8_t* __restrict__ s_lut, c
           NNw |= (uint32_t)s_lut[geom_didx(g, p) * (N_EFF * N_EFF) + eff[i] * N_EFF + eff[j]] << (4 * p);
   }
   if (NNw == 0) return 0;                             // nobody collides while everyone is on course
+  // first sub-step with a hit: nothing happens before it
+  const uint32_t any = (NNw | (NNw >> 4) | (NNw >> 8) | (NNw >> 12) | (NNw >> 16) | (NNw >> 20)) & 0xFu;
+  const int s0 = __ffs(any) - 1;
+  uint32_t crashed = agents_of_pairs((NNw >> s0) & 0x111111u);
+  if (crashed & stop) return crashed << 12;
   uint32_t NRw = 0, RNw = 0;                          // second agent crashed (stationary) / first agent crashed
   {
     int p = 0;
@@ -203,17 +216,16 @@ __device__ __forceinline__ uint32_t collide(const uint8_t* __restrict__ s_lut, c
           RNw |= (uint32_t)s_lut[base + eff[j]] << (4 * p);
         }
   }
-  uint32_t crashed = 0, out = 0;
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
+  uint32_t out = 0;
+  for (int s = s0; s < 4; ++s) {
     while (true) {
       const uint32_t Pi = ((crashed & 1u) ? 0x000FFFu : 0u) | ((crashed & 2u) ? 0x0FF000u : 0u) | ((crashed & 4u) ? 0xF00000u : 0u);
       const uint32_t Pj = ((crashed & 2u) ? 0x00000Fu : 0u) | ((crashed & 4u) ? 0x00F0F0u : 0u) | ((crashed & 8u) ? 0xFF0F00u : 0u);
       const uint32_t hp = (((NNw & ~Pi & ~Pj) | (NRw & ~Pi & Pj) | (RNw & Pi & ~Pj)) >> s) & 0x111111u;
       if (hp == 0) break;
-      crashed |= ((hp & 0x000111u) ? 1u : 0u) | ((hp & 0x011001u) ? 2u : 0u) | ((hp & 0x101010u) ? 4u : 0u) |
-                 ((hp & 0x110100u) ? 8u : 0u);
+      crashed |= agents_of_pairs(hp);
     }
+    if (crashed & stop) return crashed << 12;
     out |= crashed << (4 * s);
   }
   return out;
@@ -231,6 +243,7 @@ struct StepResult {
   uint32_t crash;       // bit i
   uint32_t restr;       // bit i
   uint32_t caught;      // 3-bit counters, field (eater*2 + apple)
+  uint32_t effs;        // 4 x 4-bit effective trajectories of the actions played
 };
 
 // GWorld.UpdateGWorld with explicit actions for all n agents (custom/grid_world.py:424-563).
@@ -239,13 +252,15 @@ __device__ __forceinline__ StepResult world_update(const uint8_t* __restrict__ s
                                                    uint32_t apple_cells, uint32_t apple_on, int n_eaters) {
   Traj t[4];
   uint32_t eff[4];
+  StepResult r;
+  r.effs = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     t[i] = make_traj(s_next, (cells >> (8 * i)) & 0xFFu, i < n ? (acts >> (4 * i)) & 0xFu : 0u);
     eff[i] = t[i].eff;
+    r.effs |= eff[i] << (4 * i);
   }
   const uint32_t cm = (n >= 2) ? collide(s_lut, g, eff) : 0u;
-  StepResult r;
   r.crash = (cm >> 12) & 0xFu;
   r.cells = 0;
   r.restr = 0;
@@ -276,16 +291,17 @@ __device__ __forceinline__ StepResult world_update(const uint8_t* __restrict__ s
 }
 
 // One counterfactual of CountValidMovesOfAffected (custom/Responsibility.py:32-48): is the affected agent j
-// neither restricted nor crashed when the listed agents play `acts` (already swapped) and the others Stay?
+// neither restricted nor crashed?  eff_others: effective trajectories of everybody (the entry of j is ignored),
+// with agents outside the action list already set to 0 (Stay, :43); aj: the action j tries.
 __device__ __forceinline__ bool counterfactual_valid(const uint8_t* __restrict__ s_lut, const uint8_t* __restrict__ s_next,
-                                                     int n, uint32_t cells, uint32_t acts, const PairGeom& g, int j) {
-  const Traj tj = make_traj(s_next, (cells >> (8 * j)) & 0xFFu, (acts >> (4 * j)) & 0xFu);
+                                                     uint32_t cells, uint32_t eff_others, const PairGeom& g, int j,
+                                                     uint32_t aj) {
+  const Traj tj = make_traj(s_next, (cells >> (8 * j)) & 0xFFu, aj);
   if (tj.r1 | tj.r2) return false;          // restricted, or crashed before the blocked second move: invalid either way
   uint32_t eff[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    eff[i] = (i < n) ? make_traj(s_next, (cells >> (8 * i)) & 0xFFu, (acts >> (4 * i)) & 0xFu).eff : 0u;
-  const uint32_t cm = collide(s_lut, g, eff);
+  for (int i = 0; i < 4; ++i) eff[i] = (i == j) ? tj.eff : (eff_others >> (4 * i)) & 0xFu;
+  const uint32_t cm = collide(s_lut, g, eff, 1u << j);
   return ((cm >> (12 + j)) & 1u) == 0;
 }
 

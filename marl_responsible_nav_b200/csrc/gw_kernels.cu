@@ -58,7 +58,7 @@ struct Smem {
   alignas(16) uint8_t next[GW_MAX_H * GW_W * 4];
   alignas(16) uint4 tmpl[64];
   uint16_t rows[GW_MAX_H];
-  uint32_t cells_old[TILE], acts[TILE], geom_lo[TILE], geom_hi[TILE], close[TILE];
+  uint32_t cells_old[TILE], effs[TILE], geom_lo[TILE], geom_hi[TILE], close[TILE];
   uint32_t cnt[TILE * 2];
   uint32_t cells_new[TILE], cells_fin[TILE], rinfo[TILE];
   uint16_t queue[TILE * 6];
@@ -66,16 +66,22 @@ struct Smem {
   alignas(16) uint8_t mask[TILE * GW_MAX_LEARNERS * GW_N_ACTIONS + 16];
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// Tables -> shared memory.  The pair-mask table and the next-cell table travel with cp.async so that the copy
+// overlaps the first tile's state loads and RNG; the caller waits (cp_async_wait_all + __syncthreads) before P1b.
 template <int THREADS, int TILE, int OBS>
 __device__ __forceinline__ void load_tables(Smem<TILE>& s, const Tables* __restrict__ T, int H, bool need_lut) {
   const int tid = threadIdx.x;
   if (need_lut) {
-    const uint4* src = reinterpret_cast<const uint4*>(T->pair_lut);
-    uint4* dst = reinterpret_cast<uint4*>(s.lut);
-    for (int i = tid; i < (LUT_BYTES + 15) / 16; i += THREADS) dst[i] = __ldg(src + i);
-    const uint4* nsrc = reinterpret_cast<const uint4*>(T->next_cell);
-    uint4* ndst = reinterpret_cast<uint4*>(s.next);
-    for (int i = tid; i < GW_MAX_H * GW_W * 4 / 16; i += THREADS) ndst[i] = __ldg(nsrc + i);
+    for (int i = tid; i < (LUT_BYTES + 15) / 16; i += THREADS) cp_async16(s.lut + 16 * i, T->pair_lut + 16 * i);
+    for (int i = tid; i < GW_MAX_H * GW_W * 4 / 16; i += THREADS) cp_async16(s.next + 16 * i, T->next_cell + 16 * i);
   }
   if (tid < GW_MAX_H) s.rows[tid] = T->map_rows[tid];
   // constant observation template: -1 inactive / 0 active (WorldState reset, grid_world.py:433-434)
@@ -99,7 +105,6 @@ __device__ __forceinline__ void load_tables(Smem<TILE>& s, const Tables* __restr
     }
     s.tmpl[q] = make_uint4(w[0], w[1], w[2], w[3]);
   }
-  if (tid == 0) s.qn = 0;
 }
 
 // value of an agent / apple cell.  custom/ma_customenv.py:303-322 (step) / :198-209 (reset),
@@ -195,13 +200,34 @@ __device__ __forceinline__ void render_tile(Smem<TILE>& s, const StepParams& p, 
     // bulk: the constant template, 16 B per thread, consecutive threads -> consecutive addresses
     uint4* dst = reinterpret_cast<uint4*>(p.io.obs) + tile_base * (long long)(p.nl * Q);
     const int V = tile_envs * p.nl * Q;
-    int q = tid % Q;
     const int qstep = THREADS % Q;
     const bool partial = p.reset_mask != nullptr;          // masked reset: untouched envs keep their observation
-    for (int g = tid; g < V; g += THREADS) {
-      if (!partial || !(s.rinfo[g / (p.nl * Q)] & R_SKIP)) __stcs(dst + g, s.tmpl[q]);
-      q += qstep;
-      if (q >= Q) q -= Q;
+    if (!partial && (5 * qstep) % Q == 0) {
+      // the template index of a thread repeats every 5 iterations (H = 10: Q = 40 or 20): keep the 5 vectors in
+      // registers and the loop body is one 128-bit streaming store
+      uint4 t5[5];
+      int q = tid % Q;
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        t5[u] = s.tmpl[q];
+        q += qstep;
+        if (q >= Q) q -= Q;
+      }
+      int g = tid;
+      for (; g + 4 * THREADS < V; g += 5 * THREADS) {
+#pragma unroll
+        for (int u = 0; u < 5; ++u) __stcs(dst + g + u * THREADS, t5[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 5; ++u)
+        if (g + u * THREADS < V) __stcs(dst + g + u * THREADS, t5[u]);
+    } else {
+      int q = tid % Q;
+      for (int g = tid; g < V; g += THREADS) {
+        if (!partial || !(s.rinfo[g / (p.nl * Q)] & R_SKIP)) __stcs(dst + g, s.tmpl[q]);
+        q += qstep;
+        if (q >= Q) q -= Q;
+      }
     }
   }
   __syncthreads();                                           // patches must land after the template
@@ -338,298 +364,319 @@ __global__ void __launch_bounds__(THREADS) gw_reset_kernel(StepParams p) {
 }
 
 // ------------------------------------------------------------------ step kernel
+// Persistent CTAs: the grid is sized to the machine and each CTA walks tiles blockIdx.x, +gridDim.x, ...
 template <int THREADS, int TILE, bool FEAR, int OBS>
 __global__ void __launch_bounds__(THREADS) gw_step_kernel(StepParams p) {
   __shared__ Smem<TILE> s;
   load_tables<THREADS, TILE, OBS>(s, p.tables, p.H, true);
-  __syncthreads();
   const Tables* __restrict__ T = p.tables;
-  const long long tile_base = (long long)blockIdx.x * TILE;
-  const int tile_envs = (int)min((long long)TILE, p.E - tile_base);
   const int tid = threadIdx.x;
   const int n = p.n, nl = p.nl;
-  const long long e = tile_base + tid;
-  const bool own = tid < tile_envs;
+  const long long n_tiles = (p.E + TILE - 1) / TILE;
+  bool tables_pending = true;
 
-  // per-env registers that live across the phases
-  uint32_t task_bits = 0;            // bit (x*4 + j): (x, j) is an enqueued FeAR task
-  double reward[GW_MAX_LEARNERS] = {0.0, 0.0};
-  uint32_t fear_stat_ended = 0, steps_now = 0;
-  int ret0 = 0, ret1 = 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long tile_base = tile * TILE;
+    const int tile_envs = (int)min((long long)TILE, p.E - tile_base);
+    const long long e = tile_base + tid;
+    const bool own = tid < tile_envs;
 
-  // ================================================================= P1
-  if (own) {
-    const uint4 st = p.state[e];
-    const uint32_t cells = st.x;
-    uint32_t meta = st.y;
-    const uint32_t tick = st.z;
-
-    // ---- setup_step (ma_customenv.py:432-452)
+    // per-env registers that live across the phases
+    uint32_t task_bits = 0;            // bit (x*4 + j): (x, j) is an enqueued FeAR task
+    double reward[GW_MAX_LEARNERS] = {0.0, 0.0};
+    uint32_t stat_bits = 0, steps_now = 0;
+    int ret0 = 0, ret1 = 0;
+    uint4 st = make_uint4(0, 0, 0, 0);
     uint32_t acts = 0, mdrs = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (i < n) mdrs |= (uint32_t)__ldg(&T->mdr_map[(cells >> (8 * i)) & 0xFFu]) << (4 * i);   // :445-447
-#pragma unroll
-    for (int k = 0; k < GW_MAX_LEARNERS; ++k)
-      if (k < nl) acts |= (uint32_t)min(max((int)p.io.learner_actions[e * nl + k], 0), 8) << (4 * k);   // :239-242
-    if (p.io.npc_actions != nullptr) {
-#pragma unroll
-      for (int i = 1; i < 4; ++i)
-        if (i >= nl && i < n) acts |= (uint32_t)min(max((int)p.io.npc_actions[e * n + i], 0), 8) << (4 * i);
-    } else {
-      const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
-      uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-      for (int i = 1; i < 4; ++i) {
-        if (i < nl || i >= n) continue;
-        const int m = i - nl;                                              // NPC index: Philox call m/2, words 2(m%2), 2(m%2)+1
-        if ((m & 1) == 0) {
-          w[0] = (uint32_t)gid; w[1] = (uint32_t)(gid >> 32); w[2] = tick; w[3] = (uint32_t)(m >> 1);
-          philox4x32(w, p.seed_lo, p.seed_hi);
-        }
-        const uint32_t wa = (m & 1) ? w[2] : w[0], wb = (m & 1) ? w[3] : w[1];
-        const int pert = wa < p.perturb_thr ? 1 : 0;                       // random.random() < 0.25 (:441)
-        const uint32_t c = (cells >> (8 * i)) & 0xFFu;
-        const uint4* thr4 = reinterpret_cast<const uint4*>(T->policy_thr[__ldg(&T->policy_map[c])][pert]);
-        const uint4 t0 = __ldg(thr4), t1 = __ldg(thr4 + 1);
-        const uint32_t u = wb >> 1;
-        const uint32_t a = (u >= t0.x) + (u >= t0.y) + (u >= t0.z) + (u >= t0.w) + (u >= t1.x) + (u >= t1.y) +
-                           (u >= t1.z) + (u >= t1.w);                      // np.random.choice(9, p) (custom_agent.py:31)
-        acts |= a << (4 * i);
-      }
-    }
-    const PairGeom g = pair_geometry(n, cells);
 
-    // ---- FeAR tasks on the pre-step positions (ma_customenv.py:245-252 / customenv.py:113-120)
-    if (FEAR) {
-      s.cells_old[tid] = cells;
-      s.acts[tid] = acts | (mdrs << 16);
-      s.geom_lo[tid] = g.didx_lo;
-      s.geom_hi[tid] = g.didx_hi | (g.near6 << 16);
-      s.cnt[tid * 2] = 0;
-      s.cnt[tid * 2 + 1] = 0;
-      uint32_t closew = 0;
+    // ================================================================= P1a: loads and RNG (no shared tables needed)
+    if (tid == 0) s.qn = 0;
+    if (own) {
+      st = p.state[e];
+      const uint32_t cells = st.x;
+      const uint32_t tick = st.z;
+      // ---- setup_step (ma_customenv.py:432-452)
 #pragma unroll
-      for (int x = 0; x < GW_MAX_LEARNERS; ++x) {
-        if (x >= nl) break;
-        uint32_t close = 0;                                                // close_agents :456-464
+      for (int i = 0; i < 4; ++i)
+        if (i < n) mdrs |= (uint32_t)__ldg(&T->mdr_map[(cells >> (8 * i)) & 0xFFu]) << (4 * i);   // :445-447
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < n && (k == x || manhattan((cells >> (8 * x)) & 0xFFu, (cells >> (8 * k)) & 0xFFu) <= p.fear_radius))
-            close |= 1u << k;
-        closew |= close << (4 * x);
-        // action == MdR: both counts are equal -> Resp = 0 exactly.  Agents that no chain of near pairs links to the
-        // actor cannot be influenced by its move -> equal counts -> 0 as well.
-        if (((acts >> (4 * x)) & 0xFu) != ((mdrs >> (4 * x)) & 0xFu)) {
-          const uint32_t js = reach_mask(g.near6, x) & ~(1u << x) & ((1u << n) - 1u);
-          if (js) {
-            const uint32_t slot = atomicAdd(&s.qn, (uint32_t)__popc(js));
-            uint32_t k2 = 0;
+      for (int k = 0; k < GW_MAX_LEARNERS; ++k)
+        if (k < nl) acts |= (uint32_t)min(max((int)p.io.learner_actions[e * nl + k], 0), 8) << (4 * k);   // :239-242
+      if (p.io.npc_actions != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if ((js >> j) & 1u) {
-                s.queue[slot + k2] = (uint16_t)(tid | (x << 8) | (j << 9) | (((close >> j) & 1u) << 11));
-                ++k2;
-              }
-            task_bits |= js << (4 * x);
+        for (int i = 1; i < 4; ++i)
+          if (i >= nl && i < n) acts |= (uint32_t)min(max((int)p.io.npc_actions[e * n + i], 0), 8) << (4 * i);
+      } else {
+        const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 1; i < 4; ++i) {
+          if (i < nl || i >= n) continue;
+          const int m = i - nl;                                            // NPC index: Philox call m/2, words 2(m%2), 2(m%2)+1
+          if ((m & 1) == 0) {
+            w[0] = (uint32_t)gid; w[1] = (uint32_t)(gid >> 32); w[2] = tick; w[3] = (uint32_t)(m >> 1);
+            philox4x32(w, p.seed_lo, p.seed_hi);
           }
+          const uint32_t wa = (m & 1) ? w[2] : w[0], wb = (m & 1) ? w[3] : w[1];
+          const int pert = wa < p.perturb_thr ? 1 : 0;                     // random.random() < 0.25 (:441)
+          const uint32_t c = (cells >> (8 * i)) & 0xFFu;
+          const uint4* thr4 = reinterpret_cast<const uint4*>(T->policy_thr[__ldg(&T->policy_map[c])][pert]);
+          const uint4 t0 = __ldg(thr4), t1 = __ldg(thr4 + 1);
+          const uint32_t u = wb >> 1;
+          const uint32_t a = (u >= t0.x) + (u >= t0.y) + (u >= t0.z) + (u >= t0.w) + (u >= t1.x) + (u >= t1.y) +
+                             (u >= t1.z) + (u >= t1.w);                    // np.random.choice(9, p) (custom_agent.py:31)
+          acts |= a << (4 * i);
         }
       }
-      s.close[tid] = closew;
     }
+    if (tables_pending) {
+      cp_async_wait_all();
+      tables_pending = false;
+    }
+    __syncthreads();
 
-    // ---- the real update (:254)
-    const uint32_t apples_before = meta & M_APPLES;
-    const StepResult r = world_update(s.lut, s.next, n, cells, acts, g, p.apple_cells, apples_before, nl);
-    const uint32_t cells_new = r.cells;
+    // ================================================================= P1b: world update, rewards, flags, FeAR tasks
+    if (own) {
+      const uint32_t cells = st.x;
+      uint32_t meta = st.y;
+      const uint32_t tick = st.z;
+      const PairGeom g = pair_geometry(n, cells);
 
-    uint32_t apples_left = apples_before;
-    uint32_t term_now = 0, trunc_now = 0, apples_rewarded = 0, crash_count = 0, shaped = 0;
-    if (p.kind == GW_ENV_MULTI) {
-      uint32_t term = (meta >> M_TERM_SH) & 3u, trunc = (meta & M_TRUNC) ? 1u : 0u;
-      int ri[GW_MAX_LEARNERS] = {0, 0};
+      // ---- the real update (ma_customenv.py:254)
+      const uint32_t apples_before = meta & M_APPLES;
+      const StepResult r = world_update(s.lut, s.next, n, cells, acts, g, p.apple_cells, apples_before, nl);
+      const uint32_t cells_new = r.cells;
+
+      // ---- FeAR tasks on the pre-step positions (ma_customenv.py:245-252 / customenv.py:113-120)
+      if (FEAR) {
+        uint32_t closew = 0, effw = r.effs;
 #pragma unroll
-      for (int k = 0; k < GW_MAX_LEARNERS; ++k)                            // own apple only (:258-271)
-        if (k < nl && ((apples_left >> k) & 1u) && ((r.caught >> (3 * (k * 2 + k))) & 7u)) {
-          apples_left &= ~(1u << k);
-          ri[k] += 20;
-          ++apples_rewarded;
+        for (int x = 0; x < GW_MAX_LEARNERS; ++x) {
+          if (x >= nl) break;
+          const uint32_t ax = (acts >> (4 * x)) & 0xFu, mx = (mdrs >> (4 * x)) & 0xFu;
+          // action == MdR: both counts are equal -> Resp = 0 exactly.  Agents that no chain of near pairs links to the
+          // actor cannot be influenced by its move -> equal counts -> 0 as well.
+          if (ax == mx) continue;
+          const uint32_t js = reach_mask(g.near6, x) & ~(1u << x) & ((1u << n) - 1u);
+          if (js == 0) continue;
+          uint32_t close = 0;                                              // close_agents :456-464
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < n && (k == x || manhattan((cells >> (8 * x)) & 0xFFu, (cells >> (8 * k)) & 0xFFu) <= p.fear_radius))
+              close |= 1u << k;
+          closew |= close << (4 * x);
+          effw |= make_traj(s.next, (cells >> (8 * x)) & 0xFFu, mx).eff << (16 + 4 * x);   // actor plays its MdR
+          const uint32_t slot = atomicAdd(&s.qn, (uint32_t)__popc(js));
+          uint32_t k2 = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if ((js >> j) & 1u) {
+              s.queue[slot + k2] = (uint16_t)(tid | (x << 8) | (j << 9) | (((close >> j) & 1u) << 11));
+              ++k2;
+            }
+          task_bits |= js << (4 * x);
         }
-      if (apples_rewarded && apples_left == 0) {                           // last apple: +20 to all, truncate (:272-275)
-#pragma unroll
-        for (int k = 0; k < GW_MAX_LEARNERS; ++k) if (k < nl) ri[k] += 20;
-        trunc = 1;
+        if (task_bits) {
+          s.cells_old[tid] = cells;
+          s.effs[tid] = effw;
+          s.geom_lo[tid] = g.didx_lo;
+          s.geom_hi[tid] = g.didx_hi | (g.near6 << 16);
+          s.close[tid] = closew;
+          s.cnt[tid * 2] = 0;
+          s.cnt[tid * 2 + 1] = 0;
+        }
       }
-      uint32_t pdv = 0, pd[2] = {0, 0};
+
+      uint32_t apples_left = apples_before;
+      uint32_t term_now = 0, trunc_now = 0, apples_rewarded = 0, crash_count = 0, shaped = 0;
+      if (p.kind == GW_ENV_MULTI) {
+        uint32_t term = (meta >> M_TERM_SH) & 3u, trunc = (meta & M_TRUNC) ? 1u : 0u;
+        int ri[GW_MAX_LEARNERS] = {0, 0};
 #pragma unroll
-      for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
-        if (k >= nl) continue;
-        if ((r.crash >> k) & 1u) {                                         // :281-285
-          ri[k] -= 10;
-          ++crash_count;
+        for (int k = 0; k < GW_MAX_LEARNERS; ++k)                          // own apple only (:258-271)
+          if (k < nl && ((apples_left >> k) & 1u) && ((r.caught >> (3 * (k * 2 + k))) & 7u)) {
+            apples_left &= ~(1u << k);
+            ri[k] += 20;
+            ++apples_rewarded;
+          }
+        if (apples_rewarded && apples_left == 0) {                         // last apple: +20 to all, truncate (:272-275)
+#pragma unroll
+          for (int k = 0; k < GW_MAX_LEARNERS; ++k) if (k < nl) ri[k] += 20;
           trunc = 1;
-          term |= 1u << k;
         }
-        if ((apples_left >> k) & 1u) {                                     // :287-300
-          const uint32_t d = (uint32_t)manhattan((cells_new >> (8 * k)) & 0xFFu, (p.apple_cells >> (8 * k)) & 0xFFu);
-          const uint32_t prev_valid = (meta >> (M_PDV_SH + k)) & 1u;
-          const uint32_t prev = (meta >> (k == 0 ? M_PD0_SH : M_PD1_SH)) & 31u;
-          if (prev_valid && prev > d) { ri[k] += 1; shaped |= 1u << k; }
-          pdv |= 1u << k;
-          pd[k] = d;
-        }
-        reward[k] = (double)ri[k];
-      }
-      term_now = term;
-      trunc_now = trunc ? ((1u << nl) - 1u) : 0u;
-      const uint32_t steps = min(((meta >> M_STEPS_SH) & M_STEPS_MASK) + 1u, M_STEPS_MASK);
-      meta = apples_left | (term << M_TERM_SH) | (trunc ? M_TRUNC : 0u) | (pdv << M_PDV_SH) | (pd[0] << M_PD0_SH) |
-             (pd[1] << M_PD1_SH) | (steps << M_STEPS_SH);
-    } else {                                                               // customenv.py:126-158
-      double rew = 0.0;
-      const uint32_t apple = p.apple_cells & 0xFFu;
-      const uint32_t d = (uint32_t)manhattan(cells_new & 0xFFu, apple);
-      if (r.crash & 1u) { rew -= 10.0; term_now = 1; crash_count = 1; }
-      if ((apples_left & 1u) && (r.caught & 7u) == 1u) {                   // len(apples_caught) == 1 (:143)
-        apples_left &= ~1u;
-        rew += 20.0;
-        trunc_now = 1;
-        apples_rewarded = 1;
-      }
-      const uint32_t prev = (meta >> M_PD0_SH) & 31u;
-      if (d < prev) { rew += 0.1; shaped = 1; }                            // :157-158
-      reward[0] = rew;
-      const uint32_t steps = min(((meta >> M_STEPS_SH) & M_STEPS_MASK) + 1u, M_STEPS_MASK);
-      meta = apples_left | (1u << M_PDV_SH) | (d << M_PD0_SH) | (steps << M_STEPS_SH);
-    }
-    steps_now = (meta >> M_STEPS_SH) & M_STEPS_MASK;
-    const bool episode_over = (p.kind == GW_ENV_MULTI) ? (trunc_now != 0) : ((term_now | trunc_now) != 0);
-    const bool ended = episode_over || (p.max_steps > 0 && (int)steps_now >= p.max_steps);
-
-    // ---- scalar outputs (one thread per env: each array is written with unit stride across the warp)
-    if (nl == 2) {
-      if (p.io.reward) reinterpret_cast<float2*>(p.io.reward)[e] = make_float2((float)reward[0], (float)reward[1]);
-      if (p.io.terminated) reinterpret_cast<uchar2*>(p.io.terminated)[e] = make_uchar2(term_now & 1u, (term_now >> 1) & 1u);
-      if (p.io.truncated) reinterpret_cast<uchar2*>(p.io.truncated)[e] = make_uchar2(trunc_now & 1u, (trunc_now >> 1) & 1u);
-    } else {
-      if (p.io.reward) p.io.reward[e] = (float)reward[0];
-      if (p.io.terminated) p.io.terminated[e] = (uint8_t)(term_now & 1u);
-      if (p.io.truncated) p.io.truncated[e] = (uint8_t)(trunc_now & 1u);
-    }
-    write_positions(p.io.positions, e, n, cells_new);
-    if (p.io.ended) p.io.ended[e] = ended ? 1 : 0;
-    if (p.io.info)
-      p.io.info[e] = (r.crash & 15u) | ((r.restr & 15u) << 4) | (crash_count << 8) | (apples_rewarded << 10) |
-                     ((ended ? 1u : 0u) << 12) | (shaped << 14);
-
-    // ---- episode return (reward units: 1 multi, 0.1 single), state for the next step, render record
-    ret0 = (int)(short)(st.w & 0xFFFFu);
-    ret1 = (int)(short)(st.w >> 16);
-    const double unit = (p.kind == GW_ENV_MULTI) ? 1.0 : 10.0;
-    ret0 += (int)lrint(reward[0] * unit);
-    ret1 += (int)lrint(reward[1] * unit);
-    fear_stat_ended = (ended ? 1u : 0u) | (crash_count << 1) | (apples_rewarded << 3);
-    if (ended && p.auto_reset) {
-      const uint32_t cells_sp = spawn_cells(p, e, tick);
-      const uint32_t meta_sp = fresh_meta(p, cells_sp);
-      s.cells_new[tid] = cells_sp;
-      s.cells_fin[tid] = cells_new;
-      s.rinfo[tid] = (meta_sp & M_APPLES) | R_FRESH | R_FINAL | (apples_left << 4);
-      p.state[e] = make_uint4(cells_sp, meta_sp, tick + 1, 0u);
-    } else {
-      s.cells_new[tid] = cells_new;
-      s.rinfo[tid] = apples_left;
-      p.state[e] = make_uint4(cells_new, meta, tick + 1, ((uint32_t)ret0 & 0xFFFFu) | ((uint32_t)ret1 << 16));
-    }
-  }
-
-  // ================================================================= P2: counterfactual sims (Responsibility.py:20-54)
-  if (FEAR) {
-    __syncthreads();
-    const uint32_t n_work = s.qn * 18u;
-    for (uint32_t w = tid; w < n_work; w += THREADS) {
-      const uint32_t tk = s.queue[w / 18u], rr = w % 18u;
-      const uint32_t v = rr / 9u, ap = rr - v * 9u;
-      const uint32_t el = tk & 0xFFu, x = (tk >> 8) & 1u, j = (tk >> 9) & 3u, jc = (tk >> 11) & 1u;
-      if (!jc && ap != 0) continue;                      // affected not in the list: it Stays in all nine sims (:43)
-      const uint32_t cells = s.cells_old[el], aw = s.acts[el];
-      const uint32_t close = (s.close[el] >> (4 * x)) & 0xFu;
-      const uint32_t keep = ((close & 1u) ? 0xFu : 0u) | ((close & 2u) ? 0xF0u : 0u) | ((close & 4u) ? 0xF00u : 0u) |
-                            ((close & 8u) ? 0xF000u : 0u);
-      uint32_t a4 = aw & keep;                           // agents outside the close list Stay (defaultAction='stay')
-      if (v == 0) a4 = (a4 & ~(0xFu << (4 * x))) | (((aw >> (16 + 4 * x)) & 0xFu) << (4 * x));   // actor plays its MdR (:169-172)
-      if (jc) a4 = (a4 & ~(0xFu << (4 * j))) | (ap << (4 * j));                                  // affected tries action ap (:34-39)
-      PairGeom g;
-      g.didx_lo = s.geom_lo[el];
-      g.didx_hi = s.geom_hi[el] & 0xFFFFu;
-      g.near6 = s.geom_hi[el] >> 16;
-      if (counterfactual_valid(s.lut, s.next, n, cells, a4, g, (int)j)) {
-        const uint32_t jslot = j - (j > x ? 1u : 0u);
-        atomicAdd(&s.cnt[el * 2 + x], (jc ? 1u : 9u) << (4 * (jslot * 2 + v)));
-      }
-    }
-    __syncthreads();
-  }
-
-  // ================================================================= P3: fear, shaped reward, statistics
-  if (own) {
-    double fear[GW_MAX_LEARNERS] = {0.0, 0.0};
-    if (FEAR) {
+        uint32_t pdv = 0, pd[2] = {0, 0};
 #pragma unroll
-      for (int x = 0; x < GW_MAX_LEARNERS; ++x) {
-        if (x >= nl) break;
-        const uint32_t tb = (task_bits >> (4 * x)) & 0xFu;
-        if (tb == 0) continue;
-        const uint32_t c = s.cnt[tid * 2 + x];
-        double rs[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-        for (int js = 0; js < 3; ++js) {
-          const int j = js + (js >= x ? 1 : 0);
-          if ((tb >> j) & 1u) rs[js] = T->resp_lut[(c >> (8 * js)) & 0xFu][(c >> (8 * js + 4)) & 0xFu];
+        for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
+          if (k >= nl) continue;
+          if ((r.crash >> k) & 1u) {                                       // :281-285
+            ri[k] -= 10;
+            ++crash_count;
+            trunc = 1;
+            term |= 1u << k;
+          }
+          if ((apples_left >> k) & 1u) {                                   // :287-300
+            const uint32_t d = (uint32_t)manhattan((cells_new >> (8 * k)) & 0xFFu, (p.apple_cells >> (8 * k)) & 0xFFu);
+            const uint32_t prev_valid = (meta >> (M_PDV_SH + k)) & 1u;
+            const uint32_t prev = (meta >> (k == 0 ? M_PD0_SH : M_PD1_SH)) & 31u;
+            if (prev_valid && prev > d) { ri[k] += 1; shaped |= 1u << k; }
+            pdv |= 1u << k;
+            pd[k] = d;
+          }
+          reward[k] = (double)ri[k];
         }
-        fear[x] = fear_sum3(n, rs[0], rs[1], rs[2]);
+        term_now = term;
+        trunc_now = trunc ? ((1u << nl) - 1u) : 0u;
+        const uint32_t steps = min(((meta >> M_STEPS_SH) & M_STEPS_MASK) + 1u, M_STEPS_MASK);
+        meta = apples_left | (term << M_TERM_SH) | (trunc ? M_TRUNC : 0u) | (pdv << M_PDV_SH) | (pd[0] << M_PD0_SH) |
+               (pd[1] << M_PD1_SH) | (steps << M_STEPS_SH);
+      } else {                                                             // customenv.py:126-158
+        double rew = 0.0;
+        const uint32_t apple = p.apple_cells & 0xFFu;
+        const uint32_t d = (uint32_t)manhattan(cells_new & 0xFFu, apple);
+        if (r.crash & 1u) { rew -= 10.0; term_now = 1; crash_count = 1; }
+        if ((apples_left & 1u) && (r.caught & 7u) == 1u) {                 // len(apples_caught) == 1 (:143)
+          apples_left &= ~1u;
+          rew += 20.0;
+          trunc_now = 1;
+          apples_rewarded = 1;
+        }
+        const uint32_t prev = (meta >> M_PD0_SH) & 31u;
+        if (d < prev) { rew += 0.1; shaped = 1; }                          // :157-158
+        reward[0] = rew;
+        const uint32_t steps = min(((meta >> M_STEPS_SH) & M_STEPS_MASK) + 1u, M_STEPS_MASK);
+        meta = apples_left | (1u << M_PDV_SH) | (d << M_PD0_SH) | (steps << M_STEPS_SH);
       }
-    }
-    if (nl == 2) {
-      if (p.io.fear) reinterpret_cast<double2*>(p.io.fear)[e] = make_double2(fear[0], fear[1]);
-      if (p.io.shaped_reward)
-        reinterpret_cast<float2*>(p.io.shaped_reward)[e] =
-            make_float2((float)(p.fear_weight * fear[0] + reward[0]), (float)(p.fear_weight * fear[1] + reward[1]));   // maddpg/agent.py:130
-    } else {
-      if (p.io.fear) p.io.fear[e] = fear[0];
-      if (p.io.shaped_reward) p.io.shaped_reward[e] = (float)(p.fear_weight * fear[0] + reward[0]);
-    }
-    // statistics: most lanes contribute nothing, so reduce over the warp first
-    const uint32_t ended = fear_stat_ended & 1u, crashes = (fear_stat_ended >> 1) & 3u, apples = (fear_stat_ended >> 3) & 3u;
-    const int nz = FEAR ? ((fear[0] != 0.0) + (fear[1] != 0.0)) : 0;
-    const unsigned act = __activemask();
-    const unsigned any = __ballot_sync(act, ended | crashes | apples | (uint32_t)nz);
-    if (any) {
+      steps_now = (meta >> M_STEPS_SH) & M_STEPS_MASK;
+      const bool episode_over = (p.kind == GW_ENV_MULTI) ? (trunc_now != 0) : ((term_now | trunc_now) != 0);
+      const bool ended = episode_over || (p.max_steps > 0 && (int)steps_now >= p.max_steps);
+
+      // ---- scalar outputs (one thread per env: each array is written with unit stride across the warp)
+      if (nl == 2) {
+        if (p.io.reward) reinterpret_cast<float2*>(p.io.reward)[e] = make_float2((float)reward[0], (float)reward[1]);
+        if (p.io.terminated) reinterpret_cast<uchar2*>(p.io.terminated)[e] = make_uchar2(term_now & 1u, (term_now >> 1) & 1u);
+        if (p.io.truncated) reinterpret_cast<uchar2*>(p.io.truncated)[e] = make_uchar2(trunc_now & 1u, (trunc_now >> 1) & 1u);
+      } else {
+        if (p.io.reward) p.io.reward[e] = (float)reward[0];
+        if (p.io.terminated) p.io.terminated[e] = (uint8_t)(term_now & 1u);
+        if (p.io.truncated) p.io.truncated[e] = (uint8_t)(trunc_now & 1u);
+      }
+      write_positions(p.io.positions, e, n, cells_new);
+      if (p.io.ended) p.io.ended[e] = ended ? 1 : 0;
+      if (p.io.info)
+        p.io.info[e] = (r.crash & 15u) | ((r.restr & 15u) << 4) | (crash_count << 8) | (apples_rewarded << 10) |
+                       ((ended ? 1u : 0u) << 12) | (shaped << 14);
+
+      // ---- episode return (reward units: 1 multi, 0.1 single), state for the next step, render record
+      ret0 = (int)(short)(st.w & 0xFFFFu);
+      ret1 = (int)(short)(st.w >> 16);
       const double unit = (p.kind == GW_ENV_MULTI) ? 1.0 : 10.0;
-      const int slot = (int)((e >> 5) & (STAT_SLOTS - 1));
-      const int lane = tid & 31;
-      const int leader = __ffs(act) - 1;
-      const unsigned w_end = __reduce_add_sync(act, ended), w_len = __reduce_add_sync(act, ended ? steps_now : 0u);
-      const unsigned w_cr = __reduce_add_sync(act, crashes), w_ap = __reduce_add_sync(act, apples);
-      const unsigned w_nz = __reduce_add_sync(act, (unsigned)nz);
-      const int w_ret = __reduce_add_sync(act, ended ? (ret0 + ret1) : 0);
-      if (lane == leader) {
-        if (w_end) {
-          atomicAdd(&p.stats[slot * 8 + ST_EPISODES], (unsigned long long)w_end);
-          atomicAdd(&p.stats[slot * 8 + ST_LEN], (unsigned long long)w_len);
-          atomicAdd(&p.stats[slot * 8 + ST_RETURN_MILLI], (unsigned long long)(long long)llrint(w_ret * (1000.0 / unit)));
-        }
-        if (w_cr) atomicAdd(&p.stats[slot * 8 + ST_CRASH], (unsigned long long)w_cr);
-        if (w_ap) atomicAdd(&p.stats[slot * 8 + ST_APPLES], (unsigned long long)w_ap);
-        if (w_nz) atomicAdd(&p.stats[slot * 8 + ST_FEAR_NZ], (unsigned long long)w_nz);
+      ret0 += (int)lrint(reward[0] * unit);
+      ret1 += (int)lrint(reward[1] * unit);
+      stat_bits = (ended ? 1u : 0u) | (crash_count << 1) | (apples_rewarded << 3);
+      if (ended && p.auto_reset) {
+        const uint32_t cells_sp = spawn_cells(p, e, tick);
+        const uint32_t meta_sp = fresh_meta(p, cells_sp);
+        s.cells_new[tid] = cells_sp;
+        s.cells_fin[tid] = cells_new;
+        s.rinfo[tid] = (meta_sp & M_APPLES) | R_FRESH | R_FINAL | (apples_left << 4);
+        p.state[e] = make_uint4(cells_sp, meta_sp, tick + 1, 0u);
+      } else {
+        s.cells_new[tid] = cells_new;
+        s.rinfo[tid] = apples_left;
+        p.state[e] = make_uint4(cells_new, meta, tick + 1, ((uint32_t)ret0 & 0xFFFFu) | ((uint32_t)ret1 << 16));
       }
-      if (nz) atomicAdd(reinterpret_cast<double*>(&p.stats[slot * 8 + ST_FEAR_BITS]), fear[0] + fear[1]);
     }
-  }
 
-  // ================================================================= P4
-  __syncthreads();
-  render_tile<THREADS, TILE, OBS>(s, p, tile_base, tile_envs);
+    // ================================================================= P2: counterfactual sims (Responsibility.py:20-54)
+    if (FEAR) {
+      __syncthreads();
+      const uint32_t n_work = s.qn * 18u;
+      for (uint32_t w = tid; w < n_work; w += THREADS) {
+        const uint32_t tk = s.queue[w / 18u], rr = w % 18u;
+        const uint32_t v = rr / 9u, ap = rr - v * 9u;
+        const uint32_t el = tk & 0xFFu, x = (tk >> 8) & 1u, j = (tk >> 9) & 3u, jc = (tk >> 11) & 1u;
+        if (!jc && ap != 0) continue;                    // affected not in the list: it Stays in all nine sims (:43)
+        const uint32_t effw = s.effs[el];
+        const uint32_t close = (s.close[el] >> (4 * x)) & 0xFu;
+        const uint32_t keep = ((close & 1u) ? 0xFu : 0u) | ((close & 2u) ? 0xF0u : 0u) | ((close & 4u) ? 0xF00u : 0u) |
+                              ((close & 8u) ? 0xF000u : 0u);
+        uint32_t eo = effw & keep;                       // agents outside the close list Stay (defaultAction='stay')
+        if (v == 0) eo = (eo & ~(0xFu << (4 * x))) | (((effw >> (16 + 4 * x)) & 0xFu) << (4 * x));   // actor plays its MdR (:169-172)
+        PairGeom g;
+        g.didx_lo = s.geom_lo[el];
+        g.didx_hi = s.geom_hi[el] & 0xFFFFu;
+        g.near6 = s.geom_hi[el] >> 16;
+        // affected tries action ap (:34-39); outside the list its action cannot be swapped in and it Stays
+        if (counterfactual_valid(s.lut, s.next, s.cells_old[el], eo, g, (int)j, jc ? ap : 0u)) {
+          const uint32_t jslot = j - (j > x ? 1u : 0u);
+          atomicAdd(&s.cnt[el * 2 + x], (jc ? 1u : 9u) << (4 * (jslot * 2 + v)));
+        }
+      }
+      __syncthreads();
+    }
+
+    // ================================================================= P3: fear, shaped reward, statistics
+    if (own) {
+      double fear[GW_MAX_LEARNERS] = {0.0, 0.0};
+      if (FEAR) {
+#pragma unroll
+        for (int x = 0; x < GW_MAX_LEARNERS; ++x) {
+          if (x >= nl) break;
+          const uint32_t tb = (task_bits >> (4 * x)) & 0xFu;
+          if (tb == 0) continue;
+          const uint32_t c = s.cnt[tid * 2 + x];
+          double rs[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+          for (int js = 0; js < 3; ++js) {
+            const int j = js + (js >= x ? 1 : 0);
+            if ((tb >> j) & 1u) rs[js] = T->resp_lut[(c >> (8 * js)) & 0xFu][(c >> (8 * js + 4)) & 0xFu];
+          }
+          fear[x] = fear_sum3(n, rs[0], rs[1], rs[2]);
+        }
+      }
+      if (nl == 2) {
+        if (p.io.fear) reinterpret_cast<double2*>(p.io.fear)[e] = make_double2(fear[0], fear[1]);
+        if (p.io.shaped_reward)
+          reinterpret_cast<float2*>(p.io.shaped_reward)[e] =
+              make_float2((float)(p.fear_weight * fear[0] + reward[0]), (float)(p.fear_weight * fear[1] + reward[1]));   // maddpg/agent.py:130
+      } else {
+        if (p.io.fear) p.io.fear[e] = fear[0];
+        if (p.io.shaped_reward) p.io.shaped_reward[e] = (float)(p.fear_weight * fear[0] + reward[0]);
+      }
+      // statistics: most lanes contribute nothing, so reduce over the warp first
+      const uint32_t ended = stat_bits & 1u, crashes = (stat_bits >> 1) & 3u, apples = (stat_bits >> 3) & 3u;
+      const int nz = FEAR ? ((fear[0] != 0.0) + (fear[1] != 0.0)) : 0;
+      const unsigned act = __activemask();
+      const unsigned any = __ballot_sync(act, ended | crashes | apples | (uint32_t)nz);
+      if (any) {
+        const double unit = (p.kind == GW_ENV_MULTI) ? 1.0 : 10.0;
+        const int slot = (int)((e >> 5) & (STAT_SLOTS - 1));
+        const int lane = tid & 31;
+        const int leader = __ffs(act) - 1;
+        const unsigned w_end = __reduce_add_sync(act, ended), w_len = __reduce_add_sync(act, ended ? steps_now : 0u);
+        const unsigned w_cr = __reduce_add_sync(act, crashes), w_ap = __reduce_add_sync(act, apples);
+        const unsigned w_nz = __reduce_add_sync(act, (unsigned)nz);
+        const int w_ret = __reduce_add_sync(act, ended ? (ret0 + ret1) : 0);
+        if (lane == leader) {
+          if (w_end) {
+            atomicAdd(&p.stats[slot * 8 + ST_EPISODES], (unsigned long long)w_end);
+            atomicAdd(&p.stats[slot * 8 + ST_LEN], (unsigned long long)w_len);
+            atomicAdd(&p.stats[slot * 8 + ST_RETURN_MILLI], (unsigned long long)(long long)llrint(w_ret * (1000.0 / unit)));
+          }
+          if (w_cr) atomicAdd(&p.stats[slot * 8 + ST_CRASH], (unsigned long long)w_cr);
+          if (w_ap) atomicAdd(&p.stats[slot * 8 + ST_APPLES], (unsigned long long)w_ap);
+          if (w_nz) atomicAdd(&p.stats[slot * 8 + ST_FEAR_NZ], (unsigned long long)w_nz);
+        }
+        if (nz) atomicAdd(reinterpret_cast<double*>(&p.stats[slot * 8 + ST_FEAR_BITS]), fear[0] + fear[1]);
+      }
+    }
+
+    // ================================================================= P4
+    __syncthreads();
+    render_tile<THREADS, TILE, OBS>(s, p, tile_base, tile_envs);
+    __syncthreads();                                       // shared arrays are reused by the next tile
+  }
+  if (tables_pending) cp_async_wait_all();                 // a CTA without tiles must not exit with copies in flight
 }
 
 // ------------------------------------------------------------------ operator-level kernels
@@ -704,10 +751,11 @@ __global__ void __launch_bounds__(128) gw_fear_kernel(const Tables* T, int n_def
   for (int i = 0; i < n; ++i)
     if (in_list == nullptr || in_list[c * 4 + i]) lst |= 1u << i;
   const PairGeom g = pair_geometry(n, cells);
-  uint32_t base = 0;
+  uint32_t base = 0;                                   // effective trajectories of the listed agents; the others Stay (:43)
 #pragma unroll
   for (int k = 0; k < 4; ++k)
-    if ((lst >> k) & 1u) base |= ((acts >> (4 * k)) & 0xFu) << (4 * k);
+    if (k < n && ((lst >> k) & 1u))
+      base |= make_traj(s.next, (cells >> (8 * k)) & 0xFFu, (acts >> (4 * k)) & 0xFu).eff << (4 * k);
   const int js = lane / 9, ap = lane - js * 9;
   const int j = js + (js >= x ? 1 : 0);
   const bool lane_on = lane < 27 && j < n;
@@ -715,12 +763,10 @@ __global__ void __launch_bounds__(128) gw_fear_kernel(const Tables* T, int n_def
 #pragma unroll
   for (int v = 0; v < 2; ++v) {
     const uint32_t av = v == 0 ? (uint32_t)min(max((int)mdr[c * 4 + x], 0), 8) : ((acts >> (4 * x)) & 0xFu);
-    uint32_t a4 = (base & ~(0xFu << (4 * x))) | (av << (4 * x));
+    const uint32_t eo = (base & ~(0xFu << (4 * x))) | (make_traj(s.next, (cells >> (8 * x)) & 0xFFu, av).eff << (4 * x));
     bool valid = false;
-    if (lane_on) {
-      if ((lst >> j) & 1u) a4 = (a4 & ~(0xFu << (4 * j))) | ((uint32_t)ap << (4 * j));   // SwapActionIDs4Agents
-      valid = counterfactual_valid(s.lut, s.next, n, cells, a4, g, j);
-    }
+    if (lane_on)                                       // SwapActionIDs4Agents only touches agents present in the list
+      valid = counterfactual_valid(s.lut, s.next, cells, eo, g, j, ((lst >> j) & 1u) ? (uint32_t)ap : 0u);
     const uint32_t b = __ballot_sync(0xFFFFFFFFu, valid);
 #pragma unroll
     for (int q = 0; q < 3; ++q) packed |= (uint32_t)__popc(b & (0x1FFu << (9 * q))) << (16 * v + 4 * q);
@@ -749,6 +795,7 @@ struct gw_handle {
   uint4* d_state = nullptr;
   unsigned long long* d_stats = nullptr;
   bool reset_done = false;
+  int sm_count = 148;
   uint64_t launches = 0;
   uint64_t env_steps = 0;
   std::string err;
@@ -937,6 +984,7 @@ int gw_create(const gw_config* cfg, gw_handle** out) {
   gw_handle* h = new (std::nothrow) gw_handle();
   if (!h) return fail(nullptr, GW_ENOMEM, "gw_create: host allocation failed");
   h->cfg = *cfg;
+  h->sm_count = prop.multiProcessorCount;
 
   gw::Tables* t = new gw::Tables();
   std::memset(t, 0, sizeof(*t));
@@ -1078,7 +1126,10 @@ int gw_step(gw_handle* h, const gw_io* io, void* stream) {
   GW_CUDA(h, cudaSetDevice(h->cfg.device));
   gw::StepParams p = make_params(h, io);
   const int tile = pick_tile(h->cfg.num_envs);
-  const unsigned blocks = (unsigned)((h->cfg.num_envs + tile - 1) / tile);
+  const long long n_tiles = (h->cfg.num_envs + tile - 1) / tile;
+  // persistent CTAs: at most `sm_count x resident CTAs per SM`, each walks several tiles and loads the tables once
+  const long long resident = (long long)h->sm_count * (tile == 256 ? 4 : 8);
+  const unsigned blocks = (unsigned)(n_tiles < resident ? n_tiles : resident);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (tile == 32) launch_step_t<128, 32>(h->cfg, p, blocks, s);
   else if (tile == 128) launch_step_t<128, 128>(h->cfg, p, blocks, s);
