@@ -52,7 +52,9 @@ enum { ST_EPISODES = 0, ST_LEN, ST_CRASH, ST_APPLES, ST_UNRES, ST_FEAR_NZ, ST_RE
 // render record per env (shared memory): what P4 needs
 constexpr uint32_t R_FRESH = 1u << 2, R_FINAL = 1u << 3, R_SKIP = 1u << 6;   // bits 0-1 apples shown in obs, 4-5 apples at final
 
-template <int TILE>
+constexpr int STAGE_BYTES_FWD = GW_MAX_LEARNERS * GW_MAX_H * GW_W * 4;
+
+template <int TILE, int NWARPS = (TILE >= 256 ? 8 : 4)>
 struct Smem {
   alignas(16) uint8_t lut[(LUT_BYTES + 15) / 16 * 16];
   alignas(16) uint8_t next[GW_MAX_H * GW_W * 4];
@@ -64,6 +66,7 @@ struct Smem {
   uint16_t queue[TILE * 6];
   uint32_t qn;
   alignas(16) uint8_t mask[TILE * GW_MAX_LEARNERS * GW_N_ACTIONS + 16];
+  alignas(16) uint8_t stage[NWARPS][STAGE_BYTES_FWD];   // per-warp observation staging rows (template + patches)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -104,6 +107,8 @@ __device__ __forceinline__ void load_tables(Smem<TILE>& s, const Tables* __restr
       }
     }
     s.tmpl[q] = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int wq = 0; wq < THREADS / 32; ++wq)
+      for (int k = 0; k < GW_MAX_LEARNERS; ++k) reinterpret_cast<uint4*>(s.stage[wq])[k * Q + q] = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -125,118 +130,78 @@ __device__ __forceinline__ void store_cell(void* obs_base, long long elem, float
   else reinterpret_cast<__nv_bfloat16*>(obs_base)[elem] = __float2bfloat16(v);
 }
 
-// patch the special cells of one env's observations (thread per env)
+// One env's observations (all learners) written by one warp.  The warp keeps a private copy of the constant
+// observation template in shared memory; the <= 5 special cells per learner (agents, own apple) are patched in
+// with scalar shared-memory stores, the rows leave as full 128-bit coalesced streaming stores (whole 128-byte lines,
+// never a partial sector), and the patched cells are set back to 0 (agents and apples only stand on active cells).
 template <int OBS>
-__device__ __forceinline__ void patch_env(void* obs_base, long long e, int cells_per_obs, int n, int nl, int kind,
-                                          uint32_t cells, uint32_t apples_left, uint32_t apple_cells, bool fresh) {
-#pragma unroll
-  for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
-    if (k >= nl) break;
-    const long long base = (e * nl + k) * (long long)cells_per_obs;
+__device__ __forceinline__ void stage_and_store_env(uint8_t* stage, void* obs_base, long long e, int H, int n, int nl,
+                                                    int kind, uint32_t cells, uint32_t apples_left, uint32_t apple_cells,
+                                                    bool fresh, int lane) {
+  const int cpo = H * GW_W;
+  const int Q = (OBS == GW_OBS_F32) ? cpo / 4 : cpo / 8;
+  // lane -> (learner k, item i): items 0..n-1 are the agents, item n is the learner's apple
+  const int per = n + 1;
+  const int k = lane >= per ? 1 : 0, i = lane - k * per;
+  int my_cell = -1;
+  float my_val = 0.0f;
+  if (lane < nl * per) {
     const bool apple_on = (kind == GW_ENV_MULTI) ? ((apples_left >> k) & 1u) : (apples_left & 1u);
     const uint32_t apple = (kind == GW_ENV_MULTI) ? (apple_cells >> (8 * k)) & 0xFFu : apple_cells & 0xFFu;
-    bool apple_covered = false;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (i >= n) break;
+    if (i < n) {
       const uint32_t c = (cells >> (8 * i)) & 0xFFu;
-      const bool here = apple_on && c == apple;
-      apple_covered |= here;
-      store_cell<OBS>(obs_base, base + c, special_value(kind, fresh, i, k, here));
+      my_cell = (int)c;
+      my_val = special_value(kind, fresh, i, k, apple_on && c == apple);
+    } else if (apple_on) {
+      bool covered = false;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) covered |= (a < n) && ((cells >> (8 * a)) & 0xFFu) == apple;
+      if (!covered) { my_cell = (int)apple; my_val = 9.0f; }
     }
-    if (apple_on && !apple_covered) store_cell<OBS>(obs_base, base + apple, 9.0f);
+    if (my_cell >= 0) {
+      if (OBS == GW_OBS_F32) reinterpret_cast<float*>(stage)[k * cpo + my_cell] = my_val;
+      else reinterpret_cast<__nv_bfloat16*>(stage)[k * cpo + my_cell] = __float2bfloat16(my_val);
+    }
   }
-}
-
-// whole observation of one env written by one warp with the special cells patched in registers
-// (used for final_obs, which only the few envs that ended in this step need)
-template <int OBS, int TILE>
-__device__ __forceinline__ void render_env_warp(const Smem<TILE>& s, void* obs_base, long long e, int H, int n, int nl,
-                                                int kind, uint32_t cells, uint32_t apples_left, uint32_t apple_cells,
-                                                bool fresh, int lane) {
-  const int cpo = H * GW_W;
-  const int per_vec = (OBS == GW_OBS_F32) ? 4 : 8;
-  const int Q = cpo / per_vec;
+  __syncwarp();
   uint4* dst = reinterpret_cast<uint4*>(obs_base) + e * (long long)(nl * Q);
-  for (int g = lane; g < nl * Q; g += 32) {
-    const int k = g / Q, q = g - k * Q;
-    float v[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      if (c >= per_vec) break;
-      const uint32_t cell = (uint32_t)(q * per_vec + c);
-      int who = -1;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (i < n && ((cells >> (8 * i)) & 0xFFu) == cell) who = i;
-      const bool apple_on = (kind == GW_ENV_MULTI) ? ((apples_left >> k) & 1u) : (apples_left & 1u);
-      const uint32_t apple = (kind == GW_ENV_MULTI) ? (apple_cells >> (8 * k)) & 0xFFu : apple_cells & 0xFFu;
-      const bool here = apple_on && apple == cell;
-      const float base = ((s.rows[cell >> 4] >> (cell & 15)) & 1) ? 0.0f : -1.0f;
-      v[c] = (who >= 0 || here) ? special_value(kind, fresh, who, k, here) : base;
-    }
-    uint4 o;
-    if (OBS == GW_OBS_F32) {
-      o = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
-    } else {
-      uint32_t w[4];
-#pragma unroll
-      for (int h = 0; h < 4; ++h)
-        w[h] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(v[2 * h])) |
-               ((uint32_t)__bfloat16_as_ushort(__float2bfloat16(v[2 * h + 1])) << 16);
-      o = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-    dst[g] = o;
+  const uint4* src = reinterpret_cast<const uint4*>(stage);
+  const int V = nl * Q;
+  uint4 v0, v1, v2, v3;
+  if (lane < V) v0 = src[lane];
+  if (lane + 32 < V) v1 = src[lane + 32];
+  if (lane + 64 < V) v2 = src[lane + 64];
+  if (lane + 96 < V) v3 = src[lane + 96];
+  if (lane < V) __stcs(dst + lane, v0);
+  if (lane + 32 < V) __stcs(dst + lane + 32, v1);
+  if (lane + 64 < V) __stcs(dst + lane + 64, v2);
+  if (lane + 96 < V) __stcs(dst + lane + 96, v3);
+  __syncwarp();
+  if (my_cell >= 0) {
+    if (OBS == GW_OBS_F32) reinterpret_cast<float*>(stage)[k * cpo + my_cell] = 0.0f;
+    else reinterpret_cast<__nv_bfloat16*>(stage)[k * cpo + my_cell] = __float2bfloat16(0.0f);
   }
+  __syncwarp();
 }
 
 // P4: observations + action masks of the tile
 template <int THREADS, int TILE, int OBS>
 __device__ __forceinline__ void render_tile(Smem<TILE>& s, const StepParams& p, long long tile_base, int tile_envs) {
-  const int tid = threadIdx.x;
-  const int cpo = p.H * GW_W;
-  const int Q = (OBS == GW_OBS_F32) ? cpo / 4 : cpo / 8;
-  if (p.io.obs != nullptr) {
-    // bulk: the constant template, 16 B per thread, consecutive threads -> consecutive addresses
-    uint4* dst = reinterpret_cast<uint4*>(p.io.obs) + tile_base * (long long)(p.nl * Q);
-    const int V = tile_envs * p.nl * Q;
-    const int qstep = THREADS % Q;
-    const bool partial = p.reset_mask != nullptr;          // masked reset: untouched envs keep their observation
-    if (!partial && (5 * qstep) % Q == 0) {
-      // the template index of a thread repeats every 5 iterations (H = 10: Q = 40 or 20): keep the 5 vectors in
-      // registers and the loop body is one 128-bit streaming store
-      uint4 t5[5];
-      int q = tid % Q;
-#pragma unroll
-      for (int u = 0; u < 5; ++u) {
-        t5[u] = s.tmpl[q];
-        q += qstep;
-        if (q >= Q) q -= Q;
-      }
-      int g = tid;
-      for (; g + 4 * THREADS < V; g += 5 * THREADS) {
-#pragma unroll
-        for (int u = 0; u < 5; ++u) __stcs(dst + g + u * THREADS, t5[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < 5; ++u)
-        if (g + u * THREADS < V) __stcs(dst + g + u * THREADS, t5[u]);
-    } else {
-      int q = tid % Q;
-      for (int g = tid; g < V; g += THREADS) {
-        if (!partial || !(s.rinfo[g / (p.nl * Q)] & R_SKIP)) __stcs(dst + g, s.tmpl[q]);
-        q += qstep;
-        if (q >= Q) q -= Q;
-      }
-    }
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int NWARPS = THREADS / 32;
+  uint8_t* stage = s.stage[warp];
+  for (int el = warp; el < tile_envs; el += NWARPS) {
+    const uint32_t ri = s.rinfo[el];
+    if (ri & R_SKIP) continue;
+    if (p.io.obs != nullptr)
+      stage_and_store_env<OBS>(stage, p.io.obs, tile_base + el, p.H, p.n, p.nl, p.kind, s.cells_new[el], ri & 3u,
+                               p.apple_cells, (ri & R_FRESH) != 0, lane);
+    if ((ri & R_FINAL) && p.io.final_obs != nullptr)      // terminal observation of an env that was just re-spawned
+      stage_and_store_env<OBS>(stage, p.io.final_obs, tile_base + el, p.H, p.n, p.nl, p.kind, s.cells_fin[el],
+                               (ri >> 4) & 3u, p.apple_cells, false, lane);
   }
-  __syncthreads();                                           // patches must land after the template
-  if (tid < tile_envs) {
-    const uint32_t ri = s.rinfo[tid];
-    if (p.io.obs != nullptr && !(ri & R_SKIP))
-      patch_env<OBS>(p.io.obs, tile_base + tid, cpo, p.n, p.nl, p.kind, s.cells_new[tid], ri & 3u, p.apple_cells,
-                     (ri & R_FRESH) != 0);
-    if (p.io.action_mask != nullptr && !(ri & R_SKIP)) {
+  if (p.io.action_mask != nullptr) {
+    if (tid < tile_envs && !(s.rinfo[tid] & R_SKIP)) {
 #pragma unroll
       for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
         if (k >= p.nl) break;
@@ -245,18 +210,6 @@ __device__ __forceinline__ void render_tile(Smem<TILE>& s, const StepParams& p, 
         for (int a = 0; a < GW_N_ACTIONS; ++a) s.mask[(tid * p.nl + k) * GW_N_ACTIONS + a] = (uint8_t)((m >> a) & 1u);
       }
     }
-  }
-  // final observations of the envs that ended (rare): one warp per such env
-  if (p.io.final_obs != nullptr) {
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int el = warp; el < tile_envs; el += THREADS / 32) {
-      const uint32_t ri = s.rinfo[el];
-      if (ri & R_FINAL)
-        render_env_warp<OBS, TILE>(s, p.io.final_obs, tile_base + el, p.H, p.n, p.nl, p.kind, s.cells_fin[el],
-                                   (ri >> 4) & 3u, p.apple_cells, false, lane);
-    }
-  }
-  if (p.io.action_mask != nullptr) {
     __syncthreads();
     const int bytes = tile_envs * p.nl * GW_N_ACTIONS;
     int8_t* dst = p.io.action_mask + tile_base * (long long)(p.nl * GW_N_ACTIONS);
@@ -875,6 +828,7 @@ static int validate(const gw_config* c, std::string& why) {
     const int r = c->apple_row[k], col = c->apple_col[k];
     if (r < 0) continue;
     if (r >= c->height || col < 0 || col >= c->width) { why = "apple outside the grid"; return GW_EINVAL; }
+    if (!((c->map_rows[r] >> col) & 1)) { why = "apple on an inactive cell"; return GW_EINVAL; }
   }
   if (c->env_kind == GW_ENV_SINGLE && c->apple_row[0] < 0) { why = "single env needs an apple"; return GW_EINVAL; }
   for (int i = 0; i < c->height * GW_W; ++i) {
