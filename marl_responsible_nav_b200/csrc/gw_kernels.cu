@@ -135,7 +135,7 @@ __device__ __forceinline__ void store_cell(void* obs_base, long long elem, float
 // with scalar shared-memory stores, the rows leave as full 128-bit coalesced streaming stores (whole 128-byte lines,
 // never a partial sector), and the patched cells are set back to 0 (agents and apples only stand on active cells).
 template <int OBS>
-__device__ __forceinline__ void stage_and_store_env(uint8_t* stage, void* obs_base, long long e, int H, int n, int nl,
+__device__ __noinline__ void stage_and_store_env(uint8_t* stage, void* obs_base, long long e, int H, int n, int nl,
                                                     int kind, uint32_t cells, uint32_t apples_left, uint32_t apple_cells,
                                                     bool fresh, int lane) {
   const int cpo = H * GW_W;
@@ -290,8 +290,9 @@ __device__ __forceinline__ void write_positions(int8_t* dst, long long e, int n,
 
 // ------------------------------------------------------------------ reset kernel
 template <int THREADS, int TILE, int OBS>
-__global__ void __launch_bounds__(THREADS) gw_reset_kernel(StepParams p) {
-  __shared__ Smem<TILE> s;
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_reset_kernel(StepParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
   load_tables<THREADS, TILE, OBS>(s, p.tables, p.H, false);
   __syncthreads();
   const long long tile_base = (long long)blockIdx.x * TILE;
@@ -319,8 +320,9 @@ __global__ void __launch_bounds__(THREADS) gw_reset_kernel(StepParams p) {
 // ------------------------------------------------------------------ step kernel
 // Persistent CTAs: the grid is sized to the machine and each CTA walks tiles blockIdx.x, +gridDim.x, ...
 template <int THREADS, int TILE, bool FEAR, int OBS>
-__global__ void __launch_bounds__(THREADS) gw_step_kernel(StepParams p) {
-  __shared__ Smem<TILE> s;
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
   load_tables<THREADS, TILE, OBS>(s, p.tables, p.H, true);
   const Tables* __restrict__ T = p.tables;
   const int tid = threadIdx.x;
@@ -1034,22 +1036,31 @@ static int pick_tile(long long E) {
   return 256;
 }
 
+template <typename K>
+static void launch_k(K kernel, const gw::StepParams& p, unsigned blocks, int threads, size_t smem, cudaStream_t s) {
+  // > 48 KB of dynamic shared memory needs the opt-in; the attribute is per function and cheap to set
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kernel<<<blocks, threads, smem, s>>>(p);
+}
+
 template <int THREADS, int TILE>
 static void launch_step_t(const gw_config& c, const gw::StepParams& p, unsigned blocks, cudaStream_t s) {
   const bool f32 = c.obs_dtype == GW_OBS_F32;
+  const size_t smem = sizeof(gw::Smem<TILE>);
   if (c.fear) {
-    if (f32) gw::gw_step_kernel<THREADS, TILE, true, GW_OBS_F32><<<blocks, THREADS, 0, s>>>(p);
-    else gw::gw_step_kernel<THREADS, TILE, true, GW_OBS_BF16><<<blocks, THREADS, 0, s>>>(p);
+    if (f32) launch_k(gw::gw_step_kernel<THREADS, TILE, true, GW_OBS_F32>, p, blocks, THREADS, smem, s);
+    else launch_k(gw::gw_step_kernel<THREADS, TILE, true, GW_OBS_BF16>, p, blocks, THREADS, smem, s);
   } else {
-    if (f32) gw::gw_step_kernel<THREADS, TILE, false, GW_OBS_F32><<<blocks, THREADS, 0, s>>>(p);
-    else gw::gw_step_kernel<THREADS, TILE, false, GW_OBS_BF16><<<blocks, THREADS, 0, s>>>(p);
+    if (f32) launch_k(gw::gw_step_kernel<THREADS, TILE, false, GW_OBS_F32>, p, blocks, THREADS, smem, s);
+    else launch_k(gw::gw_step_kernel<THREADS, TILE, false, GW_OBS_BF16>, p, blocks, THREADS, smem, s);
   }
 }
 
 template <int THREADS, int TILE>
 static void launch_reset_t(const gw_config& c, const gw::StepParams& p, unsigned blocks, cudaStream_t s) {
-  if (c.obs_dtype == GW_OBS_F32) gw::gw_reset_kernel<THREADS, TILE, GW_OBS_F32><<<blocks, THREADS, 0, s>>>(p);
-  else gw::gw_reset_kernel<THREADS, TILE, GW_OBS_BF16><<<blocks, THREADS, 0, s>>>(p);
+  const size_t smem = sizeof(gw::Smem<TILE>);
+  if (c.obs_dtype == GW_OBS_F32) launch_k(gw::gw_reset_kernel<THREADS, TILE, GW_OBS_F32>, p, blocks, THREADS, smem, s);
+  else launch_k(gw::gw_reset_kernel<THREADS, TILE, GW_OBS_BF16>, p, blocks, THREADS, smem, s);
 }
 
 extern "C" {
