@@ -184,20 +184,25 @@ __device__ __forceinline__ uint32_t agents_of_pairs(uint32_t hp) {
          ((hp & 0x110100u) ? 8u : 0u);
 }
 
-__device__ __forceinline__ uint32_t collide(const uint8_t* __restrict__ s_lut, const PairGeom& g, const uint32_t eff[4],
-                                            uint32_t stop = 0) {
-  if (g.near6 == 0) return 0;
+// effp: 4 x 4-bit effective trajectories.  pair_sel: which of the six pairs to look up.
+__device__ __forceinline__ uint32_t nn_masks(const uint8_t* __restrict__ s_lut, const PairGeom& g, uint32_t effp,
+                                             uint32_t pair_sel) {
   uint32_t NNw = 0;
-  {
-    int p = 0;
+  const uint32_t sel = g.near6 & pair_sel;
+  int p = 0;
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int j = i + 1; j < 4; ++j, ++p)
-        if ((g.near6 >> p) & 1u)
-          NNw |= (uint32_t)s_lut[geom_didx(g, p) * (N_EFF * N_EFF) + eff[i] * N_EFF + eff[j]] << (4 * p);
-  }
-  if (NNw == 0) return 0;                             // nobody collides while everyone is on course
+    for (int j = i + 1; j < 4; ++j, ++p)
+      if ((sel >> p) & 1u)
+        NNw |= (uint32_t)s_lut[geom_didx(g, p) * (N_EFF * N_EFF) + ((effp >> (4 * i)) & 0xFu) * N_EFF +
+                               ((effp >> (4 * j)) & 0xFu)] << (4 * p);
+  return NNw;
+}
+
+// The fix-point proper, given the both-on-course masks NNw != 0 of all near pairs.
+__device__ __forceinline__ uint32_t resolve(const uint8_t* __restrict__ s_lut, const PairGeom& g, uint32_t effp,
+                                            uint32_t NNw, uint32_t stop) {
   // first sub-step with a hit: nothing happens before it
   const uint32_t any = (NNw | (NNw >> 4) | (NNw >> 8) | (NNw >> 12) | (NNw >> 16) | (NNw >> 20)) & 0xFu;
   const int s0 = __ffs(any) - 1;
@@ -212,8 +217,8 @@ __device__ __forceinline__ uint32_t collide(const uint8_t* __restrict__ s_lut, c
       for (int j = i + 1; j < 4; ++j, ++p)
         if ((g.near6 >> p) & 1u) {
           const uint32_t base = geom_didx(g, p) * (N_EFF * N_EFF);
-          NRw |= (uint32_t)s_lut[base + eff[i] * N_EFF] << (4 * p);
-          RNw |= (uint32_t)s_lut[base + eff[j]] << (4 * p);
+          NRw |= (uint32_t)s_lut[base + ((effp >> (4 * i)) & 0xFu) * N_EFF] << (4 * p);
+          RNw |= (uint32_t)s_lut[base + ((effp >> (4 * j)) & 0xFu)] << (4 * p);
         }
   }
   uint32_t out = 0;
@@ -229,6 +234,14 @@ __device__ __forceinline__ uint32_t collide(const uint8_t* __restrict__ s_lut, c
     out |= crashed << (4 * s);
   }
   return out;
+}
+
+__device__ __forceinline__ uint32_t collide(const uint8_t* __restrict__ s_lut, const PairGeom& g, uint32_t effp,
+                                            uint32_t stop = 0) {
+  if (g.near6 == 0) return 0;
+  const uint32_t NNw = nn_masks(s_lut, g, effp, 0x3Fu);
+  if (NNw == 0) return 0;                             // nobody collides while everyone is on course
+  return resolve(s_lut, g, effp, NNw, stop);
 }
 
 // cell of agent at the end of sub-step s (grid_world.py:259-264 floor index; crashed => start cell)
@@ -251,16 +264,14 @@ __device__ __forceinline__ StepResult world_update(const uint8_t* __restrict__ s
                                                    int n, uint32_t cells, uint32_t acts, const PairGeom& g,
                                                    uint32_t apple_cells, uint32_t apple_on, int n_eaters) {
   Traj t[4];
-  uint32_t eff[4];
   StepResult r;
   r.effs = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     t[i] = make_traj(s_next, (cells >> (8 * i)) & 0xFFu, i < n ? (acts >> (4 * i)) & 0xFu : 0u);
-    eff[i] = t[i].eff;
-    r.effs |= eff[i] << (4 * i);
+    r.effs |= t[i].eff << (4 * i);
   }
-  const uint32_t cm = (n >= 2) ? collide(s_lut, g, eff) : 0u;
+  const uint32_t cm = (n >= 2) ? collide(s_lut, g, r.effs) : 0u;
   r.crash = (cm >> 12) & 0xFu;
   r.cells = 0;
   r.restr = 0;
@@ -290,19 +301,35 @@ __device__ __forceinline__ StepResult world_update(const uint8_t* __restrict__ s
   return r;
 }
 
-// One counterfactual of CountValidMovesOfAffected (custom/Responsibility.py:32-48): is the affected agent j
-// neither restricted nor crashed?  eff_others: effective trajectories of everybody (the entry of j is ignored),
-// with agents outside the action list already set to 0 (Stay, :43); aj: the action j tries.
-__device__ __forceinline__ bool counterfactual_valid(const uint8_t* __restrict__ s_lut, const uint8_t* __restrict__ s_next,
-                                                     uint32_t cells, uint32_t eff_others, const PairGeom& g, int j,
-                                                     uint32_t aj) {
-  const Traj tj = make_traj(s_next, (cells >> (8 * j)) & 0xFFu, aj);
-  if (tj.r1 | tj.r2) return false;          // restricted, or crashed before the blocked second move: invalid either way
-  uint32_t eff[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) eff[i] = (i == j) ? tj.eff : (eff_others >> (4 * i)) & 0xFu;
-  const uint32_t cm = collide(s_lut, g, eff, 1u << j);
-  return ((cm >> (12 + j)) & 1u) == 0;
+// pairs (01,02,03,12,13,23) that involve agent j
+__device__ __forceinline__ uint32_t pairs_of_agent(int j) {
+  return j == 0 ? 0x07u : (j == 1 ? 0x19u : (j == 2 ? 0x2Au : 0x34u));
+}
+
+// CountValidMovesOfAffected (custom/Responsibility.py:20-54) for one action list: how many of the nine actions of
+// the affected agent j leave it neither restricted nor crashed (:46).  eff_others: effective trajectories of
+// everybody else, agents outside the list already 0 (Stay, :43).  in_list = false: j is not in the list, its action
+// cannot be swapped in, so all nine simulations are the same one (j Stays) and the count is 0 or 9.
+// The pair masks that do not involve j are looked up once; per action only the <= 3 pairs of j change.
+__device__ __forceinline__ uint32_t count_valid_moves(const uint8_t* __restrict__ s_lut, const uint8_t* __restrict__ s_next,
+                                                      uint32_t cells, uint32_t eff_others, const PairGeom& g, int j,
+                                                      bool in_list) {
+  const uint32_t pj = pairs_of_agent(j);
+  const uint32_t eo = eff_others & ~(0xFu << (4 * j));
+  const uint32_t nn_fixed = nn_masks(s_lut, g, eo, 0x3Fu & ~pj);
+  const uint32_t cell_j = (cells >> (8 * j)) & 0xFFu;
+  uint32_t count = 0;
+  const uint32_t n_try = in_list ? (uint32_t)GW_N_ACTIONS : 1u;
+  for (uint32_t a = 0; a < n_try; ++a) {
+    const Traj tj = make_traj(s_next, cell_j, a);
+    if (tj.r1 | tj.r2) continue;            // restricted, or crashed before the blocked second move: invalid either way
+    const uint32_t effp = eo | (tj.eff << (4 * j));
+    const uint32_t NNw = nn_fixed | nn_masks(s_lut, g, effp, pj);
+    if (NNw == 0) { ++count; continue; }
+    const uint32_t cm = resolve(s_lut, g, effp, NNw, 1u << j);
+    if (((cm >> (12 + j)) & 1u) == 0) ++count;
+  }
+  return in_list ? count : count * 9u;
 }
 
 // np.sum over the Resp matrix (one non-zero row): numpy's 8-lane pairwise reduction adds the row as

@@ -53,6 +53,7 @@ enum { ST_EPISODES = 0, ST_LEN, ST_CRASH, ST_APPLES, ST_UNRES, ST_FEAR_NZ, ST_RE
 constexpr uint32_t R_FRESH = 1u << 2, R_FINAL = 1u << 3, R_SKIP = 1u << 6;   // bits 0-1 apples shown in obs, 4-5 apples at final
 
 constexpr int STAGE_BYTES_FWD = GW_MAX_LEARNERS * GW_MAX_H * GW_W * 4;
+constexpr int N_SPEC = GW_MAX_LEARNERS * (GW_MAX_AGENTS + 1);   // per learner: every agent + the own apple
 
 template <int TILE, int NWARPS = (TILE >= 256 ? 8 : 4)>
 struct Smem {
@@ -62,7 +63,8 @@ struct Smem {
   uint16_t rows[GW_MAX_H];
   uint32_t cells_old[TILE], effs[TILE], geom_lo[TILE], geom_hi[TILE], close[TILE];
   uint32_t cnt[TILE * 2];
-  uint32_t cells_new[TILE], cells_fin[TILE], rinfo[TILE];
+  uint32_t cells_fin[TILE], rinfo[TILE];
+  uint16_t spec[TILE][N_SPEC];                          // special cells of the tile's observations (offset | value*2 << 9)
   uint16_t queue[TILE * 6];
   uint32_t qn;
   alignas(16) uint8_t mask[TILE * GW_MAX_LEARNERS * GW_N_ACTIONS + 16];
@@ -184,33 +186,72 @@ __device__ __noinline__ void stage_and_store_env(uint8_t* stage, void* obs_base,
   __syncwarp();
 }
 
-// P4: observations + action masks of the tile
+// Special cells of one env's observations, computed by the thread that owns the env (P1b / reset) and parked in
+// shared memory for P4: entry = element offset inside the env's [n_learners, H*W] block | (2 * value) << 9.
+__device__ __forceinline__ void encode_specials(uint16_t* out, int cpo, int n, int nl, int kind, uint32_t cells,
+                                                uint32_t apples_left, uint32_t apple_cells, bool fresh) {
+#pragma unroll
+  for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
+    const bool apple_on = (k < nl) && ((kind == GW_ENV_MULTI) ? ((apples_left >> k) & 1u) : (apples_left & 1u));
+    const uint32_t apple = (kind == GW_ENV_MULTI) ? (apple_cells >> (8 * k)) & 0xFFu : apple_cells & 0xFFu;
+    bool covered = false;
+#pragma unroll
+    for (int i = 0; i < GW_MAX_AGENTS; ++i) {
+      uint32_t enc = 0xFFFFu;
+      if (k < nl && i < n) {
+        const uint32_t c = (cells >> (8 * i)) & 0xFFu;
+        const bool here = apple_on && c == apple;
+        covered |= here;
+        enc = (uint32_t)(k * cpo + (int)c) | ((uint32_t)(2.0f * special_value(kind, fresh, i, k, here)) << 9);
+      }
+      out[k * (GW_MAX_AGENTS + 1) + i] = (uint16_t)enc;
+    }
+    out[k * (GW_MAX_AGENTS + 1) + GW_MAX_AGENTS] =
+        (apple_on && !covered) ? (uint16_t)((uint32_t)(k * cpo + (int)apple) | (18u << 9)) : (uint16_t)0xFFFFu;
+  }
+}
+
+// P4: observations + action masks of the tile.  Per env: lanes 0..9 drop the pre-computed special cells into the
+// warp's staging rows, the rows leave as 128-bit streaming stores (whole lines), the cells are zeroed again.
 template <int THREADS, int TILE, int OBS>
 __device__ __forceinline__ void render_tile(Smem<TILE>& s, const StepParams& p, long long tile_base, int tile_envs) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int NWARPS = THREADS / 32;
   uint8_t* stage = s.stage[warp];
-  for (int el = warp; el < tile_envs; el += NWARPS) {
-    const uint32_t ri = s.rinfo[el];
-    if (ri & R_SKIP) continue;
-    if (p.io.obs != nullptr)
-      stage_and_store_env<OBS>(stage, p.io.obs, tile_base + el, p.H, p.n, p.nl, p.kind, s.cells_new[el], ri & 3u,
-                               p.apple_cells, (ri & R_FRESH) != 0, lane);
-    if ((ri & R_FINAL) && p.io.final_obs != nullptr)      // terminal observation of an env that was just re-spawned
-      stage_and_store_env<OBS>(stage, p.io.final_obs, tile_base + el, p.H, p.n, p.nl, p.kind, s.cells_fin[el],
-                               (ri >> 4) & 3u, p.apple_cells, false, lane);
+  const int cpo = p.H * GW_W;
+  const int V = p.nl * ((OBS == GW_OBS_F32) ? cpo / 4 : cpo / 8);
+  if (p.io.obs != nullptr) {
+    const uint4* src = reinterpret_cast<const uint4*>(stage);
+    for (int el = warp; el < tile_envs; el += NWARPS) {
+      if (s.rinfo[el] & R_SKIP) continue;
+      const uint32_t enc = (lane < N_SPEC) ? (uint32_t)s.spec[el][lane] : 0xFFFFu;
+      const uint32_t off = enc & 0x1FFu;
+      if (enc != 0xFFFFu) {
+        const float v = 0.5f * (float)(enc >> 9);
+        if (OBS == GW_OBS_F32) reinterpret_cast<float*>(stage)[off] = v;
+        else reinterpret_cast<__nv_bfloat16*>(stage)[off] = __float2bfloat16(v);
+      }
+      __syncwarp();
+      uint4* dst = reinterpret_cast<uint4*>(p.io.obs) + (tile_base + el) * (long long)V;
+      for (int v = lane; v < V; v += 32) __stcs(dst + v, src[v]);
+      __syncwarp();
+      if (enc != 0xFFFFu) {
+        if (OBS == GW_OBS_F32) reinterpret_cast<float*>(stage)[off] = 0.0f;
+        else reinterpret_cast<__nv_bfloat16*>(stage)[off] = __float2bfloat16(0.0f);
+      }
+      __syncwarp();
+    }
+  }
+  if (p.io.final_obs != nullptr) {                        // terminal observation of envs that were just re-spawned (rare)
+    for (int el = warp; el < tile_envs; el += NWARPS) {
+      const uint32_t ri = s.rinfo[el];
+      if ((ri & R_FINAL) && !(ri & R_SKIP))
+        stage_and_store_env<OBS>(stage, p.io.final_obs, tile_base + el, p.H, p.n, p.nl, p.kind, s.cells_fin[el],
+                                 (ri >> 4) & 3u, p.apple_cells, false, lane);
+    }
   }
   if (p.io.action_mask != nullptr) {
-    if (tid < tile_envs && !(s.rinfo[tid] & R_SKIP)) {
-#pragma unroll
-      for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
-        if (k >= p.nl) break;
-        const uint32_t m = action_mask_bits(s.rows, p.H, (s.cells_new[tid] >> (8 * k)) & 0xFFu);
-#pragma unroll
-        for (int a = 0; a < GW_N_ACTIONS; ++a) s.mask[(tid * p.nl + k) * GW_N_ACTIONS + a] = (uint8_t)((m >> a) & 1u);
-      }
-    }
-    __syncthreads();
+    __syncthreads();                                       // s.mask was filled by the owner threads
     const int bytes = tile_envs * p.nl * GW_N_ACTIONS;
     int8_t* dst = p.io.action_mask + tile_base * (long long)(p.nl * GW_N_ACTIONS);
     const bool partial = p.reset_mask != nullptr;
@@ -222,6 +263,19 @@ __device__ __forceinline__ void render_tile(Smem<TILE>& s, const StepParams& p, 
       for (int i = tid; i < bytes; i += THREADS)
         if (!partial || !(s.rinfo[i / (p.nl * GW_N_ACTIONS)] & R_SKIP)) dst[i] = (int8_t)s.mask[i];
     }
+  }
+}
+
+// owner thread: action masks of the (new) positions into the tile's staging area (custom/ma_customenv.py:467-506)
+template <int TILE>
+__device__ __forceinline__ void stage_masks(Smem<TILE>& s, const StepParams& p, int tid, uint32_t cells) {
+  if (p.io.action_mask == nullptr) return;
+#pragma unroll
+  for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
+    if (k >= p.nl) break;
+    const uint32_t m = action_mask_bits(s.rows, p.H, (cells >> (8 * k)) & 0xFFu);
+#pragma unroll
+    for (int a = 0; a < GW_N_ACTIONS; ++a) s.mask[(tid * p.nl + k) * GW_N_ACTIONS + a] = (uint8_t)((m >> a) & 1u);
   }
 }
 
@@ -302,13 +356,13 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_reset_kernel(StepP
     const long long e = tile_base + tid;
     if (p.reset_mask != nullptr && p.reset_mask[e] == 0) {
       s.rinfo[tid] = R_SKIP;
-      s.cells_new[tid] = 0;
     } else {
       const uint4 st = p.state[e];
       const uint32_t cells = spawn_cells(p, e, st.z);
       const uint32_t meta = fresh_meta(p, cells);
-      s.cells_new[tid] = cells;
       s.rinfo[tid] = (meta & M_APPLES) | R_FRESH;
+      encode_specials(s.spec[tid], p.H * GW_W, p.n, p.nl, p.kind, cells, meta & M_APPLES, p.apple_cells, true);
+      stage_masks(s, p, tid, cells);
       write_positions(p.io.positions, e, p.n, cells);
       p.state[e] = make_uint4(cells, meta, st.z + 1, 0u);
     }
@@ -419,8 +473,10 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
           for (int k = 0; k < 4; ++k)
             if (k < n && (k == x || manhattan((cells >> (8 * x)) & 0xFFu, (cells >> (8 * k)) & 0xFFu) <= p.fear_radius))
               close |= 1u << k;
+          const uint32_t eff_mdr = make_traj(s.next, (cells >> (8 * x)) & 0xFFu, mx).eff;   // actor plays its MdR
+          if (eff_mdr == ((r.effs >> (4 * x)) & 0xFu)) continue;           // same trajectory (e.g. both blocked): counts equal
           closew |= close << (4 * x);
-          effw |= make_traj(s.next, (cells >> (8 * x)) & 0xFFu, mx).eff << (16 + 4 * x);   // actor plays its MdR
+          effw |= eff_mdr << (16 + 4 * x);
           const uint32_t slot = atomicAdd(&s.qn, (uint32_t)__popc(js));
           uint32_t k2 = 0;
 #pragma unroll
@@ -531,13 +587,15 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
       if (ended && p.auto_reset) {
         const uint32_t cells_sp = spawn_cells(p, e, tick);
         const uint32_t meta_sp = fresh_meta(p, cells_sp);
-        s.cells_new[tid] = cells_sp;
         s.cells_fin[tid] = cells_new;
         s.rinfo[tid] = (meta_sp & M_APPLES) | R_FRESH | R_FINAL | (apples_left << 4);
+        encode_specials(s.spec[tid], p.H * GW_W, n, nl, p.kind, cells_sp, meta_sp & M_APPLES, p.apple_cells, true);
+        stage_masks(s, p, tid, cells_sp);
         p.state[e] = make_uint4(cells_sp, meta_sp, tick + 1, 0u);
       } else {
-        s.cells_new[tid] = cells_new;
         s.rinfo[tid] = apples_left;
+        encode_specials(s.spec[tid], p.H * GW_W, n, nl, p.kind, cells_new, apples_left, p.apple_cells, false);
+        stage_masks(s, p, tid, cells_new);
         p.state[e] = make_uint4(cells_new, meta, tick + 1, ((uint32_t)ret0 & 0xFFFFu) | ((uint32_t)ret1 << 16));
       }
     }
@@ -545,12 +603,10 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
     // ================================================================= P2: counterfactual sims (Responsibility.py:20-54)
     if (FEAR) {
       __syncthreads();
-      const uint32_t n_work = s.qn * 18u;
+      const uint32_t n_work = s.qn * 2u;                 // one thread per (task, actor variant): nine counterfactuals each
       for (uint32_t w = tid; w < n_work; w += THREADS) {
-        const uint32_t tk = s.queue[w / 18u], rr = w % 18u;
-        const uint32_t v = rr / 9u, ap = rr - v * 9u;
+        const uint32_t tk = s.queue[w >> 1], v = w & 1u;
         const uint32_t el = tk & 0xFFu, x = (tk >> 8) & 1u, j = (tk >> 9) & 3u, jc = (tk >> 11) & 1u;
-        if (!jc && ap != 0) continue;                    // affected not in the list: it Stays in all nine sims (:43)
         const uint32_t effw = s.effs[el];
         const uint32_t close = (s.close[el] >> (4 * x)) & 0xFu;
         const uint32_t keep = ((close & 1u) ? 0xFu : 0u) | ((close & 2u) ? 0xF0u : 0u) | ((close & 4u) ? 0xF00u : 0u) |
@@ -561,11 +617,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
         g.didx_lo = s.geom_lo[el];
         g.didx_hi = s.geom_hi[el] & 0xFFFFu;
         g.near6 = s.geom_hi[el] >> 16;
-        // affected tries action ap (:34-39); outside the list its action cannot be swapped in and it Stays
-        if (counterfactual_valid(s.lut, s.next, s.cells_old[el], eo, g, (int)j, jc ? ap : 0u)) {
-          const uint32_t jslot = j - (j > x ? 1u : 0u);
-          atomicAdd(&s.cnt[el * 2 + x], (jc ? 1u : 9u) << (4 * (jslot * 2 + v)));
-        }
+        const uint32_t cnt = count_valid_moves(s.lut, s.next, s.cells_old[el], eo, g, (int)j, jc != 0);
+        const uint32_t jslot = j - (j > x ? 1u : 0u);
+        atomicAdd(&s.cnt[el * 2 + x], cnt << (4 * (jslot * 2 + v)));
       }
       __syncthreads();
     }
@@ -711,20 +765,19 @@ __global__ void __launch_bounds__(128) gw_fear_kernel(const Tables* T, int n_def
   for (int k = 0; k < 4; ++k)
     if (k < n && ((lst >> k) & 1u))
       base |= make_traj(s.next, (cells >> (8 * k)) & 0xFFu, (acts >> (4 * k)) & 0xFu).eff << (4 * k);
-  const int js = lane / 9, ap = lane - js * 9;
+  const int js = lane >> 1, v = lane & 1;                // lanes 0..5 = (affected slot, actor plays MdR / its action)
   const int j = js + (js >= x ? 1 : 0);
-  const bool lane_on = lane < 27 && j < n;
-  uint32_t packed = 0;
-#pragma unroll
-  for (int v = 0; v < 2; ++v) {
+  uint32_t my = 0;
+  if (lane < 6 && j < n) {
     const uint32_t av = v == 0 ? (uint32_t)min(max((int)mdr[c * 4 + x], 0), 8) : ((acts >> (4 * x)) & 0xFu);
     const uint32_t eo = (base & ~(0xFu << (4 * x))) | (make_traj(s.next, (cells >> (8 * x)) & 0xFFu, av).eff << (4 * x));
-    bool valid = false;
-    if (lane_on)                                       // SwapActionIDs4Agents only touches agents present in the list
-      valid = counterfactual_valid(s.lut, s.next, cells, eo, g, j, ((lst >> j) & 1u) ? (uint32_t)ap : 0u);
-    const uint32_t b = __ballot_sync(0xFFFFFFFFu, valid);
+    my = count_valid_moves(s.lut, s.next, cells, eo, g, j, ((lst >> j) & 1u) != 0);   // SwapActionIDs4Agents: listed agents only
+  }
+  uint32_t packed = 0;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) packed |= (uint32_t)__popc(b & (0x1FFu << (9 * q))) << (16 * v + 4 * q);
+  for (int q = 0; q < 3; ++q) {
+    packed |= (uint32_t)__shfl_sync(0xFFFFFFFFu, my, 2 * q) << (4 * q);
+    packed |= (uint32_t)__shfl_sync(0xFFFFFFFFu, my, 2 * q + 1) << (16 + 4 * q);
   }
   if (lane < 4) {
     double rv = 0.0;
