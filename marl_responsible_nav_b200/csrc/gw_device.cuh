@@ -311,16 +311,17 @@ __device__ __forceinline__ uint32_t pairs_of_agent(int j) {
 // everybody else, agents outside the list already 0 (Stay, :43).  in_list = false: j is not in the list, its action
 // cannot be swapped in, so all nine simulations are the same one (j Stays) and the count is 0 or 9.
 // The pair masks that do not involve j are looked up once; per action only the <= 3 pairs of j change.
+// a_begin/a_end: sub-range of the nine actions (small batches split a list over nine threads for latency).
 __device__ __forceinline__ uint32_t count_valid_moves(const uint8_t* __restrict__ s_lut, const uint8_t* __restrict__ s_next,
                                                       uint32_t cells, uint32_t eff_others, const PairGeom& g, int j,
-                                                      bool in_list) {
+                                                      bool in_list, uint32_t a_begin = 0, uint32_t a_end = GW_N_ACTIONS) {
   const uint32_t pj = pairs_of_agent(j);
   const uint32_t eo = eff_others & ~(0xFu << (4 * j));
   const uint32_t nn_fixed = nn_masks(s_lut, g, eo, 0x3Fu & ~pj);
   const uint32_t cell_j = (cells >> (8 * j)) & 0xFFu;
   uint32_t count = 0;
-  const uint32_t n_try = in_list ? (uint32_t)GW_N_ACTIONS : 1u;
-  for (uint32_t a = 0; a < n_try; ++a) {
+  if (!in_list) { if (a_begin != 0) return 0; a_end = 1; }
+  for (uint32_t a = a_begin; a < a_end; ++a) {
     const Traj tj = make_traj(s_next, cell_j, a);
     if (tj.r1 | tj.r2) continue;            // restricted, or crashed before the blocked second move: invalid either way
     const uint32_t effp = eo | (tj.eff << (4 * j));

@@ -584,28 +584,32 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
       ret0 += (int)lrint(reward[0] * unit);
       ret1 += (int)lrint(reward[1] * unit);
       stat_bits = (ended ? 1u : 0u) | (crash_count << 1) | (apples_rewarded << 3);
+      uint32_t cells_r = cells_new, apples_r = apples_left, rflags = 0;
+      uint4 st_out = make_uint4(cells_new, meta, tick + 1, ((uint32_t)ret0 & 0xFFFFu) | ((uint32_t)ret1 << 16));
       if (ended && p.auto_reset) {
-        const uint32_t cells_sp = spawn_cells(p, e, tick);
-        const uint32_t meta_sp = fresh_meta(p, cells_sp);
+        cells_r = spawn_cells(p, e, tick);
+        const uint32_t meta_sp = fresh_meta(p, cells_r);
+        apples_r = meta_sp & M_APPLES;
+        rflags = R_FRESH | R_FINAL | (apples_left << 4);
         s.cells_fin[tid] = cells_new;
-        s.rinfo[tid] = (meta_sp & M_APPLES) | R_FRESH | R_FINAL | (apples_left << 4);
-        encode_specials(s.spec[tid], p.H * GW_W, n, nl, p.kind, cells_sp, meta_sp & M_APPLES, p.apple_cells, true);
-        stage_masks(s, p, tid, cells_sp);
-        p.state[e] = make_uint4(cells_sp, meta_sp, tick + 1, 0u);
-      } else {
-        s.rinfo[tid] = apples_left;
-        encode_specials(s.spec[tid], p.H * GW_W, n, nl, p.kind, cells_new, apples_left, p.apple_cells, false);
-        stage_masks(s, p, tid, cells_new);
-        p.state[e] = make_uint4(cells_new, meta, tick + 1, ((uint32_t)ret0 & 0xFFFFu) | ((uint32_t)ret1 << 16));
+        st_out = make_uint4(cells_r, meta_sp, tick + 1, 0u);
       }
+      p.state[e] = st_out;
+      s.rinfo[tid] = apples_r | rflags;
+      encode_specials(s.spec[tid], p.H * GW_W, n, nl, p.kind, cells_r, apples_r, p.apple_cells, (rflags & R_FRESH) != 0);
+      stage_masks(s, p, tid, cells_r);
     }
 
     // ================================================================= P2: counterfactual sims (Responsibility.py:20-54)
     if (FEAR) {
       __syncthreads();
-      const uint32_t n_work = s.qn * 2u;                 // one thread per (task, actor variant): nine counterfactuals each
+      // large tiles: one thread per (task, actor variant) runs the nine counterfactuals and shares the pair masks that
+      // do not involve the affected agent; small tiles (few envs per SM, latency-bound): one thread per counterfactual
+      constexpr uint32_t SPLIT = (TILE <= 32) ? 9u : 1u;
+      const uint32_t n_work = s.qn * 2u * SPLIT;
       for (uint32_t w = tid; w < n_work; w += THREADS) {
-        const uint32_t tk = s.queue[w >> 1], v = w & 1u;
+        const uint32_t ht = w / SPLIT, a0 = w - ht * SPLIT;
+        const uint32_t tk = s.queue[ht >> 1], v = ht & 1u;
         const uint32_t el = tk & 0xFFu, x = (tk >> 8) & 1u, j = (tk >> 9) & 3u, jc = (tk >> 11) & 1u;
         const uint32_t effw = s.effs[el];
         const uint32_t close = (s.close[el] >> (4 * x)) & 0xFu;
@@ -617,9 +621,10 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
         g.didx_lo = s.geom_lo[el];
         g.didx_hi = s.geom_hi[el] & 0xFFFFu;
         g.near6 = s.geom_hi[el] >> 16;
-        const uint32_t cnt = count_valid_moves(s.lut, s.next, s.cells_old[el], eo, g, (int)j, jc != 0);
+        const uint32_t cnt = (SPLIT == 1u) ? count_valid_moves(s.lut, s.next, s.cells_old[el], eo, g, (int)j, jc != 0)
+                                           : count_valid_moves(s.lut, s.next, s.cells_old[el], eo, g, (int)j, jc != 0, a0, a0 + 1);
         const uint32_t jslot = j - (j > x ? 1u : 0u);
-        atomicAdd(&s.cnt[el * 2 + x], cnt << (4 * (jslot * 2 + v)));
+        if (cnt) atomicAdd(&s.cnt[el * 2 + x], cnt << (4 * (jslot * 2 + v)));
       }
       __syncthreads();
     }
