@@ -28,13 +28,17 @@ constexpr int N_EFF = 13;
 constexpr int LUT_DELTAS = 81;                      // (dr + 4) * 9 + (dc + 4)
 constexpr int LUT_BYTES = LUT_DELTAS * N_EFF * N_EFF;   // 13689
 
-struct Tables {                         // device-global, read-only, built by gw_create
-  uint8_t pair_lut[LUT_BYTES + 7];      // [delta][eff_i][eff_j] -> 4-bit sub-step hit mask
-  uint8_t next_cell[GW_MAX_H * GW_W * 4];       // [cell][dir Up,Down,Left,Right] -> cell after the move (same cell if blocked)
+struct SmallTables {                    // per-step lookups, copied to shared memory by every CTA (1792 B)
+  alignas(16) uint32_t policy_thr[GW_MAX_POLICIES][2][8];   // 31-bit cdf thresholds, [policy][perturbed][k]
   uint8_t mdr_map[GW_MAX_H * GW_W];
   uint8_t policy_map[GW_MAX_H * GW_W];
-  uint32_t policy_thr[GW_MAX_POLICIES][2][8];   // 31-bit cdf thresholds, [policy][perturbed][k]
   uint8_t active_cell[GW_MAX_H * GW_W];         // row-major list of active cells (np.where order)
+};
+
+struct Tables {                         // device-global, read-only, built by gw_create
+  alignas(16) uint8_t pair_lut[LUT_BYTES + 7];      // [delta][eff_i][eff_j] -> 4-bit sub-step hit mask
+  alignas(16) uint8_t next_cell[GW_MAX_H * GW_W * 4];       // [cell][dir Up,Down,Left,Right] -> cell after the move (same cell if blocked)
+  SmallTables small;
   uint16_t map_rows[GW_MAX_H];
   int32_t n_active;
   int32_t pad_;

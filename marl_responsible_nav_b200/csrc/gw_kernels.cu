@@ -38,7 +38,7 @@ struct StepParams {
   gw_io io;
   long long E;
   long long env_id_base;
-  int n, nl, kind, H, fear_radius, max_steps, auto_reset;
+  int n, nl, kind, H, fear_radius, max_steps, auto_reset, n_active;
   uint32_t apple_cells, apple_init;   // 2 x 8-bit cells, initial apples-left bits
   uint32_t perturb_thr;               // P(perturb) * 2^32
   uint32_t seed_lo, seed_hi;
@@ -55,10 +55,11 @@ constexpr uint32_t R_FRESH = 1u << 2, R_FINAL = 1u << 3, R_SKIP = 1u << 6;   // 
 constexpr int STAGE_BYTES_FWD = GW_MAX_LEARNERS * GW_MAX_H * GW_W * 4;
 constexpr int N_SPEC = GW_MAX_LEARNERS * (GW_MAX_AGENTS + 1);   // per learner: every agent + the own apple
 
-template <int TILE, int NWARPS = (TILE >= 256 ? 8 : 4)>
+template <int TILE, int NWARPS = (TILE == 128 ? 4 : 8)>
 struct Smem {
   alignas(16) uint8_t lut[(LUT_BYTES + 15) / 16 * 16];
   alignas(16) uint8_t next[GW_MAX_H * GW_W * 4];
+  alignas(16) SmallTables small;
   alignas(16) uint4 tmpl[64];
   uint16_t rows[GW_MAX_H];
   uint32_t cells_old[TILE], effs[TILE], geom_lo[TILE], geom_hi[TILE], close[TILE];
@@ -88,6 +89,8 @@ __device__ __forceinline__ void load_tables(Smem<TILE>& s, const Tables* __restr
     for (int i = tid; i < (LUT_BYTES + 15) / 16; i += THREADS) cp_async16(s.lut + 16 * i, T->pair_lut + 16 * i);
     for (int i = tid; i < GW_MAX_H * GW_W * 4 / 16; i += THREADS) cp_async16(s.next + 16 * i, T->next_cell + 16 * i);
   }
+  for (int i = tid; i < (int)sizeof(SmallTables) / 16; i += THREADS)
+    cp_async16(reinterpret_cast<uint8_t*>(&s.small) + 16 * i, reinterpret_cast<const uint8_t*>(&T->small) + 16 * i);
   if (tid < GW_MAX_H) s.rows[tid] = T->map_rows[tid];
   // constant observation template: -1 inactive / 0 active (WorldState reset, grid_world.py:433-434)
   const int Q = (OBS == GW_OBS_F32) ? H * 4 : H * 2;
@@ -282,7 +285,7 @@ __device__ __forceinline__ void stage_masks(Smem<TILE>& s, const StepParams& p, 
 // ------------------------------------------------------------------ spawn
 // setup_env, custom/ma_customenv.py:372-380: a sorted n-subset of the active cells (row-major order).
 // Replay mode reads the recorded cells; native mode draws them from Philox (uniform over subsets).
-__device__ __forceinline__ uint32_t spawn_cells(const StepParams& p, long long e, uint32_t tick) {
+__device__ __forceinline__ uint32_t spawn_cells(const StepParams& p, const SmallTables& st, long long e, uint32_t tick) {
   uint32_t cells = 0;
   if (p.io.spawn != nullptr) {
     for (int i = 0; i < p.n; ++i) {
@@ -295,7 +298,7 @@ __device__ __forceinline__ uint32_t spawn_cells(const StepParams& p, long long e
   uint32_t w[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), tick, 0x100u};
   philox4x32(w, p.seed_lo, p.seed_hi);
   uint32_t chosen = 0;                       // up to 4 sorted indices, 8 bits each
-  const int na = p.tables->n_active;
+  const int na = p.n_active;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (k >= p.n) break;
@@ -309,7 +312,7 @@ __device__ __forceinline__ uint32_t spawn_cells(const StepParams& p, long long e
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
-    if (i < p.n) cells |= (uint32_t)__ldg(&p.tables->active_cell[(chosen >> (8 * i)) & 0xFFu]) << (8 * i);
+    if (i < p.n) cells |= (uint32_t)st.active_cell[(chosen >> (8 * i)) & 0xFFu] << (8 * i);
   return cells;
 }
 
@@ -348,6 +351,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_reset_kernel(StepP
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
   load_tables<THREADS, TILE, OBS>(s, p.tables, p.H, false);
+  cp_async_wait_all();
   __syncthreads();
   const long long tile_base = (long long)blockIdx.x * TILE;
   const int tile_envs = (int)min((long long)TILE, p.E - tile_base);
@@ -358,7 +362,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_reset_kernel(StepP
       s.rinfo[tid] = R_SKIP;
     } else {
       const uint4 st = p.state[e];
-      const uint32_t cells = spawn_cells(p, e, st.z);
+      const uint32_t cells = spawn_cells(p, s.small, e, st.z);
       const uint32_t meta = fresh_meta(p, cells);
       s.rinfo[tid] = (meta & M_APPLES) | R_FRESH;
       encode_specials(s.spec[tid], p.H * GW_W, p.n, p.nl, p.kind, cells, meta & M_APPLES, p.apple_cells, true);
@@ -397,44 +401,29 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
     int ret0 = 0, ret1 = 0;
     uint4 st = make_uint4(0, 0, 0, 0);
     uint32_t acts = 0, mdrs = 0;
+    uint32_t rw[4] = {0, 0, 0, 0}, rw2[4] = {0, 0, 0, 0};
 
     // ================================================================= P1a: loads and RNG (no shared tables needed)
     if (tid == 0) s.qn = 0;
     if (own) {
       st = p.state[e];
-      const uint32_t cells = st.x;
       const uint32_t tick = st.z;
-      // ---- setup_step (ma_customenv.py:432-452)
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (i < n) mdrs |= (uint32_t)__ldg(&T->mdr_map[(cells >> (8 * i)) & 0xFFu]) << (4 * i);   // :445-447
+      // ---- setup_step (ma_customenv.py:432-452): learner actions (:239-242), recorded NPC draws or Philox words
 #pragma unroll
       for (int k = 0; k < GW_MAX_LEARNERS; ++k)
-        if (k < nl) acts |= (uint32_t)min(max((int)p.io.learner_actions[e * nl + k], 0), 8) << (4 * k);   // :239-242
+        if (k < nl) acts |= (uint32_t)min(max((int)p.io.learner_actions[e * nl + k], 0), 8) << (4 * k);
       if (p.io.npc_actions != nullptr) {
 #pragma unroll
         for (int i = 1; i < 4; ++i)
           if (i >= nl && i < n) acts |= (uint32_t)min(max((int)p.io.npc_actions[e * n + i], 0), 8) << (4 * i);
       } else {
+        // NPC number m = i - n_learners uses Philox call m/2 (counter = global env id, tick, call), words 2(m%2), 2(m%2)+1
         const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
-        uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int i = 1; i < 4; ++i) {
-          if (i < nl || i >= n) continue;
-          const int m = i - nl;                                            // NPC index: Philox call m/2, words 2(m%2), 2(m%2)+1
-          if ((m & 1) == 0) {
-            w[0] = (uint32_t)gid; w[1] = (uint32_t)(gid >> 32); w[2] = tick; w[3] = (uint32_t)(m >> 1);
-            philox4x32(w, p.seed_lo, p.seed_hi);
-          }
-          const uint32_t wa = (m & 1) ? w[2] : w[0], wb = (m & 1) ? w[3] : w[1];
-          const int pert = wa < p.perturb_thr ? 1 : 0;                     // random.random() < 0.25 (:441)
-          const uint32_t c = (cells >> (8 * i)) & 0xFFu;
-          const uint4* thr4 = reinterpret_cast<const uint4*>(T->policy_thr[__ldg(&T->policy_map[c])][pert]);
-          const uint4 t0 = __ldg(thr4), t1 = __ldg(thr4 + 1);
-          const uint32_t u = wb >> 1;
-          const uint32_t a = (u >= t0.x) + (u >= t0.y) + (u >= t0.z) + (u >= t0.w) + (u >= t1.x) + (u >= t1.y) +
-                             (u >= t1.z) + (u >= t1.w);                    // np.random.choice(9, p) (custom_agent.py:31)
-          acts |= a << (4 * i);
+        rw[0] = (uint32_t)gid; rw[1] = (uint32_t)(gid >> 32); rw[2] = tick; rw[3] = 0u;
+        philox4x32(rw, p.seed_lo, p.seed_hi);
+        if (n - nl > 2) {
+          rw2[0] = (uint32_t)gid; rw2[1] = (uint32_t)(gid >> 32); rw2[2] = tick; rw2[3] = 1u;
+          philox4x32(rw2, p.seed_lo, p.seed_hi);
         }
       }
     }
@@ -449,6 +438,26 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
       const uint32_t cells = st.x;
       uint32_t meta = st.y;
       const uint32_t tick = st.z;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < n) mdrs |= (uint32_t)s.small.mdr_map[(cells >> (8 * i)) & 0xFFu] << (4 * i);   // :445-447
+      if (p.io.npc_actions == nullptr) {
+#pragma unroll
+        for (int i = 1; i < 4; ++i) {
+          if (i < nl || i >= n) continue;
+          const int m = i - nl;
+          const uint32_t wa = m == 0 ? rw[0] : (m == 1 ? rw[2] : rw2[0]);
+          const uint32_t wb = m == 0 ? rw[1] : (m == 1 ? rw[3] : rw2[1]);
+          const int pert = wa < p.perturb_thr ? 1 : 0;                     // random.random() < 0.25 (:441)
+          const uint32_t c = (cells >> (8 * i)) & 0xFFu;
+          const uint4* thr4 = reinterpret_cast<const uint4*>(s.small.policy_thr[s.small.policy_map[c]][pert]);
+          const uint4 t0 = thr4[0], t1 = thr4[1];
+          const uint32_t u = wb >> 1;
+          const uint32_t a = (u >= t0.x) + (u >= t0.y) + (u >= t0.z) + (u >= t0.w) + (u >= t1.x) + (u >= t1.y) +
+                             (u >= t1.z) + (u >= t1.w);                    // np.random.choice(9, p) (custom_agent.py:31)
+          acts |= a << (4 * i);
+        }
+      }
       const PairGeom g = pair_geometry(n, cells);
 
       // ---- the real update (ma_customenv.py:254)
@@ -587,7 +596,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
       uint32_t cells_r = cells_new, apples_r = apples_left, rflags = 0;
       uint4 st_out = make_uint4(cells_new, meta, tick + 1, ((uint32_t)ret0 & 0xFFFFu) | ((uint32_t)ret1 << 16));
       if (ended && p.auto_reset) {
-        cells_r = spawn_cells(p, e, tick);
+        cells_r = spawn_cells(p, s.small, e, tick);
         const uint32_t meta_sp = fresh_meta(p, cells_r);
         apples_r = meta_sp & M_APPLES;
         rflags = R_FRESH | R_FINAL | (apples_left << 4);
@@ -809,6 +818,7 @@ struct gw_handle {
   unsigned long long* d_stats = nullptr;
   bool reset_done = false;
   int sm_count = 148;
+  int n_active = 0;
   uint64_t launches = 0;
   uint64_t env_steps = 0;
   std::string err;
@@ -1003,17 +1013,18 @@ int gw_create(const gw_config* cfg, gw_handle** out) {
   gw::Tables* t = new gw::Tables();
   std::memset(t, 0, sizeof(*t));
   std::memcpy(t->map_rows, cfg->map_rows, sizeof(t->map_rows));
-  std::memcpy(t->mdr_map, cfg->mdr_map, sizeof(t->mdr_map));
-  std::memcpy(t->policy_map, cfg->policy_map, sizeof(t->policy_map));
+  std::memcpy(t->small.mdr_map, cfg->mdr_map, sizeof(t->small.mdr_map));
+  std::memcpy(t->small.policy_map, cfg->policy_map, sizeof(t->small.policy_map));
   for (int p = 0; p < cfg->n_policies; ++p) {
-    policy_thresholds(cfg->step_weights[p], cfg->dir_weights[p], false, t->policy_thr[p][0]);
-    policy_thresholds(cfg->step_weights[p], cfg->dir_weights[p], true, t->policy_thr[p][1]);
+    policy_thresholds(cfg->step_weights[p], cfg->dir_weights[p], false, t->small.policy_thr[p][0]);
+    policy_thresholds(cfg->step_weights[p], cfg->dir_weights[p], true, t->small.policy_thr[p][1]);
   }
   int na = 0;
   for (int r = 0; r < cfg->height; ++r)
     for (int c = 0; c < cfg->width; ++c)
-      if ((cfg->map_rows[r] >> c) & 1) t->active_cell[na++] = (uint8_t)((r << 4) | c);
+      if ((cfg->map_rows[r] >> c) & 1) t->small.active_cell[na++] = (uint8_t)((r << 4) | c);
   t->n_active = na;
+  h->n_active = na;
   build_next_cell(cfg, t->next_cell);
   build_pair_lut(t->pair_lut);
   for (int m = 0; m < 10; ++m)
@@ -1056,6 +1067,7 @@ static gw::StepParams make_params(gw_handle* h, const gw_io* io) {
   p.env_id_base = c.env_id_base;
   p.n = c.n_agents; p.nl = c.n_learners; p.kind = c.env_kind; p.H = c.height;
   p.fear_radius = c.fear_radius; p.max_steps = c.max_steps; p.auto_reset = c.auto_reset;
+  p.n_active = h->n_active;
   for (int k = 0; k < c.n_learners; ++k)
     if (c.apple_row[k] >= 0) {
       p.apple_cells |= (uint32_t)((c.apple_row[k] << 4) | c.apple_col[k]) << (8 * k);
@@ -1133,7 +1145,7 @@ int gw_reset(gw_handle* h, const uint8_t* reset_mask, const gw_io* io, void* str
   const int tile = pick_tile(h->cfg.num_envs);
   const unsigned blocks = (unsigned)((h->cfg.num_envs + tile - 1) / tile);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (tile == 32) launch_reset_t<128, 32>(h->cfg, p, blocks, s);
+  if (tile == 32) launch_reset_t<256, 32>(h->cfg, p, blocks, s);
   else if (tile == 128) launch_reset_t<128, 128>(h->cfg, p, blocks, s);
   else launch_reset_t<256, 256>(h->cfg, p, blocks, s);
   GW_CUDA(h, cudaGetLastError());
@@ -1154,7 +1166,7 @@ int gw_step(gw_handle* h, const gw_io* io, void* stream) {
   const long long resident = (long long)h->sm_count * (tile == 256 ? 4 : 8);
   const unsigned blocks = (unsigned)(n_tiles < resident ? n_tiles : resident);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (tile == 32) launch_step_t<128, 32>(h->cfg, p, blocks, s);
+  if (tile == 32) launch_step_t<256, 32>(h->cfg, p, blocks, s);
   else if (tile == 128) launch_step_t<128, 128>(h->cfg, p, blocks, s);
   else launch_step_t<256, 256>(h->cfg, p, blocks, s);
   GW_CUDA(h, cudaGetLastError());
