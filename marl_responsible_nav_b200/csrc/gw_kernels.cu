@@ -55,7 +55,7 @@ constexpr uint32_t R_FRESH = 1u << 2, R_FINAL = 1u << 3, R_SKIP = 1u << 6;   // 
 constexpr int STAGE_BYTES_FWD = GW_MAX_LEARNERS * GW_MAX_H * GW_W * 4;
 constexpr int N_SPEC = GW_MAX_LEARNERS * (GW_MAX_AGENTS + 1);   // per learner: every agent + the own apple
 
-template <int TILE, int NWARPS = (TILE == 128 ? 4 : 8)>
+template <int TILE, int NWARPS = 8>
 struct Smem {
   alignas(16) uint8_t lut[(LUT_BYTES + 15) / 16 * 16];
   alignas(16) uint8_t next[GW_MAX_H * GW_W * 4];
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_reset_kernel(StepP
 
 // ------------------------------------------------------------------ step kernel
 // Persistent CTAs: the grid is sized to the machine and each CTA walks tiles blockIdx.x, +gridDim.x, ...
-template <int THREADS, int TILE, bool FEAR, int OBS>
+template <int THREADS, int TILE, int SPLIT_, bool FEAR, int OBS>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
@@ -612,9 +612,10 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
     // ================================================================= P2: counterfactual sims (Responsibility.py:20-54)
     if (FEAR) {
       __syncthreads();
-      // large tiles: one thread per (task, actor variant) runs the nine counterfactuals and shares the pair masks that
-      // do not involve the affected agent; small tiles (few envs per SM, latency-bound): one thread per counterfactual
-      constexpr uint32_t SPLIT = (TILE <= 32) ? 9u : 1u;
+      // One thread per (task, actor variant, 9/SPLIT actions of the affected agent).  SPLIT = 1 shares the pair masks that
+      // do not involve the affected agent across its nine actions (throughput: many resident CTAs); SPLIT = 9 gives one
+      // thread per counterfactual (latency: few envs per SM).  The host picks by how many tiles each SM gets.
+      constexpr uint32_t SPLIT = (uint32_t)SPLIT_;
       const uint32_t n_work = s.qn * 2u * SPLIT;
       for (uint32_t w = tid; w < n_work; w += THREADS) {
         const uint32_t ht = w / SPLIT, a0 = w - ht * SPLIT;
@@ -630,8 +631,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
         g.didx_lo = s.geom_lo[el];
         g.didx_hi = s.geom_hi[el] & 0xFFFFu;
         g.near6 = s.geom_hi[el] >> 16;
+        constexpr uint32_t PER = 9u / SPLIT;
         const uint32_t cnt = (SPLIT == 1u) ? count_valid_moves(s.lut, s.next, s.cells_old[el], eo, g, (int)j, jc != 0)
-                                           : count_valid_moves(s.lut, s.next, s.cells_old[el], eo, g, (int)j, jc != 0, a0, a0 + 1);
+                                           : count_valid_moves(s.lut, s.next, s.cells_old[el], eo, g, (int)j, jc != 0, a0 * PER, a0 * PER + PER);
         const uint32_t jslot = j - (j > x ? 1u : 0u);
         if (cnt) atomicAdd(&s.cnt[el * 2 + x], cnt << (4 * (jslot * 2 + v)));
       }
@@ -1094,16 +1096,25 @@ static int check_io(gw_handle* h, const gw_io* io, bool step) {
 
 }  // extern "C" (templates below need C++ linkage)
 
-// Tile selection: small batches use 32-env tiles so that every SM gets work (E = 4096 -> 128 CTAs); large batches use
-// 256-env tiles so that the per-CTA table load is amortised.  GW_TILE=32|128|256 overrides (experiments).
+// Launch shape.  Small batches are latency-bound: 32-env tiles put work on every SM (E = 4096 -> 128 CTAs) and every
+// counterfactual gets its own thread.  Large batches are throughput-bound: 256-env tiles amortise the per-CTA table
+// load and a thread runs the nine counterfactuals of an action list.  GW_TILE=32|256 and GW_SPLIT=1|3|9 override.
 static int pick_tile(long long E) {
   if (const char* s = std::getenv("GW_TILE")) {
     const int v = std::atoi(s);
-    if (v == 32 || v == 128 || v == 256) return v;
+    if (v == 32 || v == 256) return v;
   }
-  if (E <= 32LL * 148 * 3) return 32;
-  if (E <= 128LL * 148 * 6) return 128;
-  return 256;
+  return E <= 32768 ? 32 : 256;
+}
+
+static int pick_split(long long n_tiles, int sm_count, int tile) {
+  if (const char* s = std::getenv("GW_SPLIT")) {
+    const int v = std::atoi(s);
+    if (v == 1 || v == 3 || v == 9) return v;
+  }
+  if (tile == 32) return 9;
+  const long long per_sm = (n_tiles + sm_count - 1) / sm_count;
+  return per_sm <= 2 ? 9 : (per_sm <= 4 ? 3 : 1);
 }
 
 template <typename K>
@@ -1113,16 +1124,16 @@ static void launch_k(K kernel, const gw::StepParams& p, unsigned blocks, int thr
   kernel<<<blocks, threads, smem, s>>>(p);
 }
 
-template <int THREADS, int TILE>
+template <int THREADS, int TILE, int SPLIT>
 static void launch_step_t(const gw_config& c, const gw::StepParams& p, unsigned blocks, cudaStream_t s) {
   const bool f32 = c.obs_dtype == GW_OBS_F32;
   const size_t smem = sizeof(gw::Smem<TILE>);
   if (c.fear) {
-    if (f32) launch_k(gw::gw_step_kernel<THREADS, TILE, true, GW_OBS_F32>, p, blocks, THREADS, smem, s);
-    else launch_k(gw::gw_step_kernel<THREADS, TILE, true, GW_OBS_BF16>, p, blocks, THREADS, smem, s);
+    if (f32) launch_k(gw::gw_step_kernel<THREADS, TILE, SPLIT, true, GW_OBS_F32>, p, blocks, THREADS, smem, s);
+    else launch_k(gw::gw_step_kernel<THREADS, TILE, SPLIT, true, GW_OBS_BF16>, p, blocks, THREADS, smem, s);
   } else {
-    if (f32) launch_k(gw::gw_step_kernel<THREADS, TILE, false, GW_OBS_F32>, p, blocks, THREADS, smem, s);
-    else launch_k(gw::gw_step_kernel<THREADS, TILE, false, GW_OBS_BF16>, p, blocks, THREADS, smem, s);
+    if (f32) launch_k(gw::gw_step_kernel<THREADS, TILE, 1, false, GW_OBS_F32>, p, blocks, THREADS, smem, s);
+    else launch_k(gw::gw_step_kernel<THREADS, TILE, 1, false, GW_OBS_BF16>, p, blocks, THREADS, smem, s);
   }
 }
 
@@ -1146,7 +1157,6 @@ int gw_reset(gw_handle* h, const uint8_t* reset_mask, const gw_io* io, void* str
   const unsigned blocks = (unsigned)((h->cfg.num_envs + tile - 1) / tile);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (tile == 32) launch_reset_t<256, 32>(h->cfg, p, blocks, s);
-  else if (tile == 128) launch_reset_t<128, 128>(h->cfg, p, blocks, s);
   else launch_reset_t<256, 256>(h->cfg, p, blocks, s);
   GW_CUDA(h, cudaGetLastError());
   h->reset_done = true;
@@ -1163,12 +1173,14 @@ int gw_step(gw_handle* h, const gw_io* io, void* stream) {
   const int tile = pick_tile(h->cfg.num_envs);
   const long long n_tiles = (h->cfg.num_envs + tile - 1) / tile;
   // persistent CTAs: at most `sm_count x resident CTAs per SM`, each walks several tiles and loads the tables once
-  const long long resident = (long long)h->sm_count * (tile == 256 ? 4 : 8);
+  const long long resident = (long long)h->sm_count * 4;
   const unsigned blocks = (unsigned)(n_tiles < resident ? n_tiles : resident);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (tile == 32) launch_step_t<256, 32>(h->cfg, p, blocks, s);
-  else if (tile == 128) launch_step_t<128, 128>(h->cfg, p, blocks, s);
-  else launch_step_t<256, 256>(h->cfg, p, blocks, s);
+  const int split = pick_split(n_tiles, h->sm_count, tile);
+  if (tile == 32) launch_step_t<256, 32, 9>(h->cfg, p, blocks, s);
+  else if (split == 9) launch_step_t<256, 256, 9>(h->cfg, p, blocks, s);
+  else if (split == 3) launch_step_t<256, 256, 3>(h->cfg, p, blocks, s);
+  else launch_step_t<256, 256, 1>(h->cfg, p, blocks, s);
   GW_CUDA(h, cudaGetLastError());
   h->launches += 1;
   h->env_steps += (uint64_t)h->cfg.num_envs;
