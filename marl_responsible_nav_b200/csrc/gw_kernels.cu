@@ -1114,7 +1114,7 @@ static int pick_split(long long n_tiles, int sm_count, int tile) {
   }
   if (tile == 32) return 9;
   const long long per_sm = (n_tiles + sm_count - 1) / sm_count;
-  return per_sm <= 2 ? 9 : (per_sm <= 4 ? 3 : 1);
+  return per_sm <= 2 ? 9 : (per_sm <= 8 ? 3 : 1);
 }
 
 template <typename K>
