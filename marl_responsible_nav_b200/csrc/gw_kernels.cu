@@ -69,7 +69,7 @@ struct Smem {
   uint16_t queue[TILE * 6];
   uint32_t qn;
   alignas(16) uint8_t mask[TILE * GW_MAX_LEARNERS * GW_N_ACTIONS + 16];
-  alignas(16) uint8_t stage[NWARPS][STAGE_BYTES_FWD];   // per-warp observation staging rows (template + patches)
+  alignas(16) uint8_t stage[NWARPS][2][STAGE_BYTES_FWD];   // per-warp observation staging rows (template + patches)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -113,7 +113,10 @@ __device__ __forceinline__ void load_tables(Smem<TILE>& s, const Tables* __restr
     }
     s.tmpl[q] = make_uint4(w[0], w[1], w[2], w[3]);
     for (int wq = 0; wq < THREADS / 32; ++wq)
-      for (int k = 0; k < GW_MAX_LEARNERS; ++k) reinterpret_cast<uint4*>(s.stage[wq])[k * Q + q] = make_uint4(w[0], w[1], w[2], w[3]);
+      for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
+        reinterpret_cast<uint4*>(s.stage[wq][0])[k * Q + q] = make_uint4(w[0], w[1], w[2], w[3]);
+        reinterpret_cast<uint4*>(s.stage[wq][1])[k * Q + q] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
   }
 }
 
@@ -214,42 +217,57 @@ __device__ __forceinline__ void encode_specials(uint16_t* out, int cpo, int n, i
   }
 }
 
-// P4: observations + action masks of the tile.  Per env: lanes 0..9 drop the pre-computed special cells into the
-// warp's staging rows, the rows leave as 128-bit streaming stores (whole lines), the cells are zeroed again.
+// P4: observations + action masks of the tile.  Each warp owns two staging rows that hold the constant template.
+// Per env: lanes 0..9 drop the pre-computed special cells into row A, one __syncwarp, the cells patched into row B
+// for the previous env are zeroed again (agents and apples only stand on active cells, whose template value is 0),
+// and row A leaves as 128-bit streaming stores: whole 128-byte lines, never a partial sector.  Rows alternate.
 template <int THREADS, int TILE, int OBS>
 __device__ __forceinline__ void render_tile(Smem<TILE>& s, const StepParams& p, long long tile_base, int tile_envs) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int NWARPS = THREADS / 32;
-  uint8_t* stage = s.stage[warp];
   const int cpo = p.H * GW_W;
   const int V = p.nl * ((OBS == GW_OBS_F32) ? cpo / 4 : cpo / 8);
   if (p.io.obs != nullptr) {
-    const uint4* src = reinterpret_cast<const uint4*>(stage);
-    for (int el = warp; el < tile_envs; el += NWARPS) {
-      if (s.rinfo[el] & R_SKIP) continue;
+    uint8_t* const row0 = s.stage[warp][0];
+    uint4* dst = reinterpret_cast<uint4*>(p.io.obs) + (tile_base + warp) * (long long)V + lane;
+    const long long dst_step = (long long)NWARPS * V;
+    uint32_t prev_enc = 0xFFFFu;
+    int cur = 0;
+    for (int el = warp; el < tile_envs; el += NWARPS, dst += dst_step) {
+      if (s.rinfo[el] & R_SKIP) continue;                  // warp-uniform
+      uint8_t* row = row0 + cur * STAGE_BYTES_FWD;
+      uint8_t* other = row0 + (cur ^ 1) * STAGE_BYTES_FWD;
       const uint32_t enc = (lane < N_SPEC) ? (uint32_t)s.spec[el][lane] : 0xFFFFu;
-      const uint32_t off = enc & 0x1FFu;
       if (enc != 0xFFFFu) {
         const float v = 0.5f * (float)(enc >> 9);
-        if (OBS == GW_OBS_F32) reinterpret_cast<float*>(stage)[off] = v;
-        else reinterpret_cast<__nv_bfloat16*>(stage)[off] = __float2bfloat16(v);
+        if (OBS == GW_OBS_F32) reinterpret_cast<float*>(row)[enc & 0x1FFu] = v;
+        else reinterpret_cast<__nv_bfloat16*>(row)[enc & 0x1FFu] = __float2bfloat16(v);
       }
-      __syncwarp();
-      uint4* dst = reinterpret_cast<uint4*>(p.io.obs) + (tile_base + el) * (long long)V;
-      for (int v = lane; v < V; v += 32) __stcs(dst + v, src[v]);
-      __syncwarp();
-      if (enc != 0xFFFFu) {
-        if (OBS == GW_OBS_F32) reinterpret_cast<float*>(stage)[off] = 0.0f;
-        else reinterpret_cast<__nv_bfloat16*>(stage)[off] = __float2bfloat16(0.0f);
+      __syncwarp();                                        // patches visible; the previous row has been read by everyone
+      if (prev_enc != 0xFFFFu) {
+        if (OBS == GW_OBS_F32) reinterpret_cast<float*>(other)[prev_enc & 0x1FFu] = 0.0f;
+        else reinterpret_cast<__nv_bfloat16*>(other)[prev_enc & 0x1FFu] = __float2bfloat16(0.0f);
       }
-      __syncwarp();
+      const uint4* src = reinterpret_cast<const uint4*>(row) + lane;
+#pragma unroll 4
+      for (int v = 0; v < 4; ++v)
+        if (lane + 32 * v < V) __stcs(dst + 32 * v, src[32 * v]);
+      prev_enc = enc;
+      cur ^= 1;
     }
+    __syncwarp();
+    if (prev_enc != 0xFFFFu) {                             // leave both rows clean for the next tile
+      uint8_t* last = row0 + (cur ^ 1) * STAGE_BYTES_FWD;
+      if (OBS == GW_OBS_F32) reinterpret_cast<float*>(last)[prev_enc & 0x1FFu] = 0.0f;
+      else reinterpret_cast<__nv_bfloat16*>(last)[prev_enc & 0x1FFu] = __float2bfloat16(0.0f);
+    }
+    __syncwarp();
   }
   if (p.io.final_obs != nullptr) {                        // terminal observation of envs that were just re-spawned (rare)
     for (int el = warp; el < tile_envs; el += NWARPS) {
       const uint32_t ri = s.rinfo[el];
       if ((ri & R_FINAL) && !(ri & R_SKIP))
-        stage_and_store_env<OBS>(stage, p.io.final_obs, tile_base + el, p.H, p.n, p.nl, p.kind, s.cells_fin[el],
+        stage_and_store_env<OBS>(s.stage[warp][0], p.io.final_obs, tile_base + el, p.H, p.n, p.nl, p.kind, s.cells_fin[el],
                                  (ri >> 4) & 3u, p.apple_cells, false, lane);
     }
   }
@@ -1173,7 +1191,7 @@ int gw_step(gw_handle* h, const gw_io* io, void* stream) {
   const int tile = pick_tile(h->cfg.num_envs);
   const long long n_tiles = (h->cfg.num_envs + tile - 1) / tile;
   // persistent CTAs: at most `sm_count x resident CTAs per SM`, each walks several tiles and loads the tables once
-  const long long resident = (long long)h->sm_count * 4;
+  const long long resident = (long long)h->sm_count * 3;
   const unsigned blocks = (unsigned)(n_tiles < resident ? n_tiles : resident);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int split = pick_split(n_tiles, h->sm_count, tile);
