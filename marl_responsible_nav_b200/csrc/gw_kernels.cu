@@ -52,25 +52,27 @@ enum { ST_EPISODES = 0, ST_LEN, ST_CRASH, ST_APPLES, ST_UNRES, ST_FEAR_NZ, ST_RE
 // render record per env (shared memory): what P4 needs
 constexpr uint32_t R_FRESH = 1u << 2, R_FINAL = 1u << 3, R_SKIP = 1u << 6;   // bits 0-1 apples shown in obs, 4-5 apples at final
 
-constexpr int STAGE_BYTES_FWD = GW_MAX_LEARNERS * GW_MAX_H * GW_W * 4;
 constexpr int N_SPEC = GW_MAX_LEARNERS * (GW_MAX_AGENTS + 1);   // per learner: every agent + the own apple
 
-template <int TILE, int NWARPS = 8>
+template <int TILE>
 struct Smem {
   alignas(16) uint8_t lut[(LUT_BYTES + 15) / 16 * 16];
   alignas(16) uint8_t next[GW_MAX_H * GW_W * 4];
   alignas(16) SmallTables small;
-  alignas(16) uint4 tmpl[64];
   uint16_t rows[GW_MAX_H];
-  uint32_t cells_old[TILE], effs[TILE], geom_lo[TILE], geom_hi[TILE], close[TILE];
+  union {                                                   // P1b/P2 scratch of the FeAR tasks, then the mask staging (P3/P4)
+    struct { uint32_t cells_old[TILE], effs[TILE], geom_lo[TILE], geom_hi[TILE], close[TILE]; };
+    alignas(16) uint8_t mask[TILE * GW_MAX_LEARNERS * GW_N_ACTIONS + 16];
+  };
   uint32_t cnt[TILE * 2];
   uint32_t cells_fin[TILE], rinfo[TILE];
   uint16_t spec[TILE][N_SPEC];                          // special cells of the tile's observations (offset | value*2 << 9)
   uint16_t queue[TILE * 6];
   uint32_t qn;
-  alignas(16) uint8_t mask[TILE * GW_MAX_LEARNERS * GW_N_ACTIONS + 16];
-  alignas(16) uint8_t stage[NWARPS][2][STAGE_BYTES_FWD];   // per-warp observation staging rows (template + patches)
 };
+// Behind the struct (dynamic shared memory): per warp two observation staging rows of n_learners*H*W elements each.
+template <int TILE>
+__host__ __device__ constexpr size_t smem_fixed_bytes() { return (sizeof(Smem<TILE>) + 15) / 16 * 16; }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -83,7 +85,8 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // Tables -> shared memory.  The pair-mask table and the next-cell table travel with cp.async so that the copy
 // overlaps the first tile's state loads and RNG; the caller waits (cp_async_wait_all + __syncthreads) before P1b.
 template <int THREADS, int TILE, int OBS>
-__device__ __forceinline__ void load_tables(Smem<TILE>& s, const Tables* __restrict__ T, int H, bool need_lut) {
+__device__ __forceinline__ void load_tables(Smem<TILE>& s, uint8_t* stage, const Tables* __restrict__ T, int H, int nl,
+                                            bool need_lut) {
   const int tid = threadIdx.x;
   if (need_lut) {
     for (int i = tid; i < (LUT_BYTES + 15) / 16; i += THREADS) cp_async16(s.lut + 16 * i, T->pair_lut + 16 * i);
@@ -92,9 +95,12 @@ __device__ __forceinline__ void load_tables(Smem<TILE>& s, const Tables* __restr
   for (int i = tid; i < (int)sizeof(SmallTables) / 16; i += THREADS)
     cp_async16(reinterpret_cast<uint8_t*>(&s.small) + 16 * i, reinterpret_cast<const uint8_t*>(&T->small) + 16 * i);
   if (tid < GW_MAX_H) s.rows[tid] = T->map_rows[tid];
-  // constant observation template: -1 inactive / 0 active (WorldState reset, grid_world.py:433-434)
+  // staging rows <- constant observation template: -1 inactive / 0 active (WorldState reset, grid_world.py:433-434)
   const int Q = (OBS == GW_OBS_F32) ? H * 4 : H * 2;
-  for (int q = tid; q < Q; q += THREADS) {
+  const int row_vecs = nl * Q;
+  uint4* stage4 = reinterpret_cast<uint4*>(stage);
+  for (int i = tid; i < (THREADS / 32) * 2 * row_vecs; i += THREADS) {
+    const int q = (i % row_vecs) % Q;
     uint32_t w[4];
     if (OBS == GW_OBS_F32) {
 #pragma unroll
@@ -111,12 +117,7 @@ __device__ __forceinline__ void load_tables(Smem<TILE>& s, const Tables* __restr
         w[c] = lo | (hi << 16);
       }
     }
-    s.tmpl[q] = make_uint4(w[0], w[1], w[2], w[3]);
-    for (int wq = 0; wq < THREADS / 32; ++wq)
-      for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
-        reinterpret_cast<uint4*>(s.stage[wq][0])[k * Q + q] = make_uint4(w[0], w[1], w[2], w[3]);
-        reinterpret_cast<uint4*>(s.stage[wq][1])[k * Q + q] = make_uint4(w[0], w[1], w[2], w[3]);
-      }
+    stage4[i] = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -222,21 +223,23 @@ __device__ __forceinline__ void encode_specials(uint16_t* out, int cpo, int n, i
 // for the previous env are zeroed again (agents and apples only stand on active cells, whose template value is 0),
 // and row A leaves as 128-bit streaming stores: whole 128-byte lines, never a partial sector.  Rows alternate.
 template <int THREADS, int TILE, int OBS>
-__device__ __forceinline__ void render_tile(Smem<TILE>& s, const StepParams& p, long long tile_base, int tile_envs) {
+__device__ __forceinline__ void render_tile(Smem<TILE>& s, uint8_t* stage, const StepParams& p, long long tile_base,
+                                            int tile_envs) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int NWARPS = THREADS / 32;
   const int cpo = p.H * GW_W;
   const int V = p.nl * ((OBS == GW_OBS_F32) ? cpo / 4 : cpo / 8);
   if (p.io.obs != nullptr) {
-    uint8_t* const row0 = s.stage[warp][0];
+    const int row_bytes = V * 16;
+    uint8_t* const row0 = stage + warp * 2 * row_bytes;
     uint4* dst = reinterpret_cast<uint4*>(p.io.obs) + (tile_base + warp) * (long long)V + lane;
     const long long dst_step = (long long)NWARPS * V;
     uint32_t prev_enc = 0xFFFFu;
     int cur = 0;
     for (int el = warp; el < tile_envs; el += NWARPS, dst += dst_step) {
       if (s.rinfo[el] & R_SKIP) continue;                  // warp-uniform
-      uint8_t* row = row0 + cur * STAGE_BYTES_FWD;
-      uint8_t* other = row0 + (cur ^ 1) * STAGE_BYTES_FWD;
+      uint8_t* row = row0 + cur * row_bytes;
+      uint8_t* other = row0 + (cur ^ 1) * row_bytes;
       const uint32_t enc = (lane < N_SPEC) ? (uint32_t)s.spec[el][lane] : 0xFFFFu;
       if (enc != 0xFFFFu) {
         const float v = 0.5f * (float)(enc >> 9);
@@ -257,7 +260,7 @@ __device__ __forceinline__ void render_tile(Smem<TILE>& s, const StepParams& p, 
     }
     __syncwarp();
     if (prev_enc != 0xFFFFu) {                             // leave both rows clean for the next tile
-      uint8_t* last = row0 + (cur ^ 1) * STAGE_BYTES_FWD;
+      uint8_t* last = row0 + (cur ^ 1) * row_bytes;
       if (OBS == GW_OBS_F32) reinterpret_cast<float*>(last)[prev_enc & 0x1FFu] = 0.0f;
       else reinterpret_cast<__nv_bfloat16*>(last)[prev_enc & 0x1FFu] = __float2bfloat16(0.0f);
     }
@@ -267,7 +270,7 @@ __device__ __forceinline__ void render_tile(Smem<TILE>& s, const StepParams& p, 
     for (int el = warp; el < tile_envs; el += NWARPS) {
       const uint32_t ri = s.rinfo[el];
       if ((ri & R_FINAL) && !(ri & R_SKIP))
-        stage_and_store_env<OBS>(s.stage[warp][0], p.io.final_obs, tile_base + el, p.H, p.n, p.nl, p.kind, s.cells_fin[el],
+        stage_and_store_env<OBS>(stage + warp * 2 * V * 16, p.io.final_obs, tile_base + el, p.H, p.n, p.nl, p.kind, s.cells_fin[el],
                                  (ri >> 4) & 3u, p.apple_cells, false, lane);
     }
   }
@@ -368,7 +371,8 @@ template <int THREADS, int TILE, int OBS>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_reset_kernel(StepParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
-  load_tables<THREADS, TILE, OBS>(s, p.tables, p.H, false);
+  uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
+  load_tables<THREADS, TILE, OBS>(s, stage, p.tables, p.H, p.nl, false);
   cp_async_wait_all();
   __syncthreads();
   const long long tile_base = (long long)blockIdx.x * TILE;
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_reset_kernel(StepP
     }
   }
   __syncthreads();
-  render_tile<THREADS, TILE, OBS>(s, p, tile_base, tile_envs);
+  render_tile<THREADS, TILE, OBS>(s, stage, p, tile_base, tile_envs);
 }
 
 // ------------------------------------------------------------------ step kernel
@@ -399,7 +403,8 @@ template <int THREADS, int TILE, int SPLIT_, bool FEAR, int OBS>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
-  load_tables<THREADS, TILE, OBS>(s, p.tables, p.H, true);
+  uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
+  load_tables<THREADS, TILE, OBS>(s, stage, p.tables, p.H, p.nl, true);
   const Tables* __restrict__ T = p.tables;
   const int tid = threadIdx.x;
   const int n = p.n, nl = p.nl;
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
     uint32_t stat_bits = 0, steps_now = 0;
     int ret0 = 0, ret1 = 0;
     uint4 st = make_uint4(0, 0, 0, 0);
-    uint32_t acts = 0, mdrs = 0;
+    uint32_t acts = 0, mdrs = 0, cells_render = 0;
     uint32_t rw[4] = {0, 0, 0, 0}, rw2[4] = {0, 0, 0, 0};
 
     // ================================================================= P1a: loads and RNG (no shared tables needed)
@@ -624,7 +629,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
       p.state[e] = st_out;
       s.rinfo[tid] = apples_r | rflags;
       encode_specials(s.spec[tid], p.H * GW_W, n, nl, p.kind, cells_r, apples_r, p.apple_cells, (rflags & R_FRESH) != 0);
-      stage_masks(s, p, tid, cells_r);
+      cells_render = cells_r;
     }
 
     // ================================================================= P2: counterfactual sims (Responsibility.py:20-54)
@@ -658,8 +663,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
       __syncthreads();
     }
 
-    // ================================================================= P3: fear, shaped reward, statistics
+    // ================================================================= P3: fear, shaped reward, statistics, action masks
     if (own) {
+      stage_masks(s, p, tid, cells_render);                // the FeAR scratch is dead now: its space stages the masks
       double fear[GW_MAX_LEARNERS] = {0.0, 0.0};
       if (FEAR) {
 #pragma unroll
@@ -716,10 +722,14 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
 
     // ================================================================= P4
     __syncthreads();
-    render_tile<THREADS, TILE, OBS>(s, p, tile_base, tile_envs);
+    render_tile<THREADS, TILE, OBS>(s, stage, p, tile_base, tile_envs);
     __syncthreads();                                       // shared arrays are reused by the next tile
   }
   if (tables_pending) cp_async_wait_all();                 // a CTA without tiles must not exit with copies in flight
+}
+
+static inline size_t stage_row_bytes(const gw_config& c) {
+  return (size_t)c.n_learners * c.height * GW_W * (c.obs_dtype == GW_OBS_F32 ? 4 : 2);
 }
 
 // ------------------------------------------------------------------ operator-level kernels
@@ -1145,7 +1155,7 @@ static void launch_k(K kernel, const gw::StepParams& p, unsigned blocks, int thr
 template <int THREADS, int TILE, int SPLIT>
 static void launch_step_t(const gw_config& c, const gw::StepParams& p, unsigned blocks, cudaStream_t s) {
   const bool f32 = c.obs_dtype == GW_OBS_F32;
-  const size_t smem = sizeof(gw::Smem<TILE>);
+  const size_t smem = gw::smem_fixed_bytes<TILE>() + (size_t)(THREADS / 32) * 2 * gw::stage_row_bytes(c);
   if (c.fear) {
     if (f32) launch_k(gw::gw_step_kernel<THREADS, TILE, SPLIT, true, GW_OBS_F32>, p, blocks, THREADS, smem, s);
     else launch_k(gw::gw_step_kernel<THREADS, TILE, SPLIT, true, GW_OBS_BF16>, p, blocks, THREADS, smem, s);
@@ -1157,7 +1167,7 @@ static void launch_step_t(const gw_config& c, const gw::StepParams& p, unsigned 
 
 template <int THREADS, int TILE>
 static void launch_reset_t(const gw_config& c, const gw::StepParams& p, unsigned blocks, cudaStream_t s) {
-  const size_t smem = sizeof(gw::Smem<TILE>);
+  const size_t smem = gw::smem_fixed_bytes<TILE>() + (size_t)(THREADS / 32) * 2 * gw::stage_row_bytes(c);
   if (c.obs_dtype == GW_OBS_F32) launch_k(gw::gw_reset_kernel<THREADS, TILE, GW_OBS_F32>, p, blocks, THREADS, smem, s);
   else launch_k(gw::gw_reset_kernel<THREADS, TILE, GW_OBS_BF16>, p, blocks, THREADS, smem, s);
 }
@@ -1191,7 +1201,7 @@ int gw_step(gw_handle* h, const gw_io* io, void* stream) {
   const int tile = pick_tile(h->cfg.num_envs);
   const long long n_tiles = (h->cfg.num_envs + tile - 1) / tile;
   // persistent CTAs: at most `sm_count x resident CTAs per SM`, each walks several tiles and loads the tables once
-  const long long resident = (long long)h->sm_count * 3;
+  const long long resident = (long long)h->sm_count * 4;
   const unsigned blocks = (unsigned)(n_tiles < resident ? n_tiles : resident);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int split = pick_split(n_tiles, h->sm_count, tile);
