@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-scale-points", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every step from Python instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -154,27 +155,17 @@ def run_reference(a):
 
 
 # ----------------------------------------------------------------------------- GPU path
-def run_ours(a):
+def device_timed(a, E, fear, K, W, world, rank, dev, sample_clocks=False):
+    """K timed gw_step launches over E envs on this rank (CUDA events on the launching stream, max over ranks)."""
     import torch
     import torch.distributed as dist
     from marl_responsible_nav_b200 import BatchedGridWorld
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    E, K, W = a.envs, a.steps, a.warmup
     obs_dtype = torch.float32 if a.obs == "f32" else torch.bfloat16
-    env = BatchedGridWorld(a.scenario, num_envs=E, device=dev, fear=bool(a.fear), fear_weight=-5.0, auto_reset=True,
+    env = BatchedGridWorld(a.scenario, num_envs=E, device=dev, fear=bool(fear), fear_weight=-5.0, auto_reset=True,
                            max_steps=150, obs_dtype=obs_dtype, seed=42, env_id_base=rank * E)
     L = env.n_learners
     obs_bytes = E * L * env.obs_len * (4 if a.obs == "f32" else 2)
-    # observation ring: consecutive steps write different slots, the ring is larger than L2 (126 MB) so the store
+    # observation ring: consecutive steps write different slots and the ring is larger than L2 (126 MB), so the store
     # stream cannot be absorbed by the cache -- this is also the layout of the device replay buffer
     slots = max(2, -(-(320 << 20) // obs_bytes))
     slots = min(slots, max(2, (8 << 30) // obs_bytes))
@@ -199,20 +190,19 @@ def run_ours(a):
             run(n_act, W)
         env.sync()
 
-    def timed(K):
+    def timed(k):
         if graph is None:
-            run(K, W)
+            run(k, W)
             return
-        for _ in range(K // n_act):
+        for _ in range(k // n_act):
             graph.replay()
-        run(K % n_act, W)
+        run(k % n_act, W)
 
     timed(min(K, 2 * n_act))                                      # graph warm-up
     env.sync()
     env.reset_stats()
-    l0 = env.launch_count()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(dev.index)
+    if sample_clocks and rank == 0:
         sampler.start()
     if world > 1:
         dist.barrier()
@@ -225,8 +215,7 @@ def run_ours(a):
     if world > 1:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-    launches = K                                                  # one gw_step kernel per step (graph replays are not seen by the host counter)
+    clocks = sampler.stop() if (sample_clocks and rank == 0) else None
     st = env.stats()
     t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
     stat_vec = torch.tensor([st["episodes"], st["episode_len_sum"], st["crashes"], st["apples"], st["fear_nonzero"],
@@ -234,7 +223,27 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)          # time = max over ranks
         dist.all_reduce(stat_vec, op=dist.ReduceOp.SUM)      # episode statistics over NVLink (the only collective)
-    ms = float(t_ms.item())
+    return {"ms": float(t_ms.item()), "stats": stat_vec, "env": env, "ring": ring, "slots": slots, "L": L,
+            "obs_bytes": obs_bytes, "clocks": clocks, "n_act": n_act}
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E, K, W = a.envs, a.steps, a.warmup
+    r = device_timed(a, E, a.fear, K, W, world, rank, dev, sample_clocks=True)
+    ms, stat_vec, env, ring, slots, L, obs_bytes, n_act = (r[k] for k in ("ms", "stats", "env", "ring", "slots", "L", "obs_bytes", "n_act"))
+    clocks = r["clocks"]
     value = world * E * L * K / (ms * 1e-3)
 
     # ---- e2e: public API, host action buffers, H2D + D2H inside the timed region
@@ -266,6 +275,21 @@ def run_ours(a):
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         e2e = {"value": world * E * L * Ke / float(t_e.item()), "unit": "agent-steps/s",
                "h2d_bytes_per_step": E * L, "d2h_bytes_per_step": E * L * 4 + E, "steps": Ke}
+    del env, ring, r
+
+    # ---- the same kernel at a batch that fills the GPU (the step kernel's roofline point), N = 1 only
+    scale_points = None
+    if world == 1 and not a.no_scale_points:
+        scale_points = []
+        peak, _ = peaks()
+        for Es, fs in ((1 << 20, 1), (1 << 20, 0)):
+            torch.cuda.empty_cache()
+            rs = device_timed(a, Es, fs, 128, 64, 1, 0, dev)
+            per = rs["ms"] * 1e-3 / 128
+            gbs = ALGO_BYTES_PER_AGENT_STEP[a.obs] * Es * rs["L"] / per / 1e9
+            scale_points.append({"envs": Es, "fear": bool(fs), "ms_per_step": rs["ms"] / 128,
+                                 "agent_steps_per_s": Es * rs["L"] / per, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak})
+            del rs
 
     if rank != 0:
         if world > 1:
@@ -281,12 +305,16 @@ def run_ours(a):
         "config": {"workload": workload_name(a), "envs_per_gpu": E, "global_envs": world * E,
                    "parallelism": f"env-shard x{world}, no per-step collective",
                    "l2": f"obs stores stream through a {slots}-slot ring of {slots * obs_bytes / 2**20:.0f} MiB (> 126 MB L2), "
-                         "never re-read; 64 KB of packed env state is L2-resident by design"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                         "never re-read; the packed env state (16 B/env) is L2-resident by design"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(K),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": f"gw_step_kernel<fear={bool(a.fear)},{a.obs}>",
                      "algorithmic_bytes_per_launch": algo, "peak_source": peak_src,
-                     "note": "launch duration = CUDA-event time over K back-to-back launches / K (includes launch gaps); " + ("CUDA-graph replay" if a.graph else "eager launches")},
+                     "note": "launch duration = CUDA-event time over K back-to-back launches / K (includes launch gaps); "
+                             + ("CUDA-graph replay" if a.graph else "eager launches")
+                             + f"; at {E} envs one launch moves {algo / 2**20:.1f} MiB (0.9 us at peak) and is launch/latency-bound: "
+                               "see scale_points for the same kernel at 1M envs"},
+        "scale_points": scale_points,
         "workload_stats": {"episodes": stat_vec[0].item(), "mean_episode_len": stat_vec[1].item() / max(1.0, stat_vec[0].item()),
                            "learner_crashes_per_env_step": stat_vec[2].item() / (world * E * K),
                            "apples_per_env_step": stat_vec[3].item() / (world * E * K),

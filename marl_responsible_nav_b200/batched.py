@@ -129,9 +129,11 @@ class BatchedGridWorld:
             return obs.view(self.num_envs, self.n_learners, 1, self.H, self.W)
         return obs
 
-    def _io(self, obs, final_obs, actions=None, npc_actions=None, spawn=None, outputs=True) -> N.GwIO:
+    def _io(self, obs, final_obs, actions=None, npc_actions=None, spawn=None, outputs=True, buffers=None) -> N.GwIO:
         E, L, A, dev = self.num_envs, self.n_learners, self.n_agents, self.device
         io = self._io_step if outputs else self._io_reset          # pointers to the env-owned buffers are filled once
+        if outputs:
+            self._point_outputs(io, buffers if buffers is not None else self.buf)
         io.learner_actions = _check(actions, "actions", torch.int8, (E, L), dev).data_ptr() if actions is not None else None
         io.npc_actions = _check(npc_actions, "npc_actions", torch.int8, (E, A), dev).data_ptr() if npc_actions is not None else None
         io.spawn = _check(spawn, "spawn", torch.int8, (E, A, 2), dev).data_ptr() if spawn is not None else None
@@ -143,10 +145,24 @@ class BatchedGridWorld:
         io, b = N.GwIO(), self.buf
         io.action_mask, io.positions = b.action_mask.data_ptr(), b.positions.data_ptr()
         if outputs:
-            io.reward, io.shaped_reward, io.fear = b.reward.data_ptr(), b.shaped_reward.data_ptr(), b.fear.data_ptr()
-            io.terminated, io.truncated, io.ended = b.terminated.data_ptr(), b.truncated.data_ptr(), b.ended.data_ptr()
-            io.info = b.info.data_ptr()
+            self._point_outputs(io, b)
         return io
+
+    _OUT_SPECS = (("reward", torch.float32, True), ("shaped_reward", torch.float32, True), ("fear", torch.float64, True),
+                  ("terminated", torch.uint8, True), ("truncated", torch.uint8, True), ("ended", torch.uint8, False),
+                  ("info", torch.int32, False))
+
+    def _point_outputs(self, io: N.GwIO, b):
+        """Scalar outputs go to the env's own buffers or to caller tensors of the same shapes (e.g. a replay-ring slot)."""
+        if b is getattr(self, "_last_out_owner", None):
+            return
+        E, L, dev = self.num_envs, self.n_learners, self.device
+        for name, dtype, per_learner in self._OUT_SPECS:
+            t = getattr(b, name)
+            if b is not self.buf:
+                _check(t, name, dtype, (E, L) if per_learner else (E,), dev)
+            setattr(io, name, t.data_ptr())
+        self._last_out_owner = b if b is self.buf else None
 
     def _obs_arg(self, t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
         if t is None:
@@ -182,18 +198,20 @@ class BatchedGridWorld:
         return StepOutput(obs=self._view(obs), action_mask=self.buf.action_mask, positions=self.buf.positions)
 
     def step(self, actions, npc_actions=None, spawn=None, obs_out: Optional[torch.Tensor] = None,
-             final_obs_out: Optional[torch.Tensor] = None) -> StepOutput:
+             final_obs_out: Optional[torch.Tensor] = None, buffers=None) -> StepOutput:
         """One env.step for all envs.  actions: int8 [E, n_learners].  `npc_actions` [E, n_agents] / `spawn`
-        replay recorded NPC draws / respawn cells; None = device RNG."""
+        replay recorded NPC draws / respawn cells; None = device RNG.  `buffers`: object with reward / shaped_reward /
+        fear / terminated / truncated / ended / info tensors to write instead of the env's own (ReplayRing slot)."""
         actions = self._as_i8(actions, self.device)
         npc_actions = self._as_i8(npc_actions, self.device)
         spawn = self._as_i8(spawn, self.device)
         obs = self._obs_arg(obs_out, "obs_out") if obs_out is not None else self.buf.obs
         fin = self._obs_arg(final_obs_out, "final_obs_out")
-        io = self._io(obs, fin, actions, npc_actions, spawn)
+        io = self._io(obs, fin, actions, npc_actions, spawn, buffers=buffers)
         N.check(self.lib.gw_step(self._h, C.byref(io), self._stream()), self._h, "gw_step")
-        b = self.buf
-        return StepOutput(obs=self._view(obs), action_mask=b.action_mask, positions=b.positions, reward=b.reward,
+        b = buffers if buffers is not None else self.buf
+        m = self.buf
+        return StepOutput(obs=self._view(obs), action_mask=m.action_mask, positions=m.positions, reward=b.reward,
                           shaped_reward=b.shaped_reward, fear=b.fear, terminated=b.terminated, truncated=b.truncated,
                           ended=b.ended, info=b.info, final_obs=self._view(fin) if fin is not None else None)
 

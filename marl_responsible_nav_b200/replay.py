@@ -1,0 +1,79 @@
+"""Device-resident replay ring (the reference uses AgileRL's MultiAgentReplayBuffer, maddpg/agent.py:68-73,190-197).
+
+Layout: time-major ring of T slots x E envs.  `gw_step` writes the observation of time t+1 straight into slot
+(t+1) % T (`obs_out=ring.obs_slot(t+1)`), so a transition's `next_state` is the neighbouring slot and no observation
+is stored twice; where an episode ended and the env was re-spawned inside the step, `next_state` is the terminal
+observation the kernel wrote to `final_slot(t)` (only those rows are ever written).  Rewards, done flags and the
+`ended` marker are written by the same kernel launch into per-slot buffers (`buffers_slot(t)`); the actor's continuous
+action vector is the only thing the caller copies in.
+
+Fields follow the reference: state, action (the continuous 9-vector, maddpg/agent.py:187-192), reward
+(FeAR_weight*fear + reward, :128-131), next_state, done (= terminations, :186,195).
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import torch
+
+
+class ReplayRing:
+    def __init__(self, num_envs: int, n_learners: int, obs_len: int, capacity: int, action_dim: int = 9,
+                 device="cuda", obs_dtype: torch.dtype = torch.float32):
+        """capacity: number of (env, time) transitions to keep, as MEMORY_SIZE in configs/custom*.yaml."""
+        E, L = int(num_envs), int(n_learners)
+        self.E, self.L, self.obs_len, self.action_dim = E, L, int(obs_len), int(action_dim)
+        self.T = max(3, -(-int(capacity) // E) + 1)            # +1: slot t+1 holds the next observation
+        self.device = torch.device(device)
+        dev, T = self.device, self.T
+        self.obs = torch.zeros((T, E, L, self.obs_len), dtype=obs_dtype, device=dev)
+        self.final_obs = torch.zeros((T, E, L, self.obs_len), dtype=obs_dtype, device=dev)
+        self.action = torch.zeros((T, E, L, self.action_dim), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros((T, E, L), dtype=torch.float32, device=dev)          # env reward
+        self.shaped_reward = torch.zeros((T, E, L), dtype=torch.float32, device=dev)   # what the trainer stores
+        self.fear = torch.zeros((T, E, L), dtype=torch.float64, device=dev)
+        self.terminated = torch.zeros((T, E, L), dtype=torch.uint8, device=dev)
+        self.truncated = torch.zeros((T, E, L), dtype=torch.uint8, device=dev)
+        self.ended = torch.zeros((T, E), dtype=torch.uint8, device=dev)
+        self.info = torch.zeros((T, E), dtype=torch.int32, device=dev)
+        self.t = 0                                              # number of transitions recorded per env so far
+
+    # ---- views handed to BatchedGridWorld.reset / step
+    def obs_slot(self, t: int) -> torch.Tensor:
+        return self.obs[t % self.T]
+
+    def final_slot(self, t: int) -> torch.Tensor:
+        return self.final_obs[t % self.T]
+
+    def buffers_slot(self, t: int) -> SimpleNamespace:
+        s = t % self.T
+        return SimpleNamespace(reward=self.reward[s], shaped_reward=self.shaped_reward[s], fear=self.fear[s],
+                               terminated=self.terminated[s], truncated=self.truncated[s], ended=self.ended[s],
+                               info=self.info[s])
+
+    def store_action(self, t: int, cont_actions: torch.Tensor):
+        self.action[t % self.T].copy_(cont_actions.reshape(self.E, self.L, self.action_dim))
+
+    def advance(self):
+        """Call once per env.step after the transition of time self.t has been written."""
+        self.t += 1
+
+    def __len__(self) -> int:
+        return min(self.t, self.T - 1) * self.E
+
+    # ---- sampling (uniform over the stored transitions, like random.sample over the deque)
+    def sample(self, batch_size: int, generator: Optional[torch.Generator] = None) -> Dict[str, torch.Tensor]:
+        n_t = min(self.t, self.T - 1)
+        if n_t == 0:
+            raise RuntimeError("replay ring is empty")
+        dev = self.device
+        k = torch.randint(0, n_t, (batch_size,), device=dev, generator=generator)
+        e = torch.randint(0, self.E, (batch_size,), device=dev, generator=generator)
+        t_abs = (self.t - 1) - k                                # the newest n_t time steps are valid
+        s = t_abs % self.T
+        s1 = (t_abs + 1) % self.T
+        ended = self.ended[s, e].bool()
+        nxt = torch.where(ended[:, None, None], self.final_obs[s, e], self.obs[s1, e])
+        return {"state": self.obs[s, e], "action": self.action[s, e], "reward": self.shaped_reward[s, e],
+                "next_state": nxt, "done": self.terminated[s, e], "ended": ended, "t": t_abs, "env": e}
