@@ -37,6 +37,7 @@ struct SmallTables {                    // per-step lookups, copied to shared me
 
 struct Tables {                         // device-global, read-only, built by gw_create
   alignas(16) uint8_t pair_lut[LUT_BYTES + 7];      // [delta][eff_i][eff_j] -> 4-bit sub-step hit mask
+  alignas(16) uint32_t obs_template[2][64 * 4];             // constant observation row (-1 inactive / 0 active) as f32 / bf16 16-byte vectors
   alignas(16) uint8_t next_cell[GW_MAX_H * GW_W * 4];       // [cell][dir Up,Down,Left,Right] -> cell after the move (same cell if blocked)
   SmallTables small;
   uint16_t map_rows[GW_MAX_H];

@@ -98,27 +98,10 @@ __device__ __forceinline__ void load_tables(Smem<TILE>& s, uint8_t* stage, const
   // staging rows <- constant observation template: -1 inactive / 0 active (WorldState reset, grid_world.py:433-434)
   const int Q = (OBS == GW_OBS_F32) ? H * 4 : H * 2;
   const int row_vecs = nl * Q;
-  uint4* stage4 = reinterpret_cast<uint4*>(stage);
-  for (int i = tid; i < (THREADS / 32) * 2 * row_vecs; i += THREADS) {
-    const int q = (i % row_vecs) % Q;
-    uint32_t w[4];
-    if (OBS == GW_OBS_F32) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int cell = q * 4 + c;
-        w[c] = ((T->map_rows[cell >> 4] >> (cell & 15)) & 1) ? 0u : 0xBF800000u;          // 0.0f / -1.0f
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int c0 = q * 8 + 2 * c, c1 = c0 + 1;
-        const uint32_t lo = ((T->map_rows[c0 >> 4] >> (c0 & 15)) & 1) ? 0u : 0xBF80u;      // bf16 0 / -1
-        const uint32_t hi = ((T->map_rows[c1 >> 4] >> (c1 & 15)) & 1) ? 0u : 0xBF80u;
-        w[c] = lo | (hi << 16);
-      }
-    }
-    stage4[i] = make_uint4(w[0], w[1], w[2], w[3]);
-  }
+  const uint8_t* tmpl = reinterpret_cast<const uint8_t*>(T->obs_template[OBS == GW_OBS_F32 ? 0 : 1]);
+  for (int r = 0; r < (THREADS / 32) * 2 * nl; ++r)                 // every (warp, row, learner) segment is one template copy
+    for (int q = tid; q < Q; q += THREADS) cp_async16(stage + 16 * (r * Q + q), tmpl + 16 * q);
+  (void)row_vecs;
 }
 
 // value of an agent / apple cell.  custom/ma_customenv.py:303-322 (step) / :198-209 (reset),
@@ -404,7 +387,11 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
   uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
+  // Programmatic dependent launch: let the next step's grid start its prologue (table copies) while this one runs; the
+  // env state written by the previous step is only touched after griddepcontrol.wait (no-ops without the attribute).
+  asm volatile("griddepcontrol.launch_dependents;");
   load_tables<THREADS, TILE, OBS>(s, stage, p.tables, p.H, p.nl, true);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const Tables* __restrict__ T = p.tables;
   const int tid = threadIdx.x;
   const int n = p.n, nl = p.nl;
@@ -1056,6 +1043,11 @@ int gw_create(const gw_config* cfg, gw_handle** out) {
   t->n_active = na;
   h->n_active = na;
   build_next_cell(cfg, t->next_cell);
+  for (int cell = 0; cell < GW_MAX_H * GW_W; ++cell) {
+    const bool active = (cell >> 4) < cfg->height && ((cfg->map_rows[cell >> 4] >> (cell & 15)) & 1);
+    t->obs_template[0][cell] = active ? 0u : 0xBF800000u;                                   // f32 0.0 / -1.0
+    t->obs_template[1][cell >> 1] |= (active ? 0u : 0xBF80u) << (16 * (cell & 1));           // bf16 0 / -1
+  }
   build_pair_lut(t->pair_lut);
   for (int m = 0; m < 10; ++m)
     for (int a = 0; a < 10; ++a) {
@@ -1146,10 +1138,28 @@ static int pick_split(long long n_tiles, int sm_count, int tile) {
 }
 
 template <typename K>
-static void launch_k(K kernel, const gw::StepParams& p, unsigned blocks, int threads, size_t smem, cudaStream_t s) {
+static void launch_k(K kernel, const gw::StepParams& p, unsigned blocks, int threads, size_t smem, cudaStream_t s,
+                     bool pdl = false) {
   // > 48 KB of dynamic shared memory needs the opt-in; the attribute is per function and cheap to set
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kernel<<<blocks, threads, smem, s>>>(p);
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  gw::StepParams pp = p;
+  cudaLaunchKernelEx(&cfg, kernel, pp);
+}
+
+static bool use_pdl() {
+  static const bool v = [] { const char* s = std::getenv("GW_PDL"); return !(s && std::atoi(s) == 0); }();
+  return v;
 }
 
 template <int THREADS, int TILE, int SPLIT>
@@ -1157,11 +1167,11 @@ static void launch_step_t(const gw_config& c, const gw::StepParams& p, unsigned 
   const bool f32 = c.obs_dtype == GW_OBS_F32;
   const size_t smem = gw::smem_fixed_bytes<TILE>() + (size_t)(THREADS / 32) * 2 * gw::stage_row_bytes(c);
   if (c.fear) {
-    if (f32) launch_k(gw::gw_step_kernel<THREADS, TILE, SPLIT, true, GW_OBS_F32>, p, blocks, THREADS, smem, s);
-    else launch_k(gw::gw_step_kernel<THREADS, TILE, SPLIT, true, GW_OBS_BF16>, p, blocks, THREADS, smem, s);
+    if (f32) launch_k(gw::gw_step_kernel<THREADS, TILE, SPLIT, true, GW_OBS_F32>, p, blocks, THREADS, smem, s, use_pdl());
+    else launch_k(gw::gw_step_kernel<THREADS, TILE, SPLIT, true, GW_OBS_BF16>, p, blocks, THREADS, smem, s, use_pdl());
   } else {
-    if (f32) launch_k(gw::gw_step_kernel<THREADS, TILE, 1, false, GW_OBS_F32>, p, blocks, THREADS, smem, s);
-    else launch_k(gw::gw_step_kernel<THREADS, TILE, 1, false, GW_OBS_BF16>, p, blocks, THREADS, smem, s);
+    if (f32) launch_k(gw::gw_step_kernel<THREADS, TILE, 1, false, GW_OBS_F32>, p, blocks, THREADS, smem, s, use_pdl());
+    else launch_k(gw::gw_step_kernel<THREADS, TILE, 1, false, GW_OBS_BF16>, p, blocks, THREADS, smem, s, use_pdl());
   }
 }
 
