@@ -99,8 +99,15 @@ __device__ __forceinline__ void load_tables(Smem<TILE>& s, uint8_t* stage, const
   const int Q = (OBS == GW_OBS_F32) ? H * 4 : H * 2;
   const int row_vecs = nl * Q;
   const uint8_t* tmpl = reinterpret_cast<const uint8_t*>(T->obs_template[OBS == GW_OBS_F32 ? 0 : 1]);
-  for (int r = 0; r < (THREADS / 32) * 2 * nl; ++r)                 // every (warp, row, learner) segment is one template copy
-    for (int q = tid; q < Q; q += THREADS) cp_async16(stage + 16 * (r * Q + q), tmpl + 16 * q);
+  // every (warp, row, learner) segment of Q vectors is one copy of the template; all threads share the work
+  const int total = (THREADS / 32) * 2 * row_vecs;
+  int q = tid % Q;
+  const int qstep = THREADS % Q;
+  for (int i = tid; i < total; i += THREADS) {
+    cp_async16(stage + 16 * i, tmpl + 16 * q);
+    q += qstep;
+    if (q >= Q) q -= Q;
+  }
   (void)row_vecs;
 }
 
