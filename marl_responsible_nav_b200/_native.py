@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libgridworld_b200.so")
+LIB_PATH = os.environ.get("GW_LIB") or os.path.join(HERE, "csrc", "libgridworld_b200.so")
 
 GW_MAX_AGENTS, GW_MAX_LEARNERS, GW_N_ACTIONS, GW_MAX_POLICIES, GW_MAX_H, GW_W = 4, 2, 9, 16, 16, 16
 GW_OK, GW_EINVAL, GW_ENOMEM, GW_ECUDA, GW_ENODEV, GW_ESTATE = 0, -1, -2, -3, -4, -5

@@ -95,20 +95,29 @@ __device__ __forceinline__ void load_tables(Smem<TILE>& s, uint8_t* stage, const
   for (int i = tid; i < (int)sizeof(SmallTables) / 16; i += THREADS)
     cp_async16(reinterpret_cast<uint8_t*>(&s.small) + 16 * i, reinterpret_cast<const uint8_t*>(&T->small) + 16 * i);
   if (tid < GW_MAX_H) s.rows[tid] = T->map_rows[tid];
-  // staging rows <- constant observation template: -1 inactive / 0 active (WorldState reset, grid_world.py:433-434)
+  // constant observation template (-1 inactive / 0 active, grid_world.py:433-434): one copy per CTA into the scratch
+  // area; fill_stage_rows() replicates it into the warps' staging rows once the copy has landed.  (Every CTA pulling
+  // all of its rows straight from the same few L2 lines hot-spots one L2 slice: 2x slower kernels at 4096 envs.)
   const int Q = (OBS == GW_OBS_F32) ? H * 4 : H * 2;
-  const int row_vecs = nl * Q;
   const uint8_t* tmpl = reinterpret_cast<const uint8_t*>(T->obs_template[OBS == GW_OBS_F32 ? 0 : 1]);
-  // every (warp, row, learner) segment of Q vectors is one copy of the template; all threads share the work
-  const int total = (THREADS / 32) * 2 * row_vecs;
-  int q = tid % Q;
+  for (int q = tid; q < Q; q += THREADS) cp_async16(s.mask + 16 * q, tmpl + 16 * q);
+  (void)nl;
+  (void)stage;
+}
+
+template <int THREADS, int TILE, int OBS>
+__device__ __forceinline__ void fill_stage_rows(Smem<TILE>& s, uint8_t* stage, int H, int nl) {
+  const int Q = (OBS == GW_OBS_F32) ? H * 4 : H * 2;
+  const int total = (THREADS / 32) * 2 * nl * Q;             // every (warp, row, learner) segment is one template copy
+  const uint4* src = reinterpret_cast<const uint4*>(s.mask);
+  uint4* dst = reinterpret_cast<uint4*>(stage);
+  int q = threadIdx.x % Q;
   const int qstep = THREADS % Q;
-  for (int i = tid; i < total; i += THREADS) {
-    cp_async16(stage + 16 * i, tmpl + 16 * q);
+  for (int i = threadIdx.x; i < total; i += THREADS) {
+    dst[i] = src[q];
     q += qstep;
     if (q >= Q) q -= Q;
   }
-  (void)row_vecs;
 }
 
 // value of an agent / apple cell.  custom/ma_customenv.py:303-322 (step) / :198-209 (reset),
@@ -365,6 +374,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_reset_kernel(StepP
   load_tables<THREADS, TILE, OBS>(s, stage, p.tables, p.H, p.nl, false);
   cp_async_wait_all();
   __syncthreads();
+  fill_stage_rows<THREADS, TILE, OBS>(s, stage, p.H, p.nl);
+  __syncthreads();
   const long long tile_base = (long long)blockIdx.x * TILE;
   const int tile_envs = (int)min((long long)TILE, p.E - tile_base);
   const int tid = threadIdx.x;
@@ -396,9 +407,13 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
   uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
   // Programmatic dependent launch: let the next step's grid start its prologue (table copies) while this one runs; the
   // env state written by the previous step is only touched after griddepcontrol.wait (no-ops without the attribute).
+#ifndef GW_NO_GDC
   asm volatile("griddepcontrol.launch_dependents;");
+#endif
   load_tables<THREADS, TILE, OBS>(s, stage, p.tables, p.H, p.nl, true);
+#ifndef GW_NO_GDC
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
   const Tables* __restrict__ T = p.tables;
   const int tid = threadIdx.x;
   const int n = p.n, nl = p.nl;
@@ -446,6 +461,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
     }
     if (tables_pending) {
       cp_async_wait_all();
+      __syncthreads();
+      fill_stage_rows<THREADS, TILE, OBS>(s, stage, p.H, p.nl);   // reads the scratch area that P1b overwrites
       tables_pending = false;
     }
     __syncthreads();
