@@ -405,15 +405,10 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
   uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
-  // Programmatic dependent launch: let the next step's grid start its prologue (table copies) while this one runs; the
-  // env state written by the previous step is only touched after griddepcontrol.wait (no-ops without the attribute).
-#ifndef GW_NO_GDC
-  asm volatile("griddepcontrol.launch_dependents;");
-#endif
+  // Programmatic dependent launch (when the launch carries the attribute): this grid's prologue (table copies) may run
+  // while the previous step drains; the env state it wrote is only touched after griddepcontrol.wait.
   load_tables<THREADS, TILE, OBS>(s, stage, p.tables, p.H, p.nl, true);
-#ifndef GW_NO_GDC
   asm volatile("griddepcontrol.wait;" ::: "memory");
-#endif
   const Tables* __restrict__ T = p.tables;
   const int tid = threadIdx.x;
   const int n = p.n, nl = p.nl;
@@ -733,6 +728,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
 
     // ================================================================= P4
     __syncthreads();
+    // last tile of this CTA: only observation stores are left, the next step's grid may start its prologue
+    if (tile + gridDim.x >= n_tiles) asm volatile("griddepcontrol.launch_dependents;");
     render_tile<THREADS, TILE, OBS>(s, stage, p, tile_base, tile_envs);
     __syncthreads();                                       // shared arrays are reused by the next tile
   }
