@@ -1,0 +1,232 @@
+"""Batched MADDPG on the device: the trainer-side twin of maddpg/agent.py for E parallel environments.
+
+The reference delegates the algorithm to AgileRL 1.0.15 (`MADDPG`, `MultiAgentReplayBuffer`), a third-party package
+that is neither vendored in the reference tree nor installed here, so **parity with it is unpinned**: this module
+follows what the reference itself pins down --
+
+  * network shapes, read from the shipped checkpoints: actor
+    Linear(160,128)-LayerNorm-ReLU-Linear(128,128)-LayerNorm-ReLU-Linear(128,9)-GumbelSoftmax (38 793 parameters),
+    critic Linear(2*160+2*9,128)-LayerNorm-ReLU-Linear(128,128)-LayerNorm-ReLU-Linear(128,1) (60 545 parameters);
+  * hyper-parameters and their names (configs/custom*.yaml: EXPL_NOISE, GAMMA, TAU, LR_ACTOR, LR_CRITIC, BATCH_SIZE,
+    LEARN_STEP, MEMORY_SIZE, FeAR_weight, WITH_FEAR, TRAIN_STEPS);
+  * the loop of MADDPGAgent.train (maddpg/agent.py:77-252): act -> env.step -> reward = FeAR_weight*fear + reward
+    (:128-131) -> store (state, continuous action, reward, next_state, termination) (:190-197) -> learn every
+    LEARN_STEP environment steps once BATCH_SIZE transitions exist (:201-222);
+
+and the textbook MADDPG update (centralised critics on all states and actions, actor loss -Q, soft target update).
+Everything runs on the GPU: observations are written by gw_step straight into the replay ring, the actors read them
+from there, nothing crosses to the host inside the loop.  Multi-GPU: env shards per rank, gradients all-reduced.
+"""
+from __future__ import annotations
+
+import copy
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+DEFAULT_HP = {           # configs/custom.yaml:1-26 (custom_fear_*.yaml differ in WITH_FEAR / FeAR_weight / MAX_EPISODES)
+    "CUSTOM_ENV": True, "SEED": 42, "MAX_EPISODES": 30000, "TRAIN_STEPS": 150, "CHANNELS_LAST": False,
+    "DISCRETE_ACTIONS": True, "ARCH": "mlp", "O_U_NOISE": False, "EXPL_NOISE": 0.1, "MEAN_NOISE": 0.0, "THETA": 0.15,
+    "DT": 0.01, "LR_ACTOR": 0.001, "LR_CRITIC": 0.001, "GAMMA": 0.98, "MEMORY_SIZE": 200000, "LEARN_STEP": 10,
+    "TAU": 0.01, "BATCH_SIZE": 128, "WITH_FEAR": False, "FeAR_weight": -2.0,
+}
+
+
+def preset(name: str = "custom") -> Dict:
+    """Hyper-parameter sets of configs/custom.yaml and configs/custom_fear_{1,3,5,10}.yaml."""
+    hp = dict(DEFAULT_HP)
+    if name == "custom":
+        return hp
+    if name.startswith("custom_fear_"):
+        w = float(name.rsplit("_", 1)[1])
+        hp.update(WITH_FEAR=True, FeAR_weight=-w, MAX_EPISODES=15000)
+        return hp
+    raise KeyError(name)
+
+
+def load_yaml_config(path: str) -> Dict:
+    """Read a reference-style YAML (same keys as configs/custom*.yaml); missing keys take the defaults."""
+    import yaml
+    with open(path) as f:
+        hp = dict(DEFAULT_HP)
+        hp.update(yaml.safe_load(f) or {})
+    return hp
+
+
+class GumbelSoftmax(nn.Module):
+    """Output activation of the reference's actors (`mlp_output_activation='GumbelSoftmax'`): softmax of the logits
+    perturbed with fresh Gumbel noise on every forward."""
+
+    def forward(self, logits: torch.Tensor) -> torch.Tensor:
+        u = torch.rand_like(logits).clamp_(1e-20, 1.0)
+        g = -torch.log(-torch.log(u) + 1e-20)
+        return F.softmax(logits + g, dim=-1)
+
+
+def mlp(in_dim: int, hidden: Sequence[int], out_dim: int, out_act: Optional[nn.Module]) -> nn.Sequential:
+    layers: List[nn.Module] = []
+    d = in_dim
+    for h in hidden:
+        layers += [nn.Linear(d, h), nn.LayerNorm(h), nn.ReLU()]
+        d = h
+    layers.append(nn.Linear(d, out_dim))
+    if out_act is not None:
+        layers.append(out_act)
+    return nn.Sequential(*layers)
+
+
+@dataclass
+class LearnStats:
+    """Per-agent losses of one update, kept as device tensors (reading them would synchronise the stream)."""
+    actor_loss: torch.Tensor
+    critic_loss: torch.Tensor
+
+
+class BatchedMADDPG:
+    def __init__(self, n_agents: int = 2, obs_dim: int = 160, act_dim: int = 9, hidden: Sequence[int] = (128, 128),
+                 hp: Optional[Dict] = None, device="cuda", seed: int = 0):
+        self.hp = dict(DEFAULT_HP if hp is None else hp)
+        self.n, self.obs_dim, self.act_dim = n_agents, obs_dim, act_dim
+        self.device = torch.device(device)
+        g = torch.Generator().manual_seed(seed)
+        state = torch.random.get_rng_state()
+        torch.manual_seed(int(torch.randint(0, 2**31 - 1, (1,), generator=g)))
+        crit_in = n_agents * (obs_dim + act_dim)
+        self.actors = [mlp(obs_dim, hidden, act_dim, GumbelSoftmax()).to(self.device) for _ in range(n_agents)]
+        self.critics = [mlp(crit_in, hidden, 1, None).to(self.device) for _ in range(n_agents)]
+        torch.random.set_rng_state(state)
+        self.actor_targets = [copy.deepcopy(a) for a in self.actors]
+        self.critic_targets = [copy.deepcopy(c) for c in self.critics]
+        for net in self.actor_targets + self.critic_targets:
+            for p in net.parameters():
+                p.requires_grad_(False)
+        self.actor_opt = [torch.optim.Adam(a.parameters(), lr=self.hp["LR_ACTOR"]) for a in self.actors]
+        self.critic_opt = [torch.optim.Adam(c.parameters(), lr=self.hp["LR_CRITIC"]) for c in self.critics]
+
+    def parameters(self):
+        for net in self.actors + self.critics:
+            yield from net.parameters()
+
+    def broadcast_parameters(self, src: int = 0):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            for net in self.actors + self.critics + self.actor_targets + self.critic_targets:
+                for p in net.parameters():
+                    dist.broadcast(p.data, src)
+
+    # ---- acting (maddpg/agent.py:109-122): continuous 9-vector + masked arg-max action id
+    @torch.no_grad()
+    def get_action(self, obs: torch.Tensor, action_mask: Optional[torch.Tensor] = None, training: bool = True):
+        """obs [E, n, obs_dim] (any float dtype), action_mask int8 [E, n, 9] -> (cont [E, n, 9] f32, ids int8 [E, n])."""
+        cont = []
+        for k, actor in enumerate(self.actors):
+            a = actor(obs[:, k].float())
+            if training:                                   # Gaussian exploration, EXPL_NOISE / MEAN_NOISE
+                a = (a + self.hp["MEAN_NOISE"] + self.hp["EXPL_NOISE"] * torch.randn_like(a)).clamp_(0.0, 1.0)
+            cont.append(a)
+        cont = torch.stack(cont, dim=1)
+        scores = cont if action_mask is None else cont.masked_fill(action_mask == 0, float("-inf"))
+        return cont, scores.argmax(dim=-1).to(torch.int8)
+
+    # ---- learning (textbook MADDPG; AgileRL's exact variant is not available here: parity unpinned)
+    def learn(self, batch: Dict[str, torch.Tensor]) -> LearnStats:
+        gamma, tau = self.hp["GAMMA"], self.hp["TAU"]
+        s, a, r = batch["state"].float(), batch["action"].float(), batch["reward"].float()
+        s2, done = batch["next_state"].float(), batch["done"].float()
+        B = s.shape[0]
+        flat_s, flat_s2 = s.reshape(B, -1), s2.reshape(B, -1)
+        with torch.no_grad():
+            a2 = torch.stack([self.actor_targets[k](s2[:, k]) for k in range(self.n)], dim=1)
+            crit_in2 = torch.cat([flat_s2, a2.reshape(B, -1)], dim=1)
+        a_losses, c_losses = [], []
+        for k in range(self.n):
+            with torch.no_grad():
+                q2 = self.critic_targets[k](crit_in2).squeeze(-1)
+                target = r[:, k] + gamma * (1.0 - done[:, k]) * q2
+            q = self.critics[k](torch.cat([flat_s, a.reshape(B, -1)], dim=1)).squeeze(-1)
+            c_loss = F.mse_loss(q, target)
+            self.critic_opt[k].zero_grad(set_to_none=True)
+            c_loss.backward()
+            self._allreduce_grads(self.critics[k])
+            self.critic_opt[k].step()
+            a_new = a.clone()
+            a_new[:, k] = self.actors[k](s[:, k])
+            a_loss = -self.critics[k](torch.cat([flat_s, a_new.reshape(B, -1)], dim=1)).mean()
+            self.actor_opt[k].zero_grad(set_to_none=True)
+            a_loss.backward()
+            self._allreduce_grads(self.actors[k])
+            self.actor_opt[k].step()
+            a_losses.append(a_loss.detach())
+            c_losses.append(c_loss.detach())
+        with torch.no_grad():                              # soft update, TAU
+            for net, tgt in zip(self.actors + self.critics, self.actor_targets + self.critic_targets):
+                for p, pt in zip(net.parameters(), tgt.parameters()):
+                    pt.lerp_(p, tau)
+        return LearnStats(torch.stack(a_losses), torch.stack(c_losses))
+
+    @staticmethod
+    def _allreduce_grads(net: nn.Module):
+        """Data parallel over env shards: average the gradients of one network with a single flat all-reduce
+        (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        grads = [p.grad for p in net.parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat /= dist.get_world_size()
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+
+
+class BatchedTrainer:
+    """MADDPGAgent.train (maddpg/agent.py:77-252) for E environments at once, everything on the device."""
+
+    def __init__(self, env, agent: Optional[BatchedMADDPG] = None, hp: Optional[Dict] = None,
+                 updates_per_learn: int = 1, seed: int = 0):
+        from .replay import ReplayRing
+        self.env = env
+        self.hp = dict(DEFAULT_HP if hp is None else hp)
+        self.agent = agent or BatchedMADDPG(env.n_learners, env.obs_len, 9, hp=self.hp, device=env.device, seed=seed)
+        self.ring = ReplayRing(env.num_envs, env.n_learners, env.obs_len, self.hp["MEMORY_SIZE"], 9,
+                               device=env.device, obs_dtype=env.obs_dtype)
+        self.updates_per_learn = int(updates_per_learn)
+        self.gen = torch.Generator(device=env.device).manual_seed(seed + 1)
+        self.t = 0
+        self.out = env.reset(obs_out=self.ring.obs_slot(0))
+        self.losses: List[LearnStats] = []
+
+    def train(self, env_steps: int, learn: bool = True) -> Dict[str, float]:
+        """`env_steps` synchronous steps of all E envs (auto-reset replaces the reference's per-episode outer loop;
+        the TRAIN_STEPS cap is the env's max_steps).  Returns the episode statistics gathered meanwhile."""
+        env, ring, agent, hp = self.env, self.ring, self.agent, self.hp
+        env.reset_stats()
+        for _ in range(env_steps):
+            t = self.t
+            obs = ring.obs_slot(t)
+            cont, ids = agent.get_action(obs, self.out.action_mask, training=True)
+            self.out = env.step(ids, obs_out=ring.obs_slot(t + 1), final_obs_out=ring.final_slot(t),
+                                buffers=ring.buffers_slot(t))
+            ring.store_action(t, cont)
+            ring.advance()
+            self.t += 1
+            # the reference learns every LEARN_STEP steps of its single env once BATCH_SIZE transitions exist
+            if learn and t % hp["LEARN_STEP"] == 0 and len(ring) >= hp["BATCH_SIZE"]:
+                for _ in range(self.updates_per_learn):
+                    self.losses.append(agent.learn(ring.sample(hp["BATCH_SIZE"], self.gen)))
+        return env.stats()
+
+
+def make_env(hp: Dict, num_envs: int, device="cuda", scenario="Level 3", obs_dtype=torch.float32, seed: Optional[int] = None,
+             env_id_base: int = 0):
+    """util.create_custom_ma_env (util.py:21-30) for a batch: WITH_FEAR / FeAR_weight / TRAIN_STEPS / SEED from the config."""
+    from .batched import BatchedGridWorld
+    return BatchedGridWorld(scenario, num_envs=num_envs, device=device, env_kind="multi", fear=bool(hp["WITH_FEAR"]),
+                            fear_weight=float(hp["FeAR_weight"]) if hp["WITH_FEAR"] else 0.0,
+                            max_steps=int(hp["TRAIN_STEPS"]), auto_reset=True, obs_dtype=obs_dtype,
+                            obs_layout="cnn" if hp.get("ARCH", "mlp") == "cnn" else "mlp",
+                            seed=int(hp["SEED"] if seed is None else seed), env_id_base=env_id_base)

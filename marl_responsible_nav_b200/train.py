@@ -1,0 +1,61 @@
+"""Batched counterpart of main_custom.py: `python -m marl_responsible_nav_b200.train --config custom_fear_5 --envs 4096`.
+
+Same configuration keys as configs/custom*.yaml (a YAML path or one of the preset names); POSIX paths (the reference
+hard-codes Windows-style "configs\\custom.yaml", main_custom.py:39).  Launch with torchrun for several GPUs: every rank
+owns a contiguous shard of the environments, gradients and episode statistics are all-reduced over NCCL.
+"""
+import argparse
+import json
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+from . import maddpg, sharding
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="custom", help="preset (custom, custom_fear_1/3/5/10) or path to a YAML file")
+    ap.add_argument("--envs", type=int, default=4096, help="environments over all GPUs")
+    ap.add_argument("--steps", type=int, default=1500, help="synchronous env steps (the reference: MAX_EPISODES x TRAIN_STEPS)")
+    ap.add_argument("--report", type=int, default=150)
+    ap.add_argument("--updates-per-learn", type=int, default=1)
+    a = ap.parse_args()
+    hp = maddpg.load_yaml_config(a.config) if os.path.exists(a.config) else maddpg.preset(a.config)
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    base, n = sharding.shard_range(a.envs, rank, world)
+    env = maddpg.make_env(hp, n, device=dev, env_id_base=base)
+    trainer = maddpg.BatchedTrainer(env, hp=hp, updates_per_learn=a.updates_per_learn, seed=hp["SEED"])
+    trainer.agent.broadcast_parameters(0)
+    done = 0
+    while done < a.steps:
+        k = min(a.report, a.steps - done)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st = trainer.train(k)
+        torch.cuda.synchronize()
+        el = sharding.max_over_ranks(time.perf_counter() - t0)
+        st = sharding.allreduce_stats(st)
+        done += k
+        if rank == 0:
+            eps = max(1, st["episodes"])
+            last = trainer.losses[-1] if trainer.losses else None
+            print(json.dumps({"env_steps": done, "agent_steps_per_s": st["agent_steps"] / el, "episodes": st["episodes"],
+                              "mean_return": st["return_sum"] / eps, "mean_len": st["episode_len_sum"] / eps,
+                              "crashes_per_episode": st["crashes"] / eps, "apples_per_episode": st["apples"] / eps,
+                              "fear_sum": st["fear_sum"],
+                              "critic_loss": None if last is None else float(last.critic_loss.sum()),
+                              "actor_loss": None if last is None else float(last.actor_loss.sum())}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,92 @@
+"""MADDPG twin: shapes proven by the reference's checkpoints, update sanity, gradient all-reduce (gloo),
+and the batched training loop on the GPU."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from marl_responsible_nav_b200 import maddpg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_network_shapes_match_reference_checkpoints():
+    ag = maddpg.BatchedMADDPG(2, 160, 9, device="cpu")
+    assert sum(p.numel() for p in ag.actors[0].parameters()) == 38793          # 20480+128+128+128+16384+128+128+128+1152+9
+    assert sum(p.numel() for p in ag.critics[0].parameters()) == 60545         # critic input 2*160 + 2*9 = 338
+    assert [tuple(p.shape) for p in ag.actors[0].parameters()][0] == (128, 160)
+    single = maddpg.BatchedMADDPG(1, 160, 9, device="cpu")
+    assert [tuple(p.shape) for p in single.critics[0].parameters()][0] == (128, 169)   # single-learner checkpoint: 128 x 169
+
+
+def test_presets_match_reference_configs():
+    hp = maddpg.preset("custom_fear_5")
+    assert hp["WITH_FEAR"] is True and hp["FeAR_weight"] == -5.0 and hp["GAMMA"] == 0.98 and hp["TAU"] == 0.01
+    assert hp["BATCH_SIZE"] == 128 and hp["LEARN_STEP"] == 10 and hp["MEMORY_SIZE"] == 200000 and hp["TRAIN_STEPS"] == 150
+    assert maddpg.preset("custom")["WITH_FEAR"] is False and maddpg.preset("custom_fear_10")["FeAR_weight"] == -10.0
+    ref = "/root/reference/configs/custom_fear_5.yaml"
+    if os.path.exists(ref):
+        assert maddpg.load_yaml_config(ref) == hp
+
+
+def test_get_action_respects_mask_and_learn_reduces_critic_loss():
+    torch.manual_seed(0)
+    ag = maddpg.BatchedMADDPG(2, 160, 9, device="cpu", seed=1)
+    obs = torch.randn(64, 2, 160)
+    mask = torch.ones(64, 2, 9, dtype=torch.int8)
+    mask[:, :, 5:] = 0
+    cont, ids = ag.get_action(obs, mask, training=True)
+    assert cont.shape == (64, 2, 9) and ids.dtype == torch.int8 and int(ids.max()) <= 4
+    assert float(cont.min()) >= 0.0 and float(cont.max()) <= 1.0
+    batch = {"state": obs, "action": cont, "reward": torch.randn(64, 2), "next_state": torch.randn(64, 2, 160),
+             "done": torch.zeros(64, 2, dtype=torch.uint8)}
+    first = ag.learn(batch).critic_loss
+    for _ in range(60):
+        last = ag.learn(batch).critic_loss
+    assert float(last.sum()) < 0.5 * float(first.sum())
+
+
+def _grad_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)
+    ag = maddpg.BatchedMADDPG(2, 160, 9, device="cpu", seed=7 + rank)      # different initial weights per rank ...
+    ag.broadcast_parameters(0)                                              # ... until rank 0's are broadcast
+    g = torch.Generator().manual_seed(rank)                                 # different data shard per rank
+    batch = {"state": torch.randn(32, 2, 160, generator=g), "action": torch.rand(32, 2, 9, generator=g),
+             "reward": torch.randn(32, 2, generator=g), "next_state": torch.randn(32, 2, 160, generator=g),
+             "done": torch.zeros(32, 2, dtype=torch.uint8)}
+    torch.manual_seed(5)                                                    # same Gumbel noise on both ranks
+    for _ in range(3):
+        ag.learn(batch)
+    torch.save([p.detach().clone() for p in ag.parameters()], os.path.join(out, f"params{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_keeps_ranks_in_sync(tmp_path):
+    port = 29700 + (os.getpid() % 1000)
+    mp.spawn(_grad_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    p0 = torch.load(os.path.join(str(tmp_path), "params0.pt"))
+    p1 = torch.load(os.path.join(str(tmp_path), "params1.pt"))
+    assert all(torch.allclose(a, b, atol=1e-6) for a, b in zip(p0, p1))
+
+
+@pytest.mark.gpu
+def test_batched_training_loop_runs_on_gpu():
+    hp = maddpg.preset("custom_fear_5")
+    hp["MEMORY_SIZE"] = 20000
+    env = maddpg.make_env(hp, 512)
+    tr = maddpg.BatchedTrainer(env, hp=hp, seed=0)
+    st = tr.train(40)
+    assert st["env_steps"] == 40 * 512 and st["episodes"] > 0
+    assert len(tr.losses) >= 3 and all(bool(torch.isfinite(l.critic_loss).all()) for l in tr.losses)
+    b = tr.ring.sample(256, tr.gen)
+    assert b["state"].shape == (256, 2, 160) and b["action"].shape == (256, 2, 9)
+    # stored reward is FeAR_weight * fear + env reward (maddpg/agent.py:130)
+    s = int(b["t"][0]) % tr.ring.T
+    e = int(b["env"][0])
+    want = (-5.0 * tr.ring.fear[s, e] + tr.ring.reward[s, e].double()).float()
+    assert torch.equal(b["reward"][0], want)
