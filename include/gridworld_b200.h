@@ -117,6 +117,8 @@ typedef struct gw_io {
   uint32_t* info;                /* [E] bits 0-3 crash, 4-7 restricted, 8-9 learner crashes, 10-11 apples rewarded,
                                         12 ended, 13 unresolved collisions (reference prints a warning),
                                         14-15 distance-shaping reward fired for learner 0/1 */
+  uint64_t* obs_code;            /* [E] compact form of `obs` for gw_actor_forward: bits 0-31 the four agent cells
+                                        ((row<<4)|col, 8 bits each), 32-33 apples still shown, 34 fresh spawn (0.5 marker) */
 } gw_io;
 
 typedef struct gw_stats {          /* sums since gw_create / gw_reset_stats, this handle only */
@@ -169,6 +171,32 @@ int gw_update_world(gw_handle* h, int64_t n_cases, const int8_t* n_agents_per_ca
 int gw_fear_one_actor(gw_handle* h, int64_t n_cases, const int8_t* n_agents_per_case, const int8_t* positions,
                       const int8_t* actions, const int8_t* mdr, const int8_t* actor, const uint8_t* in_list,
                       double* resp, int8_t* n_mdr, int8_t* n_act, void* stream);
+
+/* ---- actor forward (K5): AgileRL `MADDPG.get_action` as called at maddpg/agent.py:109-113 -----------------------
+ * One actor per learner: Linear(H*W,128)-LayerNorm-ReLU-Linear(128,128)-LayerNorm-ReLU-Linear(128,9)-GumbelSoftmax
+ * (shapes from the reference's checkpoints), Gaussian exploration noise, clip to [0,1], action mask,
+ * arg-max.  The observation is never read: the first layer is evaluated from `obs_code` (an observation is the
+ * constant map template plus <= 5 special cells, so W1*obs is a constant vector plus <= 5 columns of W1); the
+ * 128x128 layer runs on the tensor cores (tcgen05.mma, bf16 inputs, fp32 accumulation in TMEM).
+ * All weight pointers are HOST pointers to fp32 arrays in PyTorch layout ([out, in]); they are packed and uploaded. */
+typedef struct gw_actor_weights {
+  const float* w1; const float* b1; const float* ln1_g; const float* ln1_b;   /* [128, H*W], [128], [128], [128] */
+  const float* w2; const float* b2; const float* ln2_g; const float* ln2_b;   /* [128, 128], [128], [128], [128] */
+  const float* w3; const float* b3;                                           /* [9, 128], [9] */
+} gw_actor_weights;
+
+typedef struct gw_actor gw_actor;
+
+/* `h` provides the map (template row), agent / learner counts and the device.  weights[k] belongs to learner k. */
+int gw_actor_create(gw_handle* h, const gw_actor_weights* weights, int n_learners, gw_actor** out);
+int gw_actor_update(gw_actor* a, const gw_actor_weights* weights, int n_learners, void* stream);   /* after a learn step */
+int gw_actor_destroy(gw_actor* a);
+/* obs_code [E] (device, from gw_step / gw_reset); action_mask int8 [E, L, 9] (device, nullable);
+ * cont_actions f32 [E, L, 9] and action_ids int8 [E, L] (device outputs).  training != 0: Gumbel and Gaussian noise
+ * drawn from Philox(seed, env id, step); training == 0: plain softmax, no noise. */
+int gw_actor_forward(gw_actor* a, int64_t num_envs, const uint64_t* obs_code, const int8_t* action_mask,
+                     float* cont_actions, int8_t* action_ids, int training, float expl_noise, float mean_noise,
+                     uint64_t seed, uint64_t step, void* stream);
 
 #ifdef __cplusplus
 }

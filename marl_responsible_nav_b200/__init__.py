@@ -12,9 +12,10 @@ from .scenarios import Scenario, builtin_scenario, load_scenario_json, policy_pr
 from .batched import BatchedGridWorld, StepOutput  # noqa: F401
 from .envs import CustomMAEnv, CustomEnv  # noqa: F401
 from .replay import ReplayRing  # noqa: F401
+from .actor import FusedActor  # noqa: F401
 from . import sharding  # noqa: F401
 from . import _native  # noqa: F401
 
 __all__ = ["BatchedGridWorld", "StepOutput", "CustomMAEnv", "CustomEnv", "Scenario", "builtin_scenario",
-           "load_scenario_json", "policy_probs", "ReplayRing", "sharding"]
+           "load_scenario_json", "policy_probs", "ReplayRing", "FusedActor", "sharding"]
 __version__ = "0.1.0"

@@ -12,7 +12,12 @@ GW_OBS_F32, GW_OBS_BF16 = 0, 1
 
 EXPORTS = ["gw_abi_version", "gw_build_info", "gw_default_config", "gw_create", "gw_destroy", "gw_last_error",
            "gw_reset", "gw_step", "gw_sync", "gw_state_bytes", "gw_get_state", "gw_set_state", "gw_get_stats",
-           "gw_reset_stats", "gw_launch_count", "gw_update_world", "gw_fear_one_actor"]
+           "gw_reset_stats", "gw_launch_count", "gw_update_world", "gw_fear_one_actor", "gw_actor_create", "gw_actor_update",
+           "gw_actor_destroy", "gw_actor_forward"]
+
+
+class GwActorWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w1", "b1", "ln1_g", "ln1_b", "w2", "b2", "ln2_g", "ln2_b", "w3", "b3")]
 
 
 class GwConfig(C.Structure):
@@ -35,7 +40,7 @@ class GwConfig(C.Structure):
 class GwIO(C.Structure):
     _fields_ = [(name, C.c_void_p) for name in (
         "learner_actions", "npc_actions", "spawn", "obs", "final_obs", "reward", "shaped_reward", "fear",
-        "terminated", "truncated", "ended", "action_mask", "positions", "info")]
+        "terminated", "truncated", "ended", "action_mask", "positions", "info", "obs_code")]
 
 
 class GwStats(C.Structure):
@@ -78,6 +83,10 @@ def load():
     lib.gw_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.gw_update_world.argtypes = [vp, i64] + [vp] * 8 + [vp]
     lib.gw_fear_one_actor.argtypes = [vp, i64] + [vp] * 9 + [vp]
+    lib.gw_actor_create.argtypes = [vp, C.POINTER(GwActorWeights), C.c_int, C.POINTER(vp)]
+    lib.gw_actor_update.argtypes = [vp, C.POINTER(GwActorWeights), C.c_int, vp]
+    lib.gw_actor_destroy.argtypes = [vp]
+    lib.gw_actor_forward.argtypes = [vp, i64, vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_uint64, C.c_uint64, vp]
     if lib.gw_abi_version() != 1:
         raise RuntimeError("libgridworld_b200.so ABI version mismatch")
     _lib = lib

@@ -34,6 +34,7 @@ class StepOutput:
     ended: Optional[torch.Tensor] = None         # u8 [E]
     info: Optional[torch.Tensor] = None          # int32 [E] packed (see gridworld_b200.h)
     final_obs: Optional[torch.Tensor] = None     # like obs; rows valid where ended != 0
+    obs_code: Optional[torch.Tensor] = None      # int64 [E] compact form of obs (input of FusedActor)
 
 
 def _check(t: Optional[torch.Tensor], name, dtype, shape, device):
@@ -105,7 +106,8 @@ class BatchedGridWorld:
             truncated=torch.zeros((E, L), dtype=torch.uint8, device=dev),
             ended=torch.zeros((E,), dtype=torch.uint8, device=dev),
             info=torch.zeros((E,), dtype=torch.int32, device=dev),
-            final_obs=None)
+            final_obs=None,
+            obs_code=torch.zeros((E,), dtype=torch.int64, device=dev))
         self._io_step, self._io_reset = self._make_io(True), self._make_io(False)
 
     # ------------------------------------------------------------------ helpers
@@ -144,6 +146,7 @@ class BatchedGridWorld:
     def _make_io(self, outputs: bool) -> N.GwIO:
         io, b = N.GwIO(), self.buf
         io.action_mask, io.positions = b.action_mask.data_ptr(), b.positions.data_ptr()
+        io.obs_code = b.obs_code.data_ptr()
         if outputs:
             self._point_outputs(io, b)
         return io
@@ -195,7 +198,8 @@ class BatchedGridWorld:
             mask = _check(mask.to(torch.uint8) if mask.dtype == torch.bool else mask, "mask", torch.uint8, (self.num_envs,), self.device)
             mptr = mask.data_ptr()
         N.check(self.lib.gw_reset(self._h, mptr, C.byref(io), self._stream()), self._h, "gw_reset")
-        return StepOutput(obs=self._view(obs), action_mask=self.buf.action_mask, positions=self.buf.positions)
+        return StepOutput(obs=self._view(obs), action_mask=self.buf.action_mask, positions=self.buf.positions,
+                          obs_code=self.buf.obs_code)
 
     def step(self, actions, npc_actions=None, spawn=None, obs_out: Optional[torch.Tensor] = None,
              final_obs_out: Optional[torch.Tensor] = None, buffers=None) -> StepOutput:
@@ -213,7 +217,8 @@ class BatchedGridWorld:
         m = self.buf
         return StepOutput(obs=self._view(obs), action_mask=m.action_mask, positions=m.positions, reward=b.reward,
                           shaped_reward=b.shaped_reward, fear=b.fear, terminated=b.terminated, truncated=b.truncated,
-                          ended=b.ended, info=b.info, final_obs=self._view(fin) if fin is not None else None)
+                          ended=b.ended, info=b.info, final_obs=self._view(fin) if fin is not None else None,
+                          obs_code=m.obs_code)
 
     def sync(self):
         N.check(self.lib.gw_sync(self._h, self._stream()), self._h, "gw_sync")

@@ -1,0 +1,434 @@
+// K5: actor forward for the batched rollout (AgileRL MADDPG.get_action as called at maddpg/agent.py:109-113).
+//
+// Per learner k: obs(160) -> Linear 128 -> LayerNorm -> ReLU -> Linear 128 -> LayerNorm -> ReLU -> Linear 9 ->
+// GumbelSoftmax (+ Gaussian exploration noise, clip [0,1], action mask, arg-max).
+//
+// One CTA = 128 rows (envs) of one learner, one thread per row:
+//   layer 1  An observation is the constant map template plus <= 5 special cells, so W1*obs + b1 is a per-learner
+//            constant vector plus <= 5 columns of W1 scaled by (value - template value).  The thread builds its row from
+//            the 8-byte obs_code gw_step wrote; the 640-byte observation is never read.  LayerNorm + ReLU in registers,
+//            the row goes to shared memory as bf16 in the canonical K-major UMMA layout (8x16-byte core matrices).
+//   layer 2  [128 x 128] x [128 x 128]^T on the tensor cores: one elected thread issues 8 tcgen05.mma (M=128, N=128,
+//            K=16, bf16 -> fp32) that accumulate in TMEM, tcgen05.commit arrives on an mbarrier.
+//   epilogue each warp pulls its 32 TMEM lanes back with tcgen05.ld (thread = row, 128 fp32 accumulators), LayerNorm,
+//            ReLU, the 128 -> 9 layer, Gumbel softmax / noise / mask / arg-max, all in the row's thread.
+// sm_100a only (tcgen05 / TMEM); descriptors follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "gw_internal.h"
+
+namespace gwa {
+
+constexpr int HID = 128, NACT = GW_N_ACTIONS, ROWS = 128, MAX_CELLS = GW_MAX_H * GW_W;
+
+struct ActorParams {                     // device-resident, per learner
+  float w1t[MAX_CELLS][HID];             // W1 transposed: one 512-byte row per observation cell
+  float c1[HID];                         // b1 + W1 * template row
+  float ln1_g[HID], ln1_b[HID];
+  alignas(16) __nv_bfloat16 w2_umma[HID * HID];   // W2 [out n][in k] in the canonical K-major core-matrix layout
+  float b2[HID], ln2_g[HID], ln2_b[HID];
+  float w3[NACT][HID];
+  float b3[NACT];
+};
+
+struct FwdArgs {
+  const ActorParams* params;             // [n_learners]
+  const unsigned long long* obs_code;    // [E]
+  const int8_t* action_mask;             // [E, L, 9] or null
+  float* cont;                           // [E, L, 9]
+  int8_t* ids;                           // [E, L]
+  long long E;
+  int n, nl, kind, cpo;
+  uint32_t apple_cells;
+  int training;
+  float expl_noise, mean_noise;
+  uint32_t seed_lo, seed_hi, step_lo, step_hi;
+};
+
+// byte offset of element (row r, k) in a [128 x 128] bf16 operand tile laid out as 8x(16 B) core matrices:
+// K-chunk major, then 8-row group.  LBO (K-adjacent core matrices) = 2048 B, SBO (adjacent row groups) = 128 B.
+__host__ __device__ __forceinline__ uint32_t umma_off(int r, int k) {
+  return (uint32_t)(((k >> 3) * 16 + (r >> 3)) * 128 + (r & 7) * 16 + (k & 7) * 2);
+}
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr) {
+  // cute::UMMA::SmemDescriptor: start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46), version = 1 [46,48), SWIZZLE_NONE
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) |
+         (1ull << 46);
+}
+
+// cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b format BF16 (1) [7,10)/[10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+
+struct Smem {
+  alignas(1024) uint8_t a_tile[ROWS * HID * 2];     // activations of layer 1 (bf16, UMMA layout)
+  alignas(1024) uint8_t b_tile[HID * HID * 2];      // W2
+  alignas(16) float w3[NACT][HID];
+  float b3[NACT];
+  float b2[HID], ln2_g[HID], ln2_b[HID];
+  alignas(8) unsigned long long bar;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float gumbel_from(uint32_t w) {
+  const float u = fmaxf(((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f), 1e-20f);
+  return -__logf(-__logf(u) + 1e-20f);
+}
+__device__ __forceinline__ float gauss_from(uint32_t a, uint32_t b) {          // Box-Muller
+  const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307f * u2);
+}
+
+__global__ void __launch_bounds__(ROWS, 1) actor_forward_kernel(FwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int k = blockIdx.y;                               // learner
+  const ActorParams& P = a.params[k];
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.bar);
+
+  // ---- one-time setup: TMEM columns for the 128x128 fp32 accumulator, mbarrier, W2 / W3 / LN2 into shared memory
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(&s.tmem_base)), "n"(HID));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(P.w2_umma);
+    uint4* dst = reinterpret_cast<uint4*>(s.b_tile);
+    for (int i = tid; i < HID * HID * 2 / 16; i += ROWS) dst[i] = __ldg(src + i);
+    for (int i = tid; i < NACT * HID; i += ROWS) (&s.w3[0][0])[i] = (&P.w3[0][0])[i];
+    if (tid < NACT) s.b3[tid] = P.b3[tid];
+    s.b2[tid] = P.b2[tid];
+    s.ln2_g[tid] = P.ln2_g[tid];
+    s.ln2_b[tid] = P.ln2_b[tid];
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes of W2 -> visible to the MMA
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = s.tmem_base;
+  const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(s.a_tile);
+  const uint32_t b_addr = (uint32_t)__cvta_generic_to_shared(s.b_tile);
+  uint32_t phase = 0;
+
+  const long long n_tiles = (a.E + ROWS - 1) / ROWS;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long e = tile * ROWS + tid;
+    const bool live = e < a.E;
+
+    // ---- layer 1 from the observation code: h = c1 + sum_s (value_s - template_s) * W1[:, cell_s]; template_s = 0
+    // (agents and apples only stand on active cells)
+    int cells_s[5];
+    float vals_s[5];
+    int ns = 0;
+    if (live) {
+      const unsigned long long code = a.obs_code[e];
+      const uint32_t cells = (uint32_t)code, apples = (uint32_t)(code >> 32) & 3u;
+      const bool fresh = (code >> 34) & 1ull;
+      const bool apple_on = (a.kind == GW_ENV_MULTI) ? ((apples >> k) & 1u) : (apples & 1u);
+      const uint32_t apple = (a.kind == GW_ENV_MULTI) ? (a.apple_cells >> (8 * k)) & 0xFFu : a.apple_cells & 0xFFu;
+      bool covered = false;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i >= a.n) break;
+        const uint32_t c = (cells >> (8 * i)) & 0xFFu;
+        const bool here = apple_on && c == apple;
+        covered |= here;
+        float v;                                         // same value rules as the renderer (ma_customenv.py:303-322)
+        if (fresh) v = 0.5f;
+        else if (here || a.kind == GW_ENV_SINGLE) v = (float)(i + 1);
+        else v = (i == k) ? 1.0f : 5.0f;
+        cells_s[ns] = (int)c;
+        vals_s[ns] = here ? v + 9.0f : v;
+        ++ns;
+      }
+      if (apple_on && !covered) { cells_s[ns] = (int)apple; vals_s[ns] = 9.0f; ++ns; }
+    }
+    float mean = 0.f, m2 = 0.f;
+    // two passes over the 128 outputs in chunks of 8 (first: LayerNorm statistics, second: normalise and store)
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      float rstd = 0.f;
+      if (pass == 1) {
+        mean *= (1.0f / HID);
+        rstd = rsqrtf(fmaxf(m2 * (1.0f / HID) - mean * mean, 0.f) + 1e-5f);
+      }
+#pragma unroll 1
+      for (int j0 = 0; j0 < HID; j0 += 8) {
+        float h[8];
+        {
+          const float4 c0 = *reinterpret_cast<const float4*>(&P.c1[j0]), c1v = *reinterpret_cast<const float4*>(&P.c1[j0 + 4]);
+          h[0] = c0.x; h[1] = c0.y; h[2] = c0.z; h[3] = c0.w; h[4] = c1v.x; h[5] = c1v.y; h[6] = c1v.z; h[7] = c1v.w;
+        }
+        for (int q = 0; q < ns; ++q) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(&P.w1t[cells_s[q]][j0]));
+          const float4 w1v = __ldg(reinterpret_cast<const float4*>(&P.w1t[cells_s[q]][j0 + 4]));
+          const float v = vals_s[q];
+          h[0] = fmaf(v, w0.x, h[0]); h[1] = fmaf(v, w0.y, h[1]); h[2] = fmaf(v, w0.z, h[2]); h[3] = fmaf(v, w0.w, h[3]);
+          h[4] = fmaf(v, w1v.x, h[4]); h[5] = fmaf(v, w1v.y, h[5]); h[6] = fmaf(v, w1v.z, h[6]); h[7] = fmaf(v, w1v.w, h[7]);
+        }
+        if (pass == 0) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { mean += h[u]; m2 = fmaf(h[u], h[u], m2); }
+        } else {
+          uint32_t packed[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float x0 = fmaxf((h[2 * u] - mean) * rstd * P.ln1_g[j0 + 2 * u] + P.ln1_b[j0 + 2 * u], 0.f);
+            const float x1 = fmaxf((h[2 * u + 1] - mean) * rstd * P.ln1_g[j0 + 2 * u + 1] + P.ln1_b[j0 + 2 * u + 1], 0.f);
+            packed[u] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(live ? x0 : 0.f)) |
+                        ((uint32_t)__bfloat16_as_ushort(__float2bfloat16(live ? x1 : 0.f)) << 16);
+          }
+          *reinterpret_cast<uint4*>(s.a_tile + umma_off(tid, j0)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // activations -> visible to the tensor-core proxy
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+
+    // ---- layer 2 on the tensor cores: D[128x128] (TMEM) = A[128x128] * W2^T, eight K=16 steps, one issuing thread
+    if (tid == 0) {
+#pragma unroll
+      for (int kk = 0; kk < HID / 16; ++kk) {
+        const uint64_t da = smem_desc(a_addr + kk * 4096), db = smem_desc(b_addr + kk * 4096);
+        const uint32_t acc = kk > 0 ? 1u : 0u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(da), "l"(db), "r"(IDESC), "r"(acc)
+            : "memory");
+      }
+      // completion of all prior MMAs arrives on the mbarrier (implies tcgen05.fence::before_thread_sync)
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;");
+
+    // ---- epilogue: thread = row; its warp owns TMEM lanes 32*warp .. 32*warp+31
+    float acc[HID];
+#pragma unroll
+    for (int c0 = 0; c0 < HID; c0 += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int u = 0; u < 32; ++u) acc[c0 + u] = __uint_as_float(r[u]) + s.b2[c0 + u];
+    }
+    // TMEM has been read: the next tile's MMA may overwrite it once every warp is past this point
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    float mu = 0.f, sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < HID; ++j) { mu += acc[j]; sq = fmaf(acc[j], acc[j], sq); }
+    mu *= (1.0f / HID);
+    const float rs = rsqrtf(fmaxf(sq * (1.0f / HID) - mu * mu, 0.f) + 1e-5f);
+    float logit[NACT];
+#pragma unroll
+    for (int o = 0; o < NACT; ++o) logit[o] = s.b3[o];
+#pragma unroll
+    for (int j = 0; j < HID; ++j) {
+      const float x = fmaxf((acc[j] - mu) * rs * s.ln2_g[j] + s.ln2_b[j], 0.f);
+#pragma unroll
+      for (int o = 0; o < NACT; ++o) logit[o] = fmaf(x, s.w3[o][j], logit[o]);
+    }
+    if (live) {
+      // GumbelSoftmax head (fresh Gumbel noise per forward) + Gaussian exploration noise, both from Philox
+      uint32_t rnd[28];                                  // 9 Gumbel uniforms + 9 x 2 Box-Muller uniforms
+      if (a.training) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+          uint32_t w[4] = {(uint32_t)e, (uint32_t)((unsigned long long)e >> 32) ^ ((uint32_t)k << 24) ^ ((uint32_t)c << 28),
+                           a.step_lo, a.step_hi ^ 0xAC70u};
+          gw::philox4x32(w, a.seed_lo, a.seed_hi);
+          rnd[4 * c] = w[0]; rnd[4 * c + 1] = w[1]; rnd[4 * c + 2] = w[2]; rnd[4 * c + 3] = w[3];
+        }
+#pragma unroll
+        for (int o = 0; o < NACT; ++o) logit[o] += gumbel_from(rnd[o]);
+      }
+      float mx = logit[0];
+#pragma unroll
+      for (int o = 1; o < NACT; ++o) mx = fmaxf(mx, logit[o]);
+      float den = 0.f, pr[NACT];
+#pragma unroll
+      for (int o = 0; o < NACT; ++o) { pr[o] = __expf(logit[o] - mx); den += pr[o]; }
+      const float inv = 1.0f / den;
+      int best = 0;
+      float best_v = -1e30f;
+      const int8_t* mk = a.action_mask ? a.action_mask + (e * a.nl + k) * NACT : nullptr;
+      float* out = a.cont + (e * a.nl + k) * NACT;
+#pragma unroll
+      for (int o = 0; o < NACT; ++o) {
+        float v = pr[o] * inv;
+        if (a.training) {
+          const float g = gauss_from(rnd[9 + 2 * o], rnd[10 + 2 * o]);
+          v = fminf(fmaxf(v + a.mean_noise + a.expl_noise * g, 0.f), 1.f);
+        }
+        out[o] = v;
+        const bool ok = mk == nullptr || mk[o] != 0;
+        if (ok && v > best_v) { best_v = v; best = o; }
+      }
+      a.ids[e * a.nl + k] = (int8_t)best;
+    }
+    __syncthreads();                                     // every warp has drained TMEM and a_tile is free again
+    asm volatile("tcgen05.fence::after_thread_sync;");
+  }
+
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(HID));
+}
+
+}  // namespace gwa
+
+// ====================================================================== host side / C-ABI
+struct gw_actor {
+  gw_handle* h = nullptr;
+  gwa::ActorParams* d_params = nullptr;
+  int n_learners = 0;
+};
+
+static int pack_weights(gw_handle* h, const gw_actor_weights* w, int nl, std::vector<gwa::ActorParams>& host) {
+  const gw_config& c = h->cfg;
+  const int cpo = c.height * GW_W;
+  host.assign(nl, gwa::ActorParams());
+  for (int k = 0; k < nl; ++k) {
+    const gw_actor_weights& W = w[k];
+    if (!W.w1 || !W.b1 || !W.ln1_g || !W.ln1_b || !W.w2 || !W.b2 || !W.ln2_g || !W.ln2_b || !W.w3 || !W.b3)
+      return gw_fail(h, GW_EINVAL, "gw_actor: null weight pointer");
+    gwa::ActorParams& P = host[k];
+    std::memset(&P, 0, sizeof(P));
+    for (int j = 0; j < gwa::HID; ++j) {
+      double acc = W.b1[j];
+      for (int cell = 0; cell < cpo; ++cell) {
+        P.w1t[cell][j] = W.w1[j * cpo + cell];
+        const bool active = (c.map_rows[cell >> 4] >> (cell & 15)) & 1;
+        if (!active) acc -= (double)W.w1[j * cpo + cell];              // template value -1 on inactive cells, 0 elsewhere
+      }
+      P.c1[j] = (float)acc;
+      P.ln1_g[j] = W.ln1_g[j]; P.ln1_b[j] = W.ln1_b[j];
+      P.b2[j] = W.b2[j]; P.ln2_g[j] = W.ln2_g[j]; P.ln2_b[j] = W.ln2_b[j];
+    }
+    for (int n = 0; n < gwa::HID; ++n)
+      for (int kk = 0; kk < gwa::HID; ++kk)
+        P.w2_umma[gwa::umma_off(n, kk) / 2] = __float2bfloat16(W.w2[n * gwa::HID + kk]);
+    for (int o = 0; o < gwa::NACT; ++o) {
+      P.b3[o] = W.b3[o];
+      for (int j = 0; j < gwa::HID; ++j) P.w3[o][j] = W.w3[o * gwa::HID + j];
+    }
+  }
+  return GW_OK;
+}
+
+extern "C" {
+
+int gw_actor_create(gw_handle* h, const gw_actor_weights* weights, int n_learners, gw_actor** out) {
+  if (!h || !weights || !out) return gw_fail(h, GW_EINVAL, "gw_actor_create: null argument");
+  if (n_learners != h->cfg.n_learners) return gw_fail(h, GW_EINVAL, "gw_actor_create: one weight set per learner is required");
+  std::vector<gwa::ActorParams> host;
+  if (int rc = pack_weights(h, weights, n_learners, host)) return rc;
+  GW_CUDA(h, cudaSetDevice(h->cfg.device));
+  gw_actor* a = new (std::nothrow) gw_actor();
+  if (!a) return gw_fail(h, GW_ENOMEM, "gw_actor_create: host allocation failed");
+  a->h = h;
+  a->n_learners = n_learners;
+  cudaError_t e = cudaMalloc(&a->d_params, sizeof(gwa::ActorParams) * n_learners);
+  if (e == cudaSuccess) e = cudaMemcpy(a->d_params, host.data(), sizeof(gwa::ActorParams) * n_learners, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(gwa::actor_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(gwa::Smem) + 1024);
+  if (e != cudaSuccess) {
+    if (a->d_params) cudaFree(a->d_params);
+    delete a;
+    return gw_cuda_fail(h, e, "gw_actor_create");
+  }
+  *out = a;
+  return GW_OK;
+}
+
+int gw_actor_update(gw_actor* a, const gw_actor_weights* weights, int n_learners, void* stream) {
+  if (!a || !weights) return GW_EINVAL;
+  if (n_learners != a->n_learners) return gw_fail(a->h, GW_EINVAL, "gw_actor_update: learner count changed");
+  std::vector<gwa::ActorParams> host;
+  if (int rc = pack_weights(a->h, weights, n_learners, host)) return rc;
+  GW_CUDA(a->h, cudaSetDevice(a->h->cfg.device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GW_CUDA(a->h, cudaMemcpyAsync(a->d_params, host.data(), sizeof(gwa::ActorParams) * n_learners, cudaMemcpyHostToDevice, s));
+  GW_CUDA(a->h, cudaStreamSynchronize(s));            // `host` is a temporary
+  return GW_OK;
+}
+
+int gw_actor_destroy(gw_actor* a) {
+  if (!a) return GW_OK;
+  cudaSetDevice(a->h->cfg.device);
+  if (a->d_params) cudaFree(a->d_params);
+  delete a;
+  return GW_OK;
+}
+
+int gw_actor_forward(gw_actor* a, int64_t num_envs, const uint64_t* obs_code, const int8_t* action_mask,
+                     float* cont_actions, int8_t* action_ids, int training, float expl_noise, float mean_noise,
+                     uint64_t seed, uint64_t step, void* stream) {
+  if (!a) return GW_EINVAL;
+  gw_handle* h = a->h;
+  if (num_envs < 0 || !obs_code || !cont_actions || !action_ids) return gw_fail(h, GW_EINVAL, "gw_actor_forward: null argument");
+  if (num_envs == 0) return GW_OK;
+  GW_CUDA(h, cudaSetDevice(h->cfg.device));
+  gwa::FwdArgs f;
+  std::memset(&f, 0, sizeof(f));
+  f.params = a->d_params;
+  f.obs_code = reinterpret_cast<const unsigned long long*>(obs_code);
+  f.action_mask = action_mask;
+  f.cont = cont_actions;
+  f.ids = action_ids;
+  f.E = num_envs;
+  f.n = h->cfg.n_agents; f.nl = h->cfg.n_learners; f.kind = h->cfg.env_kind; f.cpo = h->cfg.height * GW_W;
+  for (int k = 0; k < h->cfg.n_learners; ++k)
+    if (h->cfg.apple_row[k] >= 0) f.apple_cells |= (uint32_t)((h->cfg.apple_row[k] << 4) | h->cfg.apple_col[k]) << (8 * k);
+  f.training = training; f.expl_noise = expl_noise; f.mean_noise = mean_noise;
+  f.seed_lo = (uint32_t)seed; f.seed_hi = (uint32_t)(seed >> 32);
+  f.step_lo = (uint32_t)step; f.step_hi = (uint32_t)(step >> 32);
+  const long long tiles = (num_envs + gwa::ROWS - 1) / gwa::ROWS;
+  const long long cap = (long long)h->sm_count * 2;
+  dim3 grid((unsigned)(tiles < cap ? tiles : cap), (unsigned)h->cfg.n_learners);
+  gwa::actor_forward_kernel<<<grid, gwa::ROWS, sizeof(gwa::Smem) + 1024, static_cast<cudaStream_t>(stream)>>>(f);
+  GW_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+}  // extern "C"

@@ -388,6 +388,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_reset_kernel(StepP
       const uint32_t cells = spawn_cells(p, s.small, e, st.z);
       const uint32_t meta = fresh_meta(p, cells);
       s.rinfo[tid] = (meta & M_APPLES) | R_FRESH;
+      if (p.io.obs_code) p.io.obs_code[e] = (unsigned long long)cells | ((unsigned long long)(meta & M_APPLES) << 32) | (1ull << 34);
       encode_specials(s.spec[tid], p.H * GW_W, p.n, p.nl, p.kind, cells, meta & M_APPLES, p.apple_cells, true);
       stage_masks(s, p, tid, cells);
       write_positions(p.io.positions, e, p.n, cells);
@@ -633,6 +634,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
         st_out = make_uint4(cells_r, meta_sp, tick + 1, 0u);
       }
       p.state[e] = st_out;
+      if (p.io.obs_code)
+        p.io.obs_code[e] = (unsigned long long)cells_r | ((unsigned long long)apples_r << 32) |
+                           ((rflags & R_FRESH) ? (1ull << 34) : 0ull);
       s.rinfo[tid] = apples_r | rflags;
       encode_specials(s.spec[tid], p.H * GW_W, n, nl, p.kind, cells_r, apples_r, p.apple_cells, (rflags & R_FRESH) != 0);
       cells_render = cells_r;
@@ -849,29 +853,19 @@ __global__ void __launch_bounds__(128) gw_fear_kernel(const Tables* T, int n_def
 }  // namespace gw
 
 // ====================================================================== host side / C-ABI
-struct gw_handle {
-  gw_config cfg;
-  gw::Tables* d_tables = nullptr;
-  uint4* d_state = nullptr;
-  unsigned long long* d_stats = nullptr;
-  bool reset_done = false;
-  int sm_count = 148;
-  int n_active = 0;
-  uint64_t launches = 0;
-  uint64_t env_steps = 0;
-  std::string err;
-};
+#include "gw_internal.h"
 
-static thread_local std::string g_create_err;
+thread_local std::string g_gw_create_err;
 
-static int fail(gw_handle* h, int code, const std::string& msg) {
-  if (h) h->err = msg; else g_create_err = msg;
+int gw_fail(gw_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_gw_create_err = msg;
   return code;
 }
-static int cuda_fail(gw_handle* h, cudaError_t e, const char* what) {
-  return fail(h, GW_ECUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+int gw_cuda_fail(gw_handle* h, cudaError_t e, const char* what) {
+  return gw_fail(h, GW_ECUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
 }
-#define GW_CUDA(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(h, e_, #call); } while (0)
+static int fail(gw_handle* h, int code, const std::string& msg) { return gw_fail(h, code, msg); }
+static int cuda_fail(gw_handle* h, cudaError_t e, const char* what) { return gw_cuda_fail(h, e, what); }
 
 extern "C" {
 
@@ -887,7 +881,7 @@ const char* gw_build_info(void) {
       ;
 }
 
-const char* gw_last_error(const gw_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+const char* gw_last_error(const gw_handle* h) { return h ? h->err.c_str() : g_gw_create_err.c_str(); }
 
 int gw_default_config(gw_config* cfg) {
   if (!cfg) return GW_EINVAL;

@@ -1,0 +1,54 @@
+"""GPU: the tcgen05 actor-forward kernel vs the same network evaluated by PyTorch in fp32 on the rendered observation.
+AgileRL is absent (parity unpinned); the tolerance is that of one bf16 128x128 GEMM with fp32 accumulation."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _reference(actor, obs):
+    logits = actor[:-1](obs.float())                      # everything but the GumbelSoftmax head
+    return torch.softmax(logits, dim=-1)
+
+
+@pytest.mark.parametrize("E", [100, 4096, 20000])
+def test_fused_actor_matches_torch_fp32(E):
+    from marl_responsible_nav_b200 import BatchedGridWorld, FusedActor, maddpg
+    env = BatchedGridWorld("Level 3", num_envs=E, fear=False, auto_reset=True, seed=5)
+    agent = maddpg.BatchedMADDPG(2, 160, 9, device="cuda", seed=3)
+    for a in agent.actors:                                # non-trivial LayerNorm parameters
+        for m in a:
+            if isinstance(m, torch.nn.LayerNorm):
+                torch.nn.init.normal_(m.weight, 1.0, 0.2); torch.nn.init.normal_(m.bias, 0.0, 0.2)
+    fused = FusedActor(env, agent.actors, seed=1)
+    out = env.reset()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(6):
+        cont, ids = fused.forward(out.obs_code, out.action_mask, training=False)
+        for k in range(2):
+            ref = _reference(agent.actors[k], out.obs[:, k])
+            assert torch.allclose(cont[:, k], ref, atol=2e-2), float((cont[:, k] - ref).abs().max())
+            masked = ref.masked_fill(out.action_mask[:, k] == 0, -1.0)
+            agree = (masked.argmax(-1) == ids[:, k].long()).float().mean().item()
+            assert agree > 0.97, agree
+            assert (out.action_mask[:, k].gather(1, ids[:, k].long()[:, None]) == 1).all()     # never a masked action
+        out = env.step(torch.randint(0, 9, (E, 2), generator=gen, device="cuda", dtype=torch.int8))
+
+
+def test_fused_actor_training_noise_and_update():
+    from marl_responsible_nav_b200 import BatchedGridWorld, FusedActor, maddpg
+    E = 8192
+    env = BatchedGridWorld("Level 3", num_envs=E, fear=False, seed=6)
+    agent = maddpg.BatchedMADDPG(2, 160, 9, device="cuda", seed=4)
+    fused = FusedActor(env, agent.actors, seed=2)
+    out = env.reset()
+    c1, i1 = (t.clone() for t in fused.forward(out.obs_code, out.action_mask, training=True, expl_noise=0.1))
+    c2, i2 = (t.clone() for t in fused.forward(out.obs_code, out.action_mask, training=True, expl_noise=0.1))
+    assert float(c1.min()) >= 0.0 and float(c1.max()) <= 1.0
+    assert not torch.equal(c1, c2)                        # fresh noise every step
+    assert 0.05 < (i1 != i2).float().mean().item() < 0.999
+    with torch.no_grad():                                 # new weights take effect after update()
+        agent.actors[0][-2].bias.add_(torch.tensor([50.0] + [0.0] * 8, device="cuda"))
+    fused.update(agent.actors)
+    _, ids = fused.forward(out.obs_code, None, training=False)
+    assert (ids[:, 0] == 0).all()
