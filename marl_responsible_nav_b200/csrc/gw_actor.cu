@@ -100,7 +100,7 @@ __device__ __forceinline__ float gauss_from(uint32_t a, uint32_t b) {          /
   return sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307f * u2);
 }
 
-__global__ void __launch_bounds__(ROWS, 1) actor_forward_kernel(FwdArgs a) {
+__global__ void __launch_bounds__(ROWS, 3) actor_forward_kernel(FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -170,44 +170,40 @@ __global__ void __launch_bounds__(ROWS, 1) actor_forward_kernel(FwdArgs a) {
       }
       if (apple_on && !covered) { cells_s[ns] = (int)apple; vals_s[ns] = 9.0f; ++ns; }
     }
+    // the whole row stays in registers: c1 plus the special cells' columns of W1, LayerNorm, ReLU, bf16, shared memory
+    float h[HID];
+#pragma unroll
+    for (int j0 = 0; j0 < HID; j0 += 4) {
+      const float4 c = *reinterpret_cast<const float4*>(&P.c1[j0]);
+      h[j0] = c.x; h[j0 + 1] = c.y; h[j0 + 2] = c.z; h[j0 + 3] = c.w;
+    }
+    for (int q = 0; q < ns; ++q) {
+      const float4* col = reinterpret_cast<const float4*>(P.w1t[cells_s[q]]);
+      const float v = vals_s[q];
+#pragma unroll
+      for (int j0 = 0; j0 < HID; j0 += 4) {
+        const float4 w = __ldg(col + (j0 >> 2));
+        h[j0] = fmaf(v, w.x, h[j0]); h[j0 + 1] = fmaf(v, w.y, h[j0 + 1]);
+        h[j0 + 2] = fmaf(v, w.z, h[j0 + 2]); h[j0 + 3] = fmaf(v, w.w, h[j0 + 3]);
+      }
+    }
     float mean = 0.f, m2 = 0.f;
-    // two passes over the 128 outputs in chunks of 8 (first: LayerNorm statistics, second: normalise and store)
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      float rstd = 0.f;
-      if (pass == 1) {
-        mean *= (1.0f / HID);
-        rstd = rsqrtf(fmaxf(m2 * (1.0f / HID) - mean * mean, 0.f) + 1e-5f);
-      }
-#pragma unroll 1
-      for (int j0 = 0; j0 < HID; j0 += 8) {
-        float h[8];
-        {
-          const float4 c0 = *reinterpret_cast<const float4*>(&P.c1[j0]), c1v = *reinterpret_cast<const float4*>(&P.c1[j0 + 4]);
-          h[0] = c0.x; h[1] = c0.y; h[2] = c0.z; h[3] = c0.w; h[4] = c1v.x; h[5] = c1v.y; h[6] = c1v.z; h[7] = c1v.w;
-        }
-        for (int q = 0; q < ns; ++q) {
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(&P.w1t[cells_s[q]][j0]));
-          const float4 w1v = __ldg(reinterpret_cast<const float4*>(&P.w1t[cells_s[q]][j0 + 4]));
-          const float v = vals_s[q];
-          h[0] = fmaf(v, w0.x, h[0]); h[1] = fmaf(v, w0.y, h[1]); h[2] = fmaf(v, w0.z, h[2]); h[3] = fmaf(v, w0.w, h[3]);
-          h[4] = fmaf(v, w1v.x, h[4]); h[5] = fmaf(v, w1v.y, h[5]); h[6] = fmaf(v, w1v.z, h[6]); h[7] = fmaf(v, w1v.w, h[7]);
-        }
-        if (pass == 0) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) { mean += h[u]; m2 = fmaf(h[u], h[u], m2); }
-        } else {
-          uint32_t packed[4];
+    for (int j = 0; j < HID; ++j) { mean += h[j]; m2 = fmaf(h[j], h[j], m2); }
+    mean *= (1.0f / HID);
+    const float rstd = rsqrtf(fmaxf(m2 * (1.0f / HID) - mean * mean, 0.f) + 1e-5f);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float x0 = fmaxf((h[2 * u] - mean) * rstd * P.ln1_g[j0 + 2 * u] + P.ln1_b[j0 + 2 * u], 0.f);
-            const float x1 = fmaxf((h[2 * u + 1] - mean) * rstd * P.ln1_g[j0 + 2 * u + 1] + P.ln1_b[j0 + 2 * u + 1], 0.f);
-            packed[u] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(live ? x0 : 0.f)) |
-                        ((uint32_t)__bfloat16_as_ushort(__float2bfloat16(live ? x1 : 0.f)) << 16);
-          }
-          *reinterpret_cast<uint4*>(s.a_tile + umma_off(tid, j0)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        }
+    for (int j0 = 0; j0 < HID; j0 += 8) {
+      uint32_t packed[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + 2 * u;
+        const float x0 = fmaxf((h[j] - mean) * rstd * P.ln1_g[j] + P.ln1_b[j], 0.f);
+        const float x1 = fmaxf((h[j + 1] - mean) * rstd * P.ln1_g[j + 1] + P.ln1_b[j + 1], 0.f);
+        packed[u] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(live ? x0 : 0.f)) |
+                    ((uint32_t)__bfloat16_as_ushort(__float2bfloat16(live ? x1 : 0.f)) << 16);
       }
+      *reinterpret_cast<uint4*>(s.a_tile + umma_off(tid, j0)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // activations -> visible to the tensor-core proxy
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -263,10 +259,15 @@ __global__ void __launch_bounds__(ROWS, 1) actor_forward_kernel(FwdArgs a) {
 #pragma unroll
     for (int o = 0; o < NACT; ++o) logit[o] = s.b3[o];
 #pragma unroll
-    for (int j = 0; j < HID; ++j) {
-      const float x = fmaxf((acc[j] - mu) * rs * s.ln2_g[j] + s.ln2_b[j], 0.f);
+    for (int j0 = 0; j0 < HID; j0 += 4) {
+      float x[4];
 #pragma unroll
-      for (int o = 0; o < NACT; ++o) logit[o] = fmaf(x, s.w3[o][j], logit[o]);
+      for (int u = 0; u < 4; ++u) x[u] = fmaxf((acc[j0 + u] - mu) * rs * s.ln2_g[j0 + u] + s.ln2_b[j0 + u], 0.f);
+#pragma unroll
+      for (int o = 0; o < NACT; ++o) {
+        const float4 w = *reinterpret_cast<const float4*>(&s.w3[o][j0]);      // same address in every lane: broadcast
+        logit[o] = fmaf(x[0], w.x, fmaf(x[1], w.y, fmaf(x[2], w.z, fmaf(x[3], w.w, logit[o]))));
+      }
     }
     if (live) {
       // GumbelSoftmax head (fresh Gumbel noise per forward) + Gaussian exploration noise, both from Philox
@@ -423,7 +424,7 @@ int gw_actor_forward(gw_actor* a, int64_t num_envs, const uint64_t* obs_code, co
   f.seed_lo = (uint32_t)seed; f.seed_hi = (uint32_t)(seed >> 32);
   f.step_lo = (uint32_t)step; f.step_hi = (uint32_t)(step >> 32);
   const long long tiles = (num_envs + gwa::ROWS - 1) / gwa::ROWS;
-  const long long cap = (long long)h->sm_count * 2;
+  const long long cap = (long long)h->sm_count * 3 / (h->cfg.n_learners > 0 ? h->cfg.n_learners : 1);   // 3 CTAs per SM over all learners
   dim3 grid((unsigned)(tiles < cap ? tiles : cap), (unsigned)h->cfg.n_learners);
   gwa::actor_forward_kernel<<<grid, gwa::ROWS, sizeof(gwa::Smem) + 1024, static_cast<cudaStream_t>(stream)>>>(f);
   GW_CUDA(h, cudaGetLastError());
