@@ -143,10 +143,12 @@ __global__ void __launch_bounds__(ROWS, 3) actor_forward_kernel(FwdArgs a) {
     const bool live = e < a.E;
 
     // ---- layer 1 from the observation code: h = c1 + sum_s (value_s - template_s) * W1[:, cell_s]; template_s = 0
-    // (agents and apples only stand on active cells)
-    int cells_s[5];
-    float vals_s[5];
-    int ns = 0;
+    // (agents and apples only stand on active cells).  Each lane decodes the special cells of ITS row; then the warp
+    // walks its 32 rows together: lane l owns output columns 4l..4l+3, so every W1 column is one coalesced 512-byte
+    // read, and LayerNorm is a warp reduction.
+    const int lane = tid & 31;
+    uint32_t my_cells = 0xFFFFFFFFu, my_cell4 = 0xFFu;   // up to five cells (0xFF = unused) ...
+    float my_vals[5] = {0.f, 0.f, 0.f, 0.f, 0.f};        // ... and their values
     if (live) {
       const unsigned long long code = a.obs_code[e];
       const uint32_t cells = (uint32_t)code, apples = (uint32_t)(code >> 32) & 3u;
@@ -154,56 +156,54 @@ __global__ void __launch_bounds__(ROWS, 3) actor_forward_kernel(FwdArgs a) {
       const bool apple_on = (a.kind == GW_ENV_MULTI) ? ((apples >> k) & 1u) : (apples & 1u);
       const uint32_t apple = (a.kind == GW_ENV_MULTI) ? (a.apple_cells >> (8 * k)) & 0xFFu : a.apple_cells & 0xFFu;
       bool covered = false;
+      my_cells = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        if (i >= a.n) break;
         const uint32_t c = (cells >> (8 * i)) & 0xFFu;
-        const bool here = apple_on && c == apple;
+        const bool on = i < a.n;
+        const bool here = on && apple_on && c == apple;
         covered |= here;
         float v;                                         // same value rules as the renderer (ma_customenv.py:303-322)
         if (fresh) v = 0.5f;
         else if (here || a.kind == GW_ENV_SINGLE) v = (float)(i + 1);
         else v = (i == k) ? 1.0f : 5.0f;
-        cells_s[ns] = (int)c;
-        vals_s[ns] = here ? v + 9.0f : v;
-        ++ns;
+        my_cells |= (on ? c : 0xFFu) << (8 * i);
+        my_vals[i] = here ? v + 9.0f : v;
       }
-      if (apple_on && !covered) { cells_s[ns] = (int)apple; vals_s[ns] = 9.0f; ++ns; }
+      if (apple_on && !covered) { my_cell4 = apple; my_vals[4] = 9.0f; }
     }
-    // the whole row stays in registers: c1 plus the special cells' columns of W1, LayerNorm, ReLU, bf16, shared memory
-    float h[HID];
+    const float4 c1v = *reinterpret_cast<const float4*>(&P.c1[4 * lane]);
+    const float4 g1v = *reinterpret_cast<const float4*>(&P.ln1_g[4 * lane]);
+    const float4 b1v = *reinterpret_cast<const float4*>(&P.ln1_b[4 * lane]);
+#pragma unroll 2
+    for (int i = 0; i < 32; ++i) {
+      const uint32_t rc = __shfl_sync(0xFFFFFFFFu, my_cells, i), rc4 = __shfl_sync(0xFFFFFFFFu, my_cell4, i);
+      float4 h = c1v;
 #pragma unroll
-    for (int j0 = 0; j0 < HID; j0 += 4) {
-      const float4 c = *reinterpret_cast<const float4*>(&P.c1[j0]);
-      h[j0] = c.x; h[j0 + 1] = c.y; h[j0 + 2] = c.z; h[j0 + 3] = c.w;
-    }
-    for (int q = 0; q < ns; ++q) {
-      const float4* col = reinterpret_cast<const float4*>(P.w1t[cells_s[q]]);
-      const float v = vals_s[q];
-#pragma unroll
-      for (int j0 = 0; j0 < HID; j0 += 4) {
-        const float4 w = __ldg(col + (j0 >> 2));
-        h[j0] = fmaf(v, w.x, h[j0]); h[j0 + 1] = fmaf(v, w.y, h[j0 + 1]);
-        h[j0 + 2] = fmaf(v, w.z, h[j0 + 2]); h[j0 + 3] = fmaf(v, w.w, h[j0 + 3]);
+      for (int q = 0; q < 5; ++q) {
+        const float v = __shfl_sync(0xFFFFFFFFu, my_vals[q], i);
+        const uint32_t c = q < 4 ? (rc >> (8 * q)) & 0xFFu : rc4;
+        if (c != 0xFFu) {                                // warp-uniform
+          const float4 w = __ldg(reinterpret_cast<const float4*>(P.w1t[c]) + lane);
+          h.x = fmaf(v, w.x, h.x); h.y = fmaf(v, w.y, h.y); h.z = fmaf(v, w.z, h.z); h.w = fmaf(v, w.w, h.w);
+        }
       }
-    }
-    float mean = 0.f, m2 = 0.f;
+      float sum = (h.x + h.y) + (h.z + h.w), sq = fmaf(h.x, h.x, fmaf(h.y, h.y, fmaf(h.z, h.z, h.w * h.w)));
 #pragma unroll
-    for (int j = 0; j < HID; ++j) { mean += h[j]; m2 = fmaf(h[j], h[j], m2); }
-    mean *= (1.0f / HID);
-    const float rstd = rsqrtf(fmaxf(m2 * (1.0f / HID) - mean * mean, 0.f) + 1e-5f);
-#pragma unroll
-    for (int j0 = 0; j0 < HID; j0 += 8) {
-      uint32_t packed[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = j0 + 2 * u;
-        const float x0 = fmaxf((h[j] - mean) * rstd * P.ln1_g[j] + P.ln1_b[j], 0.f);
-        const float x1 = fmaxf((h[j + 1] - mean) * rstd * P.ln1_g[j + 1] + P.ln1_b[j + 1], 0.f);
-        packed[u] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(live ? x0 : 0.f)) |
-                    ((uint32_t)__bfloat16_as_ushort(__float2bfloat16(live ? x1 : 0.f)) << 16);
+      for (int d = 16; d > 0; d >>= 1) {
+        sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+        sq += __shfl_xor_sync(0xFFFFFFFFu, sq, d);
       }
-      *reinterpret_cast<uint4*>(s.a_tile + umma_off(tid, j0)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      const float mean = sum * (1.0f / HID);
+      const float rstd = rsqrtf(fmaxf(sq * (1.0f / HID) - mean * mean, 0.f) + 1e-5f);
+      const bool row_live = (rc != 0xFFFFFFFFu);
+      const float x0 = row_live ? fmaxf((h.x - mean) * rstd * g1v.x + b1v.x, 0.f) : 0.f;
+      const float x1 = row_live ? fmaxf((h.y - mean) * rstd * g1v.y + b1v.y, 0.f) : 0.f;
+      const float x2 = row_live ? fmaxf((h.z - mean) * rstd * g1v.z + b1v.z, 0.f) : 0.f;
+      const float x3 = row_live ? fmaxf((h.w - mean) * rstd * g1v.w + b1v.w, 0.f) : 0.f;
+      const uint32_t p0 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(x0)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16(x1)) << 16);
+      const uint32_t p1 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(x2)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16(x3)) << 16);
+      *reinterpret_cast<uint2*>(s.a_tile + umma_off(warp * 32 + i, 4 * lane)) = make_uint2(p0, p1);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // activations -> visible to the tensor-core proxy
     asm volatile("tcgen05.fence::before_thread_sync;");
