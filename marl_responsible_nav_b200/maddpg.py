@@ -187,7 +187,7 @@ class BatchedTrainer:
     """MADDPGAgent.train (maddpg/agent.py:77-252) for E environments at once, everything on the device."""
 
     def __init__(self, env, agent: Optional[BatchedMADDPG] = None, hp: Optional[Dict] = None,
-                 updates_per_learn: int = 1, seed: int = 0):
+                 updates_per_learn: int = 1, seed: int = 0, fused_actor: bool = True):
         from .replay import ReplayRing
         self.env = env
         self.hp = dict(DEFAULT_HP if hp is None else hp)
@@ -199,6 +199,11 @@ class BatchedTrainer:
         self.t = 0
         self.out = env.reset(obs_out=self.ring.obs_slot(0))
         self.losses: List[LearnStats] = []
+        # acting: the fused CUDA kernel (csrc/gw_actor.cu, tensor cores) or the PyTorch modules (same weights)
+        self.fused = None
+        if fused_actor and env.device.type == "cuda" and env.obs_len == self.agent.obs_dim:
+            from .actor import FusedActor
+            self.fused = FusedActor(env, self.agent.actors, seed=seed + 2)
 
     def train(self, env_steps: int, learn: bool = True) -> Dict[str, float]:
         """`env_steps` synchronous steps of all E envs (auto-reset replaces the reference's per-episode outer loop;
@@ -208,7 +213,11 @@ class BatchedTrainer:
         for _ in range(env_steps):
             t = self.t
             obs = ring.obs_slot(t)
-            cont, ids = agent.get_action(obs, self.out.action_mask, training=True)
+            if self.fused is not None:
+                cont, ids = self.fused.forward(self.out.obs_code, self.out.action_mask, training=True,
+                                               expl_noise=hp["EXPL_NOISE"], mean_noise=hp["MEAN_NOISE"])
+            else:
+                cont, ids = agent.get_action(obs, self.out.action_mask, training=True)
             self.out = env.step(ids, obs_out=ring.obs_slot(t + 1), final_obs_out=ring.final_slot(t),
                                 buffers=ring.buffers_slot(t))
             ring.store_action(t, cont)
@@ -218,6 +227,8 @@ class BatchedTrainer:
             if learn and t % hp["LEARN_STEP"] == 0 and len(ring) >= hp["BATCH_SIZE"]:
                 for _ in range(self.updates_per_learn):
                     self.losses.append(agent.learn(ring.sample(hp["BATCH_SIZE"], self.gen)))
+                if self.fused is not None:
+                    self.fused.update(agent.actors)          # the kernel keeps its own packed copy of the weights
         return env.stats()
 
 

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1500, help="synchronous env steps (the reference: MAX_EPISODES x TRAIN_STEPS)")
     ap.add_argument("--report", type=int, default=150)
     ap.add_argument("--updates-per-learn", type=int, default=1)
+    ap.add_argument("--torch-actor", action="store_true", help="act with the PyTorch modules instead of the fused kernel")
     a = ap.parse_args()
     hp = maddpg.load_yaml_config(a.config) if os.path.exists(a.config) else maddpg.preset(a.config)
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
@@ -32,7 +33,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     base, n = sharding.shard_range(a.envs, rank, world)
     env = maddpg.make_env(hp, n, device=dev, env_id_base=base)
-    trainer = maddpg.BatchedTrainer(env, hp=hp, updates_per_learn=a.updates_per_learn, seed=hp["SEED"])
+    trainer = maddpg.BatchedTrainer(env, hp=hp, updates_per_learn=a.updates_per_learn, seed=hp["SEED"],
+                                    fused_actor=not a.torch_actor)
     trainer.agent.broadcast_parameters(0)
     done = 0
     while done < a.steps:
