@@ -219,7 +219,7 @@ def device_timed(a, E, fear, K, W, world, rank, dev, sample_clocks=False):
     st = env.stats()
     t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
     stat_vec = torch.tensor([st["episodes"], st["episode_len_sum"], st["crashes"], st["apples"], st["fear_nonzero"],
-                             st["return_sum"], st["fear_sum"], st["unresolved"]], device=dev, dtype=torch.float64)
+                             st["return_sum"], st["fear_sum"], st["unresolved"], st["fear_tasks"]], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)          # time = max over ranks
         dist.all_reduce(stat_vec, op=dist.ReduceOp.SUM)      # episode statistics over NVLink (the only collective)
@@ -243,6 +243,7 @@ def run_ours(a):
     E, K, W = a.envs, a.steps, a.warmup
     r = device_timed(a, E, a.fear, K, W, world, rank, dev, sample_clocks=True)
     ms, stat_vec, env, ring, slots, L, obs_bytes, n_act = (r[k] for k in ("ms", "stats", "env", "ring", "slots", "L", "obs_bytes", "n_act"))
+    env_agents = env.n_agents
     clocks = r["clocks"]
     value = world * E * L * K / (ms * 1e-3)
 
@@ -253,22 +254,15 @@ def run_ours(a):
         host_actions = torch.randint(0, 9, (n_act, E, L), dtype=torch.int8).pin_memory()
         host_rew = torch.empty((E, L), dtype=torch.float32).pin_memory()
         host_end = torch.empty((E,), dtype=torch.uint8).pin_memory()
-        dev_act = torch.empty((E, L), dtype=torch.int8, device=dev)
+        # env.step_host = the public host-driven call: pinned actions H2D, gw_step, rewards + ended flags D2H, stream sync
         for t in range(10):
-            dev_act.copy_(host_actions[t % n_act], non_blocking=True)
-            out = env.step(dev_act, obs_out=ring[t % slots])
-            host_rew.copy_(out.reward, non_blocking=True)
-            torch.cuda.synchronize()
+            env.step_host(host_actions[t % n_act], host_rew, host_end, obs_out=ring[t % slots])
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for t in range(Ke):
-            dev_act.copy_(host_actions[t % n_act], non_blocking=True)
-            out = env.step(dev_act, obs_out=ring[t % slots])
-            host_rew.copy_(out.reward, non_blocking=True)
-            host_end.copy_(out.ended, non_blocking=True)
-            torch.cuda.synchronize()                          # a host-driven loop needs this step's result
+            env.step_host(host_actions[t % n_act], host_rew, host_end, obs_out=ring[t % slots])   # returns synchronised
         el = time.perf_counter() - t0
         t_e = torch.tensor([el], device=dev, dtype=torch.float64)
         if world > 1:
@@ -319,7 +313,11 @@ def run_ours(a):
                            "learner_crashes_per_env_step": stat_vec[2].item() / (world * E * K),
                            "apples_per_env_step": stat_vec[3].item() / (world * E * K),
                            "fear_nonzero_per_agent_step": stat_vec[4].item() / (world * E * L * K),
-                           "unresolved": stat_vec[7].item()},
+                           "unresolved": stat_vec[7].item(),
+                           "fear_tasks_per_env_step": stat_vec[8].item() / (world * E * K),
+                           "counterfactual_sims_per_s": 18.0 * stat_vec[8].item() / (ms * 1e-3),
+                           "reference_sims_per_env_step": 108},
+        "env_steps_per_s": value / L, "entity_steps_per_s": value / L * env_agents,
     }
     if not a.no_cpu_baseline and world == 1:
         try:

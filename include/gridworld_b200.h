@@ -132,6 +132,7 @@ typedef struct gw_stats {          /* sums since gw_create / gw_reset_stats, thi
   uint64_t fear_nonzero;           /* learner-steps with fear != 0 */
   double return_sum;               /* sum of env rewards over finished episodes (all learners) */
   double fear_sum;
+  uint64_t fear_tasks;             /* (actor, affected) pairs that needed counterfactual simulation (18 sims each) */
 } gw_stats;
 
 typedef struct gw_handle gw_handle;
@@ -147,6 +148,13 @@ const char* gw_last_error(const gw_handle* h); /* h may be NULL (errors from gw_
 int gw_reset(gw_handle* h, const uint8_t* reset_mask, const gw_io* io, void* stream);
 int gw_step(gw_handle* h, const gw_io* io, void* stream);
 int gw_sync(gw_handle* h, void* stream);       /* cudaStreamSynchronize + surface async faults */
+
+/* Host-driven step (the reference's calling pattern, maddpg/agent.py:121-131: actions arrive as host integers, rewards
+ * and done flags are read on the host): copies `host_actions` [E, n_learners] int8 (pinned) to io->learner_actions,
+ * runs gw_step, copies io->reward -> host_reward f32 [E, n_learners], io->shaped_reward -> host_shaped (nullable),
+ * io->ended -> host_ended u8 [E] (nullable), and synchronises the stream.  One call, no Python between the stages. */
+int gw_step_host(gw_handle* h, const gw_io* io, const int8_t* host_actions, float* host_reward, float* host_shaped,
+                 uint8_t* host_ended, void* stream);
 
 /* packed env state (16 bytes/env) for checkpoint / resume; device or host destination */
 size_t gw_state_bytes(const gw_handle* h);

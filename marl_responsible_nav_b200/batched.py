@@ -220,6 +220,25 @@ class BatchedGridWorld:
                           ended=b.ended, info=b.info, final_obs=self._view(fin) if fin is not None else None,
                           obs_code=m.obs_code)
 
+    def step_host(self, host_actions: torch.Tensor, host_reward: torch.Tensor, host_ended: Optional[torch.Tensor] = None,
+                  host_shaped: Optional[torch.Tensor] = None, obs_out: Optional[torch.Tensor] = None) -> StepOutput:
+        """Host-driven step in one library call: pinned int8 actions [E, L] in, pinned f32 rewards [E, L] (and u8 ended
+        [E], f32 shaped rewards) out, stream synchronised on return.  Observations and masks stay on the device."""
+        for t, name in ((host_actions, "host_actions"), (host_reward, "host_reward"), (host_ended, "host_ended"), (host_shaped, "host_shaped")):
+            if t is not None and (t.is_cuda or not t.is_pinned() or not t.is_contiguous()):
+                raise ValueError(f"{name} must be a contiguous pinned host tensor")
+        if not hasattr(self, "_host_act_dev"):
+            self._host_act_dev = torch.empty((self.num_envs, self.n_learners), dtype=torch.int8, device=self.device)
+        obs = self._obs_arg(obs_out, "obs_out") if obs_out is not None else self.buf.obs
+        io = self._io(obs, None, self._host_act_dev, None, None)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        N.check(self.lib.gw_step_host(self._h, C.byref(io), p(host_actions), p(host_reward), p(host_shaped), p(host_ended),
+                                      self._stream()), self._h, "gw_step_host")
+        b = self.buf
+        return StepOutput(obs=self._view(obs), action_mask=b.action_mask, positions=b.positions, reward=b.reward,
+                          shaped_reward=b.shaped_reward, fear=b.fear, terminated=b.terminated, truncated=b.truncated,
+                          ended=b.ended, info=b.info, obs_code=b.obs_code)
+
     def sync(self):
         N.check(self.lib.gw_sync(self._h, self._stream()), self._h, "gw_sync")
 

@@ -47,7 +47,7 @@ struct StepParams {
 };
 
 constexpr int STAT_SLOTS = 1024;
-enum { ST_EPISODES = 0, ST_LEN, ST_CRASH, ST_APPLES, ST_UNRES, ST_FEAR_NZ, ST_RETURN_MILLI, ST_FEAR_BITS };
+enum { ST_EPISODES = 0, ST_LEN, ST_CRASH, ST_APPLES, ST_TASKS, ST_FEAR_NZ, ST_RETURN_MILLI, ST_FEAR_BITS };   // the 2N-pass cap never binds: no 'unresolved' counter
 
 // render record per env (shared memory): what P4 needs
 constexpr uint32_t R_FRESH = 1u << 2, R_FINAL = 1u << 3, R_SKIP = 1u << 6;   // bits 0-1 apples shown in obs, 4-5 apples at final
@@ -650,6 +650,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
       // thread per counterfactual (latency: few envs per SM).  The host picks by how many tiles each SM gets.
       constexpr uint32_t SPLIT = (uint32_t)SPLIT_;
       const uint32_t n_work = s.qn * 2u * SPLIT;
+      if (tid == 0 && s.qn) atomicAdd(&p.stats[(int)(tile & (STAT_SLOTS - 1)) * 8 + ST_TASKS], (unsigned long long)s.qn);
       for (uint32_t w = tid; w < n_work; w += THREADS) {
         const uint32_t ht = w / SPLIT, a0 = w - ht * SPLIT;
         const uint32_t tk = s.queue[ht >> 1], v = ht & 1u;
@@ -1242,6 +1243,24 @@ int gw_step(gw_handle* h, const gw_io* io, void* stream) {
   return GW_OK;
 }
 
+int gw_step_host(gw_handle* h, const gw_io* io, const int8_t* host_actions, float* host_reward, float* host_shaped,
+                 uint8_t* host_ended, void* stream) {
+  if (!h) return GW_EINVAL;
+  if (!io || !io->learner_actions || !host_actions) return fail(h, GW_EINVAL, "gw_step_host: io->learner_actions (device) and host_actions are required");
+  if ((host_reward && !io->reward) || (host_shaped && !io->shaped_reward) || (host_ended && !io->ended))
+    return fail(h, GW_EINVAL, "gw_step_host: a host destination needs the matching device output in io");
+  GW_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t E = (size_t)h->cfg.num_envs, L = (size_t)h->cfg.n_learners;
+  GW_CUDA(h, cudaMemcpyAsync(const_cast<int8_t*>(io->learner_actions), host_actions, E * L, cudaMemcpyHostToDevice, s));
+  if (int rc = gw_step(h, io, stream)) return rc;
+  if (host_reward) GW_CUDA(h, cudaMemcpyAsync(host_reward, io->reward, E * L * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (host_shaped) GW_CUDA(h, cudaMemcpyAsync(host_shaped, io->shaped_reward, E * L * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (host_ended) GW_CUDA(h, cudaMemcpyAsync(host_ended, io->ended, E, cudaMemcpyDeviceToHost, s));
+  GW_CUDA(h, cudaStreamSynchronize(s));
+  return GW_OK;
+}
+
 int gw_sync(gw_handle* h, void* stream) {
   if (!h) return GW_EINVAL;
   GW_CUDA(h, cudaSetDevice(h->cfg.device));
@@ -1290,7 +1309,7 @@ int gw_get_stats(gw_handle* h, gw_stats* out, void* stream) {
     out->episode_len_sum += r[gw::ST_LEN];
     out->crashes += r[gw::ST_CRASH];
     out->apples += r[gw::ST_APPLES];
-    out->unresolved += r[gw::ST_UNRES];
+    out->fear_tasks += r[gw::ST_TASKS];
     out->fear_nonzero += r[gw::ST_FEAR_NZ];
     ret_milli += (long long)r[gw::ST_RETURN_MILLI];
     double f;

@@ -13,7 +13,7 @@ import torch
 import torch.distributed as dist
 
 STAT_KEYS = ("env_steps", "agent_steps", "episodes", "episode_len_sum", "crashes", "apples", "unresolved",
-             "fear_nonzero", "return_sum", "fear_sum")
+             "fear_nonzero", "return_sum", "fear_sum", "fear_tasks")
 
 
 def shard_range(global_envs: int, rank: int, world: int) -> Tuple[int, int]:
@@ -34,7 +34,7 @@ def allreduce_stats(stats: Dict[str, float], device: Optional[torch.device] = No
     vec = torch.tensor([float(stats[k]) for k in STAT_KEYS], dtype=torch.float64, device=device)
     dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
     out = {k: float(v) for k, v in zip(STAT_KEYS, vec.tolist())}
-    for k in STAT_KEYS[:8]:
+    for k in STAT_KEYS[:8] + STAT_KEYS[10:]:
         out[k] = int(round(out[k]))
     return out
 

@@ -212,3 +212,26 @@ def test_errors_are_loud():
         env.step(torch.zeros((7, 2), dtype=torch.int8, device="cuda"))
     with pytest.raises(RuntimeError, match="n_agents"):
         BatchedGridWorld("Level 3", num_envs=8, n_agents=7)
+
+
+def test_step_host_matches_device_step():
+    """gw_step_host (pinned host actions in, rewards / ended out, synchronised) == gw_step on the same inputs."""
+    import torch
+    from marl_responsible_nav_b200 import BatchedGridWorld
+    E = 2048
+    a = BatchedGridWorld("Level 3", num_envs=E, fear=True, fear_weight=-5.0, seed=13)
+    b = BatchedGridWorld("Level 3", num_envs=E, fear=True, fear_weight=-5.0, seed=13)
+    a.reset(); b.reset()
+    acts = torch.randint(0, 9, (6, E, 2), dtype=torch.int8).pin_memory()
+    rew = torch.empty((E, 2), dtype=torch.float32).pin_memory()
+    shp = torch.empty((E, 2), dtype=torch.float32).pin_memory()
+    end = torch.empty((E,), dtype=torch.uint8).pin_memory()
+    for t in range(6):
+        oa = a.step_host(acts[t], rew, end, host_shaped=shp)
+        ob = b.step(acts[t].cuda())
+        assert torch.equal(rew, ob.reward.cpu()) and torch.equal(end, ob.ended.cpu()) and torch.equal(shp, ob.shaped_reward.cpu())
+        assert torch.equal(oa.obs, ob.obs) and torch.equal(oa.obs_code, ob.obs_code)
+    st = a.stats()
+    assert st["fear_tasks"] > 0 and st["fear_tasks"] == b.stats()["fear_tasks"]
+    with pytest.raises(ValueError):
+        a.step_host(acts[0].clone(), rew, end)          # not pinned
