@@ -268,7 +268,17 @@ def run_ours(a):
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         e2e = {"value": world * E * L * Ke / float(t_e.item()), "unit": "agent-steps/s",
-               "h2d_bytes_per_step": E * L, "d2h_bytes_per_step": E * L * 4 + E, "steps": Ke}
+               "h2d_bytes_per_step": E * L, "d2h_bytes_per_step": E * L * 4 + E, "steps": Ke,
+               "api": "BatchedGridWorld.step_host: cudaMemcpyAsync H2D (pinned actions) + gw_step + 2 x cudaMemcpyAsync D2H + stream sync"}
+        # the same call with zero_copy=True (the kernel reads / writes the pinned buffers itself over PCIe): reported aside
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for t in range(Ke):
+            env.step_host(host_actions[t % n_act], host_rew, host_end, obs_out=ring[t % slots], zero_copy=True)
+        t_z = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_z, op=dist.ReduceOp.MAX)
+        e2e["zero_copy_value"] = world * E * L * Ke / float(t_z.item())
     del env, ring, r
 
     # ---- the same kernel at a batch that fills the GPU (the step kernel's roofline point), N = 1 only

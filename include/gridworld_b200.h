@@ -152,9 +152,11 @@ int gw_sync(gw_handle* h, void* stream);       /* cudaStreamSynchronize + surfac
 /* Host-driven step (the reference's calling pattern, maddpg/agent.py:121-131: actions arrive as host integers, rewards
  * and done flags are read on the host): copies `host_actions` [E, n_learners] int8 (pinned) to io->learner_actions,
  * runs gw_step, copies io->reward -> host_reward f32 [E, n_learners], io->shaped_reward -> host_shaped (nullable),
- * io->ended -> host_ended u8 [E] (nullable), and synchronises the stream.  One call, no Python between the stages. */
+ * io->ended -> host_ended u8 [E] (nullable), and synchronises the stream.  One call, no Python between the stages.
+ * zero_copy != 0: no memcpy nodes at all -- the kernel itself loads the actions from the pinned host buffer and stores
+ * rewards / flags into the pinned host buffers over PCIe (unified addressing); same bytes, fewer stream operations. */
 int gw_step_host(gw_handle* h, const gw_io* io, const int8_t* host_actions, float* host_reward, float* host_shaped,
-                 uint8_t* host_ended, void* stream);
+                 uint8_t* host_ended, int zero_copy, void* stream);
 
 /* packed env state (16 bytes/env) for checkpoint / resume; device or host destination */
 size_t gw_state_bytes(const gw_handle* h);

@@ -74,7 +74,7 @@ def load():
     lib.gw_reset.argtypes = [vp, vp, C.POINTER(GwIO), vp]
     lib.gw_step.argtypes = [vp, C.POINTER(GwIO), vp]
     lib.gw_sync.argtypes = [vp, vp]
-    lib.gw_step_host.argtypes = [vp, C.POINTER(GwIO), vp, vp, vp, vp, vp]
+    lib.gw_step_host.argtypes = [vp, C.POINTER(GwIO), vp, vp, vp, vp, C.c_int, vp]
     lib.gw_state_bytes.argtypes = [vp]
     lib.gw_state_bytes.restype = C.c_size_t
     lib.gw_get_state.argtypes = [vp, vp, C.c_int, vp]

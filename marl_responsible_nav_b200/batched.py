@@ -221,9 +221,12 @@ class BatchedGridWorld:
                           obs_code=m.obs_code)
 
     def step_host(self, host_actions: torch.Tensor, host_reward: torch.Tensor, host_ended: Optional[torch.Tensor] = None,
-                  host_shaped: Optional[torch.Tensor] = None, obs_out: Optional[torch.Tensor] = None) -> StepOutput:
+                  host_shaped: Optional[torch.Tensor] = None, obs_out: Optional[torch.Tensor] = None,
+                  zero_copy: bool = False) -> StepOutput:
         """Host-driven step in one library call: pinned int8 actions [E, L] in, pinned f32 rewards [E, L] (and u8 ended
-        [E], f32 shaped rewards) out, stream synchronised on return.  Observations and masks stay on the device."""
+        [E], f32 shaped rewards) out, stream synchronised on return.  Observations and masks stay on the device.
+        zero_copy: the kernel reads / writes the pinned buffers itself over PCIe instead of separate memcpys (the
+        device-side reward / ended tensors are then not updated)."""
         for t, name in ((host_actions, "host_actions"), (host_reward, "host_reward"), (host_ended, "host_ended"), (host_shaped, "host_shaped")):
             if t is not None and (t.is_cuda or not t.is_pinned() or not t.is_contiguous()):
                 raise ValueError(f"{name} must be a contiguous pinned host tensor")
@@ -233,7 +236,7 @@ class BatchedGridWorld:
         io = self._io(obs, None, self._host_act_dev, None, None)
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         N.check(self.lib.gw_step_host(self._h, C.byref(io), p(host_actions), p(host_reward), p(host_shaped), p(host_ended),
-                                      self._stream()), self._h, "gw_step_host")
+                                      int(bool(zero_copy)), self._stream()), self._h, "gw_step_host")
         b = self.buf
         return StepOutput(obs=self._view(obs), action_mask=b.action_mask, positions=b.positions, reward=b.reward,
                           shaped_reward=b.shaped_reward, fear=b.fear, terminated=b.terminated, truncated=b.truncated,

@@ -1244,8 +1244,19 @@ int gw_step(gw_handle* h, const gw_io* io, void* stream) {
 }
 
 int gw_step_host(gw_handle* h, const gw_io* io, const int8_t* host_actions, float* host_reward, float* host_shaped,
-                 uint8_t* host_ended, void* stream) {
+                 uint8_t* host_ended, int zero_copy, void* stream) {
   if (!h) return GW_EINVAL;
+  if (zero_copy) {
+    if (!io || !host_actions) return fail(h, GW_EINVAL, "gw_step_host: io and host_actions are required");
+    gw_io z = *io;                                   // pinned host memory is device-addressable (UVA): point the kernel at it
+    z.learner_actions = host_actions;
+    if (host_reward) z.reward = host_reward;
+    if (host_shaped) z.shaped_reward = host_shaped;
+    if (host_ended) z.ended = host_ended;
+    if (int rc = gw_step(h, &z, stream)) return rc;
+    GW_CUDA(h, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return GW_OK;
+  }
   if (!io || !io->learner_actions || !host_actions) return fail(h, GW_EINVAL, "gw_step_host: io->learner_actions (device) and host_actions are required");
   if ((host_reward && !io->reward) || (host_shaped && !io->shaped_reward) || (host_ended && !io->ended))
     return fail(h, GW_EINVAL, "gw_step_host: a host destination needs the matching device output in io");

@@ -231,6 +231,11 @@ def test_step_host_matches_device_step():
         ob = b.step(acts[t].cuda())
         assert torch.equal(rew, ob.reward.cpu()) and torch.equal(end, ob.ended.cpu()) and torch.equal(shp, ob.shaped_reward.cpu())
         assert torch.equal(oa.obs, ob.obs) and torch.equal(oa.obs_code, ob.obs_code)
+    for t in range(3):                                   # zero-copy variant: same results land in the pinned buffers
+        oa = a.step_host(acts[t], rew, end, host_shaped=shp, zero_copy=True)
+        ob = b.step(acts[t].cuda())
+        assert torch.equal(rew, ob.reward.cpu()) and torch.equal(end, ob.ended.cpu()) and torch.equal(shp, ob.shaped_reward.cpu())
+        assert torch.equal(oa.obs, ob.obs)
     st = a.stats()
     assert st["fear_tasks"] > 0 and st["fear_tasks"] == b.stats()["fear_tasks"]
     with pytest.raises(ValueError):
