@@ -182,6 +182,20 @@ int gw_fear_one_actor(gw_handle* h, int64_t n_cases, const int8_t* n_agents_per_
                       const int8_t* actions, const int8_t* mdr, const int8_t* actor, const uint8_t* in_list,
                       double* resp, int8_t* n_mdr, int8_t* n_act, void* stream);
 
+/* Operator level: Responsibility.FeAR for ALL actors (custom/Responsibility.py:57-132): resp / n_mdr / n_act [C,4,4]
+ * (row = actor, column = affected).  Unlike gw_fear_one_actor the actor is NOT forced into the list: an actor outside
+ * ActionID4Agents cannot be swapped, so its row is zero, exactly as in the reference. */
+int gw_fear_matrix(gw_handle* h, int64_t n_cases, const int8_t* n_agents_per_case, const int8_t* positions,
+                   const int8_t* actions, const int8_t* mdr, const uint8_t* in_list, double* resp, int8_t* n_mdr,
+                   int8_t* n_act, void* stream);
+
+/* Operator level: Responsibility.FeAL (custom/Responsibility.py:213-303): per agent, the valid moves it has when every
+ * other listed agent plays its action (n_act) vs its Move de Rigueur (n_mdr); feal = clip(n_act / (n_mdr + 1e-6), -1, 1).
+ * Outputs [C,4]. */
+int gw_feal(gw_handle* h, int64_t n_cases, const int8_t* n_agents_per_case, const int8_t* positions,
+            const int8_t* actions, const int8_t* mdr, const uint8_t* in_list, double* feal, int8_t* n_mdr,
+            int8_t* n_act, void* stream);
+
 /* ---- actor forward (K5): AgileRL `MADDPG.get_action` as called at maddpg/agent.py:109-113 -----------------------
  * One actor per learner: Linear(H*W,128)-LayerNorm-ReLU-Linear(128,128)-LayerNorm-ReLU-Linear(128,9)-GumbelSoftmax
  * (shapes from the reference's checkpoints), Gaussian exploration noise, clip to [0,1], action mask,

@@ -309,3 +309,25 @@ class BatchedGridWorld:
         N.check(self.lib.gw_fear_one_actor(self._h, Cn, p(nper), p(pos), p(act), p(md), p(ac), p(il), p(resp), p(n_mdr),
                                            p(n_act), self._stream()), self._h, "gw_fear_one_actor")
         return resp, n_mdr, n_act
+
+    def _matrix_op(self, fn, name, tail, positions, actions, mdr, in_list, n_agents):
+        dev = self.device
+        pos, act, md = (self._as_i8(x, dev) for x in (positions, actions, mdr))
+        Cn = pos.shape[0]
+        nper = self._as_i8(n_agents, dev)
+        il = None if in_list is None else torch.as_tensor(np.asarray(in_list)).to(device=dev, dtype=torch.uint8).contiguous()
+        val = torch.empty((Cn,) + tail, dtype=torch.float64, device=dev)
+        n_mdr = torch.empty((Cn,) + tail, dtype=torch.int8, device=dev)
+        n_act = torch.empty((Cn,) + tail, dtype=torch.int8, device=dev)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        N.check(fn(self._h, Cn, p(nper), p(pos), p(act), p(md), p(il), p(val), p(n_mdr), p(n_act), self._stream()),
+                self._h, name)
+        return val, n_mdr, n_act
+
+    def fear_matrix(self, positions, actions, mdr, in_list=None, n_agents=None):
+        """Responsibility.FeAR (all actors) for C cases -> (resp f64 [C,4,4], n_mdr, n_act int8 [C,4,4])."""
+        return self._matrix_op(self.lib.gw_fear_matrix, "gw_fear_matrix", (4, 4), positions, actions, mdr, in_list, n_agents)
+
+    def feal(self, positions, actions, mdr, in_list=None, n_agents=None):
+        """Responsibility.FeAL for C cases -> (feal f64 [C,4], n_mdr, n_act int8 [C,4])."""
+        return self._matrix_op(self.lib.gw_feal, "gw_feal", (4,), positions, actions, mdr, in_list, n_agents)

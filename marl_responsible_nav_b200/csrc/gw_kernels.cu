@@ -851,6 +851,95 @@ __global__ void __launch_bounds__(128) gw_fear_kernel(const Tables* T, int n_def
   }
 }
 
+// Responsibility.FeAR for all actors (one warp per (case, actor); lanes 0..5 = (affected slot, variant)) and
+// Responsibility.FeAL (one warp per case; lanes 0..7 = (agent, variant)).
+__global__ void __launch_bounds__(128) gw_fear_matrix_kernel(const Tables* T, int n_default, long long C, const int8_t* n_per,
+                                                             const int8_t* pos, const int8_t* act, const int8_t* mdr,
+                                                             const uint8_t* in_list, double* resp, int8_t* n_mdr,
+                                                             int8_t* n_act) {
+  __shared__ OpSmem s;
+  load_op_tables(s, T);
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long c = wid >> 2;
+  const int x = (int)(wid & 3);
+  if (c >= C) return;
+  const int n = n_per ? n_per[c] : n_default;
+  uint32_t cells, acts, lst = 0;
+  load_case(c, n, pos, act, cells, acts);
+  for (int i = 0; i < n; ++i)
+    if (in_list == nullptr || in_list[c * 4 + i]) lst |= 1u << i;
+  const PairGeom g = pair_geometry(n, cells);
+  uint32_t base = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < n && ((lst >> k) & 1u))
+      base |= make_traj(s.next, (cells >> (8 * k)) & 0xFFu, (acts >> (4 * k)) & 0xFu).eff << (4 * k);
+  const int js = lane >> 1, v = lane & 1;
+  const int j = js + (js >= x ? 1 : 0);
+  uint32_t my = 0;
+  if (x < n && lane < 6 && j < n) {
+    uint32_t eo = base;
+    if (v == 0 && ((lst >> x) & 1u))                    // SwapActionIDs4Agents: only an actor present in the list plays its MdR
+      eo = (base & ~(0xFu << (4 * x))) |
+           (make_traj(s.next, (cells >> (8 * x)) & 0xFFu, (uint32_t)min(max((int)mdr[c * 4 + x], 0), 8)).eff << (4 * x));
+    my = count_valid_moves(s.lut, s.next, cells, eo, g, j, ((lst >> j) & 1u) != 0);
+  }
+  const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, my, 1);
+  if (lane < 6 && (lane & 1) == 0) {                    // even lane holds n_mdr, its neighbour n_act
+    const long long o = c * 16 + x * 4 + j;
+    if (x < n && j < n) {
+      resp[o] = T->resp_lut[my][other];
+      n_mdr[o] = (int8_t)my;
+      n_act[o] = (int8_t)other;
+    }
+  }
+  if (lane < 4) {                                       // diagonal and padding entries
+    const long long o = c * 16 + x * 4 + lane;
+    if (lane == x || x >= n || lane >= n) { resp[o] = 0.0; n_mdr[o] = 0; n_act[o] = 0; }
+  }
+}
+
+__global__ void __launch_bounds__(128) gw_feal_kernel(const Tables* T, int n_default, long long C, const int8_t* n_per,
+                                                      const int8_t* pos, const int8_t* act, const int8_t* mdr,
+                                                      const uint8_t* in_list, double* feal, int8_t* n_mdr, int8_t* n_act) {
+  __shared__ OpSmem s;
+  load_op_tables(s, T);
+  const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  const int n = n_per ? n_per[c] : n_default;
+  uint32_t cells, acts, lst = 0;
+  load_case(c, n, pos, act, cells, acts);
+  for (int i = 0; i < n; ++i)
+    if (in_list == nullptr || in_list[c * 4 + i]) lst |= 1u << i;
+  const PairGeom g = pair_geometry(n, cells);
+  const int ii = lane >> 1, v = lane & 1;               // v = 0: the others play their MdR, v = 1: their actions
+  uint32_t my = 0;
+  if (lane < 8 && ii < n) {
+    uint32_t eo = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < n && k != ii && ((lst >> k) & 1u)) {
+        const uint32_t a = v == 0 ? (uint32_t)min(max((int)mdr[c * 4 + k], 0), 8) : (acts >> (4 * k)) & 0xFu;
+        eo |= make_traj(s.next, (cells >> (8 * k)) & 0xFFu, a).eff << (4 * k);
+      }
+    my = count_valid_moves(s.lut, s.next, cells, eo, g, ii, ((lst >> ii) & 1u) != 0);
+  }
+  const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, my, 1);
+  if (lane < 8 && (lane & 1) == 0) {
+    const long long o = c * 4 + ii;
+    if (ii < n) {
+      const double r = __ddiv_rn((double)other, __dadd_rn((double)my, 0.000001));     // Responsibility.py:287-288
+      feal[o] = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+      n_mdr[o] = (int8_t)my;
+      n_act[o] = (int8_t)other;
+    } else {
+      feal[o] = 0.0; n_mdr[o] = 0; n_act[o] = 0;
+    }
+  }
+}
+
 }  // namespace gw
 
 // ====================================================================== host side / C-ABI
@@ -1361,6 +1450,36 @@ int gw_update_world(gw_handle* h, int64_t n_cases, const int8_t* n_per, const in
   const long long blocks = (n_cases + threads - 1) / threads;
   gw::gw_update_world_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
       h->d_tables, h->cfg.n_agents, n_cases, n_per, positions, actions, apples, new_positions, crash, restricted, caught);
+  GW_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int gw_fear_matrix(gw_handle* h, int64_t n_cases, const int8_t* n_per, const int8_t* positions, const int8_t* actions,
+                   const int8_t* mdr, const uint8_t* in_list, double* resp, int8_t* n_mdr, int8_t* n_act, void* stream) {
+  if (!h) return GW_EINVAL;
+  if (n_cases < 0 || !positions || !actions || !mdr || !resp || !n_mdr || !n_act)
+    return fail(h, GW_EINVAL, "gw_fear_matrix: null/invalid argument");
+  if (n_cases == 0) return GW_OK;
+  GW_CUDA(h, cudaSetDevice(h->cfg.device));
+  const long long blocks = (n_cases * 4 * 32 + 127) / 128;
+  gw::gw_fear_matrix_kernel<<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      h->d_tables, h->cfg.n_agents, n_cases, n_per, positions, actions, mdr, in_list, resp, n_mdr, n_act);
+  GW_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int gw_feal(gw_handle* h, int64_t n_cases, const int8_t* n_per, const int8_t* positions, const int8_t* actions,
+            const int8_t* mdr, const uint8_t* in_list, double* feal, int8_t* n_mdr, int8_t* n_act, void* stream) {
+  if (!h) return GW_EINVAL;
+  if (n_cases < 0 || !positions || !actions || !mdr || !feal || !n_mdr || !n_act)
+    return fail(h, GW_EINVAL, "gw_feal: null/invalid argument");
+  if (n_cases == 0) return GW_OK;
+  GW_CUDA(h, cudaSetDevice(h->cfg.device));
+  const long long blocks = (n_cases * 32 + 127) / 128;
+  gw::gw_feal_kernel<<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      h->d_tables, h->cfg.n_agents, n_cases, n_per, positions, actions, mdr, in_list, feal, n_mdr, n_act);
   GW_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return GW_OK;

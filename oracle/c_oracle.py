@@ -44,6 +44,8 @@ def load():
         lib.gwo_get_state.argtypes = [vp, vp]
         lib.gwo_update_world.argtypes = [vp, i64] + [vp] * 8
         lib.gwo_fear_one_actor.argtypes = [vp, i64] + [vp] * 10
+        lib.gwo_fear_matrix.argtypes = [vp, i64] + [vp] * 8
+        lib.gwo_feal.argtypes = [vp, i64] + [vp] * 8
         _lib = lib
     return _lib
 
@@ -145,3 +147,20 @@ class COracle:
                                          _p(n_mdr), _p(n_act), _p(fsum))
         assert rc == 0
         return resp, n_mdr, n_act, fsum
+
+    def _matrix_call(self, fn, shape_tail, positions, actions, mdr, in_list, n_agents):
+        pos, act, md, nper = _i8(positions), _i8(actions), _i8(mdr), _i8(n_agents)
+        il = None if in_list is None else np.ascontiguousarray(in_list, dtype=np.uint8)
+        Cn = pos.shape[0]
+        val = np.zeros((Cn,) + shape_tail)
+        n_mdr = np.zeros((Cn,) + shape_tail, np.int8)
+        n_act = np.zeros((Cn,) + shape_tail, np.int8)
+        rc = fn(self._h, Cn, _p(nper), _p(pos), _p(act), _p(md), _p(il), _p(val), _p(n_mdr), _p(n_act))
+        assert rc == 0
+        return val, n_mdr, n_act
+
+    def fear_matrix(self, positions, actions, mdr, in_list=None, n_agents=None):
+        return self._matrix_call(self.lib.gwo_fear_matrix, (4, 4), positions, actions, mdr, in_list, n_agents)
+
+    def feal(self, positions, actions, mdr, in_list=None, n_agents=None):
+        return self._matrix_call(self.lib.gwo_feal, (4,), positions, actions, mdr, in_list, n_agents)

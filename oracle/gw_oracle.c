@@ -648,3 +648,63 @@ EXPORT int gwo_fear_one_actor(gwo_handle* h, int64_t C, const int8_t* n_per, con
   }
   return GW_OK;
 }
+
+/* Responsibility.FeAR (all actors), custom/Responsibility.py:57-132.  An actor outside the list is never swapped. */
+EXPORT int gwo_fear_matrix(gwo_handle* h, int64_t C, const int8_t* n_per, const int8_t* pos, const int8_t* act,
+                           const int8_t* mdr, const uint8_t* in_list, double* resp, int8_t* n_mdr, int8_t* n_act) {
+  if (!h) return GW_EINVAL;
+  for (int64_t c = 0; c < C; ++c) {
+    const int n = n_per ? n_per[c] : h->cfg.n_agents;
+    cell_t loc[4];
+    int a[4] = {0, 0, 0, 0}, il[4] = {0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+      loc[i].r = pos[(c * 4 + i) * 2]; loc[i].c = pos[(c * 4 + i) * 2 + 1];
+      a[i] = act[c * 4 + i];
+      il[i] = in_list ? (in_list[c * 4 + i] != 0) : 1;
+    }
+    for (int i = 0; i < 16; ++i) { resp[c * 16 + i] = 0.0; n_mdr[c * 16 + i] = 0; n_act[c * 16 + i] = 0; }
+    for (int ii = 0; ii < n; ++ii)
+      for (int jj = 0; jj < n; ++jj) {
+        if (ii == jj) continue;
+        int la[4];
+        for (int i = 0; i < n; ++i) la[i] = a[i];
+        if (il[ii]) la[ii] = mdr[c * 4 + ii];
+        const int m = count_valid(&h->cfg, n, loc, la, il, jj);
+        const int v = count_valid(&h->cfg, n, loc, a, il, jj);
+        double r = ((double)m - (double)v) / ((double)m + 0.000001);
+        resp[c * 16 + ii * 4 + jj] = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+        n_mdr[c * 16 + ii * 4 + jj] = (int8_t)m;
+        n_act[c * 16 + ii * 4 + jj] = (int8_t)v;
+      }
+  }
+  return GW_OK;
+}
+
+/* Responsibility.FeAL, custom/Responsibility.py:213-303 */
+EXPORT int gwo_feal(gwo_handle* h, int64_t C, const int8_t* n_per, const int8_t* pos, const int8_t* act,
+                    const int8_t* mdr, const uint8_t* in_list, double* feal, int8_t* n_mdr, int8_t* n_act) {
+  if (!h) return GW_EINVAL;
+  for (int64_t c = 0; c < C; ++c) {
+    const int n = n_per ? n_per[c] : h->cfg.n_agents;
+    cell_t loc[4];
+    int a[4] = {0, 0, 0, 0}, il[4] = {0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+      loc[i].r = pos[(c * 4 + i) * 2]; loc[i].c = pos[(c * 4 + i) * 2 + 1];
+      a[i] = act[c * 4 + i];
+      il[i] = in_list ? (in_list[c * 4 + i] != 0) : 1;
+    }
+    for (int ii = 0; ii < 4; ++ii) {
+      feal[c * 4 + ii] = 0.0; n_mdr[c * 4 + ii] = 0; n_act[c * 4 + ii] = 0;
+      if (ii >= n) continue;
+      int la[4];
+      for (int i = 0; i < n; ++i) la[i] = (i == ii) ? a[i] : mdr[c * 4 + i];
+      const int m = count_valid(&h->cfg, n, loc, la, il, ii);
+      const int v = count_valid(&h->cfg, n, loc, a, il, ii);
+      double r = (double)v / ((double)m + 0.000001);
+      feal[c * 4 + ii] = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+      n_mdr[c * 4 + ii] = (int8_t)m;
+      n_act[c * 4 + ii] = (int8_t)v;
+    }
+  }
+  return GW_OK;
+}

@@ -160,6 +160,36 @@ def gen_fear_cases(n_cases=500, seed=2):
     print("fear_cases", n_cases, "nonzero", int((out["fear_sum"] != 0).sum()))
 
 
+def gen_matrix_cases(n_cases=160, seed=3):
+    """Responsibility.FeAR (all actors) and Responsibility.FeAL on full and partial action lists."""
+    rng = np.random.default_rng(seed)
+    out = dict(n=np.zeros(n_cases, np.int8), locs=-np.ones((n_cases, 4, 2), np.int8), acts=np.zeros((n_cases, 4), np.int8),
+               mdr=np.zeros((n_cases, 4), np.int8), in_list=np.zeros((n_cases, 4), bool),
+               fear=np.zeros((n_cases, 4, 4)), fear_n_mdr=np.zeros((n_cases, 4, 4), np.int8),
+               fear_n_act=np.zeros((n_cases, 4, 4), np.int8), feal=np.zeros((n_cases, 4)),
+               feal_n_mdr=np.zeros((n_cases, 4), np.int8), feal_n_act=np.zeros((n_cases, 4), np.int8))
+    for c in range(n_cases):
+        n = int(rng.choice([3, 4, 4]))
+        locs = clustered_cells(rng, n, p_cluster=0.9, radius=int(rng.choice([3, 4, 5])))
+        acts = [int(a) for a in rng.integers(0, 9, size=n)]
+        mdr = [int(a) for a in rng.integers(0, 5, size=n)]
+        in_list = [True] * n if rng.random() < 0.7 else [bool(rng.random() < 0.7) for _ in range(n)]
+        w = make_world(locs)
+        lst = [(i, acts[i]) for i in range(n) if in_list[i]]
+        mdrs = [[i, mdr[i]] for i in range(n)]
+        resp, n_mdr, n_act, _, _ = RESP.FeAR(w, lst, mdrs)
+        feal, fm, fa, _, _ = RESP.FeAL(w, lst, mdrs)
+        out["n"][c] = n; out["locs"][c, :n] = locs; out["acts"][c, :n] = acts; out["mdr"][c, :n] = mdr
+        out["in_list"][c, :n] = in_list
+        out["fear"][c, :n, :n] = resp; out["fear_n_mdr"][c, :n, :n] = n_mdr; out["fear_n_act"][c, :n, :n] = n_act
+        out["feal"][c, :n] = feal; out["feal_n_mdr"][c, :n] = fm; out["feal_n_act"][c, :n] = fa
+        if c % 40 == 0:
+            RESP.CountValidMovesOfAffected_tuple.cache_clear()
+    RESP.CountValidMovesOfAffected_tuple.cache_clear()
+    np.savez_compressed(os.path.join(HERE, "matrix_cases.npz"), **out)
+    print("matrix_cases", n_cases, "fear nonzero", int((out["fear"] != 0).any((1, 2)).sum()), "feal<1", int((out["feal"] < 0.999).any(1).sum()))
+
+
 _TARGET = [None, (-1, 0), (1, 0), (0, -1), (0, 1), (-2, 0), (2, 0), (0, -2), (0, 2)]
 
 
@@ -355,13 +385,15 @@ def gen_scenario_tables():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["scenario", "update", "fear", "ma", "single"]
+    which = sys.argv[1:] or ["scenario", "update", "fear", "matrix", "ma", "single"]
     if "scenario" in which:
         gen_scenario_tables()
     if "update" in which:
         gen_update_cases()
     if "fear" in which:
         gen_fear_cases()
+    if "matrix" in which:
+        gen_matrix_cases()
     if "ma" in which:
         gen_ma_episodes("ma_episodes.npz", [(0, False, 40), (42, False, 40), (66, False, 40),
                                             (0, True, 12), (42, True, 12), (66, True, 12), (7, True, 12)])

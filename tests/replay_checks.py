@@ -72,6 +72,12 @@ class GpuBackend:
         r = self.env.fear_one_actor(positions, actions, mdr, actor, in_list, n_agents)
         return tuple(t.cpu().numpy() for t in r) + (None,)
 
+    def fear_matrix(self, positions, actions, mdr, in_list=None, n_agents=None):
+        return tuple(t.cpu().numpy() for t in self.env.fear_matrix(positions, actions, mdr, in_list, n_agents))
+
+    def feal(self, positions, actions, mdr, in_list=None, n_agents=None):
+        return tuple(t.cpu().numpy() for t in self.env.feal(positions, actions, mdr, in_list, n_agents))
+
 
 def bf16_to_f32(u16):
     return (u16.astype(np.uint32) << 16).view(np.float32)
@@ -104,6 +110,20 @@ def check_fear_cases(make_backend):
     assert np.array_equal(resp, g["resp"])            # fp64, bit-equal (north_star allows 1e-6 relative)
     if fsum is not None:
         assert np.array_equal(fsum, g["fear_sum"])
+    return len(g["n"])
+
+
+def check_matrix_cases(make_backend):
+    """Responsibility.FeAR (all actors) and Responsibility.FeAL, full and partial action lists."""
+    g = npz("matrix_cases.npz")
+    b = make_backend(num_envs=1, fear=True)
+    pos = np.where(g["locs"] < 0, 0, g["locs"]).astype(np.int8)
+    resp, n_mdr, n_act = b.fear_matrix(pos, g["acts"], g["mdr"], in_list=g["in_list"], n_agents=g["n"])
+    assert np.array_equal(n_mdr, g["fear_n_mdr"]) and np.array_equal(n_act, g["fear_n_act"])
+    assert np.array_equal(resp, g["fear"])                    # fp64 bit-equal
+    feal, fm, fa = b.feal(pos, g["acts"], g["mdr"], in_list=g["in_list"], n_agents=g["n"])
+    assert np.array_equal(fm, g["feal_n_mdr"]) and np.array_equal(fa, g["feal_n_act"])
+    assert np.array_equal(feal, g["feal"])
     return len(g["n"])
 
 

@@ -19,6 +19,24 @@ def test_fear_cases():
     assert RC.check_fear_cases(make) == 500
 
 
+def test_fear_matrix_and_feal_cases():
+    assert RC.check_matrix_cases(make) == 160
+
+
+def test_python_oracle_fear_matrix_and_feal():
+    g = RC.npz("matrix_cases.npz")
+    region = c_oracle.builtin_scenario("Level 3").region
+    for c in range(0, 160, 4):
+        n = int(g["n"][c])
+        locs = [tuple(int(v) for v in g["locs"][c, i]) for i in range(n)]
+        lst = [(i, int(g["acts"][c, i])) for i in range(n) if g["in_list"][c, i]]
+        mdr = [int(m) for m in g["mdr"][c, :n]]
+        resp, nm, na = PO.fear_all_actors(region, locs, lst, mdr)
+        assert np.array_equal(resp, g["fear"][c, :n, :n]) and np.array_equal(nm, g["fear_n_mdr"][c, :n, :n])
+        fl, fm, fa = PO.feal(region, locs, lst, mdr)
+        assert np.array_equal(fl, g["feal"][c, :n]) and np.array_equal(fa, g["feal_n_act"][c, :n])
+
+
 def test_ma_episodes():
     assert RC.check_ma_episodes(make) > 1500
 

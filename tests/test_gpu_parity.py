@@ -24,6 +24,10 @@ def test_fear_cases_golden():
     assert RC.check_fear_cases(make) == 500
 
 
+def test_fear_matrix_and_feal_golden():
+    assert RC.check_matrix_cases(make) == 160
+
+
 def test_ma_episodes_golden():
     assert RC.check_ma_episodes(make) > 1500
 
