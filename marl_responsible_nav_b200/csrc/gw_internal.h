@@ -12,6 +12,7 @@ struct gw_handle {
   gw::Tables* d_tables = nullptr;
   uint4* d_state = nullptr;
   unsigned long long* d_stats = nullptr;
+  unsigned long long* d_trace = nullptr;     // GW_TRACE (dev)
   bool reset_done = false;
   int sm_count = 148;
   int n_active = 0;

@@ -44,6 +44,7 @@ struct StepParams {
   uint32_t seed_lo, seed_hi;
   double fear_weight;
   const uint8_t* reset_mask;          // gw_reset only
+  unsigned long long* trace;          // GW_TRACE (dev): per CTA 8 globaltimer stamps at the phase boundaries
 };
 
 constexpr int STAT_SLOTS = 1024;
@@ -401,11 +402,20 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_reset_kernel(StepP
 
 // ------------------------------------------------------------------ step kernel
 // Persistent CTAs: the grid is sized to the machine and each CTA walks tiles blockIdx.x, +gridDim.x, ...
+__device__ __forceinline__ void trace_stamp(const StepParams& p, int slot) {
+  if (p.trace != nullptr && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[(size_t)blockIdx.x * 8 + slot] = t;
+  }
+}
+
 template <int THREADS, int TILE, int SPLIT_, bool FEAR, int OBS>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
   uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
+  trace_stamp(p, 0);
   // Programmatic dependent launch (when the launch carries the attribute): this grid's prologue (table copies) may run
   // while the previous step drains; the env state it wrote is only touched after griddepcontrol.wait.
   load_tables<THREADS, TILE, OBS>(s, stage, p.tables, p.H, p.nl, true);
@@ -463,6 +473,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
     }
     __syncthreads();
 
+    trace_stamp(p, 1);
     // ================================================================= P1b: world update, rewards, flags, FeAR tasks
     if (own) {
       const uint32_t cells = st.x;
@@ -643,8 +654,10 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
     }
 
     // ================================================================= P2: counterfactual sims (Responsibility.py:20-54)
+    trace_stamp(p, 2);
     if (FEAR) {
       __syncthreads();
+      trace_stamp(p, 3);
       // One thread per (task, actor variant, 9/SPLIT actions of the affected agent).  SPLIT = 1 shares the pair masks that
       // do not involve the affected agent across its nine actions (throughput: many resident CTAs); SPLIT = 9 gives one
       // thread per counterfactual (latency: few envs per SM).  The host picks by how many tiles each SM gets.
@@ -674,6 +687,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
       __syncthreads();
     }
 
+    trace_stamp(p, 4);
     // ================================================================= P3: fear, shaped reward, statistics, action masks
     if (own) {
       stage_masks(s, p, tid, cells_render);                // the FeAR scratch is dead now: its space stages the masks
@@ -731,12 +745,15 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
       }
     }
 
+    trace_stamp(p, 5);
     // ================================================================= P4
     __syncthreads();
+    trace_stamp(p, 6);
     // last tile of this CTA: only observation stores are left, the next step's grid may start its prologue
     if (tile + gridDim.x >= n_tiles) asm volatile("griddepcontrol.launch_dependents;");
     render_tile<THREADS, TILE, OBS>(s, stage, p, tile_base, tile_envs);
     __syncthreads();                                       // shared arrays are reused by the next tile
+    trace_stamp(p, 7);
   }
   if (tables_pending) cp_async_wait_all();                 // a CTA without tiles must not exit with copies in flight
 }
@@ -1168,6 +1185,10 @@ int gw_create(const gw_config* cfg, gw_handle** out) {
   if ((e = cudaMemset(h->d_state, 0, sizeof(uint4) * (size_t)cfg->num_envs)) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMemset state"));
   if ((e = cudaMemset(h->d_stats, 0, sizeof(unsigned long long) * gw::STAT_SLOTS * 8)) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMemset stats"));
   delete t;
+  if (const char* tr = std::getenv("GW_TRACE")) {
+    if (std::atoi(tr) != 0 && cudaMalloc(&h->d_trace, sizeof(unsigned long long) * 8 * 4096) == cudaSuccess)
+      cudaMemset(h->d_trace, 0, sizeof(unsigned long long) * 8 * 4096);
+  }
   *out = h;
   return GW_OK;
 }
@@ -1178,6 +1199,7 @@ int gw_destroy(gw_handle* h) {
   if (h->d_tables) cudaFree(h->d_tables);
   if (h->d_state) cudaFree(h->d_state);
   if (h->d_stats) cudaFree(h->d_stats);
+  if (h->d_trace) cudaFree(h->d_trace);
   delete h;
   return GW_OK;
 }
@@ -1204,6 +1226,7 @@ static gw::StepParams make_params(gw_handle* h, const gw_io* io) {
   p.perturb_thr = thr >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thr;
   p.seed_lo = (uint32_t)c.seed; p.seed_hi = (uint32_t)(c.seed >> 32);
   p.fear_weight = c.fear_weight;
+  p.trace = h->d_trace;
   return p;
 }
 
@@ -1429,6 +1452,15 @@ int gw_reset_stats(gw_handle* h, void* stream) {
   GW_CUDA(h, cudaSetDevice(h->cfg.device));
   GW_CUDA(h, cudaMemsetAsync(h->d_stats, 0, sizeof(unsigned long long) * gw::STAT_SLOTS * 8, static_cast<cudaStream_t>(stream)));
   h->env_steps = 0;
+  return GW_OK;
+}
+
+// dev only: GW_TRACE=1 makes gw_create allocate a per-CTA stamp buffer; gw_debug_trace copies it out (8 x uint64 per CTA)
+int gw_debug_trace(gw_handle* h, unsigned long long* host_out, int max_ctas) {
+  if (!h || !h->d_trace || !host_out) return GW_EINVAL;
+  GW_CUDA(h, cudaSetDevice(h->cfg.device));
+  GW_CUDA(h, cudaDeviceSynchronize());
+  GW_CUDA(h, cudaMemcpy(host_out, h->d_trace, sizeof(unsigned long long) * 8 * (size_t)max_ctas, cudaMemcpyDeviceToHost));
   return GW_OK;
 }
 

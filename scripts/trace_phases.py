@@ -1,0 +1,26 @@
+"""Dev: phase timeline of gw_step at a given batch (GW_TRACE=1).  Prints per-phase medians over CTAs in microseconds."""
+import os, sys, ctypes as C
+os.environ["GW_TRACE"] = "1"
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np, torch
+from marl_responsible_nav_b200 import BatchedGridWorld
+E = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+fear = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+env = BatchedGridWorld("Level 3", num_envs=E, fear=bool(fear), auto_reset=True, seed=1)
+env.reset()
+a = torch.randint(0, 9, (E, 2), device="cuda", dtype=torch.int8)
+for _ in range(20): env.step(a)
+torch.cuda.synchronize()
+n = min(4096, (E + 31) // 32 if E <= 32768 else 592)
+buf = np.zeros((n, 8), np.uint64)
+env.lib.gw_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+rc = env.lib.gw_debug_trace(env._h, buf.ctypes.data, n)
+assert rc == 0
+b = buf.astype(np.int64)
+b = b[b[:, 0] > 0]
+t0 = b[:, 0].min()
+names = ["start", "tables+P1a done", "P1b done", "P2 barrier", "P2 done", "P3 done", "P4 barrier", "tile end"]
+print(f"E={E} fear={fear} CTAs={len(b)}  kernel span = {(b[:, 7].max() - t0) / 1e3:.2f} us (first start -> last end)")
+for i, nm in enumerate(names):
+    rel = (b[:, i] - t0) / 1e3
+    print(f"  {nm:18s} median {np.median(rel):7.2f}  min {rel.min():7.2f}  max {rel.max():7.2f} us")
