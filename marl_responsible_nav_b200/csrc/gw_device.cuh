@@ -28,7 +28,8 @@ constexpr int N_EFF = 13;
 constexpr int LUT_DELTAS = 81;                      // (dr + 4) * 9 + (dc + 4)
 constexpr int LUT_BYTES = LUT_DELTAS * N_EFF * N_EFF;   // 13689
 
-struct SmallTables {                    // per-step lookups, copied to shared memory by every CTA (1792 B)
+struct SmallTables {                    // per-step lookups, copied to shared memory by every CTA (2592 B)
+  alignas(16) double resp_lut[10][10];                      // clip((m-a)/(m+1e-6),-1,1), Responsibility.py:194-198
   alignas(16) uint32_t policy_thr[GW_MAX_POLICIES][2][8];   // 31-bit cdf thresholds, [policy][perturbed][k]
   uint8_t mdr_map[GW_MAX_H * GW_W];
   uint8_t policy_map[GW_MAX_H * GW_W];
@@ -43,7 +44,6 @@ struct Tables {                         // device-global, read-only, built by gw
   uint16_t map_rows[GW_MAX_H];
   int32_t n_active;
   int32_t pad_;
-  double resp_lut[10][10];                      // clip((m-a)/(m+1e-6),-1,1), Responsibility.py:194-198
 };
 
 // ---------------------------------------------------------------- Philox4x32-10
@@ -265,6 +265,8 @@ struct StepResult {
 };
 
 // GWorld.UpdateGWorld with explicit actions for all n agents (custom/grid_world.py:424-563).
+// OWN_APPLES: count only eater e on apple e (all the env wrappers ever look at, ma_customenv.py:264 / customenv.py:143).
+template <bool OWN_APPLES = false>
 __device__ __forceinline__ StepResult world_update(const uint8_t* __restrict__ s_lut, const uint8_t* __restrict__ s_next,
                                                    int n, uint32_t cells, uint32_t acts, const PairGeom& g,
                                                    uint32_t apple_cells, uint32_t apple_on, int n_eaters) {
@@ -299,7 +301,8 @@ __device__ __forceinline__ StepResult world_update(const uint8_t* __restrict__ s
         const uint32_t cur = (n >= 2) ? cell_at(p0, t[e], (cm >> (4 * s + e)) & 1u, s) : p0;
 #pragma unroll
         for (int k = 0; k < 2; ++k)
-          if (((apple_on >> k) & 1u) && cur == ((apple_cells >> (8 * k)) & 0xFFu)) r.caught += 1u << (3 * (e * 2 + k));
+          if ((!OWN_APPLES || k == e) && ((apple_on >> k) & 1u) && cur == ((apple_cells >> (8 * k)) & 0xFFu))
+            r.caught += 1u << (3 * (e * 2 + k));
       }
     }
   }

@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
 
       // ---- the real update (ma_customenv.py:254)
       const uint32_t apples_before = meta & M_APPLES;
-      const StepResult r = world_update(s.lut, s.next, n, cells, acts, g, p.apple_cells, apples_before, nl);
+      const StepResult r = world_update<true>(s.lut, s.next, n, cells, acts, g, p.apple_cells, apples_before, nl);
       const uint32_t cells_new = r.cells;
 
       // ---- FeAR tasks on the pre-step positions (ma_customenv.py:245-252 / customenv.py:113-120)
@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
 #pragma unroll
           for (int js = 0; js < 3; ++js) {
             const int j = js + (js >= x ? 1 : 0);
-            if ((tb >> j) & 1u) rs[js] = T->resp_lut[(c >> (8 * js)) & 0xFu][(c >> (8 * js + 4)) & 0xFu];
+            if ((tb >> j) & 1u) rs[js] = s.small.resp_lut[(c >> (8 * js)) & 0xFu][(c >> (8 * js + 4)) & 0xFu];
           }
           fear[x] = fear_sum3(n, rs[0], rs[1], rs[2]);
         }
@@ -860,7 +860,7 @@ __global__ void __launch_bounds__(128) gw_fear_kernel(const Tables* T, int n_def
       const int q = lane - (lane > x ? 1 : 0);
       m = (int8_t)((packed >> (4 * q)) & 0xF);
       a = (int8_t)((packed >> (16 + 4 * q)) & 0xF);
-      rv = T->resp_lut[m][a];
+      rv = T->small.resp_lut[m][a];
     }
     resp[c * 4 + lane] = rv;
     if (n_mdr) n_mdr[c * 4 + lane] = m;
@@ -906,7 +906,7 @@ __global__ void __launch_bounds__(128) gw_fear_matrix_kernel(const Tables* T, in
   if (lane < 6 && (lane & 1) == 0) {                    // even lane holds n_mdr, its neighbour n_act
     const long long o = c * 16 + x * 4 + j;
     if (x < n && j < n) {
-      resp[o] = T->resp_lut[my][other];
+      resp[o] = T->small.resp_lut[my][other];
       n_mdr[o] = (int8_t)my;
       n_act[o] = (int8_t)other;
     }
@@ -1175,7 +1175,7 @@ int gw_create(const gw_config* cfg, gw_handle** out) {
     for (int a = 0; a < 10; ++a) {
       volatile double v = ((double)m - (double)a) / ((double)m + 0.000001);   // Responsibility.py:194-195, EPS :12
       double cl = v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v);                      // np.clip :198
-      t->resp_lut[m][a] = cl;
+      t->small.resp_lut[m][a] = cl;
     }
   auto cleanup = [&](int rc) { delete t; gw_destroy(h); return rc; };
   if ((e = cudaMalloc(&h->d_tables, sizeof(gw::Tables))) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMalloc tables"));
