@@ -11,9 +11,9 @@
 //     every later path entry back on p0, i.e. a crashed agent is a stationary one.
 //   * The five-rule pair test (:276-390) only compares cells of the two agents, so it is translation
 //     invariant: for a pair it depends on (p0_j - p0_i, eff_i, eff_j) and on nothing else.  gw_create
-//     evaluates the literal rules (pair_hit below) once for every |delta|_1 <= 4 and every eff pair
-//     into a 13.7 KB table of 4-bit masks (bit s = the pair collides at sub-step s).  Agents further
-//     apart than 4 can never share or swap a cell within one step.
+//     evaluates the literal rules (pair_hit below) once for every |delta|_1 <= 4 (41 offsets, "diamond"
+//     index) and every eff pair into a 6.9 KB table of 4-bit masks (bit s = the pair collides at
+//     sub-step s).  Agents further apart than 4 can never share or swap a cell within one step.
 //   * The fix-point of :247-405 then runs on bit vectors: three 24-bit words hold the masks of the six
 //     pairs for (both nominal / second crashed / first crashed); one pass is a handful of logic ops.
 #pragma once
@@ -25,8 +25,19 @@
 namespace gw {
 
 constexpr int N_EFF = 13;
-constexpr int LUT_DELTAS = 81;                      // (dr + 4) * 9 + (dc + 4)
-constexpr int LUT_BYTES = LUT_DELTAS * N_EFF * N_EFF;   // 13689
+constexpr int N_DELTA = 41;                         // offsets with |dr| + |dc| <= 4 in row-major order: idx(-d) = 40 - idx(d)
+constexpr int LUT_BYTES = N_DELTA * N_EFF * N_EFF;  // 6929
+
+// Everything the world update and the counterfactual counting read, in one block that every CTA copies to shared
+// memory (9.8 KB).  Built by gw_create.
+struct SimTab {
+  alignas(16) uint8_t lut[(LUT_BYTES + 15) / 16 * 16];      // [delta][eff_i][eff_j] -> 4-bit sub-step hit mask (symmetric: [d][a][b] == [40-d][b][a])
+  alignas(16) uint8_t next[GW_MAX_H * GW_W * 4];            // [cell][dir Up,Down,Left,Right] -> cell after the move (same cell if blocked)
+  alignas(16) uint16_t rowmask[(N_DELTA * N_EFF + 7) / 8 * 8];   // [delta][eff_i] -> bit e: lut[delta][eff_i][e] != 0
+  alignas(16) uint16_t unres[GW_MAX_H * GW_W];              // [cell] -> bit a: action a is not restricted from this cell
+  alignas(16) uint8_t diamond[96];                          // (dr + 4) * 9 + (dc + 4) -> delta index (0xFF outside the diamond)
+  alignas(16) uint16_t reach[64];                           // [near6] -> 4 nibbles: agents linked to agent x by chains of near pairs
+};
 
 struct SmallTables {                    // per-step lookups, copied to shared memory by every CTA (2592 B)
   alignas(16) double resp_lut[10][10];                      // clip((m-a)/(m+1e-6),-1,1), Responsibility.py:194-198
@@ -37,9 +48,8 @@ struct SmallTables {                    // per-step lookups, copied to shared me
 };
 
 struct Tables {                         // device-global, read-only, built by gw_create
-  alignas(16) uint8_t pair_lut[LUT_BYTES + 7];      // [delta][eff_i][eff_j] -> 4-bit sub-step hit mask
+  SimTab sim;
   alignas(16) uint32_t obs_template[2][64 * 4];             // constant observation row (-1 inactive / 0 active) as f32 / bf16 16-byte vectors
-  alignas(16) uint8_t next_cell[GW_MAX_H * GW_W * 4];       // [cell][dir Up,Down,Left,Right] -> cell after the move (same cell if blocked)
   SmallTables small;
   uint16_t map_rows[GW_MAX_H];
   int32_t n_active;
@@ -123,14 +133,14 @@ __device__ __forceinline__ uint32_t action_mask_bits(const uint16_t* rows, int H
 }
 
 // ---------------------------------------------------------------- pair geometry of one env
-// near6: bit p = pair p (01,02,03,12,13,23) within Manhattan distance 4; didx: 7-bit delta index per pair.
+// near6: bit p = pair p (01,02,03,12,13,23) within Manhattan distance 4; didx: delta index (0..40) per pair.
 struct PairGeom {
   uint32_t near6;
   uint32_t didx_lo;     // pairs 0..3, 8 bits each
   uint32_t didx_hi;     // pairs 4..5
 };
 
-__device__ __forceinline__ PairGeom pair_geometry(int n, uint32_t cells) {
+__device__ __forceinline__ PairGeom pair_geometry(const SimTab& T, int n, uint32_t cells) {
   PairGeom g;
   g.near6 = g.didx_lo = g.didx_hi = 0;
   int p = 0;
@@ -143,7 +153,7 @@ __device__ __forceinline__ PairGeom pair_geometry(int n, uint32_t cells) {
         const int dr = (int)(b >> 4) - (int)(a >> 4), dc = (int)(b & 15) - (int)(a & 15);
         if (abs(dr) + abs(dc) <= 4) {
           g.near6 |= 1u << p;
-          const uint32_t di = (uint32_t)((dr + 4) * 9 + (dc + 4));
+          const uint32_t di = T.diamond[(dr + 4) * 9 + (dc + 4)];
           if (p < 4) g.didx_lo |= di << (8 * p); else g.didx_hi |= di << (8 * (p - 4));
         }
       }
@@ -157,7 +167,7 @@ __device__ __forceinline__ uint32_t geom_didx(const PairGeom& g, int p) {
 }
 
 // agents connected to x through chains of near pairs (only they can influence x's crash outcome)
-__device__ __forceinline__ uint32_t reach_mask(uint32_t near6, int x) {
+__host__ __device__ __forceinline__ uint32_t reach_mask_slow(uint32_t near6, int x) {
   uint32_t adj = 0;                                   // 4 nibbles: adjacency row per agent
   if (near6 & 1u) adj |= (2u << 0) | (1u << 4);       // (0,1)
   if (near6 & 2u) adj |= (4u << 0) | (1u << 8);       // (0,2)
@@ -166,15 +176,16 @@ __device__ __forceinline__ uint32_t reach_mask(uint32_t near6, int x) {
   if (near6 & 16u) adj |= (8u << 4) | (2u << 12);     // (1,3)
   if (near6 & 32u) adj |= (8u << 8) | (4u << 12);     // (2,3)
   uint32_t r = 1u << x;
-#pragma unroll
   for (int it = 0; it < 3; ++it) {
     uint32_t nr = r;
-#pragma unroll
     for (int a = 0; a < 4; ++a)
       if ((r >> a) & 1u) nr |= (adj >> (4 * a)) & 0xFu;
     r = nr;
   }
   return r;
+}
+__device__ __forceinline__ uint32_t reach_mask(const SimTab& T, uint32_t near6, int x) {
+  return ((uint32_t)T.reach[near6 & 63u] >> (4 * x)) & 0xFu;
 }
 
 // ---------------------------------------------------------------- collision fix-point on bit vectors
@@ -190,8 +201,7 @@ __device__ __forceinline__ uint32_t agents_of_pairs(uint32_t hp) {
 }
 
 // effp: 4 x 4-bit effective trajectories.  pair_sel: which of the six pairs to look up.
-__device__ __forceinline__ uint32_t nn_masks(const uint8_t* __restrict__ s_lut, const PairGeom& g, uint32_t effp,
-                                             uint32_t pair_sel) {
+__device__ __forceinline__ uint32_t nn_masks(const SimTab& T, const PairGeom& g, uint32_t effp, uint32_t pair_sel) {
   uint32_t NNw = 0;
   const uint32_t sel = g.near6 & pair_sel;
   int p = 0;
@@ -200,18 +210,20 @@ __device__ __forceinline__ uint32_t nn_masks(const uint8_t* __restrict__ s_lut, 
 #pragma unroll
     for (int j = i + 1; j < 4; ++j, ++p)
       if ((sel >> p) & 1u)
-        NNw |= (uint32_t)s_lut[geom_didx(g, p) * (N_EFF * N_EFF) + ((effp >> (4 * i)) & 0xFu) * N_EFF +
+        NNw |= (uint32_t)T.lut[geom_didx(g, p) * (N_EFF * N_EFF) + ((effp >> (4 * i)) & 0xFu) * N_EFF +
                                ((effp >> (4 * j)) & 0xFu)] << (4 * p);
   return NNw;
 }
 
-// The fix-point proper, given the both-on-course masks NNw != 0 of all near pairs.
-__device__ __forceinline__ uint32_t resolve(const uint8_t* __restrict__ s_lut, const PairGeom& g, uint32_t effp,
-                                            uint32_t NNw, uint32_t stop) {
-  // first sub-step with a hit: nothing happens before it
+// The fix-point proper, given the both-on-course masks NNw != 0 of all near pairs.  The reference walks the sub-steps
+// one by one and repeats passes within a sub-step (:247-405); the crashed set only changes at a sub-step with a hit, so
+// this loop jumps from hit to hit: `live` = hits still possible under the current crashed set (4 bits per pair), the
+// earliest one at or after the current sub-step crashes its agents, and the same sub-step is looked at again (= the
+// next pass).  Every round adds a crashed agent, so there are at most four.
+__device__ __forceinline__ uint32_t resolve(const SimTab& T, const PairGeom& g, uint32_t effp, uint32_t NNw, uint32_t stop) {
   const uint32_t any = (NNw | (NNw >> 4) | (NNw >> 8) | (NNw >> 12) | (NNw >> 16) | (NNw >> 20)) & 0xFu;
-  const int s0 = __ffs(any) - 1;
-  uint32_t crashed = agents_of_pairs((NNw >> s0) & 0x111111u);
+  int s = __ffs(any) - 1;
+  uint32_t crashed = agents_of_pairs((NNw >> s) & 0x111111u);
   if (crashed & stop) return crashed << 12;
   uint32_t NRw = 0, RNw = 0;                          // second agent crashed (stationary) / first agent crashed
   {
@@ -222,31 +234,29 @@ __device__ __forceinline__ uint32_t resolve(const uint8_t* __restrict__ s_lut, c
       for (int j = i + 1; j < 4; ++j, ++p)
         if ((g.near6 >> p) & 1u) {
           const uint32_t base = geom_didx(g, p) * (N_EFF * N_EFF);
-          NRw |= (uint32_t)s_lut[base + ((effp >> (4 * i)) & 0xFu) * N_EFF] << (4 * p);
-          RNw |= (uint32_t)s_lut[base + ((effp >> (4 * j)) & 0xFu)] << (4 * p);
+          NRw |= (uint32_t)T.lut[base + ((effp >> (4 * i)) & 0xFu) * N_EFF] << (4 * p);
+          RNw |= (uint32_t)T.lut[base + ((effp >> (4 * j)) & 0xFu)] << (4 * p);
         }
   }
-  uint32_t out = 0;
-  for (int s = s0; s < 4; ++s) {
-    while (true) {
-      const uint32_t Pi = ((crashed & 1u) ? 0x000FFFu : 0u) | ((crashed & 2u) ? 0x0FF000u : 0u) | ((crashed & 4u) ? 0xF00000u : 0u);
-      const uint32_t Pj = ((crashed & 2u) ? 0x00000Fu : 0u) | ((crashed & 4u) ? 0x00F0F0u : 0u) | ((crashed & 8u) ? 0xFF0F00u : 0u);
-      const uint32_t hp = (((NNw & ~Pi & ~Pj) | (NRw & ~Pi & Pj) | (RNw & Pi & ~Pj)) >> s) & 0x111111u;
-      if (hp == 0) break;
-      crashed |= agents_of_pairs(hp);
-    }
+  uint32_t out = (crashed * 0x1111u) & (0xFFFFu << (4 * s));
+  while (true) {
+    const uint32_t Pi = ((crashed & 1u) ? 0x000FFFu : 0u) | ((crashed & 2u) ? 0x0FF000u : 0u) | ((crashed & 4u) ? 0xF00000u : 0u);
+    const uint32_t Pj = ((crashed & 2u) ? 0x00000Fu : 0u) | ((crashed & 4u) ? 0x00F0F0u : 0u) | ((crashed & 8u) ? 0xFF0F00u : 0u);
+    const uint32_t live = ((NNw & ~Pi & ~Pj) | (NRw & ~Pi & Pj) | (RNw & Pi & ~Pj)) & (((0xFu << s) & 0xFu) * 0x111111u);
+    if (live == 0) break;
+    s = __ffs((live | (live >> 4) | (live >> 8) | (live >> 12) | (live >> 16) | (live >> 20)) & 0xFu) - 1;
+    crashed |= agents_of_pairs((live >> s) & 0x111111u);
     if (crashed & stop) return crashed << 12;
-    out |= crashed << (4 * s);
+    out |= (crashed * 0x1111u) & (0xFFFFu << (4 * s));
   }
   return out;
 }
 
-__device__ __forceinline__ uint32_t collide(const uint8_t* __restrict__ s_lut, const PairGeom& g, uint32_t effp,
-                                            uint32_t stop = 0) {
+__device__ __forceinline__ uint32_t collide(const SimTab& T, const PairGeom& g, uint32_t effp, uint32_t stop = 0) {
   if (g.near6 == 0) return 0;
-  const uint32_t NNw = nn_masks(s_lut, g, effp, 0x3Fu);
+  const uint32_t NNw = nn_masks(T, g, effp, 0x3Fu);
   if (NNw == 0) return 0;                             // nobody collides while everyone is on course
-  return resolve(s_lut, g, effp, NNw, stop);
+  return resolve(T, g, effp, NNw, stop);
 }
 
 // cell of agent at the end of sub-step s (grid_world.py:259-264 floor index; crashed => start cell)
@@ -267,18 +277,17 @@ struct StepResult {
 // GWorld.UpdateGWorld with explicit actions for all n agents (custom/grid_world.py:424-563).
 // OWN_APPLES: count only eater e on apple e (all the env wrappers ever look at, ma_customenv.py:264 / customenv.py:143).
 template <bool OWN_APPLES = false>
-__device__ __forceinline__ StepResult world_update(const uint8_t* __restrict__ s_lut, const uint8_t* __restrict__ s_next,
-                                                   int n, uint32_t cells, uint32_t acts, const PairGeom& g,
+__device__ __forceinline__ StepResult world_update(const SimTab& T, int n, uint32_t cells, uint32_t acts, const PairGeom& g,
                                                    uint32_t apple_cells, uint32_t apple_on, int n_eaters) {
   Traj t[4];
   StepResult r;
   r.effs = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    t[i] = make_traj(s_next, (cells >> (8 * i)) & 0xFFu, i < n ? (acts >> (4 * i)) & 0xFu : 0u);
+    t[i] = make_traj(T.next, (cells >> (8 * i)) & 0xFFu, i < n ? (acts >> (4 * i)) & 0xFu : 0u);
     r.effs |= t[i].eff << (4 * i);
   }
-  const uint32_t cm = (n >= 2) ? collide(s_lut, g, r.effs) : 0u;
+  const uint32_t cm = (n >= 2) ? collide(T, g, r.effs) : 0u;
   r.crash = (cm >> 12) & 0xFu;
   r.cells = 0;
   r.restr = 0;
@@ -318,25 +327,43 @@ __device__ __forceinline__ uint32_t pairs_of_agent(int j) {
 // the affected agent j leave it neither restricted nor crashed (:46).  eff_others: effective trajectories of
 // everybody else, agents outside the list already 0 (Stay, :43).  in_list = false: j is not in the list, its action
 // cannot be swapped in, so all nine simulations are the same one (j Stays) and the count is 0 or 9.
-// The pair masks that do not involve j are looked up once; per action only the <= 3 pairs of j change.
-// a_begin/a_end: sub-range of the nine actions (small batches split a list over nine threads for latency).
-__device__ __forceinline__ uint32_t count_valid_moves(const uint8_t* __restrict__ s_lut, const uint8_t* __restrict__ s_next,
-                                                      uint32_t cells, uint32_t eff_others, const PairGeom& g, int j,
-                                                      bool in_list, uint32_t a_begin = 0, uint32_t a_end = GW_N_ACTIONS) {
+// An unrestricted action a is the effective trajectory a (restricted ones are invalid whatever happens), so the nine
+// simulations are a walk over the bits of unres[cell_j].  j can only crash through a pair (j, k) that hits while k is
+// on course or while k stands crashed on its start cell: rowmask gives, for every near k, the trajectories of j with
+// such a hit.  All the others are valid without simulating anything; only the rest runs the fix-point.
+// a_mask: sub-set of the nine actions (small batches split a list over several threads for latency).
+__device__ __forceinline__ uint32_t count_valid_moves(const SimTab& T, uint32_t cells, uint32_t eff_others, const PairGeom& g,
+                                                      int j, bool in_list, uint32_t a_mask = 0x1FFu) {
   const uint32_t pj = pairs_of_agent(j);
   const uint32_t eo = eff_others & ~(0xFu << (4 * j));
-  const uint32_t nn_fixed = nn_masks(s_lut, g, eo, 0x3Fu & ~pj);
-  const uint32_t cell_j = (cells >> (8 * j)) & 0xFFu;
-  uint32_t count = 0;
-  if (!in_list) { if (a_begin != 0) return 0; a_end = 1; }
-  for (uint32_t a = a_begin; a < a_end; ++a) {
-    const Traj tj = make_traj(s_next, cell_j, a);
-    if (tj.r1 | tj.r2) continue;            // restricted, or crashed before the blocked second move: invalid either way
-    const uint32_t effp = eo | (tj.eff << (4 * j));
-    const uint32_t NNw = nn_fixed | nn_masks(s_lut, g, effp, pj);
-    if (NNw == 0) { ++count; continue; }
-    const uint32_t cm = resolve(s_lut, g, effp, NNw, 1u << j);
-    if (((cm >> (12 + j)) & 1u) == 0) ++count;
+  const uint32_t cand = (in_list ? (uint32_t)T.unres[(cells >> (8 * j)) & 0xFFu] : 1u) & a_mask;
+  uint32_t unsafe = 0;
+  {
+    int p = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = i + 1; k < 4; ++k, ++p)
+        if ((i == j || k == j) && ((g.near6 >> p) & 1u)) {
+          // pair (i, k): j second -> row [d][eff_i]; j first -> by symmetry row [40 - d][eff_k]
+          const uint32_t d = (k == j) ? geom_didx(g, p) : (uint32_t)(N_DELTA - 1) - geom_didx(g, p);
+          const uint32_t eother = (eo >> (4 * (k == j ? i : k))) & 0xFu;
+          unsafe |= (uint32_t)T.rowmask[d * N_EFF + eother] | (uint32_t)T.rowmask[d * N_EFF];
+        }
+  }
+  uint32_t count = (uint32_t)__popc(cand & ~unsafe);
+  uint32_t todo = cand & unsafe;
+  if (todo) {
+    const uint32_t nn_fixed = nn_masks(T, g, eo, 0x3Fu & ~pj);
+    do {
+      const uint32_t e = (uint32_t)__ffs(todo) - 1u;
+      todo &= todo - 1u;
+      const uint32_t effp = eo | (e << (4 * j));
+      const uint32_t NNw = nn_fixed | nn_masks(T, g, effp, pj);
+      if (NNw == 0) { ++count; continue; }
+      const uint32_t cm = resolve(T, g, effp, NNw, 1u << j);
+      if (((cm >> (12 + j)) & 1u) == 0) ++count;
+    } while (todo);
   }
   return in_list ? count : count * 9u;
 }

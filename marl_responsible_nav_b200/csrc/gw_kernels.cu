@@ -44,7 +44,7 @@ struct StepParams {
   uint32_t seed_lo, seed_hi;
   double fear_weight;
   const uint8_t* reset_mask;          // gw_reset only
-  unsigned long long* trace;          // GW_TRACE (dev): per CTA 8 globaltimer stamps at the phase boundaries
+  unsigned long long* trace;          // GW_TRACE (dev): per CTA 16 globaltimer stamps at the phase boundaries
 };
 
 constexpr int STAT_SLOTS = 1024;
@@ -57,8 +57,7 @@ constexpr int N_SPEC = GW_MAX_LEARNERS * (GW_MAX_AGENTS + 1);   // per learner: 
 
 template <int TILE>
 struct Smem {
-  alignas(16) uint8_t lut[(LUT_BYTES + 15) / 16 * 16];
-  alignas(16) uint8_t next[GW_MAX_H * GW_W * 4];
+  SimTab sim;
   alignas(16) SmallTables small;
   uint16_t rows[GW_MAX_H];
   union {                                                   // P1b/P2 scratch of the FeAR tasks, then the mask staging (P3/P4)
@@ -89,10 +88,9 @@ template <int THREADS, int TILE, int OBS>
 __device__ __forceinline__ void load_tables(Smem<TILE>& s, uint8_t* stage, const Tables* __restrict__ T, int H, int nl,
                                             bool need_lut) {
   const int tid = threadIdx.x;
-  if (need_lut) {
-    for (int i = tid; i < (LUT_BYTES + 15) / 16; i += THREADS) cp_async16(s.lut + 16 * i, T->pair_lut + 16 * i);
-    for (int i = tid; i < GW_MAX_H * GW_W * 4 / 16; i += THREADS) cp_async16(s.next + 16 * i, T->next_cell + 16 * i);
-  }
+  if (need_lut)
+    for (int i = tid; i < (int)sizeof(SimTab) / 16; i += THREADS)
+      cp_async16(reinterpret_cast<uint8_t*>(&s.sim) + 16 * i, reinterpret_cast<const uint8_t*>(&T->sim) + 16 * i);
   for (int i = tid; i < (int)sizeof(SmallTables) / 16; i += THREADS)
     cp_async16(reinterpret_cast<uint8_t*>(&s.small) + 16 * i, reinterpret_cast<const uint8_t*>(&T->small) + 16 * i);
   if (tid < GW_MAX_H) s.rows[tid] = T->map_rows[tid];
@@ -406,7 +404,7 @@ __device__ __forceinline__ void trace_stamp(const StepParams& p, int slot) {
   if (p.trace != nullptr && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    p.trace[(size_t)blockIdx.x * 8 + slot] = t;
+    p.trace[(size_t)blockIdx.x * 16 + slot] = t;
   }
 }
 
@@ -499,12 +497,15 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
           acts |= a << (4 * i);
         }
       }
-      const PairGeom g = pair_geometry(n, cells);
+      trace_stamp(p, 8);
+      const PairGeom g = pair_geometry(s.sim, n, cells);
+      trace_stamp(p, 9);
 
       // ---- the real update (ma_customenv.py:254)
       const uint32_t apples_before = meta & M_APPLES;
-      const StepResult r = world_update<true>(s.lut, s.next, n, cells, acts, g, p.apple_cells, apples_before, nl);
+      const StepResult r = world_update<true>(s.sim, n, cells, acts, g, p.apple_cells, apples_before, nl);
       const uint32_t cells_new = r.cells;
+      trace_stamp(p, 10);
 
       // ---- FeAR tasks on the pre-step positions (ma_customenv.py:245-252 / customenv.py:113-120)
       if (FEAR) {
@@ -516,14 +517,14 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
           // action == MdR: both counts are equal -> Resp = 0 exactly.  Agents that no chain of near pairs links to the
           // actor cannot be influenced by its move -> equal counts -> 0 as well.
           if (ax == mx) continue;
-          const uint32_t js = reach_mask(g.near6, x) & ~(1u << x) & ((1u << n) - 1u);
+          const uint32_t js = reach_mask(s.sim, g.near6, x) & ~(1u << x) & ((1u << n) - 1u);
           if (js == 0) continue;
           uint32_t close = 0;                                              // close_agents :456-464
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             if (k < n && (k == x || manhattan((cells >> (8 * x)) & 0xFFu, (cells >> (8 * k)) & 0xFFu) <= p.fear_radius))
               close |= 1u << k;
-          const uint32_t eff_mdr = make_traj(s.next, (cells >> (8 * x)) & 0xFFu, mx).eff;   // actor plays its MdR
+          const uint32_t eff_mdr = make_traj(s.sim.next, (cells >> (8 * x)) & 0xFFu, mx).eff;   // actor plays its MdR
           if (eff_mdr == ((r.effs >> (4 * x)) & 0xFu)) continue;           // same trajectory (e.g. both blocked): counts equal
           closew |= close << (4 * x);
           effw |= eff_mdr << (16 + 4 * x);
@@ -548,6 +549,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
         }
       }
 
+      trace_stamp(p, 11);
       uint32_t apples_left = apples_before;
       uint32_t term_now = 0, trunc_now = 0, apples_rewarded = 0, crash_count = 0, shaped = 0;
       if (p.kind == GW_ENV_MULTI) {
@@ -611,6 +613,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
       const bool episode_over = (p.kind == GW_ENV_MULTI) ? (trunc_now != 0) : ((term_now | trunc_now) != 0);
       const bool ended = episode_over || (p.max_steps > 0 && (int)steps_now >= p.max_steps);
 
+      trace_stamp(p, 12);
       // ---- scalar outputs (one thread per env: each array is written with unit stride across the warp)
       if (nl == 2) {
         if (p.io.reward) reinterpret_cast<float2*>(p.io.reward)[e] = make_float2((float)reward[0], (float)reward[1]);
@@ -627,6 +630,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
         p.io.info[e] = (r.crash & 15u) | ((r.restr & 15u) << 4) | (crash_count << 8) | (apples_rewarded << 10) |
                        ((ended ? 1u : 0u) << 12) | (shaped << 14);
 
+      trace_stamp(p, 13);
       // ---- episode return (reward units: 1 multi, 0.1 single), state for the next step, render record
       ret0 = (int)(short)(st.w & 0xFFFFu);
       ret1 = (int)(short)(st.w >> 16);
@@ -644,6 +648,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
         s.cells_fin[tid] = cells_new;
         st_out = make_uint4(cells_r, meta_sp, tick + 1, 0u);
       }
+      trace_stamp(p, 14);
       p.state[e] = st_out;
       if (p.io.obs_code)
         p.io.obs_code[e] = (unsigned long long)cells_r | ((unsigned long long)apples_r << 32) |
@@ -679,8 +684,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
         g.didx_hi = s.geom_hi[el] & 0xFFFFu;
         g.near6 = s.geom_hi[el] >> 16;
         constexpr uint32_t PER = 9u / SPLIT;
-        const uint32_t cnt = (SPLIT == 1u) ? count_valid_moves(s.lut, s.next, s.cells_old[el], eo, g, (int)j, jc != 0)
-                                           : count_valid_moves(s.lut, s.next, s.cells_old[el], eo, g, (int)j, jc != 0, a0 * PER, a0 * PER + PER);
+        const uint32_t cnt = count_valid_moves(s.sim, s.cells_old[el], eo, g, (int)j, jc != 0,
+                                               (SPLIT == 1u) ? 0x1FFu : (((1u << PER) - 1u) << (a0 * PER)));
         const uint32_t jslot = j - (j > x ? 1u : 0u);
         if (cnt) atomicAdd(&s.cnt[el * 2 + x], cnt << (4 * (jslot * 2 + v)));
       }
@@ -763,18 +768,12 @@ static inline size_t stage_row_bytes(const gw_config& c) {
 }
 
 // ------------------------------------------------------------------ operator-level kernels
-struct OpSmem {
-  alignas(16) uint8_t lut[(LUT_BYTES + 15) / 16 * 16];
-  alignas(16) uint8_t next[GW_MAX_H * GW_W * 4];
-};
+typedef SimTab OpSmem;
 
 __device__ __forceinline__ void load_op_tables(OpSmem& s, const Tables* __restrict__ T) {
-  const uint4* src = reinterpret_cast<const uint4*>(T->pair_lut);
-  uint4* dst = reinterpret_cast<uint4*>(s.lut);
-  for (int i = threadIdx.x; i < (LUT_BYTES + 15) / 16; i += blockDim.x) dst[i] = __ldg(src + i);
-  const uint4* nsrc = reinterpret_cast<const uint4*>(T->next_cell);
-  uint4* ndst = reinterpret_cast<uint4*>(s.next);
-  for (int i = threadIdx.x; i < GW_MAX_H * GW_W * 4 / 16; i += blockDim.x) ndst[i] = __ldg(nsrc + i);
+  const uint4* src = reinterpret_cast<const uint4*>(&T->sim);
+  uint4* dst = reinterpret_cast<uint4*>(&s);
+  for (int i = threadIdx.x; i < (int)sizeof(SimTab) / 16; i += blockDim.x) dst[i] = __ldg(src + i);
   __syncthreads();
 }
 
@@ -804,8 +803,8 @@ __global__ void __launch_bounds__(128) gw_update_world_kernel(const Tables* T, i
         apple_on |= 1u << k;
         apple_cells |= (uint32_t)(((apples[(c * 2 + k) * 2] & 15) << 4) | (apples[(c * 2 + k) * 2 + 1] & 15)) << (8 * k);
       }
-  const PairGeom g = pair_geometry(n, cells);
-  const StepResult r = world_update(s.lut, s.next, n, cells, acts, g, apple_cells, apple_on, min(2, n));
+  const PairGeom g = pair_geometry(s, n, cells);
+  const StepResult r = world_update(s, n, cells, acts, g, apple_cells, apple_on, min(2, n));
   for (int i = 0; i < 4; ++i) {
     const uint32_t cc = (r.cells >> (8 * i)) & 0xFFu;
     new_pos[(c * 4 + i) * 2] = i < n ? (int8_t)(cc >> 4) : (int8_t)-1;
@@ -833,7 +832,7 @@ __global__ void __launch_bounds__(128) gw_fear_kernel(const Tables* T, int n_def
   load_case(c, n, pos, act, cells, acts);
   for (int i = 0; i < n; ++i)
     if (in_list == nullptr || in_list[c * 4 + i]) lst |= 1u << i;
-  const PairGeom g = pair_geometry(n, cells);
+  const PairGeom g = pair_geometry(s, n, cells);
   uint32_t base = 0;                                   // effective trajectories of the listed agents; the others Stay (:43)
 #pragma unroll
   for (int k = 0; k < 4; ++k)
@@ -845,7 +844,7 @@ __global__ void __launch_bounds__(128) gw_fear_kernel(const Tables* T, int n_def
   if (lane < 6 && j < n) {
     const uint32_t av = v == 0 ? (uint32_t)min(max((int)mdr[c * 4 + x], 0), 8) : ((acts >> (4 * x)) & 0xFu);
     const uint32_t eo = (base & ~(0xFu << (4 * x))) | (make_traj(s.next, (cells >> (8 * x)) & 0xFFu, av).eff << (4 * x));
-    my = count_valid_moves(s.lut, s.next, cells, eo, g, j, ((lst >> j) & 1u) != 0);   // SwapActionIDs4Agents: listed agents only
+    my = count_valid_moves(s, cells, eo, g, j, ((lst >> j) & 1u) != 0);   // SwapActionIDs4Agents: listed agents only
   }
   uint32_t packed = 0;
 #pragma unroll
@@ -886,7 +885,7 @@ __global__ void __launch_bounds__(128) gw_fear_matrix_kernel(const Tables* T, in
   load_case(c, n, pos, act, cells, acts);
   for (int i = 0; i < n; ++i)
     if (in_list == nullptr || in_list[c * 4 + i]) lst |= 1u << i;
-  const PairGeom g = pair_geometry(n, cells);
+  const PairGeom g = pair_geometry(s, n, cells);
   uint32_t base = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k)
@@ -900,7 +899,7 @@ __global__ void __launch_bounds__(128) gw_fear_matrix_kernel(const Tables* T, in
     if (v == 0 && ((lst >> x) & 1u))                    // SwapActionIDs4Agents: only an actor present in the list plays its MdR
       eo = (base & ~(0xFu << (4 * x))) |
            (make_traj(s.next, (cells >> (8 * x)) & 0xFFu, (uint32_t)min(max((int)mdr[c * 4 + x], 0), 8)).eff << (4 * x));
-    my = count_valid_moves(s.lut, s.next, cells, eo, g, j, ((lst >> j) & 1u) != 0);
+    my = count_valid_moves(s, cells, eo, g, j, ((lst >> j) & 1u) != 0);
   }
   const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, my, 1);
   if (lane < 6 && (lane & 1) == 0) {                    // even lane holds n_mdr, its neighbour n_act
@@ -930,7 +929,7 @@ __global__ void __launch_bounds__(128) gw_feal_kernel(const Tables* T, int n_def
   load_case(c, n, pos, act, cells, acts);
   for (int i = 0; i < n; ++i)
     if (in_list == nullptr || in_list[c * 4 + i]) lst |= 1u << i;
-  const PairGeom g = pair_geometry(n, cells);
+  const PairGeom g = pair_geometry(s, n, cells);
   const int ii = lane >> 1, v = lane & 1;               // v = 0: the others play their MdR, v = 1: their actions
   uint32_t my = 0;
   if (lane < 8 && ii < n) {
@@ -941,7 +940,7 @@ __global__ void __launch_bounds__(128) gw_feal_kernel(const Tables* T, int n_def
         const uint32_t a = v == 0 ? (uint32_t)min(max((int)mdr[c * 4 + k], 0), 8) : (acts >> (4 * k)) & 0xFu;
         eo |= make_traj(s.next, (cells >> (8 * k)) & 0xFFu, a).eff << (4 * k);
       }
-    my = count_valid_moves(s.lut, s.next, cells, eo, g, ii, ((lst >> ii) & 1u) != 0);
+    my = count_valid_moves(s, cells, eo, g, ii, ((lst >> ii) & 1u) != 0);
   }
   const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, my, 1);
   if (lane < 8 && (lane & 1) == 0) {
@@ -1092,6 +1091,17 @@ static void build_next_cell(const gw_config* c, uint8_t* next) {
 
 // pair-mask table: the literal five-rule test (gw::pair_hit) for every relative start offset within Manhattan
 // distance 4 and every pair of effective trajectories, bit s = collision at sub-step s (both agents on course).
+static int diamond_index(int dr, int dc) {           // row-major rank of (dr, dc) among the offsets with |dr| + |dc| <= 4
+  int idx = 0;
+  for (int r = -4; r <= 4; ++r)
+    for (int c = -4; c <= 4; ++c) {
+      if (std::abs(r) + std::abs(c) > 4) continue;
+      if (r == dr && c == dc) return idx;
+      ++idx;
+    }
+  return -1;
+}
+
 static void build_pair_lut(uint8_t* lut) {
   static const int DR[4] = {-1, 1, 0, 0}, DC[4] = {0, 0, -1, 1};
   std::memset(lut, 0, gw::LUT_BYTES);
@@ -1122,9 +1132,46 @@ static void build_pair_lut(uint8_t* lut) {
             const int Aj = fj == 0 ? Pj : (fj == 1 ? j1 : j2), Bj = cj == 1 ? j1 : j2;
             if (gw::pair_hit(Ai, Bi, Pi, qi, fi, ci, Aj, Bj, Pj, qj, fj, cj)) mask |= (uint8_t)(1u << s);
           }
-          lut[((dr + 4) * 9 + (dc + 4)) * (gw::N_EFF * gw::N_EFF) + ei * gw::N_EFF + ej] = mask;
+          lut[diamond_index(dr, dc) * (gw::N_EFF * gw::N_EFF) + ei * gw::N_EFF + ej] = mask;
         }
     }
+}
+
+// The tables derived from the pair-mask table and the map.  Returns false if the pair table is not symmetric under
+// swapping the two agents (count_valid_moves relies on it; it is a property of the five rules, checked here anyway).
+static bool build_sim_tables(const gw_config* cfg, gw::SimTab* T) {
+  build_pair_lut(T->lut);
+  build_next_cell(cfg, T->next);
+  const int EE = gw::N_EFF * gw::N_EFF;
+  for (int d = 0; d < gw::N_DELTA; ++d)
+    for (int a = 0; a < gw::N_EFF; ++a) {
+      uint16_t m = 0;
+      for (int b = 0; b < gw::N_EFF; ++b) {
+        if (T->lut[d * EE + a * gw::N_EFF + b] != T->lut[(gw::N_DELTA - 1 - d) * EE + b * gw::N_EFF + a]) return false;
+        if (T->lut[d * EE + a * gw::N_EFF + b]) m |= (uint16_t)(1u << b);
+      }
+      T->rowmask[d * gw::N_EFF + a] = m;
+    }
+  for (int cell = 0; cell < GW_MAX_H * GW_W; ++cell) {     // actions that are not restricted (grid_world.py:481-518)
+    uint16_t m = 1;
+    for (int d = 0; d < 4; ++d) {
+      const int p1 = T->next[cell * 4 + d];
+      if (p1 == cell) continue;
+      m |= (uint16_t)(1u << (1 + d));
+      if (T->next[p1 * 4 + d] != p1) m |= (uint16_t)(1u << (5 + d));
+    }
+    T->unres[cell] = m;
+  }
+  std::memset(T->diamond, 0xFF, sizeof(T->diamond));
+  for (int dr = -4; dr <= 4; ++dr)
+    for (int dc = -4; dc <= 4; ++dc)
+      if (std::abs(dr) + std::abs(dc) <= 4) T->diamond[(dr + 4) * 9 + (dc + 4)] = (uint8_t)diamond_index(dr, dc);
+  for (int near6 = 0; near6 < 64; ++near6) {
+    uint16_t w = 0;
+    for (int x = 0; x < 4; ++x) w |= (uint16_t)(gw::reach_mask_slow((uint32_t)near6, x) << (4 * x));
+    T->reach[near6] = w;
+  }
+  return true;
 }
 
 int gw_create(const gw_config* cfg, gw_handle** out) {
@@ -1164,13 +1211,12 @@ int gw_create(const gw_config* cfg, gw_handle** out) {
       if ((cfg->map_rows[r] >> c) & 1) t->small.active_cell[na++] = (uint8_t)((r << 4) | c);
   t->n_active = na;
   h->n_active = na;
-  build_next_cell(cfg, t->next_cell);
+  if (!build_sim_tables(cfg, &t->sim)) { delete t; delete h; return fail(nullptr, GW_EINVAL, "gw_create: internal: pair table is not symmetric"); }
   for (int cell = 0; cell < GW_MAX_H * GW_W; ++cell) {
     const bool active = (cell >> 4) < cfg->height && ((cfg->map_rows[cell >> 4] >> (cell & 15)) & 1);
     t->obs_template[0][cell] = active ? 0u : 0xBF800000u;                                   // f32 0.0 / -1.0
     t->obs_template[1][cell >> 1] |= (active ? 0u : 0xBF80u) << (16 * (cell & 1));           // bf16 0 / -1
   }
-  build_pair_lut(t->pair_lut);
   for (int m = 0; m < 10; ++m)
     for (int a = 0; a < 10; ++a) {
       volatile double v = ((double)m - (double)a) / ((double)m + 0.000001);   // Responsibility.py:194-195, EPS :12
@@ -1186,8 +1232,8 @@ int gw_create(const gw_config* cfg, gw_handle** out) {
   if ((e = cudaMemset(h->d_stats, 0, sizeof(unsigned long long) * gw::STAT_SLOTS * 8)) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMemset stats"));
   delete t;
   if (const char* tr = std::getenv("GW_TRACE")) {
-    if (std::atoi(tr) != 0 && cudaMalloc(&h->d_trace, sizeof(unsigned long long) * 8 * 4096) == cudaSuccess)
-      cudaMemset(h->d_trace, 0, sizeof(unsigned long long) * 8 * 4096);
+    if (std::atoi(tr) != 0 && cudaMalloc(&h->d_trace, sizeof(unsigned long long) * 16 * 4096) == cudaSuccess)
+      cudaMemset(h->d_trace, 0, sizeof(unsigned long long) * 16 * 4096);
   }
   *out = h;
   return GW_OK;
@@ -1455,12 +1501,12 @@ int gw_reset_stats(gw_handle* h, void* stream) {
   return GW_OK;
 }
 
-// dev only: GW_TRACE=1 makes gw_create allocate a per-CTA stamp buffer; gw_debug_trace copies it out (8 x uint64 per CTA)
+// dev only: GW_TRACE=1 makes gw_create allocate a per-CTA stamp buffer; gw_debug_trace copies it out (16 x uint64 per CTA)
 int gw_debug_trace(gw_handle* h, unsigned long long* host_out, int max_ctas) {
   if (!h || !h->d_trace || !host_out) return GW_EINVAL;
   GW_CUDA(h, cudaSetDevice(h->cfg.device));
   GW_CUDA(h, cudaDeviceSynchronize());
-  GW_CUDA(h, cudaMemcpy(host_out, h->d_trace, sizeof(unsigned long long) * 8 * (size_t)max_ctas, cudaMemcpyDeviceToHost));
+  GW_CUDA(h, cudaMemcpy(host_out, h->d_trace, sizeof(unsigned long long) * 16 * (size_t)max_ctas, cudaMemcpyDeviceToHost));
   return GW_OK;
 }
 

@@ -12,15 +12,19 @@ a = torch.randint(0, 9, (E, 2), device="cuda", dtype=torch.int8)
 for _ in range(20): env.step(a)
 torch.cuda.synchronize()
 n = min(4096, (E + 31) // 32 if E <= 32768 else 592)
-buf = np.zeros((n, 8), np.uint64)
+buf = np.zeros((n, 16), np.uint64)
 env.lib.gw_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 rc = env.lib.gw_debug_trace(env._h, buf.ctypes.data, n)
 assert rc == 0
 b = buf.astype(np.int64)
 b = b[b[:, 0] > 0]
 t0 = b[:, 0].min()
-names = ["start", "tables+P1a done", "P1b done", "P2 barrier", "P2 done", "P3 done", "P4 barrier", "tile end"]
+names = ["start", "tables+P1a done", "P1b done", "P2 barrier", "P2 done", "P3 done", "P4 barrier", "tile end",
+         "P1b: sampled", "P1b: geometry", "P1b: world_update", "P1b: fear tasks", "P1b: rewards", "P1b: outputs", "P1b: spawn", "-"]
 print(f"E={E} fear={fear} CTAs={len(b)}  kernel span = {(b[:, 7].max() - t0) / 1e3:.2f} us (first start -> last end)")
-for i, nm in enumerate(names):
+order = [0, 1, 8, 9, 10, 11, 12, 13, 14, 2, 3, 4, 5, 6, 7]
+for i in order:
+    nm = names[i]
+    if not (b[:, i] > 0).all(): continue
     rel = (b[:, i] - t0) / 1e3
     print(f"  {nm:18s} median {np.median(rel):7.2f}  min {rel.min():7.2f}  max {rel.max():7.2f} us")
