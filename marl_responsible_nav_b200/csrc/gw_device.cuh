@@ -29,11 +29,11 @@ constexpr int N_DELTA = 41;                         // offsets with |dr| + |dc| 
 constexpr int LUT_BYTES = N_DELTA * N_EFF * N_EFF;  // 6929
 
 // Everything the world update and the counterfactual counting read, in one block that every CTA copies to shared
-// memory (9.8 KB).  Built by gw_create.
+// memory (13 KB).  Built by gw_create.
 struct SimTab {
   alignas(16) uint8_t lut[(LUT_BYTES + 15) / 16 * 16];      // [delta][eff_i][eff_j] -> 4-bit sub-step hit mask (symmetric: [d][a][b] == [40-d][b][a])
   alignas(16) uint8_t next[GW_MAX_H * GW_W * 4];            // [cell][dir Up,Down,Left,Right] -> cell after the move (same cell if blocked)
-  alignas(16) uint16_t rowmask[(N_DELTA * N_EFF + 7) / 8 * 8];   // [delta][eff_i] -> bit e: lut[delta][eff_i][e] != 0
+  alignas(16) uint16_t rowmask4[N_DELTA * N_EFF][4];        // [delta][eff_i][s] -> bit e: lut[delta][eff_i][e] has bit s (hit at sub-step s)
   alignas(16) uint16_t unres[GW_MAX_H * GW_W];              // [cell] -> bit a: action a is not restricted from this cell
   alignas(16) uint8_t diamond[96];                          // (dr + 4) * 9 + (dc + 4) -> delta index (0xFF outside the diamond)
   alignas(16) uint16_t reach[64];                           // [near6] -> 4 nibbles: agents linked to agent x by chains of near pairs
@@ -215,6 +215,31 @@ __device__ __forceinline__ uint32_t nn_masks(const SimTab& T, const PairGeom& g,
   return NNw;
 }
 
+// Hit-to-hit loop of the fix-point: NNw / NRw / RNw = 4-bit sub-step hit masks of the six pairs for (both on course /
+// second agent crashed / first agent crashed), s = first sub-step with a hit, crashed = the agents it crashes.
+__device__ __forceinline__ uint32_t fixpoint_loop(uint32_t NNw, uint32_t NRw, uint32_t RNw, int s, uint32_t crashed,
+                                                  uint32_t stop) {
+  uint32_t out = (crashed * 0x1111u) & (0xFFFFu << (4 * s));
+  while (true) {
+    const uint32_t Pi = ((crashed & 1u) ? 0x000FFFu : 0u) | ((crashed & 2u) ? 0x0FF000u : 0u) | ((crashed & 4u) ? 0xF00000u : 0u);
+    const uint32_t Pj = ((crashed & 2u) ? 0x00000Fu : 0u) | ((crashed & 4u) ? 0x00F0F0u : 0u) | ((crashed & 8u) ? 0xFF0F00u : 0u);
+    const uint32_t live = ((NNw & ~Pi & ~Pj) | (NRw & ~Pi & Pj) | (RNw & Pi & ~Pj)) & (((0xFu << s) & 0xFu) * 0x111111u);
+    if (live == 0) break;
+    s = __ffs((live | (live >> 4) | (live >> 8) | (live >> 12) | (live >> 16) | (live >> 20)) & 0xFu) - 1;
+    crashed |= agents_of_pairs((live >> s) & 0x111111u);
+    if (crashed & stop) return crashed << 12;
+    out |= (crashed * 0x1111u) & (0xFFFFu << (4 * s));
+  }
+  return out;
+}
+
+// the whole fix-point from the three words (NNw != 0)
+__device__ __forceinline__ uint32_t fixpoint_words(uint32_t NNw, uint32_t NRw, uint32_t RNw) {
+  const uint32_t any = (NNw | (NNw >> 4) | (NNw >> 8) | (NNw >> 12) | (NNw >> 16) | (NNw >> 20)) & 0xFu;
+  const int s = __ffs(any) - 1;
+  return fixpoint_loop(NNw, NRw, RNw, s, agents_of_pairs((NNw >> s) & 0x111111u), 0u);
+}
+
 // The fix-point proper, given the both-on-course masks NNw != 0 of all near pairs.  The reference walks the sub-steps
 // one by one and repeats passes within a sub-step (:247-405); the crashed set only changes at a sub-step with a hit, so
 // this loop jumps from hit to hit: `live` = hits still possible under the current crashed set (4 bits per pair), the
@@ -238,18 +263,7 @@ __device__ __forceinline__ uint32_t resolve(const SimTab& T, const PairGeom& g, 
           RNw |= (uint32_t)T.lut[base + ((effp >> (4 * j)) & 0xFu)] << (4 * p);
         }
   }
-  uint32_t out = (crashed * 0x1111u) & (0xFFFFu << (4 * s));
-  while (true) {
-    const uint32_t Pi = ((crashed & 1u) ? 0x000FFFu : 0u) | ((crashed & 2u) ? 0x0FF000u : 0u) | ((crashed & 4u) ? 0xF00000u : 0u);
-    const uint32_t Pj = ((crashed & 2u) ? 0x00000Fu : 0u) | ((crashed & 4u) ? 0x00F0F0u : 0u) | ((crashed & 8u) ? 0xFF0F00u : 0u);
-    const uint32_t live = ((NNw & ~Pi & ~Pj) | (NRw & ~Pi & Pj) | (RNw & Pi & ~Pj)) & (((0xFu << s) & 0xFu) * 0x111111u);
-    if (live == 0) break;
-    s = __ffs((live | (live >> 4) | (live >> 8) | (live >> 12) | (live >> 16) | (live >> 20)) & 0xFu) - 1;
-    crashed |= agents_of_pairs((live >> s) & 0x111111u);
-    if (crashed & stop) return crashed << 12;
-    out |= (crashed * 0x1111u) & (0xFFFFu << (4 * s));
-  }
-  return out;
+  return fixpoint_loop(NNw, NRw, RNw, s, crashed, stop);
 }
 
 __device__ __forceinline__ uint32_t collide(const SimTab& T, const PairGeom& g, uint32_t effp, uint32_t stop = 0) {
@@ -327,17 +341,30 @@ __device__ __forceinline__ uint32_t pairs_of_agent(int j) {
 // the affected agent j leave it neither restricted nor crashed (:46).  eff_others: effective trajectories of
 // everybody else, agents outside the list already 0 (Stay, :43).  in_list = false: j is not in the list, its action
 // cannot be swapped in, so all nine simulations are the same one (j Stays) and the count is 0 or 9.
-// An unrestricted action a is the effective trajectory a (restricted ones are invalid whatever happens), so the nine
-// simulations are a walk over the bits of unres[cell_j].  j can only crash through a pair (j, k) that hits while k is
-// on course or while k stands crashed on its start cell: rowmask gives, for every near k, the trajectories of j with
-// such a hit.  All the others are valid without simulating anything; only the rest runs the fix-point.
-// a_mask: sub-set of the nine actions (small batches split a list over several threads for latency).
+//
+// No simulation per action.  An unrestricted action a is the effective trajectory a (restricted ones are invalid
+// whatever happens), so the candidates are the bits of unres[cell_j].  Until j is hit for the first time the other
+// agents evolve exactly as they would without j (j only influences them by colliding, and then it has crashed and the
+// action is invalid anyway), so one fix-point over the three pairs that do not involve j gives every other agent k its
+// crashed sets C_s after each sub-step, and j is hit at sub-step s iff for some near k
+//     k was on course when the sub-step started (k not in C_{s-1}) and lut[d_jk][e_j][eff_k] has bit s, or
+//     k stands crashed on its start cell by the end of it (k in C_s) and lut[d_jk][e_j][0] has bit s
+// (every change of the crashed set is followed by another pass over all pairs, grid_world.py:247-405).  rowmask4 holds
+// those bits for all trajectories of j at once, so the nine answers are a few 64-bit logic operations.
 __device__ __forceinline__ uint32_t count_valid_moves(const SimTab& T, uint32_t cells, uint32_t eff_others, const PairGeom& g,
-                                                      int j, bool in_list, uint32_t a_mask = 0x1FFu) {
+                                                      int j, bool in_list) {
   const uint32_t pj = pairs_of_agent(j);
   const uint32_t eo = eff_others & ~(0xFu << (4 * j));
-  const uint32_t cand = (in_list ? (uint32_t)T.unres[(cells >> (8 * j)) & 0xFFu] : 1u) & a_mask;
-  uint32_t unsafe = 0;
+  const uint32_t cand = in_list ? (uint32_t)T.unres[(cells >> (8 * j)) & 0xFFu] : 1u;
+  // the others among themselves
+  uint32_t cm_o = 0;
+  const uint32_t nn_fixed = nn_masks(T, g, eo, 0x3Fu & ~pj);
+  if (nn_fixed) {
+    PairGeom go = g;
+    go.near6 = g.near6 & ~pj;
+    cm_o = resolve(T, go, eo, nn_fixed, 0u);
+  }
+  unsigned long long bad = 0;
   {
     int p = 0;
 #pragma unroll
@@ -346,25 +373,27 @@ __device__ __forceinline__ uint32_t count_valid_moves(const SimTab& T, uint32_t 
       for (int k = i + 1; k < 4; ++k, ++p)
         if ((i == j || k == j) && ((g.near6 >> p) & 1u)) {
           // pair (i, k): j second -> row [d][eff_i]; j first -> by symmetry row [40 - d][eff_k]
+          const int o = (k == j) ? i : k;
           const uint32_t d = (k == j) ? geom_didx(g, p) : (uint32_t)(N_DELTA - 1) - geom_didx(g, p);
-          const uint32_t eother = (eo >> (4 * (k == j ? i : k))) & 0xFu;
-          unsafe |= (uint32_t)T.rowmask[d * N_EFF + eother] | (uint32_t)T.rowmask[d * N_EFF];
+          const unsigned long long on = *reinterpret_cast<const unsigned long long*>(T.rowmask4[d * N_EFF + ((eo >> (4 * o)) & 0xFu)]);
+          if (cm_o == 0) {
+            bad |= on;                                                  // nobody else ever crashes
+          } else {
+            const unsigned long long st = *reinterpret_cast<const unsigned long long*>(T.rowmask4[d * N_EFF]);
+            const uint32_t c = (cm_o >> o) & 0x1111u;                   // bit 4s: o in C_s
+            const uint32_t cs = c, cp = c << 4;                         // C_s / C_{s-1} (C_{-1} empty)
+            unsigned long long m_on = 0, m_st = 0;
+#pragma unroll
+            for (int ss = 0; ss < 4; ++ss) {
+              if (!((cp >> (4 * ss)) & 1u)) m_on |= 0xFFFFull << (16 * ss);
+              if ((cs >> (4 * ss)) & 1u) m_st |= 0xFFFFull << (16 * ss);
+            }
+            bad |= (on & m_on) | (st & m_st);
+          }
         }
   }
-  uint32_t count = (uint32_t)__popc(cand & ~unsafe);
-  uint32_t todo = cand & unsafe;
-  if (todo) {
-    const uint32_t nn_fixed = nn_masks(T, g, eo, 0x3Fu & ~pj);
-    do {
-      const uint32_t e = (uint32_t)__ffs(todo) - 1u;
-      todo &= todo - 1u;
-      const uint32_t effp = eo | (e << (4 * j));
-      const uint32_t NNw = nn_fixed | nn_masks(T, g, effp, pj);
-      if (NNw == 0) { ++count; continue; }
-      const uint32_t cm = resolve(T, g, effp, NNw, 1u << j);
-      if (((cm >> (12 + j)) & 1u) == 0) ++count;
-    } while (todo);
-  }
+  const uint32_t bad16 = (uint32_t)(bad | (bad >> 16) | (bad >> 32) | (bad >> 48)) & 0xFFFFu;
+  const uint32_t count = (uint32_t)__popc(cand & ~bad16);
   return in_list ? count : count * 9u;
 }
 

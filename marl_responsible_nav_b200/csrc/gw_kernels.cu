@@ -220,21 +220,21 @@ __device__ __forceinline__ void encode_specials(uint16_t* out, int cpo, int n, i
 // Per env: lanes 0..9 drop the pre-computed special cells into row A, one __syncwarp, the cells patched into row B
 // for the previous env are zeroed again (agents and apples only stand on active cells, whose template value is 0),
 // and row A leaves as 128-bit streaming stores: whole 128-byte lines, never a partial sector.  Rows alternate.
+// el0 / el_step / el_end: the envs of the tile this warp renders (big kernel: warp, +NWARPS, ...; small kernel: its own four).
 template <int THREADS, int TILE, int OBS>
-__device__ __forceinline__ void render_tile(Smem<TILE>& s, uint8_t* stage, const StepParams& p, long long tile_base,
-                                            int tile_envs) {
+__device__ __forceinline__ void render_obs(Smem<TILE>& s, uint8_t* stage, const StepParams& p, long long tile_base,
+                                           int el0, int el_step, int el_end) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int NWARPS = THREADS / 32;
   const int cpo = p.H * GW_W;
   const int V = p.nl * ((OBS == GW_OBS_F32) ? cpo / 4 : cpo / 8);
   if (p.io.obs != nullptr) {
     const int row_bytes = V * 16;
     uint8_t* const row0 = stage + warp * 2 * row_bytes;
-    uint4* dst = reinterpret_cast<uint4*>(p.io.obs) + (tile_base + warp) * (long long)V + lane;
-    const long long dst_step = (long long)NWARPS * V;
+    uint4* dst = reinterpret_cast<uint4*>(p.io.obs) + (tile_base + el0) * (long long)V + lane;
+    const long long dst_step = (long long)el_step * V;
     uint32_t prev_enc = 0xFFFFu;
     int cur = 0;
-    for (int el = warp; el < tile_envs; el += NWARPS, dst += dst_step) {
+    for (int el = el0; el < el_end; el += el_step, dst += dst_step) {
       if (s.rinfo[el] & R_SKIP) continue;                  // warp-uniform
       uint8_t* row = row0 + cur * row_bytes;
       uint8_t* other = row0 + (cur ^ 1) * row_bytes;
@@ -265,13 +265,20 @@ __device__ __forceinline__ void render_tile(Smem<TILE>& s, uint8_t* stage, const
     __syncwarp();
   }
   if (p.io.final_obs != nullptr) {                        // terminal observation of envs that were just re-spawned (rare)
-    for (int el = warp; el < tile_envs; el += NWARPS) {
+    for (int el = el0; el < el_end; el += el_step) {
       const uint32_t ri = s.rinfo[el];
       if ((ri & R_FINAL) && !(ri & R_SKIP))
         stage_and_store_env<OBS>(stage + warp * 2 * V * 16, p.io.final_obs, tile_base + el, p.H, p.n, p.nl, p.kind, s.cells_fin[el],
                                  (ri >> 4) & 3u, p.apple_cells, false, lane);
     }
   }
+}
+
+template <int THREADS, int TILE, int OBS>
+__device__ __forceinline__ void render_tile(Smem<TILE>& s, uint8_t* stage, const StepParams& p, long long tile_base,
+                                            int tile_envs) {
+  const int tid = threadIdx.x;
+  render_obs<THREADS, TILE, OBS>(s, stage, p, tile_base, tid >> 5, THREADS / 32, tile_envs);
   if (p.io.action_mask != nullptr) {
     __syncthreads();                                       // s.mask was filled by the owner threads
     const int bytes = tile_envs * p.nl * GW_N_ACTIONS;
@@ -304,15 +311,23 @@ __device__ __forceinline__ void stage_masks(Smem<TILE>& s, const StepParams& p, 
 // ------------------------------------------------------------------ spawn
 // setup_env, custom/ma_customenv.py:372-380: a sorted n-subset of the active cells (row-major order).
 // Replay mode reads the recorded cells; native mode draws them from Philox (uniform over subsets).
+__device__ __forceinline__ uint32_t spawn_choose(const StepParams& p, long long e, uint32_t tick);
+__device__ __forceinline__ uint32_t cells_from_chosen(const StepParams& p, const SmallTables& st, uint32_t chosen);
+
 __device__ __forceinline__ uint32_t spawn_cells(const StepParams& p, const SmallTables& st, long long e, uint32_t tick) {
-  uint32_t cells = 0;
   if (p.io.spawn != nullptr) {
+    uint32_t cells = 0;
     for (int i = 0; i < p.n; ++i) {
       const int r = p.io.spawn[(e * p.n + i) * 2 + 0], c = p.io.spawn[(e * p.n + i) * 2 + 1];
       cells |= (uint32_t)(((r & 15) << 4) | (c & 15)) << (8 * i);
     }
     return cells;
   }
+  return cells_from_chosen(p, st, spawn_choose(p, e, tick));
+}
+
+// the n sorted indices into the active-cell list (needs no table: the small-batch kernel draws them while the tables load)
+__device__ __forceinline__ uint32_t spawn_choose(const StepParams& p, long long e, uint32_t tick) {
   const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
   uint32_t w[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), tick, 0x100u};
   philox4x32(w, p.seed_lo, p.seed_hi);
@@ -329,6 +344,11 @@ __device__ __forceinline__ uint32_t spawn_cells(const StepParams& p, const Small
     const uint32_t lowmask = (pos == 0) ? 0u : (0xFFFFFFFFu >> (32 - 8 * pos));
     chosen = (chosen & lowmask) | (d << (8 * pos)) | ((chosen & ~lowmask) << 8);
   }
+  return chosen;
+}
+
+__device__ __forceinline__ uint32_t cells_from_chosen(const StepParams& p, const SmallTables& st, uint32_t chosen) {
+  uint32_t cells = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     if (i < p.n) cells |= (uint32_t)st.active_cell[(chosen >> (8 * i)) & 0xFFu] << (8 * i);
@@ -362,6 +382,82 @@ __device__ __forceinline__ void write_positions(int8_t* dst, long long e, int n,
       dst[(e * n + i) * 2 + 1] = (int8_t)(c & 15u);
     }
   }
+}
+
+// Reward / done block of one env step: custom/ma_customenv.py:258-302 (multi) and custom/customenv.py:126-158 (single).
+// caught0 / caught1: sub-steps learner k stood on its own apple (grid_world.py:531-540).
+struct RewardOut {
+  double reward[GW_MAX_LEARNERS];
+  uint32_t meta, apples_left, term_now, trunc_now, apples_rewarded, crash_count, shaped;
+};
+
+__device__ __forceinline__ RewardOut env_rewards(const StepParams& p, int nl, uint32_t meta, uint32_t cells_new, uint32_t crash,
+                                                 uint32_t caught0, uint32_t caught1) {
+  RewardOut o;
+  o.reward[0] = o.reward[1] = 0.0;
+  const uint32_t apples_before = meta & M_APPLES;
+  uint32_t apples_left = apples_before;
+  uint32_t term_now = 0, trunc_now = 0, apples_rewarded = 0, crash_count = 0, shaped = 0;
+  if (p.kind == GW_ENV_MULTI) {
+    uint32_t term = (meta >> M_TERM_SH) & 3u, trunc = (meta & M_TRUNC) ? 1u : 0u;
+    int ri[GW_MAX_LEARNERS] = {0, 0};
+#pragma unroll
+    for (int k = 0; k < GW_MAX_LEARNERS; ++k)                          // own apple only (:258-271)
+      if (k < nl && ((apples_left >> k) & 1u) && (k == 0 ? caught0 : caught1)) {
+        apples_left &= ~(1u << k);
+        ri[k] += 20;
+        ++apples_rewarded;
+      }
+    if (apples_rewarded && apples_left == 0) {                         // last apple: +20 to all, truncate (:272-275)
+#pragma unroll
+      for (int k = 0; k < GW_MAX_LEARNERS; ++k) if (k < nl) ri[k] += 20;
+      trunc = 1;
+    }
+    uint32_t pdv = 0, pd[2] = {0, 0};
+#pragma unroll
+    for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
+      if (k >= nl) continue;
+      if ((crash >> k) & 1u) {                                         // :281-285
+        ri[k] -= 10;
+        ++crash_count;
+        trunc = 1;
+        term |= 1u << k;
+      }
+      if ((apples_left >> k) & 1u) {                                   // :287-300
+        const uint32_t d = (uint32_t)manhattan((cells_new >> (8 * k)) & 0xFFu, (p.apple_cells >> (8 * k)) & 0xFFu);
+        const uint32_t prev_valid = (meta >> (M_PDV_SH + k)) & 1u;
+        const uint32_t prev = (meta >> (k == 0 ? M_PD0_SH : M_PD1_SH)) & 31u;
+        if (prev_valid && prev > d) { ri[k] += 1; shaped |= 1u << k; }
+        pdv |= 1u << k;
+        pd[k] = d;
+      }
+      o.reward[k] = (double)ri[k];
+    }
+    term_now = term;
+    trunc_now = trunc ? ((1u << nl) - 1u) : 0u;
+    const uint32_t steps = min(((meta >> M_STEPS_SH) & M_STEPS_MASK) + 1u, M_STEPS_MASK);
+    meta = apples_left | (term << M_TERM_SH) | (trunc ? M_TRUNC : 0u) | (pdv << M_PDV_SH) | (pd[0] << M_PD0_SH) |
+           (pd[1] << M_PD1_SH) | (steps << M_STEPS_SH);
+  } else {                                                             // customenv.py:126-158
+    double rew = 0.0;
+    const uint32_t apple = p.apple_cells & 0xFFu;
+    const uint32_t d = (uint32_t)manhattan(cells_new & 0xFFu, apple);
+    if (crash & 1u) { rew -= 10.0; term_now = 1; crash_count = 1; }
+    if ((apples_left & 1u) && caught0 == 1u) {                         // len(apples_caught) == 1 (:143)
+      apples_left &= ~1u;
+      rew += 20.0;
+      trunc_now = 1;
+      apples_rewarded = 1;
+    }
+    const uint32_t prev = (meta >> M_PD0_SH) & 31u;
+    if (d < prev) { rew += 0.1; shaped = 1; }                          // :157-158
+    o.reward[0] = rew;
+    const uint32_t steps = min(((meta >> M_STEPS_SH) & M_STEPS_MASK) + 1u, M_STEPS_MASK);
+    meta = apples_left | (1u << M_PDV_SH) | (d << M_PD0_SH) | (steps << M_STEPS_SH);
+  }
+  o.meta = meta; o.apples_left = apples_left; o.term_now = term_now; o.trunc_now = trunc_now;
+  o.apples_rewarded = apples_rewarded; o.crash_count = crash_count; o.shaped = shaped;
+  return o;
 }
 
 // ------------------------------------------------------------------ reset kernel
@@ -408,7 +504,7 @@ __device__ __forceinline__ void trace_stamp(const StepParams& p, int slot) {
   }
 }
 
-template <int THREADS, int TILE, int SPLIT_, bool FEAR, int OBS>
+template <int THREADS, int TILE, bool FEAR, int OBS>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
@@ -550,65 +646,12 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
       }
 
       trace_stamp(p, 11);
-      uint32_t apples_left = apples_before;
-      uint32_t term_now = 0, trunc_now = 0, apples_rewarded = 0, crash_count = 0, shaped = 0;
-      if (p.kind == GW_ENV_MULTI) {
-        uint32_t term = (meta >> M_TERM_SH) & 3u, trunc = (meta & M_TRUNC) ? 1u : 0u;
-        int ri[GW_MAX_LEARNERS] = {0, 0};
-#pragma unroll
-        for (int k = 0; k < GW_MAX_LEARNERS; ++k)                          // own apple only (:258-271)
-          if (k < nl && ((apples_left >> k) & 1u) && ((r.caught >> (3 * (k * 2 + k))) & 7u)) {
-            apples_left &= ~(1u << k);
-            ri[k] += 20;
-            ++apples_rewarded;
-          }
-        if (apples_rewarded && apples_left == 0) {                         // last apple: +20 to all, truncate (:272-275)
-#pragma unroll
-          for (int k = 0; k < GW_MAX_LEARNERS; ++k) if (k < nl) ri[k] += 20;
-          trunc = 1;
-        }
-        uint32_t pdv = 0, pd[2] = {0, 0};
-#pragma unroll
-        for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
-          if (k >= nl) continue;
-          if ((r.crash >> k) & 1u) {                                       // :281-285
-            ri[k] -= 10;
-            ++crash_count;
-            trunc = 1;
-            term |= 1u << k;
-          }
-          if ((apples_left >> k) & 1u) {                                   // :287-300
-            const uint32_t d = (uint32_t)manhattan((cells_new >> (8 * k)) & 0xFFu, (p.apple_cells >> (8 * k)) & 0xFFu);
-            const uint32_t prev_valid = (meta >> (M_PDV_SH + k)) & 1u;
-            const uint32_t prev = (meta >> (k == 0 ? M_PD0_SH : M_PD1_SH)) & 31u;
-            if (prev_valid && prev > d) { ri[k] += 1; shaped |= 1u << k; }
-            pdv |= 1u << k;
-            pd[k] = d;
-          }
-          reward[k] = (double)ri[k];
-        }
-        term_now = term;
-        trunc_now = trunc ? ((1u << nl) - 1u) : 0u;
-        const uint32_t steps = min(((meta >> M_STEPS_SH) & M_STEPS_MASK) + 1u, M_STEPS_MASK);
-        meta = apples_left | (term << M_TERM_SH) | (trunc ? M_TRUNC : 0u) | (pdv << M_PDV_SH) | (pd[0] << M_PD0_SH) |
-               (pd[1] << M_PD1_SH) | (steps << M_STEPS_SH);
-      } else {                                                             // customenv.py:126-158
-        double rew = 0.0;
-        const uint32_t apple = p.apple_cells & 0xFFu;
-        const uint32_t d = (uint32_t)manhattan(cells_new & 0xFFu, apple);
-        if (r.crash & 1u) { rew -= 10.0; term_now = 1; crash_count = 1; }
-        if ((apples_left & 1u) && (r.caught & 7u) == 1u) {                 // len(apples_caught) == 1 (:143)
-          apples_left &= ~1u;
-          rew += 20.0;
-          trunc_now = 1;
-          apples_rewarded = 1;
-        }
-        const uint32_t prev = (meta >> M_PD0_SH) & 31u;
-        if (d < prev) { rew += 0.1; shaped = 1; }                          // :157-158
-        reward[0] = rew;
-        const uint32_t steps = min(((meta >> M_STEPS_SH) & M_STEPS_MASK) + 1u, M_STEPS_MASK);
-        meta = apples_left | (1u << M_PDV_SH) | (d << M_PD0_SH) | (steps << M_STEPS_SH);
-      }
+      const RewardOut ro = env_rewards(p, nl, meta, cells_new, r.crash, r.caught & 7u, (r.caught >> 9) & 7u);
+      reward[0] = ro.reward[0];
+      reward[1] = ro.reward[1];
+      meta = ro.meta;
+      const uint32_t apples_left = ro.apples_left, term_now = ro.term_now, trunc_now = ro.trunc_now,
+                     apples_rewarded = ro.apples_rewarded, crash_count = ro.crash_count, shaped = ro.shaped;
       steps_now = (meta >> M_STEPS_SH) & M_STEPS_MASK;
       const bool episode_over = (p.kind == GW_ENV_MULTI) ? (trunc_now != 0) : ((term_now | trunc_now) != 0);
       const bool ended = episode_over || (p.max_steps > 0 && (int)steps_now >= p.max_steps);
@@ -663,15 +706,11 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
     if (FEAR) {
       __syncthreads();
       trace_stamp(p, 3);
-      // One thread per (task, actor variant, 9/SPLIT actions of the affected agent).  SPLIT = 1 shares the pair masks that
-      // do not involve the affected agent across its nine actions (throughput: many resident CTAs); SPLIT = 9 gives one
-      // thread per counterfactual (latency: few envs per SM).  The host picks by how many tiles each SM gets.
-      constexpr uint32_t SPLIT = (uint32_t)SPLIT_;
-      const uint32_t n_work = s.qn * 2u * SPLIT;
+      // One thread per (task, actor variant): the nine counterfactual actions of the affected agent are counted at once.
+      const uint32_t n_work = s.qn * 2u;
       if (tid == 0 && s.qn) atomicAdd(&p.stats[(int)(tile & (STAT_SLOTS - 1)) * 8 + ST_TASKS], (unsigned long long)s.qn);
       for (uint32_t w = tid; w < n_work; w += THREADS) {
-        const uint32_t ht = w / SPLIT, a0 = w - ht * SPLIT;
-        const uint32_t tk = s.queue[ht >> 1], v = ht & 1u;
+        const uint32_t tk = s.queue[w >> 1], v = w & 1u;
         const uint32_t el = tk & 0xFFu, x = (tk >> 8) & 1u, j = (tk >> 9) & 3u, jc = (tk >> 11) & 1u;
         const uint32_t effw = s.effs[el];
         const uint32_t close = (s.close[el] >> (4 * x)) & 0xFu;
@@ -683,9 +722,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
         g.didx_lo = s.geom_lo[el];
         g.didx_hi = s.geom_hi[el] & 0xFFFFu;
         g.near6 = s.geom_hi[el] >> 16;
-        constexpr uint32_t PER = 9u / SPLIT;
-        const uint32_t cnt = count_valid_moves(s.sim, s.cells_old[el], eo, g, (int)j, jc != 0,
-                                               (SPLIT == 1u) ? 0x1FFu : (((1u << PER) - 1u) << (a0 * PER)));
+        const uint32_t cnt = count_valid_moves(s.sim, s.cells_old[el], eo, g, (int)j, jc != 0);
         const uint32_t jslot = j - (j > x ? 1u : 0u);
         if (cnt) atomicAdd(&s.cnt[el * 2 + x], cnt << (4 * (jslot * 2 + v)));
       }
@@ -761,6 +798,362 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
     trace_stamp(p, 7);
   }
   if (tables_pending) cp_async_wait_all();                 // a CTA without tiles must not exit with copies in flight
+}
+
+// ------------------------------------------------------------------ step kernel for small batches (latency regime)
+// One env per 8 lanes, 32 envs per CTA.  With a few thousand envs the thread-per-env kernel above leaves one warp per
+// SM walking a ~1500-instruction dependent chain; here the per-agent and per-pair work of an env runs on different
+// lanes (lanes 0-3: the agents, lanes 4-5: the learners' Move-de-Rigueur trajectories, lanes 0-5: the six pairs) and
+// the words the fix-point needs are gathered with redux.sync over the 8-lane group.  The env's FeAR tasks are counted
+// by the same 8 lanes (one (task, variant, three actions) item each), so there is no CTA-wide queue and no barrier
+// after the table copy: every warp steps and renders its own four envs and leaves.
+__device__ __forceinline__ uint32_t special_entry(int q, int cpo, int n, int nl, int kind, uint32_t cells, uint32_t apples_left,
+                                                  uint32_t apple_cells, bool fresh) {
+  const int k = q >= (GW_MAX_AGENTS + 1) ? 1 : 0, i = q - k * (GW_MAX_AGENTS + 1);
+  const bool apple_on = (k < nl) && ((kind == GW_ENV_MULTI) ? ((apples_left >> k) & 1u) : (apples_left & 1u));
+  const uint32_t apple = (kind == GW_ENV_MULTI) ? (apple_cells >> (8 * k)) & 0xFFu : apple_cells & 0xFFu;
+  if (i < GW_MAX_AGENTS) {
+    if (k >= nl || i >= n) return 0xFFFFu;
+    const uint32_t c = (cells >> (8 * i)) & 0xFFu;
+    return (uint32_t)(k * cpo + (int)c) | ((uint32_t)(2.0f * special_value(kind, fresh, i, k, apple_on && c == apple)) << 9);
+  }
+  bool covered = false;
+#pragma unroll
+  for (int a = 0; a < GW_MAX_AGENTS; ++a) covered |= (a < n) && ((cells >> (8 * a)) & 0xFFu) == apple;
+  return (apple_on && !covered) ? ((uint32_t)(k * cpo + (int)apple) | (18u << 9)) : 0xFFFFu;
+}
+
+// OR of the BITS-wide values held by lanes base .. base+N-1, value i shifted to bit BITS*i.  N independent shuffles: on a
+// latency-bound warp they pipeline, unlike a butterfly (and redux.sync takes its slow path for a part-warp mask).
+template <int N, int BITS>
+__device__ __forceinline__ uint32_t gather_lanes(unsigned gmask, uint32_t v, int base) {
+  uint32_t w = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) w |= __shfl_sync(gmask, v, base + i) << (BITS * i);
+  return w;
+}
+
+template <bool FEAR, int OBS>
+__global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
+  constexpr int THREADS = 256, TILE = 32;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
+  uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
+  trace_stamp(p, 0);
+  load_tables<THREADS, TILE, OBS>(s, stage, p.tables, p.H, p.nl, true);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = tid & 7, gsh = lane & 24;
+  constexpr unsigned FULL = 0xFFFFFFFFu;     // every shuffle / ballot below is executed by the whole converged warp: a
+                                             // part-warp mask would send each of them through the compiler's slow path
+  const int n = p.n, nl = p.nl;
+  const long long n_tiles = (p.E + TILE - 1) / TILE;
+  bool tables_pending = true;
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long tile_base = tile * TILE;
+    const int tile_envs = (int)min((long long)TILE, p.E - tile_base);
+    const int el = tid >> 3;
+    const long long e = tile_base + el;
+    const bool own = el < tile_envs;
+
+    // ================================================================= loads and RNG (no table needed)
+    uint4 st = make_uint4(0, 0, 0, 0);
+    uint32_t la = 0, npc_a = 0, chosen = 0;
+    uint32_t rw[4] = {0, 0, 0, 0}, rw2[4] = {0, 0, 0, 0};
+    if (own) {
+      st = p.state[e];
+#pragma unroll
+      for (int k = 0; k < GW_MAX_LEARNERS; ++k)
+        if (k < nl) la |= (uint32_t)min(max((int)p.io.learner_actions[e * nl + k], 0), 8) << (4 * k);
+      if (p.io.npc_actions != nullptr) {
+        if (r < 4 && r >= nl && r < n) npc_a = (uint32_t)min(max((int)p.io.npc_actions[e * n + r], 0), 8);
+      } else {
+        const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
+        rw[0] = (uint32_t)gid; rw[1] = (uint32_t)(gid >> 32); rw[2] = st.z; rw[3] = 0u;
+        philox4x32(rw, p.seed_lo, p.seed_hi);
+        if (n - nl > 2) {
+          rw2[0] = (uint32_t)gid; rw2[1] = (uint32_t)(gid >> 32); rw2[2] = st.z; rw2[3] = 1u;
+          philox4x32(rw2, p.seed_lo, p.seed_hi);
+        }
+      }
+      // the re-spawn draw of an env that ends in this step, drawn now: it hides behind the table copy
+      if (p.auto_reset && p.io.spawn == nullptr) chosen = spawn_choose(p, e, st.z);
+    }
+    if (tables_pending) {
+      cp_async_wait_all();
+      __syncthreads();
+      fill_stage_rows<THREADS, TILE, OBS>(s, stage, p.H, p.nl);
+      __syncthreads();
+      tables_pending = false;
+    }
+    trace_stamp(p, 1);
+
+    uint32_t v_end = 0, v_len = 0, v_cr = 0, v_ap = 0, v_tasks = 0, v_nz = 0;     // statistics: lane r == 0 of every group
+    int v_ret = 0;
+    double v_fear = 0.0;
+    {                                        // groups without an env (tile tail) run along on zeros; their stores are masked
+      const uint32_t cells = st.x, tick = st.z;
+      uint32_t meta = st.y;
+      // ---- agent role (setup_step :432-452, DefineActions, grid_world.py:481-518)
+      const int ai = r & 3;
+      const uint32_t c_r = (cells >> (8 * ai)) & 0xFFu;
+      const uint32_t mdr_r = (ai < n) ? (uint32_t)s.small.mdr_map[c_r] : 0u;                // :445-447
+      uint32_t a_r = 0;
+      if (r >= 4) {
+        if (r < 4 + nl) a_r = mdr_r;                                   // lanes 4, 5: learner r-4 plays its MdR
+      } else if (ai < nl) {
+        a_r = (la >> (4 * ai)) & 0xFu;                                 // :239-242
+      } else if (ai < n) {
+        if (p.io.npc_actions != nullptr) {
+          a_r = npc_a;
+        } else {
+          const int m = ai - nl;
+          const uint32_t wa = m == 0 ? rw[0] : (m == 1 ? rw[2] : rw2[0]);
+          const uint32_t wb = m == 0 ? rw[1] : (m == 1 ? rw[3] : rw2[1]);
+          const int pert = wa < p.perturb_thr ? 1 : 0;                 // random.random() < 0.25 (:441)
+          const uint4* thr4 = reinterpret_cast<const uint4*>(s.small.policy_thr[s.small.policy_map[c_r]][pert]);
+          const uint4 t0 = thr4[0], t1 = thr4[1];
+          const uint32_t u = wb >> 1;
+          a_r = (u >= t0.x) + (u >= t0.y) + (u >= t0.z) + (u >= t0.w) + (u >= t1.x) + (u >= t1.y) + (u >= t1.z) +
+                (u >= t1.w);                                           // np.random.choice(9, p) (custom_agent.py:31)
+        }
+      }
+      const Traj t = make_traj(s.sim.next, c_r, a_r);
+      // bits 0-15: the trajectories played, 16-23: the learners' MdR trajectories
+      const uint32_t effw = gather_lanes<6, 4>(FULL, t.eff, gsh);
+      // learners whose action differs from their MdR (lanes 4, 5 hold the MdR as their action)
+      const uint32_t neqb = (__ballot_sync(FULL, r >= 4 && r < 4 + nl && a_r != ((la >> (4 * (r - 4))) & 0xFu)) >> (gsh + 4)) & 3u;
+
+      trace_stamp(p, 8);
+      // ---- pair role: lane r < 6 owns pair (01,02,03,12,13,23)[r]
+      const int pi = (0x211000 >> (4 * r)) & 0xF, pj = (0x332321 >> (4 * r)) & 0xF;
+      bool near = false;
+      uint32_t didx = 0;
+      if (r < 6 && pj < n) {
+        const uint32_t a = (cells >> (8 * pi)) & 0xFFu, b = (cells >> (8 * pj)) & 0xFFu;
+        const int dr = (int)(b >> 4) - (int)(a >> 4), dc = (int)(b & 15) - (int)(a & 15);
+        if (abs(dr) + abs(dc) <= 4) {
+          near = true;
+          didx = s.sim.diamond[(dr + 4) * 9 + (dc + 4)];
+        }
+      }
+      const uint32_t near6 = (__ballot_sync(FULL, near) >> gsh) & 0x3Fu;
+      uint32_t cm = 0;
+      {
+        uint32_t nn = 0, nr = 0, rn = 0;
+        if (near && n >= 2) {
+          const uint32_t base = didx * (N_EFF * N_EFF), ei = (effw >> (4 * pi)) & 0xFu, ej = (effw >> (4 * pj)) & 0xFu;
+          nn = s.sim.lut[base + ei * N_EFF + ej];
+          nr = s.sim.lut[base + ei * N_EFF];
+          rn = s.sim.lut[base + ej];
+        }
+        if (__any_sync(FULL, nn != 0u)) {                              // (warp-uniform) somebody collides while everyone is on course
+          const uint32_t NNw = gather_lanes<6, 4>(FULL, nn, gsh), NRw = gather_lanes<6, 4>(FULL, nr, gsh),
+                         RNw = gather_lanes<6, 4>(FULL, rn, gsh);
+          if (NNw) cm = fixpoint_words(NNw, NRw, RNw);
+        }
+      }
+      const uint32_t crash = (cm >> 12) & 0xFu;
+      trace_stamp(p, 9);
+
+      // ---- agent role again: final cell, restricted flag, own apple (grid_world.py:531-563)
+      uint32_t fin = 0, caught_r = 0;
+      bool restr_r = false;
+      if (r < 4) {
+        fin = (n >= 2) ? cell_at(c_r, t, (crash >> r) & 1u, 3) : c_r;
+        restr_r = ai < n && (t.r1 | (t.r2 & ~(cm >> r) & 1u)) != 0;
+        if (r < nl && ((meta >> r) & 1u)) {
+          const uint32_t apple = (p.apple_cells >> (8 * r)) & 0xFFu;
+#pragma unroll
+          for (int ss = 0; ss < 4; ++ss) {
+            const uint32_t cur = (n >= 2) ? cell_at(c_r, t, (cm >> (4 * ss + r)) & 1u, ss) : c_r;
+            caught_r += (cur == apple) ? 1u : 0u;
+          }
+        }
+      }
+      const uint32_t cells_new = gather_lanes<4, 8>(FULL, fin, gsh);
+      const uint32_t restr = (__ballot_sync(FULL, restr_r) >> gsh) & 0xFu;
+      // own-apple catches: only "none / exactly one / more" matters (ma_customenv.py:264, customenv.py:143)
+      const uint32_t c_any = (__ballot_sync(FULL, caught_r > 0u) >> gsh) & 3u, c_one = (__ballot_sync(FULL, caught_r == 1u) >> gsh) & 3u;
+      const uint32_t caught0 = (c_one & 1u) ? 1u : ((c_any & 1u) ? 2u : 0u), caught1 = (c_one & 2u) ? 1u : ((c_any & 2u) ? 2u : 0u);
+
+      trace_stamp(p, 10);
+      // ---- rewards and flags (the same for every lane of the group)
+      const RewardOut ro = env_rewards(p, nl, meta, cells_new, crash, caught0, caught1);
+      meta = ro.meta;
+      const uint32_t steps_now = (meta >> M_STEPS_SH) & M_STEPS_MASK;
+      const bool episode_over = (p.kind == GW_ENV_MULTI) ? (ro.trunc_now != 0) : ((ro.term_now | ro.trunc_now) != 0);
+      const bool ended = episode_over || (p.max_steps > 0 && (int)steps_now >= p.max_steps);
+      int ret0 = (int)(short)(st.w & 0xFFFFu), ret1 = (int)(short)(st.w >> 16);
+      const double unit = (p.kind == GW_ENV_MULTI) ? 1.0 : 10.0;
+      ret0 += (int)lrint(ro.reward[0] * unit);
+      ret1 += (int)lrint(ro.reward[1] * unit);
+      uint32_t cells_r = cells_new, apples_r = ro.apples_left, rflags = 0;
+      uint4 st_out = make_uint4(cells_new, meta, tick + 1, ((uint32_t)ret0 & 0xFFFFu) | ((uint32_t)ret1 << 16));
+      if (ended && p.auto_reset && own) {
+        cells_r = (p.io.spawn != nullptr) ? spawn_cells(p, s.small, e, tick) : cells_from_chosen(p, s.small, chosen);
+        const uint32_t meta_sp = fresh_meta(p, cells_r);
+        apples_r = meta_sp & M_APPLES;
+        rflags = R_FRESH | R_FINAL | (ro.apples_left << 4);
+        st_out = make_uint4(cells_r, meta_sp, tick + 1, 0u);
+      }
+
+      trace_stamp(p, 11);
+      // ---- outputs: one lane per array
+      const double my_reward = (r == 0) ? ro.reward[0] : ro.reward[1];
+      if (r == 0 && own) {
+        p.state[e] = st_out;
+        s.rinfo[el] = apples_r | rflags;
+        s.cells_fin[el] = cells_new;
+        v_end = ended ? 1u : 0u; v_len = ended ? steps_now : 0u; v_cr = ro.crash_count; v_ap = ro.apples_rewarded;
+        v_ret = ended ? (ret0 + ret1) : 0;
+      }
+      if (r < nl && own && p.io.reward) p.io.reward[e * nl + r] = (float)my_reward;
+      if (r == 1 && own) write_positions(p.io.positions, e, n, cells_new);
+      if (r == 2 && own && p.io.info)
+        p.io.info[e] = (crash & 15u) | ((restr & 15u) << 4) | (ro.crash_count << 8) | (ro.apples_rewarded << 10) |
+                       ((ended ? 1u : 0u) << 12) | (ro.shaped << 14);
+      if (r == 3 && own && p.io.ended) p.io.ended[e] = ended ? 1 : 0;
+      if (r >= 4 && r < 4 + nl && own) {
+        if (p.io.terminated) p.io.terminated[e * nl + (r - 4)] = (uint8_t)((ro.term_now >> (r - 4)) & 1u);
+        if (p.io.truncated) p.io.truncated[e * nl + (r - 4)] = (uint8_t)((ro.trunc_now >> (r - 4)) & 1u);
+      }
+      if (r == 6 && own && p.io.obs_code)
+        p.io.obs_code[e] = (unsigned long long)cells_r | ((unsigned long long)apples_r << 32) |
+                           ((rflags & R_FRESH) ? (1ull << 34) : 0ull);
+
+      trace_stamp(p, 12);
+      // ---- observation specials and action masks of the (new) positions
+      {
+        const int cpo = p.H * GW_W;
+        const bool fresh = (rflags & R_FRESH) != 0;
+        s.spec[el][r] = (uint16_t)special_entry(r, cpo, n, nl, p.kind, cells_r, apples_r, p.apple_cells, fresh);
+        if (r < N_SPEC - 8) s.spec[el][r + 8] = (uint16_t)special_entry(r + 8, cpo, n, nl, p.kind, cells_r, apples_r, p.apple_cells, fresh);
+      }
+      if (p.io.action_mask != nullptr) {                               // get_action_mask :467-506: lane r tests action r + 1
+        const int a = r + 1, len = a >= 5 ? 2 : 1, d = (a - 1) & 3;
+        bool ok[GW_MAX_LEARNERS] = {false, false};
+#pragma unroll
+        for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
+          if (k >= nl) break;
+          const uint32_t pc = (cells_r >> (8 * k)) & 0xFFu;
+          const int tr = (int)(pc >> 4) + (d == 0 ? -len : d == 1 ? len : 0), tc = (int)(pc & 15) + (d == 2 ? -len : d == 3 ? len : 0);
+          ok[k] = (unsigned)tr < (unsigned)p.H && (unsigned)tc < (unsigned)GW_W && ((s.rows[tr] >> tc) & 1);
+        }
+        const uint32_t m0 = 1u | (((__ballot_sync(FULL, ok[0]) >> gsh) & 0xFFu) << 1);
+        const uint32_t m1 = 1u | (((__ballot_sync(FULL, ok[1]) >> gsh) & 0xFFu) << 1);
+        const uint32_t bits = m0 | (m1 << GW_N_ACTIONS);
+        int8_t* dst = p.io.action_mask + e * (long long)(nl * GW_N_ACTIONS);
+        if (own)
+          for (int b = r; b < nl * GW_N_ACTIONS; b += 8) dst[b] = (int8_t)((bits >> b) & 1u);
+      }
+
+      trace_stamp(p, 13);
+      // ---- FeAR (ma_customenv.py:245-252, Responsibility.py:135-210): the env's own 8 lanes count its tasks
+      double fear0 = 0.0, fear1 = 0.0;
+      if (FEAR) {
+        const int xx = r >> 2, kk = r & 3;                             // close_agents :456-464 for both actors at once
+        const bool cl = xx < nl && kk < n &&
+                        (kk == xx || manhattan((cells >> (8 * xx)) & 0xFFu, (cells >> (8 * kk)) & 0xFFu) <= p.fear_radius);
+        const uint32_t closeb = (__ballot_sync(FULL, cl) >> gsh) & 0xFFu;
+        uint32_t tm = 0;                                               // bit 4x + j: task (actor x, affected j)
+#pragma unroll
+        for (int x = 0; x < GW_MAX_LEARNERS; ++x) {
+          if (x >= nl) break;
+          if (((neqb >> x) & 1u) == 0) continue;                                            // action == MdR: Resp = 0 exactly
+          const uint32_t js = reach_mask(s.sim, near6, x) & ~(1u << x) & ((1u << n) - 1u);
+          if (js == 0) continue;
+          if (((effw >> (16 + 4 * x)) & 0xFu) == ((effw >> (4 * x)) & 0xFu)) continue;      // same trajectory: counts equal
+          tm |= js << (4 * x);
+        }
+        if (!own) tm = 0;
+        if (__any_sync(FULL, tm != 0u)) {                              // warp-uniform; groups without a task idle through it
+          PairGeom g;
+          g.near6 = near6;
+          g.didx_lo = gather_lanes<4, 8>(FULL, didx, gsh);
+          g.didx_hi = gather_lanes<2, 8>(FULL, didx, gsh + 4);
+          const int n_items = __popc(tm) * 2;                          // (task, variant): all nine actions are counted at once
+          uint32_t cw0 = 0, cw1 = 0;
+          for (int it = r; it < n_items; it += 8) {                    // no warp-level primitive inside: trip counts may differ
+            const int tk = it >> 1;
+            const uint32_t v = (uint32_t)it & 1u;
+            uint32_t mm = tm;
+            for (int q = 0; q < tk; ++q) mm &= mm - 1u;
+            const uint32_t bit = (uint32_t)__ffs(mm) - 1u, x = bit >> 2, j = bit & 3u;
+            const uint32_t close = (closeb >> (4 * x)) & 0xFu;
+            const uint32_t keep = ((close & 1u) ? 0xFu : 0u) | ((close & 2u) ? 0xF0u : 0u) | ((close & 4u) ? 0xF00u : 0u) |
+                                  ((close & 8u) ? 0xF000u : 0u);
+            uint32_t eo = effw & keep;                                 // agents outside the close list Stay (defaultAction='stay')
+            if (v == 0) eo = (eo & ~(0xFu << (4 * x))) | (((effw >> (16 + 4 * x)) & 0xFu) << (4 * x));   // actor plays its MdR (:169-172)
+            const uint32_t cnt = count_valid_moves(s.sim, cells, eo, g, (int)j, ((close >> j) & 1u) != 0);
+            const uint32_t jslot = j - (j > x ? 1u : 0u);
+            const uint32_t field = cnt << (4 * (jslot * 2 + v));
+            if (x == 0) cw0 += field; else cw1 += field;
+          }
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {                            // 4-bit fields, at most 9 each: no carry
+            cw0 += __shfl_xor_sync(FULL, cw0, o);
+            cw1 += __shfl_xor_sync(FULL, cw1, o);
+          }
+#pragma unroll
+          for (int x = 0; x < GW_MAX_LEARNERS; ++x) {
+            const uint32_t tb = (tm >> (4 * x)) & 0xFu;
+            if (tb == 0) continue;
+            const uint32_t c = x == 0 ? cw0 : cw1;
+            double rs[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int js = 0; js < 3; ++js) {
+              const int j = js + (js >= x ? 1 : 0);
+              if ((tb >> j) & 1u) rs[js] = s.small.resp_lut[(c >> (8 * js)) & 0xFu][(c >> (8 * js + 4)) & 0xFu];
+            }
+            const double f = fear_sum3(n, rs[0], rs[1], rs[2]);
+            if (x == 0) fear0 = f; else fear1 = f;
+          }
+          if (r == 0) { v_tasks = (uint32_t)__popc(tm); v_nz = (fear0 != 0.0) + (fear1 != 0.0); v_fear = fear0 + fear1; }
+        }
+      }
+      if (r < nl && own) {
+        const double f = (r == 0) ? fear0 : fear1;
+        if (p.io.fear) p.io.fear[e * nl + r] = f;
+        if (p.io.shaped_reward) p.io.shaped_reward[e * nl + r] = (float)(p.fear_weight * f + my_reward);   // maddpg/agent.py:130
+      }
+    }
+    trace_stamp(p, 2);
+
+    // ================================================================= observations of the warp's own four envs
+    __syncwarp();
+    if (tile + gridDim.x >= n_tiles) asm volatile("griddepcontrol.launch_dependents;");
+    render_obs<THREADS, TILE, OBS>(s, stage, p, tile_base, warp * 4, 1, min(tile_envs, warp * 4 + 4));
+    trace_stamp(p, 6);
+
+    // ================================================================= statistics (most warps contribute nothing)
+    {
+      const unsigned any = __ballot_sync(0xFFFFFFFFu, (v_end | v_cr | v_ap | v_tasks | v_nz) != 0u);
+      if (any) {
+        const double unit = (p.kind == GW_ENV_MULTI) ? 1.0 : 10.0;
+        const int slot = (int)(((tile_base >> 5) * 8 + warp) & (STAT_SLOTS - 1));
+        const unsigned w_end = __reduce_add_sync(0xFFFFFFFFu, v_end), w_len = __reduce_add_sync(0xFFFFFFFFu, v_len);
+        const unsigned w_cr = __reduce_add_sync(0xFFFFFFFFu, v_cr), w_ap = __reduce_add_sync(0xFFFFFFFFu, v_ap);
+        const unsigned w_nz = __reduce_add_sync(0xFFFFFFFFu, v_nz), w_tk = __reduce_add_sync(0xFFFFFFFFu, v_tasks);
+        const int w_ret = __reduce_add_sync(0xFFFFFFFFu, v_ret);
+        if (lane == 0) {
+          if (w_end) {
+            atomicAdd(&p.stats[slot * 8 + ST_EPISODES], (unsigned long long)w_end);
+            atomicAdd(&p.stats[slot * 8 + ST_LEN], (unsigned long long)w_len);
+            atomicAdd(&p.stats[slot * 8 + ST_RETURN_MILLI], (unsigned long long)(long long)llrint(w_ret * (1000.0 / unit)));
+          }
+          if (w_cr) atomicAdd(&p.stats[slot * 8 + ST_CRASH], (unsigned long long)w_cr);
+          if (w_ap) atomicAdd(&p.stats[slot * 8 + ST_APPLES], (unsigned long long)w_ap);
+          if (w_nz) atomicAdd(&p.stats[slot * 8 + ST_FEAR_NZ], (unsigned long long)w_nz);
+          if (w_tk) atomicAdd(&p.stats[slot * 8 + ST_TASKS], (unsigned long long)w_tk);
+        }
+        if (v_nz) atomicAdd(reinterpret_cast<double*>(&p.stats[slot * 8 + ST_FEAR_BITS]), v_fear);
+      }
+    }
+    __syncwarp();                                                      // s.spec / s.rinfo of this warp are rewritten by the next tile
+    trace_stamp(p, 7);
+  }
+  if (tables_pending) cp_async_wait_all();                             // a CTA without tiles must not exit with copies in flight
 }
 
 static inline size_t stage_row_bytes(const gw_config& c) {
@@ -1145,12 +1538,12 @@ static bool build_sim_tables(const gw_config* cfg, gw::SimTab* T) {
   const int EE = gw::N_EFF * gw::N_EFF;
   for (int d = 0; d < gw::N_DELTA; ++d)
     for (int a = 0; a < gw::N_EFF; ++a) {
-      uint16_t m = 0;
+      for (int ss = 0; ss < 4; ++ss) T->rowmask4[d * gw::N_EFF + a][ss] = 0;
       for (int b = 0; b < gw::N_EFF; ++b) {
         if (T->lut[d * EE + a * gw::N_EFF + b] != T->lut[(gw::N_DELTA - 1 - d) * EE + b * gw::N_EFF + a]) return false;
-        if (T->lut[d * EE + a * gw::N_EFF + b]) m |= (uint16_t)(1u << b);
+        for (int ss = 0; ss < 4; ++ss)
+          if ((T->lut[d * EE + a * gw::N_EFF + b] >> ss) & 1) T->rowmask4[d * gw::N_EFF + a][ss] |= (uint16_t)(1u << b);
       }
-      T->rowmask[d * gw::N_EFF + a] = m;
     }
   for (int cell = 0; cell < GW_MAX_H * GW_W; ++cell) {     // actions that are not restricted (grid_world.py:481-518)
     uint16_t m = 1;
@@ -1292,23 +1685,13 @@ static int check_io(gw_handle* h, const gw_io* io, bool step) {
 
 // Launch shape.  Small batches are latency-bound: 32-env tiles put work on every SM (E = 4096 -> 128 CTAs) and every
 // counterfactual gets its own thread.  Large batches are throughput-bound: 256-env tiles amortise the per-CTA table
-// load and a thread runs the nine counterfactuals of an action list.  GW_TILE=32|256 and GW_SPLIT=1|3|9 override.
+// load.  GW_TILE=32|256 overrides.
 static int pick_tile(long long E) {
   if (const char* s = std::getenv("GW_TILE")) {
     const int v = std::atoi(s);
     if (v == 32 || v == 256) return v;
   }
   return E <= 32768 ? 32 : 256;
-}
-
-static int pick_split(long long n_tiles, int sm_count, int tile) {
-  if (const char* s = std::getenv("GW_SPLIT")) {
-    const int v = std::atoi(s);
-    if (v == 1 || v == 3 || v == 9) return v;
-  }
-  if (tile == 32) return 9;
-  const long long per_sm = (n_tiles + sm_count - 1) / sm_count;
-  return per_sm <= 2 ? 9 : (per_sm <= 8 ? 3 : 1);
 }
 
 template <typename K>
@@ -1338,16 +1721,28 @@ static bool use_pdl() {
   return v;
 }
 
-template <int THREADS, int TILE, int SPLIT>
+template <int THREADS, int TILE>
 static void launch_step_t(const gw_config& c, const gw::StepParams& p, unsigned blocks, cudaStream_t s) {
   const bool f32 = c.obs_dtype == GW_OBS_F32;
   const size_t smem = gw::smem_fixed_bytes<TILE>() + (size_t)(THREADS / 32) * 2 * gw::stage_row_bytes(c);
   if (c.fear) {
-    if (f32) launch_k(gw::gw_step_kernel<THREADS, TILE, SPLIT, true, GW_OBS_F32>, p, blocks, THREADS, smem, s, use_pdl());
-    else launch_k(gw::gw_step_kernel<THREADS, TILE, SPLIT, true, GW_OBS_BF16>, p, blocks, THREADS, smem, s, use_pdl());
+    if (f32) launch_k(gw::gw_step_kernel<THREADS, TILE, true, GW_OBS_F32>, p, blocks, THREADS, smem, s, use_pdl());
+    else launch_k(gw::gw_step_kernel<THREADS, TILE, true, GW_OBS_BF16>, p, blocks, THREADS, smem, s, use_pdl());
   } else {
-    if (f32) launch_k(gw::gw_step_kernel<THREADS, TILE, 1, false, GW_OBS_F32>, p, blocks, THREADS, smem, s, use_pdl());
-    else launch_k(gw::gw_step_kernel<THREADS, TILE, 1, false, GW_OBS_BF16>, p, blocks, THREADS, smem, s, use_pdl());
+    if (f32) launch_k(gw::gw_step_kernel<THREADS, TILE, false, GW_OBS_F32>, p, blocks, THREADS, smem, s, use_pdl());
+    else launch_k(gw::gw_step_kernel<THREADS, TILE, false, GW_OBS_BF16>, p, blocks, THREADS, smem, s, use_pdl());
+  }
+}
+
+static void launch_step_small(const gw_config& c, const gw::StepParams& p, unsigned blocks, cudaStream_t s) {
+  const bool f32 = c.obs_dtype == GW_OBS_F32;
+  const size_t smem = gw::smem_fixed_bytes<32>() + (size_t)8 * 2 * gw::stage_row_bytes(c);
+  if (c.fear) {
+    if (f32) launch_k(gw::gw_step_small_kernel<true, GW_OBS_F32>, p, blocks, 256, smem, s, use_pdl());
+    else launch_k(gw::gw_step_small_kernel<true, GW_OBS_BF16>, p, blocks, 256, smem, s, use_pdl());
+  } else {
+    if (f32) launch_k(gw::gw_step_small_kernel<false, GW_OBS_F32>, p, blocks, 256, smem, s, use_pdl());
+    else launch_k(gw::gw_step_small_kernel<false, GW_OBS_BF16>, p, blocks, 256, smem, s, use_pdl());
   }
 }
 
@@ -1387,14 +1782,13 @@ int gw_step(gw_handle* h, const gw_io* io, void* stream) {
   const int tile = pick_tile(h->cfg.num_envs);
   const long long n_tiles = (h->cfg.num_envs + tile - 1) / tile;
   // persistent CTAs: at most `sm_count x resident CTAs per SM`, each walks several tiles and loads the tables once
-  const long long resident = (long long)h->sm_count * 4;
+  static const bool small_kernel = [] { const char* v = std::getenv("GW_SMALL"); return !(v && std::atoi(v) == 0); }();
+  const long long resident = (long long)h->sm_count * ((tile == 32 && small_kernel) ? 2 : 4);
   const unsigned blocks = (unsigned)(n_tiles < resident ? n_tiles : resident);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int split = pick_split(n_tiles, h->sm_count, tile);
-  if (tile == 32) launch_step_t<256, 32, 9>(h->cfg, p, blocks, s);
-  else if (split == 9) launch_step_t<256, 256, 9>(h->cfg, p, blocks, s);
-  else if (split == 3) launch_step_t<256, 256, 3>(h->cfg, p, blocks, s);
-  else launch_step_t<256, 256, 1>(h->cfg, p, blocks, s);
+  if (tile == 32 && small_kernel) launch_step_small(h->cfg, p, blocks, s);   // latency regime: 8 lanes per env, no CTA-wide phases
+  else if (tile == 32) launch_step_t<256, 32>(h->cfg, p, blocks, s);
+  else launch_step_t<256, 256>(h->cfg, p, blocks, s);
   GW_CUDA(h, cudaGetLastError());
   h->launches += 1;
   h->env_steps += (uint64_t)h->cfg.num_envs;
