@@ -124,7 +124,10 @@ class BatchedGridWorld:
             pass
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        try:                                                       # raw handle of the current stream, without building a Stream object
+            return C.c_void_p(torch._C._cuda_getCurrentRawStream(self.device.index))
+        except AttributeError:
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _view(self, obs: torch.Tensor) -> torch.Tensor:
         if self.obs_layout == "cnn":
@@ -222,31 +225,50 @@ class BatchedGridWorld:
 
     def step_host(self, host_actions: torch.Tensor, host_reward: torch.Tensor, host_ended: Optional[torch.Tensor] = None,
                   host_shaped: Optional[torch.Tensor] = None, obs_out: Optional[torch.Tensor] = None,
-                  zero_copy: bool = False) -> StepOutput:
-        """Host-driven step in one library call: pinned int8 actions [E, L] in, pinned f32 rewards [E, L] (and u8 ended
-        [E], f32 shaped rewards) out, stream synchronised on return.  Observations and masks stay on the device.
-        zero_copy: the kernel reads / writes the pinned buffers itself over PCIe instead of separate memcpys (the
-        device-side reward / ended tensors are then not updated)."""
-        if not hasattr(self, "_host_act_dev"):
-            self._host_act_dev = torch.empty((self.num_envs, self.n_learners), dtype=torch.int8, device=self.device)
-            self._pinned_ok = set()                                # is_pinned() queries the driver: check each buffer once
-        for t, name in ((host_actions, "host_actions"), (host_reward, "host_reward"), (host_ended, "host_ended"), (host_shaped, "host_shaped")):
+                  zero_copy: bool = True) -> StepOutput:
+        """Host-driven step in one library call (the reference's calling pattern, maddpg/agent.py:121-131): pinned int8
+        actions [E, L] in, pinned f32 rewards [E, L] (and u8 ended [E], f32 shaped rewards) out, stream synchronised on
+        return.  Observations and masks stay on the device.
+        zero_copy (default): the kernel itself loads the actions from the pinned buffer and stores rewards / flags into
+        the pinned buffers over PCIe; the returned StepOutput then carries the host tensors for those fields.
+        zero_copy=False: cudaMemcpyAsync H2D / D2H around the kernel and device-side copies of the outputs as well.
+        Argument checking and marshalling are done once per distinct set of buffers."""
+        obs = obs_out if obs_out is not None else self.buf.obs
+        key = (host_actions.data_ptr(), host_reward.data_ptr(), 0 if host_ended is None else host_ended.data_ptr(),
+               0 if host_shaped is None else host_shaped.data_ptr(), obs.data_ptr(), zero_copy)
+        cache = self.__dict__.setdefault("_host_calls", {})
+        ent = cache.get(key)
+        if ent is None:
+            ent = self._prepare_host_call(host_actions, host_reward, host_ended, host_shaped, obs_out, zero_copy)
+            if len(cache) >= 4096:
+                cache.clear()
+            cache[key] = ent
+        ioref, pa, pr, ps, pe, zc, out, _ = ent
+        rc = self.lib.gw_step_host(self._h, ioref, pa, pr, ps, pe, zc, self._stream())
+        if rc:
+            N.check(rc, self._h, "gw_step_host")
+        return out
+
+    def _prepare_host_call(self, host_actions, host_reward, host_ended, host_shaped, obs_out, zero_copy):
+        E, L = self.num_envs, self.n_learners
+        for t, name, dtype, shape in ((host_actions, "host_actions", torch.int8, (E, L)), (host_reward, "host_reward", torch.float32, (E, L)),
+                                      (host_ended, "host_ended", torch.uint8, (E,)), (host_shaped, "host_shaped", torch.float32, (E, L))):
             if t is None:
                 continue
-            key = (t.data_ptr(), t.numel(), t.dtype)
-            if key not in self._pinned_ok:
-                if t.is_cuda or not t.is_pinned() or not t.is_contiguous():
-                    raise ValueError(f"{name} must be a contiguous pinned host tensor")
-                self._pinned_ok.add(key)
+            if t.is_cuda or not t.is_pinned() or not t.is_contiguous() or t.dtype != dtype or tuple(t.shape) != shape:
+                raise ValueError(f"{name} must be a contiguous pinned host tensor of dtype {dtype} and shape {shape}")
+        if not hasattr(self, "_host_act_dev"):
+            self._host_act_dev = torch.empty((E, L), dtype=torch.int8, device=self.device)
         obs = self._obs_arg(obs_out, "obs_out") if obs_out is not None else self.buf.obs
-        io = self._io(obs, None, self._host_act_dev, None, None)
+        io = N.GwIO()
+        C.memmove(C.byref(io), C.byref(self._io(obs, None, self._host_act_dev, None, None)), C.sizeof(N.GwIO))   # own copy
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
-        N.check(self.lib.gw_step_host(self._h, C.byref(io), p(host_actions), p(host_reward), p(host_shaped), p(host_ended),
-                                      int(bool(zero_copy)), self._stream()), self._h, "gw_step_host")
         b = self.buf
-        return StepOutput(obs=self._view(obs), action_mask=b.action_mask, positions=b.positions, reward=b.reward,
-                          shaped_reward=b.shaped_reward, fear=b.fear, terminated=b.terminated, truncated=b.truncated,
-                          ended=b.ended, info=b.info, obs_code=b.obs_code)
+        pick = (lambda host, dev: host if (zero_copy and host is not None) else dev)
+        out = StepOutput(obs=self._view(obs), action_mask=b.action_mask, positions=b.positions, reward=pick(host_reward, b.reward),
+                         shaped_reward=pick(host_shaped, b.shaped_reward), fear=b.fear, terminated=b.terminated,
+                         truncated=b.truncated, ended=pick(host_ended, b.ended), info=b.info, obs_code=b.obs_code)
+        return (C.byref(io), p(host_actions), p(host_reward), p(host_shaped), p(host_ended), int(bool(zero_copy)), out, io)   # io kept alive
 
     def sync(self):
         N.check(self.lib.gw_sync(self._h, self._stream()), self._h, "gw_sync")

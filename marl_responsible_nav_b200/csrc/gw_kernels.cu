@@ -44,6 +44,7 @@ struct StepParams {
   uint32_t seed_lo, seed_hi;
   double fear_weight;
   const uint8_t* reset_mask;          // gw_reset only
+  int pdl_early;                      // small grids: let the next step's grid start its prologue right away
   unsigned long long* trace;          // GW_TRACE (dev): per CTA 16 globaltimer stamps at the phase boundaries
 };
 
@@ -807,6 +808,14 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
 // the words the fix-point needs are gathered with redux.sync over the 8-lane group.  The env's FeAR tasks are counted
 // by the same 8 lanes (one (task, variant, three actions) item each), so there is no CTA-wide queue and no barrier
 // after the table copy: every warp steps and renders its own four envs and leaves.
+template <int OBS>
+__device__ __forceinline__ void patch_cell(uint8_t* row, uint32_t enc, bool set) {
+  if (enc == 0xFFFFu) return;
+  const float v = set ? 0.5f * (float)(enc >> 9) : 0.0f;
+  if (OBS == GW_OBS_F32) reinterpret_cast<float*>(row)[enc & 0x1FFu] = v;
+  else reinterpret_cast<__nv_bfloat16*>(row)[enc & 0x1FFu] = __float2bfloat16(v);
+}
+
 __device__ __forceinline__ uint32_t special_entry(int q, int cpo, int n, int nl, int kind, uint32_t cells, uint32_t apples_left,
                                                   uint32_t apple_cells, bool fresh) {
   const int k = q >= (GW_MAX_AGENTS + 1) ? 1 : 0, i = q - k * (GW_MAX_AGENTS + 1);
@@ -815,7 +824,10 @@ __device__ __forceinline__ uint32_t special_entry(int q, int cpo, int n, int nl,
   if (i < GW_MAX_AGENTS) {
     if (k >= nl || i >= n) return 0xFFFFu;
     const uint32_t c = (cells >> (8 * i)) & 0xFFu;
-    return (uint32_t)(k * cpo + (int)c) | ((uint32_t)(2.0f * special_value(kind, fresh, i, k, apple_on && c == apple)) << 9);
+    const bool here = apple_on && c == apple;
+    // twice special_value(): 0.5 fresh marker / raw id (apple cell, single env) / 1 self / 5 other; +9 on the apple
+    const uint32_t v2 = (fresh ? 1u : ((here || kind == GW_ENV_SINGLE) ? 2u * (uint32_t)(i + 1) : (i == k ? 2u : 10u))) + (here ? 18u : 0u);
+    return (uint32_t)(k * cpo + (int)c) | (v2 << 9);
   }
   bool covered = false;
 #pragma unroll
@@ -841,6 +853,7 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
   uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
   trace_stamp(p, 0);
   load_tables<THREADS, TILE, OBS>(s, stage, p.tables, p.H, p.nl, true);
+  trace_stamp(p, 3);
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = tid & 7, gsh = lane & 24;
   constexpr unsigned FULL = 0xFFFFFFFFu;     // every shuffle / ballot below is executed by the whole converged warp: a
@@ -848,6 +861,12 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
   const int n = p.n, nl = p.nl;
   const long long n_tiles = (p.E + TILE - 1) / TILE;
   bool tables_pending = true;
+  const int cpo = p.H * GW_W;
+  const int Q = (OBS == GW_OBS_F32) ? cpo / 4 : cpo / 8;               // 16-byte vectors per learner observation
+  const int V = nl * Q, row_bytes = V * 16;
+  uint8_t* const rows4 = stage + (size_t)warp * 4 * row_bytes;         // this warp's staging rows
+  uint8_t* const myrow = rows4 + (lane >> 3) * row_bytes;              // this group's env
+  if (p.pdl_early) asm volatile("griddepcontrol.launch_dependents;");
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long tile_base = tile * TILE;
@@ -862,6 +881,8 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
     uint32_t rw[4] = {0, 0, 0, 0}, rw2[4] = {0, 0, 0, 0};
     if (own) {
       st = p.state[e];
+      if (p.trace != nullptr && st.z == 0xFFFFFFFFu) st.x++;   // dev: the stamp below waits for the load
+      trace_stamp(p, 4);
 #pragma unroll
       for (int k = 0; k < GW_MAX_LEARNERS; ++k)
         if (k < nl) la |= (uint32_t)min(max((int)p.io.learner_actions[e * nl + k], 0), 8) << (4 * k);
@@ -879,15 +900,27 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
       // the re-spawn draw of an env that ends in this step, drawn now: it hides behind the table copy
       if (p.auto_reset && p.io.spawn == nullptr) chosen = spawn_choose(p, e, st.z);
     }
+    trace_stamp(p, 5);
     if (tables_pending) {
       cp_async_wait_all();
       __syncthreads();
-      fill_stage_rows<THREADS, TILE, OBS>(s, stage, p.H, p.nl);
-      __syncthreads();
+      trace_stamp(p, 14);
+      // the warp's four staging rows (one per env of the warp) <- the constant template; warp-private from here on
+      const uint4* src = reinterpret_cast<const uint4*>(s.mask);
+      uint4* dst = reinterpret_cast<uint4*>(rows4);
+      int q = lane % Q;
+      const int qstep = 32 % Q;
+      for (int i = lane; i < 4 * V; i += 32) {
+        dst[i] = src[q];
+        q += qstep;
+        if (q >= Q) q -= Q;
+      }
+      __syncwarp();
       tables_pending = false;
     }
     trace_stamp(p, 1);
 
+    uint32_t enc0 = 0xFFFFu, enc1 = 0xFFFFu;                           // the two special cells this lane patches into its env's row
     uint32_t v_end = 0, v_len = 0, v_cr = 0, v_ap = 0, v_tasks = 0, v_nz = 0;     // statistics: lane r == 0 of every group
     int v_ret = 0;
     double v_fear = 0.0;
@@ -1024,11 +1057,10 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
 
       trace_stamp(p, 12);
       // ---- observation specials and action masks of the (new) positions
-      {
-        const int cpo = p.H * GW_W;
+      if (own) {
         const bool fresh = (rflags & R_FRESH) != 0;
-        s.spec[el][r] = (uint16_t)special_entry(r, cpo, n, nl, p.kind, cells_r, apples_r, p.apple_cells, fresh);
-        if (r < N_SPEC - 8) s.spec[el][r + 8] = (uint16_t)special_entry(r + 8, cpo, n, nl, p.kind, cells_r, apples_r, p.apple_cells, fresh);
+        enc0 = special_entry(r, cpo, n, nl, p.kind, cells_r, apples_r, p.apple_cells, fresh);
+        if (r < N_SPEC - 8) enc1 = special_entry(r + 8, cpo, n, nl, p.kind, cells_r, apples_r, p.apple_cells, fresh);
       }
       if (p.io.action_mask != nullptr) {                               // get_action_mask :467-506: lane r tests action r + 1
         const int a = r + 1, len = a >= 5 ? 2 : 1, d = (a - 1) & 3;
@@ -1121,9 +1153,38 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
     trace_stamp(p, 2);
 
     // ================================================================= observations of the warp's own four envs
-    __syncwarp();
-    if (tile + gridDim.x >= n_tiles) asm volatile("griddepcontrol.launch_dependents;");
-    render_obs<THREADS, TILE, OBS>(s, stage, p, tile_base, warp * 4, 1, min(tile_envs, warp * 4 + 4));
+    // Every lane drops its special cells into its env's staging row, the four rows (contiguous, like the four
+    // observations in HBM) leave as 128-bit streaming stores, and the cells are set back to the template's 0.
+    if (!p.pdl_early && tile + gridDim.x >= n_tiles) asm volatile("griddepcontrol.launch_dependents;");
+    if (p.io.obs != nullptr) {
+      patch_cell<OBS>(myrow, enc0, true);
+      patch_cell<OBS>(myrow, enc1, true);
+      __syncwarp();
+      const int total = max(0, min(4, tile_envs - warp * 4)) * V;
+      const uint4* src = reinterpret_cast<const uint4*>(rows4) + lane;
+      uint4* dst = reinterpret_cast<uint4*>(p.io.obs) + (tile_base + warp * 4) * (long long)V + lane;
+      for (int base = 0; base < total; base += 32 * 5) {
+        uint4 v[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+          if (base + 32 * i + lane < total) v[i] = src[base + 32 * i];
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+          if (base + 32 * i + lane < total) __stcs(dst + base + 32 * i, v[i]);
+      }
+      __syncwarp();
+      patch_cell<OBS>(myrow, enc0, false);
+      patch_cell<OBS>(myrow, enc1, false);
+      __syncwarp();
+    }
+    if (p.io.final_obs != nullptr) {                       // terminal observation of envs that were just re-spawned (rare)
+      for (int el4 = warp * 4; el4 < min(tile_envs, warp * 4 + 4); ++el4) {
+        const uint32_t ri = s.rinfo[el4];
+        if (ri & R_FINAL)
+          stage_and_store_env<OBS>(rows4, p.io.final_obs, tile_base + el4, p.H, n, nl, p.kind, s.cells_fin[el4], (ri >> 4) & 3u,
+                                   p.apple_cells, false, lane);
+      }
+    }
     trace_stamp(p, 6);
 
     // ================================================================= statistics (most warps contribute nothing)
@@ -1669,6 +1730,12 @@ static gw::StepParams make_params(gw_handle* h, const gw_io* io) {
   return p;
 }
 
+static inline cudaError_t use_device(int device) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur == device) return cudaSuccess;
+  return cudaSetDevice(device);
+}
+
 static bool misaligned(const void* p, size_t a) { return p && (reinterpret_cast<uintptr_t>(p) % a) != 0; }
 
 static int check_io(gw_handle* h, const gw_io* io, bool step) {
@@ -1697,8 +1764,22 @@ static int pick_tile(long long E) {
 template <typename K>
 static void launch_k(K kernel, const gw::StepParams& p, unsigned blocks, int threads, size_t smem, cudaStream_t s,
                      bool pdl = false) {
-  // > 48 KB of dynamic shared memory needs the opt-in; the attribute is per function and cheap to set
-  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // > 48 KB of dynamic shared memory needs the opt-in; raised (never lowered) per (device, function)
+  {
+    struct Seen { int dev; const void* fn; size_t smem; };
+    static thread_local Seen seen[64];
+    static thread_local int n_seen = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int at = -1;
+    for (int i = 0; i < n_seen; ++i)
+      if (seen[i].dev == dev && seen[i].fn == (const void*)kernel) at = i;
+    if (at < 0 || seen[at].smem < smem) {
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (at >= 0) seen[at].smem = smem;
+      else if (n_seen < 64) seen[n_seen++] = Seen{dev, (const void*)kernel, smem};
+    }
+  }
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(blocks);
@@ -1734,15 +1815,21 @@ static void launch_step_t(const gw_config& c, const gw::StepParams& p, unsigned 
   }
 }
 
-static void launch_step_small(const gw_config& c, const gw::StepParams& p, unsigned blocks, cudaStream_t s) {
+static void launch_step_small(const gw_config& c, gw::StepParams& p, unsigned blocks, int sm_count, cudaStream_t s) {
+  // Programmatic dependent launch: when this grid and the next one fit on the machine together (one CTA per SM each), the
+  // next step's CTAs start at once, copy their tables while this step runs and wait (griddepcontrol.wait) for its results.
+  // GW_PDL=0 turns it off, GW_PDL=1 turns the late trigger on for every size (measured: it only pays for small grids).
+  static const int pdl_env = [] { const char* v = std::getenv("GW_PDL"); return v ? std::atoi(v) : -1; }();
+  p.pdl_early = (pdl_env != 0 && (int)blocks <= sm_count) ? 1 : 0;
   const bool f32 = c.obs_dtype == GW_OBS_F32;
-  const size_t smem = gw::smem_fixed_bytes<32>() + (size_t)8 * 2 * gw::stage_row_bytes(c);
+  const size_t smem = gw::smem_fixed_bytes<32>() + (size_t)8 * 4 * gw::stage_row_bytes(c);
+  const bool pdl = p.pdl_early != 0 || use_pdl();
   if (c.fear) {
-    if (f32) launch_k(gw::gw_step_small_kernel<true, GW_OBS_F32>, p, blocks, 256, smem, s, use_pdl());
-    else launch_k(gw::gw_step_small_kernel<true, GW_OBS_BF16>, p, blocks, 256, smem, s, use_pdl());
+    if (f32) launch_k(gw::gw_step_small_kernel<true, GW_OBS_F32>, p, blocks, 256, smem, s, pdl);
+    else launch_k(gw::gw_step_small_kernel<true, GW_OBS_BF16>, p, blocks, 256, smem, s, pdl);
   } else {
-    if (f32) launch_k(gw::gw_step_small_kernel<false, GW_OBS_F32>, p, blocks, 256, smem, s, use_pdl());
-    else launch_k(gw::gw_step_small_kernel<false, GW_OBS_BF16>, p, blocks, 256, smem, s, use_pdl());
+    if (f32) launch_k(gw::gw_step_small_kernel<false, GW_OBS_F32>, p, blocks, 256, smem, s, pdl);
+    else launch_k(gw::gw_step_small_kernel<false, GW_OBS_BF16>, p, blocks, 256, smem, s, pdl);
   }
 }
 
@@ -1777,7 +1864,7 @@ int gw_step(gw_handle* h, const gw_io* io, void* stream) {
   if (!h) return GW_EINVAL;
   if (int rc = check_io(h, io, true)) return rc;
   if (!h->reset_done) return fail(h, GW_ESTATE, "gw_step: call gw_reset first");
-  GW_CUDA(h, cudaSetDevice(h->cfg.device));
+  GW_CUDA(h, use_device(h->cfg.device));
   gw::StepParams p = make_params(h, io);
   const int tile = pick_tile(h->cfg.num_envs);
   const long long n_tiles = (h->cfg.num_envs + tile - 1) / tile;
@@ -1786,7 +1873,7 @@ int gw_step(gw_handle* h, const gw_io* io, void* stream) {
   const long long resident = (long long)h->sm_count * ((tile == 32 && small_kernel) ? 2 : 4);
   const unsigned blocks = (unsigned)(n_tiles < resident ? n_tiles : resident);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (tile == 32 && small_kernel) launch_step_small(h->cfg, p, blocks, s);   // latency regime: 8 lanes per env, no CTA-wide phases
+  if (tile == 32 && small_kernel) launch_step_small(h->cfg, p, blocks, h->sm_count, s);   // latency regime: 8 lanes per env, no CTA-wide phases
   else if (tile == 32) launch_step_t<256, 32>(h->cfg, p, blocks, s);
   else launch_step_t<256, 256>(h->cfg, p, blocks, s);
   GW_CUDA(h, cudaGetLastError());

@@ -22,10 +22,11 @@ t0 = b[:, 0].min()
 names = ["start", "tables+P1a done", "P1b done", "P2 barrier", "P2 done", "P3 done", "P4 barrier", "tile end",
          "P1b: sampled", "P1b: geometry", "P1b: world_update", "P1b: fear tasks", "P1b: rewards", "P1b: outputs", "P1b: spawn", "-"]
 if os.environ.get("GW_SMALL", "1") != "0" and E <= 32768:
-    names = ["start", "tables+P1a done", "step done (warp 0)", "-", "-", "-", "render done (warp 0)", "tile end (warp 0)",
-             "traj + effw", "collisions", "final cells", "rewards+spawn", "outputs", "specials+masks", "-", "-"]
+    names = ["start", "tables+P1a done", "step done (warp 0)", "cp.async issued", "state arrived", "philox done", "render done (warp 0)", "tile end (warp 0)",
+             "traj + effw", "collisions", "final cells", "rewards+spawn", "outputs", "specials+masks", "tables landed + barrier", "-"]
+    order = [0, 3, 4, 5, 14, 1, 8, 9, 10, 11, 12, 13, 2, 6, 7]
 print(f"E={E} fear={fear} CTAs={len(b)}  kernel span = {(b[:, 7].max() - t0) / 1e3:.2f} us (first start -> last end)")
-order = [0, 1, 8, 9, 10, 11, 12, 13, 14, 2, 3, 4, 5, 6, 7]
+order = locals().get('order', [0, 1, 8, 9, 10, 11, 12, 13, 14, 2, 3, 4, 5, 6, 7])
 for i in order:
     nm = names[i]
     if not (b[:, i] > 0).all(): continue

@@ -230,16 +230,22 @@ def test_step_host_matches_device_step():
     rew = torch.empty((E, 2), dtype=torch.float32).pin_memory()
     shp = torch.empty((E, 2), dtype=torch.float32).pin_memory()
     end = torch.empty((E,), dtype=torch.uint8).pin_memory()
-    for t in range(6):
+    for t in range(6):                                   # default: the kernel reads / writes the pinned buffers itself
         oa = a.step_host(acts[t], rew, end, host_shaped=shp)
         ob = b.step(acts[t].cuda())
         assert torch.equal(rew, ob.reward.cpu()) and torch.equal(end, ob.ended.cpu()) and torch.equal(shp, ob.shaped_reward.cpu())
         assert torch.equal(oa.obs, ob.obs) and torch.equal(oa.obs_code, ob.obs_code)
-    for t in range(3):                                   # zero-copy variant: same results land in the pinned buffers
-        oa = a.step_host(acts[t], rew, end, host_shaped=shp, zero_copy=True)
+        assert oa.reward is rew and oa.ended is end and oa.shaped_reward is shp
+    for t in range(3):                                   # memcpy variant: same results, device-side copies as well
+        oa = a.step_host(acts[t], rew, end, host_shaped=shp, zero_copy=False)
         ob = b.step(acts[t].cuda())
         assert torch.equal(rew, ob.reward.cpu()) and torch.equal(end, ob.ended.cpu()) and torch.equal(shp, ob.shaped_reward.cpu())
-        assert torch.equal(oa.obs, ob.obs)
+        assert torch.equal(oa.obs, ob.obs) and torch.equal(oa.reward, ob.reward)
+    ring = torch.empty((2,) + tuple(ob.obs.shape), dtype=ob.obs.dtype, device="cuda")
+    for t in range(4):                                   # cached marshalling: alternating buffers still hit the right ones
+        oa = a.step_host(acts[t], rew, end, obs_out=ring[t % 2])
+        ob = b.step(acts[t].cuda())
+        assert torch.equal(rew, ob.reward.cpu()) and torch.equal(ring[t % 2], ob.obs) and oa.obs.data_ptr() == ring[t % 2].data_ptr()
     st = a.stats()
     assert st["fear_tasks"] > 0 and st["fear_tasks"] == b.stats()["fear_tasks"]
     with pytest.raises(ValueError):
