@@ -221,6 +221,28 @@ __device__ __forceinline__ void encode_specials(uint16_t* out, int cpo, int n, i
 // Per env: lanes 0..9 drop the pre-computed special cells into row A, one __syncwarp, the cells patched into row B
 // for the previous env are zeroed again (agents and apples only stand on active cells, whose template value is 0),
 // and row A leaves as 128-bit streaming stores: whole 128-byte lines, never a partial sector.  Rows alternate.
+template <int OBS>
+__device__ __forceinline__ void patch_cell(uint8_t* row, uint32_t enc, bool set) {
+  if (enc == 0xFFFFu) return;
+  const float v = set ? 0.5f * (float)(enc >> 9) : 0.0f;
+  if (OBS == GW_OBS_F32) reinterpret_cast<float*>(row)[enc & 0x1FFu] = v;
+  else reinterpret_cast<__nv_bfloat16*>(row)[enc & 0x1FFu] = __float2bfloat16(v);
+}
+
+// ---- TMA bulk copies shared -> global (cp.async.bulk, bulk async-groups)
+__device__ __forceinline__ void fence_proxy_async_smem() {    // generic-proxy writes to shared memory -> visible to the async proxy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_row(void* gdst, const void* ssrc, int bytes) {
+  const uint32_t src = (uint32_t)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\ncp.async.bulk.commit_group;"
+               ::"l"(gdst), "r"(src), "r"(bytes) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {             // at most N of this thread's bulk groups still read shared memory
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
 // el0 / el_step / el_end: the envs of the tile this warp renders (big kernel: warp, +NWARPS, ...; small kernel: its own four).
 template <int THREADS, int TILE, int OBS>
 __device__ __forceinline__ void render_obs(Smem<TILE>& s, uint8_t* stage, const StepParams& p, long long tile_base,
@@ -229,40 +251,34 @@ __device__ __forceinline__ void render_obs(Smem<TILE>& s, uint8_t* stage, const 
   const int cpo = p.H * GW_W;
   const int V = p.nl * ((OBS == GW_OBS_F32) ? cpo / 4 : cpo / 8);
   if (p.io.obs != nullptr) {
+    // Rows leave through the TMA: lanes 0..9 patch the special cells into the warp's staging row, one lane issues a bulk
+    // shared->global copy of the whole row (cp.async.bulk: whole 128-byte lines, no LSU traffic for the payload), and the
+    // row is cleaned up two envs later, once the copy has read it.  Two rows alternate.
     const int row_bytes = V * 16;
     uint8_t* const row0 = stage + warp * 2 * row_bytes;
-    uint4* dst = reinterpret_cast<uint4*>(p.io.obs) + (tile_base + el0) * (long long)V + lane;
-    const long long dst_step = (long long)el_step * V;
-    uint32_t prev_enc = 0xFFFFu;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(p.io.obs) + (tile_base + el0) * (long long)row_bytes;
+    const long long dst_step = (long long)el_step * row_bytes;
+    uint32_t enc_a = 0xFFFFu, enc_b = 0xFFFFu;             // what this lane patched into row 0 / row 1
     int cur = 0;
     for (int el = el0; el < el_end; el += el_step, dst += dst_step) {
       if (s.rinfo[el] & R_SKIP) continue;                  // warp-uniform
       uint8_t* row = row0 + cur * row_bytes;
-      uint8_t* other = row0 + (cur ^ 1) * row_bytes;
       const uint32_t enc = (lane < N_SPEC) ? (uint32_t)s.spec[el][lane] : 0xFFFFu;
-      if (enc != 0xFFFFu) {
-        const float v = 0.5f * (float)(enc >> 9);
-        if (OBS == GW_OBS_F32) reinterpret_cast<float*>(row)[enc & 0x1FFu] = v;
-        else reinterpret_cast<__nv_bfloat16*>(row)[enc & 0x1FFu] = __float2bfloat16(v);
-      }
-      __syncwarp();                                        // patches visible; the previous row has been read by everyone
-      if (prev_enc != 0xFFFFu) {
-        if (OBS == GW_OBS_F32) reinterpret_cast<float*>(other)[prev_enc & 0x1FFu] = 0.0f;
-        else reinterpret_cast<__nv_bfloat16*>(other)[prev_enc & 0x1FFu] = __float2bfloat16(0.0f);
-      }
-      const uint4* src = reinterpret_cast<const uint4*>(row) + lane;
-#pragma unroll 4
-      for (int v = 0; v < 4; ++v)
-        if (lane + 32 * v < V) __stcs(dst + 32 * v, src[32 * v]);
-      prev_enc = enc;
+      if (lane == 0) bulk_wait_read<1>();                  // the copy issued from this row two envs ago has read it
+      __syncwarp();
+      patch_cell<OBS>(row, cur ? enc_b : enc_a, false);
+      __syncwarp();                                        // another lane may patch the cell this one just cleared
+      patch_cell<OBS>(row, enc, true);
+      if (cur) enc_b = enc; else enc_a = enc;
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) bulk_store_row(dst, row, row_bytes);
       cur ^= 1;
     }
+    if (lane == 0) bulk_wait_read<0>();                    // leave both rows clean for the next tile
     __syncwarp();
-    if (prev_enc != 0xFFFFu) {                             // leave both rows clean for the next tile
-      uint8_t* last = row0 + (cur ^ 1) * row_bytes;
-      if (OBS == GW_OBS_F32) reinterpret_cast<float*>(last)[prev_enc & 0x1FFu] = 0.0f;
-      else reinterpret_cast<__nv_bfloat16*>(last)[prev_enc & 0x1FFu] = __float2bfloat16(0.0f);
-    }
+    patch_cell<OBS>(row0, enc_a, false);
+    patch_cell<OBS>(row0 + row_bytes, enc_b, false);
     __syncwarp();
   }
   if (p.io.final_obs != nullptr) {                        // terminal observation of envs that were just re-spawned (rare)
@@ -808,14 +824,6 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
 // the words the fix-point needs are gathered with redux.sync over the 8-lane group.  The env's FeAR tasks are counted
 // by the same 8 lanes (one (task, variant, three actions) item each), so there is no CTA-wide queue and no barrier
 // after the table copy: every warp steps and renders its own four envs and leaves.
-template <int OBS>
-__device__ __forceinline__ void patch_cell(uint8_t* row, uint32_t enc, bool set) {
-  if (enc == 0xFFFFu) return;
-  const float v = set ? 0.5f * (float)(enc >> 9) : 0.0f;
-  if (OBS == GW_OBS_F32) reinterpret_cast<float*>(row)[enc & 0x1FFu] = v;
-  else reinterpret_cast<__nv_bfloat16*>(row)[enc & 0x1FFu] = __float2bfloat16(v);
-}
-
 __device__ __forceinline__ uint32_t special_entry(int q, int cpo, int n, int nl, int kind, uint32_t cells, uint32_t apples_left,
                                                   uint32_t apple_cells, bool fresh) {
   const int k = q >= (GW_MAX_AGENTS + 1) ? 1 : 0, i = q - k * (GW_MAX_AGENTS + 1);
@@ -1159,18 +1167,12 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
     if (p.io.obs != nullptr) {
       patch_cell<OBS>(myrow, enc0, true);
       patch_cell<OBS>(myrow, enc1, true);
+      fence_proxy_async_smem();
       __syncwarp();
-      const int total = max(0, min(4, tile_envs - warp * 4)) * V;
-      const uint4* src = reinterpret_cast<const uint4*>(rows4) + lane;
-      uint4* dst = reinterpret_cast<uint4*>(p.io.obs) + (tile_base + warp * 4) * (long long)V + lane;
-      for (int base = 0; base < total; base += 32 * 5) {
-        uint4 v[5];
-#pragma unroll
-        for (int i = 0; i < 5; ++i)
-          if (base + 32 * i + lane < total) v[i] = src[base + 32 * i];
-#pragma unroll
-        for (int i = 0; i < 5; ++i)
-          if (base + 32 * i + lane < total) __stcs(dst + base + 32 * i, v[i]);
+      const int n_here = max(0, min(4, tile_envs - warp * 4));
+      if (lane == 0 && n_here > 0) {                       // four rows, contiguous here and in HBM: one TMA copy
+        bulk_store_row(reinterpret_cast<uint8_t*>(p.io.obs) + (tile_base + warp * 4) * (long long)row_bytes, rows4, n_here * row_bytes);
+        bulk_wait_read<0>();
       }
       __syncwarp();
       patch_cell<OBS>(myrow, enc0, false);
@@ -1750,15 +1752,21 @@ static int check_io(gw_handle* h, const gw_io* io, bool step) {
 
 }  // extern "C" (templates below need C++ linkage)
 
-// Launch shape.  Small batches are latency-bound: 32-env tiles put work on every SM (E = 4096 -> 128 CTAs) and every
-// counterfactual gets its own thread.  Large batches are throughput-bound: 256-env tiles amortise the per-CTA table
-// load.  GW_TILE=32|256 overrides.
+// Launch shape (measured on B200, profiles/README.md).  Up to ~6k envs the step is latency-bound and the 8-lanes-per-env
+// kernel wins (32-env CTAs: E = 4096 -> 128 CTAs, one per SM); up to ~24k envs thread-per-env with 32-env tiles still
+// puts work on every SM; beyond that 256-env tiles amortise the per-CTA table copy and the kernel runs at the memory
+// system's pace.  GW_TILE=32|256 and GW_SMALL=0|1 override (dev).
 static int pick_tile(long long E) {
   if (const char* s = std::getenv("GW_TILE")) {
     const int v = std::atoi(s);
     if (v == 32 || v == 256) return v;
   }
-  return E <= 32768 ? 32 : 256;
+  return E <= 24576 ? 32 : 256;
+}
+
+static bool pick_small(long long E) {
+  if (const char* s = std::getenv("GW_SMALL")) return std::atoi(s) != 0;
+  return E <= 6144;
 }
 
 template <typename K>
@@ -1869,7 +1877,7 @@ int gw_step(gw_handle* h, const gw_io* io, void* stream) {
   const int tile = pick_tile(h->cfg.num_envs);
   const long long n_tiles = (h->cfg.num_envs + tile - 1) / tile;
   // persistent CTAs: at most `sm_count x resident CTAs per SM`, each walks several tiles and loads the tables once
-  static const bool small_kernel = [] { const char* v = std::getenv("GW_SMALL"); return !(v && std::atoi(v) == 0); }();
+  const bool small_kernel = pick_small(h->cfg.num_envs);
   const long long resident = (long long)h->sm_count * ((tile == 32 && small_kernel) ? 2 : 4);
   const unsigned blocks = (unsigned)(n_tiles < resident ? n_tiles : resident);
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -21,7 +21,7 @@ b = b[b[:, 0] > 0]
 t0 = b[:, 0].min()
 names = ["start", "tables+P1a done", "P1b done", "P2 barrier", "P2 done", "P3 done", "P4 barrier", "tile end",
          "P1b: sampled", "P1b: geometry", "P1b: world_update", "P1b: fear tasks", "P1b: rewards", "P1b: outputs", "P1b: spawn", "-"]
-if os.environ.get("GW_SMALL", "1") != "0" and E <= 32768:
+if os.environ.get("GW_SMALL", "1") != "0" and E <= 6144:
     names = ["start", "tables+P1a done", "step done (warp 0)", "cp.async issued", "state arrived", "philox done", "render done (warp 0)", "tile end (warp 0)",
              "traj + effw", "collisions", "final cells", "rewards+spawn", "outputs", "specials+masks", "tables landed + barrier", "-"]
     order = [0, 3, 4, 5, 14, 1, 8, 9, 10, 11, 12, 13, 2, 6, 7]
