@@ -45,13 +45,12 @@ struct SmallTables {                    // per-step lookups, copied to shared me
   uint8_t mdr_map[GW_MAX_H * GW_W];
   uint8_t policy_map[GW_MAX_H * GW_W];
   uint8_t active_cell[GW_MAX_H * GW_W];         // row-major list of active cells (np.where order)
+  uint16_t map_rows[GW_MAX_H];                  // bit c of map_rows[r] = cell (r, c) is active
 };
 
 struct Tables {                         // device-global, read-only, built by gw_create
-  SimTab sim;
-  alignas(16) uint32_t obs_template[2][64 * 4];             // constant observation row (-1 inactive / 0 active) as f32 / bf16 16-byte vectors
-  SmallTables small;
-  uint16_t map_rows[GW_MAX_H];
+  SimTab sim;                           // sim + small are contiguous here and in shared memory: one TMA copy per CTA
+  alignas(16) SmallTables small;
   int32_t n_active;
   int32_t pad_;
 };

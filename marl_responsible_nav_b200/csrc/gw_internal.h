@@ -10,6 +10,7 @@
 struct gw_handle {
   gw_config cfg;
   gw::Tables* d_tables = nullptr;
+  uint8_t* d_stage_init = nullptr;           // replicated observation rows for the kernels' prologue copy
   uint4* d_state = nullptr;
   unsigned long long* d_stats = nullptr;
   unsigned long long* d_trace = nullptr;     // GW_TRACE (dev)

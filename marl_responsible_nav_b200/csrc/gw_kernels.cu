@@ -11,6 +11,7 @@
 //                          (full 512 B per warp instruction, coalesced), then the <= 5 special cells per observation
 //                          are patched with 4-byte stores that hit the lines just written (they merge in L2)
 // State is 16 B/env and lives in HBM/L2 between launches; nothing else is kept by the library.
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -33,6 +34,7 @@ constexpr uint32_t M_APPLES = 0x3u, M_TERM_SH = 2, M_TRUNC = 1u << 4, M_PDV_SH =
 
 struct StepParams {
   const Tables* tables;
+  const uint8_t* stage_init;      // GW_STAGE_ROWS replicated observation rows (template), see load_tables
   uint4* state;
   unsigned long long* stats;      // [STAT_SLOTS][8]
   gw_io io;
@@ -48,6 +50,7 @@ struct StepParams {
   unsigned long long* trace;          // GW_TRACE (dev): per CTA 16 globaltimer stamps at the phase boundaries
 };
 
+constexpr int STAGE_ROWS = 32;         // rows in the replicated block: 8 warps x up to 4 staging rows
 constexpr int STAT_SLOTS = 1024;
 enum { ST_EPISODES = 0, ST_LEN, ST_CRASH, ST_APPLES, ST_TASKS, ST_FEAR_NZ, ST_RETURN_MILLI, ST_FEAR_BITS };   // the 2N-pass cap never binds: no 'unresolved' counter
 
@@ -60,7 +63,7 @@ template <int TILE>
 struct Smem {
   SimTab sim;
   alignas(16) SmallTables small;
-  uint16_t rows[GW_MAX_H];
+  alignas(8) unsigned long long bar;                        // mbarrier of the prologue's TMA copies
   union {                                                   // P1b/P2 scratch of the FeAR tasks, then the mask staging (P3/P4)
     struct { uint32_t cells_old[TILE], effs[TILE], geom_lo[TILE], geom_hi[TILE], close[TILE]; };
     alignas(16) uint8_t mask[TILE * GW_MAX_LEARNERS * GW_N_ACTIONS + 16];
@@ -75,50 +78,54 @@ struct Smem {
 template <int TILE>
 __host__ __device__ constexpr size_t smem_fixed_bytes() { return (sizeof(Smem<TILE>) + 15) / 16 * 16; }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+// ---- prologue: tables and staging rows arrive by TMA (cp.async.bulk global -> shared, completion on an mbarrier)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-
-// Tables -> shared memory.  The pair-mask table and the next-cell table travel with cp.async so that the copy
-// overlaps the first tile's state loads and RNG; the caller waits (cp_async_wait_all + __syncthreads) before P1b.
-template <int THREADS, int TILE, int OBS>
-__device__ __forceinline__ void load_tables(Smem<TILE>& s, uint8_t* stage, const Tables* __restrict__ T, int H, int nl,
-                                            bool need_lut) {
-  const int tid = threadIdx.x;
-  if (need_lut)
-    for (int i = tid; i < (int)sizeof(SimTab) / 16; i += THREADS)
-      cp_async16(reinterpret_cast<uint8_t*>(&s.sim) + 16 * i, reinterpret_cast<const uint8_t*>(&T->sim) + 16 * i);
-  for (int i = tid; i < (int)sizeof(SmallTables) / 16; i += THREADS)
-    cp_async16(reinterpret_cast<uint8_t*>(&s.small) + 16 * i, reinterpret_cast<const uint8_t*>(&T->small) + 16 * i);
-  if (tid < GW_MAX_H) s.rows[tid] = T->map_rows[tid];
-  // constant observation template (-1 inactive / 0 active, grid_world.py:433-434): one copy per CTA into the scratch
-  // area; fill_stage_rows() replicates it into the warps' staging rows once the copy has landed.  (Every CTA pulling
-  // all of its rows straight from the same few L2 lines hot-spots one L2 slice: 2x slower kernels at 4096 envs.)
-  const int Q = (OBS == GW_OBS_F32) ? H * 4 : H * 2;
-  const uint8_t* tmpl = reinterpret_cast<const uint8_t*>(T->obs_template[OBS == GW_OBS_F32 ? 0 : 1]);
-  for (int q = tid; q < Q; q += THREADS) cp_async16(s.mask + 16 * q, tmpl + 16 * q);
-  (void)nl;
-  (void)stage;
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "GW_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra GW_WAIT_DONE;\n\t"
+      "bra GW_WAIT_LOOP;\n\t"
+      "GW_WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity)
+      : "memory");
 }
 
-template <int THREADS, int TILE, int OBS>
-__device__ __forceinline__ void fill_stage_rows(Smem<TILE>& s, uint8_t* stage, int H, int nl) {
-  const int Q = (OBS == GW_OBS_F32) ? H * 4 : H * 2;
-  const int total = (THREADS / 32) * 2 * nl * Q;             // every (warp, row, learner) segment is one template copy
-  const uint4* src = reinterpret_cast<const uint4*>(s.mask);
-  uint4* dst = reinterpret_cast<uint4*>(stage);
-  int q = threadIdx.x % Q;
-  const int qstep = THREADS % Q;
-  for (int i = threadIdx.x; i < total; i += THREADS) {
-    dst[i] = src[q];
-    q += qstep;
-    if (q >= Q) q -= Q;
+// One thread issues two bulk copies: the lookup tables (sim + small, 15.6 KB) and `stage_rows` pre-replicated copies of
+// the constant observation row (-1 inactive / 0 active, grid_world.py:433-434) for the warps' staging rows.  They
+// overlap the first tile's state loads and RNG (and, under programmatic dependent launch, the previous step); everybody
+// waits on the mbarrier (tables_wait) before the first table lookup.  The replicated rows live in a per-handle global
+// block, so the CTAs stream distinct L2 lines instead of all hammering the five lines of a single template row.
+template <int TILE>
+__device__ __forceinline__ void load_tables(Smem<TILE>& s, uint8_t* stage, const StepParams& p, int stage_rows, int row_bytes) {
+  const uint32_t bar = smem_u32(&s.bar);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    constexpr uint32_t tab_bytes = (uint32_t)(offsetof(Smem<TILE>, small) - offsetof(Smem<TILE>, sim) + sizeof(SmallTables));
+    static_assert(tab_bytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+    static_assert(offsetof(Smem<TILE>, small) - offsetof(Smem<TILE>, sim) == offsetof(Tables, small) - offsetof(Tables, sim), "layout");
+    const uint32_t st_bytes = (uint32_t)(stage_rows * row_bytes);
+    mbar_expect_tx(bar, tab_bytes + st_bytes);
+    bulk_load(&s.sim, &p.tables->sim, tab_bytes, bar);
+    bulk_load(stage, p.stage_init, st_bytes, bar);
   }
 }
+template <int TILE>
+__device__ __forceinline__ void tables_wait(Smem<TILE>& s) { mbar_wait(smem_u32(&s.bar), 0u); }
 
 // value of an agent / apple cell.  custom/ma_customenv.py:303-322 (step) / :198-209 (reset),
 // custom/customenv.py:161-163 / :341-344 (single env: raw ids, every remaining apple).
@@ -319,7 +326,7 @@ __device__ __forceinline__ void stage_masks(Smem<TILE>& s, const StepParams& p, 
 #pragma unroll
   for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
     if (k >= p.nl) break;
-    const uint32_t m = action_mask_bits(s.rows, p.H, (cells >> (8 * k)) & 0xFFu);
+    const uint32_t m = action_mask_bits(s.small.map_rows, p.H, (cells >> (8 * k)) & 0xFFu);
 #pragma unroll
     for (int a = 0; a < GW_N_ACTIONS; ++a) s.mask[(tid * p.nl + k) * GW_N_ACTIONS + a] = (uint8_t)((m >> a) & 1u);
   }
@@ -483,11 +490,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_reset_kernel(StepP
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
   uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
-  load_tables<THREADS, TILE, OBS>(s, stage, p.tables, p.H, p.nl, false);
-  cp_async_wait_all();
-  __syncthreads();
-  fill_stage_rows<THREADS, TILE, OBS>(s, stage, p.H, p.nl);
-  __syncthreads();
+  load_tables<TILE>(s, stage, p, (THREADS / 32) * 2, p.nl * p.H * GW_W * (OBS == GW_OBS_F32 ? 4 : 2));
+  tables_wait(s);
   const long long tile_base = (long long)blockIdx.x * TILE;
   const int tile_envs = (int)min((long long)TILE, p.E - tile_base);
   const int tid = threadIdx.x;
@@ -529,9 +533,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
   trace_stamp(p, 0);
   // Programmatic dependent launch (when the launch carries the attribute): this grid's prologue (table copies) may run
   // while the previous step drains; the env state it wrote is only touched after griddepcontrol.wait.
-  load_tables<THREADS, TILE, OBS>(s, stage, p.tables, p.H, p.nl, true);
+  load_tables<TILE>(s, stage, p, (THREADS / 32) * 2, p.nl * p.H * GW_W * (OBS == GW_OBS_F32 ? 4 : 2));
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  const Tables* __restrict__ T = p.tables;
   const int tid = threadIdx.x;
   const int n = p.n, nl = p.nl;
   const long long n_tiles = (p.E + TILE - 1) / TILE;
@@ -577,9 +580,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
       }
     }
     if (tables_pending) {
-      cp_async_wait_all();
-      __syncthreads();
-      fill_stage_rows<THREADS, TILE, OBS>(s, stage, p.H, p.nl);   // reads the scratch area that P1b overwrites
+      tables_wait(s);
       tables_pending = false;
     }
     __syncthreads();
@@ -814,7 +815,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
     __syncthreads();                                       // shared arrays are reused by the next tile
     trace_stamp(p, 7);
   }
-  if (tables_pending) cp_async_wait_all();                 // a CTA without tiles must not exit with copies in flight
+  if (tables_pending) tables_wait(s);                      // a CTA without tiles must not exit with copies in flight
 }
 
 // ------------------------------------------------------------------ step kernel for small batches (latency regime)
@@ -860,7 +861,7 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
   Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
   uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
   trace_stamp(p, 0);
-  load_tables<THREADS, TILE, OBS>(s, stage, p.tables, p.H, p.nl, true);
+  load_tables<TILE>(s, stage, p, 32, p.nl * p.H * GW_W * (OBS == GW_OBS_F32 ? 4 : 2));
   trace_stamp(p, 3);
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = tid & 7, gsh = lane & 24;
@@ -910,20 +911,8 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
     }
     trace_stamp(p, 5);
     if (tables_pending) {
-      cp_async_wait_all();
-      __syncthreads();
+      tables_wait(s);                                                  // tables + the warps' staging rows have landed
       trace_stamp(p, 14);
-      // the warp's four staging rows (one per env of the warp) <- the constant template; warp-private from here on
-      const uint4* src = reinterpret_cast<const uint4*>(s.mask);
-      uint4* dst = reinterpret_cast<uint4*>(rows4);
-      int q = lane % Q;
-      const int qstep = 32 % Q;
-      for (int i = lane; i < 4 * V; i += 32) {
-        dst[i] = src[q];
-        q += qstep;
-        if (q >= Q) q -= Q;
-      }
-      __syncwarp();
       tables_pending = false;
     }
     trace_stamp(p, 1);
@@ -1078,7 +1067,7 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
           if (k >= nl) break;
           const uint32_t pc = (cells_r >> (8 * k)) & 0xFFu;
           const int tr = (int)(pc >> 4) + (d == 0 ? -len : d == 1 ? len : 0), tc = (int)(pc & 15) + (d == 2 ? -len : d == 3 ? len : 0);
-          ok[k] = (unsigned)tr < (unsigned)p.H && (unsigned)tc < (unsigned)GW_W && ((s.rows[tr] >> tc) & 1);
+          ok[k] = (unsigned)tr < (unsigned)p.H && (unsigned)tc < (unsigned)GW_W && ((s.small.map_rows[tr] >> tc) & 1);
         }
         const uint32_t m0 = 1u | (((__ballot_sync(FULL, ok[0]) >> gsh) & 0xFFu) << 1);
         const uint32_t m1 = 1u | (((__ballot_sync(FULL, ok[1]) >> gsh) & 0xFFu) << 1);
@@ -1216,7 +1205,7 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
     __syncwarp();                                                      // s.spec / s.rinfo of this warp are rewritten by the next tile
     trace_stamp(p, 7);
   }
-  if (tables_pending) cp_async_wait_all();                             // a CTA without tiles must not exit with copies in flight
+  if (tables_pending) tables_wait(s);                                  // a CTA without tiles must not exit with copies in flight
 }
 
 static inline size_t stage_row_bytes(const gw_config& c) {
@@ -1654,7 +1643,7 @@ int gw_create(const gw_config* cfg, gw_handle** out) {
 
   gw::Tables* t = new gw::Tables();
   std::memset(t, 0, sizeof(*t));
-  std::memcpy(t->map_rows, cfg->map_rows, sizeof(t->map_rows));
+  std::memcpy(t->small.map_rows, cfg->map_rows, sizeof(t->small.map_rows));
   std::memcpy(t->small.mdr_map, cfg->mdr_map, sizeof(t->small.mdr_map));
   std::memcpy(t->small.policy_map, cfg->policy_map, sizeof(t->small.policy_map));
   for (int p = 0; p < cfg->n_policies; ++p) {
@@ -1668,11 +1657,17 @@ int gw_create(const gw_config* cfg, gw_handle** out) {
   t->n_active = na;
   h->n_active = na;
   if (!build_sim_tables(cfg, &t->sim)) { delete t; delete h; return fail(nullptr, GW_EINVAL, "gw_create: internal: pair table is not symmetric"); }
-  for (int cell = 0; cell < GW_MAX_H * GW_W; ++cell) {
-    const bool active = (cell >> 4) < cfg->height && ((cfg->map_rows[cell >> 4] >> (cell & 15)) & 1);
-    t->obs_template[0][cell] = active ? 0u : 0xBF800000u;                                   // f32 0.0 / -1.0
-    t->obs_template[1][cell >> 1] |= (active ? 0u : 0xBF80u) << (16 * (cell & 1));           // bf16 0 / -1
-  }
+  // replicated observation rows: n_learners copies of the map template (-1 inactive / 0 active) per row
+  const size_t row_bytes = (size_t)cfg->n_learners * cfg->height * GW_W * (cfg->obs_dtype == GW_OBS_F32 ? 4 : 2);
+  std::string stage_init(row_bytes * gw::STAGE_ROWS, '\0');
+  for (int r = 0; r < gw::STAGE_ROWS; ++r)
+    for (int k = 0; k < cfg->n_learners; ++k)
+      for (int cell = 0; cell < cfg->height * GW_W; ++cell) {
+        const bool active = (cfg->map_rows[cell >> 4] >> (cell & 15)) & 1;
+        const size_t idx = ((size_t)r * cfg->n_learners + k) * cfg->height * GW_W + cell;
+        if (cfg->obs_dtype == GW_OBS_F32) reinterpret_cast<uint32_t*>(&stage_init[0])[idx] = active ? 0u : 0xBF800000u;   // 0.0f / -1.0f
+        else reinterpret_cast<uint16_t*>(&stage_init[0])[idx] = active ? (uint16_t)0 : (uint16_t)0xBF80u;               // bf16 0 / -1
+      }
   for (int m = 0; m < 10; ++m)
     for (int a = 0; a < 10; ++a) {
       volatile double v = ((double)m - (double)a) / ((double)m + 0.000001);   // Responsibility.py:194-195, EPS :12
@@ -1684,6 +1679,8 @@ int gw_create(const gw_config* cfg, gw_handle** out) {
   if ((e = cudaMalloc(&h->d_state, sizeof(uint4) * (size_t)cfg->num_envs)) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMalloc state"));
   if ((e = cudaMalloc(&h->d_stats, sizeof(unsigned long long) * gw::STAT_SLOTS * 8)) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMalloc stats"));
   if ((e = cudaMemcpy(h->d_tables, t, sizeof(gw::Tables), cudaMemcpyHostToDevice)) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMemcpy tables"));
+  if ((e = cudaMalloc(&h->d_stage_init, stage_init.size())) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMalloc stage rows"));
+  if ((e = cudaMemcpy(h->d_stage_init, stage_init.data(), stage_init.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMemcpy stage rows"));
   if ((e = cudaMemset(h->d_state, 0, sizeof(uint4) * (size_t)cfg->num_envs)) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMemset state"));
   if ((e = cudaMemset(h->d_stats, 0, sizeof(unsigned long long) * gw::STAT_SLOTS * 8)) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMemset stats"));
   delete t;
@@ -1699,6 +1696,7 @@ int gw_destroy(gw_handle* h) {
   if (!h) return GW_OK;
   cudaSetDevice(h->cfg.device);
   if (h->d_tables) cudaFree(h->d_tables);
+  if (h->d_stage_init) cudaFree(h->d_stage_init);
   if (h->d_state) cudaFree(h->d_state);
   if (h->d_stats) cudaFree(h->d_stats);
   if (h->d_trace) cudaFree(h->d_trace);
@@ -1711,6 +1709,7 @@ static gw::StepParams make_params(gw_handle* h, const gw_io* io) {
   std::memset(&p, 0, sizeof(p));
   const gw_config& c = h->cfg;
   p.tables = h->d_tables;
+  p.stage_init = h->d_stage_init;
   p.state = h->d_state;
   p.stats = h->d_stats;
   if (io) p.io = *io;
