@@ -1753,14 +1753,14 @@ static int check_io(gw_handle* h, const gw_io* io, bool step) {
 
 // Launch shape (measured on B200, profiles/README.md).  Up to ~6k envs the step is latency-bound and the 8-lanes-per-env
 // kernel wins (32-env CTAs: E = 4096 -> 128 CTAs, one per SM); up to ~24k envs thread-per-env with 32-env tiles still
-// puts work on every SM; beyond that 256-env tiles amortise the per-CTA table copy and the kernel runs at the memory
-// system's pace.  GW_TILE=32|256 and GW_SMALL=0|1 override (dev).
+// puts work on every SM; beyond that 128- and (from ~200k envs) 256-env tiles amortise the per-CTA table copy and the
+// kernel runs at the memory system's pace.  GW_TILE=32|128|256 and GW_SMALL=0|1 override (dev).
 static int pick_tile(long long E) {
   if (const char* s = std::getenv("GW_TILE")) {
     const int v = std::atoi(s);
-    if (v == 32 || v == 256) return v;
+    if (v == 32 || v == 128 || v == 256) return v;
   }
-  return E <= 24576 ? 32 : 256;
+  return E <= 24576 ? 32 : (E <= 196608 ? 128 : 256);
 }
 
 static bool pick_small(long long E) {
@@ -1860,6 +1860,7 @@ int gw_reset(gw_handle* h, const uint8_t* reset_mask, const gw_io* io, void* str
   const unsigned blocks = (unsigned)((h->cfg.num_envs + tile - 1) / tile);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (tile == 32) launch_reset_t<256, 32>(h->cfg, p, blocks, s);
+  else if (tile == 128) launch_reset_t<256, 128>(h->cfg, p, blocks, s);
   else launch_reset_t<256, 256>(h->cfg, p, blocks, s);
   GW_CUDA(h, cudaGetLastError());
   h->reset_done = true;
@@ -1882,6 +1883,7 @@ int gw_step(gw_handle* h, const gw_io* io, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (tile == 32 && small_kernel) launch_step_small(h->cfg, p, blocks, h->sm_count, s);   // latency regime: 8 lanes per env, no CTA-wide phases
   else if (tile == 32) launch_step_t<256, 32>(h->cfg, p, blocks, s);
+  else if (tile == 128) launch_step_t<256, 128>(h->cfg, p, blocks, s);
   else launch_step_t<256, 256>(h->cfg, p, blocks, s);
   GW_CUDA(h, cudaGetLastError());
   h->launches += 1;

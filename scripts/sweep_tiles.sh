@@ -1,1 +1,12 @@
-for E in 16384 65536 262144; do for tile in 32 128 256; do for fear in 1 0; do GW_TILE=$tile python bench.py --envs $E --fear $fear --steps 320 --warmup 64 --no-cpu-baseline --no-e2e --no-scale-points | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('E=$E tile=$tile fear=$fear', 'us/step=%.2f'%(1e3*d['ms_per_step']), 'Msteps/s=%.1f'%(d['value']/1e6), 'frac=%.3f'%d['roofline']['frac'])"; done; done; done
+#!/bin/bash
+# dev: thread-per-env kernel with 32/64/128/256-env tiles across batch sizes
+for E in 8192 16384 32768 65536 131072 262144; do
+  for T in 32 64 128 256; do
+    GW_SMALL=0 GW_TILE=$T python bench.py --envs $E --fear ${FEAR:-1} --steps 640 --warmup 64 --no-cpu-baseline --no-e2e --no-scale-points 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); print('E %7d tile %3d: %8.3f us/step  %.3f G agent-steps/s' % ($E, $T, d['ms_per_step']*1e3, d['value']/1e9))
+"
+  done
+done
