@@ -10,6 +10,7 @@
 struct gw_handle {
   gw_config cfg;
   gw::Tables* d_tables = nullptr;
+  unsigned int* d_tile_ctr = nullptr;        // dynamic tile scheduling of the thread-per-env step kernel
   uint8_t* d_stage_init = nullptr;           // replicated observation rows for the kernels' prologue copy
   uint4* d_state = nullptr;
   unsigned long long* d_stats = nullptr;
