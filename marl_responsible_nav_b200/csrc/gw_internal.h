@@ -10,6 +10,7 @@
 struct gw_handle {
   gw_config cfg;
   gw::Tables* d_tables = nullptr;
+  uint4* d_rng_cache = nullptr;              // small-batch kernel: next step's random words per env (tagged)
   unsigned int* d_tile_ctr = nullptr;        // dynamic tile scheduling of the thread-per-env step kernel
   uint8_t* d_stage_init = nullptr;           // replicated observation rows for the kernels' prologue copy
   uint4* d_state = nullptr;

@@ -35,6 +35,7 @@ constexpr uint32_t M_APPLES = 0x3u, M_TERM_SH = 2, M_TRUNC = 1u << 4, M_PDV_SH =
 struct StepParams {
   const Tables* tables;
   const uint8_t* stage_init;      // GW_STAGE_ROWS replicated observation rows (template), see load_tables
+  uint4* rng_cache;               // [E][2] small-batch kernel: next step's Philox words + re-spawn draw, tagged with their tick
   unsigned int* tile_ctr;         // [0] tiles handed out beyond the first wave, [1] CTAs that finished (self-resetting)
   uint4* state;
   unsigned long long* stats;      // [STAT_SLOTS][8]
@@ -749,7 +750,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_step_kernel(StepPa
         g.didx_lo = s.geom_lo[el];
         g.didx_hi = s.geom_hi[el] & 0xFFFFu;
         g.near6 = s.geom_hi[el] >> 16;
-        const uint32_t cnt = count_valid_moves(s.sim, s.cells_old[el], eo, g, (int)j, jc != 0);
+        const uint32_t cnt = count_valid_moves_p6(s.sim, s.cells_old[el], eo, g, (int)j, jc != 0);
         const uint32_t jslot = j - (j > x ? 1u : 0u);
         if (cnt) atomicAdd(&s.cnt[el * 2 + x], cnt << (4 * (jslot * 2 + v)));
       }
@@ -871,6 +872,19 @@ __device__ __forceinline__ uint32_t gather_lanes(unsigned gmask, uint32_t v, int
   return w;
 }
 
+// Philox words of one env step: NPC call 0 (rw), NPC call 1 (rw2, three NPCs only) and the re-spawn draw.
+__device__ __forceinline__ void draw_step_randoms(const StepParams& p, long long e, uint32_t tick, bool three_npcs, uint32_t rw[4],
+                                                  uint32_t rw2[4], uint32_t& chosen) {
+  const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
+  rw[0] = (uint32_t)gid; rw[1] = (uint32_t)(gid >> 32); rw[2] = tick; rw[3] = 0u;
+  philox4x32(rw, p.seed_lo, p.seed_hi);
+  if (three_npcs) {
+    rw2[0] = (uint32_t)gid; rw2[1] = (uint32_t)(gid >> 32); rw2[2] = tick; rw2[3] = 1u;
+    philox4x32(rw2, p.seed_lo, p.seed_hi);
+  }
+  chosen = spawn_choose(p, e, tick);
+}
+
 template <bool FEAR, int OBS>
 __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
   constexpr int THREADS = 256, TILE = 32;
@@ -907,24 +921,21 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
     uint32_t rw[4] = {0, 0, 0, 0}, rw2[4] = {0, 0, 0, 0};
     if (own) {
       st = p.state[e];
-      if (p.trace != nullptr && st.z == 0xFFFFFFFFu) st.x++;   // dev: the stamp below waits for the load
-      trace_stamp(p, 4);
+      // The random words of this step were drawn at the end of the previous one (they only depend on seed, env id and
+      // tick) and parked next to the state; the tag tells whether they belong to this tick (not after reset / set_state).
+      uint4 c0 = make_uint4(0, 0, 0, 0), c1 = make_uint4(0, 0, 0, ~st.z);
+      if (p.rng_cache != nullptr) { c0 = p.rng_cache[2 * e]; c1 = p.rng_cache[2 * e + 1]; }
 #pragma unroll
       for (int k = 0; k < GW_MAX_LEARNERS; ++k)
         if (k < nl) la |= (uint32_t)min(max((int)p.io.learner_actions[e * nl + k], 0), 8) << (4 * k);
-      if (p.io.npc_actions != nullptr) {
-        if (r < 4 && r >= nl && r < n) npc_a = (uint32_t)min(max((int)p.io.npc_actions[e * n + r], 0), 8);
+      if (p.io.npc_actions != nullptr && r < 4 && r >= nl && r < n) npc_a = (uint32_t)min(max((int)p.io.npc_actions[e * n + r], 0), 8);
+      if (c1.w == st.z) {
+        rw[0] = c0.x; rw[1] = c0.y; rw[2] = c0.z; rw[3] = c0.w;
+        rw2[0] = c1.x; rw2[1] = c1.y;
+        chosen = c1.z;
       } else {
-        const unsigned long long gid = (unsigned long long)(p.env_id_base + e);
-        rw[0] = (uint32_t)gid; rw[1] = (uint32_t)(gid >> 32); rw[2] = st.z; rw[3] = 0u;
-        philox4x32(rw, p.seed_lo, p.seed_hi);
-        if (n - nl > 2) {
-          rw2[0] = (uint32_t)gid; rw2[1] = (uint32_t)(gid >> 32); rw2[2] = st.z; rw2[3] = 1u;
-          philox4x32(rw2, p.seed_lo, p.seed_hi);
-        }
+        draw_step_randoms(p, e, st.z, n - nl > 2, rw, rw2, chosen);
       }
-      // the re-spawn draw of an env that ends in this step, drawn now: it hides behind the table copy
-      if (p.auto_reset && p.io.spawn == nullptr) chosen = spawn_choose(p, e, st.z);
     }
     trace_stamp(p, 5);
     if (tables_pending) {
@@ -1113,33 +1124,57 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
           tm |= js << (4 * x);
         }
         if (!own) tm = 0;
-        if (__any_sync(FULL, tm != 0u)) {                              // warp-uniform; groups without a task idle through it
-          PairGeom g;
-          g.near6 = near6;
-          g.didx_lo = gather_lanes<4, 8>(FULL, didx, gsh);
-          g.didx_hi = gather_lanes<2, 8>(FULL, didx, gsh + 4);
-          const int n_items = __popc(tm) * 2;                          // (task, variant): all nine actions are counted at once
-          uint32_t cw0 = 0, cw1 = 0;
-          for (int it = r; it < n_items; it += 8) {                    // no warp-level primitive inside: trip counts may differ
-            const int tk = it >> 1;
-            const uint32_t v = (uint32_t)it & 1u;
-            uint32_t mm = tm;
-            for (int q = 0; q < tk; ++q) mm &= mm - 1u;
-            const uint32_t bit = (uint32_t)__ffs(mm) - 1u, x = bit >> 2, j = bit & 3u;
-            const uint32_t close = (closeb >> (4 * x)) & 0xFu;
-            const uint32_t keep = ((close & 1u) ? 0xFu : 0u) | ((close & 2u) ? 0xF0u : 0u) | ((close & 4u) ? 0xF00u : 0u) |
-                                  ((close & 8u) ? 0xF000u : 0u);
-            uint32_t eo = effw & keep;                                 // agents outside the close list Stay (defaultAction='stay')
-            if (v == 0) eo = (eo & ~(0xFu << (4 * x))) | (((effw >> (16 + 4 * x)) & 0xFu) << (4 * x));   // actor plays its MdR (:169-172)
-            const uint32_t cnt = count_valid_moves(s.sim, cells, eo, g, (int)j, ((close >> j) & 1u) != 0);
-            const uint32_t jslot = j - (j > x ? 1u : 0u);
-            const uint32_t field = cnt << (4 * (jslot * 2 + v));
-            if (x == 0) cw0 += field; else cw1 += field;
-          }
+        // Work items (task, variant) of the warp's four envs are dealt to its 32 lanes, whichever env they belong to: a
+        // lane fetches the env's words from that group's first lane, counts (count_valid_moves: no per-action loop), and
+        // the counts travel back as warp-wide sums per group.  One round unless the four envs hold more than 16 tasks.
+        uint32_t cw0 = 0, cw1 = 0;
+        const int n_it = 2 * __popc(tm);
+        const int c0 = __shfl_sync(FULL, n_it, 0), c1 = __shfl_sync(FULL, n_it, 8), c2 = __shfl_sync(FULL, n_it, 16),
+                  c3 = __shfl_sync(FULL, n_it, 24);
+        const int total = c0 + c1 + c2 + c3;
+        if (total > 0) {                                               // warp-uniform
+          const uint32_t my_lo = gather_lanes<4, 8>(FULL, didx, gsh), my_hi = gather_lanes<2, 8>(FULL, didx, gsh + 4);
+          const uint32_t my_misc = closeb | (tm << 8) | (near6 << 16);
+          uint32_t f0 = 0, f1 = 0;                                     // this lane's contributions (to the env of its item)
+          int item_g = 0;
+          for (int base = 0; base < total; base += 32) {
+            const int it = base + lane;
+            const int gq = (it >= c0) + (it >= c0 + c1) + (it >= c0 + c1 + c2);
+            const int local = it - (gq > 0 ? c0 : 0) - (gq > 1 ? c1 : 0) - (gq > 2 ? c2 : 0);
+            const int src = 8 * gq;
+            const uint32_t cells_g = __shfl_sync(FULL, cells, src), effw_g = __shfl_sync(FULL, effw, src),
+                           misc_g = __shfl_sync(FULL, my_misc, src), lo_g = __shfl_sync(FULL, my_lo, src),
+                           hi_g = __shfl_sync(FULL, my_hi, src);
+            if (it < total) {
+              const uint32_t v = (uint32_t)local & 1u;
+              uint32_t mm = (misc_g >> 8) & 0xFFu;
+              for (int q = 0; q < (local >> 1); ++q) mm &= mm - 1u;
+              const uint32_t bit = (uint32_t)__ffs(mm) - 1u, x = bit >> 2, j = bit & 3u;
+              const uint32_t close = (misc_g >> (4 * x)) & 0xFu;
+              const uint32_t keep = ((close & 1u) ? 0xFu : 0u) | ((close & 2u) ? 0xF0u : 0u) | ((close & 4u) ? 0xF00u : 0u) |
+                                    ((close & 8u) ? 0xF000u : 0u);
+              uint32_t eo = effw_g & keep;                             // agents outside the close list Stay (defaultAction='stay')
+              if (v == 0) eo = (eo & ~(0xFu << (4 * x))) | (((effw_g >> (16 + 4 * x)) & 0xFu) << (4 * x));   // actor plays its MdR (:169-172)
+              PairGeom g;
+              g.near6 = (misc_g >> 16) & 0x3Fu;
+              g.didx_lo = lo_g;
+              g.didx_hi = hi_g;
+              const uint32_t cnt = count_valid_moves(s.sim, cells_g, eo, g, (int)j, ((close >> j) & 1u) != 0);
+              const uint32_t jslot = j - (j > x ? 1u : 0u);
+              const uint32_t field = cnt << (4 * (jslot * 2 + v));
+              if (x == 0) f0 += field; else f1 += field;
+              item_g = gq;
+            }
+            // the sums of this round go back to their groups (4-bit fields, at most 9 each: no carry)
+            uint32_t cw0r = 0, cw1r = 0;
 #pragma unroll
-          for (int o = 1; o < 8; o <<= 1) {                            // 4-bit fields, at most 9 each: no carry
-            cw0 += __shfl_xor_sync(FULL, cw0, o);
-            cw1 += __shfl_xor_sync(FULL, cw1, o);
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t s0 = __reduce_add_sync(FULL, (it < total && item_g == q) ? f0 : 0u);
+              const uint32_t s1 = __reduce_add_sync(FULL, (it < total && item_g == q) ? f1 : 0u);
+              if ((lane >> 3) == q) { cw0r = s0; cw1r = s1; }
+            }
+            cw0 += cw0r; cw1 += cw1r;
+            f0 = f1 = 0;
           }
 #pragma unroll
           for (int x = 0; x < GW_MAX_LEARNERS; ++x) {
@@ -1176,10 +1211,17 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
       fence_proxy_async_smem();
       __syncwarp();
       const int n_here = max(0, min(4, tile_envs - warp * 4));
-      if (lane == 0 && n_here > 0) {                       // four rows, contiguous here and in HBM: one TMA copy
+      if (lane == 0 && n_here > 0)                         // four rows, contiguous here and in HBM: one TMA copy
         bulk_store_row(reinterpret_cast<uint8_t*>(p.io.obs) + (tile_base + warp * 4) * (long long)row_bytes, rows4, n_here * row_bytes);
-        bulk_wait_read<0>();
+      if (p.rng_cache != nullptr && own) {                 // while the copy reads the rows: the next step's random words
+        uint32_t nrw[4] = {0, 0, 0, 0}, nrw2[4] = {0, 0, 0, 0}, nchosen = 0;
+        draw_step_randoms(p, e, st.z + 1, n - nl > 2, nrw, nrw2, nchosen);
+        if (r == 0) {
+          p.rng_cache[2 * e] = make_uint4(nrw[0], nrw[1], nrw[2], nrw[3]);
+          p.rng_cache[2 * e + 1] = make_uint4(nrw2[0], nrw2[1], nchosen, st.z + 1);
+        }
       }
+      if (lane == 0 && n_here > 0) bulk_wait_read<0>();
       __syncwarp();
       patch_cell<OBS>(myrow, enc0, false);
       patch_cell<OBS>(myrow, enc1, false);
@@ -1422,6 +1464,8 @@ __global__ void __launch_bounds__(128) gw_feal_kernel(const Tables* T, int n_def
 
 // ====================================================================== host side / C-ABI
 #include "gw_internal.h"
+
+static bool pick_small(long long E);
 
 thread_local std::string g_gw_create_err;
 
@@ -1696,6 +1740,10 @@ int gw_create(const gw_config* cfg, gw_handle** out) {
   if ((e = cudaMalloc(&h->d_state, sizeof(uint4) * (size_t)cfg->num_envs)) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMalloc state"));
   if ((e = cudaMalloc(&h->d_stats, sizeof(unsigned long long) * gw::STAT_SLOTS * 8)) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMalloc stats"));
   if ((e = cudaMemcpy(h->d_tables, t, sizeof(gw::Tables), cudaMemcpyHostToDevice)) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMemcpy tables"));
+  if (pick_small(cfg->num_envs)) {               // tag ~tick never matches: the first step draws its own words
+    if ((e = cudaMalloc(&h->d_rng_cache, 2 * sizeof(uint4) * (size_t)cfg->num_envs)) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMalloc rng cache"));
+    if ((e = cudaMemset(h->d_rng_cache, 0xA5, 2 * sizeof(uint4) * (size_t)cfg->num_envs)) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMemset rng cache"));
+  }
   if ((e = cudaMalloc(&h->d_tile_ctr, 2 * sizeof(unsigned int))) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMalloc tile counter"));
   if ((e = cudaMemset(h->d_tile_ctr, 0, 2 * sizeof(unsigned int))) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMemset tile counter"));
   if ((e = cudaMalloc(&h->d_stage_init, stage_init.size())) != cudaSuccess) return cleanup(cuda_fail(nullptr, e, "cudaMalloc stage rows"));
@@ -1717,6 +1765,7 @@ int gw_destroy(gw_handle* h) {
   if (h->d_tables) cudaFree(h->d_tables);
   if (h->d_stage_init) cudaFree(h->d_stage_init);
   if (h->d_tile_ctr) cudaFree(h->d_tile_ctr);
+  if (h->d_rng_cache) cudaFree(h->d_rng_cache);
   if (h->d_state) cudaFree(h->d_state);
   if (h->d_stats) cudaFree(h->d_stats);
   if (h->d_trace) cudaFree(h->d_trace);
@@ -1731,6 +1780,7 @@ static gw::StepParams make_params(gw_handle* h, const gw_io* io) {
   p.tables = h->d_tables;
   p.stage_init = h->d_stage_init;
   p.tile_ctr = h->d_tile_ctr;
+  p.rng_cache = h->d_rng_cache;
   static const int dyn_env = [] { const char* v = std::getenv("GW_DYN"); return v ? std::atoi(v) : 1; }();
   p.dyn_tiles = dyn_env;
   p.state = h->d_state;
