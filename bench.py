@@ -27,6 +27,18 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 ALGO_BYTES_PER_AGENT_STEP = {"f32": 668.0, "bf16": 348.0}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+# (profiles/r1c_*_ncu_raw.csv; Level 3, f32 obs): (envs, fear) -> bytes
+NCU_DRAM_BYTES = {(4096, 1): 372.5e3 + 0.0, (1 << 20, 1): 19.89e6 + 1417.0e6, (1 << 20, 0): 19.33e6 + 1378.6e6}
+
+
+def kernel_name(envs, fear, obs):
+    """The kernel gw_step picks for this batch (csrc/gw_kernels.cu: pick_small / pick_tile)."""
+    f = "true" if fear else "false"
+    if envs <= 6144:
+        return f"gw_step_small_kernel<{f},{obs}>"
+    tile = 32 if envs <= 24576 else (128 if envs <= 196608 else 256)
+    return f"gw_step_kernel<256,{tile},{f},{obs}>"
 METRIC = "agent-steps/sec (batched envs, device-timed) at 1/2/4/8 B200 vs CPU ref"
 
 
@@ -293,8 +305,10 @@ def run_ours(a):
             rs = device_timed(a, Es, fs, 128, 64, 1, 0, dev)
             per = rs["ms"] * 1e-3 / 128
             gbs = ALGO_BYTES_PER_AGENT_STEP[a.obs] * Es * rs["L"] / per / 1e9
-            scale_points.append({"envs": Es, "fear": bool(fs), "ms_per_step": rs["ms"] / 128,
-                                 "agent_steps_per_s": Es * rs["L"] / per, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak})
+            scale_points.append({"envs": Es, "fear": bool(fs), "kernel": kernel_name(Es, fs, a.obs), "ms_per_step": rs["ms"] / 128,
+                                 "agent_steps_per_s": Es * rs["L"] / per, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak,
+                                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_AGENT_STEP[a.obs] * Es * rs["L"],
+                                 "traffic": NCU_DRAM_BYTES.get((Es, fs)) if (a.obs == "f32" and a.scenario == "Level 3") else None})
             del rs
 
     if rank != 0:
@@ -314,12 +328,15 @@ def run_ours(a):
                          "never re-read; the packed env state (16 B/env) is L2-resident by design"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(K),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": f"gw_step_kernel<fear={bool(a.fear)},{a.obs}>",
+                     "traffic": NCU_DRAM_BYTES.get((E, int(bool(a.fear)))) if (a.obs == "f32" and a.scenario == "Level 3") else None,
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1c_*_ncu_raw.csv); "
+                                       "at 4096 envs the stores are still in L2 when the kernel ends, so DRAM writes show as 0",
+                     "kernel": kernel_name(E, a.fear, a.obs),
                      "algorithmic_bytes_per_launch": algo, "peak_source": peak_src,
                      "note": "launch duration = CUDA-event time over K back-to-back launches / K (includes launch gaps); "
                              + ("CUDA-graph replay" if a.graph else "eager launches")
-                             + f"; at {E} envs one launch moves {algo / 2**20:.1f} MiB (0.9 us at peak) and is launch/latency-bound: "
-                               "see scale_points for the same kernel at 1M envs"},
+                             + f"; at {E} envs one launch moves {algo / 2**20:.1f} MiB ({algo / peak / 1e3:.2f} us at peak): small batches are "
+                               "launch/latency-bound, see scale_points for the step kernel at 1M envs"},
         "scale_points": scale_points,
         "workload_stats": {"episodes": stat_vec[0].item(), "mean_episode_len": stat_vec[1].item() / max(1.0, stat_vec[0].item()),
                            "learner_crashes_per_env_step": stat_vec[2].item() / (world * E * K),

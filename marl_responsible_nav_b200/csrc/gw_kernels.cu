@@ -521,7 +521,12 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) gw_reset_kernel(StepP
 
 // ------------------------------------------------------------------ step kernel
 // Persistent CTAs: the grid is sized to the machine and each CTA walks tiles blockIdx.x, +gridDim.x, ...
+// Phase stamps are a dev facility: compiled in only with -DGW_ENABLE_TRACE (scripts/trace_phases.py builds that variant).
 __device__ __forceinline__ void trace_stamp(const StepParams& p, int slot) {
+#ifndef GW_ENABLE_TRACE
+  (void)p; (void)slot;
+  return;
+#endif
   if (p.trace != nullptr && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -1,6 +1,14 @@
 """Dev: phase timeline of gw_step at a given batch (GW_TRACE=1).  Prints per-phase medians over CTAs in microseconds."""
 import os, sys, ctypes as C
 os.environ["GW_TRACE"] = "1"
+# the stamps are compiled in only with -DGW_ENABLE_TRACE: build that variant next to the product library
+import subprocess
+_root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "marl_responsible_nav_b200", "csrc")
+_lib = os.path.join(_root, "libgridworld_b200_trace.so")
+if not os.path.exists(_lib) or any(os.path.getmtime(os.path.join(_root, f)) > os.path.getmtime(_lib) for f in ("gw_kernels.cu", "gw_device.cuh", "gw_actor.cu")):
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+                    "-DGW_ENABLE_TRACE", "-o", _lib, "gw_kernels.cu", "gw_actor.cu"], cwd=_root, check=True)
+os.environ["GW_LIB"] = _lib
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np, torch
 from marl_responsible_nav_b200 import BatchedGridWorld
