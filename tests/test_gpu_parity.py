@@ -110,6 +110,16 @@ def test_rollout_no_autoreset_sticky_flags():
     _rollout_vs_oracle(1024, 30, seed=6, fear=False, auto_reset=False, max_steps=0)
 
 
+def test_rollout_every_kernel_variant():
+    """gw_step picks its kernel by batch size (8-lanes-per-env kernel, thread-per-env with 32 / 128 / 256-env tiles,
+    fixed-stride or dynamic tiles): every variant against the oracle, FeAR on, odd sizes for the tile tails."""
+    _rollout_vs_oracle(6144, 10, seed=21, fear=True, fear_weight=-5.0)          # small-batch kernel, largest size
+    _rollout_vs_oracle(6145 + 2000, 10, seed=22, fear=True, fear_weight=-5.0)   # thread per env, 32-env tiles
+    _rollout_vs_oracle(40001, 6, seed=23, fear=True, fear_weight=-5.0, threads=16)      # 128-env tiles
+    _rollout_vs_oracle(200003, 3, seed=24, fear=True, obs_bf16=True, threads=16)        # 256-env tiles, fixed stride
+    _rollout_vs_oracle(4 * 592 * 256 + 77, 2, seed=25, fear=True, obs_bf16=True, threads=16)   # dynamic tiles
+
+
 def test_large_batch_properties_1m():
     """Config[3] size (1M envs): size-independent properties instead of an oracle diff --
     agents stay on active cells and distinct, crashed agents do not move, masks match positions,
