@@ -357,9 +357,25 @@ def run_ours(a):
         except Exception as exc:   # the checker failing must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "agent-steps/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {exc}"}
-    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return line
+
+
+class _QuietStdout:
+    """Everything libraries write to fd 1 while the bench runs (NCCL prints its version line there) goes to stderr, so
+    that stdout carries exactly the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 if __name__ == "__main__":
@@ -367,4 +383,7 @@ if __name__ == "__main__":
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        with _QuietStdout():
+            result = run_ours(args)
+        if result is not None:
+            print(json.dumps(result))
