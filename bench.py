@@ -266,33 +266,45 @@ def run_ours(a):
         host_actions = torch.randint(0, 9, (n_act, E, L), dtype=torch.int8).pin_memory()
         host_rew = torch.empty((E, L), dtype=torch.float32).pin_memory()
         host_end = torch.empty((E,), dtype=torch.uint8).pin_memory()
-        # env.step_host = the public host-driven call: pinned actions H2D, gw_step, rewards + ended flags D2H, stream sync
-        for t in range(10):
-            env.step_host(host_actions[t % n_act], host_rew, host_end, obs_out=ring[t % slots])
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for t in range(Ke):
-            env.step_host(host_actions[t % n_act], host_rew, host_end, obs_out=ring[t % slots])   # returns synchronised
-        el = time.perf_counter() - t0
-        t_e = torch.tensor([el], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * E * L * Ke / float(t_e.item()), "unit": "agent-steps/s",
-               "h2d_bytes_per_step": E * L, "d2h_bytes_per_step": E * L * 4 + E, "steps": Ke,
-               "api": "BatchedGridWorld.step_host (default): one gw_step launch whose kernel loads the step's actions from the "
-                      "pinned host buffer and stores rewards + ended flags into pinned host buffers over PCIe, then a stream sync; "
-                      "observations stay in HBM (replay ring)"}
-        # the same call with zero_copy=False (cudaMemcpyAsync H2D + gw_step + 2 x cudaMemcpyAsync D2H + stream sync): reported aside
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for t in range(Ke):
-            env.step_host(host_actions[t % n_act], host_rew, host_end, obs_out=ring[t % slots], zero_copy=False)
-        t_z = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t_z, op=dist.ReduceOp.MAX)
-        e2e["memcpy_value"] = world * E * L * Ke / float(t_z.item())
+        # env.step_host = the public host-driven call: pinned actions in, rewards + ended flags out in pinned host memory,
+        # complete on return.  Default mode for this batch: the resident step kernel (no launch / stream sync per step).
+        import math
+
+        def host_loop(n, **kw):
+            for t in range(n):
+                env.step_host(host_actions[t % n_act], host_rew, host_end, obs_out=ring[t % slots], **kw)   # returns with the results on the host
+
+        def timed_host_loop(**kw):
+            host_loop(min(256, max(10, math.lcm(n_act, slots))), **kw)      # every (actions, ring slot) pair seen once: marshalling cached
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            host_loop(Ke, **kw)
+            el = time.perf_counter() - t0
+            env.sync()
+            t_e = torch.tensor([el], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+            return world * E * L * Ke / float(t_e.item())
+
+        srv0 = env.server_info()
+        e2e = {"value": timed_host_loop(), "unit": "agent-steps/s",
+               "h2d_bytes_per_step": E * L, "d2h_bytes_per_step": E * L * 4 + E, "steps": Ke}
+        srv1 = env.server_info()
+        resident = srv1["launches"] > srv0["launches"]
+        e2e["api"] = ("BatchedGridWorld.step_host (default" + (", resident step kernel): the kernel stays on the GPU between steps, "
+                      "takes each step's doorbell from pinned host memory, loads the actions from the pinned host buffer, stores rewards + "
+                      "ended flags into pinned host buffers over PCIe and signals completion through pinned host memory"
+                      if resident else "): one gw_step launch whose kernel loads the step's actions from the pinned host buffer and "
+                      "stores rewards + ended flags into pinned host buffers over PCIe, then a stream sync") +
+                      "; observations stay in HBM (replay ring)")
+        e2e["resident_kernel_launches"] = srv1["launches"] - srv0["launches"]
+        # the same call, one launch + stream sync per step (resident=False), and with cudaMemcpyAsync H2D / D2H around
+        # the kernel (zero_copy=False): reported aside
+        if resident:
+            e2e["launch_per_step_value"] = timed_host_loop(resident=False)
+        e2e["memcpy_value"] = timed_host_loop(zero_copy=False)
     del env, ring, r
 
     # ---- the same kernel at a batch that fills the GPU (the step kernel's roofline point), N = 1 only

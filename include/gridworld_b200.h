@@ -154,9 +154,23 @@ int gw_sync(gw_handle* h, void* stream);       /* cudaStreamSynchronize + surfac
  * runs gw_step, copies io->reward -> host_reward f32 [E, n_learners], io->shaped_reward -> host_shaped (nullable),
  * io->ended -> host_ended u8 [E] (nullable), and synchronises the stream.  One call, no Python between the stages.
  * zero_copy != 0: no memcpy nodes at all -- the kernel itself loads the actions from the pinned host buffer and stores
- * rewards / flags into the pinned host buffers over PCIe (unified addressing); same bytes, fewer stream operations. */
+ * rewards / flags into the pinned host buffers over PCIe (unified addressing); same bytes, fewer stream operations.
+ * zero_copy == GW_HOST_RESIDENT (2): as 1, but through a RESIDENT kernel (handles that use the small-batch kernel; larger
+ * ones fall back to 1).  The first call launches it on `stream`; it keeps the tables in shared memory, polls a doorbell
+ * in pinned host memory, steps, and reports completion through pinned host memory, so a step costs neither a launch nor
+ * a stream synchronisation.  On return the host buffers hold the step's results and the device outputs (observations,
+ * masks ...) are complete in HBM; work queued on `stream` runs once the resident kernel has left: at the next gw_* call
+ * on this handle other than gw_step_host(mode 2) (they all stop it first), at gw_server_stop, or by itself after
+ * GW_SERVER_IDLE_US (default 1000) microseconds without a step -- a later call relaunches it transparently. */
+#define GW_HOST_MEMCPY 0
+#define GW_HOST_ZERO_COPY 1
+#define GW_HOST_RESIDENT 2
 int gw_step_host(gw_handle* h, const gw_io* io, const int8_t* host_actions, float* host_reward, float* host_shaped,
                  uint8_t* host_ended, int zero_copy, void* stream);
+int gw_server_stop(gw_handle* h);                 /* no-op when the resident kernel is not running */
+/* running: 1 resident now, 0 not, -1 given up for this handle (kernel launches block in this process -- profiler,
+ * CUDA_LAUNCH_BLOCKING -- so mode 2 runs as mode 1); any pointer may be NULL */
+int gw_server_info(gw_handle* h, int* running, uint64_t* launches, uint64_t* relaunches, int* n_sets);
 
 /* packed env state (16 bytes/env) for checkpoint / resume; device or host destination */
 size_t gw_state_bytes(const gw_handle* h);

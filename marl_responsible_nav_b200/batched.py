@@ -225,15 +225,22 @@ class BatchedGridWorld:
 
     def step_host(self, host_actions: torch.Tensor, host_reward: torch.Tensor, host_ended: Optional[torch.Tensor] = None,
                   host_shaped: Optional[torch.Tensor] = None, obs_out: Optional[torch.Tensor] = None,
-                  zero_copy: bool = True) -> StepOutput:
+                  zero_copy: bool = True, resident: Optional[bool] = None) -> StepOutput:
         """Host-driven step in one library call (the reference's calling pattern, maddpg/agent.py:121-131): pinned int8
         actions [E, L] in, pinned f32 rewards [E, L] (and u8 ended [E], f32 shaped rewards) out, stream synchronised on
         return.  Observations and masks stay on the device.
         zero_copy (default): the kernel itself loads the actions from the pinned buffer and stores rewards / flags into
         the pinned buffers over PCIe; the returned StepOutput then carries the host tensors for those fields.
         zero_copy=False: cudaMemcpyAsync H2D / D2H around the kernel and device-side copies of the outputs as well.
+        resident (default: on for zero_copy with batches that use the small-batch kernel, <= 6144 envs): the step is
+        served by a kernel that stays on the GPU between calls (doorbell and completion word in pinned host memory, no
+        launch and no stream synchronisation per step; gridworld_b200.h, GW_HOST_RESIDENT).  The host buffers are valid
+        on return as before; GPU work queued behind it on the stream (reading obs, say) starts once the kernel has left:
+        at the next call of any other method of this object (`sync()` included), or by itself after 1 ms without a step.
         Argument checking and marshalling are done once per distinct set of buffers."""
         obs = obs_out if obs_out is not None else self.buf.obs
+        if zero_copy and (resident or (resident is None and self.num_envs <= 6144)):
+            zero_copy = 2
         key = (host_actions.data_ptr(), host_reward.data_ptr(), 0 if host_ended is None else host_ended.data_ptr(),
                0 if host_shaped is None else host_shaped.data_ptr(), obs.data_ptr(), zero_copy)
         cache = self.__dict__.setdefault("_host_calls", {})
@@ -268,10 +275,18 @@ class BatchedGridWorld:
         out = StepOutput(obs=self._view(obs), action_mask=b.action_mask, positions=b.positions, reward=pick(host_reward, b.reward),
                          shaped_reward=pick(host_shaped, b.shaped_reward), fear=b.fear, terminated=b.terminated,
                          truncated=b.truncated, ended=pick(host_ended, b.ended), info=b.info, obs_code=b.obs_code)
-        return (C.byref(io), p(host_actions), p(host_reward), p(host_shaped), p(host_ended), int(bool(zero_copy)), out, io)   # io kept alive
+        return (C.byref(io), p(host_actions), p(host_reward), p(host_shaped), p(host_ended), int(zero_copy), out, io)   # io kept alive
 
     def sync(self):
+        """Stream synchronisation (a resident step kernel is told to leave first)."""
         N.check(self.lib.gw_sync(self._h, self._stream()), self._h, "gw_sync")
+
+    def server_info(self) -> Dict[str, int]:
+        """Resident step kernel: running now, launches so far, relaunches after an idle exit, registered buffer sets."""
+        r, n = C.c_int(), C.c_int()
+        a, b = C.c_uint64(), C.c_uint64()
+        N.check(self.lib.gw_server_info(self._h, C.byref(r), C.byref(a), C.byref(b), C.byref(n)), self._h, "gw_server_info")
+        return {"running": int(r.value), "launches": int(a.value), "relaunches": int(b.value), "buffer_sets": int(n.value)}
 
     def stats(self) -> Dict[str, float]:
         s = N.GwStats()

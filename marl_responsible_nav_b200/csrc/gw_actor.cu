@@ -406,6 +406,7 @@ int gw_actor_forward(gw_actor* a, int64_t num_envs, const uint64_t* obs_code, co
                      uint64_t seed, uint64_t step, void* stream) {
   if (!a) return GW_EINVAL;
   gw_handle* h = a->h;
+  if (int rc = gw_server_stop(h)) return rc;           // a resident step kernel would hold this stream
   if (num_envs < 0 || !obs_code || !cont_actions || !action_ids) return gw_fail(h, GW_EINVAL, "gw_actor_forward: null argument");
   if (num_envs == 0) return GW_OK;
   GW_CUDA(h, cudaSetDevice(h->cfg.device));

@@ -2,13 +2,33 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include <cuda_runtime.h>
 
 #include "gw_device.cuh"
 
+// Resident step server (gw_step_host mode 2, gw_kernels.cu): mailboxes and the registered buffer sets.
+constexpr int GW_SRV_SETS = 1024;
+struct gw_server {
+  bool allocated = false, running = false, disabled = false;   // disabled: launches block here (profiler), see server_step
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  gw_io* h_stage = nullptr;                  // pinned staging of one table entry (same allocation as the doorbell)
+  unsigned long long* h_bell = nullptr;      // pinned host (one allocation): doorbell word ...
+  unsigned int* h_resp = nullptr;            // ... and, one cache line further, [0] completed seq [1] generation that has left
+  unsigned long long* d_bell = nullptr;      // device (one allocation): relay word, arrival counter
+  unsigned int* d_arrive = nullptr;
+  gw_io* d_io_table = nullptr;               // [GW_SRV_SETS]
+  std::vector<gw_io> sets;                   // host mirror of the table
+  int last_set = -1, blocked_starts = 0;
+  unsigned int seq = 0, generation = 0;
+  unsigned long long idle_ns = 1000000ull;
+  uint64_t launches = 0, relaunches = 0;
+};
+
 struct gw_handle {
   gw_config cfg;
+  gw_server srv;
   gw::Tables* d_tables = nullptr;
   uint4* d_rng_cache = nullptr;              // small-batch kernel: next step's random words per env (tagged)
   unsigned int* d_tile_ctr = nullptr;        // dynamic tile scheduling of the thread-per-env step kernel

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <ctime>
 #include <new>
 #include <string>
 
@@ -103,6 +104,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "bra GW_WAIT_LOOP;\n\t"
       "GW_WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity)
       : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
 // One thread issues two bulk copies: the lookup tables (sim + small, 15.6 KB) and `stage_rows` pre-replicated copies of
@@ -890,28 +902,42 @@ __device__ __forceinline__ void draw_step_randoms(const StepParams& p, long long
   chosen = spawn_choose(p, e, tick);
 }
 
-template <bool FEAR, int OBS>
-__global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
-  constexpr int THREADS = 256, TILE = 32;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
-  uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
-  trace_stamp(p, 0);
-  load_tables<TILE>(s, stage, p, 32, p.nl * p.H * GW_W * (OBS == GW_OBS_F32 ? 4 : 2));
-  trace_stamp(p, 3);
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+// One result array of a tile, shared memory -> (host or device) global memory: a single bulk copy when the destination
+// and the size allow it (16-byte granules), plain stores otherwise (tile tails, odd alignments).  Called by a whole warp.
+__device__ __forceinline__ void server_flush(void* gdst, const void* ssrc, int bytes, int lane) {
+  if (((reinterpret_cast<uintptr_t>(gdst) | (uintptr_t)bytes) & 15u) == 0) {
+    if (lane == 0 && bytes > 0) bulk_store_row(gdst, ssrc, bytes);
+  } else if (((reinterpret_cast<uintptr_t>(gdst) | (uintptr_t)bytes) & 3u) == 0) {
+    for (int i = lane; i < bytes / 4; i += 32) static_cast<uint32_t*>(gdst)[i] = static_cast<const uint32_t*>(ssrc)[i];
+  } else {
+    for (int i = lane; i < bytes; i += 32) static_cast<uint8_t*>(gdst)[i] = static_cast<const uint8_t*>(ssrc)[i];
+  }
+}
+
+// The step of the CTA's tiles (tile = blockIdx.x, += gridDim.x).  SERVER: called once per command by the resident kernel
+// below -- inputs that the host rewrites between two calls are loaded past the L1 (ordinary L2-level loads after the
+// system-scope acquire fence that follows the doorbell: `ld.volatile` reads of host memory are served one PCIe round
+// trip after the other, ~50 ns per request, measured 50-100 us per step at 4096 envs).
+template <bool FEAR, int OBS, bool SERVER>
+__device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& s, uint8_t* stage, bool& tables_pending) {
+  constexpr int TILE = 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = tid & 7, gsh = lane & 24;
   constexpr unsigned FULL = 0xFFFFFFFFu;     // every shuffle / ballot below is executed by the whole converged warp: a
                                              // part-warp mask would send each of them through the compiler's slow path
   const int n = p.n, nl = p.nl;
   const long long n_tiles = (p.E + TILE - 1) / TILE;
-  bool tables_pending = true;
   const int cpo = p.H * GW_W;
   const int Q = (OBS == GW_OBS_F32) ? cpo / 4 : cpo / 8;               // 16-byte vectors per learner observation
   const int V = nl * Q, row_bytes = V * 16;
   uint8_t* const rows4 = stage + (size_t)warp * 4 * row_bytes;         // this warp's staging rows
   uint8_t* const myrow = rows4 + (lane >> 3) * row_bytes;              // this group's env
-  if (p.pdl_early) asm volatile("griddepcontrol.launch_dependents;");
+  if (!SERVER && p.pdl_early) asm volatile("griddepcontrol.launch_dependents;");
+
+  // SERVER: rewards / shaped rewards / ended flags (the results the host reads) are collected per tile and leave as one
+  // bulk copy per array: written lane by lane into host memory they are ~12k small PCIe writes per step (measured: 40 us).
+  __shared__ __align__(16) float out_rew[SERVER ? TILE * GW_MAX_LEARNERS : 1], out_shp[SERVER ? TILE * GW_MAX_LEARNERS : 1];
+  __shared__ __align__(16) uint8_t out_end[SERVER ? TILE : 1];
+  __shared__ __align__(16) int8_t act_s[SERVER ? TILE * GW_MAX_LEARNERS + 16 : 16];   // SERVER: the tile's learner actions, fetched once
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long tile_base = tile * TILE;
@@ -919,11 +945,25 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
     const int el = tid >> 3;
     const long long e = tile_base + el;
     const bool own = el < tile_envs;
+    if (SERVER && tile != (long long)blockIdx.x) {                      // the previous tile's result copies have read the staging
+      if (tid == 0) bulk_wait_read<0>();
+      __syncthreads();
+    }
 
     // ================================================================= loads and RNG (no table needed)
     uint4 st = make_uint4(0, 0, 0, 0);
     uint32_t la = 0, npc_a = 0, chosen = 0;
     uint32_t rw[4] = {0, 0, 0, 0}, rw2[4] = {0, 0, 0, 0};
+    bool act_staged = false;
+    if (SERVER) {
+      // The actions come out of pinned HOST memory: fetched lane by lane, the tile's 64 bytes turn into 16 read requests
+      // per CTA and the PCIe read queue becomes the step's critical path (measured: CTAs finish 5-8 us apart).  A few
+      // lanes fetch them in 16-byte pieces instead; the state loads below overlap the round trip.
+      const int8_t* ap = p.io.learner_actions + tile_base * nl;
+      act_staged = (reinterpret_cast<uintptr_t>(ap) & 15u) == 0;       // CTA-uniform
+      if (act_staged && tid < (tile_envs * nl + 15) / 16)
+        reinterpret_cast<uint4*>(act_s)[tid] = __ldcg(reinterpret_cast<const uint4*>(ap) + tid);   // stays inside the last 16-byte granule
+    }
     if (own) {
       st = p.state[e];
       // The random words of this step were drawn at the end of the previous one (they only depend on seed, env id and
@@ -932,8 +972,9 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
       if (p.rng_cache != nullptr) { c0 = p.rng_cache[2 * e]; c1 = p.rng_cache[2 * e + 1]; }
 #pragma unroll
       for (int k = 0; k < GW_MAX_LEARNERS; ++k)
-        if (k < nl) la |= (uint32_t)min(max((int)p.io.learner_actions[e * nl + k], 0), 8) << (4 * k);
-      if (p.io.npc_actions != nullptr && r < 4 && r >= nl && r < n) npc_a = (uint32_t)min(max((int)p.io.npc_actions[e * n + r], 0), 8);
+        if (k < nl && !act_staged) la |= (uint32_t)min(max((int)(SERVER ? __ldcg(p.io.learner_actions + e * nl + k) : p.io.learner_actions[e * nl + k]), 0), 8) << (4 * k);
+      if (p.io.npc_actions != nullptr && r < 4 && r >= nl && r < n)
+        npc_a = (uint32_t)min(max((int)(SERVER ? __ldcg(p.io.npc_actions + e * n + r) : p.io.npc_actions[e * n + r]), 0), 8);
       if (c1.w == st.z) {
         rw[0] = c0.x; rw[1] = c0.y; rw[2] = c0.z; rw[3] = c0.w;
         rw2[0] = c1.x; rw2[1] = c1.y;
@@ -941,6 +982,12 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
       } else {
         draw_step_randoms(p, e, st.z, n - nl > 2, rw, rw2, chosen);
       }
+    }
+    if (SERVER && act_staged) {
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < GW_MAX_LEARNERS; ++k)
+        if (k < nl && own) la |= (uint32_t)min(max((int)act_s[el * nl + k], 0), 8) << (4 * k);
     }
     trace_stamp(p, 5);
     if (tables_pending) {
@@ -1071,12 +1118,18 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
         v_end = ended ? 1u : 0u; v_len = ended ? steps_now : 0u; v_cr = ro.crash_count; v_ap = ro.apples_rewarded;
         v_ret = ended ? (ret0 + ret1) : 0;
       }
-      if (r < nl && own && p.io.reward) p.io.reward[e * nl + r] = (float)my_reward;
+      if (r < nl && own && p.io.reward) {
+        if (SERVER) out_rew[el * nl + r] = (float)my_reward;
+        else p.io.reward[e * nl + r] = (float)my_reward;
+      }
       if (r == 1 && own) write_positions(p.io.positions, e, n, cells_new);
       if (r == 2 && own && p.io.info)
         p.io.info[e] = (crash & 15u) | ((restr & 15u) << 4) | (ro.crash_count << 8) | (ro.apples_rewarded << 10) |
                        ((ended ? 1u : 0u) << 12) | (ro.shaped << 14);
-      if (r == 3 && own && p.io.ended) p.io.ended[e] = ended ? 1 : 0;
+      if (r == 3 && own && p.io.ended) {
+        if (SERVER) out_end[el] = ended ? 1 : 0;
+        else p.io.ended[e] = ended ? 1 : 0;
+      }
       if (r >= 4 && r < 4 + nl && own) {
         if (p.io.terminated) p.io.terminated[e * nl + (r - 4)] = (uint8_t)((ro.term_now >> (r - 4)) & 1u);
         if (p.io.truncated) p.io.truncated[e * nl + (r - 4)] = (uint8_t)((ro.trunc_now >> (r - 4)) & 1u);
@@ -1201,15 +1254,29 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
       if (r < nl && own) {
         const double f = (r == 0) ? fear0 : fear1;
         if (p.io.fear) p.io.fear[e * nl + r] = f;
-        if (p.io.shaped_reward) p.io.shaped_reward[e * nl + r] = (float)(p.fear_weight * f + my_reward);   // maddpg/agent.py:130
+        if (p.io.shaped_reward) {
+          const float sh = (float)(p.fear_weight * f + my_reward);                                        // maddpg/agent.py:130
+          if (SERVER) out_shp[el * nl + r] = sh;
+          else p.io.shaped_reward[e * nl + r] = sh;
+        }
       }
     }
     trace_stamp(p, 2);
+    if (SERVER) {
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (warp == 0) {
+        const int nr = tile_envs * nl;
+        if (p.io.reward) server_flush(p.io.reward + tile_base * nl, out_rew, nr * 4, lane);
+        if (p.io.shaped_reward) server_flush(p.io.shaped_reward + tile_base * nl, out_shp, nr * 4, lane);
+        if (p.io.ended) server_flush(p.io.ended + tile_base, out_end, tile_envs, lane);
+      }
+    }
 
     // ================================================================= observations of the warp's own four envs
     // Every lane drops its special cells into its env's staging row, the four rows (contiguous, like the four
     // observations in HBM) leave as 128-bit streaming stores, and the cells are set back to the template's 0.
-    if (!p.pdl_early && tile + gridDim.x >= n_tiles) asm volatile("griddepcontrol.launch_dependents;");
+    if (!SERVER && !p.pdl_early && tile + gridDim.x >= n_tiles) asm volatile("griddepcontrol.launch_dependents;");
     if (p.io.obs != nullptr) {
       patch_cell<OBS>(myrow, enc0, true);
       patch_cell<OBS>(myrow, enc1, true);
@@ -1269,7 +1336,144 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
     __syncwarp();                                                      // s.spec / s.rinfo of this warp are rewritten by the next tile
     trace_stamp(p, 7);
   }
+}
+
+template <bool FEAR, int OBS>
+__global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
+  constexpr int TILE = 32;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
+  uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
+  trace_stamp(p, 0);
+  load_tables<TILE>(s, stage, p, 32, p.nl * p.H * GW_W * (OBS == GW_OBS_F32 ? 4 : 2));
+  trace_stamp(p, 3);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  bool tables_pending = true;
+  small_step_tiles<FEAR, OBS, false>(p, s, stage, tables_pending);
   if (tables_pending) tables_wait(s);                                  // a CTA without tiles must not exit with copies in flight
+}
+
+// ------------------------------------------------------------------ resident step server (gw_step_host, mode 2)
+// A host-driven step costs a kernel launch and a stream synchronisation on top of the kernel (about 20 of the 29 us per
+// step at 4096 envs).  The resident kernel stays on the SMs between steps instead: tables and staging rows are loaded
+// once, CTA 0 polls a doorbell word in pinned host memory and relays it through a word in device memory, every CTA
+// steps its tiles (same code as gw_step_small_kernel), and the last CTA to finish writes the step's sequence number
+// into pinned host memory, where the host spins on it.  Liveness: only CTA 0 decides to leave (STOP from the host, or
+// no doorbell for idle_ns) and says so in device memory (for the other CTAs) and in host memory (for the host, which
+// relaunches and rings again if its doorbell crossed the exit).  The grid is sized to be co-resident.
+struct ServerParams {
+  const unsigned long long* host_bell;   // pinned host: (seq << 32) | (op << 16) | buffer set
+  unsigned int* host_resp;               // pinned host: [0] last completed seq, [1] generation of the launch that has left
+  unsigned long long* dev_bell;          // device relay of the doorbell word
+  unsigned int* dev_arrive;              // CTAs done, monotonic within a launch
+  const gw_io* io_table;                 // device: the registered buffer sets
+  unsigned int first_seq, generation;
+  unsigned long long idle_ns;
+};
+enum { SRV_OP_STEP = 1, SRV_OP_STOP = 2, SRV_OP_EXIT = 3 };
+
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_volatile_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <bool FEAR, int OBS>
+__global__ void __launch_bounds__(256, 2) gw_step_server_kernel(StepParams p, ServerParams sp) {
+  constexpr int TILE = 32;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
+  uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
+  __shared__ unsigned long long cmd_s;
+  __shared__ __align__(16) unsigned long long io_s[(sizeof(gw_io) + 7) / 8];
+  load_tables<TILE>(s, stage, p, 32, p.nl * p.H * GW_W * (OBS == GW_OBS_F32 ? 4 : 2));
+  tables_wait(s);
+  unsigned int seq = sp.first_seq, rounds = 0;
+#ifdef GW_ENABLE_TRACE
+  unsigned long long tr_acc[5] = {0, 0, 0, 0, 0}, tr_t = 0;   // thread 0: time in wait / table entry / step / drain / arrive
+#define SRV_TRACE(k) do { if (threadIdx.x == 0) { const unsigned long long n_ = global_ns(); tr_acc[k] += n_ - tr_t; tr_t = n_; } } while (0)
+#else
+#define SRV_TRACE(k) do { } while (0)
+#endif
+  for (;;) {
+#ifdef GW_ENABLE_TRACE
+    if (threadIdx.x == 0) tr_t = global_ns();
+#endif
+    if (threadIdx.x == 0) {
+      unsigned long long w;
+      const unsigned long long t0 = global_ns();
+      if (blockIdx.x == 0) {
+        for (;;) {
+          w = ld_volatile_u64(sp.host_bell);
+          if ((unsigned int)(w >> 32) == seq) break;
+          if (global_ns() - t0 > sp.idle_ns) { w = ((unsigned long long)seq << 32) | ((unsigned long long)SRV_OP_EXIT << 16); break; }
+        }
+        asm volatile("fence.acq_rel.sys;" ::: "memory");               // what the host wrote before ringing is visible from here on
+        st_volatile_u64(sp.dev_bell, w);
+      } else {
+        for (;;) {
+          w = ld_volatile_u64(sp.dev_bell);
+          const int ahead = (int)((unsigned int)(w >> 32) - seq);
+          if (ahead == 0) break;
+          // never taken while CTA 0 lives (it always relays an exit); a CTA that only became resident after the others
+          // had left finds a later exit word, and the time bound keeps a fault elsewhere from turning into a hang
+          if ((ahead > 0 && ((w >> 16) & 0xFFu) != SRV_OP_STEP) || global_ns() - t0 > 4ull * sp.idle_ns + 2000000000ull) {
+            w = (unsigned long long)SRV_OP_EXIT << 16;
+            break;
+          }
+        }
+        // acquire at GPU scope: CTA 0 acquired the host's writes at system scope before it relayed the word (causality is
+        // transitive), and system-scope fences issued by every CTA are served one after the other (~50 ns each, measured)
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      }
+      cmd_s = w;
+    }
+    __syncthreads();
+    const unsigned long long w = cmd_s;
+    if (((w >> 16) & 0xFFu) != SRV_OP_STEP) break;
+    SRV_TRACE(0);
+    if (threadIdx.x < (int)((sizeof(gw_io) + 7) / 8))
+      io_s[threadIdx.x] = __ldcv(reinterpret_cast<const unsigned long long*>(sp.io_table + (w & 0xFFFFu)) + threadIdx.x);
+    __syncthreads();
+    StepParams q = p;
+    q.io = *reinterpret_cast<const gw_io*>(io_s);
+    bool tables_pending = false;
+    SRV_TRACE(1);
+    small_step_tiles<FEAR, OBS, true>(q, s, stage, tables_pending);
+    SRV_TRACE(2);
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // this thread's observation rows have landed
+    __syncthreads();
+    SRV_TRACE(3);
+    if (threadIdx.x == 0) {
+      // Release at GPU scope per CTA (cumulative over what the barrier ordered before it), one system-scope fence by the
+      // last CTA before the completion word: fences are cumulative, so it covers every CTA's stores into host memory.
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      const unsigned int prev = atomicAdd(sp.dev_arrive, 1u);
+      if (prev == gridDim.x * (rounds + 1u) - 1u) {                    // last CTA of this step
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        st_volatile_u32(sp.host_resp, seq);
+      }
+    }
+    SRV_TRACE(4);
+    ++seq;
+    ++rounds;
+  }
+#ifdef GW_ENABLE_TRACE
+  if (threadIdx.x == 0 && p.trace != nullptr) {
+    for (int k = 0; k < 5; ++k) p.trace[(size_t)blockIdx.x * 16 + k] = tr_acc[k];   // this launch only
+    p.trace[(size_t)blockIdx.x * 16 + 5] = rounds;
+  }
+#endif
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    st_volatile_u32(sp.host_resp + 1, sp.generation);
+  }
 }
 
 static inline size_t stage_row_bytes(const gw_config& c) {
@@ -1764,9 +1968,14 @@ int gw_create(const gw_config* cfg, gw_handle** out) {
   return GW_OK;
 }
 
+static int server_stop(gw_handle* h);
+static void server_free(gw_handle* h);
+
 int gw_destroy(gw_handle* h) {
   if (!h) return GW_OK;
   cudaSetDevice(h->cfg.device);
+  server_stop(h);
+  server_free(h);
   if (h->d_tables) cudaFree(h->d_tables);
   if (h->d_stage_init) cudaFree(h->d_stage_init);
   if (h->d_tile_ctr) cudaFree(h->d_tile_ctr);
@@ -1925,10 +2134,209 @@ static void launch_reset_t(const gw_config& c, const gw::StepParams& p, unsigned
   else launch_k(gw::gw_reset_kernel<THREADS, TILE, GW_OBS_BF16>, p, blocks, THREADS, smem, s);
 }
 
+// ---- resident step server, host side -------------------------------------------------------------------------------
+static inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#elif defined(__aarch64__)
+  asm volatile("yield" ::: "memory");
+#endif
+}
+static inline double wall_s() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+static inline unsigned int host_load_u32(const unsigned int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+
+static void server_free(gw_handle* h) {
+  gw_server& v = h->srv;
+  if (v.h_bell) cudaFreeHost(v.h_bell);
+  if (v.d_bell) cudaFree(v.d_bell);
+  if (v.d_io_table) cudaFree(v.d_io_table);
+  if (v.copy_stream) cudaStreamDestroy(v.copy_stream);
+  v = gw_server();
+}
+
+static int server_alloc(gw_handle* h) {
+  gw_server& v = h->srv;
+  if (v.allocated) return GW_OK;
+  void* hp = nullptr;
+  GW_CUDA(h, cudaHostAlloc(&hp, 512, cudaHostAllocPortable | cudaHostAllocMapped));
+  std::memset(hp, 0, 512);
+  v.h_bell = static_cast<unsigned long long*>(hp);
+  v.h_resp = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(hp) + 128);
+  v.h_stage = reinterpret_cast<gw_io*>(static_cast<uint8_t*>(hp) + 256);
+  GW_CUDA(h, cudaStreamCreateWithFlags(&v.copy_stream, cudaStreamNonBlocking));
+  void* dp = nullptr;
+  GW_CUDA(h, cudaMalloc(&dp, 256));
+  GW_CUDA(h, cudaMemset(dp, 0, 256));
+  v.d_bell = static_cast<unsigned long long*>(dp);
+  v.d_arrive = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(dp) + 128);
+  GW_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&v.d_io_table), sizeof(gw_io) * GW_SRV_SETS));
+  if (const char* e = std::getenv("GW_SERVER_IDLE_US")) {
+    const long long us = std::atoll(e);
+    if (us > 0) v.idle_ns = (unsigned long long)us * 1000ull;
+  }
+  v.sets.reserve(64);
+  v.allocated = true;
+  return GW_OK;
+}
+
+// The resident kernel leaves (STOP, or it had already left after idle_ns without a doorbell).  Everything it wrote is
+// visible to later work on any stream once this returns.
+static int server_stop(gw_handle* h) {
+  gw_server& v = h->srv;
+  if (!v.running) return GW_OK;
+  v.running = false;
+  v.seq += 1;
+  __atomic_store_n(v.h_bell, ((unsigned long long)v.seq << 32) | ((unsigned long long)gw::SRV_OP_STOP << 16), __ATOMIC_RELEASE);
+  GW_CUDA(h, cudaStreamSynchronize(v.stream));     // bounded: CTA 0 answers within a poll, and gives up by itself after idle_ns
+  if (host_load_u32(v.h_resp + 1) != v.generation) return fail(h, GW_ECUDA, "step server ended without signing off");
+  return GW_OK;
+}
+
+template <typename K>
+static void launch_server_k(K kernel, const gw::StepParams& p, const gw::ServerParams& sp, unsigned blocks, size_t smem, cudaStream_t s) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kernel<<<blocks, 256, smem, s>>>(p, sp);
+}
+
+static int server_start(gw_handle* h, cudaStream_t s, unsigned int first_seq) {
+  gw_server& v = h->srv;
+  const gw_config& c = h->cfg;
+  GW_CUDA(h, use_device(c.device));
+  v.generation += 1;
+  if (v.generation == 0) v.generation = 1;
+  __atomic_store_n(v.h_resp + 1, 0u, __ATOMIC_RELEASE);
+  GW_CUDA(h, cudaMemsetAsync(v.d_bell, 0, 256, s));
+  gw::StepParams p = make_params(h, nullptr);
+  p.pdl_early = 0;
+  gw::ServerParams sp;
+  sp.host_bell = v.h_bell; sp.host_resp = v.h_resp; sp.dev_bell = v.d_bell; sp.dev_arrive = v.d_arrive;
+  sp.io_table = v.d_io_table; sp.first_seq = first_seq; sp.generation = v.generation; sp.idle_ns = v.idle_ns;
+  const long long n_tiles = (c.num_envs + 31) / 32, resident = (long long)h->sm_count * 2;   // __launch_bounds__(256, 2), < 114 KB each
+  const unsigned blocks = (unsigned)(n_tiles < resident ? n_tiles : resident);
+  const size_t smem = gw::smem_fixed_bytes<32>() + (size_t)8 * 4 * gw::stage_row_bytes(c);
+  const bool f32 = c.obs_dtype == GW_OBS_F32;
+  if (c.fear) {
+    if (f32) launch_server_k(gw::gw_step_server_kernel<true, GW_OBS_F32>, p, sp, blocks, smem, s);
+    else launch_server_k(gw::gw_step_server_kernel<true, GW_OBS_BF16>, p, sp, blocks, smem, s);
+  } else {
+    if (f32) launch_server_k(gw::gw_step_server_kernel<false, GW_OBS_F32>, p, sp, blocks, smem, s);
+    else launch_server_k(gw::gw_step_server_kernel<false, GW_OBS_BF16>, p, sp, blocks, smem, s);
+  }
+  GW_CUDA(h, cudaGetLastError());
+  // a kernel that has already left when its launch returns sat out its idle time inside the launch call
+  v.blocked_starts = (host_load_u32(v.h_resp + 1) == v.generation) ? v.blocked_starts + 1 : 0;
+  v.running = true;
+  v.stream = s;
+  v.launches += 1;
+  h->launches += 1;
+  return GW_OK;
+}
+
+// index of this buffer set in the device table (registered on first sight)
+static int server_set_index(gw_handle* h, const gw_io& z, int* out) {
+  gw_server& v = h->srv;
+  if (v.last_set >= 0 && std::memcmp(&v.sets[v.last_set], &z, sizeof(gw_io)) == 0) { *out = v.last_set; return GW_OK; }
+  const int n = (int)v.sets.size();
+  for (int k = 1; k <= n; ++k) {                    // callers cycle through their buffers: look just after the last hit first
+    const int i = (v.last_set + k + n) % n;
+    if (std::memcmp(&v.sets[i], &z, sizeof(gw_io)) == 0) { *out = v.last_set = i; return GW_OK; }
+  }
+  if (n >= GW_SRV_SETS) {                           // full: start over (entries in use must not change under the kernel)
+    if (int rc = server_stop(h)) return rc;
+    v.sets.clear();
+  }
+  // Appending is safe while the kernel runs (no doorbell names the new entry yet); the copy goes through its own
+  // stream, since anything on the kernel's stream would wait for the kernel.
+  const int i = (int)v.sets.size();
+  v.sets.push_back(z);
+  std::memcpy(v.h_stage, &z, sizeof(gw_io));
+  GW_CUDA(h, cudaMemcpyAsync(v.d_io_table + i, v.h_stage, sizeof(gw_io), cudaMemcpyHostToDevice, v.copy_stream));
+  GW_CUDA(h, cudaStreamSynchronize(v.copy_stream));
+  *out = v.last_set = i;
+  return GW_OK;
+}
+
+constexpr int SRV_RETRY_PLAIN = 1;     // server_step: not served, take the launch-per-step path
+
+static int server_step(gw_handle* h, const gw_io& z, cudaStream_t s) {
+  gw_server& v = h->srv;
+  if (v.blocked_starts >= 2) {
+    // Launches do not return while the kernel runs (a profiler or CUDA_LAUNCH_BLOCKING serialises them): every step
+    // would cost two idle periods.  This handle goes back to one launch per step.
+    v.disabled = true;
+    return SRV_RETRY_PLAIN;
+  }
+  if (int rc = server_alloc(h)) return rc;
+  int set = 0;
+  if (int rc = server_set_index(h, z, &set)) return rc;
+  if (v.running && v.stream != s)
+    if (int rc = server_stop(h)) return rc;
+  if (v.seq >= 0xFFFFFF00u) {                        // sequence numbers are 32 bits: start over
+    if (int rc = server_stop(h)) return rc;
+    v.seq = 0;
+    __atomic_store_n(v.h_bell, 0ull, __ATOMIC_RELEASE);
+    __atomic_store_n(v.h_resp, 0u, __ATOMIC_RELEASE);
+  }
+  const unsigned int seq = ++v.seq;
+  if (!v.running)
+    if (int rc = server_start(h, s, seq)) return rc;
+  __atomic_store_n(v.h_bell, ((unsigned long long)seq << 32) | ((unsigned long long)gw::SRV_OP_STEP << 16) | (unsigned long long)set,
+                   __ATOMIC_RELEASE);
+  double t0 = 0.0;
+  int starts = 0;
+  for (unsigned long long spins = 1;; ++spins) {
+    if (host_load_u32(v.h_resp) == seq) break;
+    if (host_load_u32(v.h_resp + 1) == v.generation) {
+      // the kernel left (idle) -- either before it saw this doorbell, or right after completing it
+      v.running = false;
+      GW_CUDA(h, cudaStreamSynchronize(s));
+      if (host_load_u32(v.h_resp) == seq) break;
+      if (++starts > 2) {                       // keeps leaving before it sees the doorbell: one launch per step from now on
+        v.disabled = true;                      // (nothing of this step has run: CTA 0 alone accepts a doorbell, and it did not)
+        return SRV_RETRY_PLAIN;
+      }
+      v.relaunches += 1;
+      if (int rc = server_start(h, s, seq)) return rc;   // the doorbell still rings
+      t0 = 0.0;
+      continue;
+    }
+    if ((spins & 0x3FFFu) == 0) {
+      const double now = wall_s();
+      if (t0 == 0.0) t0 = now;
+      const cudaError_t q = cudaStreamQuery(s);
+      if (q != cudaErrorNotReady && q != cudaSuccess) { v.running = false; return cuda_fail(h, q, "step server"); }
+      if (now - t0 > 10.0) { v.running = false; return fail(h, GW_ECUDA, "step server: no completion within 10 s"); }
+    }
+    cpu_relax();
+  }
+  h->env_steps += (uint64_t)h->cfg.num_envs;
+  return GW_OK;
+}
+
 extern "C" {
+
+int gw_server_stop(gw_handle* h) {
+  if (!h) return GW_EINVAL;
+  return server_stop(h);
+}
+
+int gw_server_info(gw_handle* h, int* running, uint64_t* launches, uint64_t* relaunches, int* n_sets) {
+  if (!h) return GW_EINVAL;
+  gw_server& v = h->srv;
+  if (running) *running = v.disabled ? -1 : ((v.running && host_load_u32(v.h_resp + 1) != v.generation) ? 1 : 0);
+  if (launches) *launches = v.launches;
+  if (relaunches) *relaunches = v.relaunches;
+  if (n_sets) *n_sets = (int)v.sets.size();
+  return GW_OK;
+}
 
 int gw_reset(gw_handle* h, const uint8_t* reset_mask, const gw_io* io, void* stream) {
   if (!h) return GW_EINVAL;
+  if (int rc = server_stop(h)) return rc;
   if (int rc = check_io(h, io, false)) return rc;
   if (!h->reset_done && reset_mask) return fail(h, GW_ESTATE, "gw_reset: the first reset must cover all envs (reset_mask = NULL)");
   GW_CUDA(h, cudaSetDevice(h->cfg.device));
@@ -1948,6 +2356,7 @@ int gw_reset(gw_handle* h, const uint8_t* reset_mask, const gw_io* io, void* str
 
 int gw_step(gw_handle* h, const gw_io* io, void* stream) {
   if (!h) return GW_EINVAL;
+  if (int rc = server_stop(h)) return rc;
   if (int rc = check_io(h, io, true)) return rc;
   if (!h->reset_done) return fail(h, GW_ESTATE, "gw_step: call gw_reset first");
   GW_CUDA(h, use_device(h->cfg.device));
@@ -1979,6 +2388,12 @@ int gw_step_host(gw_handle* h, const gw_io* io, const int8_t* host_actions, floa
     if (host_reward) z.reward = host_reward;
     if (host_shaped) z.shaped_reward = host_shaped;
     if (host_ended) z.ended = host_ended;
+    if (zero_copy == GW_HOST_RESIDENT && pick_small(h->cfg.num_envs) && !h->srv.disabled) {
+      if (int rc = check_io(h, &z, true)) return rc;
+      if (!h->reset_done) return fail(h, GW_ESTATE, "gw_step_host: call gw_reset first");
+      const int rc = server_step(h, z, static_cast<cudaStream_t>(stream));
+      if (rc != SRV_RETRY_PLAIN) return rc;
+    }
     if (int rc = gw_step(h, &z, stream)) return rc;
     GW_CUDA(h, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     return GW_OK;
@@ -2000,6 +2415,7 @@ int gw_step_host(gw_handle* h, const gw_io* io, const int8_t* host_actions, floa
 
 int gw_sync(gw_handle* h, void* stream) {
   if (!h) return GW_EINVAL;
+  if (int rc = server_stop(h)) return rc;
   GW_CUDA(h, cudaSetDevice(h->cfg.device));
   GW_CUDA(h, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   GW_CUDA(h, cudaGetLastError());
@@ -2010,6 +2426,7 @@ size_t gw_state_bytes(const gw_handle* h) { return h ? sizeof(uint4) * (size_t)h
 
 int gw_get_state(gw_handle* h, void* dst, int dst_is_device, void* stream) {
   if (!h || !dst) return fail(h, GW_EINVAL, "gw_get_state: null argument");
+  if (int rc = server_stop(h)) return rc;
   GW_CUDA(h, cudaSetDevice(h->cfg.device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   GW_CUDA(h, cudaMemcpyAsync(dst, h->d_state, gw_state_bytes(h), dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
@@ -2019,6 +2436,7 @@ int gw_get_state(gw_handle* h, void* dst, int dst_is_device, void* stream) {
 
 int gw_set_state(gw_handle* h, const void* src, int src_is_device, void* stream) {
   if (!h || !src) return fail(h, GW_EINVAL, "gw_set_state: null argument");
+  if (int rc = server_stop(h)) return rc;
   GW_CUDA(h, cudaSetDevice(h->cfg.device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   GW_CUDA(h, cudaMemcpyAsync(h->d_state, src, gw_state_bytes(h), src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
@@ -2029,6 +2447,7 @@ int gw_set_state(gw_handle* h, const void* src, int src_is_device, void* stream)
 
 int gw_get_stats(gw_handle* h, gw_stats* out, void* stream) {
   if (!h || !out) return fail(h, GW_EINVAL, "gw_get_stats: null argument");
+  if (int rc = server_stop(h)) return rc;
   GW_CUDA(h, cudaSetDevice(h->cfg.device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   static_assert(sizeof(unsigned long long) == 8, "");
@@ -2063,6 +2482,7 @@ int gw_get_stats(gw_handle* h, gw_stats* out, void* stream) {
 
 int gw_reset_stats(gw_handle* h, void* stream) {
   if (!h) return GW_EINVAL;
+  if (int rc = server_stop(h)) return rc;
   GW_CUDA(h, cudaSetDevice(h->cfg.device));
   GW_CUDA(h, cudaMemsetAsync(h->d_stats, 0, sizeof(unsigned long long) * gw::STAT_SLOTS * 8, static_cast<cudaStream_t>(stream)));
   h->env_steps = 0;
@@ -2072,6 +2492,7 @@ int gw_reset_stats(gw_handle* h, void* stream) {
 // dev only: GW_TRACE=1 makes gw_create allocate a per-CTA stamp buffer; gw_debug_trace copies it out (16 x uint64 per CTA)
 int gw_debug_trace(gw_handle* h, unsigned long long* host_out, int max_ctas) {
   if (!h || !h->d_trace || !host_out) return GW_EINVAL;
+  if (int rc = server_stop(h)) return rc;
   GW_CUDA(h, cudaSetDevice(h->cfg.device));
   GW_CUDA(h, cudaDeviceSynchronize());
   GW_CUDA(h, cudaMemcpy(host_out, h->d_trace, sizeof(unsigned long long) * 16 * (size_t)max_ctas, cudaMemcpyDeviceToHost));
@@ -2088,6 +2509,7 @@ int gw_update_world(gw_handle* h, int64_t n_cases, const int8_t* n_per, const in
                     const int8_t* apples, int8_t* new_positions, uint8_t* crash, uint8_t* restricted, int8_t* caught,
                     void* stream) {
   if (!h) return GW_EINVAL;
+  if (int rc = server_stop(h)) return rc;
   if (n_cases < 0 || !positions || !actions || !new_positions || !crash || !restricted)
     return fail(h, GW_EINVAL, "gw_update_world: null/invalid argument");
   if (n_cases == 0) return GW_OK;
@@ -2104,6 +2526,7 @@ int gw_update_world(gw_handle* h, int64_t n_cases, const int8_t* n_per, const in
 int gw_fear_matrix(gw_handle* h, int64_t n_cases, const int8_t* n_per, const int8_t* positions, const int8_t* actions,
                    const int8_t* mdr, const uint8_t* in_list, double* resp, int8_t* n_mdr, int8_t* n_act, void* stream) {
   if (!h) return GW_EINVAL;
+  if (int rc = server_stop(h)) return rc;
   if (n_cases < 0 || !positions || !actions || !mdr || !resp || !n_mdr || !n_act)
     return fail(h, GW_EINVAL, "gw_fear_matrix: null/invalid argument");
   if (n_cases == 0) return GW_OK;
@@ -2119,6 +2542,7 @@ int gw_fear_matrix(gw_handle* h, int64_t n_cases, const int8_t* n_per, const int
 int gw_feal(gw_handle* h, int64_t n_cases, const int8_t* n_per, const int8_t* positions, const int8_t* actions,
             const int8_t* mdr, const uint8_t* in_list, double* feal, int8_t* n_mdr, int8_t* n_act, void* stream) {
   if (!h) return GW_EINVAL;
+  if (int rc = server_stop(h)) return rc;
   if (n_cases < 0 || !positions || !actions || !mdr || !feal || !n_mdr || !n_act)
     return fail(h, GW_EINVAL, "gw_feal: null/invalid argument");
   if (n_cases == 0) return GW_OK;
@@ -2135,6 +2559,7 @@ int gw_fear_one_actor(gw_handle* h, int64_t n_cases, const int8_t* n_per, const 
                       const int8_t* mdr, const int8_t* actor, const uint8_t* in_list, double* resp, int8_t* n_mdr,
                       int8_t* n_act, void* stream) {
   if (!h) return GW_EINVAL;
+  if (int rc = server_stop(h)) return rc;
   if (n_cases < 0 || !positions || !actions || !mdr || !actor || !resp)
     return fail(h, GW_EINVAL, "gw_fear_one_actor: null/invalid argument");
   if (n_cases == 0) return GW_OK;

@@ -19,8 +19,12 @@ def timeit(f, k=K):
     for i in range(k): f(i)
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / k * 1e6
-print("step_host memcpy   : %.2f us" % timeit(lambda i: env.step_host(ha[i % 64], hr, he)))
-print("step_host zero-copy: %.2f us" % timeit(lambda i: env.step_host(ha[i % 64], hr, he, zero_copy=True)))
+print("step_host memcpy   : %.2f us" % timeit(lambda i: env.step_host(ha[i % 64], hr, he, zero_copy=False)))
+print("step_host zero-copy: %.2f us" % timeit(lambda i: env.step_host(ha[i % 64], hr, he, zero_copy=True, resident=False)))
+for i in range(64): env.step_host(ha[i], hr, he, resident=True)
+print("step_host resident : %.2f us" % timeit(lambda i: env.step_host(ha[i % 64], hr, he, resident=True)))
+print("  server:", env.server_info())
+env.sync()
 # raw library call with prebuilt arguments
 io = env._io(env.buf.obs, None, env._host_act_dev, None, None)
 ioref = C.byref(io)
@@ -28,6 +32,8 @@ pa = [C.c_void_p(ha[i].data_ptr()) for i in range(64)]
 pr, pe = C.c_void_p(hr.data_ptr()), C.c_void_p(he.data_ptr())
 st = env._stream()
 lib, h = env.lib, env._h
+print("raw gw_step_host resident : %.2f us" % timeit(lambda i: lib.gw_step_host(h, ioref, pa[i % 64], pr, None, pe, 2, st)))
+env.sync()
 print("raw gw_step_host zero-copy: %.2f us" % timeit(lambda i: lib.gw_step_host(h, ioref, pa[i % 64], pr, None, pe, 1, st)))
 print("raw gw_step_host memcpy   : %.2f us" % timeit(lambda i: lib.gw_step_host(h, ioref, pa[i % 64], pr, None, pe, 0, st)))
 da = torch.randint(0, 9, (E, L), dtype=torch.int8, device="cuda")

@@ -260,3 +260,93 @@ def test_step_host_matches_device_step():
     assert st["fear_tasks"] > 0 and st["fear_tasks"] == b.stats()["fear_tasks"]
     with pytest.raises(ValueError):
         a.step_host(acts[0].clone(), rew, end)          # not pinned
+
+
+@pytest.mark.parametrize("E,fear,bf16", [(4096, True, False), (1001, True, True), (6144, False, False), (77, True, False)])
+def test_step_host_resident_kernel(E, fear, bf16):
+    """gw_step_host mode 2 (resident kernel: doorbell / completion word in pinned host memory) == gw_step, step after
+    step and in the final state; survives idle exits, relaunches, and other calls in between."""
+    import time
+    import torch
+    from marl_responsible_nav_b200 import BatchedGridWorld
+    kw = dict(num_envs=E, fear=fear, fear_weight=-5.0, seed=21, obs_dtype=torch.bfloat16 if bf16 else torch.float32)
+    a = BatchedGridWorld("Level 3", **kw)
+    b = BatchedGridWorld("Level 3", **kw)
+    a.reset(); b.reset()
+    T = 96
+    acts = torch.randint(0, 9, (T, E, 2), dtype=torch.int8).pin_memory()
+    dacts = acts.cuda()
+    rew = [torch.empty((E, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
+    shp = torch.empty((E, 2), dtype=torch.float32).pin_memory()
+    end = torch.empty((E,), dtype=torch.uint8).pin_memory()
+    ring = torch.empty((4,) + tuple(a.buf.obs.shape), dtype=a.buf.obs.dtype, device="cuda")
+    ref_obs = torch.empty_like(ring)
+    exp = []
+    for t in range(T):                                   # the expected results first: nothing else touches the GPU below
+        ob = b.step(dacts[t])
+        exp.append((ob.reward.cpu(), ob.shaped_reward.cpu(), ob.ended.cpu()))
+        if t >= T - 4:
+            ref_obs[t % 4].copy_(ob.obs)
+    torch.cuda.synchronize()
+    for t in range(T):
+        oa = a.step_host(acts[t], rew[t % 2], end, host_shaped=shp, obs_out=ring[t % 4], resident=True)
+        assert oa.reward is rew[t % 2]
+        assert torch.equal(rew[t % 2], exp[t][0]) and torch.equal(shp, exp[t][1]) and torch.equal(end, exp[t][2]), t
+        if t == 40:
+            assert a.server_info()["running"] == 1
+            time.sleep(0.02)                             # > idle time: the kernel leaves by itself, the next call relaunches it
+            assert a.server_info()["running"] == 0
+        if t == 60:
+            a.sync()                                     # any other call stops it
+            assert a.server_info()["running"] == 0
+    info = a.server_info()
+    assert 3 <= info["launches"] <= 6 and info["buffer_sets"] == T
+    a.sync()
+    assert torch.equal(ring, ref_obs)
+    assert torch.equal(a.state_dict(), b.state_dict())
+    sa, sb = a.stats(), b.stats()
+    for k in sa:                                         # the two float sums are atomics: same terms, order may differ
+        assert sa[k] == sb[k] if k not in ("fear_sum", "return_sum") else abs(sa[k] - sb[k]) <= 1e-9 * max(1.0, abs(sb[k])), k
+    # the same pinned buffers rewritten by the host before every step: the kernel must see the new bytes, not a cached copy
+    one = torch.empty((E, 2), dtype=torch.int8).pin_memory()
+    for t in range(24):
+        one.copy_(acts[T - 1 - t])
+        a.step_host(one, rew[0], end, resident=True)
+        ob = b.step(dacts[T - 1 - t])
+        assert torch.equal(rew[0], ob.reward.cpu()) and torch.equal(end, ob.ended.cpu()), t
+    # device steps and resident steps interleave on the same handle
+    for t in range(8):
+        if t % 2:
+            oa = a.step_host(acts[t], rew[0], end, resident=True)
+            r_a = rew[0].clone()
+        else:
+            r_a = a.step(dacts[t]).reward.cpu()
+        assert torch.equal(r_a, b.step(dacts[t]).reward.cpu())
+    assert torch.equal(a.state_dict(), b.state_dict())
+    a.close(); b.close()
+
+
+def test_step_host_resident_falls_back_when_launches_block():
+    """Under CUDA_LAUNCH_BLOCKING=1 (as under a profiler) a launch only returns when the kernel has ended, so a resident
+    kernel can never be rung: mode 2 must notice, step through the ordinary launch, and give the same results."""
+    import subprocess, sys, os
+    code = r"""
+import torch
+from marl_responsible_nav_b200 import BatchedGridWorld
+E = 512
+a = BatchedGridWorld("Level 3", num_envs=E, fear=True, fear_weight=-5.0, seed=5); b = BatchedGridWorld("Level 3", num_envs=E, fear=True, fear_weight=-5.0, seed=5)
+a.reset(); b.reset()
+acts = torch.randint(0, 9, (6, E, 2), dtype=torch.int8).pin_memory()
+rew = torch.empty((E, 2), dtype=torch.float32).pin_memory(); end = torch.empty((E,), dtype=torch.uint8).pin_memory()
+for t in range(6):
+    a.step_host(acts[t], rew, end, resident=True)
+    ob = b.step(acts[t].cuda())
+    assert torch.equal(rew, ob.reward.cpu()) and torch.equal(end, ob.ended.cpu()), t
+assert a.server_info()["running"] == -1, a.server_info()
+assert torch.equal(a.state_dict(), b.state_dict())
+print("OK")
+"""
+    env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "OK" in res.stdout, res.stdout + res.stderr
