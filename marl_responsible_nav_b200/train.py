@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--report", type=int, default=150)
     ap.add_argument("--updates-per-learn", type=int, default=1)
     ap.add_argument("--torch-actor", action="store_true", help="act with the PyTorch modules instead of the fused kernel")
+    ap.add_argument("--save", default=None, help="write the agents here in the reference's checkpoint format (maddpg/agent.py:255-266)")
+    ap.add_argument("--load", default=None, help="resume from a checkpoint of the reference / of --save (maddpg/agent.py:268-283)")
     a = ap.parse_args()
     hp = maddpg.load_yaml_config(a.config) if os.path.exists(a.config) else maddpg.preset(a.config)
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
@@ -33,7 +35,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     base, n = sharding.shard_range(a.envs, rank, world)
     env = maddpg.make_env(hp, n, device=dev, env_id_base=base)
-    trainer = maddpg.BatchedTrainer(env, hp=hp, updates_per_learn=a.updates_per_learn, seed=hp["SEED"],
+    agent = None
+    if a.load:
+        from . import checkpoint
+        agent = checkpoint.load_reference_checkpoint(a.load, device=dev, hp=hp)
+    trainer = maddpg.BatchedTrainer(env, agent=agent, hp=hp, updates_per_learn=a.updates_per_learn, seed=hp["SEED"],
                                     fused_actor=not a.torch_actor)
     trainer.agent.broadcast_parameters(0)
     done = 0
@@ -55,6 +61,9 @@ def main():
                               "fear_sum": st["fear_sum"],
                               "critic_loss": None if last is None else float(last.critic_loss.sum()),
                               "actor_loss": None if last is None else float(last.actor_loss.sum())}), flush=True)
+    if a.save and rank == 0:
+        from . import checkpoint
+        checkpoint.save_reference_checkpoint(trainer.agent, a.save, steps=[done * a.envs])
     if world > 1:
         dist.destroy_process_group()
 
