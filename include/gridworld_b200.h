@@ -230,8 +230,11 @@ int gw_actor_create(gw_handle* h, const gw_actor_weights* weights, int n_learner
 int gw_actor_update(gw_actor* a, const gw_actor_weights* weights, int n_learners, void* stream);   /* after a learn step */
 int gw_actor_destroy(gw_actor* a);
 /* obs_code [E] (device, from gw_step / gw_reset); action_mask int8 [E, L, 9] (device, nullable);
- * cont_actions f32 [E, L, 9] and action_ids int8 [E, L] (device outputs).  training != 0: Gumbel and Gaussian noise
- * drawn from Philox(seed, env id, step); training == 0: plain softmax, no noise. */
+ * cont_actions f32 [E, L, 9] and action_ids int8 [E, L] (device outputs).  Noise comes from Philox(seed, env id, learner,
+ * step).  training == 1: Gumbel noise of the output activation + Gaussian exploration noise (maddpg/agent.py:109-113,
+ * training=True); training == 2: Gumbel noise only -- what the reference's evaluation does (customeval.py:90-94,
+ * training=False: the GumbelSoftmax activation still samples on every forward); training == 0: plain softmax, no
+ * noise (deterministic; tests). */
 int gw_actor_forward(gw_actor* a, int64_t num_envs, const uint64_t* obs_code, const int8_t* action_mask,
                      float* cont_actions, int8_t* action_ids, int training, float expl_noise, float mean_noise,
                      uint64_t seed, uint64_t step, void* stream);

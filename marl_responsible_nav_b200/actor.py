@@ -64,8 +64,12 @@ class FusedActor:
         del keep
 
     def forward(self, obs_code: torch.Tensor, action_mask: torch.Tensor = None, training: bool = True,
-                expl_noise: float = 0.1, mean_noise: float = 0.0):
-        """-> (cont_actions f32 [E, L, 9], action_ids int8 [E, L]); both are views of buffers reused by the next call."""
+                expl_noise: float = 0.1, mean_noise: float = 0.0, gumbel: bool = None):
+        """-> (cont_actions f32 [E, L, 9], action_ids int8 [E, L]); both are views of buffers reused by the next call.
+        training=True: Gumbel noise of the output activation + Gaussian exploration noise.  training=False: no noise at
+        all, unless gumbel=True, which is the reference's evaluation mode (its GumbelSoftmax activation samples on every
+        forward, `training=False` only drops the exploration noise)."""
+        mode = 1 if training else (2 if gumbel else 0)
         if obs_code.dtype != torch.int64 or obs_code.numel() != self.E or not obs_code.is_cuda:
             raise ValueError("obs_code must be the int64 [E] tensor written by BatchedGridWorld.step / reset")
         mptr = None
@@ -74,7 +78,7 @@ class FusedActor:
                 raise ValueError("action_mask must be a contiguous int8 [E, L, 9] tensor")
             mptr = action_mask.data_ptr()
         N.check(self.lib.gw_actor_forward(self._h, self.E, obs_code.data_ptr(), mptr, self.cont.data_ptr(),
-                                          self.ids.data_ptr(), int(bool(training)), float(expl_noise), float(mean_noise),
+                                          self.ids.data_ptr(), mode, float(expl_noise), float(mean_noise),
                                           self.seed, self.step, self.env._stream()), self.env._h, "gw_actor_forward")
         self.step += 1
         return self.cont, self.ids

@@ -3,15 +3,19 @@
 // Per learner k: obs(160) -> Linear 128 -> LayerNorm -> ReLU -> Linear 128 -> LayerNorm -> ReLU -> Linear 9 ->
 // GumbelSoftmax (+ Gaussian exploration noise, clip [0,1], action mask, arg-max).
 //
-// One CTA = 128 rows (envs) of one learner, one thread per row:
+// One CTA = 256 threads on a tile of up to 128 rows (envs) of one learner:
 //   layer 1  An observation is the constant map template plus <= 5 special cells, so W1*obs + b1 is a per-learner
-//            constant vector plus <= 5 columns of W1 scaled by (value - template value).  The thread builds its row from
-//            the 8-byte obs_code gw_step wrote; the 640-byte observation is never read.  LayerNorm + ReLU in registers,
-//            the row goes to shared memory as bf16 in the canonical K-major UMMA layout (8x16-byte core matrices).
-//   layer 2  [128 x 128] x [128 x 128]^T on the tensor cores: one elected thread issues 8 tcgen05.mma (M=128, N=128,
-//            K=16, bf16 -> fp32) that accumulate in TMEM, tcgen05.commit arrives on an mbarrier.
-//   epilogue each warp pulls its 32 TMEM lanes back with tcgen05.ld (thread = row, 128 fp32 accumulators), LayerNorm,
-//            ReLU, the 128 -> 9 layer, Gumbel softmax / noise / mask / arg-max, all in the row's thread.
+//            constant vector plus <= 5 columns of W1 scaled by (value - template value).  Built from the 8-byte obs_code
+//            gw_step wrote; the 640-byte observation is never read.  Each of the 8 warps walks its share of the rows
+//            together (lane l owns output columns 4l..4l+3: a W1 column is one coalesced 512-byte read, LayerNorm is a
+//            warp reduction); the row goes to shared memory as bf16 in the canonical K-major UMMA layout.
+//   layer 2  [128 x 128] x [128 x 128]^T on the tensor cores: W2 arrives by one TMA bulk copy (already in UMMA layout in
+//            HBM), one elected thread issues 8 tcgen05.mma (M=128, N=128, K=16, bf16 -> fp32) that accumulate in TMEM,
+//            tcgen05.commit arrives on an mbarrier.
+//   epilogue warps w and w+4 share TMEM lanes 32*(w&3).. (a warp reaches the lane quarter of its id mod 4), 64 columns
+//            each (tcgen05.ld, thread = row): LayerNorm sums and the 128 -> 9 products are halved between the two
+//            threads of a row and joined through shared memory; the first one finishes Gumbel softmax / noise / mask /
+//            arg-max.  Small batches use half-full tiles (64 rows) so that the grid covers the machine.
 // sm_100a only (tcgen05 / TMEM); descriptors follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
 #include <cstdio>
 #include <cstring>
@@ -45,9 +49,10 @@ struct FwdArgs {
   float* cont;                           // [E, L, 9]
   int8_t* ids;                           // [E, L]
   long long E;
+  int rows_per_tile;                      // 128, or 64 (half-full tiles) when the batch is too small to fill the machine
   int n, nl, kind, cpo;
   uint32_t apple_cells;
-  int training;
+  int gumbel, explore;                   // Gumbel noise of the output activation; Gaussian exploration noise (training)
   float expl_noise, mean_noise;
   uint32_t seed_lo, seed_hi, step_lo, step_hi;
 };
@@ -87,9 +92,13 @@ struct Smem {
   alignas(16) float w3[NACT][HID];
   float b3[NACT];
   float b2[HID], ln2_g[HID], ln2_b[HID];
-  alignas(8) unsigned long long bar;
+  alignas(8) float2 part[2][ROWS];                  // epilogue: LayerNorm partial (sum, sum of squares) per column half and row
+  float plog[ROWS][NACT + 1];                       // epilogue: the upper column half's share of the 9 logits
+  uint32_t rnd[ROWS][29];                           // Philox words of the head's noise, drawn by all threads while the MMA runs
+  alignas(8) unsigned long long bar, bar_w;         // MMA completion; arrival of W2
   uint32_t tmem_base;
 };
+constexpr int THREADS = 256;
 
 __device__ __forceinline__ float gumbel_from(uint32_t w) {
   const float u = fmaxf(((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f), 1e-20f);
@@ -100,15 +109,16 @@ __device__ __forceinline__ float gauss_from(uint32_t a, uint32_t b) {          /
   return sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307f * u2);
 }
 
-__global__ void __launch_bounds__(ROWS, 3) actor_forward_kernel(FwdArgs a) {
+__global__ void __launch_bounds__(THREADS, 2) actor_forward_kernel(FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int k = blockIdx.y;                               // learner
   const ActorParams& P = a.params[k];
-  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.bar);
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.bar), bar_w = (uint32_t)__cvta_generic_to_shared(&s.bar_w);
+  const int RT = a.rows_per_tile;
 
-  // ---- one-time setup: TMEM columns for the 128x128 fp32 accumulator, mbarrier, W2 / W3 / LN2 into shared memory
+  // ---- one-time setup: TMEM columns for the 128x128 fp32 accumulator, mbarriers, W2 by TMA, W3 / LN2 into shared memory
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      (uint32_t)__cvta_generic_to_shared(&s.tmem_base)), "n"(HID));
@@ -116,19 +126,21 @@ __global__ void __launch_bounds__(ROWS, 3) actor_forward_kernel(FwdArgs a) {
   }
   if (tid == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "n"(HID * HID * 2) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(s.b_tile)), "l"(P.w2_umma), "n"(HID * HID * 2), "r"(bar_w) : "memory");
   }
   {
-    const uint4* src = reinterpret_cast<const uint4*>(P.w2_umma);
-    uint4* dst = reinterpret_cast<uint4*>(s.b_tile);
-    for (int i = tid; i < HID * HID * 2 / 16; i += ROWS) dst[i] = __ldg(src + i);
-    for (int i = tid; i < NACT * HID; i += ROWS) (&s.w3[0][0])[i] = (&P.w3[0][0])[i];
+    for (int i = tid; i < NACT * HID; i += THREADS) (&s.w3[0][0])[i] = (&P.w3[0][0])[i];
     if (tid < NACT) s.b3[tid] = P.b3[tid];
-    s.b2[tid] = P.b2[tid];
-    s.ln2_g[tid] = P.ln2_g[tid];
-    s.ln2_b[tid] = P.ln2_b[tid];
+    if (tid < HID) {
+      s.b2[tid] = P.b2[tid];
+      s.ln2_g[tid] = P.ln2_g[tid];
+      s.ln2_b[tid] = P.ln2_b[tid];
+    }
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes of W2 -> visible to the MMA
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
@@ -136,53 +148,55 @@ __global__ void __launch_bounds__(ROWS, 3) actor_forward_kernel(FwdArgs a) {
   const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(s.a_tile);
   const uint32_t b_addr = (uint32_t)__cvta_generic_to_shared(s.b_tile);
   uint32_t phase = 0;
+  bool w2_pending = true;
 
-  const long long n_tiles = (a.E + ROWS - 1) / ROWS;
+  const int rpw = RT / 8;                                  // rows of a tile per warp in layer 1 (16 or 8)
+  const int q = warp & 3, hf = warp >> 2;                  // epilogue: TMEM lane quarter, column half
+  const int m = q * 32 + lane;                             // epilogue: this thread's row of the tile
+  const long long n_tiles = (a.E + RT - 1) / RT;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long e = tile * ROWS + tid;
-    const bool live = e < a.E;
-
     // ---- layer 1 from the observation code: h = c1 + sum_s (value_s - template_s) * W1[:, cell_s]; template_s = 0
-    // (agents and apples only stand on active cells).  Each lane decodes the special cells of ITS row; then the warp
-    // walks its 32 rows together: lane l owns output columns 4l..4l+3, so every W1 column is one coalesced 512-byte
-    // read, and LayerNorm is a warp reduction.
-    const int lane = tid & 31;
+    // (agents and apples only stand on active cells).  Lane i < rpw decodes the special cells of the warp's i-th row;
+    // then the warp walks its rows together: lane l owns output columns 4l..4l+3.
     uint32_t my_cells = 0xFFFFFFFFu, my_cell4 = 0xFFu;   // up to five cells (0xFF = unused) ...
     float my_vals[5] = {0.f, 0.f, 0.f, 0.f, 0.f};        // ... and their values
-    if (live) {
-      const unsigned long long code = a.obs_code[e];
-      const uint32_t cells = (uint32_t)code, apples = (uint32_t)(code >> 32) & 3u;
-      const bool fresh = (code >> 34) & 1ull;
-      const bool apple_on = (a.kind == GW_ENV_MULTI) ? ((apples >> k) & 1u) : (apples & 1u);
-      const uint32_t apple = (a.kind == GW_ENV_MULTI) ? (a.apple_cells >> (8 * k)) & 0xFFu : a.apple_cells & 0xFFu;
-      bool covered = false;
-      my_cells = 0;
+    {
+      const long long e1 = tile * RT + warp * rpw + lane;
+      if (lane < rpw && e1 < a.E) {
+        const unsigned long long code = a.obs_code[e1];
+        const uint32_t cells = (uint32_t)code, apples = (uint32_t)(code >> 32) & 3u;
+        const bool fresh = (code >> 34) & 1ull;
+        const bool apple_on = (a.kind == GW_ENV_MULTI) ? ((apples >> k) & 1u) : (apples & 1u);
+        const uint32_t apple = (a.kind == GW_ENV_MULTI) ? (a.apple_cells >> (8 * k)) & 0xFFu : a.apple_cells & 0xFFu;
+        bool covered = false;
+        my_cells = 0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t c = (cells >> (8 * i)) & 0xFFu;
-        const bool on = i < a.n;
-        const bool here = on && apple_on && c == apple;
-        covered |= here;
-        float v;                                         // same value rules as the renderer (ma_customenv.py:303-322)
-        if (fresh) v = 0.5f;
-        else if (here || a.kind == GW_ENV_SINGLE) v = (float)(i + 1);
-        else v = (i == k) ? 1.0f : 5.0f;
-        my_cells |= (on ? c : 0xFFu) << (8 * i);
-        my_vals[i] = here ? v + 9.0f : v;
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t c = (cells >> (8 * i)) & 0xFFu;
+          const bool on = i < a.n;
+          const bool here = on && apple_on && c == apple;
+          covered |= here;
+          float v;                                         // same value rules as the renderer (ma_customenv.py:303-322)
+          if (fresh) v = 0.5f;
+          else if (here || a.kind == GW_ENV_SINGLE) v = (float)(i + 1);
+          else v = (i == k) ? 1.0f : 5.0f;
+          my_cells |= (on ? c : 0xFFu) << (8 * i);
+          my_vals[i] = here ? v + 9.0f : v;
+        }
+        if (apple_on && !covered) { my_cell4 = apple; my_vals[4] = 9.0f; }
       }
-      if (apple_on && !covered) { my_cell4 = apple; my_vals[4] = 9.0f; }
     }
     const float4 c1v = *reinterpret_cast<const float4*>(&P.c1[4 * lane]);
     const float4 g1v = *reinterpret_cast<const float4*>(&P.ln1_g[4 * lane]);
     const float4 b1v = *reinterpret_cast<const float4*>(&P.ln1_b[4 * lane]);
 #pragma unroll 2
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < rpw; ++i) {
       const uint32_t rc = __shfl_sync(0xFFFFFFFFu, my_cells, i), rc4 = __shfl_sync(0xFFFFFFFFu, my_cell4, i);
       float4 h = c1v;
 #pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const float v = __shfl_sync(0xFFFFFFFFu, my_vals[q], i);
-        const uint32_t c = q < 4 ? (rc >> (8 * q)) & 0xFFu : rc4;
+      for (int qq = 0; qq < 5; ++qq) {
+        const float v = __shfl_sync(0xFFFFFFFFu, my_vals[qq], i);
+        const uint32_t c = qq < 4 ? (rc >> (8 * qq)) & 0xFFu : rc4;
         if (c != 0xFFu) {                                // warp-uniform
           const float4 w = __ldg(reinterpret_cast<const float4*>(P.w1t[c]) + lane);
           h.x = fmaf(v, w.x, h.x); h.y = fmaf(v, w.y, h.y); h.z = fmaf(v, w.z, h.z); h.w = fmaf(v, w.w, h.w);
@@ -203,15 +217,17 @@ __global__ void __launch_bounds__(ROWS, 3) actor_forward_kernel(FwdArgs a) {
       const float x3 = row_live ? fmaxf((h.w - mean) * rstd * g1v.w + b1v.w, 0.f) : 0.f;
       const uint32_t p0 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(x0)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16(x1)) << 16);
       const uint32_t p1 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(x2)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16(x3)) << 16);
-      *reinterpret_cast<uint2*>(s.a_tile + umma_off(warp * 32 + i, 4 * lane)) = make_uint2(p0, p1);
+      *reinterpret_cast<uint2*>(s.a_tile + umma_off(warp * rpw + i, 4 * lane)) = make_uint2(p0, p1);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // activations -> visible to the tensor-core proxy
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    // ---- layer 2 on the tensor cores: D[128x128] (TMEM) = A[128x128] * W2^T, eight K=16 steps, one issuing thread
+    // ---- layer 2 on the tensor cores: D[128x128] (TMEM) = A[128x128] * W2^T, eight K=16 steps, one issuing thread.
+    // (Rows RT..127 of a half-full tile hold whatever shared memory held: they only reach accumulator rows nobody reads.)
     if (tid == 0) {
+      if (w2_pending) mbar_wait(bar_w, 0u);
 #pragma unroll
       for (int kk = 0; kk < HID / 16; ++kk) {
         const uint64_t da = smem_desc(a_addr + kk * 4096), db = smem_desc(b_addr + kk * 4096);
@@ -225,63 +241,93 @@ __global__ void __launch_bounds__(ROWS, 3) actor_forward_kernel(FwdArgs a) {
       // completion of all prior MMAs arrives on the mbarrier (implies tcgen05.fence::before_thread_sync)
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
     }
+    w2_pending = false;
+    // ---- while the tensor cores work: the random words of the head (9 Gumbel uniforms + 9 x 2 Box-Muller uniforms per
+    // row, a pure function of seed / env / learner / step), 256 / RT threads per row
+    if (a.gumbel | a.explore) {
+      const int tpr = THREADS / RT, rr = tid / tpr;
+      const long long er = tile * RT + rr;
+      const int n_calls = a.explore ? 7 : 3;
+      if (er < a.E)
+        for (int c = tid % tpr; c < n_calls; c += tpr) {
+          uint32_t w[4] = {(uint32_t)er, (uint32_t)((unsigned long long)er >> 32) ^ ((uint32_t)k << 24) ^ ((uint32_t)c << 28),
+                           a.step_lo, a.step_hi ^ 0xAC70u};
+          gw::philox4x32(w, a.seed_lo, a.seed_hi);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) s.rnd[rr][4 * c + u] = w[u];
+        }
+    }
+    const bool quarter_on = q * 32 < RT;                   // warp-uniform: a half-full tile fills lane quarters 0 and 1
+    const long long e = tile * RT + m;
+    const bool live = quarter_on && m < RT && e < a.E;
+    float acc[HID / 2];
+    float mu_p = 0.f, sq_p = 0.f;
     mbar_wait(bar, phase);
     phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    // ---- epilogue: thread = row; its warp owns TMEM lanes 32*warp .. 32*warp+31
-    float acc[HID];
+    // ---- epilogue, first half: this thread's 64 accumulator columns of its row
+    if (quarter_on) {
 #pragma unroll
-    for (int c0 = 0; c0 < HID; c0 += 32) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int c0 = 0; c0 < HID / 2; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * (HID / 2) + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int u = 0; u < 32; ++u) acc[c0 + u] = __uint_as_float(r[u]) + s.b2[c0 + u];
-    }
-    // TMEM has been read: the next tile's MMA may overwrite it once every warp is past this point
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    float mu = 0.f, sq = 0.f;
-#pragma unroll
-    for (int j = 0; j < HID; ++j) { mu += acc[j]; sq = fmaf(acc[j], acc[j], sq); }
-    mu *= (1.0f / HID);
-    const float rs = rsqrtf(fmaxf(sq * (1.0f / HID) - mu * mu, 0.f) + 1e-5f);
-    float logit[NACT];
-#pragma unroll
-    for (int o = 0; o < NACT; ++o) logit[o] = s.b3[o];
-#pragma unroll
-    for (int j0 = 0; j0 < HID; j0 += 4) {
-      float x[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) x[u] = fmaxf((acc[j0 + u] - mu) * rs * s.ln2_g[j0 + u] + s.ln2_b[j0 + u], 0.f);
-#pragma unroll
-      for (int o = 0; o < NACT; ++o) {
-        const float4 w = *reinterpret_cast<const float4*>(&s.w3[o][j0]);      // same address in every lane: broadcast
-        logit[o] = fmaf(x[0], w.x, fmaf(x[1], w.y, fmaf(x[2], w.z, fmaf(x[3], w.w, logit[o]))));
+        for (int u = 0; u < 32; ++u) acc[c0 + u] = __uint_as_float(r[u]) + s.b2[hf * (HID / 2) + c0 + u];
       }
-    }
-    if (live) {
-      // GumbelSoftmax head (fresh Gumbel noise per forward) + Gaussian exploration noise, both from Philox
-      uint32_t rnd[28];                                  // 9 Gumbel uniforms + 9 x 2 Box-Muller uniforms
-      if (a.training) {
 #pragma unroll
-        for (int c = 0; c < 7; ++c) {
-          uint32_t w[4] = {(uint32_t)e, (uint32_t)((unsigned long long)e >> 32) ^ ((uint32_t)k << 24) ^ ((uint32_t)c << 28),
-                           a.step_lo, a.step_hi ^ 0xAC70u};
-          gw::philox4x32(w, a.seed_lo, a.seed_hi);
-          rnd[4 * c] = w[0]; rnd[4 * c + 1] = w[1]; rnd[4 * c + 2] = w[2]; rnd[4 * c + 3] = w[3];
+      for (int j = 0; j < HID / 2; ++j) { mu_p += acc[j]; sq_p = fmaf(acc[j], acc[j], sq_p); }
+      s.part[hf][m] = make_float2(mu_p, sq_p);
+    }
+    // TMEM has been read: the next tile's MMA may overwrite it once every warp is past the barrier
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();                                       // LayerNorm partials of both column halves are in shared memory
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    float logit[NACT];
+    if (quarter_on) {
+      const float2 other = s.part[hf ^ 1][m];
+      const float mu = (mu_p + other.x) * (1.0f / HID);
+      const float rs = rsqrtf(fmaxf((sq_p + other.y) * (1.0f / HID) - mu * mu, 0.f) + 1e-5f);
+#pragma unroll
+      for (int o = 0; o < NACT; ++o) logit[o] = hf == 0 ? s.b3[o] : 0.f;
+#pragma unroll
+      for (int j0 = 0; j0 < HID / 2; j0 += 4) {
+        float x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = hf * (HID / 2) + j0 + u;
+          x[u] = fmaxf((acc[j0 + u] - mu) * rs * s.ln2_g[j] + s.ln2_b[j], 0.f);
         }
 #pragma unroll
-        for (int o = 0; o < NACT; ++o) logit[o] += gumbel_from(rnd[o]);
+        for (int o = 0; o < NACT; ++o) {
+          const float4 w = *reinterpret_cast<const float4*>(&s.w3[o][hf * (HID / 2) + j0]);   // same address in every lane: broadcast
+          logit[o] = fmaf(x[0], w.x, fmaf(x[1], w.y, fmaf(x[2], w.z, fmaf(x[3], w.w, logit[o]))));
+        }
+      }
+      if (hf == 1) {
+#pragma unroll
+        for (int o = 0; o < NACT; ++o) s.plog[m][o] = logit[o];
+      }
+    }
+    __syncthreads();                                       // the upper half's share of the logits is in shared memory
+    if (live && hf == 0) {
+#pragma unroll
+      for (int o = 0; o < NACT; ++o) logit[o] += s.plog[m][o];
+      // GumbelSoftmax head (the reference's output activation draws fresh Gumbel noise on EVERY forward, evaluation
+      // included) + Gaussian exploration noise (training), both from the Philox words drawn above
+      if (a.gumbel) {
+#pragma unroll
+        for (int o = 0; o < NACT; ++o) logit[o] += gumbel_from(s.rnd[m][o]);
       }
       float mx = logit[0];
 #pragma unroll
@@ -297,8 +343,8 @@ __global__ void __launch_bounds__(ROWS, 3) actor_forward_kernel(FwdArgs a) {
 #pragma unroll
       for (int o = 0; o < NACT; ++o) {
         float v = pr[o] * inv;
-        if (a.training) {
-          const float g = gauss_from(rnd[9 + 2 * o], rnd[10 + 2 * o]);
+        if (a.explore) {
+          const float g = gauss_from(s.rnd[m][9 + 2 * o], s.rnd[m][10 + 2 * o]);
           v = fminf(fmaxf(v + a.mean_noise + a.expl_noise * g, 0.f), 1.f);
         }
         out[o] = v;
@@ -307,9 +353,10 @@ __global__ void __launch_bounds__(ROWS, 3) actor_forward_kernel(FwdArgs a) {
       }
       a.ids[e * a.nl + k] = (int8_t)best;
     }
-    __syncthreads();                                     // every warp has drained TMEM and a_tile is free again
-    asm volatile("tcgen05.fence::after_thread_sync;");
+    // a_tile / part / plog are rewritten by the next tile only after its first barrier, which every warp reaches after
+    // it is done with them
   }
+  if (w2_pending && tid == 0) mbar_wait(bar_w, 0u);        // a CTA without tiles must not exit with the copy in flight
 
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(HID));
@@ -421,13 +468,17 @@ int gw_actor_forward(gw_actor* a, int64_t num_envs, const uint64_t* obs_code, co
   f.n = h->cfg.n_agents; f.nl = h->cfg.n_learners; f.kind = h->cfg.env_kind; f.cpo = h->cfg.height * GW_W;
   for (int k = 0; k < h->cfg.n_learners; ++k)
     if (h->cfg.apple_row[k] >= 0) f.apple_cells |= (uint32_t)((h->cfg.apple_row[k] << 4) | h->cfg.apple_col[k]) << (8 * k);
-  f.training = training; f.expl_noise = expl_noise; f.mean_noise = mean_noise;
+  if (training < 0 || training > 2) return gw_fail(h, GW_EINVAL, "gw_actor_forward: training must be 0, 1 or 2");
+  f.gumbel = training != 0; f.explore = training == 1; f.expl_noise = expl_noise; f.mean_noise = mean_noise;
   f.seed_lo = (uint32_t)seed; f.seed_hi = (uint32_t)(seed >> 32);
   f.step_lo = (uint32_t)step; f.step_hi = (uint32_t)(step >> 32);
-  const long long tiles = (num_envs + gwa::ROWS - 1) / gwa::ROWS;
-  const long long cap = (long long)h->sm_count * 3 / (h->cfg.n_learners > 0 ? h->cfg.n_learners : 1);   // 3 CTAs per SM over all learners
+  const int nl = h->cfg.n_learners > 0 ? h->cfg.n_learners : 1;
+  // half-full tiles while full ones would leave SMs without a CTA (latency regime)
+  f.rows_per_tile = ((num_envs + gwa::ROWS - 1) / gwa::ROWS) * nl < (long long)h->sm_count ? gwa::ROWS / 2 : gwa::ROWS;
+  const long long tiles = (num_envs + f.rows_per_tile - 1) / f.rows_per_tile;
+  const long long cap = (long long)h->sm_count * 2 / nl;               // 2 CTAs per SM over all learners
   dim3 grid((unsigned)(tiles < cap ? tiles : cap), (unsigned)h->cfg.n_learners);
-  gwa::actor_forward_kernel<<<grid, gwa::ROWS, sizeof(gwa::Smem) + 1024, static_cast<cudaStream_t>(stream)>>>(f);
+  gwa::actor_forward_kernel<<<grid, gwa::THREADS, sizeof(gwa::Smem) + 1024, static_cast<cudaStream_t>(stream)>>>(f);
   GW_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return GW_OK;

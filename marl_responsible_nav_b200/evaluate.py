@@ -48,7 +48,7 @@ def evaluate(agent: maddpg.BatchedMADDPG, num_envs: int = 4096, episodes: int = 
         for _ in range(check_every):
             mask = out.action_mask if masked else None
             if fused is not None:
-                _, ids = fused.forward(out.obs_code, mask, training=False)
+                _, ids = fused.forward(out.obs_code, mask, training=False, gumbel=True)   # as the torch module below
             else:
                 _, ids = agent.get_action(out.obs, mask, training=False)
             out = env.step(ids)

@@ -52,3 +52,27 @@ def test_fused_actor_training_noise_and_update():
     fused.update(agent.actors)
     _, ids = fused.forward(out.obs_code, None, training=False)
     assert (ids[:, 0] == 0).all()
+
+
+def test_fused_actor_evaluation_mode_samples_gumbel_only():
+    """training=False, gumbel=True (the reference's evaluation: the output activation still samples): actions follow the
+    softmax probabilities -- arg-max of logits + Gumbel noise is a sample of the categorical distribution -- and the
+    values stay a probability vector (no exploration noise, no clipping)."""
+    from marl_responsible_nav_b200 import BatchedGridWorld, FusedActor, maddpg
+    E = 16384
+    env = BatchedGridWorld("Level 3", num_envs=E, fear=False, seed=8)
+    agent = maddpg.BatchedMADDPG(2, 160, 9, device="cuda", seed=9)
+    with torch.no_grad():
+        agent.actors[0][-2].bias.copy_(torch.linspace(-1.0, 1.0, 9))
+    fused = FusedActor(env, agent.actors, seed=3)
+    out = env.reset()
+    cont, ids = (t.clone() for t in fused.forward(out.obs_code, None, training=False, gumbel=True))   # views of reused buffers
+    assert torch.allclose(cont.sum(-1), torch.ones_like(cont.sum(-1)), atol=1e-4)
+    p = _reference(agent.actors[0], out.obs[:, 0]).mean(0)                       # expected action frequencies
+    freq = torch.bincount(ids[:, 0].long(), minlength=9).float() / E
+    assert (freq - p).abs().max().item() < 0.02, (freq, p)
+    cont2, ids2 = fused.forward(out.obs_code, None, training=False, gumbel=True)
+    assert (ids != ids2).float().mean().item() > 0.3                             # fresh noise every call
+    d1, i1 = (t.clone() for t in fused.forward(out.obs_code, None, training=False))
+    d2, i2 = fused.forward(out.obs_code, None, training=False)
+    assert torch.equal(d1, d2) and torch.equal(i1, i2)                           # deterministic without it
