@@ -228,6 +228,8 @@ typedef struct gw_actor gw_actor;
 /* `h` provides the map (template row), agent / learner counts and the device.  weights[k] belongs to learner k. */
 int gw_actor_create(gw_handle* h, const gw_actor_weights* weights, int n_learners, gw_actor** out);
 int gw_actor_update(gw_actor* a, const gw_actor_weights* weights, int n_learners, void* stream);   /* after a learn step */
+/* the same from DEVICE tensors (fp32, the layouts above): packed by a kernel on `stream`, no host copy, no synchronisation */
+int gw_actor_update_device(gw_actor* a, const gw_actor_weights* dev_weights, int n_learners, void* stream);
 int gw_actor_destroy(gw_actor* a);
 /* obs_code [E] (device, from gw_step / gw_reset); action_mask int8 [E, L, 9] (device, nullable);
  * cont_actions f32 [E, L, 9] and action_ids int8 [E, L] (device outputs).  Noise comes from Philox(seed, env id, learner,

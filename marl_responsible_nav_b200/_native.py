@@ -12,7 +12,7 @@ GW_OBS_F32, GW_OBS_BF16 = 0, 1
 
 EXPORTS = ["gw_abi_version", "gw_build_info", "gw_default_config", "gw_create", "gw_destroy", "gw_last_error",
            "gw_reset", "gw_step", "gw_step_host", "gw_server_stop", "gw_server_info", "gw_sync", "gw_state_bytes", "gw_get_state", "gw_set_state", "gw_get_stats",
-           "gw_reset_stats", "gw_launch_count", "gw_update_world", "gw_fear_one_actor", "gw_fear_matrix", "gw_feal", "gw_actor_create", "gw_actor_update",
+           "gw_reset_stats", "gw_launch_count", "gw_update_world", "gw_fear_one_actor", "gw_fear_matrix", "gw_feal", "gw_actor_create", "gw_actor_update", "gw_actor_update_device",
            "gw_actor_destroy", "gw_actor_forward"]
 
 
@@ -90,6 +90,7 @@ def load():
     lib.gw_feal.argtypes = [vp, i64] + [vp] * 8 + [vp]
     lib.gw_actor_create.argtypes = [vp, C.POINTER(GwActorWeights), C.c_int, C.POINTER(vp)]
     lib.gw_actor_update.argtypes = [vp, C.POINTER(GwActorWeights), C.c_int, vp]
+    lib.gw_actor_update_device.argtypes = [vp, C.POINTER(GwActorWeights), C.c_int, vp]
     lib.gw_actor_destroy.argtypes = [vp]
     lib.gw_actor_forward.argtypes = [vp, i64, vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_uint64, C.c_uint64, vp]
     if lib.gw_abi_version() != 1:

@@ -58,7 +58,21 @@ class FusedActor:
         return arr, keep
 
     def update(self, actors: Sequence[nn.Sequential]):
-        """Re-upload the weights (after a learn step)."""
+        """Refresh the kernel's packed copy of the weights (after a learn step).  Parameters that live on the env's
+        device are packed there by a kernel, in stream order; anything else goes through the host."""
+        tensors = []
+        for actor in actors:
+            lin, ln = _linear_norm_layers(actor)
+            tensors.append([lin[0].weight, lin[0].bias, ln[0].weight, ln[0].bias, lin[1].weight, lin[1].bias, ln[1].weight,
+                            ln[1].bias, lin[2].weight, lin[2].bias])
+        if len(actors) == self.L and all(t.device == self.env.device and t.dtype == torch.float32 and t.is_contiguous()
+                                         for ts in tensors for t in ts):
+            arr = (N.GwActorWeights * self.L)()
+            for k, ts in enumerate(tensors):
+                for name, t in zip(("w1", "b1", "ln1_g", "ln1_b", "w2", "b2", "ln2_g", "ln2_b", "w3", "b3"), ts):
+                    setattr(arr[k], name, t.data_ptr())
+            N.check(self.lib.gw_actor_update_device(self._h, arr, self.L, self.env._stream()), self.env._h, "gw_actor_update_device")
+            return
         w, keep = self._pack(actors)
         N.check(self.lib.gw_actor_update(self._h, w, self.L, self.env._stream()), self.env._h, "gw_actor_update")
         del keep

@@ -60,6 +60,15 @@ def _init_dict(num_inputs: int, num_outputs: int, hidden: List[int], out_act: Op
             "support": None, "rainbow": False, "noise_std": 0.5, "device": torch.device("cpu"), "accelerator": None}
 
 
+def _portable_optimizer_state(opt: torch.optim.Optimizer) -> Dict:
+    """Adam state as the reference writes it: CPU tensors, no device-side step counters (`capturable` is how this
+    package keeps the update inside a CUDA graph; a CPU run of the reference could not step such an optimiser)."""
+    sd = opt.state_dict()
+    state = {k: {n: (v.detach().cpu().clone() if torch.is_tensor(v) else v) for n, v in st.items()} for k, st in sd["state"].items()}
+    groups = [dict(g, capturable=False) if "capturable" in g else dict(g) for g in sd["param_groups"]]
+    return {"state": state, "param_groups": groups}
+
+
 def load_reference_checkpoint(path: str, device="cuda", hp: Optional[Dict] = None) -> maddpg.BatchedMADDPG:
     """A BatchedMADDPG with the networks, target networks, optimiser moments and hyper-parameters of a checkpoint written
     by the reference (or by `save_reference_checkpoint`)."""
@@ -87,7 +96,15 @@ def load_reference_checkpoint(path: str, device="cuda", hp: Optional[Dict] = Non
     for opts, key in ((agent.actor_opt, "actor_optimizers_state_dict"), (agent.critic_opt, "critic_optimizers_state_dict")):
         for opt, sd in zip(opts, ck.get(key, [])):
             try:
+                cap = [g.get("capturable", False) for g in opt.param_groups]
                 opt.load_state_dict(sd)
+                for g, c in zip(opt.param_groups, cap):              # keep this side's choice (CUDA graphs), not the file's
+                    if "capturable" in g:
+                        g["capturable"] = c
+                if any(cap):
+                    for st in opt.state.values():
+                        if torch.is_tensor(st.get("step")):
+                            st["step"] = st["step"].to(device=agent.device, dtype=torch.float32)
             except (ValueError, KeyError):                           # a fresh optimiser is a valid way to resume
                 pass
     agent.steps = list(ck.get("steps", [0]))
@@ -118,6 +135,6 @@ def save_reference_checkpoint(agent: maddpg.BatchedMADDPG, path: str, steps: Opt
         ck[f"{theirs}_init_dict"] = [_init_dict(agent.obs_dim if actor else crit_in, agent.act_dim if actor else 1, hidden,
                                                 "GumbelSoftmax" if actor else None) for _ in range(n)]
         ck[f"{theirs}_state_dict"] = [_to_reference_names(net) for net in getattr(agent, ours)]
-    ck["actor_optimizers_state_dict"] = [o.state_dict() for o in agent.actor_opt]
-    ck["critic_optimizers_state_dict"] = [o.state_dict() for o in agent.critic_opt]
+    ck["actor_optimizers_state_dict"] = [_portable_optimizer_state(o) for o in agent.actor_opt]
+    ck["critic_optimizers_state_dict"] = [_portable_optimizer_state(o) for o in agent.critic_opt]
     torch.save(ck, path)

@@ -362,6 +362,39 @@ __global__ void __launch_bounds__(THREADS, 2) actor_forward_kernel(FwdArgs a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(HID));
 }
 
+// Weights straight from the trainer's device tensors (torch layout, fp32) into the kernel's packed form: the same
+// arithmetic as pack_weights below (c1 accumulated in double, in cell order), without the trip through the host.
+struct PackArgs {
+  gw_actor_weights w[GW_MAX_LEARNERS];   // DEVICE pointers
+  ActorParams* out;                      // [n_learners]
+  uint16_t map_rows[GW_MAX_H];
+  int cpo;
+};
+
+__global__ void __launch_bounds__(256) actor_pack_kernel(PackArgs a) {
+  const gw_actor_weights& W = a.w[blockIdx.y];
+  ActorParams& P = a.out[blockIdx.y];
+  const int cpo = a.cpo, stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cpo * HID; i += stride) {
+    const int cell = i / HID, j = i % HID;
+    P.w1t[cell][j] = W.w1[j * cpo + cell];
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HID * HID; i += stride) {
+    const int n = i / HID, kk = i % HID;
+    P.w2_umma[umma_off(n, kk) / 2] = __float2bfloat16(W.w2[i]);
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NACT * HID; i += stride) (&P.w3[0][0])[i] = W.w3[i];
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < HID; j += stride) {
+    double acc = W.b1[j];
+    for (int cell = 0; cell < cpo; ++cell)
+      if (!((a.map_rows[cell >> 4] >> (cell & 15)) & 1)) acc -= (double)W.w1[j * cpo + cell];   // template value -1 on inactive cells
+    P.c1[j] = (float)acc;
+    P.ln1_g[j] = W.ln1_g[j]; P.ln1_b[j] = W.ln1_b[j];
+    P.b2[j] = W.b2[j]; P.ln2_g[j] = W.ln2_g[j]; P.ln2_b[j] = W.ln2_b[j];
+    if (j < NACT) P.b3[j] = W.b3[j];
+  }
+}
+
 }  // namespace gwa
 
 // ====================================================================== host side / C-ABI
@@ -437,6 +470,29 @@ int gw_actor_update(gw_actor* a, const gw_actor_weights* weights, int n_learners
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   GW_CUDA(a->h, cudaMemcpyAsync(a->d_params, host.data(), sizeof(gwa::ActorParams) * n_learners, cudaMemcpyHostToDevice, s));
   GW_CUDA(a->h, cudaStreamSynchronize(s));            // `host` is a temporary
+  return GW_OK;
+}
+
+int gw_actor_update_device(gw_actor* a, const gw_actor_weights* dev_weights, int n_learners, void* stream) {
+  if (!a || !dev_weights) return GW_EINVAL;
+  gw_handle* h = a->h;
+  if (n_learners != a->n_learners || n_learners > GW_MAX_LEARNERS) return gw_fail(h, GW_EINVAL, "gw_actor_update_device: learner count changed");
+  if (int rc = gw_server_stop(h)) return rc;
+  gwa::PackArgs p;
+  std::memset(&p, 0, sizeof(p));
+  for (int k = 0; k < n_learners; ++k) {
+    const gw_actor_weights& W = dev_weights[k];
+    if (!W.w1 || !W.b1 || !W.ln1_g || !W.ln1_b || !W.w2 || !W.b2 || !W.ln2_g || !W.ln2_b || !W.w3 || !W.b3)
+      return gw_fail(h, GW_EINVAL, "gw_actor_update_device: null weight pointer");
+    p.w[k] = W;
+  }
+  p.out = a->d_params;
+  for (int r = 0; r < GW_MAX_H; ++r) p.map_rows[r] = h->cfg.map_rows[r];
+  p.cpo = h->cfg.height * GW_W;
+  GW_CUDA(h, cudaSetDevice(h->cfg.device));
+  gwa::actor_pack_kernel<<<dim3(40, (unsigned)n_learners), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  GW_CUDA(h, cudaGetLastError());
+  h->launches += 1;
   return GW_OK;
 }
 

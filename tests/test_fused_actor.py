@@ -76,3 +76,23 @@ def test_fused_actor_evaluation_mode_samples_gumbel_only():
     d1, i1 = (t.clone() for t in fused.forward(out.obs_code, None, training=False))
     d2, i2 = fused.forward(out.obs_code, None, training=False)
     assert torch.equal(d1, d2) and torch.equal(i1, i2)                           # deterministic without it
+
+
+def test_device_side_weight_packing_equals_host_packing():
+    """FusedActor.update packs CUDA parameters with a kernel; the result is the host packing of gw_actor_create bit for bit."""
+    from marl_responsible_nav_b200 import BatchedGridWorld, FusedActor, maddpg
+    E = 3000
+    env = BatchedGridWorld("Level 3", num_envs=E, fear=False, seed=11)
+    a1 = maddpg.BatchedMADDPG(2, 160, 9, device="cuda", seed=21)
+    a2 = maddpg.BatchedMADDPG(2, 160, 9, device="cuda", seed=22)
+    host_packed = FusedActor(env, a1.actors, seed=4)               # packed on the host at creation
+    dev_packed = FusedActor(env, a2.actors, seed=4)
+    dev_packed.update(a1.actors)                                   # other weights first, then a1's through the device path
+    out = env.reset()
+    c1, i1 = (t.clone() for t in host_packed.forward(out.obs_code, out.action_mask, training=False))
+    c2, i2 = dev_packed.forward(out.obs_code, out.action_mask, training=False)
+    assert torch.equal(c1, c2) and torch.equal(i1, i2)
+    cpu_actors = [torch.nn.Sequential(*[m for m in a]).cpu() for a in maddpg.BatchedMADDPG(2, 160, 9, device="cpu", seed=21).actors]
+    dev_packed.update(cpu_actors)                                  # CPU parameters still take the host path
+    c3, _ = dev_packed.forward(out.obs_code, out.action_mask, training=False)
+    assert torch.isfinite(c3).all()
