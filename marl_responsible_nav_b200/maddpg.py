@@ -140,7 +140,7 @@ class BatchedMADDPG:
         ~250 small kernels, 6 ms of launches in eager mode) is captured into one CUDA graph after three eager calls
         and replayed from then on; with several ranks the gradient all-reduce keeps it eager."""
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        if not graph or self.device.type != "cuda" or multi:
+        if not graph or self.device.type != "cuda" or multi:     # (capturing the NCCL all-reduces hung here: 2 ranks, torch 2.11)
             return self._learn(batch)
         keys = ("state", "action", "reward", "next_state", "done")
         if self._graph is not None:
