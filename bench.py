@@ -28,8 +28,8 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 ALGO_BYTES_PER_AGENT_STEP = {"f32": 668.0, "bf16": 348.0}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r1c_*_ncu_raw.csv; Level 3, f32 obs): (envs, fear) -> bytes
-NCU_DRAM_BYTES = {(4096, 1): 372.5e3 + 0.0, (1 << 20, 1): 19.89e6 + 1417.0e6, (1 << 20, 0): 19.33e6 + 1378.6e6}
+# (profiles/r1d_*_ncu_raw.csv; Level 3, f32 obs): (envs, fear) -> bytes
+NCU_DRAM_BYTES = {(4096, 1): 370.0e3 + 0.0, (1 << 20, 1): 23.2e6 + 1413.0e6, (1 << 20, 0): 19.33e6 + 1378.3e6}
 
 
 def kernel_name(envs, fear, obs):
@@ -341,7 +341,7 @@ def run_ours(a):
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(K),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_DRAM_BYTES.get((E, int(bool(a.fear)))) if (a.obs == "f32" and a.scenario == "Level 3") else None,
-                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1c_*_ncu_raw.csv); "
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1d_*_ncu_raw.csv); "
                                        "at 4096 envs the stores are still in L2 when the kernel ends, so DRAM writes show as 0",
                      "kernel": kernel_name(E, a.fear, a.obs),
                      "algorithmic_bytes_per_launch": algo, "peak_source": peak_src,

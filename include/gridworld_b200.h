@@ -155,8 +155,8 @@ int gw_sync(gw_handle* h, void* stream);       /* cudaStreamSynchronize + surfac
  * io->ended -> host_ended u8 [E] (nullable), and synchronises the stream.  One call, no Python between the stages.
  * zero_copy != 0: no memcpy nodes at all -- the kernel itself loads the actions from the pinned host buffer and stores
  * rewards / flags into the pinned host buffers over PCIe (unified addressing); same bytes, fewer stream operations.
- * zero_copy == GW_HOST_RESIDENT (2): as 1, but through a RESIDENT kernel (handles that use the small-batch kernel; larger
- * ones fall back to 1).  The first call launches it on `stream`; it keeps the tables in shared memory, polls a doorbell
+ * zero_copy == GW_HOST_RESIDENT (2): as 1, but through a RESIDENT kernel (handles of up to 24 576 envs; larger ones fall
+ * back to 1).  The first call launches it on `stream`; it keeps the tables in shared memory, polls a doorbell
  * in pinned host memory, steps, and reports completion through pinned host memory, so a step costs neither a launch nor
  * a stream synchronisation.  On return the host buffers hold the step's results and the device outputs (observations,
  * masks ...) are complete in HBM; work queued on `stream` runs once the resident kernel has left: at the next gw_* call

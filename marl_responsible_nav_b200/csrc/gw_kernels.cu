@@ -2050,6 +2050,13 @@ static int pick_tile(long long E) {
   return E <= 24576 ? 32 : (E <= 196608 ? 128 : 256);
 }
 
+// Resident step kernel (gw_step_host mode 2): the 8-lanes-per-env body walking several tiles per CTA still beats a launch
+// per step well past the small-batch threshold (measured, profiles/README.md); GW_RESIDENT_MAX overrides (dev).
+static bool pick_resident(long long E) {
+  static const long long lim = [] { const char* v = std::getenv("GW_RESIDENT_MAX"); return v ? std::atoll(v) : 24576ll; }();
+  return E <= lim;
+}
+
 static bool pick_small(long long E) {
   if (const char* s = std::getenv("GW_SMALL")) return std::atoi(s) != 0;
   return E <= 6144;
@@ -2388,7 +2395,7 @@ int gw_step_host(gw_handle* h, const gw_io* io, const int8_t* host_actions, floa
     if (host_reward) z.reward = host_reward;
     if (host_shaped) z.shaped_reward = host_shaped;
     if (host_ended) z.ended = host_ended;
-    if (zero_copy == GW_HOST_RESIDENT && pick_small(h->cfg.num_envs) && !h->srv.disabled) {
+    if (zero_copy == GW_HOST_RESIDENT && pick_resident(h->cfg.num_envs) && !h->srv.disabled) {
       if (int rc = check_io(h, &z, true)) return rc;
       if (!h->reset_done) return fail(h, GW_ESTATE, "gw_step_host: call gw_reset first");
       const int rc = server_step(h, z, static_cast<cudaStream_t>(stream));

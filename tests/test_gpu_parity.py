@@ -262,7 +262,8 @@ def test_step_host_matches_device_step():
         a.step_host(acts[0].clone(), rew, end)          # not pinned
 
 
-@pytest.mark.parametrize("E,fear,bf16", [(4096, True, False), (1001, True, True), (6144, False, False), (77, True, False)])
+@pytest.mark.parametrize("E,fear,bf16", [(4096, True, False), (1001, True, True), (6144, False, False), (77, True, False),
+                                         (12000, True, False)])      # 12000 envs: 375 tiles on 296 CTAs, some walk two tiles
 def test_step_host_resident_kernel(E, fear, bf16):
     """gw_step_host mode 2 (resident kernel: doorbell / completion word in pinned host memory) == gw_step, step after
     step and in the final state; survives idle exits, relaunches, and other calls in between."""
