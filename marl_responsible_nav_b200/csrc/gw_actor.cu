@@ -3,19 +3,22 @@
 // Per learner k: obs(160) -> Linear 128 -> LayerNorm -> ReLU -> Linear 128 -> LayerNorm -> ReLU -> Linear 9 ->
 // GumbelSoftmax (+ Gaussian exploration noise, clip [0,1], action mask, arg-max).
 //
-// One CTA = 256 threads on a tile of up to 128 rows (envs) of one learner:
-//   layer 1  An observation is the constant map template plus <= 5 special cells, so W1*obs + b1 is a per-learner
-//            constant vector plus <= 5 columns of W1 scaled by (value - template value).  Built from the 8-byte obs_code
-//            gw_step wrote; the 640-byte observation is never read.  Each of the 8 warps walks its share of the rows
-//            together (lane l owns output columns 4l..4l+3: a W1 column is one coalesced 512-byte read, LayerNorm is a
-//            warp reduction); the row goes to shared memory as bf16 in the canonical K-major UMMA layout.
-//   layer 2  [128 x 128] x [128 x 128]^T on the tensor cores: W2 arrives by one TMA bulk copy (already in UMMA layout in
-//            HBM), one elected thread issues 8 tcgen05.mma (M=128, N=128, K=16, bf16 -> fp32) that accumulate in TMEM,
-//            tcgen05.commit arrives on an mbarrier.
-//   epilogue warps w and w+4 share TMEM lanes 32*(w&3).. (a warp reaches the lane quarter of its id mod 4), 64 columns
-//            each (tcgen05.ld, thread = row): LayerNorm sums and the 128 -> 9 products are halved between the two
-//            threads of a row and joined through shared memory; the first one finishes Gumbel softmax / noise / mask /
-//            arg-max.  Small batches use half-full tiles (64 rows) so that the grid covers the machine.
+// One CTA = 512 threads on a tile of up to 128 rows (envs) of one learner; both 128-wide layers run on the tensor cores:
+//   layer 1  An observation is the constant map template plus <= 5 special cells, so W1*obs + b1 = c1 + W1 * delta with
+//            c1 = b1 + W1 * template (fp32, exact) and delta non-zero in <= 5 cells.  The A operand is an all-zero
+//            [128 x cells] bf16 tile in which each row's thread drops its <= 5 values (0.5, 1..5, 9.5, 10..14: exact in
+//            bf16) -- built from the 8-byte obs_code gw_step wrote; the 640-byte observation is never read.  cells / 16
+//            tcgen05.mma (M=128, N=128, K=16, bf16 -> fp32) against W1 (bf16, UMMA layout, one TMA bulk copy) accumulate
+//            in TMEM columns 0..127.
+//   LN 1     warps w, w+4, w+8, w+12 reach the same TMEM lane quarter (a warp's lanes are those of its id mod 4) and take
+//            32 of the 128 columns each (tcgen05.ld, thread = row): + c1, LayerNorm (partial sums joined through shared
+//            memory), ReLU, bf16 into the A operand of layer 2 (UMMA K-major core matrices; it reuses the space of the
+//            layer-1 operand, which is cleared again once layer 2 has read it).
+//   layer 2  [128 x 128] x W2^T: 8 tcgen05.mma into TMEM columns 128..255, tcgen05.commit arrives on an mbarrier.
+//   epilogue the same four-way column split: LayerNorm, ReLU and the 128 -> 9 products per column group, joined through
+//            shared memory; the first group finishes Gumbel softmax / noise / mask / arg-max.  The Philox words of the
+//            noise are drawn by all threads while layer 1 runs.  Small batches use half-full tiles (64 rows) so that the
+//            grid covers the machine.
 // sm_100a only (tcgen05 / TMEM); descriptors follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
 #include <cstdio>
 #include <cstring>
@@ -33,8 +36,8 @@ namespace gwa {
 constexpr int HID = 128, NACT = GW_N_ACTIONS, ROWS = 128, MAX_CELLS = GW_MAX_H * GW_W;
 
 struct ActorParams {                     // device-resident, per learner
-  float w1t[MAX_CELLS][HID];             // W1 transposed: one 512-byte row per observation cell
-  float c1[HID];                         // b1 + W1 * template row
+  alignas(16) __nv_bfloat16 w1_umma[HID * MAX_CELLS];   // W1 [out n][in cell] in the canonical K-major core-matrix layout
+  float c1[HID];                         // b1 + W1 * template row (fp32)
   float ln1_g[HID], ln1_b[HID];
   alignas(16) __nv_bfloat16 w2_umma[HID * HID];   // W2 [out n][in k] in the canonical K-major core-matrix layout
   float b2[HID], ln2_g[HID], ln2_b[HID];
@@ -86,19 +89,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
-struct Smem {
-  alignas(1024) uint8_t a_tile[ROWS * HID * 2];     // activations of layer 1 (bf16, UMMA layout)
-  alignas(1024) uint8_t b_tile[HID * HID * 2];      // W2
+constexpr int THREADS = 512, NGRP = THREADS / 128;   // column groups of the epilogues (warps sharing a TMEM lane quarter)
+constexpr int CPG = HID / NGRP;                       // columns per group
+
+// Dynamic shared memory: [a_tile: 128 x cells bf16 (layer-1 operand; its first 32 KB double as the layer-2 operand)]
+// [w1: 128 x cells bf16] [Fixed]
+struct Fixed {
+  alignas(1024) uint8_t w2[HID * HID * 2];
   alignas(16) float w3[NACT][HID];
   float b3[NACT];
-  float b2[HID], ln2_g[HID], ln2_b[HID];
-  alignas(8) float2 part[2][ROWS];                  // epilogue: LayerNorm partial (sum, sum of squares) per column half and row
-  float plog[ROWS][NACT + 1];                       // epilogue: the upper column half's share of the 9 logits
-  uint32_t rnd[ROWS][29];                           // Philox words of the head's noise, drawn by all threads while the MMA runs
-  alignas(8) unsigned long long bar, bar_w;         // MMA completion; arrival of W2
+  float c1[HID], ln1_g[HID], ln1_b[HID], b2[HID], ln2_g[HID], ln2_b[HID];
+  alignas(8) float2 part[NGRP][ROWS];               // LayerNorm partial (sum, sum of squares) per column group and row
+  float plog[NGRP - 1][ROWS][NACT + 1];             // the other groups' shares of the 9 logits
+  uint32_t rnd[ROWS][29];                           // Philox words of the head's noise
+  alignas(8) unsigned long long bar, bar_w;         // MMA completion; arrival of W1 / W2
   uint32_t tmem_base;
 };
-constexpr int THREADS = 256;
+__host__ __device__ inline size_t smem_bytes(int cells) { return (size_t)2 * ROWS * cells * 2 + sizeof(Fixed) + 1024; }
 
 __device__ __forceinline__ float gumbel_from(uint32_t w) {
   const float u = fmaxf(((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f), 1e-20f);
@@ -109,141 +116,125 @@ __device__ __forceinline__ float gauss_from(uint32_t a, uint32_t b) {          /
   return sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307f * u2);
 }
 
-__global__ void __launch_bounds__(THREADS, 2) actor_forward_kernel(FwdArgs a) {
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void mma_k16(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, int k_steps) {
+  for (int kk = 0; kk < k_steps; ++kk) {
+    const uint64_t da = smem_desc(a_addr + kk * 4096), db = smem_desc(b_addr + kk * 4096);
+    const uint32_t acc = kk > 0 ? 1u : 0u;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(acc)
+        : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  const int cells = a.cpo;                                 // K of layer 1: a multiple of 16 (H x 16)
+  const uint32_t op_bytes = (uint32_t)ROWS * cells * 2;
+  uint8_t* const a_tile = smem_raw;
+  uint8_t* const w1_tile = smem_raw + op_bytes;
+  Fixed& s = *reinterpret_cast<Fixed*>(smem_raw + 2 * (size_t)op_bytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int k = blockIdx.y;                               // learner
   const ActorParams& P = a.params[k];
   const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.bar), bar_w = (uint32_t)__cvta_generic_to_shared(&s.bar_w);
   const int RT = a.rows_per_tile;
 
-  // ---- one-time setup: TMEM columns for the 128x128 fp32 accumulator, mbarriers, W2 by TMA, W3 / LN2 into shared memory
+  // ---- one-time setup: 256 TMEM columns (two 128x128 fp32 accumulators), mbarriers, W1 / W2 by TMA, the small vectors
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     (uint32_t)__cvta_generic_to_shared(&s.tmem_base)), "n"(HID));
+                     (uint32_t)__cvta_generic_to_shared(&s.tmem_base)), "n"(2 * HID));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "n"(HID * HID * 2) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(op_bytes + (uint32_t)(HID * HID * 2)) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"((uint32_t)__cvta_generic_to_shared(s.b_tile)), "l"(P.w2_umma), "n"(HID * HID * 2), "r"(bar_w) : "memory");
+                 ::"r"((uint32_t)__cvta_generic_to_shared(w1_tile)), "l"(P.w1_umma), "r"(op_bytes), "r"(bar_w) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(s.w2)), "l"(P.w2_umma), "n"(HID * HID * 2), "r"(bar_w) : "memory");
   }
   {
+    for (int i = tid; i < (int)(op_bytes / 16); i += THREADS) reinterpret_cast<uint4*>(a_tile)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < NACT * HID; i += THREADS) (&s.w3[0][0])[i] = (&P.w3[0][0])[i];
     if (tid < NACT) s.b3[tid] = P.b3[tid];
     if (tid < HID) {
-      s.b2[tid] = P.b2[tid];
-      s.ln2_g[tid] = P.ln2_g[tid];
-      s.ln2_b[tid] = P.ln2_b[tid];
+      s.c1[tid] = P.c1[tid]; s.ln1_g[tid] = P.ln1_g[tid]; s.ln1_b[tid] = P.ln1_b[tid];
+      s.b2[tid] = P.b2[tid]; s.ln2_g[tid] = P.ln2_g[tid]; s.ln2_b[tid] = P.ln2_b[tid];
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = s.tmem_base;
-  const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(s.a_tile);
-  const uint32_t b_addr = (uint32_t)__cvta_generic_to_shared(s.b_tile);
+  const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(a_tile);
+  const uint32_t w1_addr = (uint32_t)__cvta_generic_to_shared(w1_tile);
+  const uint32_t w2_addr = (uint32_t)__cvta_generic_to_shared(s.w2);
   uint32_t phase = 0;
-  bool w2_pending = true;
+  bool w_pending = true;
 
-  const int rpw = RT / 8;                                  // rows of a tile per warp in layer 1 (16 or 8)
-  const int q = warp & 3, hf = warp >> 2;                  // epilogue: TMEM lane quarter, column half
-  const int m = q * 32 + lane;                             // epilogue: this thread's row of the tile
+  const int q = warp & 3, cg = warp >> 2;                  // TMEM lane quarter, column group
+  const int m = q * 32 + lane;                             // this thread's row of the tile
+  const int col0 = cg * CPG;
+  const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+  const bool quarter_on = q * 32 < RT;                     // warp-uniform: a half-full tile fills lane quarters 0 and 1
   const long long n_tiles = (a.E + RT - 1) / RT;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    // ---- layer 1 from the observation code: h = c1 + sum_s (value_s - template_s) * W1[:, cell_s]; template_s = 0
-    // (agents and apples only stand on active cells).  Lane i < rpw decodes the special cells of the warp's i-th row;
-    // then the warp walks its rows together: lane l owns output columns 4l..4l+3.
-    uint32_t my_cells = 0xFFFFFFFFu, my_cell4 = 0xFFu;   // up to five cells (0xFF = unused) ...
-    float my_vals[5] = {0.f, 0.f, 0.f, 0.f, 0.f};        // ... and their values
-    {
-      const long long e1 = tile * RT + warp * rpw + lane;
-      if (lane < rpw && e1 < a.E) {
-        const unsigned long long code = a.obs_code[e1];
-        const uint32_t cells = (uint32_t)code, apples = (uint32_t)(code >> 32) & 3u;
-        const bool fresh = (code >> 34) & 1ull;
-        const bool apple_on = (a.kind == GW_ENV_MULTI) ? ((apples >> k) & 1u) : (apples & 1u);
-        const uint32_t apple = (a.kind == GW_ENV_MULTI) ? (a.apple_cells >> (8 * k)) & 0xFFu : a.apple_cells & 0xFFu;
-        bool covered = false;
-        my_cells = 0;
+    const long long e = tile * RT + m;
+    const bool live = quarter_on && m < RT && e < a.E;
+
+    // ---- layer-1 operand: the row's special cells (delta against the template, which is 0 on every active cell)
+    if (cg == 0 && live) {
+      const unsigned long long code = a.obs_code[e];
+      const uint32_t cellsw = (uint32_t)code, apples = (uint32_t)(code >> 32) & 3u;
+      const bool fresh = (code >> 34) & 1ull;
+      const bool apple_on = (a.kind == GW_ENV_MULTI) ? ((apples >> k) & 1u) : (apples & 1u);
+      const uint32_t apple = (a.kind == GW_ENV_MULTI) ? (a.apple_cells >> (8 * k)) & 0xFFu : a.apple_cells & 0xFFu;
+      bool covered = false;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t c = (cells >> (8 * i)) & 0xFFu;
-          const bool on = i < a.n;
-          const bool here = on && apple_on && c == apple;
-          covered |= here;
-          float v;                                         // same value rules as the renderer (ma_customenv.py:303-322)
-          if (fresh) v = 0.5f;
-          else if (here || a.kind == GW_ENV_SINGLE) v = (float)(i + 1);
-          else v = (i == k) ? 1.0f : 5.0f;
-          my_cells |= (on ? c : 0xFFu) << (8 * i);
-          my_vals[i] = here ? v + 9.0f : v;
-        }
-        if (apple_on && !covered) { my_cell4 = apple; my_vals[4] = 9.0f; }
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t c = (cellsw >> (8 * i)) & 0xFFu;
+        const bool here = i < a.n && apple_on && c == apple;
+        covered |= here;
+        float v;                                           // same value rules as the renderer (ma_customenv.py:303-322)
+        if (fresh) v = 0.5f;
+        else if (here || a.kind == GW_ENV_SINGLE) v = (float)(i + 1);
+        else v = (i == k) ? 1.0f : 5.0f;
+        if (i < a.n && (int)c < cells) *reinterpret_cast<__nv_bfloat16*>(a_tile + umma_off(m, (int)c)) = __float2bfloat16(here ? v + 9.0f : v);
       }
+      if (apple_on && !covered && (int)apple < cells) *reinterpret_cast<__nv_bfloat16*>(a_tile + umma_off(m, (int)apple)) = __float2bfloat16(9.0f);
     }
-    const float4 c1v = *reinterpret_cast<const float4*>(&P.c1[4 * lane]);
-    const float4 g1v = *reinterpret_cast<const float4*>(&P.ln1_g[4 * lane]);
-    const float4 b1v = *reinterpret_cast<const float4*>(&P.ln1_b[4 * lane]);
-#pragma unroll 2
-    for (int i = 0; i < rpw; ++i) {
-      const uint32_t rc = __shfl_sync(0xFFFFFFFFu, my_cells, i), rc4 = __shfl_sync(0xFFFFFFFFu, my_cell4, i);
-      float4 h = c1v;
-#pragma unroll
-      for (int qq = 0; qq < 5; ++qq) {
-        const float v = __shfl_sync(0xFFFFFFFFu, my_vals[qq], i);
-        const uint32_t c = qq < 4 ? (rc >> (8 * qq)) & 0xFFu : rc4;
-        if (c != 0xFFu) {                                // warp-uniform
-          const float4 w = __ldg(reinterpret_cast<const float4*>(P.w1t[c]) + lane);
-          h.x = fmaf(v, w.x, h.x); h.y = fmaf(v, w.y, h.y); h.z = fmaf(v, w.z, h.z); h.w = fmaf(v, w.w, h.w);
-        }
-      }
-      float sum = (h.x + h.y) + (h.z + h.w), sq = fmaf(h.x, h.x, fmaf(h.y, h.y, fmaf(h.z, h.z, h.w * h.w)));
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
-        sq += __shfl_xor_sync(0xFFFFFFFFu, sq, d);
-      }
-      const float mean = sum * (1.0f / HID);
-      const float rstd = rsqrtf(fmaxf(sq * (1.0f / HID) - mean * mean, 0.f) + 1e-5f);
-      const bool row_live = (rc != 0xFFFFFFFFu);
-      const float x0 = row_live ? fmaxf((h.x - mean) * rstd * g1v.x + b1v.x, 0.f) : 0.f;
-      const float x1 = row_live ? fmaxf((h.y - mean) * rstd * g1v.y + b1v.y, 0.f) : 0.f;
-      const float x2 = row_live ? fmaxf((h.z - mean) * rstd * g1v.z + b1v.z, 0.f) : 0.f;
-      const float x3 = row_live ? fmaxf((h.w - mean) * rstd * g1v.w + b1v.w, 0.f) : 0.f;
-      const uint32_t p0 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(x0)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16(x1)) << 16);
-      const uint32_t p1 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(x2)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16(x3)) << 16);
-      *reinterpret_cast<uint2*>(s.a_tile + umma_off(warp * rpw + i, 4 * lane)) = make_uint2(p0, p1);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // activations -> visible to the tensor-core proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // operand -> visible to the tensor-core proxy
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    // ---- layer 2 on the tensor cores: D[128x128] (TMEM) = A[128x128] * W2^T, eight K=16 steps, one issuing thread.
-    // (Rows RT..127 of a half-full tile hold whatever shared memory held: they only reach accumulator rows nobody reads.)
+    // ---- layer 1 on the tensor cores: D0[128x128] (TMEM columns 0..127) = A[128 x cells] * W1^T
     if (tid == 0) {
-      if (w2_pending) mbar_wait(bar_w, 0u);
-#pragma unroll
-      for (int kk = 0; kk < HID / 16; ++kk) {
-        const uint64_t da = smem_desc(a_addr + kk * 4096), db = smem_desc(b_addr + kk * 4096);
-        const uint32_t acc = kk > 0 ? 1u : 0u;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(da), "l"(db), "r"(IDESC), "r"(acc)
-            : "memory");
-      }
+      if (w_pending) mbar_wait(bar_w, 0u);
+      mma_k16(tmem, a_addr, w1_addr, cells / 16);
       // completion of all prior MMAs arrives on the mbarrier (implies tcgen05.fence::before_thread_sync)
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
     }
-    w2_pending = false;
-    // ---- while the tensor cores work: the random words of the head (9 Gumbel uniforms + 9 x 2 Box-Muller uniforms per
-    // row, a pure function of seed / env / learner / step), 256 / RT threads per row
+    w_pending = false;
+    // ---- meanwhile: the random words of the head (9 Gumbel uniforms + 9 x 2 Box-Muller uniforms per row, a pure function
+    // of seed / env / learner / step), 512 / RT threads per row
     if (a.gumbel | a.explore) {
       const int tpr = THREADS / RT, rr = tid / tpr;
       const long long er = tile * RT + rr;
@@ -257,72 +248,113 @@ __global__ void __launch_bounds__(THREADS, 2) actor_forward_kernel(FwdArgs a) {
           for (int u = 0; u < 4; ++u) s.rnd[rr][4 * c + u] = w[u];
         }
     }
-    const bool quarter_on = q * 32 < RT;                   // warp-uniform: a half-full tile fills lane quarters 0 and 1
-    const long long e = tile * RT + m;
-    const bool live = quarter_on && m < RT && e < a.E;
-    float acc[HID / 2];
+    float acc[CPG];
     float mu_p = 0.f, sq_p = 0.f;
     mbar_wait(bar, phase);
     phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    // ---- epilogue, first half: this thread's 64 accumulator columns of its row
+    // ---- LayerNorm 1 + ReLU -> operand of layer 2 (this thread: 32 columns of its row)
     if (quarter_on) {
+      uint32_t r[32];
+      tmem_ld32(lane_addr + (uint32_t)col0, r);
 #pragma unroll
-      for (int c0 = 0; c0 < HID / 2; c0 += 32) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * (HID / 2) + c0);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int u = 0; u < 32; ++u) acc[c0 + u] = __uint_as_float(r[u]) + s.b2[hf * (HID / 2) + c0 + u];
+      for (int u = 0; u < CPG; ++u) {
+        acc[u] = __uint_as_float(r[u]) + s.c1[col0 + u];
+        mu_p += acc[u];
+        sq_p = fmaf(acc[u], acc[u], sq_p);
       }
-#pragma unroll
-      for (int j = 0; j < HID / 2; ++j) { mu_p += acc[j]; sq_p = fmaf(acc[j], acc[j], sq_p); }
-      s.part[hf][m] = make_float2(mu_p, sq_p);
+      s.part[cg][m] = make_float2(mu_p, sq_p);
     }
-    // TMEM has been read: the next tile's MMA may overwrite it once every warp is past the barrier
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();                                       // LayerNorm partials of both column halves are in shared memory
+    __syncthreads();                                       // partial sums of the four column groups; layer 1 has read its operand
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    if (quarter_on) {
+      float su = 0.f, sq = 0.f;
+#pragma unroll
+      for (int g = 0; g < NGRP; ++g) { const float2 pp = s.part[g][m]; su += pp.x; sq += pp.y; }
+      const float mu = su * (1.0f / HID);
+      const float rs = rsqrtf(fmaxf(sq * (1.0f / HID) - mu * mu, 0.f) + 1e-5f);
+#pragma unroll
+      for (int c8 = 0; c8 < CPG; c8 += 8) {                // one 16-byte core-matrix row per 8 columns
+        uint32_t pk[4];
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+          const int j = col0 + c8 + u;
+          const float x0 = live ? fmaxf((acc[c8 + u] - mu) * rs * s.ln1_g[j] + s.ln1_b[j], 0.f) : 0.f;
+          const float x1 = live ? fmaxf((acc[c8 + u + 1] - mu) * rs * s.ln1_g[j + 1] + s.ln1_b[j + 1], 0.f) : 0.f;
+          pk[u >> 1] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(x0)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16(x1)) << 16);
+        }
+        *reinterpret_cast<uint4*>(a_tile + umma_off(m, col0 + c8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+
+    // ---- layer 2: D1[128x128] (TMEM columns 128..255) = A2[128x128] * W2^T.  (Rows RT..127 of a half-full tile hold
+    // whatever the layer-1 operand held there -- zeros: they only reach accumulator rows nobody reads.)
+    if (tid == 0) {
+      mma_k16(tmem + (uint32_t)HID, a_addr, w2_addr, HID / 16);
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    }
+    mu_p = 0.f; sq_p = 0.f;
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;");
+
+    // ---- epilogue: LayerNorm 2 + ReLU + this column group's share of the 128 -> 9 layer
+    if (quarter_on) {
+      uint32_t r[32];
+      tmem_ld32(lane_addr + (uint32_t)(HID + col0), r);
+#pragma unroll
+      for (int u = 0; u < CPG; ++u) {
+        acc[u] = __uint_as_float(r[u]) + s.b2[col0 + u];
+        mu_p += acc[u];
+        sq_p = fmaf(acc[u], acc[u], sq_p);
+      }
+      s.part[cg][m] = make_float2(mu_p, sq_p);
+    }
+    // layer 2 has read its operand: back to the all-zero layer-1 operand for the next tile
+    for (int i = tid; i < (int)(op_bytes / 16); i += THREADS) reinterpret_cast<uint4*>(a_tile)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     float logit[NACT];
     if (quarter_on) {
-      const float2 other = s.part[hf ^ 1][m];
-      const float mu = (mu_p + other.x) * (1.0f / HID);
-      const float rs = rsqrtf(fmaxf((sq_p + other.y) * (1.0f / HID) - mu * mu, 0.f) + 1e-5f);
+      float su = 0.f, sq = 0.f;
 #pragma unroll
-      for (int o = 0; o < NACT; ++o) logit[o] = hf == 0 ? s.b3[o] : 0.f;
+      for (int g = 0; g < NGRP; ++g) { const float2 pp = s.part[g][m]; su += pp.x; sq += pp.y; }
+      const float mu = su * (1.0f / HID);
+      const float rs = rsqrtf(fmaxf(sq * (1.0f / HID) - mu * mu, 0.f) + 1e-5f);
 #pragma unroll
-      for (int j0 = 0; j0 < HID / 2; j0 += 4) {
+      for (int o = 0; o < NACT; ++o) logit[o] = cg == 0 ? s.b3[o] : 0.f;
+#pragma unroll
+      for (int j0 = 0; j0 < CPG; j0 += 4) {
         float x[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int j = hf * (HID / 2) + j0 + u;
+          const int j = col0 + j0 + u;
           x[u] = fmaxf((acc[j0 + u] - mu) * rs * s.ln2_g[j] + s.ln2_b[j], 0.f);
         }
 #pragma unroll
         for (int o = 0; o < NACT; ++o) {
-          const float4 w = *reinterpret_cast<const float4*>(&s.w3[o][hf * (HID / 2) + j0]);   // same address in every lane: broadcast
+          const float4 w = *reinterpret_cast<const float4*>(&s.w3[o][col0 + j0]);   // same address in every lane: broadcast
           logit[o] = fmaf(x[0], w.x, fmaf(x[1], w.y, fmaf(x[2], w.z, fmaf(x[3], w.w, logit[o]))));
         }
       }
-      if (hf == 1) {
+      if (cg > 0) {
 #pragma unroll
-        for (int o = 0; o < NACT; ++o) s.plog[m][o] = logit[o];
+        for (int o = 0; o < NACT; ++o) s.plog[cg - 1][m][o] = logit[o];
       }
     }
-    __syncthreads();                                       // the upper half's share of the logits is in shared memory
-    if (live && hf == 0) {
+    __syncthreads();                                       // the other groups' shares of the logits are in shared memory
+    if (live && cg == 0) {
 #pragma unroll
-      for (int o = 0; o < NACT; ++o) logit[o] += s.plog[m][o];
+      for (int g = 0; g < NGRP - 1; ++g)
+#pragma unroll
+        for (int o = 0; o < NACT; ++o) logit[o] += s.plog[g][m][o];
       // GumbelSoftmax head (the reference's output activation draws fresh Gumbel noise on EVERY forward, evaluation
       // included) + Gaussian exploration noise (training), both from the Philox words drawn above
       if (a.gumbel) {
@@ -353,13 +385,13 @@ __global__ void __launch_bounds__(THREADS, 2) actor_forward_kernel(FwdArgs a) {
       }
       a.ids[e * a.nl + k] = (int8_t)best;
     }
-    // a_tile / part / plog are rewritten by the next tile only after its first barrier, which every warp reaches after
-    // it is done with them
+    // part / plog / rnd / the operand tile are rewritten by the next tile only behind barriers that every warp reaches
+    // after it is done with them
   }
-  if (w2_pending && tid == 0) mbar_wait(bar_w, 0u);        // a CTA without tiles must not exit with the copy in flight
+  if (w_pending && tid == 0) mbar_wait(bar_w, 0u);         // a CTA without tiles must not exit with the copies in flight
 
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(HID));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * HID));
 }
 
 // Weights straight from the trainer's device tensors (torch layout, fp32) into the kernel's packed form: the same
@@ -376,8 +408,8 @@ __global__ void __launch_bounds__(256) actor_pack_kernel(PackArgs a) {
   ActorParams& P = a.out[blockIdx.y];
   const int cpo = a.cpo, stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cpo * HID; i += stride) {
-    const int cell = i / HID, j = i % HID;
-    P.w1t[cell][j] = W.w1[j * cpo + cell];
+    const int j = i / cpo, cell = i % cpo;
+    P.w1_umma[umma_off(j, cell) / 2] = __float2bfloat16(W.w1[i]);
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HID * HID; i += stride) {
     const int n = i / HID, kk = i % HID;
@@ -417,7 +449,7 @@ static int pack_weights(gw_handle* h, const gw_actor_weights* w, int nl, std::ve
     for (int j = 0; j < gwa::HID; ++j) {
       double acc = W.b1[j];
       for (int cell = 0; cell < cpo; ++cell) {
-        P.w1t[cell][j] = W.w1[j * cpo + cell];
+        P.w1_umma[gwa::umma_off(j, cell) / 2] = __float2bfloat16(W.w1[j * cpo + cell]);
         const bool active = (c.map_rows[cell >> 4] >> (cell & 15)) & 1;
         if (!active) acc -= (double)W.w1[j * cpo + cell];              // template value -1 on inactive cells, 0 elsewhere
       }
@@ -451,7 +483,8 @@ int gw_actor_create(gw_handle* h, const gw_actor_weights* weights, int n_learner
   cudaError_t e = cudaMalloc(&a->d_params, sizeof(gwa::ActorParams) * n_learners);
   if (e == cudaSuccess) e = cudaMemcpy(a->d_params, host.data(), sizeof(gwa::ActorParams) * n_learners, cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(gwa::actor_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(gwa::Smem) + 1024);
+    e = cudaFuncSetAttribute(gwa::actor_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)gwa::smem_bytes(h->cfg.height * GW_W));
   if (e != cudaSuccess) {
     if (a->d_params) cudaFree(a->d_params);
     delete a;
@@ -532,9 +565,9 @@ int gw_actor_forward(gw_actor* a, int64_t num_envs, const uint64_t* obs_code, co
   // half-full tiles while full ones would leave SMs without a CTA (latency regime)
   f.rows_per_tile = ((num_envs + gwa::ROWS - 1) / gwa::ROWS) * nl < (long long)h->sm_count ? gwa::ROWS / 2 : gwa::ROWS;
   const long long tiles = (num_envs + f.rows_per_tile - 1) / f.rows_per_tile;
-  const long long cap = (long long)h->sm_count * 2 / nl;               // 2 CTAs per SM over all learners
+  const long long cap = (long long)h->sm_count / nl > 0 ? (long long)h->sm_count / nl : 1;   // one 512-thread CTA per SM over all learners
   dim3 grid((unsigned)(tiles < cap ? tiles : cap), (unsigned)h->cfg.n_learners);
-  gwa::actor_forward_kernel<<<grid, gwa::THREADS, sizeof(gwa::Smem) + 1024, static_cast<cudaStream_t>(stream)>>>(f);
+  gwa::actor_forward_kernel<<<grid, gwa::THREADS, gwa::smem_bytes(f.cpo), static_cast<cudaStream_t>(stream)>>>(f);
   GW_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return GW_OK;
