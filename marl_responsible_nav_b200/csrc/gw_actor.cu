@@ -21,6 +21,7 @@
 //            grid covers the machine.
 // sm_100a only (tcgen05 / TMEM); descriptors follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -89,23 +90,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
-constexpr int THREADS = 512, NGRP = THREADS / 128;   // column groups of the epilogues (warps sharing a TMEM lane quarter)
-constexpr int CPG = HID / NGRP;                       // columns per group
+constexpr int THREADS = 512;
 
-// Dynamic shared memory: [a_tile: 128 x cells bf16 (layer-1 operand; its first 32 KB double as the layer-2 operand)]
-// [w1: 128 x cells bf16] [Fixed]
+// GROUPS = 1: the CTA's 16 warps work on one tile (four column groups in the epilogues) -- shortest path for one tile,
+// used while the batch does not fill the machine.  GROUPS = 2: two groups of 8 warps work on two tiles out of phase (two
+// column groups each, own operand tile, own TMEM columns, own barriers), sharing W1 / W2: while one group waits for its
+// MMAs or barriers the other one has the issue slots.
+// Dynamic shared memory: [GROUPS x a_tile: 128 x cells bf16 (layer-1 operand; its first 32 KB double as the layer-2
+// operand)] [w1: 128 x cells bf16] [Fixed<GROUPS>]
+template <int GROUPS>
 struct Fixed {
+  static constexpr int NGRP = THREADS / GROUPS / 128;         // column groups of the epilogues (warps sharing a TMEM lane quarter)
   alignas(1024) uint8_t w2[HID * HID * 2];
   alignas(16) float w3[NACT][HID];
   float b3[NACT];
   float c1[HID], ln1_g[HID], ln1_b[HID], b2[HID], ln2_g[HID], ln2_b[HID];
-  alignas(8) float2 part[NGRP][ROWS];               // LayerNorm partial (sum, sum of squares) per column group and row
-  float plog[NGRP - 1][ROWS][NACT + 1];             // the other groups' shares of the 9 logits
-  uint32_t rnd[ROWS][29];                           // Philox words of the head's noise
-  alignas(8) unsigned long long bar, bar_w;         // MMA completion; arrival of W1 / W2
+  alignas(8) float2 part[GROUPS][NGRP][ROWS];       // LayerNorm partial (sum, sum of squares) per column group and row
+  float plog[GROUPS][NGRP - 1][ROWS][NACT + 1];     // the other column groups' shares of the 9 logits
+  uint32_t rnd[GROUPS][ROWS][29];                   // Philox words of the head's noise
+  alignas(8) unsigned long long bar[GROUPS], bar_w; // MMA completion per group; arrival of W1 / W2
   uint32_t tmem_base;
 };
-__host__ __device__ inline size_t smem_bytes(int cells) { return (size_t)2 * ROWS * cells * 2 + sizeof(Fixed) + 1024; }
+template <int GROUPS>
+__host__ __device__ inline size_t smem_bytes(int cells) { return (size_t)(GROUPS + 1) * ROWS * cells * 2 + sizeof(Fixed<GROUPS>) + 1024; }
 
 __device__ __forceinline__ float gumbel_from(uint32_t w) {
   const float u = fmaxf(((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f), 1e-20f);
@@ -141,27 +148,34 @@ __device__ __forceinline__ void mma_k16(uint32_t tmem_d, uint32_t a_addr, uint32
   }
 }
 
+template <int GROUPS>
 __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
+  constexpr int TPG = THREADS / GROUPS, NGRP = Fixed<GROUPS>::NGRP, CPG = HID / NGRP;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int cells = a.cpo;                                 // K of layer 1: a multiple of 16 (H x 16)
   const uint32_t op_bytes = (uint32_t)ROWS * cells * 2;
-  uint8_t* const a_tile = smem_raw;
-  uint8_t* const w1_tile = smem_raw + op_bytes;
-  Fixed& s = *reinterpret_cast<Fixed*>(smem_raw + 2 * (size_t)op_bytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gi = tid / TPG, lt = tid % TPG;                // group, thread within the group
+  uint8_t* const a_tile = smem_raw + (size_t)gi * op_bytes;
+  uint8_t* const w1_tile = smem_raw + (size_t)GROUPS * op_bytes;
+  Fixed<GROUPS>& s = *reinterpret_cast<Fixed<GROUPS>*>(smem_raw + (size_t)(GROUPS + 1) * op_bytes);
+  auto group_sync = [&]() {                                // barrier of this group's TPG threads (id 0 is __syncthreads)
+    if (GROUPS == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + gi), "n"(TPG) : "memory");
+  };
   const int k = blockIdx.y;                               // learner
   const ActorParams& P = a.params[k];
-  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.bar), bar_w = (uint32_t)__cvta_generic_to_shared(&s.bar_w);
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.bar[gi]), bar_w = (uint32_t)__cvta_generic_to_shared(&s.bar_w);
   const int RT = a.rows_per_tile;
 
-  // ---- one-time setup: 256 TMEM columns (two 128x128 fp32 accumulators), mbarriers, W1 / W2 by TMA, the small vectors
+  // ---- one-time setup: 256 TMEM columns per group (two 128x128 fp32 accumulators), mbarriers, W1 / W2 by TMA, the small vectors
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     (uint32_t)__cvta_generic_to_shared(&s.tmem_base)), "n"(2 * HID));
+                     (uint32_t)__cvta_generic_to_shared(&s.tmem_base)), "n"(GROUPS * 2 * HID));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    mbar_init(bar, 1);
+    for (int g = 0; g < GROUPS; ++g) mbar_init((uint32_t)__cvta_generic_to_shared(&s.bar[g]), 1);
     mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(op_bytes + (uint32_t)(HID * HID * 2)) : "memory");
@@ -171,7 +185,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
                  ::"r"((uint32_t)__cvta_generic_to_shared(s.w2)), "l"(P.w2_umma), "n"(HID * HID * 2), "r"(bar_w) : "memory");
   }
   {
-    for (int i = tid; i < (int)(op_bytes / 16); i += THREADS) reinterpret_cast<uint4*>(a_tile)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = lt; i < (int)(op_bytes / 16); i += TPG) reinterpret_cast<uint4*>(a_tile)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < NACT * HID; i += THREADS) (&s.w3[0][0])[i] = (&P.w3[0][0])[i];
     if (tid < NACT) s.b3[tid] = P.b3[tid];
     if (tid < HID) {
@@ -182,20 +196,21 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
-  const uint32_t tmem = s.tmem_base;
+  const uint32_t tmem_all = s.tmem_base;
+  const uint32_t tmem = tmem_all + (uint32_t)(gi * 2 * HID);   // this group's columns
   const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(a_tile);
   const uint32_t w1_addr = (uint32_t)__cvta_generic_to_shared(w1_tile);
   const uint32_t w2_addr = (uint32_t)__cvta_generic_to_shared(s.w2);
   uint32_t phase = 0;
   bool w_pending = true;
 
-  const int q = warp & 3, cg = warp >> 2;                  // TMEM lane quarter, column group
+  const int q = warp & 3, cg = (lt >> 5) >> 2;             // TMEM lane quarter (warp id mod 4: TPG is a multiple of 128), column group
   const int m = q * 32 + lane;                             // this thread's row of the tile
   const int col0 = cg * CPG;
   const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
   const bool quarter_on = q * 32 < RT;                     // warp-uniform: a half-full tile fills lane quarters 0 and 1
   const long long n_tiles = (a.E + RT - 1) / RT;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (long long tile = (long long)blockIdx.x * GROUPS + gi; tile < n_tiles; tile += (long long)gridDim.x * GROUPS) {
     const long long e = tile * RT + m;
     const bool live = quarter_on && m < RT && e < a.E;
 
@@ -222,11 +237,11 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // operand -> visible to the tensor-core proxy
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
+    group_sync();
     asm volatile("tcgen05.fence::after_thread_sync;");
 
     // ---- layer 1 on the tensor cores: D0[128x128] (TMEM columns 0..127) = A[128 x cells] * W1^T
-    if (tid == 0) {
+    if (lt == 0) {
       if (w_pending) mbar_wait(bar_w, 0u);
       mma_k16(tmem, a_addr, w1_addr, cells / 16);
       // completion of all prior MMAs arrives on the mbarrier (implies tcgen05.fence::before_thread_sync)
@@ -236,16 +251,16 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
     // ---- meanwhile: the random words of the head (9 Gumbel uniforms + 9 x 2 Box-Muller uniforms per row, a pure function
     // of seed / env / learner / step), 512 / RT threads per row
     if (a.gumbel | a.explore) {
-      const int tpr = THREADS / RT, rr = tid / tpr;
+      const int tpr = TPG / RT, rr = lt / tpr;
       const long long er = tile * RT + rr;
       const int n_calls = a.explore ? 7 : 3;
       if (er < a.E)
-        for (int c = tid % tpr; c < n_calls; c += tpr) {
+        for (int c = lt % tpr; c < n_calls; c += tpr) {
           uint32_t w[4] = {(uint32_t)er, (uint32_t)((unsigned long long)er >> 32) ^ ((uint32_t)k << 24) ^ ((uint32_t)c << 28),
                            a.step_lo, a.step_hi ^ 0xAC70u};
           gw::philox4x32(w, a.seed_lo, a.seed_hi);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) s.rnd[rr][4 * c + u] = w[u];
+          for (int u = 0; u < 4; ++u) s.rnd[gi][rr][4 * c + u] = w[u];
         }
     }
     float acc[CPG];
@@ -256,23 +271,26 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
 
     // ---- LayerNorm 1 + ReLU -> operand of layer 2 (this thread: 32 columns of its row)
     if (quarter_on) {
-      uint32_t r[32];
-      tmem_ld32(lane_addr + (uint32_t)col0, r);
 #pragma unroll
-      for (int u = 0; u < CPG; ++u) {
-        acc[u] = __uint_as_float(r[u]) + s.c1[col0 + u];
-        mu_p += acc[u];
-        sq_p = fmaf(acc[u], acc[u], sq_p);
+      for (int c0 = 0; c0 < CPG; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(lane_addr + (uint32_t)(col0 + c0), r);
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          acc[c0 + u] = __uint_as_float(r[u]) + s.c1[col0 + c0 + u];
+          mu_p += acc[c0 + u];
+          sq_p = fmaf(acc[c0 + u], acc[c0 + u], sq_p);
+        }
       }
-      s.part[cg][m] = make_float2(mu_p, sq_p);
+      s.part[gi][cg][m] = make_float2(mu_p, sq_p);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();                                       // partial sums of the four column groups; layer 1 has read its operand
+    group_sync();                                       // partial sums of the four column groups; layer 1 has read its operand
     asm volatile("tcgen05.fence::after_thread_sync;");
     if (quarter_on) {
       float su = 0.f, sq = 0.f;
 #pragma unroll
-      for (int g = 0; g < NGRP; ++g) { const float2 pp = s.part[g][m]; su += pp.x; sq += pp.y; }
+      for (int g = 0; g < NGRP; ++g) { const float2 pp = s.part[gi][g][m]; su += pp.x; sq += pp.y; }
       const float mu = su * (1.0f / HID);
       const float rs = rsqrtf(fmaxf(sq * (1.0f / HID) - mu * mu, 0.f) + 1e-5f);
 #pragma unroll
@@ -290,12 +308,12 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
+    group_sync();
     asm volatile("tcgen05.fence::after_thread_sync;");
 
     // ---- layer 2: D1[128x128] (TMEM columns 128..255) = A2[128x128] * W2^T.  (Rows RT..127 of a half-full tile hold
     // whatever the layer-1 operand held there -- zeros: they only reach accumulator rows nobody reads.)
-    if (tid == 0) {
+    if (lt == 0) {
       mma_k16(tmem + (uint32_t)HID, a_addr, w2_addr, HID / 16);
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
     }
@@ -306,26 +324,29 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
 
     // ---- epilogue: LayerNorm 2 + ReLU + this column group's share of the 128 -> 9 layer
     if (quarter_on) {
-      uint32_t r[32];
-      tmem_ld32(lane_addr + (uint32_t)(HID + col0), r);
 #pragma unroll
-      for (int u = 0; u < CPG; ++u) {
-        acc[u] = __uint_as_float(r[u]) + s.b2[col0 + u];
-        mu_p += acc[u];
-        sq_p = fmaf(acc[u], acc[u], sq_p);
+      for (int c0 = 0; c0 < CPG; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(lane_addr + (uint32_t)(HID + col0 + c0), r);
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          acc[c0 + u] = __uint_as_float(r[u]) + s.b2[col0 + c0 + u];
+          mu_p += acc[c0 + u];
+          sq_p = fmaf(acc[c0 + u], acc[c0 + u], sq_p);
+        }
       }
-      s.part[cg][m] = make_float2(mu_p, sq_p);
+      s.part[gi][cg][m] = make_float2(mu_p, sq_p);
     }
     // layer 2 has read its operand: back to the all-zero layer-1 operand for the next tile
-    for (int i = tid; i < (int)(op_bytes / 16); i += THREADS) reinterpret_cast<uint4*>(a_tile)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = lt; i < (int)(op_bytes / 16); i += TPG) reinterpret_cast<uint4*>(a_tile)[i] = make_uint4(0, 0, 0, 0);
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
+    group_sync();
     asm volatile("tcgen05.fence::after_thread_sync;");
     float logit[NACT];
     if (quarter_on) {
       float su = 0.f, sq = 0.f;
 #pragma unroll
-      for (int g = 0; g < NGRP; ++g) { const float2 pp = s.part[g][m]; su += pp.x; sq += pp.y; }
+      for (int g = 0; g < NGRP; ++g) { const float2 pp = s.part[gi][g][m]; su += pp.x; sq += pp.y; }
       const float mu = su * (1.0f / HID);
       const float rs = rsqrtf(fmaxf(sq * (1.0f / HID) - mu * mu, 0.f) + 1e-5f);
 #pragma unroll
@@ -346,20 +367,20 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
       }
       if (cg > 0) {
 #pragma unroll
-        for (int o = 0; o < NACT; ++o) s.plog[cg - 1][m][o] = logit[o];
+        for (int o = 0; o < NACT; ++o) s.plog[gi][cg - 1][m][o] = logit[o];
       }
     }
-    __syncthreads();                                       // the other groups' shares of the logits are in shared memory
+    group_sync();                                       // the other groups' shares of the logits are in shared memory
     if (live && cg == 0) {
 #pragma unroll
       for (int g = 0; g < NGRP - 1; ++g)
 #pragma unroll
-        for (int o = 0; o < NACT; ++o) logit[o] += s.plog[g][m][o];
+        for (int o = 0; o < NACT; ++o) logit[o] += s.plog[gi][g][m][o];
       // GumbelSoftmax head (the reference's output activation draws fresh Gumbel noise on EVERY forward, evaluation
       // included) + Gaussian exploration noise (training), both from the Philox words drawn above
       if (a.gumbel) {
 #pragma unroll
-        for (int o = 0; o < NACT; ++o) logit[o] += gumbel_from(s.rnd[m][o]);
+        for (int o = 0; o < NACT; ++o) logit[o] += gumbel_from(s.rnd[gi][m][o]);
       }
       float mx = logit[0];
 #pragma unroll
@@ -376,7 +397,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
       for (int o = 0; o < NACT; ++o) {
         float v = pr[o] * inv;
         if (a.explore) {
-          const float g = gauss_from(s.rnd[m][9 + 2 * o], s.rnd[m][10 + 2 * o]);
+          const float g = gauss_from(s.rnd[gi][m][9 + 2 * o], s.rnd[gi][m][10 + 2 * o]);
           v = fminf(fmaxf(v + a.mean_noise + a.expl_noise * g, 0.f), 1.f);
         }
         out[o] = v;
@@ -388,10 +409,10 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
     // part / plog / rnd / the operand tile are rewritten by the next tile only behind barriers that every warp reaches
     // after it is done with them
   }
-  if (w_pending && tid == 0) mbar_wait(bar_w, 0u);         // a CTA without tiles must not exit with the copies in flight
+  if (w_pending && tid == 0) mbar_wait(bar_w, 0u);         // a CTA whose first group has no tile must not exit with the copies in flight
 
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * HID));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_all), "n"(GROUPS * 2 * HID));
 }
 
 // Weights straight from the trainer's device tensors (torch layout, fp32) into the kernel's packed form: the same
@@ -483,8 +504,11 @@ int gw_actor_create(gw_handle* h, const gw_actor_weights* weights, int n_learner
   cudaError_t e = cudaMalloc(&a->d_params, sizeof(gwa::ActorParams) * n_learners);
   if (e == cudaSuccess) e = cudaMemcpy(a->d_params, host.data(), sizeof(gwa::ActorParams) * n_learners, cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(gwa::actor_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)gwa::smem_bytes(h->cfg.height * GW_W));
+    e = cudaFuncSetAttribute(gwa::actor_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)gwa::smem_bytes<1>(h->cfg.height * GW_W));
+  if (e == cudaSuccess && gwa::smem_bytes<2>(h->cfg.height * GW_W) <= (size_t)227 * 1024)
+    e = cudaFuncSetAttribute(gwa::actor_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)gwa::smem_bytes<2>(h->cfg.height * GW_W));
   if (e != cudaSuccess) {
     if (a->d_params) cudaFree(a->d_params);
     delete a;
@@ -566,8 +590,18 @@ int gw_actor_forward(gw_actor* a, int64_t num_envs, const uint64_t* obs_code, co
   f.rows_per_tile = ((num_envs + gwa::ROWS - 1) / gwa::ROWS) * nl < (long long)h->sm_count ? gwa::ROWS / 2 : gwa::ROWS;
   const long long tiles = (num_envs + f.rows_per_tile - 1) / f.rows_per_tile;
   const long long cap = (long long)h->sm_count / nl > 0 ? (long long)h->sm_count / nl : 1;   // one 512-thread CTA per SM over all learners
-  dim3 grid((unsigned)(tiles < cap ? tiles : cap), (unsigned)h->cfg.n_learners);
-  gwa::actor_forward_kernel<<<grid, gwa::THREADS, gwa::smem_bytes(f.cpo), static_cast<cudaStream_t>(stream)>>>(f);
+  // two tiles in flight per CTA once every SM has at least two tiles to work on (and the second operand tile fits)
+  static const int groups_env = [] { const char* v = std::getenv("GW_ACTOR_GROUPS"); return v ? std::atoi(v) : 0; }();
+  const bool two = groups_env ? groups_env == 2
+                              : (tiles >= 2 * cap && gwa::smem_bytes<2>(f.cpo) <= (size_t)227 * 1024);
+  if (two && gwa::smem_bytes<2>(f.cpo) <= (size_t)227 * 1024) {
+    const long long pairs = (tiles + 1) / 2;
+    dim3 grid((unsigned)(pairs < cap ? pairs : cap), (unsigned)h->cfg.n_learners);
+    gwa::actor_forward_kernel<2><<<grid, gwa::THREADS, gwa::smem_bytes<2>(f.cpo), static_cast<cudaStream_t>(stream)>>>(f);
+  } else {
+    dim3 grid((unsigned)(tiles < cap ? tiles : cap), (unsigned)h->cfg.n_learners);
+    gwa::actor_forward_kernel<1><<<grid, gwa::THREADS, gwa::smem_bytes<1>(f.cpo), static_cast<cudaStream_t>(stream)>>>(f);
+  }
   GW_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return GW_OK;
