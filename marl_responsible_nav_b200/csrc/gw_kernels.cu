@@ -1,16 +1,22 @@
 // libgridworld_b200.so -- kernels + C-ABI (include/gridworld_b200.h).  sm_100a only.
 //
-// Kernel layout (v2).  A CTA owns a tile of TILE consecutive environments and runs four phases:
-//   P1  thread per env   : load the 16-byte packed state (coalesced), fetch/draw actions, advance the world with the
-//                          pair-mask table (gw_device.cuh), rewards / done flags / auto-reset, scalar outputs,
-//                          enqueue the FeAR tasks (actor x, affected j) that can be non-zero
-//   P2  thread per sim   : the CTA drains the task queue, one counterfactual per thread (18 per task), counts land in
-//                          4-bit fields of a shared-memory word per (env, actor) via atomicAdd
-//   P3  thread per env   : counts -> Resp LUT -> fear, shaped reward, episode statistics (warp-reduced atomics)
-//   P4  CTA cooperative  : observations: every thread streams 16-byte copies of the constant map row-template
-//                          (full 512 B per warp instruction, coalesced), then the <= 5 special cells per observation
-//                          are patched with 4-byte stores that hit the lines just written (they merge in L2)
-// State is 16 B/env and lives in HBM/L2 between launches; nothing else is kept by the library.
+// Three step kernels share the device code of gw_device.cuh (pair-mask table, fix-point, bit-parallel FeAR counting);
+// gw_step picks one by batch size (pick_small / pick_tile, thresholds measured on B200, profiles/README.md):
+//   gw_step_small_kernel   <= 6144 envs: 8 lanes per env, 32 envs per 256-thread CTA, no CTA-wide phase -- every warp steps
+//                          its four envs, patches their observation rows in shared memory and issues one TMA bulk store
+//   gw_step_kernel<TILE>   thread per env, persistent CTAs walking tiles of 32 / 128 / 256 envs in four phases:
+//       P1  thread per env          : 16-byte packed state (coalesced), actions / Philox, world update via the pair-mask
+//                                     table, rewards / done flags / auto-reset, scalar outputs, FeAR task queue
+//       P2  thread per (task, variant): count_valid_moves (no loop over actions), counts into 4-bit fields of a shared word
+//       P3  thread per env          : counts -> Resp LUT -> fear, shaped reward, statistics (warp-reduced atomics), masks
+//       P4  warp per env            : observation row = staging copy of the constant template + <= 10 patched cells,
+//                                     leaves as ONE TMA bulk store of whole 128-byte lines (double-buffered rows)
+//     tiles after a CTA's first come from a global counter when there are >= 4 per CTA (self-resetting)
+//   gw_step_server_kernel  the small kernel's body inside a RESIDENT kernel for the host-driven step (gw_step_host mode 2):
+//                          doorbell / completion word in pinned host memory, no launch or stream sync per step
+// Prologue of all of them: one thread brings the 15.6 KB table block and the pre-replicated staging rows in by TMA
+// (cp.async.bulk + mbarrier).  State is 16 B/env and lives in HBM/L2 between launches; nothing else is kept by the library.
+// DESIGN.md section 5 has the reasoning and the measurements behind each choice.
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
