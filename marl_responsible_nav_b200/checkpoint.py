@@ -65,7 +65,13 @@ def _portable_optimizer_state(opt: torch.optim.Optimizer) -> Dict:
     package keeps the update inside a CUDA graph; a CPU run of the reference could not step such an optimiser)."""
     sd = opt.state_dict()
     state = {k: {n: (v.detach().cpu().clone() if torch.is_tensor(v) else v) for n, v in st.items()} for k, st in sd["state"].items()}
-    groups = [dict(g, capturable=False) if "capturable" in g else dict(g) for g in sd["param_groups"]]
+    groups = []
+    for g in sd["param_groups"]:
+        g = dict(g)
+        for key, plain in (("capturable", False), ("fused", None), ("foreach", None)):
+            if key in g:
+                g[key] = plain
+        groups.append(g)
     return {"state": state, "param_groups": groups}
 
 
@@ -96,11 +102,11 @@ def load_reference_checkpoint(path: str, device="cuda", hp: Optional[Dict] = Non
     for opts, key in ((agent.actor_opt, "actor_optimizers_state_dict"), (agent.critic_opt, "critic_optimizers_state_dict")):
         for opt, sd in zip(opts, ck.get(key, [])):
             try:
-                cap = [g.get("capturable", False) for g in opt.param_groups]
+                mine = [{k: g[k] for k in ("capturable", "fused", "foreach") if k in g} for g in opt.param_groups]
+                cap = [m.get("capturable", False) for m in mine]
                 opt.load_state_dict(sd)
-                for g, c in zip(opt.param_groups, cap):              # keep this side's choice (CUDA graphs), not the file's
-                    if "capturable" in g:
-                        g["capturable"] = c
+                for g, m in zip(opt.param_groups, mine):             # keep this side's choices (CUDA graphs, fused step), not the file's
+                    g.update(m)
                 if any(cap):
                     for st in opt.state.values():
                         if torch.is_tensor(st.get("step")):

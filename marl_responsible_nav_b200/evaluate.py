@@ -37,6 +37,8 @@ def evaluate(agent: maddpg.BatchedMADDPG, num_envs: int = 4096, episodes: int = 
     dev = env.device
     played = torch.zeros(num_envs, dtype=torch.int32, device=dev)
     acc = torch.zeros(5, dtype=torch.float64, device=dev)            # destinations, crashes, steps, return, fear
+    vals = torch.zeros((5, num_envs), dtype=torch.float64, device=dev)
+    vals[2] = 1.0
     out = env.reset()
     torch.cuda.synchronize(dev)
     t0, steps = time.perf_counter(), 0
@@ -54,12 +56,12 @@ def evaluate(agent: maddpg.BatchedMADDPG, num_envs: int = 4096, episodes: int = 
             out = env.step(ids)
             live = played < k
             info = out.info
-            acc[0] += (((info >> 10) & 3) * live).sum()
-            acc[1] += (((info >> 8) & 3) * live).sum()
-            acc[2] += live.sum()
-            acc[3] += (out.reward.sum(dim=1) * live).sum()
+            vals[0] = (info >> 10) & 3                      # apples rewarded in this step
+            vals[1] = (info >> 8) & 3                       # learner crashes
+            vals[3] = out.reward.sum(dim=1)
             if fear:
-                acc[4] += (out.fear.sum(dim=1) * live).sum()
+                vals[4] = out.fear.sum(dim=1)
+            acc += (vals * live).sum(dim=1)                 # vals[2] stays 1: steps
             played += (out.ended != 0) & live
         steps += check_every
         if bool((played >= k).all()):                       # synchronises; every `check_every` steps only
