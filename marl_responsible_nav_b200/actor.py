@@ -78,12 +78,18 @@ class FusedActor:
         del keep
 
     def forward(self, obs_code: torch.Tensor, action_mask: torch.Tensor = None, training: bool = True,
-                expl_noise: float = 0.1, mean_noise: float = 0.0, gumbel: bool = None):
+                expl_noise: float = 0.1, mean_noise: float = 0.0, gumbel: bool = None, cont_out: torch.Tensor = None):
         """-> (cont_actions f32 [E, L, 9], action_ids int8 [E, L]); both are views of buffers reused by the next call.
         training=True: Gumbel noise of the output activation + Gaussian exploration noise.  training=False: no noise at
         all, unless gumbel=True, which is the reference's evaluation mode (its GumbelSoftmax activation samples on every
         forward, `training=False` only drops the exploration noise)."""
         mode = 1 if training else (2 if gumbel else 0)
+        cont = self.cont
+        if cont_out is not None:                           # e.g. the replay ring's action slot: no copy afterwards
+            if cont_out.dtype != torch.float32 or tuple(cont_out.shape) != (self.E, self.L, 9) or not cont_out.is_contiguous() \
+                    or cont_out.device != self.cont.device:
+                raise ValueError("cont_out must be a contiguous float32 [E, L, 9] tensor on the env's device")
+            cont = cont_out
         if obs_code.dtype != torch.int64 or obs_code.numel() != self.E or not obs_code.is_cuda:
             raise ValueError("obs_code must be the int64 [E] tensor written by BatchedGridWorld.step / reset")
         mptr = None
@@ -91,11 +97,11 @@ class FusedActor:
             if action_mask.dtype != torch.int8 or tuple(action_mask.shape) != (self.E, self.L, 9) or not action_mask.is_contiguous():
                 raise ValueError("action_mask must be a contiguous int8 [E, L, 9] tensor")
             mptr = action_mask.data_ptr()
-        N.check(self.lib.gw_actor_forward(self._h, self.E, obs_code.data_ptr(), mptr, self.cont.data_ptr(),
+        N.check(self.lib.gw_actor_forward(self._h, self.E, obs_code.data_ptr(), mptr, cont.data_ptr(),
                                           self.ids.data_ptr(), mode, float(expl_noise), float(mean_noise),
                                           self.seed, self.step, self.env._stream()), self.env._h, "gw_actor_forward")
         self.step += 1
-        return self.cont, self.ids
+        return cont, self.ids
 
     def close(self):
         if getattr(self, "_h", None):

@@ -162,12 +162,21 @@ class BatchedGridWorld:
         """Scalar outputs go to the env's own buffers or to caller tensors of the same shapes (e.g. a replay-ring slot)."""
         if b is getattr(self, "_last_out_owner", None):
             return
-        E, L, dev = self.num_envs, self.n_learners, self.device
-        for name, dtype, per_learner in self._OUT_SPECS:
-            t = getattr(b, name)
-            if b is not self.buf:
-                _check(t, name, dtype, (E, L) if per_learner else (E,), dev)
-            setattr(io, name, t.data_ptr())
+        ptrs = getattr(b, "_gw_ptrs", None)                        # checked once per buffer object (a replay-ring slot comes back)
+        if ptrs is None or ptrs[0] is not self:
+            E, L, dev = self.num_envs, self.n_learners, self.device
+            vals = []
+            for name, dtype, per_learner in self._OUT_SPECS:
+                t = getattr(b, name)
+                if b is not self.buf:
+                    _check(t, name, dtype, (E, L) if per_learner else (E,), dev)
+                vals.append(t.data_ptr())
+            ptrs = (self, tuple(vals))
+            try:
+                b._gw_ptrs = ptrs
+            except AttributeError:
+                pass
+        (io.reward, io.shaped_reward, io.fear, io.terminated, io.truncated, io.ended, io.info) = ptrs[1]
         self._last_out_owner = b if b is self.buf else None
 
     def _obs_arg(self, t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:

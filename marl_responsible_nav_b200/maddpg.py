@@ -245,14 +245,15 @@ class BatchedTrainer:
         for _ in range(env_steps):
             t = self.t
             obs = ring.obs_slot(t)
-            if self.fused is not None:
+            if self.fused is not None:                     # the kernel writes the continuous actions into the ring itself
                 cont, ids = self.fused.forward(self.out.obs_code, self.out.action_mask, training=True,
-                                               expl_noise=hp["EXPL_NOISE"], mean_noise=hp["MEAN_NOISE"])
+                                               expl_noise=hp["EXPL_NOISE"], mean_noise=hp["MEAN_NOISE"],
+                                               cont_out=ring.action_slot(t))
             else:
                 cont, ids = agent.get_action(obs, self.out.action_mask, training=True)
+                ring.store_action(t, cont)
             self.out = env.step(ids, obs_out=ring.obs_slot(t + 1), final_obs_out=ring.final_slot(t),
                                 buffers=ring.buffers_slot(t))
-            ring.store_action(t, cont)
             ring.advance()
             self.t += 1
             # the reference learns every LEARN_STEP steps of its single env once BATCH_SIZE transitions exist

@@ -38,22 +38,28 @@ class ReplayRing:
         self.ended = torch.zeros((T, E), dtype=torch.uint8, device=dev)
         self.info = torch.zeros((T, E), dtype=torch.int32, device=dev)
         self.t = 0                                              # number of transitions recorded per env so far
+        # per-slot views, built once: slicing nine tensors per env step costs more host time than the step kernel takes
+        self._obs_v, self._final_v, self._action_v = list(self.obs.unbind(0)), list(self.final_obs.unbind(0)), list(self.action.unbind(0))
+        self._slot_v = [SimpleNamespace(reward=self.reward[s], shaped_reward=self.shaped_reward[s], fear=self.fear[s],
+                                        terminated=self.terminated[s], truncated=self.truncated[s], ended=self.ended[s],
+                                        info=self.info[s]) for s in range(T)]
 
     # ---- views handed to BatchedGridWorld.reset / step
     def obs_slot(self, t: int) -> torch.Tensor:
-        return self.obs[t % self.T]
+        return self._obs_v[t % self.T]
 
     def final_slot(self, t: int) -> torch.Tensor:
-        return self.final_obs[t % self.T]
+        return self._final_v[t % self.T]
 
     def buffers_slot(self, t: int) -> SimpleNamespace:
-        s = t % self.T
-        return SimpleNamespace(reward=self.reward[s], shaped_reward=self.shaped_reward[s], fear=self.fear[s],
-                               terminated=self.terminated[s], truncated=self.truncated[s], ended=self.ended[s],
-                               info=self.info[s])
+        return self._slot_v[t % self.T]
+
+    def action_slot(self, t: int) -> torch.Tensor:
+        """[E, L, action_dim] f32: where the actor writes its continuous actions of time t (FusedActor.forward(cont_out=...))."""
+        return self._action_v[t % self.T]
 
     def store_action(self, t: int, cont_actions: torch.Tensor):
-        self.action[t % self.T].copy_(cont_actions.reshape(self.E, self.L, self.action_dim))
+        self._action_v[t % self.T].copy_(cont_actions.reshape(self.E, self.L, self.action_dim))
 
     def advance(self):
         """Call once per env.step after the transition of time self.t has been written."""
