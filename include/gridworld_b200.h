@@ -167,6 +167,12 @@ int gw_sync(gw_handle* h, void* stream);       /* cudaStreamSynchronize + surfac
 #define GW_HOST_RESIDENT 2
 int gw_step_host(gw_handle* h, const gw_io* io, const int8_t* host_actions, float* host_reward, float* host_shaped,
                  uint8_t* host_ended, int zero_copy, void* stream);
+/* The same call with its arguments stored in the handle: bindings whose per-argument marshalling costs as much as a PCIe
+ * round trip (ctypes: ~1 us for the eight arguments) prepare each distinct set of buffers once and run it by token. */
+int gw_host_call_prepare(gw_handle* h, const gw_io* io, const int8_t* host_actions, float* host_reward, float* host_shaped,
+                         uint8_t* host_ended, int zero_copy, int* token);
+int gw_host_call_run(gw_handle* h, int token, void* stream);
+int gw_host_call_reset(gw_handle* h);             /* forget every prepared call */
 int gw_server_stop(gw_handle* h);                 /* no-op when the resident kernel is not running */
 /* running: 1 resident now, 0 not, -1 given up for this handle (kernel launches block in this process -- profiler,
  * CUDA_LAUNCH_BLOCKING -- so mode 2 runs as mode 1); any pointer may be NULL */

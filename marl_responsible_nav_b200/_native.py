@@ -11,7 +11,7 @@ GW_ENV_MULTI, GW_ENV_SINGLE = 0, 1
 GW_OBS_F32, GW_OBS_BF16 = 0, 1
 
 EXPORTS = ["gw_abi_version", "gw_build_info", "gw_default_config", "gw_create", "gw_destroy", "gw_last_error",
-           "gw_reset", "gw_step", "gw_step_host", "gw_server_stop", "gw_server_info", "gw_sync", "gw_state_bytes", "gw_get_state", "gw_set_state", "gw_get_stats",
+           "gw_reset", "gw_step", "gw_step_host", "gw_host_call_prepare", "gw_host_call_run", "gw_host_call_reset", "gw_server_stop", "gw_server_info", "gw_sync", "gw_state_bytes", "gw_get_state", "gw_set_state", "gw_get_stats",
            "gw_reset_stats", "gw_launch_count", "gw_update_world", "gw_fear_one_actor", "gw_fear_matrix", "gw_feal", "gw_actor_create", "gw_actor_update", "gw_actor_update_device",
            "gw_actor_destroy", "gw_actor_forward"]
 
@@ -75,6 +75,9 @@ def load():
     lib.gw_step.argtypes = [vp, C.POINTER(GwIO), vp]
     lib.gw_sync.argtypes = [vp, vp]
     lib.gw_step_host.argtypes = [vp, C.POINTER(GwIO), vp, vp, vp, vp, C.c_int, vp]
+    lib.gw_host_call_prepare.argtypes = [vp, C.POINTER(GwIO), vp, vp, vp, vp, C.c_int, C.POINTER(C.c_int)]
+    lib.gw_host_call_run.argtypes = [vp, C.c_int, vp]
+    lib.gw_host_call_reset.argtypes = [vp]
     lib.gw_server_stop.argtypes = [vp]
     lib.gw_server_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
     lib.gw_state_bytes.argtypes = [vp]

@@ -109,6 +109,7 @@ class BatchedGridWorld:
             final_obs=None,
             obs_code=torch.zeros((E,), dtype=torch.int64, device=dev))
         self._io_step, self._io_reset = self._make_io(True), self._make_io(False)
+        self._host_calls = {}                                      # step_host: (buffer pointers, mode) -> (library token, StepOutput)
 
     # ------------------------------------------------------------------ helpers
     def close(self):
@@ -253,15 +254,15 @@ class BatchedGridWorld:
             zero_copy = 2
         key = (host_actions.data_ptr(), host_reward.data_ptr(), 0 if host_ended is None else host_ended.data_ptr(),
                0 if host_shaped is None else host_shaped.data_ptr(), obs.data_ptr(), zero_copy)
-        cache = self.__dict__.setdefault("_host_calls", {})
+        cache = self._host_calls
         ent = cache.get(key)
         if ent is None:
-            ent = self._prepare_host_call(host_actions, host_reward, host_ended, host_shaped, obs_out, zero_copy)
-            if len(cache) >= 4096:
+            if len(cache) >= 4096:                                 # tokens live in the library: forget both sides together
                 cache.clear()
-            cache[key] = ent
-        ioref, pa, pr, ps, pe, zc, out, _ = ent
-        rc = self.lib.gw_step_host(self._h, ioref, pa, pr, ps, pe, zc, self._stream())
+                N.check(self.lib.gw_host_call_reset(self._h), self._h, "gw_host_call_reset")
+            ent = cache[key] = self._prepare_host_call(host_actions, host_reward, host_ended, host_shaped, obs_out, zero_copy)
+        token, out = ent
+        rc = self.lib.gw_host_call_run(self._h, token, self._stream())
         if rc:
             N.check(rc, self._h, "gw_step_host")
         return out
@@ -285,7 +286,10 @@ class BatchedGridWorld:
         out = StepOutput(obs=self._view(obs), action_mask=b.action_mask, positions=b.positions, reward=pick(host_reward, b.reward),
                          shaped_reward=pick(host_shaped, b.shaped_reward), fear=b.fear, terminated=b.terminated,
                          truncated=b.truncated, ended=pick(host_ended, b.ended), info=b.info, obs_code=b.obs_code)
-        return (C.byref(io), p(host_actions), p(host_reward), p(host_shaped), p(host_ended), int(zero_copy), out, io)   # io kept alive
+        token = C.c_int()
+        N.check(self.lib.gw_host_call_prepare(self._h, C.byref(io), p(host_actions), p(host_reward), p(host_shaped), p(host_ended),
+                                              int(zero_copy), C.byref(token)), self._h, "gw_host_call_prepare")
+        return (int(token.value), out)
 
     def sync(self):
         """Stream synchronisation (a resident step kernel is told to leave first)."""

@@ -26,9 +26,16 @@ struct gw_server {
   uint64_t launches = 0, relaunches = 0;
 };
 
+struct gw_host_call {                        // arguments of one gw_step_host call, prepared once (gw_host_call_prepare)
+  gw_io io;
+  const int8_t* actions; float* reward; float* shaped; uint8_t* ended;
+  int mode;
+};
+
 struct gw_handle {
   gw_config cfg;
   gw_server srv;
+  std::vector<gw_host_call> host_calls;
   gw::Tables* d_tables = nullptr;
   uint4* d_rng_cache = nullptr;              // small-batch kernel: next step's random words per env (tagged)
   unsigned int* d_tile_ctr = nullptr;        // dynamic tile scheduling of the thread-per-env step kernel

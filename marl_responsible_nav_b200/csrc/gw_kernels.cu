@@ -2426,6 +2426,28 @@ int gw_step_host(gw_handle* h, const gw_io* io, const int8_t* host_actions, floa
   return GW_OK;
 }
 
+int gw_host_call_prepare(gw_handle* h, const gw_io* io, const int8_t* host_actions, float* host_reward, float* host_shaped,
+                         uint8_t* host_ended, int zero_copy, int* token) {
+  if (!h || !io || !host_actions || !token) return fail(h, GW_EINVAL, "gw_host_call_prepare: null argument");
+  if (h->host_calls.size() >= (size_t)1 << 20) return fail(h, GW_ENOMEM, "gw_host_call_prepare: too many prepared calls");
+  h->host_calls.push_back(gw_host_call{*io, host_actions, host_reward, host_shaped, host_ended, zero_copy});
+  *token = (int)h->host_calls.size() - 1;
+  return GW_OK;
+}
+
+int gw_host_call_reset(gw_handle* h) {            // forget every prepared call (tokens become invalid)
+  if (!h) return GW_EINVAL;
+  h->host_calls.clear();
+  return GW_OK;
+}
+
+int gw_host_call_run(gw_handle* h, int token, void* stream) {
+  if (!h) return GW_EINVAL;
+  if (token < 0 || (size_t)token >= h->host_calls.size()) return fail(h, GW_EINVAL, "gw_host_call_run: unknown token");
+  const gw_host_call& c = h->host_calls[(size_t)token];
+  return gw_step_host(h, &c.io, c.actions, c.reward, c.shaped, c.ended, c.mode, stream);
+}
+
 int gw_sync(gw_handle* h, void* stream) {
   if (!h) return GW_EINVAL;
   if (int rc = server_stop(h)) return rc;
