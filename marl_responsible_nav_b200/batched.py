@@ -291,6 +291,12 @@ class BatchedGridWorld:
                                               int(zero_copy), C.byref(token)), self._h, "gw_host_call_prepare")
         return (int(token.value), out)
 
+    def pinned_io(self) -> "PinnedIO":
+        """Host-visible input / output block for host-driven use of a small batch (the E = 1 drop-in classes)."""
+        if getattr(self, "_pinned_io", None) is None:
+            self._pinned_io = PinnedIO(self)
+        return self._pinned_io
+
     def sync(self):
         """Stream synchronisation (a resident step kernel is told to leave first)."""
         N.check(self.lib.gw_sync(self._h, self._stream()), self._h, "gw_sync")
@@ -382,3 +388,77 @@ class BatchedGridWorld:
     def feal(self, positions, actions, mdr, in_list=None, n_agents=None):
         """Responsibility.FeAL for C cases -> (feal f64 [C,4], n_mdr, n_act int8 [C,4])."""
         return self._matrix_op(self.lib.gw_feal, "gw_feal", (4,), positions, actions, mdr, in_list, n_agents)
+
+
+class PinnedIO:
+    """Every input and output of reset / step in pinned HOST memory, read and written by the kernels themselves over PCIe
+    (unified addressing), exposed as numpy arrays: one library call per step, no device-to-host copy, no tensor op.  The
+    step goes through `gw_step_host` with the resident kernel (include/gridworld_b200.h, GW_HOST_RESIDENT), so after the
+    first step there is no kernel launch and no stream synchronisation either.  Meant for the single-env front-ends
+    (`CustomMAEnv`, `CustomEnv`: ~45 us per step instead of ~300 us with tensor copies); at a few KB per env it is the
+    wrong tool for large batches, whose observations belong in HBM.
+
+    Fill `actions` (and, in replay mode, `npc_actions` / `spawn`), call `step()` / `reset()`, read the other arrays."""
+
+    def __init__(self, env: BatchedGridWorld):
+        if env.obs_dtype != torch.float32:
+            raise ValueError("PinnedIO exposes float32 observations")
+        if env.num_envs > 8192:
+            raise ValueError("PinnedIO is meant for small batches (<= 8192 envs)")
+        self.env = env
+        E, L, A = env.num_envs, env.n_learners, env.n_agents
+        spec = (("actions", np.int8, (E, L)), ("npc_actions", np.int8, (E, A)), ("spawn", np.int8, (E, A, 2)),
+                ("obs", np.float32, (E, L, env.obs_len)), ("final_obs", np.float32, (E, L, env.obs_len)),
+                ("reward", np.float32, (E, L)), ("shaped_reward", np.float32, (E, L)), ("fear", np.float64, (E, L)),
+                ("terminated", np.uint8, (E, L)), ("truncated", np.uint8, (E, L)), ("ended", np.uint8, (E,)),
+                ("action_mask", np.int8, (E, L, N.GW_N_ACTIONS)), ("positions", np.int8, (E, A, 2)), ("info", np.uint32, (E,)),
+                ("obs_code", np.uint64, (E,)))
+        off, offs = 0, {}
+        for name, dt, shape in spec:
+            offs[name] = off
+            off += -(-int(np.prod(shape)) * np.dtype(dt).itemsize // 64) * 64          # 64-byte slots: every alignment rule holds
+        self._block = torch.zeros(off, dtype=torch.uint8).pin_memory()                   # one pinned allocation
+        raw = self._block.numpy()
+        base = self._block.data_ptr()
+        ptr = {}
+        for name, dt, shape in spec:
+            n = int(np.prod(shape)) * np.dtype(dt).itemsize
+            setattr(self, name, raw[offs[name]:offs[name] + n].view(dt).reshape(shape))
+            ptr[name] = base + offs[name]
+        self._ptr = ptr
+        self.replay = False                     # True: `npc_actions` / `spawn` are inputs (recorded draws); False: device RNG
+        self._io = {}
+
+    def _make_io(self, step: bool, replay: bool) -> N.GwIO:
+        io, p = N.GwIO(), self._ptr
+        for name in ("obs", "action_mask", "positions", "obs_code"):
+            setattr(io, name, p[name])
+        if step:
+            for name in ("final_obs", "reward", "shaped_reward", "fear", "terminated", "truncated", "ended", "info"):
+                setattr(io, name, p[name])
+            io.learner_actions = p["actions"]
+            if replay:
+                io.npc_actions = p["npc_actions"]
+        if replay:
+            io.spawn = p["spawn"]
+        return io
+
+    def _get_io(self, step: bool):
+        key = (step, bool(self.replay))
+        io = self._io.get(key)
+        if io is None:
+            io = self._io[key] = self._make_io(*key)
+        return io
+
+    def reset(self):
+        """gw_reset for all envs (spawn cells from `spawn` in replay mode); the arrays are valid on return."""
+        env = self.env
+        N.check(env.lib.gw_reset(env._h, None, C.byref(self._get_io(False)), env._stream()), env._h, "gw_reset")
+        env.sync()
+
+    def step(self):
+        """One step with `actions` (and `npc_actions` / `spawn` in replay mode); the arrays are valid on return."""
+        env = self.env
+        rc = env.lib.gw_step_host(env._h, C.byref(self._get_io(True)), self._ptr["actions"], None, None, None, 2, env._stream())
+        if rc:
+            N.check(rc, env._h, "gw_step_host")

@@ -364,7 +364,8 @@ __device__ __forceinline__ uint32_t spawn_cells(const StepParams& p, const Small
   if (p.io.spawn != nullptr) {
     uint32_t cells = 0;
     for (int i = 0; i < p.n; ++i) {
-      const int r = p.io.spawn[(e * p.n + i) * 2 + 0], c = p.io.spawn[(e * p.n + i) * 2 + 1];
+      // L2-level loads: under the resident kernel the array may sit in host memory and change between two steps
+      const int r = __ldcg(p.io.spawn + (e * p.n + i) * 2 + 0), c = __ldcg(p.io.spawn + (e * p.n + i) * 2 + 1);
       cells |= (uint32_t)(((r & 15) << 4) | (c & 15)) << (8 * i);
     }
     return cells;

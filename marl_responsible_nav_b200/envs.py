@@ -83,6 +83,8 @@ class CustomMAEnv:
         self._mirror = _HostMirror(self.scenario)
         self._gw = BatchedGridWorld(self.scenario, num_envs=1, device=device, env_kind="multi", fear=fear,
                                     n_learners=N_INTELLIGENT_AGENTS, max_steps=0, auto_reset=False)
+        self._io = self._gw.pinned_io()                       # inputs / outputs in pinned host memory, written by the kernels
+        self._io.replay = True                                 # spawn cells and NPC draws come from the host RNG mirror
         self._locs = None
         self.num_moves = 0
 
@@ -103,26 +105,27 @@ class CustomMAEnv:
     def close(self):
         pass
 
-    def _obs_dict(self, obs: torch.Tensor) -> Dict[str, np.ndarray]:
-        o = obs[0].to(torch.float64).cpu().numpy().reshape(len(self.possible_agents), *self.scenario.shape)
+    def _obs_dict(self) -> Dict[str, np.ndarray]:
+        o = self._io.obs[0].astype(np.float64).reshape(len(self.possible_agents), *self.scenario.shape)
         return {a: o[k] for k, a in enumerate(self.possible_agents)}
 
-    def _mask_dict(self, mask: torch.Tensor):
-        m = mask[0].cpu().numpy()
-        return {a: {"action_mask": m[k].copy()} for k, a in enumerate(self.possible_agents)}
+    def _mask_dict(self):
+        m = self._io.action_mask[0].copy()
+        return {a: {"action_mask": m[k]} for k, a in enumerate(self.possible_agents)}
 
     def reset(self, seed=None, options=None):
         # `seed` / `options` are ignored, exactly like the reference (:169,:183)
         spawn = self._mirror.spawn(self.rng, self._gw.n_agents)
-        out = self._gw.reset(spawn=np.asarray(spawn, dtype=np.int8)[None])
+        self._io.spawn[0] = spawn
+        self._io.reset()
         self._locs = spawn
         self.agents = self.possible_agents[:]
         self.num_moves = 0
         self.terminations = {a: False for a in self.agents}
         self.truncation = {a: False for a in self.agents}
-        self.observations = self._obs_dict(out.obs)
+        self.observations = self._obs_dict()
         info = {"fear": 0.0}
-        info.update(self._mask_dict(out.action_mask))
+        info.update(self._mask_dict())
         return self.observations, info
 
     def step(self, actions):
@@ -132,27 +135,26 @@ class CustomMAEnv:
             raise RuntimeError("step() called before reset()")
         npc = self._mirror.npc_actions(self._locs)             # setup_step (:233), all agents draw
         self.num_moves += 1
-        la = np.asarray([int(np.asarray(a).item()) for a in actions], dtype=np.int8)[None]
-        out = self._gw.step(la, npc_actions=np.asarray(npc, dtype=np.int8)[None])
-        pos = out.positions[0].cpu().numpy()
-        self._locs = [(int(r), int(c)) for r, c in pos]
-        rew = out.reward[0].cpu().numpy()
-        term = out.terminated[0].cpu().numpy()
-        trunc = out.truncated[0].cpu().numpy()
-        fear = out.fear[0].cpu().numpy()
-        info_bits = int(out.info[0].item())
-        self.observations = self._obs_dict(out.obs)
+        io = self._io
+        for k in range(len(self.possible_agents)):
+            io.actions[0, k] = int(np.asarray(actions[k]).item())
+        io.npc_actions[0] = npc
+        io.step()                                              # one library call; the arrays below are host memory
+        self._locs = [(int(r), int(c)) for r, c in io.positions[0]]
+        rew, term, trunc, fear = io.reward[0], io.terminated[0], io.truncated[0], io.fear[0]
+        info_bits = int(io.info[0])
+        self.observations = self._obs_dict()
         self.rewards = {a: int(rew[k]) for k, a in enumerate(self.agents)}
         self.terminations = {a: bool(term[k]) for k, a in enumerate(self.agents)}
         self.truncation = {a: bool(trunc[k]) for k, a in enumerate(self.agents)}
         info = {"fear": {a: np.float64(fear[k]) if self.fear else 0.0 for k, a in enumerate(self.agents)},
                 "agent_crashes": (info_bits >> 8) & 3, "apples_caught": (info_bits >> 10) & 3}
-        info.update(self._mask_dict(out.action_mask))
+        info.update(self._mask_dict())
         return self.observations, self.rewards, self.terminations, self.truncation, info
 
     def get_action_mask(self, agent):                          # :467-506 (mask of the current position)
         k = int(agent[-1])
-        return {"action_mask": self._gw.buf.action_mask[0, k].cpu().numpy().copy()}
+        return {"action_mask": self._io.action_mask[0, k].copy()}
 
 
 class CustomEnv:
@@ -174,17 +176,20 @@ class CustomEnv:
         self._mirror = _HostMirror(self.scenario)
         self._gw = BatchedGridWorld(self.scenario, num_envs=1, device=device, env_kind="single", fear=fear,
                                     n_learners=1, max_steps=0, auto_reset=False)
+        self._io = self._gw.pinned_io()
+        self._io.replay = True
         self._locs = None
         self._apple_left = False
 
     def reset(self, seed=None, options=None):
         spawn = self._mirror.spawn(type(self).rng, self._gw.n_agents)      # :235-236
-        out = self._gw.reset(spawn=np.asarray(spawn, dtype=np.int8)[None])
+        self._io.spawn[0] = spawn
+        self._io.reset()
         self._locs = spawn
         self._apple_left = True
         self.episode_reward = 0
         self.episode_length = 0
-        self.observation = out.obs[0, 0].to(torch.float64).cpu().numpy().reshape(self.scenario.shape)
+        self.observation = self._io.obs[0, 0].astype(np.float64).reshape(self.scenario.shape)
         return self.observation, {}
 
     def step(self, action):
@@ -193,13 +198,14 @@ class CustomEnv:
         npc = self._mirror.npc_actions(self._locs)                         # :83-103
         if not self._apple_left:
             raise StopIteration                                            # next(iter({})) in the reference (:132)
-        la = np.asarray([[int(np.asarray(action[0]).item())]], dtype=np.int8)
-        out = self._gw.step(la, npc_actions=np.asarray(npc, dtype=np.int8)[None])
-        pos = out.positions[0].cpu().numpy()
-        self._locs = [(int(r), int(c)) for r, c in pos]
-        bits = int(out.info[0].item())
-        terminated = bool(out.terminated[0, 0].item())
-        truncated = bool(out.truncated[0, 0].item())
+        io = self._io
+        io.actions[0, 0] = int(np.asarray(action[0]).item())
+        io.npc_actions[0] = npc
+        io.step()
+        self._locs = [(int(r), int(c)) for r, c in io.positions[0]]
+        bits = int(io.info[0])
+        terminated = bool(io.terminated[0, 0])
+        truncated = bool(io.truncated[0, 0])
         # the reference's reward is a Python int unless the +0.1 shaping fired (:126-158); rebuild it from the
         # kernel's flags so that the value is bit-identical in fp64 (the fp32 tensor is the batched output)
         reward = 0
@@ -212,10 +218,10 @@ class CustomEnv:
             reward += 0.1
         self.episode_reward += reward
         self.episode_length += 1
-        self.observation = out.obs[0, 0].to(torch.float64).cpu().numpy().reshape(self.scenario.shape)
+        self.observation = io.obs[0, 0].astype(np.float64).reshape(self.scenario.shape)
         info = {"episode": {"r": self.episode_reward, "l": self.episode_length},
                 "restricted": bool((bits >> 4) & 1),
-                "fear": np.float64(out.fear[0, 0].item())}
+                "fear": np.float64(io.fear[0, 0])}
         return self.observation, [reward], [terminated], truncated, info
 
     def render(self, mode="human"):
