@@ -109,7 +109,9 @@ class BatchedMADDPG:
         self.actor_opt = [torch.optim.Adam(a.parameters(), lr=self.hp["LR_ACTOR"], **kw) for a in self.actors]
         self.critic_opt = [torch.optim.Adam(c.parameters(), lr=self.hp["LR_CRITIC"], **kw) for c in self.critics]
         self._graph = None                                 # (CUDAGraph, static batch, static LearnStats) once captured
+        self._segments = None                              # several ranks: the update as a chain of graphs (see _learn_segmented)
         self._eager_learns = 0
+        self.force_segmented = False                       # tests: take the multi-rank path in a one-rank process group
 
     def parameters(self):
         for net in self.actors + self.critics:
@@ -139,10 +141,12 @@ class BatchedMADDPG:
     def learn(self, batch: Dict[str, torch.Tensor], graph: bool = True) -> LearnStats:
         """One MADDPG update.  On a single GPU the whole update (4 forward/backward passes, 4 Adam steps, soft update:
         ~250 small kernels, 6 ms of launches in eager mode) is captured into one CUDA graph after three eager calls
-        and replayed from then on; with several ranks the gradient all-reduce keeps it eager."""
+        and replayed from then on; with several ranks it is a chain of graphs cut at the gradient all-reduces."""
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        if not graph or self.device.type != "cuda" or multi:     # (capturing the NCCL all-reduces hung here: 2 ranks, torch 2.11)
+        if not graph or self.device.type != "cuda":
             return self._learn(batch)
+        if multi or self.force_segmented:
+            return self._learn_segmented(batch)
         keys = ("state", "action", "reward", "next_state", "done")
         if self._graph is not None:
             g, static, out, shapes = self._graph
@@ -163,6 +167,104 @@ class BatchedMADDPG:
         self._graph = (g, static, out, {k: tuple(batch[k].shape) for k in keys})
         g.replay()                                         # capture only records: this is the update for `batch`
         return LearnStats(out.actor_loss.clone(), out.critic_loss.clone())
+
+    # ---- several ranks: the same update cut into CUDA graphs at the gradient all-reduces
+    def _learn_segmented(self, batch: Dict[str, torch.Tensor]) -> LearnStats:
+        """Data-parallel update.  Capturing the NCCL all-reduces inside one graph hung (2 ranks, torch 2.11), so the update
+        is cut where gradients are exchanged: per agent  [critic forward/backward] AR [critic step, actor
+        forward/backward] AR [actor step]  -- 2n+1 graphs (neighbouring pieces share one) and 2n eager all-reduces, each
+        on ONE flat gradient buffer per network (the parameters' .grad are views into it: no cat / split kernels)."""
+        keys = ("state", "action", "reward", "next_state", "done")
+        seg = self._segments
+        if seg is not None and not all(tuple(batch[k].shape) == seg["shapes"][k] for k in keys):
+            seg = self._segments = None
+            self._eager_learns = 0
+        if seg is None:
+            if self._eager_learns < 3:                     # warm-up with real (eager) updates
+                self._eager_learns += 1
+                return self._learn(batch)
+            seg = self._segments = self._capture_segments({k: batch[k].float().clone() for k in keys},
+                                                           {k: tuple(batch[k].shape) for k in keys})
+        else:
+            for k in keys:
+                seg["static"][k].copy_(batch[k])
+        world = dist.get_world_size()
+        for g, flat in zip(seg["graphs"], seg["reduce_after"]):
+            g.replay()
+            if flat is not None:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                flat.div_(world)
+        return LearnStats(seg["a_loss"].clone(), seg["c_loss"].clone())
+
+    def _flat_grads(self, net: nn.Module) -> torch.Tensor:
+        """One flat gradient buffer for `net`; every parameter's .grad becomes a view into it (kept from then on)."""
+        ps = list(net.parameters())
+        flat = torch.zeros(sum(p.numel() for p in ps), dtype=ps[0].dtype, device=ps[0].device)
+        off = 0
+        for p in ps:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        return flat
+
+    def _capture_segments(self, static: Dict[str, torch.Tensor], shapes) -> Dict:
+        gamma, tau, n = self.hp["GAMMA"], self.hp["TAU"], self.n
+        s, a, r, s2, done = (static[k] for k in ("state", "action", "reward", "next_state", "done"))
+        B = s.shape[0]
+        fa = [self._flat_grads(net) for net in self.actors]
+        fc = [self._flat_grads(net) for net in self.critics]
+        a_loss = torch.zeros(n, device=self.device)
+        c_loss = torch.zeros(n, device=self.device)
+        ctx = {}
+
+        def critic_pass(k):                                # [critic forward / backward]
+            if k == 0:
+                ctx["flat_s"], flat_s2 = s.reshape(B, -1), s2.reshape(B, -1)
+                with torch.no_grad():
+                    a2 = torch.stack([self.actor_targets[j](s2[:, j]) for j in range(n)], dim=1)
+                    ctx["crit_in2"] = torch.cat([flat_s2, a2.reshape(B, -1)], dim=1)
+            with torch.no_grad():
+                q2 = self.critic_targets[k](ctx["crit_in2"]).squeeze(-1)
+                target = r[:, k] + gamma * (1.0 - done[:, k]) * q2
+            q = self.critics[k](torch.cat([ctx["flat_s"], a.reshape(B, -1)], dim=1)).squeeze(-1)
+            loss = F.mse_loss(q, target)
+            fc[k].zero_()
+            loss.backward()
+            c_loss[k] = loss.detach()
+
+        def actor_pass(k):                                 # [critic step, actor forward / backward]
+            self.critic_opt[k].step()
+            a_new = a.clone()
+            a_new[:, k] = self.actors[k](s[:, k])
+            loss = -self.critics[k](torch.cat([ctx["flat_s"], a_new.reshape(B, -1)], dim=1)).mean()
+            fa[k].zero_()
+            loss.backward()                                # also reaches the critic's gradients: zeroed before their next use
+            a_loss[k] = loss.detach()
+
+        def finish():
+            with torch.no_grad():
+                src = [p for net in self.actors + self.critics for p in net.parameters()]
+                dst = [p for net in self.actor_targets + self.critic_targets for p in net.parameters()]
+                torch._foreach_lerp_(dst, src, tau)
+
+        pieces = []                                        # (functions run in this graph, buffer to all-reduce after it)
+        for k in range(n):
+            head = [lambda k=k: self.actor_opt[k - 1].step()] if k > 0 else []
+            pieces.append((head + [lambda k=k: critic_pass(k)], fc[k]))
+            pieces.append(([lambda k=k: actor_pass(k)], fa[k]))
+        pieces.append(([lambda: self.actor_opt[n - 1].step(), finish], None))
+        torch.cuda.synchronize(self.device)
+        graphs, pool = [], None
+        for fns, _ in pieces:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                for fn in fns:
+                    fn()
+            pool = g.pool() if pool is None else pool
+            graphs.append(g)
+        seg = {"graphs": graphs, "reduce_after": [f for _, f in pieces], "static": static, "shapes": shapes,
+               "a_loss": a_loss, "c_loss": c_loss, "ctx": ctx, "flat": (fa, fc)}
+        # capture only records: replay now, with the exchanges, so that this call is the update for `batch`
+        return seg
 
     def _learn(self, batch: Dict[str, torch.Tensor]) -> LearnStats:
         gamma, tau = self.hp["GAMMA"], self.hp["TAU"]

@@ -90,3 +90,31 @@ def test_batched_training_loop_runs_on_gpu():
     e = int(b["env"][0])
     want = (-5.0 * tr.ring.fear[s, e] + tr.ring.reward[s, e].double()).float()
     assert torch.equal(b["reward"][0], want)
+
+
+@pytest.mark.gpu
+def test_segmented_graph_update_on_one_rank(tmp_path):
+    """The multi-rank update (a chain of CUDA graphs cut at the gradient all-reduces, flat gradient buffers) run in a
+    one-rank NCCL group: it learns (critic loss on a fixed batch falls), moves the target networks, and keeps every
+    .grad a view of its network's flat buffer.  scripts/check_segmented_learn.py is the two-rank version (ranks stay
+    bit-identical; run under torchrun)."""
+    dev = torch.device("cuda", 0)
+    dist.init_process_group("nccl", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1, device_id=dev)
+    try:
+        ag = maddpg.BatchedMADDPG(2, 160, 9, device=dev, seed=5)
+        ag.force_segmented = True
+        g = torch.Generator(device=dev).manual_seed(1)
+        batch = {"state": torch.randn(128, 2, 160, device=dev, generator=g), "next_state": torch.randn(128, 2, 160, device=dev, generator=g),
+                 "action": torch.rand(128, 2, 9, device=dev, generator=g), "reward": torch.randn(128, 2, device=dev, generator=g),
+                 "done": torch.zeros(128, 2, device=dev)}
+        tgt0 = [p.clone() for p in ag.critic_targets[0].parameters()]
+        losses = [float(ag.learn(batch).critic_loss.sum()) for _ in range(40)]
+        assert ag._segments is not None and len(ag._segments["graphs"]) == 5
+        assert losses[-1] < 0.2 * losses[0], (losses[0], losses[-1])
+        assert any(not torch.equal(a, b) for a, b in zip(tgt0, ag.critic_targets[0].parameters()))
+        fa, fc = ag._segments["flat"]
+        for net, flat in zip(ag.actors + ag.critics, fa + fc):
+            lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+            assert all(lo <= p.grad.data_ptr() < hi for p in net.parameters())
+    finally:
+        dist.destroy_process_group()
