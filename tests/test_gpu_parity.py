@@ -351,3 +351,30 @@ print("OK")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "OK" in res.stdout, res.stdout + res.stderr
+
+
+def test_pinned_io_block_matches_tensor_api():
+    """PinnedIO (every input and output in one pinned host block, stepped by the resident kernel; what the E = 1 drop-in
+    classes use) against the tensor API on the same seed, device-RNG mode, 96 envs."""
+    import numpy as np
+    import torch
+    from marl_responsible_nav_b200 import BatchedGridWorld
+    E = 96
+    a = BatchedGridWorld("Level 3", num_envs=E, fear=True, fear_weight=-5.0, seed=31)
+    b = BatchedGridWorld("Level 3", num_envs=E, fear=True, fear_weight=-5.0, seed=31)
+    io = a.pinned_io()
+    io.reset()
+    ob = b.reset()
+    assert np.array_equal(io.obs, ob.obs.cpu().numpy()) and np.array_equal(io.positions, ob.positions.cpu().numpy())
+    assert np.array_equal(io.action_mask, ob.action_mask.cpu().numpy())
+    rng = np.random.default_rng(3)
+    for t in range(40):
+        la = rng.integers(0, 9, size=(E, 2)).astype(np.int8)
+        io.actions[:] = la
+        io.step()
+        ob = b.step(la)
+        for name in ("obs", "reward", "shaped_reward", "fear", "terminated", "truncated", "ended", "action_mask", "positions"):
+            assert np.array_equal(getattr(io, name), getattr(ob, name).cpu().numpy()), (t, name)
+        assert np.array_equal(io.info, ob.info.cpu().numpy().view(np.uint32)), t
+        assert np.array_equal(io.obs_code, ob.obs_code.cpu().numpy().view(np.uint64)), t
+    assert torch.equal(a.state_dict(), b.state_dict())
