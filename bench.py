@@ -239,6 +239,58 @@ def device_timed(a, E, fear, K, W, world, rank, dev, sample_clocks=False):
             "obs_bytes": obs_bytes, "clocks": clocks, "n_act": n_act}
 
 
+def masked_uniform_runs(a, E, dev, seeds=(0, 42, 66), steps=384):
+    """the same workload with learner actions drawn uniformly among the ALLOWED actions (get_action_mask) --
+    fewer wall bumps, another crash rate -- for three env seeds.  The action of step t+1 depends on the mask step t wrote,
+    so the sampler (three small PyTorch kernels) sits between the steps and inside the timed region; the loop is replayed
+    from a CUDA graph like the headline loop.  Reported next to the headline, never instead of it."""
+    import torch
+    from marl_responsible_nav_b200 import BatchedGridWorld
+    out = []
+    for seed in seeds:
+        env = BatchedGridWorld(a.scenario, num_envs=E, device=dev, fear=bool(a.fear), fear_weight=-5.0, auto_reset=True,
+                               max_steps=150, seed=seed)
+        gen = torch.Generator(device=dev).manual_seed(seed)
+        state = {"o": env.reset()}
+        u = torch.empty((E, env.n_learners, 9), device=dev)
+
+        def run(n):
+            for _ in range(n):
+                u.uniform_(0.01, 1.0, generator=gen)
+                ids = (u * state["o"].action_mask).argmax(-1).to(torch.int8)
+                state["o"] = env.step(ids)
+
+        run(32)
+        env.sync()
+        g = torch.cuda.CUDAGraph()
+        try:
+            g.register_generator_state(gen)
+            with torch.cuda.graph(g):
+                run(64)
+        except Exception:                                   # no graph-safe generator support: eager launches
+            g = None
+        env.sync()
+        env.reset_stats()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        if g is None:
+            run(steps)
+        else:
+            for _ in range(steps // 64):
+                g.replay()
+        ev1.record()
+        torch.cuda.synchronize()
+        st = env.stats()
+        n = float(E * steps)                                # (the library's own step counter does not see graph replays)
+        out.append({"seed": seed, "steps": steps, "graph": g is not None,
+                    "agent_steps_per_s": E * env.n_learners * steps / (ev0.elapsed_time(ev1) * 1e-3),
+                    "learner_crashes_per_env_step": st["crashes"] / n, "apples_per_env_step": st["apples"] / n,
+                    "mean_episode_len": st["episode_len_sum"] / max(1, st["episodes"]),
+                    "fear_nonzero_per_agent_step": st["fear_nonzero"] / (n * env.n_learners)})
+        env.close()
+    return out
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -307,6 +359,14 @@ def run_ours(a):
         e2e["memcpy_value"] = timed_host_loop(zero_copy=False)
     del env, ring, r
 
+    # ---- masked-uniform learner actions, seeds {0, 42, 66}, N = 1 only
+    variants = None
+    if world == 1 and not a.no_scale_points:
+        try:
+            variants = masked_uniform_runs(a, E, dev)
+        except Exception as exc:                            # an extra: must not cost the headline line
+            variants = [{"failed": repr(exc)}]
+
     # ---- the same kernel at a batch that fills the GPU (the step kernel's roofline point), N = 1 only
     scale_points = None
     if world == 1 and not a.no_scale_points:
@@ -349,7 +409,7 @@ def run_ours(a):
                              + ("CUDA-graph replay" if a.graph else "eager launches")
                              + f"; at {E} envs one launch moves {algo / 2**20:.1f} MiB ({algo / peak / 1e3:.2f} us at peak): small batches are "
                                "launch/latency-bound, see scale_points for the step kernel at 1M envs"},
-        "scale_points": scale_points,
+        "scale_points": scale_points, "masked_uniform_runs": variants,
         "workload_stats": {"episodes": stat_vec[0].item(), "mean_episode_len": stat_vec[1].item() / max(1.0, stat_vec[0].item()),
                            "learner_crashes_per_env_step": stat_vec[2].item() / (world * E * K),
                            "apples_per_env_step": stat_vec[3].item() / (world * E * K),
