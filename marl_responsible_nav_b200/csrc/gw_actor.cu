@@ -3,22 +3,24 @@
 // Per learner k: obs(160) -> Linear 128 -> LayerNorm -> ReLU -> Linear 128 -> LayerNorm -> ReLU -> Linear 9 ->
 // GumbelSoftmax (+ Gaussian exploration noise, clip [0,1], action mask, arg-max).
 //
-// One CTA = 512 threads on a tile of up to 128 rows (envs) of one learner; both 128-wide layers run on the tensor cores:
+// One CTA = 512 threads on tiles of up to 128 rows (envs) of one learner; all three layers run on the tensor cores:
 //   layer 1  An observation is the constant map template plus <= 5 special cells, so W1*obs + b1 = c1 + W1 * delta with
 //            c1 = b1 + W1 * template (fp32, exact) and delta non-zero in <= 5 cells.  The A operand is an all-zero
 //            [128 x cells] bf16 tile in which each row's thread drops its <= 5 values (0.5, 1..5, 9.5, 10..14: exact in
 //            bf16) -- built from the 8-byte obs_code gw_step wrote; the 640-byte observation is never read.  cells / 16
 //            tcgen05.mma (M=128, N=128, K=16, bf16 -> fp32) against W1 (bf16, UMMA layout, one TMA bulk copy) accumulate
 //            in TMEM columns 0..127.
-//   LN 1     warps w, w+4, w+8, w+12 reach the same TMEM lane quarter (a warp's lanes are those of its id mod 4) and take
-//            32 of the 128 columns each (tcgen05.ld, thread = row): + c1, LayerNorm (partial sums joined through shared
-//            memory), ReLU, bf16 into the A operand of layer 2 (UMMA K-major core matrices; it reuses the space of the
-//            layer-1 operand, which is cleared again once layer 2 has read it).
-//   layer 2  [128 x 128] x W2^T: 8 tcgen05.mma into TMEM columns 128..255, tcgen05.commit arrives on an mbarrier.
-//   epilogue the same four-way column split: LayerNorm, ReLU and the 128 -> 9 products per column group, joined through
-//            shared memory; the first group finishes Gumbel softmax / noise / mask / arg-max.  The Philox words of the
-//            noise are drawn by all threads while layer 1 runs.  Small batches use half-full tiles (64 rows) so that the
-//            grid covers the machine.
+//   LN 1     warps that share a TMEM lane quarter (a warp's lanes are those of its id mod 4) split the 128 columns
+//            (tcgen05.ld, thread = row): + c1, LayerNorm (partial sums joined through shared memory), ReLU, bf16 into the
+//            A operand of layer 2 (UMMA K-major core matrices; it reuses the space of the layer-1 operand).
+//   layer 2  [128 x 128] x W2^T: 8 tcgen05.mma into TMEM columns 128..255.
+//   LN 2     the same column split: + b2, LayerNorm, ReLU, bf16 into the A operand of layer 3 (same space again).
+//   layer 3  [128 x 128] x W3p^T with W3 padded from 9 to 16 outputs: 8 tcgen05.mma with N = 16 into TMEM columns 0..15;
+//            the operand tile is cleared for the next tile once they have completed.
+//   head     the first column group reads the 9 logits of its row (+ b3) and finishes Gumbel softmax / exploration noise /
+//            clip / mask / arg-max.  The Philox words of the noise are drawn by all threads while layer 1 runs.
+// Small batches use half-full tiles (64 rows) so that the grid covers the machine; large ones keep two tiles in flight per
+// CTA (two 8-warp groups out of phase, see Fixed<GROUPS>).
 // sm_100a only (tcgen05 / TMEM); descriptors follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
 #include <cstdio>
 #include <cstdlib>
@@ -42,7 +44,7 @@ struct ActorParams {                     // device-resident, per learner
   float ln1_g[HID], ln1_b[HID];
   alignas(16) __nv_bfloat16 w2_umma[HID * HID];   // W2 [out n][in k] in the canonical K-major core-matrix layout
   float b2[HID], ln2_g[HID], ln2_b[HID];
-  float w3[NACT][HID];
+  alignas(16) __nv_bfloat16 w3_umma[16 * HID];   // W3 [out o, padded to 16][in j] in the canonical K-major core-matrix layout
   float b3[NACT];
 };
 
@@ -67,14 +69,20 @@ __host__ __device__ __forceinline__ uint32_t umma_off(int r, int k) {
   return (uint32_t)(((k >> 3) * 16 + (r >> 3)) * 128 + (r & 7) * 16 + (k & 7) * 2);
 }
 
-__device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr) {
+// the same for a 16-row operand (W3 padded from 9 to 16 outputs): two 8-row groups per K chunk, LBO = 256 B
+__host__ __device__ __forceinline__ uint32_t umma_off16(int r, int k) {
+  return (uint32_t)(((k >> 3) * 2 + (r >> 3)) * 128 + (r & 7) * 16 + (k & 7) * 2);
+}
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_bytes = 2048u) {
   // cute::UMMA::SmemDescriptor: start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46), version = 1 [46,48), SWIZZLE_NONE
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) |
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) |
          (1ull << 46);
 }
 
 // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b format BF16 (1) [7,10)/[10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+constexpr uint32_t IDESC_N16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);   // layer 3
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -102,11 +110,10 @@ template <int GROUPS>
 struct Fixed {
   static constexpr int NGRP = THREADS / GROUPS / 128;         // column groups of the epilogues (warps sharing a TMEM lane quarter)
   alignas(1024) uint8_t w2[HID * HID * 2];
-  alignas(16) float w3[NACT][HID];
+  alignas(128) uint8_t w3[16 * HID * 2];             // W3 padded to 16 outputs, bf16, UMMA layout
   float b3[NACT];
   float c1[HID], ln1_g[HID], ln1_b[HID], b2[HID], ln2_g[HID], ln2_b[HID];
   alignas(8) float2 part[GROUPS][NGRP][ROWS];       // LayerNorm partial (sum, sum of squares) per column group and row
-  float plog[GROUPS][NGRP - 1][ROWS][NACT + 1];     // the other column groups' shares of the 9 logits
   uint32_t rnd[GROUPS][ROWS][29];                   // Philox words of the head's noise
   alignas(8) unsigned long long bar[GROUPS], bar_w; // MMA completion per group; arrival of W1 / W2
   uint32_t tmem_base;
@@ -136,14 +143,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ void mma_k16(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, int k_steps) {
+// k_steps MMAs of K = 16: A is a 128-row operand tile, B has `b_rows` (= N) rows
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void mma_k16(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, int k_steps, uint32_t idesc = IDESC,
+                                        uint32_t b_rows = 128u) {
+  const uint32_t b_lbo = b_rows * 16u;                     // bytes between K-adjacent core matrices of B
   for (int kk = 0; kk < k_steps; ++kk) {
-    const uint64_t da = smem_desc(a_addr + kk * 4096), db = smem_desc(b_addr + kk * 4096);
+    const uint64_t da = smem_desc(a_addr + kk * 4096), db = smem_desc(b_addr + kk * 2 * b_lbo, b_lbo);
     const uint32_t acc = kk > 0 ? 1u : 0u;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(acc)
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
         : "memory");
   }
 }
@@ -178,15 +198,16 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
     for (int g = 0; g < GROUPS; ++g) mbar_init((uint32_t)__cvta_generic_to_shared(&s.bar[g]), 1);
     mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(op_bytes + (uint32_t)(HID * HID * 2)) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(op_bytes + (uint32_t)(HID * HID * 2 + 16 * HID * 2)) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"((uint32_t)__cvta_generic_to_shared(w1_tile)), "l"(P.w1_umma), "r"(op_bytes), "r"(bar_w) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"((uint32_t)__cvta_generic_to_shared(s.w2)), "l"(P.w2_umma), "n"(HID * HID * 2), "r"(bar_w) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(s.w3)), "l"(P.w3_umma), "n"(16 * HID * 2), "r"(bar_w) : "memory");
   }
   {
     for (int i = lt; i < (int)(op_bytes / 16); i += TPG) reinterpret_cast<uint4*>(a_tile)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < NACT * HID; i += THREADS) (&s.w3[0][0])[i] = (&P.w3[0][0])[i];
     if (tid < NACT) s.b3[tid] = P.b3[tid];
     if (tid < HID) {
       s.c1[tid] = P.c1[tid]; s.ln1_g[tid] = P.ln1_g[tid]; s.ln1_b[tid] = P.ln1_b[tid];
@@ -201,6 +222,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
   const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(a_tile);
   const uint32_t w1_addr = (uint32_t)__cvta_generic_to_shared(w1_tile);
   const uint32_t w2_addr = (uint32_t)__cvta_generic_to_shared(s.w2);
+  const uint32_t w3_addr = (uint32_t)__cvta_generic_to_shared(s.w3);
   uint32_t phase = 0;
   bool w_pending = true;
 
@@ -322,7 +344,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
     phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    // ---- epilogue: LayerNorm 2 + ReLU + this column group's share of the 128 -> 9 layer
+    // ---- LayerNorm 2 + ReLU -> operand of layer 3 (again this thread's columns of its row, again in the operand tile)
     if (quarter_on) {
 #pragma unroll
       for (int c0 = 0; c0 < CPG; c0 += 32) {
@@ -337,12 +359,9 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
       }
       s.part[gi][cg][m] = make_float2(mu_p, sq_p);
     }
-    // layer 2 has read its operand: back to the all-zero layer-1 operand for the next tile
-    for (int i = lt; i < (int)(op_bytes / 16); i += TPG) reinterpret_cast<uint4*>(a_tile)[i] = make_uint4(0, 0, 0, 0);
     asm volatile("tcgen05.fence::before_thread_sync;");
-    group_sync();
+    group_sync();                                       // partial sums of the column groups; layer 2 has read its operand
     asm volatile("tcgen05.fence::after_thread_sync;");
-    float logit[NACT];
     if (quarter_on) {
       float su = 0.f, sq = 0.f;
 #pragma unroll
@@ -350,32 +369,44 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
       const float mu = su * (1.0f / HID);
       const float rs = rsqrtf(fmaxf(sq * (1.0f / HID) - mu * mu, 0.f) + 1e-5f);
 #pragma unroll
-      for (int o = 0; o < NACT; ++o) logit[o] = cg == 0 ? s.b3[o] : 0.f;
+      for (int c8 = 0; c8 < CPG; c8 += 8) {
+        uint32_t pk[4];
 #pragma unroll
-      for (int j0 = 0; j0 < CPG; j0 += 4) {
-        float x[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = col0 + j0 + u;
-          x[u] = fmaxf((acc[j0 + u] - mu) * rs * s.ln2_g[j] + s.ln2_b[j], 0.f);
+        for (int u = 0; u < 8; u += 2) {
+          const int j = col0 + c8 + u;
+          const float x0 = live ? fmaxf((acc[c8 + u] - mu) * rs * s.ln2_g[j] + s.ln2_b[j], 0.f) : 0.f;
+          const float x1 = live ? fmaxf((acc[c8 + u + 1] - mu) * rs * s.ln2_g[j + 1] + s.ln2_b[j + 1], 0.f) : 0.f;
+          pk[u >> 1] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(x0)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16(x1)) << 16);
         }
-#pragma unroll
-        for (int o = 0; o < NACT; ++o) {
-          const float4 w = *reinterpret_cast<const float4*>(&s.w3[o][col0 + j0]);   // same address in every lane: broadcast
-          logit[o] = fmaf(x[0], w.x, fmaf(x[1], w.y, fmaf(x[2], w.z, fmaf(x[3], w.w, logit[o]))));
-        }
-      }
-      if (cg > 0) {
-#pragma unroll
-        for (int o = 0; o < NACT; ++o) s.plog[gi][cg - 1][m][o] = logit[o];
+        *reinterpret_cast<uint4*>(a_tile + umma_off(m, col0 + c8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
     }
-    group_sync();                                       // the other groups' shares of the logits are in shared memory
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    group_sync();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+
+    // ---- layer 3: D[128 x 16] (TMEM columns 0..15; the layer-1 accumulator is long consumed) = A3[128x128] * W3p^T
+    if (lt == 0) {
+      mma_k16(tmem, a_addr, w3_addr, HID / 16, IDESC_N16, 16u);
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    // layer 3 has read its operand: back to the all-zero layer-1 operand for the next tile
+    for (int i = lt; i < (int)(op_bytes / 16); i += TPG) reinterpret_cast<uint4*>(a_tile)[i] = make_uint4(0, 0, 0, 0);
+    float logit[NACT];
+    if (quarter_on && cg == 0) {
+      uint32_t r[16];
+      tmem_ld16(lane_addr, r);
+#pragma unroll
+      for (int o = 0; o < NACT; ++o) logit[o] = __uint_as_float(r[o]) + s.b3[o];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    group_sync();                                       // operand tile cleared, accumulators read: the next tile may start
+    asm volatile("tcgen05.fence::after_thread_sync;");
     if (live && cg == 0) {
-#pragma unroll
-      for (int g = 0; g < NGRP - 1; ++g)
-#pragma unroll
-        for (int o = 0; o < NACT; ++o) logit[o] += s.plog[gi][g][m][o];
       // GumbelSoftmax head (the reference's output activation draws fresh Gumbel noise on EVERY forward, evaluation
       // included) + Gaussian exploration noise (training), both from the Philox words drawn above
       if (a.gumbel) {
@@ -406,7 +437,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
       }
       a.ids[e * a.nl + k] = (int8_t)best;
     }
-    // part / plog / rnd / the operand tile are rewritten by the next tile only behind barriers that every warp reaches
+    // part / rnd / the operand tile are rewritten by the next tile only behind barriers that every warp reaches
     // after it is done with them
   }
   if (w_pending && tid == 0) mbar_wait(bar_w, 0u);         // a CTA whose first group has no tile must not exit with the copies in flight
@@ -436,7 +467,8 @@ __global__ void __launch_bounds__(256) actor_pack_kernel(PackArgs a) {
     const int n = i / HID, kk = i % HID;
     P.w2_umma[umma_off(n, kk) / 2] = __float2bfloat16(W.w2[i]);
   }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NACT * HID; i += stride) (&P.w3[0][0])[i] = W.w3[i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NACT * HID; i += stride)      // rows 9..15 stay zero (gw_actor_create)
+    P.w3_umma[umma_off16(i / HID, i % HID) / 2] = __float2bfloat16(W.w3[i]);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < HID; j += stride) {
     double acc = W.b1[j];
     for (int cell = 0; cell < cpo; ++cell)
@@ -483,7 +515,7 @@ static int pack_weights(gw_handle* h, const gw_actor_weights* w, int nl, std::ve
         P.w2_umma[gwa::umma_off(n, kk) / 2] = __float2bfloat16(W.w2[n * gwa::HID + kk]);
     for (int o = 0; o < gwa::NACT; ++o) {
       P.b3[o] = W.b3[o];
-      for (int j = 0; j < gwa::HID; ++j) P.w3[o][j] = W.w3[o * gwa::HID + j];
+      for (int j = 0; j < gwa::HID; ++j) P.w3_umma[gwa::umma_off16(o, j) / 2] = __float2bfloat16(W.w3[o * gwa::HID + j]);
     }
   }
   return GW_OK;
