@@ -112,7 +112,7 @@ struct Fixed {
   alignas(1024) uint8_t w2[HID * HID * 2];
   alignas(128) uint8_t w3[16 * HID * 2];             // W3 padded to 16 outputs, bf16, UMMA layout
   float b3[NACT];
-  float c1[HID], ln1_g[HID], ln1_b[HID], b2[HID], ln2_g[HID], ln2_b[HID];
+  alignas(16) float c1[HID], ln1_g[HID], ln1_b[HID], b2[HID], ln2_g[HID], ln2_b[HID];
   alignas(8) float2 part[GROUPS][NGRP][ROWS];       // LayerNorm partial (sum, sum of squares) per column group and row
   uint32_t rnd[GROUPS][ROWS][29];                   // Philox words of the head's noise
   alignas(8) unsigned long long bar[GROUPS], bar_w; // MMA completion per group; arrival of W1 / W2
@@ -315,15 +315,20 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
       for (int g = 0; g < NGRP; ++g) { const float2 pp = s.part[gi][g][m]; su += pp.x; sq += pp.y; }
       const float mu = su * (1.0f / HID);
       const float rs = rsqrtf(fmaxf(sq * (1.0f / HID) - mu * mu, 0.f) + 1e-5f);
+      const float nmr = -mu * rs;
 #pragma unroll
       for (int c8 = 0; c8 < CPG; c8 += 8) {                // one 16-byte core-matrix row per 8 columns
+        const float4 g0 = *reinterpret_cast<const float4*>(&s.ln1_g[col0 + c8]), g1 = *reinterpret_cast<const float4*>(&s.ln1_g[col0 + c8 + 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&s.ln1_b[col0 + c8]), b1 = *reinterpret_cast<const float4*>(&s.ln1_b[col0 + c8 + 4]);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         uint32_t pk[4];
 #pragma unroll
         for (int u = 0; u < 8; u += 2) {
-          const int j = col0 + c8 + u;
-          const float x0 = live ? fmaxf((acc[c8 + u] - mu) * rs * s.ln1_g[j] + s.ln1_b[j], 0.f) : 0.f;
-          const float x1 = live ? fmaxf((acc[c8 + u + 1] - mu) * rs * s.ln1_g[j + 1] + s.ln1_b[j + 1], 0.f) : 0.f;
-          pk[u >> 1] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(x0)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16(x1)) << 16);
+          // (acc - mu) * rs as one fma, then the affine part, ReLU; rows without an env produce zeros
+          const float x0 = live ? fmaxf(fmaf(fmaf(acc[c8 + u], rs, nmr), gg[u], bb[u]), 0.f) : 0.f;
+          const float x1 = live ? fmaxf(fmaf(fmaf(acc[c8 + u + 1], rs, nmr), gg[u + 1], bb[u + 1]), 0.f) : 0.f;
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);          // one cvt for the pair
+          pk[u >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
         }
         *reinterpret_cast<uint4*>(a_tile + umma_off(m, col0 + c8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
@@ -368,15 +373,20 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
       for (int g = 0; g < NGRP; ++g) { const float2 pp = s.part[gi][g][m]; su += pp.x; sq += pp.y; }
       const float mu = su * (1.0f / HID);
       const float rs = rsqrtf(fmaxf(sq * (1.0f / HID) - mu * mu, 0.f) + 1e-5f);
+      const float nmr = -mu * rs;
 #pragma unroll
-      for (int c8 = 0; c8 < CPG; c8 += 8) {
+      for (int c8 = 0; c8 < CPG; c8 += 8) {                // one 16-byte core-matrix row per 8 columns
+        const float4 g0 = *reinterpret_cast<const float4*>(&s.ln2_g[col0 + c8]), g1 = *reinterpret_cast<const float4*>(&s.ln2_g[col0 + c8 + 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&s.ln2_b[col0 + c8]), b1 = *reinterpret_cast<const float4*>(&s.ln2_b[col0 + c8 + 4]);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         uint32_t pk[4];
 #pragma unroll
         for (int u = 0; u < 8; u += 2) {
-          const int j = col0 + c8 + u;
-          const float x0 = live ? fmaxf((acc[c8 + u] - mu) * rs * s.ln2_g[j] + s.ln2_b[j], 0.f) : 0.f;
-          const float x1 = live ? fmaxf((acc[c8 + u + 1] - mu) * rs * s.ln2_g[j + 1] + s.ln2_b[j + 1], 0.f) : 0.f;
-          pk[u >> 1] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(x0)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16(x1)) << 16);
+          // (acc - mu) * rs as one fma, then the affine part, ReLU; rows without an env produce zeros
+          const float x0 = live ? fmaxf(fmaf(fmaf(acc[c8 + u], rs, nmr), gg[u], bb[u]), 0.f) : 0.f;
+          const float x1 = live ? fmaxf(fmaf(fmaf(acc[c8 + u + 1], rs, nmr), gg[u + 1], bb[u + 1]), 0.f) : 0.f;
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);          // one cvt for the pair
+          pk[u >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
         }
         *reinterpret_cast<uint4*>(a_tile + umma_off(m, col0 + c8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
