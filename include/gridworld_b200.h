@@ -216,6 +216,37 @@ int gw_feal(gw_handle* h, int64_t n_cases, const int8_t* n_agents_per_case, cons
             const int8_t* actions, const int8_t* mdr, const uint8_t* in_list, double* feal, int8_t* n_mdr,
             int8_t* n_act, void* stream);
 
+/* ---- replay sampling (K4, read side): `memory.sample(BATCH_SIZE)` as called at maddpg/agent.py:209-211 -----------
+ * The replay ring is caller-owned device memory (time-major: T slots x E envs) that gw_step filled through gw_io:
+ * slot t % T holds observation t, slot (t+1) % T the next one; `final_obs` holds the terminal observation of the rows
+ * whose episode ended in that step (`ended` != 0).  One kernel draws `batch` (time, env) pairs uniformly over the
+ * newest min(t_now, T-1) time steps (with replacement; Philox(seed, sample index, draw)) and gathers
+ * state / action / reward / next_state / done into f32 batch tensors -- the fields of maddpg/agent.py:70. */
+typedef struct gw_replay_view {
+  uint32_t struct_size;          /* sizeof(gw_replay_view) */
+  int32_t obs_dtype;             /* GW_OBS_F32 / GW_OBS_BF16: element type of obs / final_obs */
+  int64_t slots;                 /* T >= 3 */
+  int64_t num_envs;              /* E */
+  int32_t n_learners;            /* L */
+  int32_t obs_len;               /* H*W */
+  int32_t action_dim;            /* 9 */
+  int32_t pad_;
+  const void* obs;               /* [T, E, L, obs_len] */
+  const void* final_obs;         /* [T, E, L, obs_len] */
+  const float* action;           /* [T, E, L, action_dim] the actor's continuous action vectors */
+  const float* reward;           /* [T, E, L] what the trainer stores (the shaped reward) */
+  const uint8_t* terminated;     /* [T, E, L] */
+  const uint8_t* ended;          /* [T, E] */
+} gw_replay_view;
+
+/* t_now = transitions recorded per env so far.  t_in / env_in (device int64 [batch], both or neither): take these
+ * indices instead of drawing (absolute time steps within the stored window).  Outputs (device): state / next_state
+ * f32 [batch, L, obs_len], action f32 [batch, L, action_dim], reward / done f32 [batch, L]; t_out / env_out int64
+ * [batch], nullable.  `h` provides the device, the error string and the launch count.  Stream-ordered, no sync. */
+int gw_replay_sample(gw_handle* h, const gw_replay_view* ring, int64_t t_now, int64_t batch, uint64_t seed,
+                     uint64_t draw, const int64_t* t_in, const int64_t* env_in, float* state, float* action,
+                     float* reward, float* next_state, float* done, int64_t* t_out, int64_t* env_out, void* stream);
+
 /* ---- actor forward (K5): AgileRL `MADDPG.get_action` as called at maddpg/agent.py:109-113 -----------------------
  * One actor per learner: Linear(H*W,128)-LayerNorm-ReLU-Linear(128,128)-LayerNorm-ReLU-Linear(128,9)-GumbelSoftmax
  * (shapes from the reference's checkpoints), Gaussian exploration noise, clip to [0,1], action mask,

@@ -152,7 +152,8 @@ class BatchedMADDPG:
             g, static, out, shapes = self._graph
             if all(tuple(batch[k].shape) == shapes[k] for k in keys):
                 for k in keys:
-                    static[k].copy_(batch[k])
+                    if batch[k] is not static[k]:          # the sampler may have written into the graph's inputs itself
+                        static[k].copy_(batch[k])
                 g.replay()
                 return LearnStats(out.actor_loss.clone(), out.critic_loss.clone())
             self._graph, self._eager_learns = None, 0      # another batch shape: start over
@@ -167,6 +168,15 @@ class BatchedMADDPG:
         self._graph = (g, static, out, {k: tuple(batch[k].shape) for k in keys})
         g.replay()                                         # capture only records: this is the update for `batch`
         return LearnStats(out.actor_loss.clone(), out.critic_loss.clone())
+
+    def static_inputs(self) -> Optional[Dict[str, torch.Tensor]]:
+        """The captured update's input tensors (None before the capture): a sampler that fills them directly saves
+        the five copies per update."""
+        if self._graph is not None:
+            return self._graph[1]
+        if self._segments is not None:
+            return self._segments["static"]
+        return None
 
     # ---- several ranks: the same update cut into CUDA graphs at the gradient all-reduces
     def _learn_segmented(self, batch: Dict[str, torch.Tensor]) -> LearnStats:
@@ -187,7 +197,8 @@ class BatchedMADDPG:
                                                            {k: tuple(batch[k].shape) for k in keys})
         else:
             for k in keys:
-                seg["static"][k].copy_(batch[k])
+                if batch[k] is not seg["static"][k]:
+                    seg["static"][k].copy_(batch[k])
         world = dist.get_world_size()
         for g, flat in zip(seg["graphs"], seg["reduce_after"]):
             g.replay()
@@ -321,7 +332,7 @@ class BatchedTrainer:
     """MADDPGAgent.train (maddpg/agent.py:77-252) for E environments at once, everything on the device."""
 
     def __init__(self, env, agent: Optional[BatchedMADDPG] = None, hp: Optional[Dict] = None,
-                 updates_per_learn: int = 1, seed: int = 0, fused_actor: bool = True):
+                 updates_per_learn: int = 1, seed: int = 0, fused_actor: bool = True, fused_sampler: bool = True):
         from .replay import ReplayRing
         self.env = env
         self.hp = dict(DEFAULT_HP if hp is None else hp)
@@ -330,6 +341,8 @@ class BatchedTrainer:
                                device=env.device, obs_dtype=env.obs_dtype)
         self.updates_per_learn = int(updates_per_learn)
         self.gen = torch.Generator(device=env.device).manual_seed(seed + 1)
+        self.fused_sampler = bool(fused_sampler) and env.device.type == "cuda"      # csrc/gw_replay.cu
+        self.sample_seed, self._batch = seed + 1, None
         self.t = 0
         self.out = env.reset(obs_out=self.ring.obs_slot(0))
         self.losses: List[LearnStats] = []
@@ -338,6 +351,18 @@ class BatchedTrainer:
         if fused_actor and env.device.type == "cuda" and env.obs_len == self.agent.obs_dim:
             from .actor import FusedActor
             self.fused = FusedActor(env, self.agent.actors, seed=seed + 2)
+
+    def _sample(self, batch_size: int) -> Dict[str, torch.Tensor]:
+        """One batch for `learn`.  On the GPU: one gw_replay_sample launch (indices drawn and rows gathered by the
+        kernel), written straight into the captured update's input tensors once they exist."""
+        if not self.fused_sampler:
+            return self.ring.sample(batch_size, self.gen)
+        dst = self.agent.static_inputs()
+        if dst is not None and tuple(dst["state"].shape) == (batch_size, self.ring.L, self.ring.obs_len):
+            return self.ring.sample_fused(self.env, batch_size, seed=self.sample_seed, out=dst)
+        if self._batch is None or self._batch["state"].shape[0] != batch_size:
+            self._batch = self.ring.new_batch(batch_size)
+        return self.ring.sample_fused(self.env, batch_size, seed=self.sample_seed, out=self._batch)
 
     def train(self, env_steps: int, learn: bool = True) -> Dict[str, float]:
         """`env_steps` synchronous steps of all E envs (auto-reset replaces the reference's per-episode outer loop;
@@ -361,7 +386,7 @@ class BatchedTrainer:
             # the reference learns every LEARN_STEP steps of its single env once BATCH_SIZE transitions exist
             if learn and t % hp["LEARN_STEP"] == 0 and len(ring) >= hp["BATCH_SIZE"]:
                 for _ in range(self.updates_per_learn):
-                    self.losses.append(agent.learn(ring.sample(hp["BATCH_SIZE"], self.gen)))
+                    self.losses.append(agent.learn(self._sample(hp["BATCH_SIZE"])))
                 if self.fused is not None:
                     self.fused.update(agent.actors)          # the kernel keeps its own packed copy of the weights
         return env.stats()

@@ -68,6 +68,61 @@ class ReplayRing:
     def __len__(self) -> int:
         return min(self.t, self.T - 1) * self.E
 
+    # ---- sampling in one kernel (csrc/gw_replay.cu): draws the indices and gathers the batch on the device
+    def _view(self):
+        import ctypes as C
+        from . import _native as N
+        v = getattr(self, "_c_view", None)
+        if v is None:
+            v = N.GwReplayView()
+            v.struct_size = C.sizeof(N.GwReplayView)
+            v.obs_dtype = {torch.float32: N.GW_OBS_F32, torch.bfloat16: N.GW_OBS_BF16}[self.obs.dtype]
+            v.slots, v.num_envs, v.n_learners, v.obs_len, v.action_dim = self.T, self.E, self.L, self.obs_len, self.action_dim
+            v.obs, v.final_obs, v.action = self.obs.data_ptr(), self.final_obs.data_ptr(), self.action.data_ptr()
+            v.reward, v.terminated, v.ended = self.shaped_reward.data_ptr(), self.terminated.data_ptr(), self.ended.data_ptr()
+            self._c_view = v
+        return v
+
+    def new_batch(self, batch_size: int) -> Dict[str, torch.Tensor]:
+        """f32 batch tensors of the shapes `sample_fused` fills (what BatchedMADDPG.learn consumes)."""
+        B, L, dev = int(batch_size), self.L, self.device
+        f = dict(dtype=torch.float32, device=dev)
+        return {"state": torch.empty((B, L, self.obs_len), **f), "action": torch.empty((B, L, self.action_dim), **f),
+                "reward": torch.empty((B, L), **f), "next_state": torch.empty((B, L, self.obs_len), **f),
+                "done": torch.empty((B, L), **f), "t": torch.empty((B,), dtype=torch.int64, device=dev),
+                "env": torch.empty((B,), dtype=torch.int64, device=dev)}
+
+    def sample_fused(self, env, batch_size: int, seed: int = 0, out: Optional[Dict[str, torch.Tensor]] = None,
+                     indices=None) -> Dict[str, torch.Tensor]:
+        """`memory.sample(BATCH_SIZE)` (maddpg/agent.py:209-211) as ONE kernel launch: gw_replay_sample draws
+        `batch_size` (time, env) pairs with Philox(seed, sample, draw number) -- uniform over the stored transitions,
+        with replacement -- and gathers the five fields into `out` (f32; `new_batch` makes one).  `indices` =
+        (t_abs, env) int64 device tensors to gather instead of drawing.  `env` is the BatchedGridWorld that owns the
+        library handle; there is no PyTorch fallback."""
+        import ctypes as C
+        from . import _native as N
+        if self.device.type != "cuda":
+            raise RuntimeError("sample_fused needs the CUDA library (ring on a CUDA device); there is no CPU path")
+        B = int(batch_size)
+        out = self.new_batch(B) if out is None else out
+        for k, shape in (("state", (B, self.L, self.obs_len)), ("action", (B, self.L, self.action_dim)), ("reward", (B, self.L)),
+                         ("next_state", (B, self.L, self.obs_len)), ("done", (B, self.L))):
+            t = out[k]
+            if t.dtype != torch.float32 or tuple(t.shape) != shape or not t.is_contiguous() or t.device != self.device:
+                raise ValueError(f"sample_fused: out[{k!r}] must be a contiguous f32 tensor of shape {shape} on {self.device}")
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        t_in = env_in = None
+        if indices is not None:
+            t_in, env_in = (x.to(device=self.device, dtype=torch.int64).contiguous() for x in indices)
+            if t_in.shape != (B,) or env_in.shape != (B,):
+                raise ValueError("sample_fused: indices must be two int64 vectors of length batch_size")
+        self._draws = getattr(self, "_draws", 0) + (indices is None)
+        N.check(env.lib.gw_replay_sample(env._h, C.byref(self._view()), self.t, B, int(seed) & (2 ** 64 - 1), self._draws,
+                                         p(t_in), p(env_in), p(out["state"]), p(out["action"]), p(out["reward"]),
+                                         p(out["next_state"]), p(out["done"]), p(out.get("t")), p(out.get("env")),
+                                         env._stream()), env._h, "gw_replay_sample")
+        return out
+
     # ---- sampling (uniform over the stored transitions, like random.sample over the deque)
     def sample(self, batch_size: int, generator: Optional[torch.Generator] = None) -> Dict[str, torch.Tensor]:
         n_t = min(self.t, self.T - 1)

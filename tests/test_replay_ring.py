@@ -70,3 +70,74 @@ def test_ring_filled_by_step_kernel():
     ended_rows = batch["ended"]
     if ended_rows.any():
         assert not (batch["next_state"][ended_rows] == 0.5).any()
+
+
+def _fill_ring(env, ring, steps, seed=3):
+    gen = torch.Generator(device="cuda").manual_seed(seed + ring.t)
+    if ring.t == 0:
+        env.reset(obs_out=ring.obs_slot(0))
+    for t in range(ring.t, ring.t + steps):
+        acts = torch.randint(0, 9, (env.num_envs, env.n_learners), generator=gen, device="cuda", dtype=torch.int8)
+        env.step(acts, obs_out=ring.obs_slot(t + 1), final_obs_out=ring.final_slot(t), buffers=ring.buffers_slot(t))
+        ring.store_action(t, torch.rand((env.num_envs, env.n_learners, 9), generator=gen, device="cuda"))
+        ring.advance()
+    return gen
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("obs_dtype", [torch.float32, torch.bfloat16])
+def test_fused_sampler_matches_torch_indexing(obs_dtype):
+    """gw_replay_sample (one kernel) against ReplayRing.sample's PyTorch indexing on the same (time, env) pairs:
+    every field bit for bit, for fp32 and bf16 rings, with a ring that has wrapped around."""
+    from marl_responsible_nav_b200 import BatchedGridWorld
+    E = 257                                                   # odd: rows of every alignment class
+    env = BatchedGridWorld("Level 3", num_envs=E, fear=True, fear_weight=-5.0, auto_reset=True, seed=5, obs_dtype=obs_dtype)
+    ring = ReplayRing(E, env.n_learners, env.obs_len, capacity=7 * E, obs_dtype=obs_dtype)
+    gen = _fill_ring(env, ring, 23)
+    assert ring.t > ring.T                                    # wrapped
+    B = 1000
+    ref = ring.sample(B, gen)
+    assert ref["ended"].any() and not ref["ended"].all()      # both next_state sources are exercised
+    got = ring.sample_fused(env, B, indices=(ref["t"], ref["env"]))
+    assert torch.equal(got["t"], ref["t"]) and torch.equal(got["env"], ref["env"])
+    for k in ("state", "action", "reward", "next_state"):
+        assert got[k].dtype == torch.float32
+        assert torch.equal(got[k], ref[k].float()), k
+    assert torch.equal(got["done"], ref["done"].float())
+    env.sync()
+
+
+@pytest.mark.gpu
+def test_fused_sampler_draws_uniform_valid_indices():
+    from marl_responsible_nav_b200 import BatchedGridWorld
+    E = 64
+    env = BatchedGridWorld("Level 3", num_envs=E, fear=False, auto_reset=True, seed=9)
+    ring = ReplayRing(E, env.n_learners, env.obs_len, capacity=8 * E)
+    empty_err = pytest.raises(RuntimeError, match="empty")
+    with empty_err:
+        ring.sample_fused(env, 8)
+    _fill_ring(env, ring, 5)                                  # 5 of 8 storable time steps so far
+    B = 1 << 16
+    a = ring.sample_fused(env, B, seed=1)
+    t, e = a["t"].clone(), a["env"].clone()
+    assert int(t.min()) == 0 and int(t.max()) == 4 and int(e.min()) == 0 and int(e.max()) == E - 1
+    ct = torch.bincount(t, minlength=5).double() / B
+    ce = torch.bincount(e, minlength=E).double() / B
+    assert (ct - 1 / 5).abs().max() < 0.01 and (ce - 1 / E).abs().max() < 0.003      # ~6 sigma
+    # gathered rows belong to the drawn indices
+    chk = ring.sample_fused(env, B, indices=(t, e), out=ring.new_batch(B))
+    assert torch.equal(chk["state"], ring.obs[t % ring.T, e]) and torch.equal(chk["reward"], ring.shaped_reward[t % ring.T, e])
+    # the next draw differs, the same (seed, draw number) repeats
+    b = ring.sample_fused(env, B, seed=1)
+    assert not torch.equal(b["t"], t)
+    ring._draws -= 1
+    c = ring.sample_fused(env, B, seed=1)
+    assert torch.equal(c["t"], b["t"]) and torch.equal(c["env"], b["env"])
+    d = ring.sample_fused(env, B, seed=2)
+    assert not torch.equal(d["env"], c["env"])
+    _fill_ring(env, ring, 30)                                 # wrapped: only the newest T-1 steps may be drawn
+    w = ring.sample_fused(env, B, seed=1)
+    assert int(w["t"].min()) == ring.t - (ring.T - 1) and int(w["t"].max()) == ring.t - 1
+    with pytest.raises(ValueError):
+        ring.sample_fused(env, 16, out=ring.new_batch(8))
+    env.sync()
