@@ -111,6 +111,8 @@ class BatchedMADDPG:
         self._graph = None                                 # (CUDAGraph, static batch, static LearnStats) once captured
         self._segments = None                              # several ranks: the update as a chain of graphs (see _learn_segmented)
         self._eager_learns = 0
+        self.parallel_agents = True                        # one-GPU graph: the agents' updates are parallel branches (see _learn)
+        self._side_streams: List[torch.cuda.Stream] = []
         self.force_segmented = False                       # tests: take the multi-rank path in a one-rank process group
 
     def parameters(self):
@@ -164,7 +166,7 @@ class BatchedMADDPG:
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            out = self._learn(static)
+            out = self._learn(static, parallel=self.parallel_agents)
         self._graph = (g, static, out, {k: tuple(batch[k].shape) for k in keys})
         g.replay()                                         # capture only records: this is the update for `batch`
         return LearnStats(out.actor_loss.clone(), out.critic_loss.clone())
@@ -277,7 +279,11 @@ class BatchedMADDPG:
         # capture only records: replay now, with the exchanges, so that this call is the update for `batch`
         return seg
 
-    def _learn(self, batch: Dict[str, torch.Tensor]) -> LearnStats:
+    def _learn(self, batch: Dict[str, torch.Tensor], parallel: bool = False) -> LearnStats:
+        """`parallel` (only while capturing the one-GPU graph): agent k's critic / actor update touches nothing agent j's
+        reads -- own critic, own actor, own optimisers; the other agents' actions come from the batch -- so the agents'
+        passes are recorded on forked streams and become parallel branches of the graph.  Same kernels, same operands,
+        same results as the sequential order; the ~120 launch-latency-sized kernels per agent overlap."""
         gamma, tau = self.hp["GAMMA"], self.hp["TAU"]
         s, a, r = batch["state"].float(), batch["action"].float(), batch["reward"].float()
         s2, done = batch["next_state"].float(), batch["done"].float()
@@ -286,12 +292,15 @@ class BatchedMADDPG:
         with torch.no_grad():
             a2 = torch.stack([self.actor_targets[k](s2[:, k]) for k in range(self.n)], dim=1)
             crit_in2 = torch.cat([flat_s2, a2.reshape(B, -1)], dim=1)
-        a_losses, c_losses = [], []
-        for k in range(self.n):
+            crit_in = torch.cat([flat_s, a.reshape(B, -1)], dim=1)
+        a_losses: List[Optional[torch.Tensor]] = [None] * self.n
+        c_losses: List[Optional[torch.Tensor]] = [None] * self.n
+
+        def agent_pass(k: int):
             with torch.no_grad():
                 q2 = self.critic_targets[k](crit_in2).squeeze(-1)
                 target = r[:, k] + gamma * (1.0 - done[:, k]) * q2
-            q = self.critics[k](torch.cat([flat_s, a.reshape(B, -1)], dim=1)).squeeze(-1)
+            q = self.critics[k](crit_in).squeeze(-1)
             c_loss = F.mse_loss(q, target)
             self.critic_opt[k].zero_grad(set_to_none=True)
             c_loss.backward()
@@ -304,8 +313,23 @@ class BatchedMADDPG:
             a_loss.backward()
             self._allreduce_grads(self.actors[k])
             self.actor_opt[k].step()
-            a_losses.append(a_loss.detach())
-            c_losses.append(c_loss.detach())
+            a_losses[k], c_losses[k] = a_loss.detach(), c_loss.detach()
+
+        if parallel and self.n > 1 and self.device.type == "cuda":
+            cur = torch.cuda.current_stream(self.device)
+            while len(self._side_streams) < self.n - 1:
+                self._side_streams.append(torch.cuda.Stream(self.device))
+            side = self._side_streams[:self.n - 1]
+            for st in side:                                 # fork after the shared prologue, before agent 0's work is recorded
+                st.wait_stream(cur)
+            for k in range(self.n):
+                with torch.cuda.stream(cur if k == 0 else side[k - 1]):
+                    agent_pass(k)
+            for st in side:                                 # join
+                cur.wait_stream(st)
+        else:
+            for k in range(self.n):
+                agent_pass(k)
         with torch.no_grad():                              # soft update, TAU (one multi-tensor kernel, not 40 small ones)
             src = [p for net in self.actors + self.critics for p in net.parameters()]
             dst = [p for net in self.actor_targets + self.critic_targets for p in net.parameters()]

@@ -83,6 +83,10 @@ class ReplayRing:
             self._c_view = v
         return v
 
+    def _same_device(self, t: torch.Tensor) -> bool:
+        return t.device.type == self.device.type and (self.device.index is None or t.device.index is None
+                                                       or t.device.index == self.device.index)
+
     def new_batch(self, batch_size: int) -> Dict[str, torch.Tensor]:
         """f32 batch tensors of the shapes `sample_fused` fills (what BatchedMADDPG.learn consumes)."""
         B, L, dev = int(batch_size), self.L, self.device
@@ -105,22 +109,33 @@ class ReplayRing:
             raise RuntimeError("sample_fused needs the CUDA library (ring on a CUDA device); there is no CPU path")
         B = int(batch_size)
         out = self.new_batch(B) if out is None else out
-        for k, shape in (("state", (B, self.L, self.obs_len)), ("action", (B, self.L, self.action_dim)), ("reward", (B, self.L)),
-                         ("next_state", (B, self.L, self.obs_len)), ("done", (B, self.L))):
-            t = out[k]
-            if t.dtype != torch.float32 or tuple(t.shape) != shape or not t.is_contiguous() or t.device != self.device:
-                raise ValueError(f"sample_fused: out[{k!r}] must be a contiguous f32 tensor of shape {shape} on {self.device}")
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        prep = self._prepared.get(id(out)) if hasattr(self, "_prepared") else None
+        if prep is None or prep[0] is not out or prep[1] != B:      # checked once per set of batch tensors
+            for k, shape in (("state", (B, self.L, self.obs_len)), ("action", (B, self.L, self.action_dim)), ("reward", (B, self.L)),
+                             ("next_state", (B, self.L, self.obs_len)), ("done", (B, self.L))):
+                t = out[k]
+                if t.dtype != torch.float32 or tuple(t.shape) != shape or not t.is_contiguous() or not self._same_device(t):
+                    raise ValueError(f"sample_fused: out[{k!r}] must be a contiguous f32 tensor of shape {shape} on {self.device}")
+            for k in ("t", "env"):
+                t = out.get(k)
+                if t is not None and (t.dtype != torch.int64 or tuple(t.shape) != (B,) or not t.is_contiguous() or not self._same_device(t)):
+                    raise ValueError(f"sample_fused: out[{k!r}] must be a contiguous int64 vector of length {B} on {self.device}")
+            prep = (out, B, tuple(p(out.get(k)) for k in ("state", "action", "reward", "next_state", "done", "t", "env")),
+                    C.byref(self._view()))
+            if not hasattr(self, "_prepared"):
+                self._prepared = {}
+            if len(self._prepared) > 64:
+                self._prepared.clear()
+            self._prepared[id(out)] = prep
         t_in = env_in = None
         if indices is not None:
             t_in, env_in = (x.to(device=self.device, dtype=torch.int64).contiguous() for x in indices)
             if t_in.shape != (B,) or env_in.shape != (B,):
                 raise ValueError("sample_fused: indices must be two int64 vectors of length batch_size")
         self._draws = getattr(self, "_draws", 0) + (indices is None)
-        N.check(env.lib.gw_replay_sample(env._h, C.byref(self._view()), self.t, B, int(seed) & (2 ** 64 - 1), self._draws,
-                                         p(t_in), p(env_in), p(out["state"]), p(out["action"]), p(out["reward"]),
-                                         p(out["next_state"]), p(out["done"]), p(out.get("t")), p(out.get("env")),
-                                         env._stream()), env._h, "gw_replay_sample")
+        N.check(env.lib.gw_replay_sample(env._h, prep[3], self.t, B, int(seed) & (2 ** 64 - 1), self._draws,
+                                         p(t_in), p(env_in), *prep[2], env._stream()), env._h, "gw_replay_sample")
         return out
 
     # ---- sampling (uniform over the stored transitions, like random.sample over the deque)

@@ -118,3 +118,31 @@ def test_segmented_graph_update_on_one_rank(tmp_path):
             assert all(lo <= p.grad.data_ptr() < hi for p in net.parameters())
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_parallel_agent_branches_equal_sequential_graph():
+    """One-GPU update graph with the agents' passes as parallel branches (forked streams during capture) against the
+    same graph recorded sequentially: same initial weights, same batches, same random stream -> the same weights."""
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(1)
+    batches = [{"state": torch.randn(128, 2, 160, device=dev, generator=g), "next_state": torch.randn(128, 2, 160, device=dev, generator=g),
+                "action": torch.rand(128, 2, 9, device=dev, generator=g), "reward": torch.randn(128, 2, device=dev, generator=g),
+                "done": (torch.rand(128, 2, device=dev, generator=g) < 0.1).float()} for _ in range(4)]
+    results = []
+    for parallel in (False, True):
+        ag = maddpg.BatchedMADDPG(2, 160, 9, device=dev, seed=5)
+        ag.parallel_agents = parallel
+        torch.manual_seed(11)
+        torch.cuda.manual_seed(11)
+        losses = [ag.learn(batches[i % 4]) for i in range(12)]
+        assert ag._graph is not None                       # three eager updates, then the captured graph
+        assert len(ag._side_streams) == (1 if parallel else 0)
+        torch.cuda.synchronize()
+        results.append(([p.detach().clone() for p in ag.parameters()] +
+                        [p.detach().clone() for net in ag.actor_targets + ag.critic_targets for p in net.parameters()],
+                        torch.stack([l.critic_loss for l in losses])))
+    (p_seq, l_seq), (p_par, l_par) = results
+    assert torch.allclose(l_seq, l_par, rtol=1e-5, atol=1e-6)
+    worst = max(float((a - b).abs().max()) for a, b in zip(p_seq, p_par))
+    assert worst <= 1e-6, worst
