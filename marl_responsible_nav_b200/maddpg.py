@@ -166,7 +166,7 @@ class BatchedMADDPG:
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            out = self._learn(static, parallel=self.parallel_agents)
+            out = self._learn(static, parallel=True)       # branches unless parallel_agents is off
         self._graph = (g, static, out, {k: tuple(batch[k].shape) for k in keys})
         g.replay()                                         # capture only records: this is the update for `batch`
         return LearnStats(out.actor_loss.clone(), out.critic_loss.clone())
@@ -183,9 +183,10 @@ class BatchedMADDPG:
     # ---- several ranks: the same update cut into CUDA graphs at the gradient all-reduces
     def _learn_segmented(self, batch: Dict[str, torch.Tensor]) -> LearnStats:
         """Data-parallel update.  Capturing the NCCL all-reduces inside one graph hung (2 ranks, torch 2.11), so the update
-        is cut where gradients are exchanged: per agent  [critic forward/backward] AR [critic step, actor
-        forward/backward] AR [actor step]  -- 2n+1 graphs (neighbouring pieces share one) and 2n eager all-reduces, each
-        on ONE flat gradient buffer per network (the parameters' .grad are views into it: no cat / split kernels)."""
+        is cut where gradients are exchanged:  [critics forward/backward] AR [critic steps, actors forward/backward] AR
+        [actor steps, soft update]  -- three graphs with the agents as parallel branches and two eager all-reduces, each
+        on ONE flat gradient buffer (all critics / all actors; the parameters' .grad are views into it: no cat / split
+        kernels).  (First version: per agent, five graphs and four all-reduces, 0.98 ms per update on two ranks.)"""
         keys = ("state", "action", "reward", "next_state", "done")
         seg = self._segments
         if seg is not None and not all(tuple(batch[k].shape) == seg["shapes"][k] for k in keys):
@@ -209,38 +210,66 @@ class BatchedMADDPG:
                 flat.div_(world)
         return LearnStats(seg["a_loss"].clone(), seg["c_loss"].clone())
 
-    def _flat_grads(self, net: nn.Module) -> torch.Tensor:
-        """One flat gradient buffer for `net`; every parameter's .grad becomes a view into it (kept from then on)."""
-        ps = list(net.parameters())
-        flat = torch.zeros(sum(p.numel() for p in ps), dtype=ps[0].dtype, device=ps[0].device)
-        off = 0
-        for p in ps:
-            p.grad = flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
-        return flat
+    def _flat_grads(self, nets: Sequence[nn.Module]):
+        """One flat gradient buffer for all of `nets`; every parameter's .grad becomes a view into it (kept from then
+        on).  Returns (buffer, [the slice of each net])."""
+        ps = [list(net.parameters()) for net in nets]
+        flat = torch.zeros(sum(p.numel() for l in ps for p in l), dtype=ps[0][0].dtype, device=ps[0][0].device)
+        off, parts = 0, []
+        for l in ps:
+            lo = off
+            for p in l:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            parts.append(flat[lo:off])
+        return flat, parts
+
+    def _branches(self, fn):
+        """Record fn(k) for every agent: on forked streams (parallel branches of the graph being captured) or in turn."""
+        if not (self.parallel_agents and self.n > 1 and self.device.type == "cuda"):
+            for k in range(self.n):
+                fn(k)
+            return
+        cur = torch.cuda.current_stream(self.device)
+        while len(self._side_streams) < self.n - 1:
+            self._side_streams.append(torch.cuda.Stream(self.device))
+        side = self._side_streams[:self.n - 1]
+        for st in side:                                     # fork here, before agent 0's work is recorded
+            st.wait_stream(cur)
+        for k in range(self.n):
+            with torch.cuda.stream(cur if k == 0 else side[k - 1]):
+                fn(k)
+        for st in side:                                     # join
+            cur.wait_stream(st)
 
     def _capture_segments(self, static: Dict[str, torch.Tensor], shapes) -> Dict:
+        """Three graphs: [all critics forward / backward] AR [critic steps, all actors forward / backward] AR [actor
+        steps, soft update]; inside each the agents are parallel branches (an agent's update reads nothing another
+        agent's writes, see _learn), and each exchange is ONE all-reduce over the flat gradients of all critics /
+        all actors."""
         gamma, tau, n = self.hp["GAMMA"], self.hp["TAU"], self.n
         s, a, r, s2, done = (static[k] for k in ("state", "action", "reward", "next_state", "done"))
         B = s.shape[0]
-        fa = [self._flat_grads(net) for net in self.actors]
-        fc = [self._flat_grads(net) for net in self.critics]
+        fa_all, fa = self._flat_grads(self.actors)
+        fc_all, fc = self._flat_grads(self.critics)
         a_loss = torch.zeros(n, device=self.device)
         c_loss = torch.zeros(n, device=self.device)
         ctx = {}
 
+        def prologue():
+            ctx["flat_s"], flat_s2 = s.reshape(B, -1), s2.reshape(B, -1)
+            with torch.no_grad():
+                a2 = torch.stack([self.actor_targets[j](s2[:, j]) for j in range(n)], dim=1)
+                ctx["crit_in2"] = torch.cat([flat_s2, a2.reshape(B, -1)], dim=1)
+                ctx["crit_in"] = torch.cat([ctx["flat_s"], a.reshape(B, -1)], dim=1)
+            fc_all.zero_()
+
         def critic_pass(k):                                # [critic forward / backward]
-            if k == 0:
-                ctx["flat_s"], flat_s2 = s.reshape(B, -1), s2.reshape(B, -1)
-                with torch.no_grad():
-                    a2 = torch.stack([self.actor_targets[j](s2[:, j]) for j in range(n)], dim=1)
-                    ctx["crit_in2"] = torch.cat([flat_s2, a2.reshape(B, -1)], dim=1)
             with torch.no_grad():
                 q2 = self.critic_targets[k](ctx["crit_in2"]).squeeze(-1)
                 target = r[:, k] + gamma * (1.0 - done[:, k]) * q2
-            q = self.critics[k](torch.cat([ctx["flat_s"], a.reshape(B, -1)], dim=1)).squeeze(-1)
+            q = self.critics[k](ctx["crit_in"]).squeeze(-1)
             loss = F.mse_loss(q, target)
-            fc[k].zero_()
             loss.backward()
             c_loss[k] = loss.detach()
 
@@ -249,7 +278,6 @@ class BatchedMADDPG:
             a_new = a.clone()
             a_new[:, k] = self.actors[k](s[:, k])
             loss = -self.critics[k](torch.cat([ctx["flat_s"], a_new.reshape(B, -1)], dim=1)).mean()
-            fa[k].zero_()
             loss.backward()                                # also reaches the critic's gradients: zeroed before their next use
             a_loss[k] = loss.detach()
 
@@ -259,12 +287,11 @@ class BatchedMADDPG:
                 dst = [p for net in self.actor_targets + self.critic_targets for p in net.parameters()]
                 torch._foreach_lerp_(dst, src, tau)
 
-        pieces = []                                        # (functions run in this graph, buffer to all-reduce after it)
-        for k in range(n):
-            head = [lambda k=k: self.actor_opt[k - 1].step()] if k > 0 else []
-            pieces.append((head + [lambda k=k: critic_pass(k)], fc[k]))
-            pieces.append(([lambda k=k: actor_pass(k)], fa[k]))
-        pieces.append(([lambda: self.actor_opt[n - 1].step(), finish], None))
+        pieces = [                                         # (functions run in this graph, buffer to all-reduce after it)
+            ([prologue, lambda: self._branches(critic_pass)], fc_all),
+            ([fa_all.zero_, lambda: self._branches(actor_pass)], fa_all),
+            ([lambda: self._branches(lambda k: self.actor_opt[k].step()), finish], None),
+        ]
         torch.cuda.synchronize(self.device)
         graphs, pool = [], None
         for fns, _ in pieces:
@@ -315,18 +342,8 @@ class BatchedMADDPG:
             self.actor_opt[k].step()
             a_losses[k], c_losses[k] = a_loss.detach(), c_loss.detach()
 
-        if parallel and self.n > 1 and self.device.type == "cuda":
-            cur = torch.cuda.current_stream(self.device)
-            while len(self._side_streams) < self.n - 1:
-                self._side_streams.append(torch.cuda.Stream(self.device))
-            side = self._side_streams[:self.n - 1]
-            for st in side:                                 # fork after the shared prologue, before agent 0's work is recorded
-                st.wait_stream(cur)
-            for k in range(self.n):
-                with torch.cuda.stream(cur if k == 0 else side[k - 1]):
-                    agent_pass(k)
-            for st in side:                                 # join
-                cur.wait_stream(st)
+        if parallel:
+            self._branches(agent_pass)
         else:
             for k in range(self.n):
                 agent_pass(k)
