@@ -155,7 +155,9 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "agent-steps/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32 cells + f64 FeAR", "data": "synthetic",
-        "config": {"workload": workload_name(a), "sample": f"{sample_envs} of {a.envs} envs per step, {a.steps} steps",
+        "config": {"workload": workload_name(a), "envs_per_gpu": a.envs, "global_envs": a.gpus * a.envs,
+                   "parallelism": "host threads (one CPU arm per run, rank 0)",
+                   "sample": f"{sample_envs} of {a.envs} envs per step, {a.steps} steps",
                    "note": "reference is pure Python (cannot travel to the GPU box): this is its C restatement "
                            "(oracle/gw_oracle.c, pinned to reference-recorded golden vectors), all host threads"},
         "cpu_baseline": {"value": r["value"], "unit": "agent-steps/s", "cores": r["cores"], "kind": "port",

@@ -38,6 +38,7 @@ class ReplayRing:
         self.ended = torch.zeros((T, E), dtype=torch.uint8, device=dev)
         self.info = torch.zeros((T, E), dtype=torch.int32, device=dev)
         self.t = 0                                              # number of transitions recorded per env so far
+        self._draws, self._prepared, self._c_view = 0, {}, None  # sample_fused: draw counter, marshalled argument sets, ring view
         # per-slot views, built once: slicing nine tensors per env step costs more host time than the step kernel takes
         self._obs_v, self._final_v, self._action_v = list(self.obs.unbind(0)), list(self.final_obs.unbind(0)), list(self.action.unbind(0))
         self._slot_v = [SimpleNamespace(reward=self.reward[s], shaped_reward=self.shaped_reward[s], fear=self.fear[s],
@@ -72,7 +73,7 @@ class ReplayRing:
     def _view(self):
         import ctypes as C
         from . import _native as N
-        v = getattr(self, "_c_view", None)
+        v = self._c_view
         if v is None:
             v = N.GwReplayView()
             v.struct_size = C.sizeof(N.GwReplayView)
@@ -86,6 +87,8 @@ class ReplayRing:
     def _same_device(self, t: torch.Tensor) -> bool:
         return t.device.type == self.device.type and (self.device.index is None or t.device.index is None
                                                        or t.device.index == self.device.index)
+
+    _FIELDS = ("state", "action", "reward", "next_state", "done")
 
     def new_batch(self, batch_size: int) -> Dict[str, torch.Tensor]:
         """f32 batch tensors of the shapes `sample_fused` fills (what BatchedMADDPG.learn consumes)."""
@@ -110,8 +113,9 @@ class ReplayRing:
         B = int(batch_size)
         out = self.new_batch(B) if out is None else out
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
-        prep = self._prepared.get(id(out)) if hasattr(self, "_prepared") else None
-        if prep is None or prep[0] is not out or prep[1] != B:      # checked once per set of batch tensors
+        prep = self._prepared.get(id(out))
+        if (prep is None or prep[0] is not out or prep[1] != B
+                or any(out[k].data_ptr() != q for k, q in zip(self._FIELDS, prep[4]))):   # checked once per set of batch tensors
             for k, shape in (("state", (B, self.L, self.obs_len)), ("action", (B, self.L, self.action_dim)), ("reward", (B, self.L)),
                              ("next_state", (B, self.L, self.obs_len)), ("done", (B, self.L))):
                 t = out[k]
@@ -122,9 +126,7 @@ class ReplayRing:
                 if t is not None and (t.dtype != torch.int64 or tuple(t.shape) != (B,) or not t.is_contiguous() or not self._same_device(t)):
                     raise ValueError(f"sample_fused: out[{k!r}] must be a contiguous int64 vector of length {B} on {self.device}")
             prep = (out, B, tuple(p(out.get(k)) for k in ("state", "action", "reward", "next_state", "done", "t", "env")),
-                    C.byref(self._view()))
-            if not hasattr(self, "_prepared"):
-                self._prepared = {}
+                    C.byref(self._view()), tuple(out[k].data_ptr() for k in self._FIELDS))
             if len(self._prepared) > 64:
                 self._prepared.clear()
             self._prepared[id(out)] = prep
@@ -133,7 +135,7 @@ class ReplayRing:
             t_in, env_in = (x.to(device=self.device, dtype=torch.int64).contiguous() for x in indices)
             if t_in.shape != (B,) or env_in.shape != (B,):
                 raise ValueError("sample_fused: indices must be two int64 vectors of length batch_size")
-        self._draws = getattr(self, "_draws", 0) + (indices is None)
+        self._draws += indices is None
         N.check(env.lib.gw_replay_sample(env._h, prep[3], self.t, B, int(seed) & (2 ** 64 - 1), self._draws,
                                          p(t_in), p(env_in), *prep[2], env._stream()), env._h, "gw_replay_sample")
         return out
