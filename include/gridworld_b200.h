@@ -247,6 +247,17 @@ int gw_replay_sample(gw_handle* h, const gw_replay_view* ring, int64_t t_now, in
                      uint64_t draw, const int64_t* t_in, const int64_t* env_in, float* state, float* action,
                      float* reward, float* next_state, float* done, int64_t* t_out, int64_t* env_out, void* stream);
 
+/* ---- MADDPG update, element-wise part: LayerNorm + ReLU of the reference's networks -----------------
+ * (Linear -> LayerNorm -> ReLU, hidden 128: configs/mlp.yaml:3) as one kernel forward and one backward; the
+ * GEMMs of the update stay with cuBLAS.  width must be 128; all pointers device, fp32, 16-byte aligned rows.
+ * forward: y = relu((x - mean) * rstd * gamma + beta), mean / rstd [rows] kept for the backward.
+ * backward: dx [rows, 128], dgamma / dbeta [128] (overwritten, not accumulated). */
+int gw_ln_relu_forward(gw_handle* h, int64_t rows, int32_t width, const float* x, const float* gamma, const float* beta,
+                       float eps, float* y, float* mean, float* rstd, void* stream);
+int gw_ln_relu_backward(gw_handle* h, int64_t rows, int32_t width, const float* dy, const float* x, const float* mean,
+                        const float* rstd, const float* gamma, const float* beta, float* dx, float* dgamma, float* dbeta,
+                        void* stream);
+
 /* ---- actor forward (K5): AgileRL `MADDPG.get_action` as called at maddpg/agent.py:109-113 -----------------------
  * One actor per learner: Linear(H*W,128)-LayerNorm-ReLU-Linear(128,128)-LayerNorm-ReLU-Linear(128,9)-GumbelSoftmax
  * (shapes from the reference's checkpoints), Gaussian exploration noise, clip to [0,1], action mask,

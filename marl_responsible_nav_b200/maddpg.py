@@ -67,6 +67,70 @@ class GumbelSoftmax(nn.Module):
         return F.softmax(logits + g, dim=-1)
 
 
+class TrainOps:
+    """The library's trainer-side kernels (csrc/gw_train_ops.cu) bound to one env handle (device, stream, error string)."""
+    WIDTH = 128
+
+    def __init__(self, env):
+        import ctypes as C
+        from . import _native as N
+        self.C, self.N, self.env, self.lib = C, N, env, env.lib
+
+    def ln_relu_forward(self, x, gamma, beta, eps, y, mean, rstd):
+        p, env = self.C.c_void_p, self.env
+        self.N.check(self.lib.gw_ln_relu_forward(env._h, x.shape[0], x.shape[1], p(x.data_ptr()), p(gamma.data_ptr()),
+                                                 p(beta.data_ptr()), float(eps), p(y.data_ptr()), p(mean.data_ptr()),
+                                                 p(rstd.data_ptr()), env._stream()), env._h, "gw_ln_relu_forward")
+
+    def ln_relu_backward(self, dy, x, mean, rstd, gamma, beta, dx, dgamma, dbeta):
+        p, env = self.C.c_void_p, self.env
+        self.N.check(self.lib.gw_ln_relu_backward(env._h, x.shape[0], x.shape[1], p(dy.data_ptr()), p(x.data_ptr()),
+                                                  p(mean.data_ptr()), p(rstd.data_ptr()), p(gamma.data_ptr()),
+                                                  p(beta.data_ptr()), p(dx.data_ptr()), p(dgamma.data_ptr()),
+                                                  p(dbeta.data_ptr()), env._stream()), env._h, "gw_ln_relu_backward")
+
+
+class _LayerNormReLU(torch.autograd.Function):
+    """relu(layer_norm(x)) over the last dimension (128): one library kernel forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, ops):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        mean = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        ops.ln_relu_forward(x, gamma, beta, eps, y, mean, rstd)
+        ctx.save_for_backward(x, gamma, beta, mean, rstd)
+        ctx.ops = ops
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx, dgamma, dbeta = torch.empty_like(x), torch.empty_like(gamma), torch.empty_like(beta)
+        ctx.ops.ln_relu_backward(dy, x, mean, rstd, gamma, beta, dx, dgamma, dbeta)
+        return dx, dgamma, dbeta, None, None
+
+
+def forward_mlp(net: nn.Sequential, x: torch.Tensor, ops: Optional[TrainOps]) -> torch.Tensor:
+    """net(x), with every LayerNorm(128) -> ReLU pair run by the fused kernels when `ops` is given (CUDA, fp32).
+    The modules and their parameter names stay what the checkpoints and the actor kernel expect."""
+    if ops is None or not x.is_cuda:
+        return net(x)
+    mods, i = list(net), 0
+    while i < len(mods):
+        m = mods[i]
+        if (isinstance(m, nn.LayerNorm) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU) and m.elementwise_affine
+                and tuple(m.normalized_shape) == (TrainOps.WIDTH,) and x.dtype == torch.float32 and x.dim() == 2):
+            x = _LayerNormReLU.apply(x, m.weight, m.bias, m.eps, ops)
+            i += 2
+        else:
+            x = m(x)
+            i += 1
+    return x
+
+
 def mlp(in_dim: int, hidden: Sequence[int], out_dim: int, out_act: Optional[nn.Module]) -> nn.Sequential:
     layers: List[nn.Module] = []
     d = in_dim
@@ -112,8 +176,18 @@ class BatchedMADDPG:
         self._segments = None                              # several ranks: the update as a chain of graphs (see _learn_segmented)
         self._eager_learns = 0
         self.parallel_agents = True                        # one-GPU graph: the agents' updates are parallel branches (see _learn)
-        self._side_streams: List[torch.cuda.Stream] = []
+        self._side_streams: Dict[object, List[torch.cuda.Stream]] = {}
+        self.ops: Optional[TrainOps] = None                # fused LayerNorm+ReLU kernels of the library (attach_ops)
         self.force_segmented = False                       # tests: take the multi-rank path in a one-rank process group
+
+    def attach_ops(self, env):
+        """Run the update's LayerNorm + ReLU pairs through the library's kernels (`env` provides handle and stream).
+        Invalidates captured graphs."""
+        self.ops = TrainOps(env) if env is not None else None
+        self._graph, self._segments, self._eager_learns = None, None, 0
+
+    def _fwd(self, net: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+        return forward_mlp(net, x, self.ops)
 
     def parameters(self):
         for net in self.actors + self.critics:
@@ -224,30 +298,37 @@ class BatchedMADDPG:
             parts.append(flat[lo:off])
         return flat, parts
 
-    def _branches(self, fn):
-        """Record fn(k) for every agent: on forked streams (parallel branches of the graph being captured) or in turn."""
-        if not (self.parallel_agents and self.n > 1 and self.device.type == "cuda"):
-            for k in range(self.n):
-                fn(k)
+    def _fork_join(self, fns, key="agents", enabled: bool = True):
+        """Record every fn of `fns`: the first on the current stream, the others on forked streams (parallel branches of
+        the graph being captured), joined before returning; in turn when branching is off.  `key` names the set of side
+        streams, so that an inner fork inside one agent's branch does not share streams with another agent's."""
+        if not (enabled and self.parallel_agents and len(fns) > 1 and self.device.type == "cuda"):
+            for fn in fns:
+                fn()
             return
         cur = torch.cuda.current_stream(self.device)
-        while len(self._side_streams) < self.n - 1:
-            self._side_streams.append(torch.cuda.Stream(self.device))
-        side = self._side_streams[:self.n - 1]
-        for st in side:                                     # fork here, before agent 0's work is recorded
+        side = self._side_streams.setdefault(key, [])
+        while len(side) < len(fns) - 1:
+            side.append(torch.cuda.Stream(self.device))
+        side = side[:len(fns) - 1]
+        for st in side:                                     # fork here, before the first branch's work is recorded
             st.wait_stream(cur)
-        for k in range(self.n):
-            with torch.cuda.stream(cur if k == 0 else side[k - 1]):
-                fn(k)
+        for i, fn in enumerate(fns):
+            with torch.cuda.stream(cur if i == 0 else side[i - 1]):
+                fn()
         for st in side:                                     # join
             cur.wait_stream(st)
+
+    def _branches(self, fn, enabled: bool = True):
+        """fn(k) for every agent, as parallel branches."""
+        self._fork_join([lambda k=k: fn(k) for k in range(self.n)], "agents", enabled)
 
     def _capture_segments(self, static: Dict[str, torch.Tensor], shapes) -> Dict:
         """Three graphs: [all critics forward / backward] AR [critic steps, all actors forward / backward] AR [actor
         steps, soft update]; inside each the agents are parallel branches (an agent's update reads nothing another
         agent's writes, see _learn), and each exchange is ONE all-reduce over the flat gradients of all critics /
         all actors."""
-        gamma, tau, n = self.hp["GAMMA"], self.hp["TAU"], self.n
+        tau, n = self.hp["TAU"], self.n
         s, a, r, s2, done = (static[k] for k in ("state", "action", "reward", "next_state", "done"))
         B = s.shape[0]
         fa_all, fa = self._flat_grads(self.actors)
@@ -259,25 +340,25 @@ class BatchedMADDPG:
         def prologue():
             ctx["flat_s"], flat_s2 = s.reshape(B, -1), s2.reshape(B, -1)
             with torch.no_grad():
-                a2 = torch.stack([self.actor_targets[j](s2[:, j]) for j in range(n)], dim=1)
-                ctx["crit_in2"] = torch.cat([flat_s2, a2.reshape(B, -1)], dim=1)
+                a2 = [None] * n
+                self._branches(lambda j: a2.__setitem__(j, self._fwd(self.actor_targets[j], s2[:, j])))
+                ctx["crit_in2"] = torch.cat([flat_s2, torch.stack(a2, dim=1).reshape(B, -1)], dim=1)
                 ctx["crit_in"] = torch.cat([ctx["flat_s"], a.reshape(B, -1)], dim=1)
             fc_all.zero_()
 
-        def critic_pass(k):                                # [critic forward / backward]
-            with torch.no_grad():
-                q2 = self.critic_targets[k](ctx["crit_in2"]).squeeze(-1)
-                target = r[:, k] + gamma * (1.0 - done[:, k]) * q2
-            q = self.critics[k](ctx["crit_in"]).squeeze(-1)
-            loss = F.mse_loss(q, target)
+        def critic_pass(k):                                # [critic forward / backward]; the target is an inner branch
+            box = {}
+            self._fork_join([lambda: box.__setitem__("q", self._fwd(self.critics[k], ctx["crit_in"]).squeeze(-1)),
+                             lambda: box.__setitem__("target", self._td_target(k, ctx["crit_in2"], r, done))], ("inner", k))
+            loss = F.mse_loss(box["q"], box["target"])
             loss.backward()
             c_loss[k] = loss.detach()
 
         def actor_pass(k):                                 # [critic step, actor forward / backward]
             self.critic_opt[k].step()
             a_new = a.clone()
-            a_new[:, k] = self.actors[k](s[:, k])
-            loss = -self.critics[k](torch.cat([ctx["flat_s"], a_new.reshape(B, -1)], dim=1)).mean()
+            a_new[:, k] = self._fwd(self.actors[k], s[:, k])
+            loss = -self._fwd(self.critics[k], torch.cat([ctx["flat_s"], a_new.reshape(B, -1)], dim=1)).mean()
             loss.backward()                                # also reaches the critic's gradients: zeroed before their next use
             a_loss[k] = loss.detach()
 
@@ -311,47 +392,56 @@ class BatchedMADDPG:
         reads -- own critic, own actor, own optimisers; the other agents' actions come from the batch -- so the agents'
         passes are recorded on forked streams and become parallel branches of the graph.  Same kernels, same operands,
         same results as the sequential order; the ~120 launch-latency-sized kernels per agent overlap."""
-        gamma, tau = self.hp["GAMMA"], self.hp["TAU"]
+        tau = self.hp["TAU"]
         s, a, r = batch["state"].float(), batch["action"].float(), batch["reward"].float()
         s2, done = batch["next_state"].float(), batch["done"].float()
         B = s.shape[0]
         flat_s, flat_s2 = s.reshape(B, -1), s2.reshape(B, -1)
         with torch.no_grad():
-            a2 = torch.stack([self.actor_targets[k](s2[:, k]) for k in range(self.n)], dim=1)
-            crit_in2 = torch.cat([flat_s2, a2.reshape(B, -1)], dim=1)
+            a2 = [None] * self.n
+            self._branches(lambda k: a2.__setitem__(k, self._fwd(self.actor_targets[k], s2[:, k])), parallel)
+            crit_in2 = torch.cat([flat_s2, torch.stack(a2, dim=1).reshape(B, -1)], dim=1)
             crit_in = torch.cat([flat_s, a.reshape(B, -1)], dim=1)
         a_losses: List[Optional[torch.Tensor]] = [None] * self.n
         c_losses: List[Optional[torch.Tensor]] = [None] * self.n
 
         def agent_pass(k: int):
-            with torch.no_grad():
-                q2 = self.critic_targets[k](crit_in2).squeeze(-1)
-                target = r[:, k] + gamma * (1.0 - done[:, k]) * q2
-            q = self.critics[k](crit_in).squeeze(-1)
-            c_loss = F.mse_loss(q, target)
-            self.critic_opt[k].zero_grad(set_to_none=True)
-            c_loss.backward()
-            self._allreduce_grads(self.critics[k])
-            self.critic_opt[k].step()
+            box = {}
+
+            def critic_update():                           # the TD target is an inner branch next to the critic's forward
+                self._fork_join([lambda: box.__setitem__("q", self._fwd(self.critics[k], crit_in).squeeze(-1)),
+                                 lambda: box.__setitem__("target", self._td_target(k, crit_in2, r, done))], ("inner", k), parallel)
+                c_loss = F.mse_loss(box["q"], box["target"])
+                self.critic_opt[k].zero_grad(set_to_none=True)
+                c_loss.backward()
+                self._allreduce_grads(self.critics[k])
+                self.critic_opt[k].step()
+                box["c_loss"] = c_loss.detach()
+
+            # the actor's forward needs nothing of the critic's update: a third branch (its backward follows it there)
+            self._fork_join([critic_update, lambda: box.__setitem__("a_k", self._fwd(self.actors[k], s[:, k]))], ("actor", k), parallel)
+            c_loss = box["c_loss"]
             a_new = a.clone()
-            a_new[:, k] = self.actors[k](s[:, k])
-            a_loss = -self.critics[k](torch.cat([flat_s, a_new.reshape(B, -1)], dim=1)).mean()
+            a_new[:, k] = box["a_k"]
+            a_loss = -self._fwd(self.critics[k], torch.cat([flat_s, a_new.reshape(B, -1)], dim=1)).mean()
             self.actor_opt[k].zero_grad(set_to_none=True)
             a_loss.backward()
             self._allreduce_grads(self.actors[k])
             self.actor_opt[k].step()
             a_losses[k], c_losses[k] = a_loss.detach(), c_loss.detach()
 
-        if parallel:
-            self._branches(agent_pass)
-        else:
-            for k in range(self.n):
-                agent_pass(k)
+        self._branches(agent_pass, parallel)
         with torch.no_grad():                              # soft update, TAU (one multi-tensor kernel, not 40 small ones)
             src = [p for net in self.actors + self.critics for p in net.parameters()]
             dst = [p for net in self.actor_targets + self.critic_targets for p in net.parameters()]
             torch._foreach_lerp_(dst, src, tau)
         return LearnStats(torch.stack(a_losses), torch.stack(c_losses))
+
+    @torch.no_grad()
+    def _td_target(self, k: int, crit_in2: torch.Tensor, r: torch.Tensor, done: torch.Tensor) -> torch.Tensor:
+        """r + GAMMA (1 - done) Q_target(next state, target actors' actions) for agent k."""
+        q2 = self._fwd(self.critic_targets[k], crit_in2).squeeze(-1)
+        return r[:, k] + self.hp["GAMMA"] * (1.0 - done[:, k]) * q2
 
     @staticmethod
     def _allreduce_grads(net: nn.Module):
@@ -373,13 +463,15 @@ class BatchedTrainer:
     """MADDPGAgent.train (maddpg/agent.py:77-252) for E environments at once, everything on the device."""
 
     def __init__(self, env, agent: Optional[BatchedMADDPG] = None, hp: Optional[Dict] = None,
-                 updates_per_learn: int = 1, seed: int = 0, fused_actor: bool = True, fused_sampler: bool = True):
+                 updates_per_learn: int = 1, seed: int = 0, fused_actor: bool = True, fused_sampler: bool = True, fused_ops: bool = True):
         from .replay import ReplayRing
         self.env = env
         self.hp = dict(DEFAULT_HP if hp is None else hp)
         self.agent = agent or BatchedMADDPG(env.n_learners, env.obs_len, 9, hp=self.hp, device=env.device, seed=seed)
         self.ring = ReplayRing(env.num_envs, env.n_learners, env.obs_len, self.hp["MEMORY_SIZE"], 9,
                                device=env.device, obs_dtype=env.obs_dtype)
+        if fused_ops and env.device.type == "cuda" and self.agent.ops is None:
+            self.agent.attach_ops(env)
         self.updates_per_learn = int(updates_per_learn)
         self.gen = torch.Generator(device=env.device).manual_seed(seed + 1)
         self.fused_sampler = bool(fused_sampler) and env.device.type == "cuda"      # csrc/gw_replay.cu

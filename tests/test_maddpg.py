@@ -137,7 +137,7 @@ def test_parallel_agent_branches_equal_sequential_graph():
         torch.cuda.manual_seed(11)
         losses = [ag.learn(batches[i % 4]) for i in range(12)]
         assert ag._graph is not None                       # three eager updates, then the captured graph
-        assert len(ag._side_streams) == (1 if parallel else 0)
+        assert sorted(map(str, ag._side_streams)) == (sorted(map(str, ["agents", ("inner", 0), ("inner", 1), ("actor", 0), ("actor", 1)])) if parallel else [])
         torch.cuda.synchronize()
         results.append(([p.detach().clone() for p in ag.parameters()] +
                         [p.detach().clone() for net in ag.actor_targets + ag.critic_targets for p in net.parameters()],
@@ -146,3 +146,61 @@ def test_parallel_agent_branches_equal_sequential_graph():
     assert torch.allclose(l_seq, l_par, rtol=1e-5, atol=1e-6)
     worst = max(float((a - b).abs().max()) for a, b in zip(p_seq, p_par))
     assert worst <= 1e-6, worst
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows", [128, 1, 77, 300])
+def test_fused_layernorm_relu_matches_torch(rows):
+    """gw_ln_relu_forward / _backward (one kernel each) against torch.nn.LayerNorm + ReLU with autograd, fp32: rows = 128
+    is the update's batch (one CTA writes dgamma / dbeta), 300 takes the several-CTA path (atomic column sums)."""
+    from marl_responsible_nav_b200 import BatchedGridWorld
+    dev = torch.device("cuda", 0)
+    env = BatchedGridWorld("Level 3", num_envs=32, fear=False, seed=1)
+    ops = maddpg.TrainOps(env)
+    g = torch.Generator(device=dev).manual_seed(rows)
+    ln = torch.nn.LayerNorm(128).to(dev)
+    with torch.no_grad():
+        ln.weight.copy_(torch.randn(128, device=dev, generator=g))
+        ln.bias.copy_(0.3 * torch.randn(128, device=dev, generator=g))
+    x = (3.0 * torch.randn(rows, 128, device=dev, generator=g) + 1.5).requires_grad_(True)
+    up = torch.randn(rows, 128, device=dev, generator=g)
+    ref = torch.relu(ln(x))
+    ref.backward(up)
+    want = (ref.detach().clone(), x.grad.clone(), ln.weight.grad.clone(), ln.bias.grad.clone())
+    x.grad = None
+    ln.zero_grad(set_to_none=True)
+    got = maddpg.forward_mlp(torch.nn.Sequential(ln, torch.nn.ReLU()), x, ops)
+    got.backward(up)
+    env.sync()
+    assert torch.allclose(got, want[0], rtol=1e-5, atol=1e-5)
+    assert torch.equal(got == 0, want[0] == 0) or float(((got == 0) != (want[0] == 0)).float().mean()) < 1e-4   # same ReLU mask
+    assert torch.allclose(x.grad, want[1], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(ln.weight.grad, want[2], rtol=1e-4, atol=1e-4)
+    assert torch.allclose(ln.bias.grad, want[3], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_update_with_fused_ops_tracks_the_torch_modules():
+    """The same update (eager) with and without the fused LayerNorm+ReLU kernels, from the same weights and noise:
+    parameters stay together to fp32 rounding over several updates."""
+    from marl_responsible_nav_b200 import BatchedGridWorld
+    dev = torch.device("cuda", 0)
+    env = BatchedGridWorld("Level 3", num_envs=32, fear=False, seed=1)
+    g = torch.Generator(device=dev).manual_seed(2)
+    batch = {"state": torch.randn(128, 2, 160, device=dev, generator=g), "next_state": torch.randn(128, 2, 160, device=dev, generator=g),
+             "action": torch.rand(128, 2, 9, device=dev, generator=g), "reward": torch.randn(128, 2, device=dev, generator=g),
+             "done": torch.zeros(128, 2, device=dev)}
+    res = []
+    for fused in (False, True):
+        ag = maddpg.BatchedMADDPG(2, 160, 9, device=dev, seed=5)
+        if fused:
+            ag.attach_ops(env)
+        torch.manual_seed(3)
+        torch.cuda.manual_seed(3)
+        for _ in range(5):
+            st = ag.learn(batch, graph=False)
+        torch.cuda.synchronize()
+        res.append(([p.detach().clone() for p in ag.parameters()], st.critic_loss.clone()))
+    worst = max(float((a - b).abs().max()) for a, b in zip(res[0][0], res[1][0]))
+    assert worst < 2e-4, worst                              # Adam's normalised steps amplify rounding differences of tiny gradients
+    assert torch.allclose(res[0][1], res[1][1], rtol=1e-3)
