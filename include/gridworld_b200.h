@@ -258,6 +258,13 @@ int gw_ln_relu_backward(gw_handle* h, int64_t rows, int32_t width, const float* 
                         const float* rstd, const float* gamma, const float* beta, float* dx, float* dgamma, float* dbeta,
                         void* stream);
 
+/* Backward of y = x W^T + b (torch.nn.Linear; x [batch, in] with row stride x_row_stride, W [out, in], dy [batch, out]
+ * contiguous) in one launch: dW [out, in] = dy^T x, db [out] = column sums of dy, dx [batch, in] = dy W (dx nullable:
+ * the input needs no gradient).  fp32 FMA, outputs overwritten. */
+int gw_linear_backward(gw_handle* h, int32_t batch, int32_t in_features, int32_t out_features, const float* dy,
+                       const float* x, int32_t x_row_stride, const float* w, float* dw, float* db, float* dx,
+                       void* stream);
+
 /* ---- actor forward (K5): AgileRL `MADDPG.get_action` as called at maddpg/agent.py:109-113 -----------------------
  * One actor per learner: Linear(H*W,128)-LayerNorm-ReLU-Linear(128,128)-LayerNorm-ReLU-Linear(128,9)-GumbelSoftmax
  * (shapes from the reference's checkpoints), Gaussian exploration noise, clip to [0,1], action mask,

@@ -13,7 +13,7 @@ GW_OBS_F32, GW_OBS_BF16 = 0, 1
 EXPORTS = ["gw_abi_version", "gw_build_info", "gw_default_config", "gw_create", "gw_destroy", "gw_last_error",
            "gw_reset", "gw_step", "gw_step_host", "gw_host_call_prepare", "gw_host_call_run", "gw_host_call_reset", "gw_server_stop", "gw_server_info", "gw_sync", "gw_state_bytes", "gw_get_state", "gw_set_state", "gw_get_stats",
            "gw_reset_stats", "gw_launch_count", "gw_update_world", "gw_fear_one_actor", "gw_fear_matrix", "gw_feal", "gw_actor_create", "gw_actor_update", "gw_actor_update_device",
-           "gw_actor_destroy", "gw_actor_forward", "gw_replay_sample", "gw_ln_relu_forward", "gw_ln_relu_backward"]
+           "gw_actor_destroy", "gw_actor_forward", "gw_replay_sample", "gw_ln_relu_forward", "gw_ln_relu_backward", "gw_linear_backward"]
 
 
 class GwActorWeights(C.Structure):
@@ -106,6 +106,7 @@ def load():
     lib.gw_replay_sample.argtypes = [vp, C.POINTER(GwReplayView), i64, i64, C.c_uint64, C.c_uint64] + [vp] * 9 + [vp]
     lib.gw_ln_relu_forward.argtypes = [vp, i64, C.c_int32, vp, vp, vp, C.c_float, vp, vp, vp, vp]
     lib.gw_ln_relu_backward.argtypes = [vp, i64, C.c_int32] + [vp] * 9 + [vp]
+    lib.gw_linear_backward.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     if lib.gw_abi_version() != 1:
         raise RuntimeError("libgridworld_b200.so ABI version mismatch")
     _lib = lib

@@ -96,6 +96,71 @@ __global__ void __launch_bounds__(BWD_THREADS) ln_relu_bwd_kernel(const float* _
   }
 }
 
+// ---- Linear backward: dW = dy^T x, db = column sums of dy, dx = dy W in ONE launch (PyTorch: two cuBLAS GEMMs and a
+// reduction kernel, three dependent launches).  At batch 128 and widths <= 338 each product is ~10 MFLOP -- a fraction
+// of a microsecond of fp32 FMA throughput -- so a plain shared-memory tiling is enough: 32x32 output tiles, K in chunks
+// of 32, 256 threads with 2x2 outputs each.  The first n_g1 CTAs own tiles of dW (those of tile column 0 also sum dy's
+// columns for db), the others tiles of dx.
+struct LinBwdArgs {
+  const float* dy; const float* x; const float* w;
+  float* dw; float* db; float* dx;
+  int batch, in, out, ldx;
+  int tiles_n, n_g1;
+};
+
+__global__ void __launch_bounds__(256) linear_bwd_kernel(const LinBwdArgs a) {
+  __shared__ float As[32][33];
+  __shared__ float Bs[32][33];
+  int t = blockIdx.x;
+  const bool g1 = t < a.n_g1;
+  if (!g1) t -= a.n_g1;
+  const int tm = t / a.tiles_n, tn = t - tm * a.tiles_n;
+  const int M = g1 ? a.out : a.batch, N = a.in, K = g1 ? a.batch : a.out;
+  const float* __restrict__ bsrc = g1 ? a.x : a.w;
+  const int ldb = g1 ? a.ldx : a.in;
+  const int m0 = tm * 32, n0 = tn * 32;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc00 = 0.f, acc01 = 0.f, acc10 = 0.f, acc11 = 0.f, colsum = 0.f;
+  const bool sums = g1 && tn == 0 && threadIdx.x < 32;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    for (int i = threadIdx.x; i < 1024; i += 256) {
+      const int hi = i >> 5, lo = i & 31;
+      float v;
+      if (g1) {                                             // A(k, m) = dy[k][m]: rows of dy are contiguous in m
+        v = (k0 + hi < K && m0 + lo < M) ? a.dy[(long long)(k0 + hi) * a.out + m0 + lo] : 0.f;
+        As[hi][lo] = v;
+      } else {                                              // A(k, m) = dy[m][k]: contiguous in k, stored transposed
+        v = (k0 + lo < K && m0 + hi < M) ? a.dy[(long long)(m0 + hi) * a.out + k0 + lo] : 0.f;
+        As[lo][hi] = v;
+      }
+      Bs[hi][lo] = (k0 + hi < K && n0 + lo < N) ? bsrc[(long long)(k0 + hi) * ldb + n0 + lo] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float a0 = As[k][ty], a1 = As[k][ty + 16], b0 = Bs[k][tx], b1 = Bs[k][tx + 16];
+      acc00 = fmaf(a0, b0, acc00); acc01 = fmaf(a0, b1, acc01);
+      acc10 = fmaf(a1, b0, acc10); acc11 = fmaf(a1, b1, acc11);
+    }
+    if (sums) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) colsum += As[k][threadIdx.x];
+    }
+    __syncthreads();
+  }
+  float* __restrict__ c = g1 ? a.dw : a.dx;
+  const int m_a = m0 + ty, m_b = m0 + ty + 16, n_a = n0 + tx, n_b = n0 + tx + 16;
+  if (m_a < M) {
+    if (n_a < N) c[(long long)m_a * N + n_a] = acc00;
+    if (n_b < N) c[(long long)m_a * N + n_b] = acc01;
+  }
+  if (m_b < M) {
+    if (n_a < N) c[(long long)m_b * N + n_a] = acc10;
+    if (n_b < N) c[(long long)m_b * N + n_b] = acc11;
+  }
+  if (sums && m0 + (int)threadIdx.x < M) a.db[m0 + threadIdx.x] = colsum;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
@@ -131,6 +196,24 @@ extern "C" int gw_ln_relu_backward(gw_handle* h, int64_t rows, int32_t width, co
     GW_CUDA(h, cudaMemsetAsync(dbeta, 0, LN_W * sizeof(float), st));
   }
   ln_relu_bwd_kernel<<<grid, BWD_THREADS, 0, st>>>(dy, x, mean, rstd, gamma, beta, dx, dgamma, dbeta, rows);
+  GW_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+extern "C" int gw_linear_backward(gw_handle* h, int32_t batch, int32_t in_features, int32_t out_features, const float* dy,
+                                  const float* x, int32_t x_row_stride, const float* w, float* dw, float* db, float* dx,
+                                  void* stream) {
+  if (h == nullptr) return GW_EINVAL;
+  if (batch < 1 || in_features < 1 || out_features < 1 || x_row_stride < in_features || !dy || !x || !w || !dw || !db)
+    return gw_fail(h, GW_EINVAL, "gw_linear_backward: bad argument");
+  LinBwdArgs a;
+  a.dy = dy; a.x = x; a.w = w; a.dw = dw; a.db = db; a.dx = dx;
+  a.batch = batch; a.in = in_features; a.out = out_features; a.ldx = x_row_stride;
+  a.tiles_n = (in_features + 31) / 32;
+  a.n_g1 = ((out_features + 31) / 32) * a.tiles_n;
+  const int n_g2 = dx != nullptr ? ((batch + 31) / 32) * a.tiles_n : 0;
+  linear_bwd_kernel<<<(unsigned)(a.n_g1 + n_g2), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   GW_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return GW_OK;

@@ -71,10 +71,11 @@ class TrainOps:
     """The library's trainer-side kernels (csrc/gw_train_ops.cu) bound to one env handle (device, stream, error string)."""
     WIDTH = 128
 
-    def __init__(self, env):
+    def __init__(self, env, linear_backward: bool = True):
         import ctypes as C
         from . import _native as N
         self.C, self.N, self.env, self.lib = C, N, env, env.lib
+        self.use_linear_backward = bool(linear_backward)    # forward_mlp: Linear backward through gw_linear_backward
 
     def ln_relu_forward(self, x, gamma, beta, eps, y, mean, rstd):
         p, env = self.C.c_void_p, self.env
@@ -82,12 +83,39 @@ class TrainOps:
                                                  p(beta.data_ptr()), float(eps), p(y.data_ptr()), p(mean.data_ptr()),
                                                  p(rstd.data_ptr()), env._stream()), env._h, "gw_ln_relu_forward")
 
+    def linear_backward(self, dy, x, weight, dw, db, dx):
+        p, env = self.C.c_void_p, self.env
+        self.N.check(self.lib.gw_linear_backward(env._h, x.shape[0], x.shape[1], weight.shape[0], p(dy.data_ptr()),
+                                                 p(x.data_ptr()), x.stride(0), p(weight.data_ptr()), p(dw.data_ptr()),
+                                                 p(db.data_ptr()), p(dx.data_ptr()) if dx is not None else None,
+                                                 env._stream()), env._h, "gw_linear_backward")
+
     def ln_relu_backward(self, dy, x, mean, rstd, gamma, beta, dx, dgamma, dbeta):
         p, env = self.C.c_void_p, self.env
         self.N.check(self.lib.gw_ln_relu_backward(env._h, x.shape[0], x.shape[1], p(dy.data_ptr()), p(x.data_ptr()),
                                                   p(mean.data_ptr()), p(rstd.data_ptr()), p(gamma.data_ptr()),
                                                   p(beta.data_ptr()), p(dx.data_ptr()), p(dgamma.data_ptr()),
                                                   p(dbeta.data_ptr()), env._stream()), env._h, "gw_ln_relu_backward")
+
+
+class _Linear(torch.autograd.Function):
+    """torch.nn.functional.linear whose backward is ONE library kernel (dW, db and dx; PyTorch: two GEMMs + a reduction)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, ops):
+        ctx.save_for_backward(x, weight)
+        ctx.ops = ops
+        return F.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        dw = torch.empty_like(weight)
+        db = torch.empty((weight.shape[0],), dtype=weight.dtype, device=weight.device)
+        dx = torch.empty((x.shape[0], x.shape[1]), dtype=x.dtype, device=x.device) if ctx.needs_input_grad[0] else None
+        ctx.ops.linear_backward(dy, x, weight, dw, db, dx)
+        return dx, dw, db, None
 
 
 class _LayerNormReLU(torch.autograd.Function):
@@ -114,7 +142,8 @@ class _LayerNormReLU(torch.autograd.Function):
 
 
 def forward_mlp(net: nn.Sequential, x: torch.Tensor, ops: Optional[TrainOps]) -> torch.Tensor:
-    """net(x), with every LayerNorm(128) -> ReLU pair run by the fused kernels when `ops` is given (CUDA, fp32).
+    """net(x), with every LayerNorm(128) -> ReLU pair run by the fused kernels and every Linear's backward by the
+    one-launch kernel when `ops` is given (CUDA, fp32).
     The modules and their parameter names stay what the checkpoints and the actor kernel expect."""
     if ops is None or not x.is_cuda:
         return net(x)
@@ -125,6 +154,10 @@ def forward_mlp(net: nn.Sequential, x: torch.Tensor, ops: Optional[TrainOps]) ->
                 and tuple(m.normalized_shape) == (TrainOps.WIDTH,) and x.dtype == torch.float32 and x.dim() == 2):
             x = _LayerNormReLU.apply(x, m.weight, m.bias, m.eps, ops)
             i += 2
+        elif (ops.use_linear_backward and isinstance(m, nn.Linear) and m.bias is not None and torch.is_grad_enabled() and x.dtype == torch.float32
+              and x.dim() == 2 and x.stride(1) == 1 and x.stride(0) >= x.shape[1] and m.weight.is_contiguous()):
+            x = _Linear.apply(x, m.weight, m.bias, ops)
+            i += 1
         else:
             x = m(x)
             i += 1
@@ -180,10 +213,11 @@ class BatchedMADDPG:
         self.ops: Optional[TrainOps] = None                # fused LayerNorm+ReLU kernels of the library (attach_ops)
         self.force_segmented = False                       # tests: take the multi-rank path in a one-rank process group
 
-    def attach_ops(self, env):
-        """Run the update's LayerNorm + ReLU pairs through the library's kernels (`env` provides handle and stream).
-        Invalidates captured graphs."""
-        self.ops = TrainOps(env) if env is not None else None
+    def attach_ops(self, env, linear_backward: bool = False):
+        """Run the update's LayerNorm + ReLU pairs through the library's kernels (`env` provides handle and stream);
+        `linear_backward`: also every Linear's backward as one launch (measured: no gain over cuBLAS's three kernels at
+        batch 128 -- 145.0 vs 144.8 M agent-steps/s -- hence off by default).  Invalidates captured graphs."""
+        self.ops = TrainOps(env, linear_backward=linear_backward) if env is not None else None
         self._graph, self._segments, self._eager_learns = None, None, 0
 
     def _fwd(self, net: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
@@ -463,7 +497,8 @@ class BatchedTrainer:
     """MADDPGAgent.train (maddpg/agent.py:77-252) for E environments at once, everything on the device."""
 
     def __init__(self, env, agent: Optional[BatchedMADDPG] = None, hp: Optional[Dict] = None,
-                 updates_per_learn: int = 1, seed: int = 0, fused_actor: bool = True, fused_sampler: bool = True, fused_ops: bool = True):
+                 updates_per_learn: int = 1, seed: int = 0, fused_actor: bool = True, fused_sampler: bool = True, fused_ops: bool = True,
+                 fused_linear_bwd: bool = False):
         from .replay import ReplayRing
         self.env = env
         self.hp = dict(DEFAULT_HP if hp is None else hp)
@@ -471,7 +506,7 @@ class BatchedTrainer:
         self.ring = ReplayRing(env.num_envs, env.n_learners, env.obs_len, self.hp["MEMORY_SIZE"], 9,
                                device=env.device, obs_dtype=env.obs_dtype)
         if fused_ops and env.device.type == "cuda" and self.agent.ops is None:
-            self.agent.attach_ops(env)
+            self.agent.attach_ops(env, linear_backward=fused_linear_bwd)
         self.updates_per_learn = int(updates_per_learn)
         self.gen = torch.Generator(device=env.device).manual_seed(seed + 1)
         self.fused_sampler = bool(fused_sampler) and env.device.type == "cuda"      # csrc/gw_replay.cu

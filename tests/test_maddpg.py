@@ -204,3 +204,36 @@ def test_update_with_fused_ops_tracks_the_torch_modules():
     worst = max(float((a - b).abs().max()) for a, b in zip(res[0][0], res[1][0]))
     assert worst < 2e-4, worst                              # Adam's normalised steps amplify rounding differences of tiny gradients
     assert torch.allclose(res[0][1], res[1][1], rtol=1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch,n_in,n_out,strided,x_grad", [(128, 338, 128, False, False), (128, 338, 128, False, True),
+                                                              (128, 128, 128, False, True), (128, 128, 1, False, True),
+                                                              (128, 160, 128, True, False), (128, 128, 9, False, True),
+                                                              (77, 45, 33, True, True), (1, 128, 128, False, True)])
+def test_fused_linear_backward_matches_torch(batch, n_in, n_out, strided, x_grad):
+    """gw_linear_backward (dW, db, dx in one launch) against autograd of torch.nn.functional.linear, fp32: the shapes of
+    the update (critic 338-128-128-1, actor 160-128-128-9, the actor's input a strided slice of the batch) and ragged ones."""
+    from marl_responsible_nav_b200 import BatchedGridWorld
+    dev = torch.device("cuda", 0)
+    env = BatchedGridWorld("Level 3", num_envs=32, fear=False, seed=1)
+    ops = maddpg.TrainOps(env)
+    g = torch.Generator(device=dev).manual_seed(batch + n_in)
+    lin = torch.nn.Linear(n_in, n_out).to(dev)
+    base = torch.randn(batch, 2, n_in, device=dev, generator=g)
+    x = (base[:, 1] if strided else base[:, 1].contiguous()).detach().requires_grad_(x_grad)
+    up = torch.randn(batch, n_out, device=dev, generator=g)
+    lin(x).backward(up)
+    want = (lin.weight.grad.clone(), lin.bias.grad.clone(), x.grad.clone() if x_grad else None)
+    lin.zero_grad(set_to_none=True)
+    x.grad = None
+    y = maddpg.forward_mlp(torch.nn.Sequential(lin), x, ops)
+    assert torch.equal(y, lin(x))
+    y.backward(up)
+    env.sync()
+    tol = dict(rtol=1e-4, atol=1e-4)
+    assert torch.allclose(lin.weight.grad, want[0], **tol) and torch.allclose(lin.bias.grad, want[1], **tol)
+    if x_grad:
+        assert torch.allclose(x.grad, want[2], **tol)
+    else:
+        assert x.grad is None
