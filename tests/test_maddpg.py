@@ -237,3 +237,25 @@ def test_fused_linear_backward_matches_torch(batch, n_in, n_out, strided, x_grad
         assert torch.allclose(x.grad, want[2], **tol)
     else:
         assert x.grad is None
+
+
+def test_host_side_of_the_fused_update_paths_on_cpu():
+    """No GPU: forward_mlp without the library is the module itself, branching is off (functions run in turn), the
+    update exposes no graph inputs, and the fused sampler refuses a CPU ring (there is no CPU path)."""
+    from marl_responsible_nav_b200.replay import ReplayRing
+    torch.manual_seed(0)
+    net = maddpg.mlp(160, (128, 128), 9, None)
+    x = torch.randn(5, 160)
+    assert torch.equal(maddpg.forward_mlp(net, x, None), net(x))
+    ag = maddpg.BatchedMADDPG(2, 160, 9, device="cpu", seed=1)
+    assert ag.ops is None and ag.static_inputs() is None
+    order = []
+    ag._fork_join([lambda: order.append("a"), lambda: order.append("b"), lambda: order.append("c")], "k")
+    ag._branches(lambda k: order.append(k))
+    assert order == ["a", "b", "c", 0, 1] and ag._side_streams == {}
+    ring = ReplayRing(4, 2, 160, capacity=40, device="cpu")
+    b = ring.new_batch(8)
+    assert b["state"].shape == (8, 2, 160) and b["done"].dtype == torch.float32 and b["t"].dtype == torch.int64
+    ring.advance()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ring.sample_fused(None, 8)
