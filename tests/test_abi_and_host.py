@@ -40,6 +40,35 @@ def test_config_struct_layout_matches_library():
     assert cfg.perturb_prob == 0.25 and cfg.fear_radius == 5 and cfg.max_steps == 150
 
 
+def test_header_is_plain_c_and_ctypes_mirrors_match(tmp_path):
+    """include/gridworld_b200.h compiles as C99 (the boundary a cgo / JNI / ctypes binding would include), and every
+    struct mirrored in _native.py has the size and field offsets the C compiler gives it."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("gcc not found")
+    mirrors = {"gw_config": N.GwConfig, "gw_io": N.GwIO, "gw_stats": N.GwStats, "gw_actor_weights": N.GwActorWeights,
+               "gw_replay_view": N.GwReplayView}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "gridworld_b200.h")}"',
+             'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in mirrors.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the product path must fail loudly (never route through the oracle)."""
     import torch
