@@ -10,6 +10,8 @@ timeout 200 python scripts/trace_server.py 4096 > gpurun_out/${R}_server_trace.t
 for E in 4096 8192 16384; do echo "== $E envs"; timeout 100 python scripts/e2e_breakdown.py $E 2>&1; done > gpurun_out/${R}_e2e_breakdown.txt
 timeout 300 python scripts/bench_rollout.py > gpurun_out/${R}_rollout.log 2>&1
 timeout 300 python -m marl_responsible_nav_b200.train --config custom_fear_10 --envs 4096 --steps 1200 --report 300 2>&1 | grep env_steps > gpurun_out/${R}_train_1gpu.log
+timeout 100 python scripts/trainer_breakdown.py > gpurun_out/${R}_trainer_breakdown.log 2>&1
+timeout 100 python scripts/bench_sampler.py > gpurun_out/${R}_sampler.log 2>&1
 CMD="python bench.py --steps 128 --warmup 64 --no-cpu-baseline --no-scale-points"
 $CMD > gpurun_out/${R}_bench_short_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/${R}_bench_launches.csv $CMD > gpurun_out/${R}_ncu_launchlist.log 2>&1
