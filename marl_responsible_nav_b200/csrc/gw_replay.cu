@@ -88,7 +88,11 @@ __global__ void __launch_bounds__(128) gw_replay_sample_kernel(const SampleArgs 
   }
   t_abs = __shfl_sync(0xffffffffu, t_abs, 0);
   e = __shfl_sync(0xffffffffu, e, 0);
-  const long long s = t_abs % r.slots, s1 = (t_abs + 1) % r.slots;
+  // caller-supplied indices are not trusted with the address arithmetic: wrap the time, clamp the env
+  long long s = t_abs % r.slots;
+  if (s < 0) s += r.slots;
+  const long long s1 = s + 1 == r.slots ? 0 : s + 1;
+  e = e < 0 ? 0 : (e >= r.num_envs ? r.num_envs - 1 : e);
   const long long row = s * r.num_envs + e, row1 = s1 * r.num_envs + e;
   const int L = r.n_learners, n_obs = L * r.obs_len, n_act = L * r.action_dim;
   const bool ended = r.ended[row] != 0;
