@@ -65,6 +65,11 @@ def workload_name(a):
             f"{a.envs} envs per GPU, {a.obs} MLP obs, uniform synthetic learner actions, device-RNG NPCs, auto-reset)")
 
 
+def bench_config(a, world):
+    """`config` of the JSON line: the same keys and values in both arms (ours / --impl reference)."""
+    return {"workload": workload_name(a), "envs_per_gpu": a.envs, "global_envs": world * a.envs}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -155,11 +160,11 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "agent-steps/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32 cells + f64 FeAR", "data": "synthetic",
-        "config": {"workload": workload_name(a), "envs_per_gpu": a.envs, "global_envs": a.gpus * a.envs,
-                   "parallelism": "host threads (one CPU arm per run, rank 0)",
-                   "sample": f"{sample_envs} of {a.envs} envs per step, {a.steps} steps",
-                   "note": "reference is pure Python (cannot travel to the GPU box): this is its C restatement "
-                           "(oracle/gw_oracle.c, pinned to reference-recorded golden vectors), all host threads"},
+        "config": bench_config(a, a.gpus),
+        "parallelism": "host threads (one CPU arm per run, rank 0)",
+        "sample": f"{sample_envs} of {a.envs} envs per step, {a.steps} steps",
+        "note": "C restatement of the reference path (oracle/gw_oracle.c, pinned to reference-recorded golden vectors), all "
+                "host threads; the reference's own Python env is timed next to it (reference_python)",
         "cpu_baseline": {"value": r["value"], "unit": "agent-steps/s", "cores": r["cores"], "kind": "port",
                          "sample": f"{sample_envs} envs x {a.steps} steps"},
         "e2e": {"value": r["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -195,26 +200,41 @@ def device_timed(a, E, fear, K, W, world, rank, dev, sample_clocks=False):
 
     run(W)
     env.sync()
-    # The timed loop is replayed from a CUDA graph of n_act consecutive steps (each with its own action tensor and ring
-    # slot), so that the device is not waiting on the Python/ctypes call between launches (--no-graph: eager launches).
-    graph = None
-    if a.graph:
+    # The timed loop is replayed from CUDA graphs, whatever K is: one graph of g = min(K, n_act) consecutive steps (each
+    # with its own action tensor and ring slot) replayed K // g times, plus a second graph for the K % g steps left, so
+    # that the device never waits on a Python/ctypes call between launches (--no-graph: eager launches).
+    graph = tail = None
+    g_steps = min(K, n_act)
+    plan = {"graph_steps": 0, "graph_replays": 0, "tail_graph_steps": 0, "eager_steps": K}
+    if a.graph and K > 0:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            run(n_act, W)
+            run(g_steps, W)
+        if K % g_steps:
+            tail = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(tail):
+                run(K % g_steps, W + g_steps)
         env.sync()
+        plan = {"graph_steps": g_steps, "graph_replays": K // g_steps, "tail_graph_steps": K % g_steps, "eager_steps": 0}
 
     def timed(k):
         if graph is None:
             run(k, W)
             return
-        for _ in range(k // n_act):
+        for _ in range(k // g_steps):
             graph.replay()
-        run(k % n_act, W)
+        if k % g_steps:
+            if tail is not None and k % g_steps == K % g_steps:
+                tail.replay()
+            else:
+                run(k % g_steps, W)
 
-    timed(min(K, 2 * n_act))                                      # graph warm-up
+    timed(K)                                                      # graph warm-up (the same launches as the timed region)
     env.sync()
     env.reset_stats()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush.zero_()                                                 # L2 flush (256 MiB > 126 MB): nothing of the warm-up stays cached
+    del flush
     sampler = ClockSampler(dev.index)
     if sample_clocks and rank == 0:
         sampler.start()
@@ -238,7 +258,7 @@ def device_timed(a, E, fear, K, W, world, rank, dev, sample_clocks=False):
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)          # time = max over ranks
         dist.all_reduce(stat_vec, op=dist.ReduceOp.SUM)      # episode statistics over NVLink (the only collective)
     return {"ms": float(t_ms.item()), "stats": stat_vec, "env": env, "ring": ring, "slots": slots, "L": L,
-            "obs_bytes": obs_bytes, "clocks": clocks, "n_act": n_act}
+            "obs_bytes": obs_bytes, "clocks": clocks, "n_act": n_act, "plan": plan}
 
 
 def masked_uniform_runs(a, E, dev, seeds=(0, 42, 66), steps=384):
@@ -310,7 +330,7 @@ def run_ours(a):
     r = device_timed(a, E, a.fear, K, W, world, rank, dev, sample_clocks=True)
     ms, stat_vec, env, ring, slots, L, obs_bytes, n_act = (r[k] for k in ("ms", "stats", "env", "ring", "slots", "L", "obs_bytes", "n_act"))
     env_agents = env.n_agents
-    clocks = r["clocks"]
+    clocks, r_plan = r["clocks"], r["plan"]
     value = world * E * L * K / (ms * 1e-3)
 
     # ---- e2e: public API, host action buffers, H2D + D2H inside the timed region
@@ -369,21 +389,30 @@ def run_ours(a):
         except Exception as exc:                            # an extra: must not cost the headline line
             variants = [{"failed": repr(exc)}]
 
-    # ---- the same kernel at a batch that fills the GPU (the step kernel's roofline point), N = 1 only
+    # ---- the same kernel at batches that fill the GPU: 1 M envs on one GPU (the step kernel's roofline point); with
+    # several ranks BASELINE.json configs[3]'s split -- 10^6 envs over the ranks, statistics all-reduced
     scale_points = None
-    if world == 1 and not a.no_scale_points:
+    if not a.no_scale_points:
         scale_points = []
         peak, _ = peaks()
-        for Es, fs in ((1 << 20, 1), (1 << 20, 0)):
-            torch.cuda.empty_cache()
-            rs = device_timed(a, Es, fs, 128, 64, 1, 0, dev)
-            per = rs["ms"] * 1e-3 / 128
-            gbs = ALGO_BYTES_PER_AGENT_STEP[a.obs] * Es * rs["L"] / per / 1e9
-            scale_points.append({"envs": Es, "fear": bool(fs), "kernel": kernel_name(Es, fs, a.obs), "ms_per_step": rs["ms"] / 128,
-                                 "agent_steps_per_s": Es * rs["L"] / per, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak,
-                                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_AGENT_STEP[a.obs] * Es * rs["L"],
-                                 "traffic": NCU_DRAM_BYTES.get((Es, fs)) if (a.obs == "f32" and a.scenario == "Level 3") else None})
-            del rs
+        points = ((1 << 20, 1), (1 << 20, 0)) if world == 1 else ((1000000 // world, 1),)
+        for Es, fs in points:
+            try:
+                torch.cuda.empty_cache()
+                rs = device_timed(a, Es, fs, 128, 64, world, rank, dev)
+                per = rs["ms"] * 1e-3 / 128
+                gbs = ALGO_BYTES_PER_AGENT_STEP[a.obs] * Es * rs["L"] / per / 1e9
+                scale_points.append({"envs_per_gpu": Es, "global_envs": Es * world, "fear": bool(fs), "kernel": kernel_name(Es, fs, a.obs),
+                                     "ms_per_step": rs["ms"] / 128, "agent_steps_per_s": world * Es * rs["L"] / per,
+                                     "achieved_gbs_per_gpu": gbs, "frac_of_hbm_peak": gbs / peak,
+                                     "algorithmic_bytes_per_launch": ALGO_BYTES_PER_AGENT_STEP[a.obs] * Es * rs["L"],
+                                     "launch_plan": rs["plan"],
+                                     "traffic": NCU_DRAM_BYTES.get((Es, fs)) if (a.obs == "f32" and a.scenario == "Level 3") else None})
+                del rs
+            except Exception as exc:                        # an extra: must not cost the headline line
+                scale_points.append({"envs_per_gpu": Es, "failed": repr(exc)})
+                if world > 1:
+                    break                                   # the ranks may be out of step: no further collectives in extras
 
     if rank != 0:
         if world > 1:
@@ -396,10 +425,11 @@ def run_ours(a):
         "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 cells / int32 rewards / f64 FeAR; obs " + a.obs, "data": "synthetic",
-        "config": {"workload": workload_name(a), "envs_per_gpu": E, "global_envs": world * E,
-                   "parallelism": f"env-shard x{world}, no per-step collective",
-                   "l2": f"obs stores stream through a {slots}-slot ring of {slots * obs_bytes / 2**20:.0f} MiB (> 126 MB L2), "
-                         "never re-read; the packed env state (16 B/env) is L2-resident by design"},
+        "config": bench_config(a, world),
+        "parallelism": f"env-shard x{world}, no per-step collective",
+        "l2": f"L2 flushed (256 MiB write) before the timed region; obs stores stream through a {slots}-slot ring of "
+              f"{slots * obs_bytes / 2**20:.0f} MiB (> 126 MB L2), never re-read; the packed env state (16 B/env) is L2-resident by design",
+        "launch_plan": r_plan,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(K),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_DRAM_BYTES.get((E, int(bool(a.fear)))) if (a.obs == "f32" and a.scenario == "Level 3") else None,
@@ -408,7 +438,8 @@ def run_ours(a):
                      "kernel": kernel_name(E, a.fear, a.obs),
                      "algorithmic_bytes_per_launch": algo, "peak_source": peak_src,
                      "note": "launch duration = CUDA-event time over K back-to-back launches / K (includes launch gaps); "
-                             + ("CUDA-graph replay" if a.graph else "eager launches")
+                             + (f"CUDA graphs: {r_plan['graph_replays']} x {r_plan['graph_steps']} steps + {r_plan['tail_graph_steps']} steps"
+                                if r_plan["eager_steps"] == 0 else f"{r_plan['eager_steps']} eager launches")
                              + f"; at {E} envs one launch moves {algo / 2**20:.1f} MiB ({algo / peak / 1e3:.2f} us at peak): small batches are "
                                "launch/latency-bound, see scale_points for the step kernel at 1M envs"},
         "scale_points": scale_points, "masked_uniform_runs": variants,
