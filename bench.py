@@ -32,9 +32,11 @@ ALGO_BYTES_PER_AGENT_STEP = {"f32": 668.0, "bf16": 348.0}      # SURVEY.md secti
 NCU_DRAM_BYTES = {(4096, 1): 370.0e3 + 0.0, (1 << 20, 1): 23.2e6 + 1413.0e6, (1 << 20, 0): 19.33e6 + 1378.3e6}
 
 
-def kernel_name(envs, fear, obs):
-    """The kernel gw_step picks for this batch (csrc/gw_kernels.cu: pick_small / pick_tile)."""
+def kernel_name(envs, fear, obs, mode="step"):
+    """The kernel gw_step picks for this batch (csrc/gw_kernels.cu: pick_small / pick_tile); gw_rollout has one."""
     f = "true" if fear else "false"
+    if mode == "rollout":
+        return f"gw_rollout_kernel<{f},{obs}>"
     if envs <= 6144:
         return f"gw_step_small_kernel<{f},{obs}>"
     tile = 32 if envs <= 24576 else (128 if envs <= 196608 else 256)
@@ -54,9 +56,14 @@ def parse():
     ap.add_argument("--scenario", default="Level 3")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-python", action="store_true", help="skip timing the reference's own Python env")
+    ap.add_argument("--python-seconds", type=float, default=8.0, help="seconds per setting (FeAR off / on) of the Python reference leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-scale-points", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every step from Python instead of replaying a CUDA graph")
+    ap.add_argument("--mode", default="rollout", choices=["rollout", "step"],
+                    help="rollout: gw_rollout, up to --rollout-steps env steps per launch (default); step: one gw_step launch per step")
+    ap.add_argument("--rollout-steps", type=int, default=64, help="env steps per gw_rollout launch")
     return ap.parse_args()
 
 
@@ -142,6 +149,17 @@ def time_cpu_oracle(a, seconds, steps=None, warmup=2):
             "envs": E, "stats": o.stats()}
 
 
+def time_reference_python(seconds=8.0):
+    """The reference's own Python env (unmodified files staged into baseline/_ref by build()) on every host core, FeAR off
+    and on, in a child process (forked workers must not inherit this process's CUDA context)."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "reference_python.py"), "--seconds", str(seconds)]
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=seconds * 2 + 120)
+        return json.loads(res.stdout.strip().splitlines()[-1])
+    except Exception as exc:
+        return {"kind": "reference-python", "unavailable": repr(exc)}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -166,7 +184,8 @@ def run_reference(a):
         "note": "C restatement of the reference path (oracle/gw_oracle.c, pinned to reference-recorded golden vectors), all "
                 "host threads; the reference's own Python env is timed next to it (reference_python)",
         "cpu_baseline": {"value": r["value"], "unit": "agent-steps/s", "cores": r["cores"], "kind": "port",
-                         "sample": f"{sample_envs} envs x {a.steps} steps"},
+                         "sample": f"{sample_envs} envs x {a.steps} steps",
+                         "reference_python": None if a.no_reference_python else time_reference_python(a.python_seconds)},
         "e2e": {"value": r["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -174,6 +193,75 @@ def run_reference(a):
 
 
 # ----------------------------------------------------------------------------- GPU path
+ROLL_FIELDS = ("obs", "reward", "shaped_reward", "fear", "terminated", "truncated", "ended", "info", "positions", "obs_code",
+               "action_mask")       # what a gw_step call of the bench writes as well (no final_obs)
+
+
+def device_timed_rollout(a, E, fear, K, W, world, rank, dev, sample_clocks=False):
+    """K timed env steps over E envs on this rank through gw_rollout: ceil(K / T) launches of up to T = --rollout-steps
+    steps each, every step with its own action tensor and its own slot of the output rings (CUDA events on the launching
+    stream, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from marl_responsible_nav_b200 import BatchedGridWorld
+    obs_dtype = torch.float32 if a.obs == "f32" else torch.bfloat16
+    env = BatchedGridWorld(a.scenario, num_envs=E, device=dev, fear=bool(fear), fear_weight=-5.0, auto_reset=True,
+                           max_steps=150, obs_dtype=obs_dtype, seed=42, env_id_base=rank * E)
+    L = env.n_learners
+    obs_bytes = E * L * env.obs_len * (4 if a.obs == "f32" else 2)
+    T = max(1, int(a.rollout_steps))
+    slots = max(2, -(-(320 << 20) // obs_bytes), T + 1)          # ring larger than L2 (126 MB), as in device_timed
+    slots = min(slots, max(2, (8 << 30) // obs_bytes))
+    rings = env.new_rings(slots, fields=ROLL_FIELDS)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    n_act = 64
+    actions = torch.randint(0, 9, (n_act, E, L), generator=gen, device=dev, dtype=torch.int8)
+    env.reset(obs_out=rings.obs[0])
+
+    def run(n, t0):
+        done, launches = 0, 0
+        while done < n:
+            k = min(T, n - done)
+            env.rollout(actions, k, rings, first_slot=(t0 + done) % slots, first_action=(t0 + done) % n_act)
+            done += k
+            launches += 1
+        return launches
+
+    run(W, 0)
+    run(K, W)                                                     # the same launches as the timed region, untimed
+    env.sync()
+    env.reset_stats()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush.zero_()                                                 # L2 flush (256 MiB > 126 MB)
+    del flush
+    sampler = ClockSampler(dev.index)
+    if sample_clocks and rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    launches = run(K, W + K)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if (sample_clocks and rank == 0) else None
+    st = env.stats()
+    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    stat_vec = torch.tensor([st["episodes"], st["episode_len_sum"], st["crashes"], st["apples"], st["fear_nonzero"],
+                             st["return_sum"], st["fear_sum"], st["unresolved"], st["fear_tasks"]], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stat_vec, op=dist.ReduceOp.SUM)
+    plan = {"mode": "rollout", "rollout_launches": launches, "steps_per_launch": min(T, K), "graph_steps": 0, "graph_replays": 0,
+            "tail_graph_steps": 0, "eager_steps": 0}
+    return {"ms": float(t_ms.item()), "stats": stat_vec, "env": env, "ring": rings.obs, "slots": slots, "L": L,
+            "obs_bytes": obs_bytes, "clocks": clocks, "n_act": n_act, "plan": plan, "launches": launches}
+
+
 def device_timed(a, E, fear, K, W, world, rank, dev, sample_clocks=False):
     """K timed gw_step launches over E envs on this rank (CUDA events on the launching stream, max over ranks)."""
     import torch
@@ -205,7 +293,7 @@ def device_timed(a, E, fear, K, W, world, rank, dev, sample_clocks=False):
     # that the device never waits on a Python/ctypes call between launches (--no-graph: eager launches).
     graph = tail = None
     g_steps = min(K, n_act)
-    plan = {"graph_steps": 0, "graph_replays": 0, "tail_graph_steps": 0, "eager_steps": K}
+    plan = {"mode": "step", "graph_steps": 0, "graph_replays": 0, "tail_graph_steps": 0, "eager_steps": K}
     if a.graph and K > 0:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
@@ -215,7 +303,7 @@ def device_timed(a, E, fear, K, W, world, rank, dev, sample_clocks=False):
             with torch.cuda.graph(tail):
                 run(K % g_steps, W + g_steps)
         env.sync()
-        plan = {"graph_steps": g_steps, "graph_replays": K // g_steps, "tail_graph_steps": K % g_steps, "eager_steps": 0}
+        plan = {"mode": "step", "graph_steps": g_steps, "graph_replays": K // g_steps, "tail_graph_steps": K % g_steps, "eager_steps": 0}
 
     def timed(k):
         if graph is None:
@@ -258,7 +346,7 @@ def device_timed(a, E, fear, K, W, world, rank, dev, sample_clocks=False):
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)          # time = max over ranks
         dist.all_reduce(stat_vec, op=dist.ReduceOp.SUM)      # episode statistics over NVLink (the only collective)
     return {"ms": float(t_ms.item()), "stats": stat_vec, "env": env, "ring": ring, "slots": slots, "L": L,
-            "obs_bytes": obs_bytes, "clocks": clocks, "n_act": n_act, "plan": plan}
+            "obs_bytes": obs_bytes, "clocks": clocks, "n_act": n_act, "plan": plan, "launches": K}
 
 
 def masked_uniform_runs(a, E, dev, seeds=(0, 42, 66), steps=384):
@@ -327,7 +415,18 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     E, K, W = a.envs, a.steps, a.warmup
-    r = device_timed(a, E, a.fear, K, W, world, rank, dev, sample_clocks=True)
+    rollout_mode = a.mode == "rollout" and E <= 65536           # beyond that the thread-per-env step kernel is the faster one
+    per_step = None
+    if rollout_mode:
+        # the same K steps with one gw_step launch per step (CUDA-graph replay), reported next to the headline
+        rs = device_timed(a, E, a.fear, K, W, world, rank, dev)
+        per_step = {"value": world * E * rs["L"] * K / (rs["ms"] * 1e-3), "unit": "agent-steps/s", "ms_per_step": rs["ms"] / K,
+                    "kernel": kernel_name(E, a.fear, a.obs), "launch_plan": rs["plan"]}
+        rs["env"].close()
+        del rs
+        torch.cuda.empty_cache()
+    r = (device_timed_rollout if rollout_mode else device_timed)(a, E, a.fear, K, W, world, rank, dev, sample_clocks=True)
+    n_launches = r["launches"]
     ms, stat_vec, env, ring, slots, L, obs_bytes, n_act = (r[k] for k in ("ms", "stats", "env", "ring", "slots", "L", "obs_bytes", "n_act"))
     env_agents = env.n_agents
     clocks, r_plan = r["clocks"], r["plan"]
@@ -430,18 +529,20 @@ def run_ours(a):
         "l2": f"L2 flushed (256 MiB write) before the timed region; obs stores stream through a {slots}-slot ring of "
               f"{slots * obs_bytes / 2**20:.0f} MiB (> 126 MB L2), never re-read; the packed env state (16 B/env) is L2-resident by design",
         "launch_plan": r_plan,
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(K),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(n_launches), "launch_per_step": per_step,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_DRAM_BYTES.get((E, int(bool(a.fear)))) if (a.obs == "f32" and a.scenario == "Level 3") else None,
+                     "traffic": (NCU_DRAM_BYTES.get((E, int(bool(a.fear)))) if (a.obs == "f32" and a.scenario == "Level 3" and r_plan["mode"] == "step") else None),
                      "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1d_*_ncu_raw.csv); "
                                        "at 4096 envs the stores are still in L2 when the kernel ends, so DRAM writes show as 0",
-                     "kernel": kernel_name(E, a.fear, a.obs),
-                     "algorithmic_bytes_per_launch": algo, "peak_source": peak_src,
-                     "note": "launch duration = CUDA-event time over K back-to-back launches / K (includes launch gaps); "
-                             + (f"CUDA graphs: {r_plan['graph_replays']} x {r_plan['graph_steps']} steps + {r_plan['tail_graph_steps']} steps"
-                                if r_plan["eager_steps"] == 0 else f"{r_plan['eager_steps']} eager launches")
-                             + f"; at {E} envs one launch moves {algo / 2**20:.1f} MiB ({algo / peak / 1e3:.2f} us at peak): small batches are "
-                               "launch/latency-bound, see scale_points for the step kernel at 1M envs"},
+                     "kernel": kernel_name(E, a.fear, a.obs, r_plan["mode"]),
+                     "algorithmic_bytes_per_launch": algo * K / n_launches, "algorithmic_bytes_per_step": algo, "peak_source": peak_src,
+                     "launch_ms": ms / n_launches,
+                     "note": "achieved = algorithmic bytes of the K timed steps / CUDA-event time over the timed region (includes launch gaps); "
+                             + (f"gw_rollout: {n_launches} launch(es) of up to {r_plan['steps_per_launch']} env steps each" if r_plan["mode"] == "rollout"
+                                else (f"CUDA graphs: {r_plan['graph_replays']} x {r_plan['graph_steps']} steps + {r_plan['tail_graph_steps']} steps"
+                                      if r_plan["eager_steps"] == 0 else f"{r_plan['eager_steps']} eager launches"))
+                             + f"; at {E} envs one step moves {algo / 2**20:.1f} MiB ({algo / peak / 1e3:.2f} us at peak): small batches are "
+                               "latency-bound (a warp's dependent chain per step), see scale_points for the step kernel at 1M envs"},
         "scale_points": scale_points, "masked_uniform_runs": variants,
         "workload_stats": {"episodes": stat_vec[0].item(), "mean_episode_len": stat_vec[1].item() / max(1.0, stat_vec[0].item()),
                            "learner_crashes_per_env_step": stat_vec[2].item() / (world * E * K),
@@ -459,6 +560,8 @@ def run_ours(a):
             line["cpu_baseline"] = {"value": c["value"], "unit": "agent-steps/s", "cores": c["cores"], "kind": "port",
                                     "sample": f"{c['envs']} envs x {c['steps']} steps ({c['seconds']:.1f} s), C restatement "
                                               "of the reference path (oracle/gw_oracle.c), all host threads"}
+            if not a.no_reference_python:
+                line["cpu_baseline"]["reference_python"] = time_reference_python(a.python_seconds)
         except Exception as exc:   # the checker failing must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "agent-steps/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {exc}"}

@@ -149,6 +149,29 @@ int gw_reset(gw_handle* h, const uint8_t* reset_mask, const gw_io* io, void* str
 int gw_step(gw_handle* h, const gw_io* io, void* stream);
 int gw_sync(gw_handle* h, void* stream);       /* cudaStreamSynchronize + surface async faults */
 
+/* Device-side rollout: `steps` consecutive gw_step's in ONE launch -- the inner loop of MADDPGAgent.train
+ * (maddpg/agent.py:85-197: env.step, reward shaping, replay write) for a whole batch, when the actions of those steps
+ * are already on the device (recorded / scripted action streams, open-loop evaluation, or the rollout of a policy
+ * whose actions were computed ahead).  Environments are independent, so a CTA steps its 32 envs `steps` times without
+ * any grid-wide synchronisation; packed state and random words stay in registers between the steps.
+ * `rings` holds the pointers of slot 0 of TIME-MAJOR arrays (the replay ring's layout):
+ *   outputs [ring_slots, <per-step shape of gw_io>]: the transition of step k (reward, shaped_reward, fear, terminated,
+ *   truncated, ended, info, positions, final_obs) goes to slot (first_slot + k) % ring_slots, what the policy reads
+ *   next (obs, obs_code, action_mask) to the slot after it, (first_slot + k + 1) % ring_slots;
+ *   inputs [action_slots, ...] (learner_actions; npc_actions / spawn in replay mode): step k reads slot
+ *   (first_action + k) % action_slots.
+ * rings->obs and rings->learner_actions are required.  Results are bit-identical to `steps` gw_step calls.
+ * Stream-ordered, no synchronisation, CUDA-graph capturable. */
+typedef struct gw_rollout_plan {
+  uint32_t struct_size;          /* sizeof(gw_rollout_plan) */
+  int32_t steps;
+  int64_t ring_slots;
+  int64_t first_slot;
+  int64_t action_slots;
+  int64_t first_action;
+} gw_rollout_plan;
+int gw_rollout(gw_handle* h, const gw_io* rings, const gw_rollout_plan* plan, void* stream);
+
 /* Host-driven step (the reference's calling pattern, maddpg/agent.py:121-131: actions arrive as host integers, rewards
  * and done flags are read on the host): copies `host_actions` [E, n_learners] int8 (pinned) to io->learner_actions,
  * runs gw_step, copies io->reward -> host_reward f32 [E, n_learners], io->shaped_reward -> host_shaped (nullable),

@@ -11,7 +11,7 @@ GW_ENV_MULTI, GW_ENV_SINGLE = 0, 1
 GW_OBS_F32, GW_OBS_BF16 = 0, 1
 
 EXPORTS = ["gw_abi_version", "gw_build_info", "gw_default_config", "gw_create", "gw_destroy", "gw_last_error",
-           "gw_reset", "gw_step", "gw_step_host", "gw_host_call_prepare", "gw_host_call_run", "gw_host_call_reset", "gw_server_stop", "gw_server_info", "gw_sync", "gw_state_bytes", "gw_get_state", "gw_set_state", "gw_get_stats",
+           "gw_reset", "gw_step", "gw_rollout", "gw_step_host", "gw_host_call_prepare", "gw_host_call_run", "gw_host_call_reset", "gw_server_stop", "gw_server_info", "gw_sync", "gw_state_bytes", "gw_get_state", "gw_set_state", "gw_get_stats",
            "gw_reset_stats", "gw_launch_count", "gw_update_world", "gw_fear_one_actor", "gw_fear_matrix", "gw_feal", "gw_actor_create", "gw_actor_update", "gw_actor_update_device",
            "gw_actor_destroy", "gw_actor_forward", "gw_replay_sample", "gw_ln_relu_forward", "gw_ln_relu_backward", "gw_linear_backward"]
 
@@ -50,6 +50,11 @@ class GwIO(C.Structure):
         "terminated", "truncated", "ended", "action_mask", "positions", "info", "obs_code")]
 
 
+class GwRolloutPlan(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("steps", C.c_int32), ("ring_slots", C.c_int64), ("first_slot", C.c_int64),
+                ("action_slots", C.c_int64), ("first_action", C.c_int64)]
+
+
 class GwStats(C.Structure):
     _fields_ = [("env_steps", C.c_uint64), ("agent_steps", C.c_uint64), ("episodes", C.c_uint64),
                 ("episode_len_sum", C.c_uint64), ("crashes", C.c_uint64), ("apples", C.c_uint64),
@@ -80,6 +85,7 @@ def load():
     lib.gw_last_error.restype = C.c_char_p
     lib.gw_reset.argtypes = [vp, vp, C.POINTER(GwIO), vp]
     lib.gw_step.argtypes = [vp, C.POINTER(GwIO), vp]
+    lib.gw_rollout.argtypes = [vp, C.POINTER(GwIO), C.POINTER(GwRolloutPlan), vp]
     lib.gw_sync.argtypes = [vp, vp]
     lib.gw_step_host.argtypes = [vp, C.POINTER(GwIO), vp, vp, vp, vp, C.c_int, vp]
     lib.gw_host_call_prepare.argtypes = [vp, C.POINTER(GwIO), vp, vp, vp, vp, C.c_int, C.POINTER(C.c_int)]

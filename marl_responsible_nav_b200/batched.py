@@ -233,6 +233,64 @@ class BatchedGridWorld:
                           ended=b.ended, info=b.info, final_obs=self._view(fin) if fin is not None else None,
                           obs_code=m.obs_code)
 
+    # ---- device-side rollout: T steps per launch (gw_rollout)
+    _RING_SPECS = (("obs", None, ("L", "O")), ("final_obs", None, ("L", "O")), ("reward", torch.float32, ("L",)),
+                   ("shaped_reward", torch.float32, ("L",)), ("fear", torch.float64, ("L",)), ("terminated", torch.uint8, ("L",)),
+                   ("truncated", torch.uint8, ("L",)), ("ended", torch.uint8, ()), ("info", torch.int32, ()),
+                   ("positions", torch.int8, ("A", 2)), ("obs_code", torch.int64, ()), ("action_mask", torch.int8, ("L", 9)))
+
+    def new_rings(self, slots: int, fields: Optional[Sequence[str]] = None) -> "SimpleNamespace":
+        """Time-major output rings for `rollout`: one tensor [slots, E, ...] per output of gw_step (`fields` = subset;
+        "obs" is always there).  A ReplayRing has the same attribute names and works as well."""
+        from types import SimpleNamespace
+        dims = {"L": self.n_learners, "O": self.obs_len, "A": self.n_agents}
+        ns = SimpleNamespace()
+        for name, dtype, tail in self._RING_SPECS:
+            if fields is not None and name not in fields and name != "obs":
+                setattr(ns, name, None)
+                continue
+            shape = (int(slots), self.num_envs) + tuple(dims.get(d, d) for d in tail)
+            setattr(ns, name, torch.zeros(shape, dtype=dtype or self.obs_dtype, device=self.device))
+        return ns
+
+    def rollout(self, actions: torch.Tensor, steps: int, rings, first_slot: int = 0, first_action: int = 0,
+                npc_actions: Optional[torch.Tensor] = None, spawn: Optional[torch.Tensor] = None):
+        """`steps` consecutive env steps in ONE kernel launch (gw_rollout): the inner loop of MADDPGAgent.train
+        (maddpg/agent.py:85-197) for actions that are already on the device.  actions: int8 [A, E, n_learners]; step k
+        plays actions[(first_action + k) % A] and writes its transition into slot (first_slot + k) % T of `rings`
+        (time-major tensors [T, E, ...] named like StepOutput's fields: `new_rings`, or a ReplayRing) and the observation /
+        obs_code / action mask that follow it into the slot after.  Replay mode: npc_actions [A, E, n_agents], spawn
+        [A, E, n_agents, 2] with the same indexing.  Bit-identical to `steps` calls of step()."""
+        E, L, A, dev = self.num_envs, self.n_learners, self.n_agents, self.device
+        actions = self._as_i8(actions, dev)
+        if actions.dim() != 3 or tuple(actions.shape[1:]) != (E, L):
+            raise ValueError(f"actions: expected int8 [A, {E}, {L}]")
+        n_act = actions.shape[0]
+        T = int(rings.obs.shape[0])
+        dims = {"L": L, "O": self.obs_len, "A": A}
+        io = N.GwIO()
+        io.learner_actions = actions.data_ptr()
+        for name, t, tail in (("npc_actions", npc_actions, (A,)), ("spawn", spawn, (A, 2))):
+            if t is not None:
+                t = self._as_i8(t, dev)
+                if tuple(t.shape) != (n_act, E) + tail:
+                    raise ValueError(f"{name}: expected int8 {(n_act, E) + tail}")
+                setattr(io, name, t.data_ptr())
+        keep = [actions, npc_actions, spawn]
+        for name, dtype, tail in self._RING_SPECS:
+            t = getattr(rings, name, None)
+            if t is None:
+                continue
+            if name in ("obs", "final_obs"):
+                if t.dtype != self.obs_dtype or t.device != dev or not t.is_contiguous() or t.shape[0] != T or t[0].numel() != E * L * self.obs_len:
+                    raise ValueError(f"rings.{name}: need a contiguous {self.obs_dtype} tensor [T, E, L, {self.obs_len}] on {dev}")
+            else:
+                _check(t, "rings." + name, dtype, (T, E) + tuple(dims.get(d, d) for d in tail), dev)
+            setattr(io, name, t.data_ptr())
+        plan = N.GwRolloutPlan(C.sizeof(N.GwRolloutPlan), int(steps), T, int(first_slot) % T, n_act, int(first_action) % n_act)
+        N.check(self.lib.gw_rollout(self._h, C.byref(io), C.byref(plan), self._stream()), self._h, "gw_rollout")
+        return rings
+
     def step_host(self, host_actions: torch.Tensor, host_reward: torch.Tensor, host_ended: Optional[torch.Tensor] = None,
                   host_shaped: Optional[torch.Tensor] = None, obs_out: Optional[torch.Tensor] = None,
                   zero_copy: bool = True, resident: Optional[bool] = None) -> StepOutput:

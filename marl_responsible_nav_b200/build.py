@@ -10,7 +10,8 @@ LIB = os.path.join(CSRC, "libgridworld_b200.so")
 SOURCES = ["gw_kernels.cu", "gw_actor.cu", "gw_replay.cu", "gw_train_ops.cu"]
 HEADERS = ["gw_device.cuh", "gw_internal.h", os.path.join("..", "..", "include", "gridworld_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
+OBJ_DIR = os.path.join(CSRC, "_obj")          # per-source objects (git-ignored): only stale sources are recompiled
 
 
 def _nvcc():
@@ -28,14 +29,31 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compile every stale source to an object (in parallel), then link the shared library."""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    hdr_t = max(os.path.getmtime(os.path.join(CSRC, f)) for f in HEADERS)
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        objs.append(obj)
+        if (not force and os.path.exists(obj)
+                and os.path.getmtime(obj) > max(hdr_t, os.path.getmtime(os.path.join(CSRC, src)))):
+            continue
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + out)
+        if verbose:
+            sys.stderr.write(out)
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs, cwd=CSRC,
+                         capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        sys.stderr.write(res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB
 
 

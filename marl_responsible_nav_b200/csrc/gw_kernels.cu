@@ -921,12 +921,21 @@ __device__ __forceinline__ void server_flush(void* gdst, const void* ssrc, int b
   }
 }
 
+// gw_rollout: several steps per launch (see the ROLL notes in small_step_tiles)
+struct RollParams {
+  int steps;
+  long long ring_slots, first_slot;       // time-major output rings: slot of step 0's transition
+  long long action_slots, first_action;   // time-major action arrays: slot of step 0's actions
+  int wait_full;                          // steps > ring_slots - 1: a slot is written more than once per launch
+};
+
 // The step of the CTA's tiles (tile = blockIdx.x, += gridDim.x).  SERVER: called once per command by the resident kernel
 // below -- inputs that the host rewrites between two calls are loaded past the L1 (ordinary L2-level loads after the
 // system-scope acquire fence that follows the doorbell: `ld.volatile` reads of host memory are served one PCIe round
 // trip after the other, ~50 ns per request, measured 50-100 us per step at 4096 envs).
-template <bool FEAR, int OBS, bool SERVER>
-__device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& s, uint8_t* stage, bool& tables_pending) {
+template <bool FEAR, int OBS, bool SERVER, bool ROLL = false>
+__device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& s, uint8_t* stage, bool& tables_pending,
+                                                 const RollParams* rp = nullptr) {
   constexpr int TILE = 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = tid & 7, gsh = lane & 24;
   constexpr unsigned FULL = 0xFFFFFFFFu;     // every shuffle / ballot below is executed by the whole converged warp: a
@@ -938,7 +947,7 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
   const int V = nl * Q, row_bytes = V * 16;
   uint8_t* const rows4 = stage + (size_t)warp * 4 * row_bytes;         // this warp's staging rows
   uint8_t* const myrow = rows4 + (lane >> 3) * row_bytes;              // this group's env
-  if (!SERVER && p.pdl_early) asm volatile("griddepcontrol.launch_dependents;");
+  if (!SERVER && !ROLL && p.pdl_early) asm volatile("griddepcontrol.launch_dependents;");
 
   // SERVER: rewards / shaped rewards / ended flags (the results the host reads) are collected per tile and leave as one
   // bulk copy per array: written lane by lane into host memory they are ~12k small PCIe writes per step (measured: 40 us).
@@ -962,6 +971,20 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
     uint32_t la = 0, npc_a = 0, chosen = 0;
     uint32_t rw[4] = {0, 0, 0, 0}, rw2[4] = {0, 0, 0, 0};
     bool act_staged = false;
+    // ROLL (gw_rollout): the tile is stepped n_steps times by this CTA; state and random words stay in registers between
+    // the steps, the outputs of step k go to slot (first_slot + k) of the caller's time-major rings (observation, obs_code
+    // and action mask -- what the policy reads next -- to the slot after it), the actions come from slot (first_action + k).
+    const int n_steps = ROLL ? rp->steps : 1;
+    long long slot_t = ROLL ? rp->first_slot : 0, slot_a = ROLL ? rp->first_action : 0;
+    uint32_t la_next = 0;
+    uint4 st_carry = make_uint4(0, 0, 0, 0);
+    for (int k_step = 0; k_step < n_steps; ++k_step) {
+    const long long slot_o = (ROLL && slot_t + 1 >= rp->ring_slots) ? 0 : slot_t + 1;
+    const long long et = ROLL ? slot_t * p.E + e : e;                  // index into the transition arrays (rewards, flags ...)
+    const long long eo = ROLL ? slot_o * p.E + e : e;                  // ... the observation-side arrays
+    const long long ea = ROLL ? slot_a * p.E + e : e;                  // ... the action arrays
+    const bool first_step = !ROLL || k_step == 0, last_step = !ROLL || k_step + 1 == n_steps;
+    la = 0; npc_a = 0;
     if (SERVER) {
       // The actions come out of pinned HOST memory: fetched lane by lane, the tile's 64 bytes turn into 16 read requests
       // per CTA and the PCIe read queue becomes the step's critical path (measured: CTAs finish 5-8 us apart).  A few
@@ -971,17 +994,12 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
       if (act_staged && tid < (tile_envs * nl + 15) / 16)
         reinterpret_cast<uint4*>(act_s)[tid] = __ldcg(reinterpret_cast<const uint4*>(ap) + tid);   // stays inside the last 16-byte granule
     }
-    if (own) {
+    if (own && first_step) {
       st = p.state[e];
       // The random words of this step were drawn at the end of the previous one (they only depend on seed, env id and
       // tick) and parked next to the state; the tag tells whether they belong to this tick (not after reset / set_state).
       uint4 c0 = make_uint4(0, 0, 0, 0), c1 = make_uint4(0, 0, 0, ~st.z);
       if (p.rng_cache != nullptr) { c0 = p.rng_cache[2 * e]; c1 = p.rng_cache[2 * e + 1]; }
-#pragma unroll
-      for (int k = 0; k < GW_MAX_LEARNERS; ++k)
-        if (k < nl && !act_staged) la |= (uint32_t)min(max((int)(SERVER ? __ldcg(p.io.learner_actions + e * nl + k) : p.io.learner_actions[e * nl + k]), 0), 8) << (4 * k);
-      if (p.io.npc_actions != nullptr && r < 4 && r >= nl && r < n)
-        npc_a = (uint32_t)min(max((int)(SERVER ? __ldcg(p.io.npc_actions + e * n + r) : p.io.npc_actions[e * n + r]), 0), 8);
       if (c1.w == st.z) {
         rw[0] = c0.x; rw[1] = c0.y; rw[2] = c0.z; rw[3] = c0.w;
         rw2[0] = c1.x; rw2[1] = c1.y;
@@ -989,6 +1007,25 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
       } else {
         draw_step_randoms(p, e, st.z, n - nl > 2, rw, rw2, chosen);
       }
+    }
+    if (own) {
+      if (!ROLL || first_step) {
+#pragma unroll
+        for (int k = 0; k < GW_MAX_LEARNERS; ++k)
+          if (k < nl && !act_staged) la |= (uint32_t)min(max((int)(SERVER ? __ldcg(p.io.learner_actions + ea * nl + k) : p.io.learner_actions[ea * nl + k]), 0), 8) << (4 * k);
+      } else {
+        la = la_next;                                                  // fetched while the previous step ran
+      }
+      if (ROLL && !last_step) {                                        // the next step's actions: in flight during this step
+        const long long slot_a1 = (slot_a + 1 >= rp->action_slots) ? 0 : slot_a + 1;
+        const long long ea1 = slot_a1 * p.E + e;
+        la_next = 0;
+#pragma unroll
+        for (int k = 0; k < GW_MAX_LEARNERS; ++k)
+          if (k < nl) la_next |= (uint32_t)min(max((int)p.io.learner_actions[ea1 * nl + k], 0), 8) << (4 * k);
+      }
+      if (p.io.npc_actions != nullptr && r < 4 && r >= nl && r < n)
+        npc_a = (uint32_t)min(max((int)(SERVER ? __ldcg(p.io.npc_actions + ea * n + r) : p.io.npc_actions[ea * n + r]), 0), 8);
     }
     if (SERVER && act_staged) {
       __syncthreads();
@@ -1108,7 +1145,7 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
       uint32_t cells_r = cells_new, apples_r = ro.apples_left, rflags = 0;
       uint4 st_out = make_uint4(cells_new, meta, tick + 1, ((uint32_t)ret0 & 0xFFFFu) | ((uint32_t)ret1 << 16));
       if (ended && p.auto_reset && own) {
-        cells_r = (p.io.spawn != nullptr) ? spawn_cells(p, s.small, e, tick) : cells_from_chosen(p, s.small, chosen);
+        cells_r = (p.io.spawn != nullptr) ? spawn_cells(p, s.small, ea, tick) : cells_from_chosen(p, s.small, chosen);
         const uint32_t meta_sp = fresh_meta(p, cells_r);
         apples_r = meta_sp & M_APPLES;
         rflags = R_FRESH | R_FINAL | (ro.apples_left << 4);
@@ -1118,8 +1155,9 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
       trace_stamp(p, 11);
       // ---- outputs: one lane per array
       const double my_reward = (r == 0) ? ro.reward[0] : ro.reward[1];
+      st_carry = st_out;
       if (r == 0 && own) {
-        p.state[e] = st_out;
+        if (last_step) p.state[e] = st_out;
         s.rinfo[el] = apples_r | rflags;
         s.cells_fin[el] = cells_new;
         v_end = ended ? 1u : 0u; v_len = ended ? steps_now : 0u; v_cr = ro.crash_count; v_ap = ro.apples_rewarded;
@@ -1127,22 +1165,22 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
       }
       if (r < nl && own && p.io.reward) {
         if (SERVER) out_rew[el * nl + r] = (float)my_reward;
-        else p.io.reward[e * nl + r] = (float)my_reward;
+        else p.io.reward[et * nl + r] = (float)my_reward;
       }
-      if (r == 1 && own) write_positions(p.io.positions, e, n, cells_new);
+      if (r == 1 && own) write_positions(p.io.positions, et, n, cells_new);
       if (r == 2 && own && p.io.info)
-        p.io.info[e] = (crash & 15u) | ((restr & 15u) << 4) | (ro.crash_count << 8) | (ro.apples_rewarded << 10) |
+        p.io.info[et] = (crash & 15u) | ((restr & 15u) << 4) | (ro.crash_count << 8) | (ro.apples_rewarded << 10) |
                        ((ended ? 1u : 0u) << 12) | (ro.shaped << 14);
       if (r == 3 && own && p.io.ended) {
         if (SERVER) out_end[el] = ended ? 1 : 0;
-        else p.io.ended[e] = ended ? 1 : 0;
+        else p.io.ended[et] = ended ? 1 : 0;
       }
       if (r >= 4 && r < 4 + nl && own) {
-        if (p.io.terminated) p.io.terminated[e * nl + (r - 4)] = (uint8_t)((ro.term_now >> (r - 4)) & 1u);
-        if (p.io.truncated) p.io.truncated[e * nl + (r - 4)] = (uint8_t)((ro.trunc_now >> (r - 4)) & 1u);
+        if (p.io.terminated) p.io.terminated[et * nl + (r - 4)] = (uint8_t)((ro.term_now >> (r - 4)) & 1u);
+        if (p.io.truncated) p.io.truncated[et * nl + (r - 4)] = (uint8_t)((ro.trunc_now >> (r - 4)) & 1u);
       }
       if (r == 6 && own && p.io.obs_code)
-        p.io.obs_code[e] = (unsigned long long)cells_r | ((unsigned long long)apples_r << 32) |
+        p.io.obs_code[eo] = (unsigned long long)cells_r | ((unsigned long long)apples_r << 32) |
                            ((rflags & R_FRESH) ? (1ull << 34) : 0ull);
 
       trace_stamp(p, 12);
@@ -1165,7 +1203,7 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
         const uint32_t m0 = 1u | (((__ballot_sync(FULL, ok[0]) >> gsh) & 0xFFu) << 1);
         const uint32_t m1 = 1u | (((__ballot_sync(FULL, ok[1]) >> gsh) & 0xFFu) << 1);
         const uint32_t bits = m0 | (m1 << GW_N_ACTIONS);
-        int8_t* dst = p.io.action_mask + e * (long long)(nl * GW_N_ACTIONS);
+        int8_t* dst = p.io.action_mask + eo * (long long)(nl * GW_N_ACTIONS);
         if (own)
           for (int b = r; b < nl * GW_N_ACTIONS; b += 8) dst[b] = (int8_t)((bits >> b) & 1u);
       }
@@ -1260,11 +1298,11 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
       }
       if (r < nl && own) {
         const double f = (r == 0) ? fear0 : fear1;
-        if (p.io.fear) p.io.fear[e * nl + r] = f;
+        if (p.io.fear) p.io.fear[et * nl + r] = f;
         if (p.io.shaped_reward) {
           const float sh = (float)(p.fear_weight * f + my_reward);                                        // maddpg/agent.py:130
           if (SERVER) out_shp[el * nl + r] = sh;
-          else p.io.shaped_reward[e * nl + r] = sh;
+          else p.io.shaped_reward[et * nl + r] = sh;
         }
       }
     }
@@ -1283,7 +1321,7 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
     // ================================================================= observations of the warp's own four envs
     // Every lane drops its special cells into its env's staging row, the four rows (contiguous, like the four
     // observations in HBM) leave as 128-bit streaming stores, and the cells are set back to the template's 0.
-    if (!SERVER && !p.pdl_early && tile + gridDim.x >= n_tiles) asm volatile("griddepcontrol.launch_dependents;");
+    if (!SERVER && !ROLL && !p.pdl_early && tile + gridDim.x >= n_tiles) asm volatile("griddepcontrol.launch_dependents;");
     if (p.io.obs != nullptr) {
       patch_cell<OBS>(myrow, enc0, true);
       patch_cell<OBS>(myrow, enc1, true);
@@ -1291,16 +1329,25 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
       __syncwarp();
       const int n_here = max(0, min(4, tile_envs - warp * 4));
       if (lane == 0 && n_here > 0)                         // four rows, contiguous here and in HBM: one TMA copy
-        bulk_store_row(reinterpret_cast<uint8_t*>(p.io.obs) + (tile_base + warp * 4) * (long long)row_bytes, rows4, n_here * row_bytes);
-      if (p.rng_cache != nullptr && own) {                 // while the copy reads the rows: the next step's random words
+        bulk_store_row(reinterpret_cast<uint8_t*>(p.io.obs) + ((ROLL ? slot_o * p.E : 0) + tile_base + warp * 4) * (long long)row_bytes, rows4, n_here * row_bytes);
+      if ((p.rng_cache != nullptr || (ROLL && !last_step)) && own) {   // while the copy reads the rows: the next step's random words
         uint32_t nrw[4] = {0, 0, 0, 0}, nrw2[4] = {0, 0, 0, 0}, nchosen = 0;
         draw_step_randoms(p, e, st.z + 1, n - nl > 2, nrw, nrw2, nchosen);
-        if (r == 0) {
+        if (r == 0 && last_step && p.rng_cache != nullptr) {
           p.rng_cache[2 * e] = make_uint4(nrw[0], nrw[1], nrw[2], nrw[3]);
           p.rng_cache[2 * e + 1] = make_uint4(nrw2[0], nrw2[1], nchosen, st.z + 1);
         }
+        if (ROLL) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { rw[q] = nrw[q]; rw2[q] = nrw2[q]; }
+          chosen = nchosen;
+        }
       }
-      if (lane == 0 && n_here > 0) bulk_wait_read<0>();
+      if (lane == 0 && n_here > 0) {
+        // a ring shorter than the launch is written twice by this thread: the first copy must have landed, not just been read
+        if (ROLL && rp->wait_full) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        else bulk_wait_read<0>();
+      }
       __syncwarp();
       patch_cell<OBS>(myrow, enc0, false);
       patch_cell<OBS>(myrow, enc1, false);
@@ -1310,7 +1357,7 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
       for (int el4 = warp * 4; el4 < min(tile_envs, warp * 4 + 4); ++el4) {
         const uint32_t ri = s.rinfo[el4];
         if (ri & R_FINAL)
-          stage_and_store_env<OBS>(rows4, p.io.final_obs, tile_base + el4, p.H, n, nl, p.kind, s.cells_fin[el4], (ri >> 4) & 3u,
+          stage_and_store_env<OBS>(rows4, p.io.final_obs, (ROLL ? slot_t * p.E : 0) + tile_base + el4, p.H, n, nl, p.kind, s.cells_fin[el4], (ri >> 4) & 3u,
                                    p.apple_cells, false, lane);
       }
     }
@@ -1342,6 +1389,12 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
     }
     __syncwarp();                                                      // s.spec / s.rinfo of this warp are rewritten by the next tile
     trace_stamp(p, 7);
+    if (ROLL) {
+      st = st_carry;
+      slot_t = slot_o;
+      slot_a = (slot_a + 1 >= rp->action_slots) ? 0 : slot_a + 1;
+    }
+    }                                                                  // steps of this tile
   }
 }
 
@@ -1358,6 +1411,22 @@ __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
   bool tables_pending = true;
   small_step_tiles<FEAR, OBS, false>(p, s, stage, tables_pending);
   if (tables_pending) tables_wait(s);                                  // a CTA without tiles must not exit with copies in flight
+}
+
+// ------------------------------------------------------------------ device-side rollout: T steps per launch (gw_rollout)
+// Envs are independent, so a CTA steps its 32 envs T times with no grid-wide synchronisation: tables and staging rows are
+// loaded once, packed state and random words stay in registers, each step's actions are fetched while the previous step
+// runs, and every step's outputs go to their own slot of the caller's time-major rings (the replay ring's layout).
+template <bool FEAR, int OBS>
+__global__ void __launch_bounds__(256, 2) gw_rollout_kernel(StepParams p, RollParams rp) {
+  constexpr int TILE = 32;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
+  uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
+  load_tables<TILE>(s, stage, p, 32, p.nl * p.H * GW_W * (OBS == GW_OBS_F32 ? 4 : 2));
+  bool tables_pending = true;
+  small_step_tiles<FEAR, OBS, false, true>(p, s, stage, tables_pending, &rp);
+  if (tables_pending) tables_wait(s);
 }
 
 // ------------------------------------------------------------------ resident step server (gw_step_host, mode 2)
@@ -2389,6 +2458,62 @@ int gw_step(gw_handle* h, const gw_io* io, void* stream) {
   GW_CUDA(h, cudaGetLastError());
   h->launches += 1;
   h->env_steps += (uint64_t)h->cfg.num_envs;
+  return GW_OK;
+}
+
+}  // extern "C"
+
+template <typename K>
+static void launch_rollout_k(K kernel, const gw::StepParams& p, const gw::RollParams& rp, unsigned blocks, size_t smem, cudaStream_t s) {
+  static thread_local const void* raised_fn = nullptr;
+  static thread_local size_t raised = 0;
+  if (raised_fn != (const void*)kernel || raised < smem) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    raised_fn = (const void*)kernel;
+    raised = smem;
+  }
+  kernel<<<blocks, 256, smem, s>>>(p, rp);
+}
+
+extern "C" {
+
+int gw_rollout(gw_handle* h, const gw_io* rings, const gw_rollout_plan* plan, void* stream) {
+  if (!h) return GW_EINVAL;
+  if (int rc = server_stop(h)) return rc;
+  if (!plan || plan->struct_size != sizeof(gw_rollout_plan)) return fail(h, GW_EINVAL, "gw_rollout: plan missing or struct_size mismatch");
+  if (int rc = check_io(h, rings, true)) return rc;
+  if (!rings->obs) return fail(h, GW_EINVAL, "gw_rollout: the observation ring is required");
+  if (plan->steps < 1 || plan->ring_slots < 1 || plan->action_slots < 1 || plan->first_slot < 0 || plan->first_slot >= plan->ring_slots ||
+      plan->first_action < 0 || plan->first_action >= plan->action_slots)
+    return fail(h, GW_EINVAL, "gw_rollout: steps >= 1, 0 <= first_slot < ring_slots, 0 <= first_action < action_slots");
+  if (!h->reset_done) return fail(h, GW_ESTATE, "gw_rollout: call gw_reset first");
+  const gw_config& c = h->cfg;
+  // slot strides must keep every slot as aligned as slot 0 (check_io looked at slot 0)
+  const size_t E = (size_t)c.num_envs, L = (size_t)c.n_learners;
+  if ((rings->fear && (E * L * 8) % 16) || (rings->positions && (E * (size_t)c.n_agents * 2) % 8) ||
+      ((rings->terminated || rings->truncated) && (E * L) % 2) || ((rings->reward || rings->shaped_reward) && (E * L * 4) % 8))
+    return fail(h, GW_EINVAL, "gw_rollout: num_envs x n_learners must be even for time-major rings");
+  GW_CUDA(h, use_device(c.device));
+  gw::StepParams p = make_params(h, rings);
+  p.pdl_early = 0;
+  gw::RollParams rp;
+  rp.steps = plan->steps; rp.ring_slots = plan->ring_slots; rp.first_slot = plan->first_slot;
+  rp.action_slots = plan->action_slots; rp.first_action = plan->first_action;
+  rp.wait_full = (long long)plan->steps >= plan->ring_slots ? 1 : 0;
+  const unsigned blocks = (unsigned)((c.num_envs + 31) / 32);      // one tile per CTA: nothing is shared between tiles
+  const size_t smem = gw::smem_fixed_bytes<32>() + (size_t)8 * 4 * gw::stage_row_bytes(c);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool f32 = c.obs_dtype == GW_OBS_F32;
+  if (c.fear) {
+    if (f32) launch_rollout_k(gw::gw_rollout_kernel<true, GW_OBS_F32>, p, rp, blocks, smem, s);
+    else launch_rollout_k(gw::gw_rollout_kernel<true, GW_OBS_BF16>, p, rp, blocks, smem, s);
+  } else {
+    if (f32) launch_rollout_k(gw::gw_rollout_kernel<false, GW_OBS_F32>, p, rp, blocks, smem, s);
+    else launch_rollout_k(gw::gw_rollout_kernel<false, GW_OBS_BF16>, p, rp, blocks, smem, s);
+  }
+  GW_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  h->env_steps += (uint64_t)c.num_envs * (uint64_t)plan->steps;
   return GW_OK;
 }
 
