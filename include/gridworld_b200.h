@@ -310,8 +310,8 @@ int gw_actor_update(gw_actor* a, const gw_actor_weights* weights, int n_learners
 int gw_actor_update_device(gw_actor* a, const gw_actor_weights* dev_weights, int n_learners, void* stream);
 int gw_actor_destroy(gw_actor* a);
 /* obs_code [E] (device, from gw_step / gw_reset); action_mask int8 [E, L, 9] (device, nullable);
- * cont_actions f32 [E, L, 9] and action_ids int8 [E, L] (device outputs).  Noise comes from Philox(seed, env id, learner,
- * step).  training == 1: Gumbel noise of the output activation + Gaussian exploration noise (maddpg/agent.py:109-113,
+ * cont_actions f32 [E, L, 9] and action_ids int8 [E, L] (device outputs).  Noise comes from Philox(seed, GLOBAL env id =
+ * cfg.env_id_base + row, learner, step): a sharded rollout draws what the unsharded one draws.  training == 1: Gumbel noise of the output activation + Gaussian exploration noise (maddpg/agent.py:109-113,
  * training=True); training == 2: Gumbel noise only -- what the reference's evaluation does (customeval.py:90-94,
  * training=False: the GumbelSoftmax activation still samples on every forward); training == 0: plain softmax, no
  * noise (deterministic; tests). */

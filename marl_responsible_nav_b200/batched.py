@@ -67,6 +67,7 @@ class BatchedGridWorld:
         self.n_agents = int(n_agents if n_agents is not None else sc.n_agents)
         self.n_learners = int(n_learners if n_learners is not None else (2 if env_kind == "multi" else 1))
         self.num_envs = int(num_envs)
+        self.env_id_base = int(env_id_base)
         self.H, self.W = sc.shape
         self.obs_len = self.H * self.W
         if obs_dtype not in (torch.float32, torch.bfloat16):

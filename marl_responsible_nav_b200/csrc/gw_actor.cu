@@ -55,6 +55,7 @@ struct FwdArgs {
   float* cont;                           // [E, L, 9]
   int8_t* ids;                           // [E, L]
   long long E;
+  long long env_id_base;                 // global id of row 0: the noise is keyed by the GLOBAL env id (independent of the sharding)
   int rows_per_tile;                      // 128, or 64 (half-full tiles) when the batch is too small to fill the machine
   int n, nl, kind, cpo;
   uint32_t apple_cells;
@@ -278,7 +279,8 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
       const int n_calls = a.explore ? 7 : 3;
       if (er < a.E)
         for (int c = lt % tpr; c < n_calls; c += tpr) {
-          uint32_t w[4] = {(uint32_t)er, (uint32_t)((unsigned long long)er >> 32) ^ ((uint32_t)k << 24) ^ ((uint32_t)c << 28),
+          const unsigned long long ge = (unsigned long long)(a.env_id_base + er);
+          uint32_t w[4] = {(uint32_t)ge, (uint32_t)(ge >> 32) ^ ((uint32_t)k << 24) ^ ((uint32_t)c << 28),
                            a.step_lo, a.step_hi ^ 0xAC70u};
           gw::philox4x32(w, a.seed_lo, a.seed_hi);
 #pragma unroll
@@ -620,6 +622,7 @@ int gw_actor_forward(gw_actor* a, int64_t num_envs, const uint64_t* obs_code, co
   f.cont = cont_actions;
   f.ids = action_ids;
   f.E = num_envs;
+  f.env_id_base = h->cfg.env_id_base;
   f.n = h->cfg.n_agents; f.nl = h->cfg.n_learners; f.kind = h->cfg.env_kind; f.cpo = h->cfg.height * GW_W;
   for (int k = 0; k < h->cfg.n_learners; ++k)
     if (h->cfg.apple_row[k] >= 0) f.apple_cells |= (uint32_t)((h->cfg.apple_row[k] << 4) | h->cfg.apple_col[k]) << (8 * k);

@@ -498,19 +498,33 @@ class BatchedTrainer:
 
     def __init__(self, env, agent: Optional[BatchedMADDPG] = None, hp: Optional[Dict] = None,
                  updates_per_learn: int = 1, seed: int = 0, fused_actor: bool = True, fused_sampler: bool = True, fused_ops: bool = True,
-                 fused_linear_bwd: bool = False):
+                 fused_linear_bwd: bool = False, learn_cadence: str = "reference", global_envs: Optional[int] = None):
+        """learn_cadence: "reference" = the rule of maddpg/agent.py:199-224 applied to the GLOBAL env count (see
+        `learn_schedule`); "batched" = one block of `updates_per_learn` updates every LEARN_STEP vector steps whatever
+        E is (round 1's loop: 1 update per LEARN_STEP * E transitions, a much lower update-to-data ratio than the
+        reference's).  global_envs: environments over all ranks (default: this shard x world size); the schedule and
+        the BATCH_SIZE gate are computed from it so that every rank takes the same decisions."""
         from .replay import ReplayRing
         self.env = env
         self.hp = dict(DEFAULT_HP if hp is None else hp)
+        if learn_cadence not in ("reference", "batched"):
+            raise ValueError("learn_cadence must be 'reference' or 'batched'")
+        self.learn_cadence = learn_cadence
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.global_envs = int(global_envs) if global_envs is not None else env.num_envs * world
+        self.min_shard = self.global_envs // world              # the smallest shard (sharding.shard_range): rank-invariant gate
+        self.updates_done = 0
         self.agent = agent or BatchedMADDPG(env.n_learners, env.obs_len, 9, hp=self.hp, device=env.device, seed=seed)
         self.ring = ReplayRing(env.num_envs, env.n_learners, env.obs_len, self.hp["MEMORY_SIZE"], 9,
                                device=env.device, obs_dtype=env.obs_dtype)
         if fused_ops and env.device.type == "cuda" and self.agent.ops is None:
             self.agent.attach_ops(env, linear_backward=fused_linear_bwd)
         self.updates_per_learn = int(updates_per_learn)
-        self.gen = torch.Generator(device=env.device).manual_seed(seed + 1)
+        self.gen = torch.Generator(device=env.device).manual_seed(seed + 1 + int(getattr(env, "env_id_base", 0)))
         self.fused_sampler = bool(fused_sampler) and env.device.type == "cuda"      # csrc/gw_replay.cu
-        self.sample_seed, self._batch = seed + 1, None
+        # replay draws: every rank samples its own shard, so the draw streams must differ between ranks (the actor's and the
+        # env's noise are keyed by the global env id instead and do not depend on the sharding)
+        self.sample_seed, self._batch = (seed + 1) ^ (int(getattr(env, "env_id_base", 0)) * 0x9E3779B97F4A7C15 & (2 ** 63 - 1)), None
         self.t = 0
         self.out = env.reset(obs_out=self.ring.obs_slot(0))
         self.losses: List[LearnStats] = []
@@ -532,6 +546,19 @@ class BatchedTrainer:
             self._batch = self.ring.new_batch(batch_size)
         return self.ring.sample_fused(self.env, batch_size, seed=self.sample_seed, out=self._batch)
 
+    def learn_schedule(self, t: int) -> int:
+        """Number of updates after vector step `t` (0-based), before the BATCH_SIZE gate.
+        reference (maddpg/agent.py:199-224, num_envs = all environments):
+          LEARN_STEP > num_envs: one update every LEARN_STEP // num_envs steps (:201-213);
+          otherwise num_envs // LEARN_STEP updates after EVERY step (:214-224).
+        batched: `updates_per_learn` updates every LEARN_STEP steps."""
+        ls, E = int(self.hp["LEARN_STEP"]), self.global_envs
+        if self.learn_cadence == "batched":
+            return self.updates_per_learn if t % ls == 0 else 0
+        if ls > E:
+            return 1 if t % (ls // E) == 0 else 0
+        return E // ls
+
     def train(self, env_steps: int, learn: bool = True) -> Dict[str, float]:
         """`env_steps` synchronous steps of all E envs (auto-reset replaces the reference's per-episode outer loop;
         the TRAIN_STEPS cap is the env's max_steps).  Returns the episode statistics gathered meanwhile."""
@@ -551,13 +578,24 @@ class BatchedTrainer:
                                 buffers=ring.buffers_slot(t))
             ring.advance()
             self.t += 1
-            # the reference learns every LEARN_STEP steps of its single env once BATCH_SIZE transitions exist
-            if learn and t % hp["LEARN_STEP"] == 0 and len(ring) >= hp["BATCH_SIZE"]:
-                for _ in range(self.updates_per_learn):
-                    self.losses.append(agent.learn(self._sample(hp["BATCH_SIZE"])))
-                if self.fused is not None:
-                    self.fused.update(agent.actors)          # the kernel keeps its own packed copy of the weights
+            # maddpg/agent.py:199-224: learn once `len(memory) >= BATCH_SIZE`; the count of stored transitions is taken
+            # on the smallest shard so that all ranks start in the same step (their all-reduces pair up)
+            n_upd = self.learn_schedule(t) if learn else 0
+            if n_upd and min(ring.t, ring.T - 1) * self.min_shard >= hp["BATCH_SIZE"]:
+                self._learn_block(n_upd)
         return env.stats()
+
+
+    def _learn_block(self, n_upd: int):
+        """`n_upd` consecutive updates (sample + learn each), then refresh the actor kernel's packed weights."""
+        agent, hp = self.agent, self.hp
+        for _ in range(n_upd):
+            self.losses.append(agent.learn(self._sample(hp["BATCH_SIZE"])))
+            if len(self.losses) > 1024:                      # keep the tail only: the reference cadence makes hundreds per step
+                del self.losses[:512]
+        self.updates_done += n_upd
+        if self.fused is not None:
+            self.fused.update(agent.actors)                  # the kernel keeps its own packed copy of the weights
 
 
 def make_env(hp: Dict, num_envs: int, device="cuda", scenario="Level 3", obs_dtype=torch.float32, seed: Optional[int] = None,

@@ -21,7 +21,10 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="environments over all GPUs")
     ap.add_argument("--steps", type=int, default=1500, help="synchronous env steps (the reference: MAX_EPISODES x TRAIN_STEPS)")
     ap.add_argument("--report", type=int, default=150)
-    ap.add_argument("--updates-per-learn", type=int, default=1)
+    ap.add_argument("--learn-cadence", choices=("reference", "batched"), default="reference",
+                    help="reference: maddpg/agent.py:199-224 on the global env count (envs // LEARN_STEP updates after every "
+                         "vector step); batched: --updates-per-learn updates every LEARN_STEP vector steps")
+    ap.add_argument("--updates-per-learn", type=int, default=1, help="batched cadence only")
     ap.add_argument("--torch-actor", action="store_true", help="act with the PyTorch modules instead of the fused kernel")
     ap.add_argument("--torch-sampler", action="store_true", help="sample the replay ring with PyTorch indexing instead of gw_replay_sample")
     ap.add_argument("--torch-ops", action="store_true", help="LayerNorm + ReLU of the update by PyTorch instead of gw_ln_relu_forward / _backward")
@@ -42,12 +45,14 @@ def main():
         from . import checkpoint
         agent = checkpoint.load_reference_checkpoint(a.load, device=dev, hp=hp)
     trainer = maddpg.BatchedTrainer(env, agent=agent, hp=hp, updates_per_learn=a.updates_per_learn, seed=hp["SEED"],
-                                    fused_actor=not a.torch_actor, fused_sampler=not a.torch_sampler, fused_ops=not a.torch_ops)
+                                    fused_actor=not a.torch_actor, fused_sampler=not a.torch_sampler, fused_ops=not a.torch_ops,
+                                    learn_cadence=a.learn_cadence, global_envs=a.envs)
     trainer.agent.broadcast_parameters(0)
     done = 0
     while done < a.steps:
         k = min(a.report, a.steps - done)
         torch.cuda.synchronize()
+        upd0 = trainer.updates_done
         t0 = time.perf_counter()
         st = trainer.train(k)
         torch.cuda.synchronize()
@@ -60,7 +65,8 @@ def main():
             print(json.dumps({"env_steps": done, "agent_steps_per_s": st["agent_steps"] / el, "episodes": st["episodes"],
                               "mean_return": st["return_sum"] / eps, "mean_len": st["episode_len_sum"] / eps,
                               "crashes_per_episode": st["crashes"] / eps, "apples_per_episode": st["apples"] / eps,
-                              "fear_sum": st["fear_sum"],
+                              "fear_sum": st["fear_sum"], "updates": trainer.updates_done,
+                              "updates_per_s": (trainer.updates_done - upd0) / el,
                               "critic_loss": None if last is None else float(last.critic_loss.sum()),
                               "actor_loss": None if last is None else float(last.actor_loss.sum())}), flush=True)
     if a.save and rank == 0:

@@ -14,7 +14,7 @@ hp = maddpg.preset("custom_fear_10")
 env = maddpg.make_env(hp, 4096)
 res = {}
 for name, kw in (("default", {}), ("fused_linear_bwd", {"fused_linear_bwd": True}), ("torch_ops", {"fused_ops": False})):
-    tr = maddpg.BatchedTrainer(env, hp=hp, seed=0, **kw)
+    tr = maddpg.BatchedTrainer(env, hp=hp, seed=0, learn_cadence="batched", **kw)
     tr.train(200)                                        # graph captured, ring filled
     ag = tr.agent
     torch.cuda.synchronize()

@@ -259,3 +259,24 @@ def test_host_side_of_the_fused_update_paths_on_cpu():
     ring.advance()
     with pytest.raises(RuntimeError, match="no CPU path"):
         ring.sample_fused(None, 8)
+
+
+def test_learn_schedule_follows_the_reference_cadence():
+    """maddpg/agent.py:199-224: LEARN_STEP > num_envs -> one update every LEARN_STEP // num_envs steps; otherwise
+    num_envs // LEARN_STEP updates after every step.  `batched` is round 1's rule (a block every LEARN_STEP steps)."""
+    from types import SimpleNamespace
+    sched = maddpg.BatchedTrainer.learn_schedule
+
+    def counts(E, ls, steps, cadence="reference", upl=1):
+        tr = SimpleNamespace(hp={"LEARN_STEP": ls}, global_envs=E, learn_cadence=cadence, updates_per_learn=upl)
+        return [sched(tr, t) for t in range(steps)]
+
+    assert counts(1, 10, 21) == [1 if t % 10 == 0 else 0 for t in range(21)]          # the reference's own run: num_envs = 1
+    assert counts(4, 10, 6) == [1 if t % 2 == 0 else 0 for t in range(6)]             # 10 // 4 = 2
+    assert counts(10, 10, 3) == [1, 1, 1]                                               # not (LEARN_STEP > num_envs): 10 // 10
+    assert counts(4096, 10, 3) == [409, 409, 409]
+    assert counts(4096, 10, 21, "batched", 3) == [3 if t % 10 == 0 else 0 for t in range(21)]
+    # update-to-data ratio of the reference rule: one update per ~LEARN_STEP transitions whatever E is
+    for E in (1, 4, 64, 4096):
+        n = sum(counts(E, 10, 200))
+        assert abs(n / (200 * E) - 0.1) < 0.03
