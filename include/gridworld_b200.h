@@ -288,6 +288,77 @@ int gw_linear_backward(gw_handle* h, int32_t batch, int32_t in_features, int32_t
                        const float* x, int32_t x_row_stride, const float* w, float* dw, float* db, float* dx,
                        void* stream);
 
+/* ---- fused MADDPG update: `agent.learn(experiences)` as called at maddpg/agent.py:209-213, :218-224 --------
+ * One persistent cooperative kernel runs whole updates: (optionally) draw + gather the batch from the replay ring, target
+ * actors, TD target, critic forward / backward, Adam, the actor loss through the updated critic, actor backward, Adam,
+ * soft target update (TAU) -- for all agents, `updates` times per launch (the reference learns num_envs // LEARN_STEP
+ * times after every env step, maddpg/agent.py:214-224).  Networks: the reference's shapes: actor
+ * Linear(obs_len,128)-LayerNorm-ReLU-Linear(128,128)-LayerNorm-ReLU-Linear(128,action_dim)-GumbelSoftmax, critic
+ * Linear(n*(obs_len+action_dim),128)-LN-ReLU-Linear(128,128)-LN-ReLU-Linear(128,1).  fp32 FMA arithmetic throughout
+ * (the reference trains in fp32; the update is latency-bound, not FLOP-bound: 0.23 GFLOP per update).
+ * All buffers are caller-owned DEVICE memory (PyTorch tensors); parameters live in flat fp32 vectors in which every
+ * network is one block in torch parameter order (w1,b1,ln1_g,ln1_b,w2,b2,ln2_g,ln2_b,w3,b3), actors first, then critics,
+ * each block starting at a multiple of 4 floats -- the nn.Parameters of the Python twin are views into them. */
+typedef struct gw_learner_config {
+  uint32_t struct_size;          /* sizeof(gw_learner_config) */
+  int32_t n_agents;              /* 1..GW_MAX_LEARNERS */
+  int32_t obs_len;               /* H*W, a multiple of 16 */
+  int32_t action_dim;            /* 9 */
+  int32_t batch;                 /* BATCH_SIZE: a multiple of 32, <= 512 */
+  float lr_actor, lr_critic;     /* LR_ACTOR, LR_CRITIC (Adam, betas / eps below) */
+  float gamma, tau;              /* GAMMA, TAU */
+  float beta1, beta2, adam_eps;  /* 0.9, 0.999, 1e-8 */
+  float ln_eps;                  /* 1e-5 */
+  uint64_t seed;                 /* Gumbel noise of the actors' output activation: Philox(seed; row, agent, update) */
+} gw_learner_config;
+
+typedef struct gw_learner_layout {
+  uint32_t struct_size;          /* sizeof(gw_learner_layout) */
+  int32_t n_nets;                /* 2 * n_agents: actors 0..n-1, critics n..2n-1 */
+  int64_t net_offset[2 * GW_MAX_LEARNERS];   /* floats, into every parameter-shaped vector */
+  int64_t net_params[2 * GW_MAX_LEARNERS];   /* 38 793 / 60 545 for the reference's shapes */
+  int64_t param_floats;          /* length of params / targets / adam_m / adam_v / grads */
+  int64_t scratch_bytes;         /* activations, partial sums, batch staging, grid barrier */
+} gw_learner_layout;
+
+typedef struct gw_learner_buffers {
+  float* params;                 /* [param_floats] online networks */
+  float* targets;                /* [param_floats] target networks */
+  float* adam_m;                 /* [param_floats] exp_avg */
+  float* adam_v;                 /* [param_floats] exp_avg_sq */
+  float* grads;                  /* [param_floats] gradients of the last update (what a data-parallel run all-reduces) */
+  float* adam_steps;             /* [n_nets] f32 step counters (torch.optim.Adam(capturable=True) keeps the same) */
+  void* scratch;                 /* [scratch_bytes], 256-byte aligned, zero-filled once by the caller */
+} gw_learner_buffers;
+
+/* an explicit batch (device, f32, contiguous): state / next_state [B, n, obs_len], action [B, n, action_dim], reward / done
+ * [B, n].  gumbel_next / gumbel_cur [B, n, action_dim], nullable: Gumbel noise g (already -log(-log u)) added to the logits
+ * of the target actors (on next_state) / the actors (on state) instead of the kernel's own Philox draws (tests). */
+typedef struct gw_learn_batch {
+  const float* state; const float* action; const float* reward; const float* next_state; const float* done;
+  const float* gumbel_next; const float* gumbel_cur;
+} gw_learn_batch;
+
+typedef struct gw_learner gw_learner;
+#define GW_LEARN_ALL 0           /* the whole update */
+#define GW_LEARN_CRITIC_GRADS 1  /* data-parallel runs: up to the critics' gradients (in `grads`) ... all-reduce them ... */
+#define GW_LEARN_ACTOR_GRADS 2   /* ... critic Adam steps, actor loss, up to the actors' gradients ... all-reduce ... */
+#define GW_LEARN_FINISH 3        /* ... actor Adam steps, soft updates */
+int gw_learner_layout_of(const gw_learner_config* cfg, gw_learner_layout* out);   /* host arithmetic only */
+int gw_learner_create(gw_handle* h, const gw_learner_config* cfg, const gw_learner_buffers* buf, gw_learner** out);
+int gw_learner_destroy(gw_learner* l);
+/* `updates` consecutive updates in one launch.  Exactly one of `batch` (updates must be 1) and `ring` is given; with
+ * `ring` update u draws its batch like gw_replay_sample(seed = sample_seed, draw = draw_base + u) and gathers it inside
+ * the kernel.  segment: GW_LEARN_ALL, or one of the three pieces of a data-parallel update (updates must be 1; grads are
+ * multiplied by grad_scale -- 1 / world size after a SUM all-reduce -- when they are applied).  losses: device f32
+ * [updates, 2, n_agents] (actor loss, critic loss per agent), nullable.  Stream-ordered, no synchronisation, capturable. */
+int gw_learner_update(gw_learner* l, const gw_learn_batch* batch, const gw_replay_view* ring, int64_t t_now,
+                      uint64_t sample_seed, uint64_t draw_base, int32_t updates, int32_t segment, float grad_scale,
+                      float* losses, void* stream);
+/* intermediate tensors of the last update, by name (tests / debugging): "a2", "q", "y", "dq", "anew", "ax", "dz2", "dh1",
+ * "dz1", "adz2", "adh1", "adz1", and "<pass>.<z1|h1|st1|z2|h2|st2>" with pass in ta / ct / c / ac / c2; index = agent */
+int gw_learner_debug_ptr(gw_learner* l, const char* name, int index, float** ptr, int64_t* floats);
+
 /* ---- actor forward (K5): AgileRL `MADDPG.get_action` as called at maddpg/agent.py:109-113 -----------------------
  * One actor per learner: Linear(H*W,128)-LayerNorm-ReLU-Linear(128,128)-LayerNorm-ReLU-Linear(128,9)-GumbelSoftmax
  * (shapes from the reference's checkpoints), Gaussian exploration noise, clip to [0,1], action mask,

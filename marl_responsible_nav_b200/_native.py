@@ -13,7 +13,8 @@ GW_OBS_F32, GW_OBS_BF16 = 0, 1
 EXPORTS = ["gw_abi_version", "gw_build_info", "gw_default_config", "gw_create", "gw_destroy", "gw_last_error",
            "gw_reset", "gw_step", "gw_rollout", "gw_step_host", "gw_host_call_prepare", "gw_host_call_run", "gw_host_call_reset", "gw_server_stop", "gw_server_info", "gw_sync", "gw_state_bytes", "gw_get_state", "gw_set_state", "gw_get_stats",
            "gw_reset_stats", "gw_launch_count", "gw_update_world", "gw_fear_one_actor", "gw_fear_matrix", "gw_feal", "gw_actor_create", "gw_actor_update", "gw_actor_update_device",
-           "gw_actor_destroy", "gw_actor_forward", "gw_replay_sample", "gw_ln_relu_forward", "gw_ln_relu_backward", "gw_linear_backward"]
+           "gw_actor_destroy", "gw_actor_forward", "gw_replay_sample", "gw_ln_relu_forward", "gw_ln_relu_backward", "gw_linear_backward",
+           "gw_learner_layout_of", "gw_learner_create", "gw_learner_destroy", "gw_learner_update", "gw_learner_debug_ptr"]
 
 
 class GwActorWeights(C.Structure):
@@ -25,6 +26,29 @@ class GwReplayView(C.Structure):
                 ("n_learners", C.c_int32), ("obs_len", C.c_int32), ("action_dim", C.c_int32), ("pad_", C.c_int32),
                 ("obs", C.c_void_p), ("final_obs", C.c_void_p), ("action", C.c_void_p), ("reward", C.c_void_p),
                 ("terminated", C.c_void_p), ("ended", C.c_void_p)]
+
+
+class GwLearnerConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("n_agents", C.c_int32), ("obs_len", C.c_int32), ("action_dim", C.c_int32),
+                ("batch", C.c_int32), ("lr_actor", C.c_float), ("lr_critic", C.c_float), ("gamma", C.c_float),
+                ("tau", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
+                ("ln_eps", C.c_float), ("seed", C.c_uint64)]
+
+
+class GwLearnerLayout(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("n_nets", C.c_int32), ("net_offset", C.c_int64 * (2 * GW_MAX_LEARNERS)),
+                ("net_params", C.c_int64 * (2 * GW_MAX_LEARNERS)), ("param_floats", C.c_int64), ("scratch_bytes", C.c_int64)]
+
+
+class GwLearnerBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("params", "targets", "adam_m", "adam_v", "grads", "adam_steps", "scratch")]
+
+
+class GwLearnBatch(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("state", "action", "reward", "next_state", "done", "gumbel_next", "gumbel_cur")]
+
+
+GW_LEARN_ALL, GW_LEARN_CRITIC_GRADS, GW_LEARN_ACTOR_GRADS, GW_LEARN_FINISH = 0, 1, 2, 3
 
 
 class GwConfig(C.Structure):
@@ -113,6 +137,12 @@ def load():
     lib.gw_ln_relu_forward.argtypes = [vp, i64, C.c_int32, vp, vp, vp, C.c_float, vp, vp, vp, vp]
     lib.gw_ln_relu_backward.argtypes = [vp, i64, C.c_int32] + [vp] * 9 + [vp]
     lib.gw_linear_backward.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_int32, vp, vp, vp, vp, vp]
+    lib.gw_learner_layout_of.argtypes = [C.POINTER(GwLearnerConfig), C.POINTER(GwLearnerLayout)]
+    lib.gw_learner_create.argtypes = [vp, C.POINTER(GwLearnerConfig), C.POINTER(GwLearnerBuffers), C.POINTER(vp)]
+    lib.gw_learner_destroy.argtypes = [vp]
+    lib.gw_learner_update.argtypes = [vp, C.POINTER(GwLearnBatch), C.POINTER(GwReplayView), i64, C.c_uint64, C.c_uint64,
+                                      C.c_int32, C.c_int32, C.c_float, vp, vp]
+    lib.gw_learner_debug_ptr.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(vp), C.POINTER(i64)]
     if lib.gw_abi_version() != 1:
         raise RuntimeError("libgridworld_b200.so ABI version mismatch")
     _lib = lib

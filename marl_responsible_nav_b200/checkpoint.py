@@ -121,6 +121,8 @@ def load_reference_checkpoint(path: str, device="cuda", hp: Optional[Dict] = Non
 def save_reference_checkpoint(agent: maddpg.BatchedMADDPG, path: str, steps: Optional[List[int]] = None) -> None:
     """Write `agent` as the dict AgileRL's `MADDPG.load_checkpoint` (maddpg/agent.py:271-283) expects."""
     n, hp = agent.n, agent.hp
+    if getattr(agent, "learner", None) is not None:
+        agent.learner.export_steps()                                 # the kernel counts Adam steps per network
     hidden = [m.out_features for m in agent.actors[0] if isinstance(m, nn.Linear)][:-1]
     crit_in = n * (agent.obs_dim + agent.act_dim)
     noise = lambda v: [np.full((1, agent.act_dim), float(v)) for _ in range(n)]

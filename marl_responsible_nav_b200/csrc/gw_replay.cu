@@ -10,9 +10,7 @@
 // number), the warp copies the two 1 280-byte observation rows with 128-bit loads / stores and the short fields with
 // one lane each.  A batch of 128 moves 0.35 MB: the kernel is launch-bound (a few microseconds) and replaces the ~25
 // indexing kernels of the PyTorch formulation.
-#include <cuda_bf16.h>
-
-#include "gw_internal.h"
+#include "gw_replay_dev.cuh"
 
 namespace {
 
@@ -28,43 +26,6 @@ struct SampleArgs {
   long long* t_out; long long* env_out;
 };
 
-__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-
-// n elements of one observation row -> f32
-template <typename T>
-__device__ __forceinline__ void copy_row(const T* __restrict__ src, float* __restrict__ dst, int n, int lane, bool vec);
-
-template <>
-__device__ __forceinline__ void copy_row<float>(const float* __restrict__ src, float* __restrict__ dst, int n, int lane,
-                                                bool vec) {
-  if (vec) {
-    for (int i = lane * 4; i < n; i += 128) *reinterpret_cast<float4*>(dst + i) = load4(src + i);
-  } else {
-    for (int i = lane; i < n; i += 32) dst[i] = src[i];
-  }
-}
-
-template <>
-__device__ __forceinline__ void copy_row<__nv_bfloat16>(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
-                                                        int n, int lane, bool vec) {
-  if (vec) {
-    for (int i = lane * 8; i < n; i += 256) {
-      const uint4 v = *reinterpret_cast<const uint4*>(src + i);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {                      // bf16 -> f32 is a 16-bit shift
-        o[2 * j] = __uint_as_float(w[j] << 16);
-        o[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
-      }
-      *reinterpret_cast<float4*>(dst + i) = make_float4(o[0], o[1], o[2], o[3]);
-      *reinterpret_cast<float4*>(dst + i + 4) = make_float4(o[4], o[5], o[6], o[7]);
-    }
-  } else {
-    for (int i = lane; i < n; i += 32) dst[i] = __bfloat162float(src[i]);
-  }
-}
-
 template <typename T>
 __global__ void __launch_bounds__(128) gw_replay_sample_kernel(const SampleArgs a, const bool vec) {
   const int lane = threadIdx.x & 31;
@@ -77,13 +38,7 @@ __global__ void __launch_bounds__(128) gw_replay_sample_kernel(const SampleArgs 
       t_abs = a.t_in[b];
       e = a.env_in[b];
     } else {
-      uint32_t c[4] = {(uint32_t)b, (uint32_t)(b >> 32), (uint32_t)a.draw, (uint32_t)(a.draw >> 32)};
-      gw::philox4x32(c, a.k0, a.k1);
-      // 64-bit words scaled to the range (multiply-high): bias < range / 2^64
-      const unsigned long long u0 = ((unsigned long long)c[0] << 32) | c[1], u1 = ((unsigned long long)c[2] << 32) | c[3];
-      const long long k = (long long)__umul64hi(u0, (unsigned long long)a.n_valid);
-      e = (long long)__umul64hi(u1, (unsigned long long)r.num_envs);
-      t_abs = a.t_now - 1 - k;                           // the newest n_valid time steps are stored
+      gwr::draw_index(b, a.draw, a.k0, a.k1, a.t_now, a.n_valid, r.num_envs, t_abs, e);
     }
   }
   t_abs = __shfl_sync(0xffffffffu, t_abs, 0);
@@ -98,8 +53,8 @@ __global__ void __launch_bounds__(128) gw_replay_sample_kernel(const SampleArgs 
   const bool ended = r.ended[row] != 0;
   const T* obs = static_cast<const T*>(r.obs);
   const T* fin = static_cast<const T*>(r.final_obs);
-  copy_row<T>(obs + row * n_obs, a.state + b * n_obs, n_obs, lane, vec);
-  copy_row<T>(ended ? fin + row * n_obs : obs + row1 * n_obs, a.next_state + b * n_obs, n_obs, lane, vec);
+  gwr::copy_row<T>(obs + row * n_obs, a.state + b * n_obs, n_obs, lane, vec);
+  gwr::copy_row<T>(ended ? fin + row * n_obs : obs + row1 * n_obs, a.next_state + b * n_obs, n_obs, lane, vec);
   for (int i = lane; i < n_act; i += 32) a.action[b * n_act + i] = r.action[row * n_act + i];
   if (lane < L) {
     a.reward[b * L + lane] = r.reward[row * L + lane];
@@ -139,7 +94,7 @@ extern "C" int gw_replay_sample(gw_handle* h, const gw_replay_view* ring, int64_
   SampleArgs a;
   a.ring = r;
   a.t_now = t_now; a.n_valid = n_valid; a.batch = batch;
-  a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32) ^ 0x52455053u;   // "REPS": own key space next to the env's streams
+  gwr::sample_key(seed, a.k0, a.k1);
   a.draw = draw;
   a.t_in = reinterpret_cast<const long long*>(t_in); a.env_in = reinterpret_cast<const long long*>(env_in);
   a.state = state; a.action = action; a.reward = reward; a.next_state = next_state; a.done = done;

@@ -212,6 +212,15 @@ class BatchedMADDPG:
         self._side_streams: Dict[object, List[torch.cuda.Stream]] = {}
         self.ops: Optional[TrainOps] = None                # fused LayerNorm+ReLU kernels of the library (attach_ops)
         self.force_segmented = False                       # tests: take the multi-rank path in a one-rank process group
+        self.learner = None                                # FusedLearner (learner.py): the update as one kernel, see attach_learner
+
+    def attach_learner(self, env, seed: int = 0):
+        """Run every update through gw_learner_update (csrc/gw_maddpg.cu).  The parameters of the modules and the moments
+        of the optimisers become views into the learner's flat vectors; `learn` routes there from now on."""
+        from .learner import FusedLearner
+        self.learner = FusedLearner(env, self, seed=seed)
+        self._graph, self._segments, self._eager_learns = None, None, 0
+        return self.learner
 
     def attach_ops(self, env, linear_backward: bool = False):
         """Run the update's LayerNorm + ReLU pairs through the library's kernels (`env` provides handle and stream);
@@ -253,6 +262,9 @@ class BatchedMADDPG:
         ~250 small kernels, 6 ms of launches in eager mode) is captured into one CUDA graph after three eager calls
         and replayed from then on; with several ranks it is a chain of graphs cut at the gradient all-reduces."""
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if self.learner is not None and not multi:         # one kernel launch (several ranks: FusedLearner.learn_from_ring)
+            last = self.learner.learn(batch)[0].clone()
+            return LearnStats(last[0], last[1])
         if not graph or self.device.type != "cuda":
             return self._learn(batch)
         if multi or self.force_segmented:
@@ -498,12 +510,15 @@ class BatchedTrainer:
 
     def __init__(self, env, agent: Optional[BatchedMADDPG] = None, hp: Optional[Dict] = None,
                  updates_per_learn: int = 1, seed: int = 0, fused_actor: bool = True, fused_sampler: bool = True, fused_ops: bool = True,
-                 fused_linear_bwd: bool = False, learn_cadence: str = "reference", global_envs: Optional[int] = None):
+                 fused_linear_bwd: bool = False, learn_cadence: str = "reference", global_envs: Optional[int] = None,
+                 fused_learner: bool = True):
         """learn_cadence: "reference" = the rule of maddpg/agent.py:199-224 applied to the GLOBAL env count (see
         `learn_schedule`); "batched" = one block of `updates_per_learn` updates every LEARN_STEP vector steps whatever
         E is (round 1's loop: 1 update per LEARN_STEP * E transitions, a much lower update-to-data ratio than the
         reference's).  global_envs: environments over all ranks (default: this shard x world size); the schedule and
-        the BATCH_SIZE gate are computed from it so that every rank takes the same decisions."""
+        the BATCH_SIZE gate are computed from it so that every rank takes the same decisions.
+        fused_learner: the update as ONE kernel that also draws its batches from the ring (learner.py, csrc/gw_maddpg.cu);
+        off = round 1's CUDA graph of PyTorch / library kernels (fused_sampler / fused_ops choose its pieces)."""
         from .replay import ReplayRing
         self.env = env
         self.hp = dict(DEFAULT_HP if hp is None else hp)
@@ -517,7 +532,10 @@ class BatchedTrainer:
         self.agent = agent or BatchedMADDPG(env.n_learners, env.obs_len, 9, hp=self.hp, device=env.device, seed=seed)
         self.ring = ReplayRing(env.num_envs, env.n_learners, env.obs_len, self.hp["MEMORY_SIZE"], 9,
                                device=env.device, obs_dtype=env.obs_dtype)
-        if fused_ops and env.device.type == "cuda" and self.agent.ops is None:
+        self.learner = None
+        if fused_learner and env.device.type == "cuda":
+            self.learner = self.agent.learner if self.agent.learner is not None else self.agent.attach_learner(env, seed=seed + 3)
+        elif fused_ops and env.device.type == "cuda" and self.agent.ops is None:
             self.agent.attach_ops(env, linear_backward=fused_linear_bwd)
         self.updates_per_learn = int(updates_per_learn)
         self.gen = torch.Generator(device=env.device).manual_seed(seed + 1 + int(getattr(env, "env_id_base", 0)))
@@ -589,10 +607,14 @@ class BatchedTrainer:
     def _learn_block(self, n_upd: int):
         """`n_upd` consecutive updates (sample + learn each), then refresh the actor kernel's packed weights."""
         agent, hp = self.agent, self.hp
-        for _ in range(n_upd):
-            self.losses.append(agent.learn(self._sample(hp["BATCH_SIZE"])))
-            if len(self.losses) > 1024:                      # keep the tail only: the reference cadence makes hundreds per step
-                del self.losses[:512]
+        if self.learner is not None:                         # one launch for the whole block (csrc/gw_maddpg.cu)
+            last = self.learner.learn_from_ring(self.ring, n_upd, self.sample_seed)[n_upd - 1].clone()
+            self.losses.append(LearnStats(last[0], last[1]))
+        else:
+            for _ in range(n_upd):
+                self.losses.append(agent.learn(self._sample(hp["BATCH_SIZE"])))
+        if len(self.losses) > 1024:                          # keep the tail only: the reference cadence makes hundreds per step
+            del self.losses[:512]
         self.updates_done += n_upd
         if self.fused is not None:
             self.fused.update(agent.actors)                  # the kernel keeps its own packed copy of the weights
