@@ -355,6 +355,16 @@ int gw_learner_destroy(gw_learner* l);
 int gw_learner_update(gw_learner* l, const gw_learn_batch* batch, const gw_replay_view* ring, int64_t t_now,
                       uint64_t sample_seed, uint64_t draw_base, int32_t updates, int32_t segment, float grad_scale,
                       float* losses, void* stream);
+/* Two implementations of the same update: GW_LEARN_KERNEL_PHASE (csrc/gw_maddpg.cu: one CTA per SM, a grid barrier
+ * between the ~19 steps, fp32 FMA, every supported shape) and GW_LEARN_KERNEL_CLUSTER (csrc/gw_maddpg_cluster.cu: clusters
+ * of 4 CTAs carry 16 batch rows through a whole forward / backward chain over distributed shared memory, 3xTF32 tensor-core
+ * tiles, four grid barriers per update; the reference's shape only: 2 learners, obs_len 160, batch % 16 == 0, batch <= 256 on
+ * a B200).  AUTO = cluster where possible.  gw_learner_kernel returns the kind the next update will run. */
+#define GW_LEARN_KERNEL_AUTO 0
+#define GW_LEARN_KERNEL_PHASE 1
+#define GW_LEARN_KERNEL_CLUSTER 2
+int gw_learner_set_kernel(gw_learner* l, int32_t kind);
+int gw_learner_kernel(const gw_learner* l);
 /* intermediate tensors of the last update, by name (tests / debugging): "a2", "q", "y", "dq", "anew", "ax", "dz2", "dh1",
  * "dz1", "adz2", "adh1", "adz1", and "<pass>.<z1|h1|st1|z2|h2|st2>" with pass in ta / ct / c / ac / c2; index = agent */
 int gw_learner_debug_ptr(gw_learner* l, const char* name, int index, float** ptr, int64_t* floats);

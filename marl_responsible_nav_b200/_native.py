@@ -14,7 +14,7 @@ EXPORTS = ["gw_abi_version", "gw_build_info", "gw_default_config", "gw_create", 
            "gw_reset", "gw_step", "gw_rollout", "gw_step_host", "gw_host_call_prepare", "gw_host_call_run", "gw_host_call_reset", "gw_server_stop", "gw_server_info", "gw_sync", "gw_state_bytes", "gw_get_state", "gw_set_state", "gw_get_stats",
            "gw_reset_stats", "gw_launch_count", "gw_update_world", "gw_fear_one_actor", "gw_fear_matrix", "gw_feal", "gw_actor_create", "gw_actor_update", "gw_actor_update_device",
            "gw_actor_destroy", "gw_actor_forward", "gw_replay_sample", "gw_ln_relu_forward", "gw_ln_relu_backward", "gw_linear_backward",
-           "gw_learner_layout_of", "gw_learner_create", "gw_learner_destroy", "gw_learner_update", "gw_learner_debug_ptr"]
+           "gw_learner_layout_of", "gw_learner_create", "gw_learner_destroy", "gw_learner_update", "gw_learner_debug_ptr", "gw_learner_set_kernel", "gw_learner_kernel"]
 
 
 class GwActorWeights(C.Structure):
@@ -49,6 +49,7 @@ class GwLearnBatch(C.Structure):
 
 
 GW_LEARN_ALL, GW_LEARN_CRITIC_GRADS, GW_LEARN_ACTOR_GRADS, GW_LEARN_FINISH = 0, 1, 2, 3
+GW_LEARN_KERNEL_AUTO, GW_LEARN_KERNEL_PHASE, GW_LEARN_KERNEL_CLUSTER = 0, 1, 2
 
 
 class GwConfig(C.Structure):
@@ -142,6 +143,8 @@ def load():
     lib.gw_learner_destroy.argtypes = [vp]
     lib.gw_learner_update.argtypes = [vp, C.POINTER(GwLearnBatch), C.POINTER(GwReplayView), i64, C.c_uint64, C.c_uint64,
                                       C.c_int32, C.c_int32, C.c_float, vp, vp]
+    lib.gw_learner_set_kernel.argtypes = [vp, C.c_int32]
+    lib.gw_learner_kernel.argtypes = [vp]
     lib.gw_learner_debug_ptr.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(vp), C.POINTER(i64)]
     if lib.gw_abi_version() != 1:
         raise RuntimeError("libgridworld_b200.so ABI version mismatch")

@@ -23,128 +23,16 @@
 //                 as per-CTA partial sums that the Adam phase adds in a fixed order (deterministic, no atomics).
 //   Adam phases   element-wise over the flat parameter vectors: gradient (matrix gradients from the GEMM phases, vector
 //                 gradients from the partial sums), Adam step (torch.optim.Adam arithmetic), soft update of the target.
-#include <cstring>
-#include <map>
-#include <string>
-
-#include "gw_replay_dev.cuh"
+#include "gw_maddpg.cuh"
 
 namespace gwl {
 
-constexpr int HID = 128;
-constexpr int THREADS = 256;
-constexpr int WARPS = THREADS / 32;
 constexpr int TM = 32, TN = 32;
 constexpr int RED_LD = 36;                 // reduction tile row stride: conflict-free for all three thread mappings
-constexpr int MAXN = GW_MAX_LEARNERS;
-constexpr int NA = GW_N_ACTIONS;           // action_dim: compile-time, the row phases keep per-action values in registers
 constexpr int RB = WARPS;                  // rows per row-phase task (one per warp)
 constexpr int MAX_SLOTS = 12;              // 128-wide partial-sum vectors per row task (actor backward: 9 + 3)
 static_assert(GW_N_ACTIONS + 3 <= MAX_SLOTS && GW_N_ACTIONS <= 16, "partial-sum slots");
 
-struct NetLayout {                         // offsets (floats) inside one network's block; ln gamma = b + HID, beta = b + 2 HID
-  int in, out, w1, b1, w2, b2, w3, b3, total, small;
-};
-__host__ __device__ inline NetLayout make_layout(int in, int out) {
-  NetLayout L;
-  L.in = in; L.out = out;
-  L.w1 = 0; L.b1 = HID * in;
-  L.w2 = L.b1 + 3 * HID; L.b2 = L.w2 + HID * HID;
-  L.w3 = L.b2 + 3 * HID; L.b3 = L.w3 + out * HID;
-  L.total = L.b3 + out;
-  L.small = 6 * HID + out * (HID + 1);     // compact index space of the vector parameters: [b1 g1 be1 | b2 g2 be2 | w3 b3]
-  return L;
-}
-__device__ __forceinline__ int compact_index(const NetLayout& L, int idx) {   // -1: a matrix element (w1 / w2)
-  if (idx >= L.w3) return 6 * HID + (idx - L.w3);
-  if (idx >= L.b2) return 3 * HID + (idx - L.b2);
-  if (idx >= L.w2) return -1;
-  if (idx >= L.b1) return idx - L.b1;
-  return -1;
-}
-
-struct Pass { float *z1, *h1, *st1, *z2, *h2, *st2; };   // one forward pass of one network: [B,H] x4, statistics [B,2] x2
-
-struct Scratch {
-  float *S, *S2, *ACT, *R, *D;               // the gathered batch (fused sampling)
-  Pass ta[MAXN], ct[MAXN], c[MAXN], ac[MAXN], c2[MAXN];
-  float* a2;                                 // [B, n*A] target actors' actions on next_state
-  float *anew[MAXN], *ax[MAXN];              // [B, A] actor i on state; [B, n*A] batch actions with block i replaced
-  float *q[MAXN], *y[MAXN], *dq[MAXN];       // [B]
-  float *dz2[MAXN], *dh1[MAXN], *dz1[MAXN];  // critic backward (TD pass, then the actor-loss pass)
-  float *adz2[MAXN], *adh1[MAXN], *adz1[MAXN];
-  float* pb[2 * MAXN];                       // [B / RB][small] partial sums per network
-  float* lp;                                 // [2n][B / RB] loss partial sums (critics, then actors)
-  unsigned* bar;                             // grid barrier: arrivals, generation
-};
-
-enum { ADAM_FROM_G = 1, ADAM_WRITE_G = 2, ADAM_APPLY = 4 };   // vector gradients already in G / store gradients in G / step
-
-enum Phase {
-  PH_GATHER = 0, PH_L1, PH_L2, PH_HEADS, PH_CT_L2, PH_TD, PH_C_BWD2, PH_C_LN1, PH_C_DW1, PH_ADAM_C,
-  PH_C2_L1, PH_C2_L2, PH_ALOSS, PH_C2_DH1, PH_ACT_BWD, PH_A_BWD2, PH_A_LN1, PH_A_DW1, PH_ADAM_A, PH_COUNT
-};
-
-struct LearnArgs {
-  int n, O, A, B, CI, SO, SA;                // agents, obs_len, action_dim, batch, critic input, n*O, n*A
-  NetLayout la, lc;
-  long long net_off[2 * MAXN];
-  float *P, *T, *M, *V, *G, *steps;
-  Scratch s;
-  const float *bS, *bS2, *bACT, *bR, *bD;    // the batch the update reads (the staging above or the caller's tensors)
-  const float *gum_next, *gum_cur;
-  gw_replay_view ring;
-  int sample;
-  long long t_now, n_valid;
-  uint32_t rk0, rk1, gk0, gk1;
-  unsigned long long draw_base, upd_base;
-  int updates, ph_begin, ph_end;
-  int adam_mode[2];                          // [critics, actors]: ADAM_FROM_G | ADAM_WRITE_G | ADAM_APPLY
-  float grad_scale, lr_a, lr_c, gamma, tau, beta1, beta2, eps, ln_eps;
-  float* losses;
-};
-
-// ------------------------------------------------------------------------------------------------ small device helpers
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float sum4(const float4 v) { return (v.x + v.y) + (v.z + v.w); }
-__device__ __forceinline__ float dot4(const float4 a, const float4 b) { return (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w); }
-__device__ __forceinline__ float4 mul4(const float4 a, const float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
-__device__ __forceinline__ float4 scale4(const float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
-__device__ __forceinline__ void st4(float* p, const float4 v) { *reinterpret_cast<float4*>(p) = v; }
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-
-// Grid barrier (all CTAs are co-resident: cooperative launch).  Everything a CTA wrote before it is visible to every CTA
-// after it: the arriving thread fences (cumulative over the CTA's writes through bar.sync), the last arrival bumps the
-// generation, waiters spin on it with volatile loads.  Data produced inside the launch is only ever read with .cg loads
-// (L2), so no stale L1 line can be hit.
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned n_ctas) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned gen = *reinterpret_cast<volatile unsigned*>(bar + 1);
-    __threadfence();
-    if (atomicAdd(bar, 1u) == n_ctas - 1) {
-      *reinterpret_cast<volatile unsigned*>(bar) = 0u;
-      __threadfence();
-      atomicAdd(bar + 1, 1u);
-    } else {
-      while (*reinterpret_cast<volatile unsigned*>(bar + 1) == gen) {}
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
 
 // `rows` rows of `len` floats, row r at src + r * ld -> dst + r * dld (shared); columns [len, fill) are zero-filled.
 // 16-byte cp.async where alignment allows, else 8-/4-byte L2 loads.
@@ -386,48 +274,6 @@ struct RowSmem {                                    // carved from the dynamic s
   float* wa;                                        // [A][HID] critic first-layer action columns (actor backward)
 };
 
-// this lane's 4 columns of a LayerNorm'd row: xhat, and the statistics (computed here)
-__device__ __forceinline__ float4 ln_row(const float4 z, float eps, float& mu, float& rs) {
-  mu = warp_sum(sum4(z)) * (1.0f / HID);
-  const float4 d = make_float4(z.x - mu, z.y - mu, z.z - mu, z.w - mu);
-  const float var = warp_sum(dot4(d, d)) * (1.0f / HID);
-  rs = rsqrtf(var + eps);
-  return scale4(d, rs);
-}
-__device__ __forceinline__ float4 affine_relu(const float4 xh, const float4 g, const float4 b) {
-  return make_float4(fmaxf(fmaf(xh.x, g.x, b.x), 0.f), fmaxf(fmaf(xh.y, g.y, b.y), 0.f), fmaxf(fmaf(xh.z, g.z, b.z), 0.f),
-                     fmaxf(fmaf(xh.w, g.w, b.w), 0.f));
-}
-// LayerNorm + ReLU backward for one row: dh -> dz; dy (= dh where the ReLU passed) and xhat are returned for dgamma / dbeta
-__device__ __forceinline__ float4 ln_relu_bwd_row(const float4 dh, const float4 h, const float4 xh, const float4 g, float rs,
-                                                  float4& dy) {
-  dy = make_float4(h.x > 0.f ? dh.x : 0.f, h.y > 0.f ? dh.y : 0.f, h.z > 0.f ? dh.z : 0.f, h.w > 0.f ? dh.w : 0.f);
-  const float4 dxh = mul4(dy, g);
-  const float m1 = warp_sum(sum4(dxh)) * (1.0f / HID);
-  const float m2 = warp_sum(dot4(dxh, xh)) * (1.0f / HID);
-  return make_float4(rs * (dxh.x - m1 - xh.x * m2), rs * (dxh.y - m1 - xh.y * m2), rs * (dxh.z - m1 - xh.z * m2),
-                     rs * (dxh.w - m1 - xh.w * m2));
-}
-__device__ __forceinline__ float4 xhat_of(const float4 z, float mu, float rs) {
-  return make_float4((z.x - mu) * rs, (z.y - mu) * rs, (z.z - mu) * rs, (z.w - mu) * rs);
-}
-
-// Gumbel noise of one (update, row, agent, which) as 9 values: g = -log(-log(u) + 1e-20), u uniform in (0, 1)
-__device__ __forceinline__ float gumbel_of(uint32_t w) {
-  const float u = ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  return -logf(-logf(u) + 1e-20f);
-}
-__device__ __forceinline__ void gumbel_row(const LearnArgs& a, unsigned long long upd, int row, int agent, int which, float (&g)[NA]) {
-#pragma unroll
-  for (int c = 0; 4 * c < NA; ++c) {
-    uint32_t w[4] = {(uint32_t)row, (uint32_t)agent | ((uint32_t)which << 8) | ((uint32_t)c << 16), (uint32_t)upd,
-                     (uint32_t)(upd >> 32) ^ 0x6C6561u};
-    gw::philox4x32(w, a.gk0, a.gk1);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (4 * c + i < NA) g[4 * c + i] = gumbel_of(w[i]);
-  }
-}
 
 // partial sums of one row task -> global [rb][small]: vectors by compact offset, scalars likewise
 __device__ void flush_partials(const RowSmem& rs, int slots, const int* slot_off, float* pb_rb, int n_sc, const int* sc_off) {
@@ -471,6 +317,7 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_kernel(const LearnArgs a)
   for (int u = 0; u < a.updates; ++u) {
     const unsigned long long upd = a.upd_base + (unsigned long long)u;
     for (int ph = a.ph_begin; ph < a.ph_end; ++ph) {
+      if (blockIdx.x == 0 && tid == 0 && u == a.updates - 1) a.s.trace[ph] = phase_clock();
       switch (ph) {
         // ============================================================ batch draw + gather (maddpg/agent.py:209-211)
         case PH_GATHER: {
@@ -861,6 +708,7 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_kernel(const LearnArgs a)
   }
   // step counters of the optimisers whose Adam phase ran in this launch
   if (blockIdx.x == 0 && tid == 0) {
+    a.s.trace[a.ph_end] = phase_clock();
     for (int k = 0; k < 2 * n; ++k) {
       const int ph = k < n ? PH_ADAM_A : PH_ADAM_C;
       if (ph >= a.ph_begin && ph < a.ph_end && (a.adam_mode[k < n ? 1 : 0] & ADAM_APPLY)) a.steps[k] = step0[k] + (float)a.updates;
@@ -870,18 +718,6 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_kernel(const LearnArgs a)
 
 }  // namespace gwl
 
-// ---------------------------------------------------------------------------------------------------- host side
-struct gw_learner {
-  gw_handle* h = nullptr;
-  gw_learner_config cfg;
-  gw_learner_layout lay;
-  gw_learner_buffers buf;
-  gwl::LearnArgs args;
-  std::map<std::string, std::pair<float*, int64_t>> dbg;
-  size_t smem = 0;
-  int grid = 0;
-  unsigned long long updates_done = 0;
-};
 
 namespace {
 
@@ -897,7 +733,8 @@ int check_cfg(const gw_learner_config* c) {
 inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 // carve the scratch block; base == nullptr only measures
-int64_t carve(const gw_learner_config& c, char* base, gwl::Scratch* s, std::map<std::string, std::pair<float*, int64_t>>* dbg) {
+int64_t carve(const gw_learner_config& c, char* base, gwl::Scratch* s, std::map<std::string, std::pair<float*, int64_t>>* dbg,
+              float** cluster = nullptr) {
   const int n = c.n_agents, B = c.batch, O = c.obs_len, A = c.action_dim, H = gwl::HID;
   const gwl::NetLayout la = gwl::make_layout(O, A), lc = gwl::make_layout(n * (O + A), 1);
   int64_t off = 0;
@@ -910,6 +747,7 @@ int64_t carve(const gw_learner_config& c, char* base, gwl::Scratch* s, std::map<
   gwl::Scratch t;
   std::memset(&t, 0, sizeof(t));
   t.bar = reinterpret_cast<unsigned*>(take(64, nullptr, 0));
+  t.trace = reinterpret_cast<unsigned long long*>(take(2 * 64, "trace", 0));
   t.S = take((int64_t)B * n * O, "S", 0); t.S2 = take((int64_t)B * n * O, "S2", 0);
   t.ACT = take((int64_t)B * n * A, "ACT", 0); t.R = take((int64_t)B * n, "R", 0); t.D = take((int64_t)B * n, "D", 0);
   const char* names[5] = {"ta", "ct", "c", "ac", "c2"};
@@ -933,6 +771,8 @@ int64_t carve(const gw_learner_config& c, char* base, gwl::Scratch* s, std::map<
     t.pb[n + i] = take((int64_t)(B / gwl::RB) * lc.small, nullptr, 0);
   }
   t.lp = take((int64_t)2 * n * (B / gwl::RB), nullptr, 0);
+  float* cl = take(gwc_scratch_floats(c) + 4, nullptr, 0);
+  if (cluster) *cluster = cl;
   if (s) *s = t;
   return off;
 }
@@ -994,7 +834,7 @@ extern "C" int gw_learner_create(gw_handle* h, const gw_learner_config* cfg, con
   a.la = gwl::make_layout(a.O, a.A); a.lc = gwl::make_layout(a.CI, 1);
   for (int k = 0; k < 2 * a.n; ++k) a.net_off[k] = l->lay.net_offset[k];
   a.P = buf->params; a.T = buf->targets; a.M = buf->adam_m; a.V = buf->adam_v; a.G = buf->grads; a.steps = buf->adam_steps;
-  carve(*cfg, static_cast<char*>(buf->scratch), &a.s, &l->dbg);
+  carve(*cfg, static_cast<char*>(buf->scratch), &a.s, &l->dbg, &l->cluster_scratch);
   a.gk0 = (uint32_t)cfg->seed; a.gk1 = (uint32_t)(cfg->seed >> 32) ^ 0x47554D42u;     // "GUMB"
   a.lr_a = cfg->lr_actor; a.lr_c = cfg->lr_critic; a.gamma = cfg->gamma; a.tau = cfg->tau;
   a.beta1 = cfg->beta1; a.beta2 = cfg->beta2; a.eps = cfg->adam_eps; a.ln_eps = cfg->ln_eps;
@@ -1005,6 +845,7 @@ extern "C" int gw_learner_create(gw_handle* h, const gw_learner_config* cfg, con
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gwl::gw_learn_kernel, gwl::THREADS, l->smem);
   if (e != cudaSuccess || per_sm < 1) { delete l; return gw_fail(h, GW_ECUDA, "gw_learner_create: the update kernel does not fit on an SM"); }
   l->grid = h->sm_count;                             // one CTA per SM, all co-resident (cooperative launch)
+  l->cluster_grid = gwc_prepare(l);                  // the fast path, where the shape and the device allow it
   *out = l;
   return GW_OK;
 }
@@ -1012,6 +853,22 @@ extern "C" int gw_learner_create(gw_handle* h, const gw_learner_config* cfg, con
 extern "C" int gw_learner_destroy(gw_learner* l) {
   delete l;
   return GW_OK;
+}
+
+extern "C" int gw_learner_set_kernel(gw_learner* l, int32_t kind) {
+  if (!l) return GW_EINVAL;
+  if (kind < GW_LEARN_KERNEL_AUTO || kind > GW_LEARN_KERNEL_CLUSTER) return gw_fail(l->h, GW_EINVAL, "gw_learner_set_kernel: bad kind");
+  if (kind == GW_LEARN_KERNEL_CLUSTER && l->cluster_grid == 0)
+    return gw_fail(l->h, GW_EINVAL, "gw_learner_set_kernel: the cluster kernel needs 2 learners, obs_len 160, batch % 16 == 0 and 2 * batch / 16 co-resident "
+                   "clusters of 4 CTAs (this device: " + std::to_string(l->cluster_max_active) + ")");
+  l->kernel_kind = kind;
+  return GW_OK;
+}
+
+extern "C" int gw_learner_kernel(const gw_learner* l) {
+  if (!l) return GW_EINVAL;
+  if (l->kernel_kind == GW_LEARN_KERNEL_AUTO) return l->cluster_grid > 0 ? GW_LEARN_KERNEL_CLUSTER : GW_LEARN_KERNEL_PHASE;
+  return l->kernel_kind;
 }
 
 extern "C" int gw_learner_debug_ptr(gw_learner* l, const char* name, int index, float** ptr, int64_t* floats) {
@@ -1084,6 +941,12 @@ extern "C" int gw_learner_update(gw_learner* l, const gw_learn_batch* batch, con
       break;
   }
   GW_CUDA(h, cudaSetDevice(h->cfg.device));
+  if (gw_learner_kernel(l) == GW_LEARN_KERNEL_CLUSTER) {
+    if (int rc = gwc_launch(l, a, segment, static_cast<cudaStream_t>(stream))) return rc;
+    h->launches += 1;
+    if (segment == GW_LEARN_ALL || segment == GW_LEARN_FINISH) l->updates_done += (unsigned long long)updates;
+    return GW_OK;
+  }
   void* params[] = {&a};
   GW_CUDA(h, cudaLaunchCooperativeKernel((const void*)gwl::gw_learn_kernel, dim3((unsigned)l->grid), dim3(gwl::THREADS), params,
                                          l->smem, static_cast<cudaStream_t>(stream)));

@@ -24,6 +24,10 @@ from . import _native as N
 
 
 class FusedLearner:
+    phase_names = ("gather", "l1", "l2", "heads", "ct_l2", "td", "c_bwd2", "c_ln1", "c_dw1", "adam_c", "c2_l1", "c2_l2", "aloss",
+                   "c2_dh1", "act_bwd", "a_bwd2", "a_ln1", "a_dw1", "adam_a")   # csrc/gw_maddpg.cu enum Phase
+    n_phases = len(phase_names)
+
     def __init__(self, env, agent, batch_size: Optional[int] = None, seed: int = 0):
         """env: the BatchedGridWorld that owns the library handle and the stream; agent: a BatchedMADDPG on env.device
         with the reference's network shapes (hidden [128, 128], 9 actions)."""
@@ -97,6 +101,18 @@ class FusedLearner:
                     steps.append(step)
                     off += m
                 self._step_tensors.append(steps)
+
+    KERNELS = {"auto": N.GW_LEARN_KERNEL_AUTO, "phase": N.GW_LEARN_KERNEL_PHASE, "cluster": N.GW_LEARN_KERNEL_CLUSTER}
+
+    def set_kernel(self, kind: str):
+        """"cluster" (csrc/gw_maddpg_cluster.cu: row-block clusters, 3xTF32 tensor-core tiles, 4 grid barriers per update),
+        "phase" (csrc/gw_maddpg.cu: fp32 FMA, 19 grid-wide steps, every supported shape) or "auto" (cluster where the
+        shape and the device allow it).  Raises if "cluster" is not possible for this learner."""
+        N.check(self.lib.gw_learner_set_kernel(self._h, self.KERNELS[kind]), self.env._h, "gw_learner_set_kernel")
+
+    @property
+    def kernel(self) -> str:
+        return {v: k for k, v in self.KERNELS.items()}[self.lib.gw_learner_kernel(self._h)]
 
     def export_steps(self):
         """Write the kernel's per-network Adam step counters into the torch optimisers' per-parameter `step` entries

@@ -16,7 +16,9 @@ tr = maddpg.BatchedTrainer(env, hp=hp, seed=0)
 tr.train(60, learn=False)                                # fill the ring
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for U in (1, 8, 64, 409):
+kinds = [k for k in sys.argv[2:] if k in ("cluster", "phase")] or [tr.learner.kernel]
+for kind, U in [(k, U) for k in kinds for U in (1, 8, 64, 409)]:
+    tr.learner.set_kernel(kind)
     tr.learner.learn_from_ring(tr.ring, U, tr.sample_seed)          # warm-up
     torch.cuda.synchronize()
     reps = max(2, 512 // U)
@@ -26,7 +28,7 @@ for U in (1, 8, 64, 409):
     b.record()
     torch.cuda.synchronize()
     us = a.elapsed_time(b) * 1e3 / (reps * U)
-    print(json.dumps({"updates_per_launch": U, "us_per_update": round(us, 2), "updates_per_s": round(1e6 / us),
+    print(json.dumps({"kernel": kind, "updates_per_launch": U, "us_per_update": round(us, 2), "updates_per_s": round(1e6 / us),
                       "gflops": round(0.23e9 / us / 1e3, 1)}), flush=True)
 losses = tr.learner.learn_from_ring(tr.ring, 4, tr.sample_seed)
 print("losses of the last updates (actor | critic per agent):", losses.cpu().tolist()[-1], flush=True)

@@ -81,7 +81,7 @@ def _torch_update(ag, batch, g_next, g_cur):
     return cg, agr, losses
 
 
-def _pair(dev, n, B, seed=5, obs_len=160):
+def _pair(dev, n, B, seed=5, obs_len=160, kernel="auto"):
     from marl_responsible_nav_b200 import BatchedGridWorld
     from marl_responsible_nav_b200.learner import FusedLearner
     env = BatchedGridWorld("Level 3", num_envs=32, fear=False, seed=1)
@@ -99,7 +99,9 @@ def _pair(dev, n, B, seed=5, obs_len=160):
             dst.load_state_dict(src.state_dict())
         for dst, src in zip(ref.actor_targets + ref.critic_targets, ref.actors + ref.critics):
             dst.load_state_dict(src.state_dict())
-    return env, ref, ag, FusedLearner(env, ag, batch_size=B, seed=3)
+    learner = FusedLearner(env, ag, batch_size=B, seed=3)
+    learner.set_kernel(kernel)
+    return env, ref, ag, learner
 
 
 def _rel(a, b):
@@ -107,13 +109,17 @@ def _rel(a, b):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,B", [(2, 128), (1, 128), (2, 32), (2, 256)])
-def test_one_update_matches_autograd(n, B):
+@pytest.mark.parametrize("n,B,kernel", [(2, 128, "cluster"), (2, 32, "cluster"), (2, 64, "cluster"), (2, 128, "phase"), (1, 128, "phase"),
+                                        (2, 32, "phase"), (2, 256, "phase")])
+def test_one_update_matches_autograd(n, B, kernel):
     """Gradients within 1e-4 (relative to the tensor's largest entry) of fp32 autograd, losses within 1e-5 relative, and
     after the Adam steps + soft update the parameters / targets / moments agree (Adam divides by sqrt(v): the first step
     moves every weight by ~lr whatever its gradient, so parameters are compared to 2e-5 absolute = 2 % of lr)."""
     dev = torch.device("cuda", 0)
-    env, ref, ag, learner = _pair(dev, n, B)
+    if kernel == "phase" and B % 32:
+        pytest.skip("the phase kernel tiles the batch by 32")
+    env, ref, ag, learner = _pair(dev, n, B, kernel=kernel)
+    assert learner.kernel == kernel
     batch, g_next, g_cur = _batch(dev, B, n, seed=B + n)
     cg, agr, want_loss = _torch_update(ref, batch, g_next, g_cur)
     losses = learner.learn(batch, g_next, g_cur)
@@ -141,10 +147,11 @@ def test_one_update_matches_autograd(n, B):
 
 
 @pytest.mark.gpu
-def test_intermediates_match_torch():
+@pytest.mark.parametrize("kernel", ["cluster", "phase"])
+def test_intermediates_match_torch(kernel):
     """The kernel's activations against the modules: target actions, Q, TD target (debug tensors)."""
     dev = torch.device("cuda", 0)
-    env, ref, ag, learner = _pair(dev, 2, 128)
+    env, ref, ag, learner = _pair(dev, 2, 128, kernel=kernel)
     batch, g_next, g_cur = _batch(dev, 128, 2, seed=9)
     s, a, r, s2, d = (batch[k] for k in ("state", "action", "reward", "next_state", "done"))
     with torch.no_grad():
@@ -164,11 +171,12 @@ def test_intermediates_match_torch():
 
 
 @pytest.mark.gpu
-def test_several_updates_track_autograd():
+@pytest.mark.parametrize("kernel", ["cluster", "phase"])
+def test_several_updates_track_autograd(kernel):
     """Eight consecutive updates on changing batches: the critic losses follow the PyTorch run (1e-3 relative; Adam's
     normalised steps amplify rounding differences) and the parameters stay within 3e-4."""
     dev = torch.device("cuda", 0)
-    env, ref, ag, learner = _pair(dev, 2, 128)
+    env, ref, ag, learner = _pair(dev, 2, 128, kernel=kernel)
     for it in range(8):
         batch, g_next, g_cur = _batch(dev, 128, 2, seed=100 + it)
         _, _, want = _torch_update(ref, batch, g_next, g_cur)
@@ -191,8 +199,9 @@ def _filled_ring(env_n=64, steps=12, obs_dtype=torch.float32, seed=0):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["cluster", "phase"])
 @pytest.mark.parametrize("obs_dtype", [torch.float32, torch.bfloat16])
-def test_ring_mode_equals_explicit_batches(obs_dtype):
+def test_ring_mode_equals_explicit_batches(obs_dtype, kernel):
     """U updates in ONE launch, each drawing + gathering its batch inside the kernel, against U one-update launches on
     the batches `ring.sample_fused` returns for the same draw numbers: bit-identical parameters, targets and losses
     (same kernel, same inputs, same noise keys)."""
@@ -202,6 +211,7 @@ def test_ring_mode_equals_explicit_batches(obs_dtype):
     ring, U = tr.ring, 5
     agents = [maddpg.BatchedMADDPG(2, 160, 9, hp=hp, device=dev, seed=8) for _ in range(2)]
     la, lb = (FusedLearner(env, ag, seed=4) for ag in agents)
+    la.set_kernel(kernel); lb.set_kernel(kernel)
     draws0 = ring._draws
     got = la.learn_from_ring(ring, U, sample_seed=77).clone()
     assert ring._draws == draws0 + U and la.updates_done == U
@@ -218,12 +228,13 @@ def test_ring_mode_equals_explicit_batches(obs_dtype):
 
 
 @pytest.mark.gpu
-def test_segments_equal_the_whole_update():
+@pytest.mark.parametrize("kernel", ["cluster", "phase"])
+def test_segments_equal_the_whole_update(kernel):
     """The three pieces of a data-parallel update (critic gradients | critic steps + actor gradients | actor steps) run
     back to back with grad_scale 1 give exactly the one-launch update."""
     dev = torch.device("cuda", 0)
-    env, ref, ag, la = _pair(dev, 2, 128)
-    env2, _, ag2, lb = _pair(dev, 2, 128)
+    env, ref, ag, la = _pair(dev, 2, 128, kernel=kernel)
+    env2, _, ag2, lb = _pair(dev, 2, 128, kernel=kernel)
     for it in range(3):
         batch, g_next, g_cur = _batch(dev, 128, 2, seed=40 + it)
         l1 = la.learn(batch, g_next, g_cur).clone()
@@ -245,7 +256,7 @@ def test_trainer_learns_through_the_fused_kernel():
     hp["MEMORY_SIZE"] = 20000
     env = maddpg.make_env(hp, 256)
     tr = maddpg.BatchedTrainer(env, hp=hp, seed=0)
-    assert tr.learner is not None
+    assert tr.learner is not None and tr.learner.kernel == "cluster"
     p0 = tr.learner.params.clone()
     tr.train(6)
     env.sync()
