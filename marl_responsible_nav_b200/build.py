@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
         if (not force and os.path.exists(obj)
                 and os.path.getmtime(obj) > max(hdr_t, os.path.getmtime(os.path.join(CSRC, src)))):
             continue
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("GW_NVCC_FLAGS", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, pr in procs:
         out, _ = pr.communicate()

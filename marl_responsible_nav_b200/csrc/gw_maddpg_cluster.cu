@@ -40,7 +40,7 @@ constexpr int AXLD = 24;
 // dynamic shared memory (floats)
 constexpr int SM_X = 0, SM_X2 = SM_X + RR * XLD, SM_EX = SM_X2 + RR * XLD, SM_PV = SM_EX + 2 * 3 * RR * ALD;
 constexpr int SM_RING = SM_PV + 3 * RR * ALD, SM_RED = SM_RING + NSLOT * SLOT, SM_OUT = SM_RED + WARPS * RR * RLD;
-constexpr int SM_PERS = SM_OUT + RR * OLD, PERS_FLOATS = 2560, SM_MISC = SM_PERS + PERS_FLOATS, MISC_FLOATS = 2432;
+constexpr int SM_PERS = SM_OUT + RR * OLD, PERS_FLOATS = 3360, SM_MISC = SM_PERS + PERS_FLOATS, MISC_FLOATS = 2432;
 constexpr int SM_TOTAL = SM_MISC + MISC_FLOATS;
 static_assert(SM_TOTAL * 4 <= 227 * 1024, "shared memory plan");
 static_assert(2 * RR * ALD <= RR * XLD, "two activation buffers live where next_state was staged");
@@ -52,8 +52,9 @@ constexpr int MI_W1ACT = 944 /* [9][128] */, MI_LOSS = 2096;
 static_assert(MI_LOSS + 16 <= MISC_FLOATS, "misc plan");
 // PERS sub-offsets (vectors that must outlive their ring slot)
 constexpr int PE_G1 = 0, PE_BE1 = 128, PE_G2 = 256, PE_BE2 = 384, PE_W3 = 512;         // critic (phase A: c, phase B: c2)
-constexpr int PE_AG1 = 640, PE_ABE1 = 768, PE_AG2 = 896, PE_ABE2 = 1024, PE_AW3 = 1152; // actor (phase B), W3 [9][128] + b3 at +1152
-constexpr int PE_AB3 = PE_AW3 + NA * HID;
+constexpr int PE_AG1 = 640, PE_ABE1 = 768, PE_AG2 = 896, PE_ABE2 = 1024, PE_AW3 = 1152; // actor (phase B); W3 as [16][ALD] (rows >= 9 zero), then b3
+constexpr int PE_AB3 = PE_AW3 + 16 * ALD;
+constexpr int W3P = 16 * ALD + 16;          // a padded head: W3 [16][ALD] K-major, rows >= NA zero, then the bias
 constexpr int PE_T0 = 640, PE_T1 = 896;                                               // phase A: gamma | beta of target actor 0 / 1 (layer 1, then layer 2)
 static_assert(PE_AB3 + 16 <= PERS_FLOATS, "pers plan");
 
@@ -144,6 +145,50 @@ __device__ __forceinline__ void mma_tile(float (&acc)[2][4], const float* __rest
     }
   }
 }
+// Gumbel noise of action q for (update, row, agent, which): the same Philox words gumbel_row hands out, one action per lane
+__device__ __forceinline__ float gumbel_lane(const LearnArgs& a, unsigned long long upd, int row, int agent, int which, int q) {
+  uint32_t w[4] = {(uint32_t)row, (uint32_t)agent | ((uint32_t)which << 8) | ((uint32_t)(q >> 2) << 16), (uint32_t)upd,
+                   (uint32_t)(upd >> 32) ^ 0x6C6561u};
+  gw::philox4x32(w, a.gk0, a.gk1);
+  const int i = q & 3;
+  return gumbel_of(i == 0 ? w[0] : i == 1 ? w[1] : i == 2 ? w[2] : w[3]);
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// softmax over the NA values held by lanes 0 .. NA-1 (one per lane); lane q returns probability q, the other lanes 0
+__device__ __forceinline__ float softmax_lanes(float v, int lane) {
+  v = lane < NA ? v : -3.4e38f;
+  const float mx = warp_max(v);
+  const float e = lane < NA ? expf(v - mx) : 0.f;
+  const float den = warp_sum(e);
+  return e * (1.0f / den);
+}
+// softmax over the NA values held by lanes c = lane & 15 < NA of each half warp; lane c returns probability c, the others 0
+__device__ __forceinline__ float softmax_half(float v, int c) {
+  v = c < NA ? v : -3.4e38f;
+  float mx = v;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float e = c < NA ? expf(v - mx) : 0.f;
+  float den = e;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+  return e * (1.0f / den);
+}
+// logits of one row: lane q < NA gets h . W3[q] + b3[q]   (h: this lane's 4 columns; W3 [NA][HID] then b3 in shared memory)
+__device__ __forceinline__ float head_logit_lane(const float4 h, const float* w3, int lane) {
+  float mine = 0.f;
+#pragma unroll
+  for (int q = 0; q < NA; ++q) {
+    const float s = warp_sum(dot4(h, *reinterpret_cast<const float4*>(w3 + q * HID + 4 * lane)));
+    mine = lane == q ? s : mine;
+  }
+  return lane < NA ? mine + w3[NA * HID + lane] : 0.f;
+}
+
 __device__ __forceinline__ void zero_acc(float (&acc)[2][4]) {
 #pragma unroll
   for (int nb = 0; nb < 2; ++nb)
@@ -194,7 +239,10 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rank = (int)cluster_rank(), col0 = rank * CW;
   const int B = a.B, NRB = B / RR;
-  const int cid = blockIdx.x / CL, ag = cid / NRB, rb = cid - ag * NRB, row0 = rb * RR;
+  // clusters beyond the 2 * B / 16 that own row blocks are helpers: they only take part in the Adam phases and the barriers
+  const int cid = blockIdx.x / CL;
+  const bool worker = cid < N2 * NRB;
+  const int ag = worker ? cid / NRB : 0, rb = worker ? cid - ag * NRB : 0, row0 = rb * RR;
   const unsigned n_ctas = gridDim.x;
   const NetLayout la = a.la, lc = a.lc;
   float* X = sm + SM_X; float* X2 = sm + SM_X2; float* EX = sm + SM_EX; float* PV = sm + SM_PV; float* RING = sm + SM_RING;
@@ -207,7 +255,7 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
   auto slot_v = [&](int p) { return RING + (p % NSLOT) * SLOT + SLOT_W; };
   float step0[2 * MAXN];
   for (int k = 0; k < 2 * N2; ++k) step0[k] = __ldcg(a.steps + k);
-  for (int i = tid; i < SM_TOTAL; i += THREADS) sm[i] = 0.f;      // every later content is a finite float (padding is multiplied by 0)
+  if (worker) for (int i = tid; i < SM_TOTAL; i += THREADS) sm[i] = 0.f;      // every later content is a finite float (padding is multiplied by 0)
   __syncthreads();
   cluster_sync();                                                 // peers' shared memory exists and is zeroed before anyone writes into it
   int round = 0;                                                  // all-gather rounds done (parity selects the exchange set)
@@ -374,10 +422,43 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
     mma_tile<0, 1>(acc, A, ALD, wt + (warp & 1) * 16, TLD, 8 * (warp >> 1), HID, 32);
   };
 
+  // output layer of an actor on the tensor cores: logits[16 rows][16] = h [16][HID] . w3p^T over the 8 warps' k-slices, joined
+  // through RED; thread (r = tid >> 4, c = tid & 15) returns logit c of row r (bias added for c < NA)
+  auto head_logits = [&](const float* h, const float* w3p) -> float {
+    float acc[2][4];
+    zero_acc(acc);
+    mma_tile<0, 0>(acc, h, ALD, w3p, ALD, 8 * warp, HID, 64);
+    const int g = lane >> 2, t = lane & 3;
+    float* my = RED + warp * RR * RLD;
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb) {
+      *reinterpret_cast<float2*>(my + g * RLD + nb * 8 + 2 * t) = make_float2(acc[nb][0], acc[nb][1]);
+      *reinterpret_cast<float2*>(my + (g + 8) * RLD + nb * 8 + 2 * t) = make_float2(acc[nb][2], acc[nb][3]);
+    }
+    __syncthreads();
+    const int r = tid >> 4, c = tid & 15;
+    float v = c < NA ? w3p[16 * ALD + c] : 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) v += RED[w * RR * RLD + r * RLD + c];
+    __syncthreads();
+    return v;
+  };
+#ifdef GW_LEARN_TRACE
+  int tpk = 0;
+#define TP() do { if (blockIdx.x == 0 && tid == 0 && u == a.updates - 1 && tpk < 100) a.s.trace[8 + tpk] = phase_clock(); ++tpk; } while (0)
+#else
+#define TP() do { } while (0)
+#endif
   for (int u = 0; u < a.updates; ++u) {
     const unsigned long long upd = a.upd_base + (unsigned long long)u;
+#ifdef GW_LEARN_TRACE
+    tpk = 0;
+#endif
     for (int ph = ca.cp_begin; ph < ca.cp_end; ++ph) {
       if (blockIdx.x == 0 && tid == 0 && u == a.updates - 1) a.s.trace[ph] = phase_clock();
+      if (ph == 0 || ph == 2) {
+        if (!worker) { grid_barrier(a.s.bar, n_ctas); continue; }   // (phases A / B are never the last one of a launch)
+      }
       if (ph == 0) {
         // ======================================================================================== phase A: critic gradients
         const float* Tc = a.T + a.net_off[N2 + ag];           // target critic
@@ -397,8 +478,9 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
             case 7: case 8: { const float* net = a.T + a.net_off[p - 7];
               load_w(w, ALD, a.T, a.net_off[p - 7] + la.w2 + (long long)col0 * HID, HID, HID); load_layer_vecs(v, net, la.b2, col0, false, 0, 0); } break;
             case 9: load_w(w, ALD, a.P, a.net_off[N2 + ag] + lc.w2 + (long long)col0 * HID, HID, HID); load_layer_vecs(v, Pc, lc.b2, col0, true, lc.w3, lc.b3); break;
-            case 10: for (int k = 0; k < N2; ++k) { const float* net = a.T + a.net_off[k];
-              load_vec(w + k * (NA * HID + 16), net + la.w3, NA * HID / 4); load_vec(w + k * (NA * HID + 16) + NA * HID, net + la.b3, 3); } break;
+            case 10: for (int k = 0; k < N2; ++k) { const float* net = a.T + a.net_off[k];   // the target actors' heads, padded layout
+              for (int i = tid; i < NA * (HID / 4); i += THREADS) cp_async16(w + k * W3P + (i >> 5) * ALD + 4 * (i & 31), net + la.w3 + 4 * i);
+              load_vec(w + k * W3P + 16 * ALD, net + la.b3, 3); } break;
             case 11: load_w(w, 26, a.T, c1 + SO, CI, SA); load_layer_vecs(v, Tc, lc.b1, col0, false, 0, 0); break;
             case 12: load_w(w, ALD, a.T, a.net_off[N2 + ag] + lc.w2 + (long long)col0 * HID, HID, HID); load_layer_vecs(v, Tc, lc.b2, col0, true, lc.w3, lc.b3); break;
             case 13: load_wt(w, Pc + lc.w2, col0, HID); break;
@@ -412,11 +494,13 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
           issue(p + 2);
         };
         stage_rows(true, u);
+        TP();
         issue(0); issue(1);
         float acc_t[N2][2][4], acc_c[2][4], acc_ct[2][4];
         zero_acc(acc_t[0]); zero_acc(acc_t[1]); zero_acc(acc_c); zero_acc(acc_ct);
         // ---- round 1: first layers
         ready(0, true);  gemm(acc_t[0], X2, XLD, slot_w(0), 168, O);
+        TP();
         float* TAh[N2] = {pv(0), pv(1)};
         float* XH2 = pv(2); float* XH1 = pv(3); float* H1 = pv(4);   // 3, 4: where next_state is staged, dead after this round's GEMMs
         float* A2 = MISC + MI_AXA;                                  // target actions [16][24], zero padded
@@ -427,16 +511,23 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
           for (int i = tid; i < 2 * HID; i += THREADS) PERS[PE_T0 + i] = slot_v(0)[V_G + i];
         }
         ready(1);  gemm(acc_t[1], X2 + O, XLD, slot_w(1), 168, O);
+        TP();
         reduce_exchange(acc_t[1], slot_v(1) + V_B, ex(round & 1, 1));
         for (int i = tid; i < 2 * HID; i += THREADS) PERS[PE_T1 + i] = slot_v(1)[V_G + i];
         ready(2);  gemm(acc_c, X, XLD, slot_w(2), 170, O);
+        TP();
         ready(3);  gemm(acc_c, X + O, XLD, slot_w(3), 170, O);
+        TP();
         ready(4);  gemm(acc_c, X + SO, XLD, slot_w(4), 26, 24);
+        TP();
         reduce_exchange(acc_c, slot_v(4) + V_B, ex(round & 1, 2));
         for (int i = tid; i < 2 * HID; i += THREADS) PERS[PE_G1 + i] = slot_v(4)[V_G + i];     // gamma1 | beta1 of the critic
         ready(5);  gemm(acc_ct, X2, XLD, slot_w(5), 170, O);
+        TP();
         ready(6);  gemm(acc_ct, X2 + O, XLD, slot_w(6), 170, O);
+        TP();
         cluster_sync();
+        TP();
         float4 hreg[2];
         {
           const int set = round & 1;
@@ -449,52 +540,39 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
         float acc2[2][4];
         for (int k = 0; k < N2; ++k) {
           ready(7 + k);
+          TP();
           zero_acc(acc2);
           gemm(acc2, TAh[k], ALD, slot_w(7 + k), ALD, HID);
           reduce_exchange(acc2, slot_v(7 + k) + V_B, ex(round & 1, k));
           for (int i = tid; i < 2 * HID; i += THREADS) PERS[(k ? PE_T1 : PE_T0) + i] = slot_v(7 + k)[V_G + i];   // layer-1 values were consumed before round 2
         }
         ready(9);
+        TP();
         zero_acc(acc2);
         gemm(acc2, H1, ALD, slot_w(9), ALD, HID);
         reduce_exchange(acc2, slot_v(9) + V_B, ex(round & 1, 2));
         for (int i = tid; i < 3 * HID; i += THREADS) PERS[PE_G2 + i] = slot_v(9)[V_G + i];     // gamma2 | beta2 | w3 of the critic
         const float b3c = slot_v(9)[V_B3];
         ready(10);
+        TP();
+        for (int i = tid; i < N2 * 7 * ALD; i += THREADS) slot_w(10)[(i / (7 * ALD)) * W3P + NA * ALD + i % (7 * ALD)] = 0.f;   // rows 9..15 of the padded heads
         cluster_sync();
+        TP();
         {
           const int set = round & 1;
           // target actors' heads: Gumbel-softmax actions on next_state -> A2[:, k * 9 ...]
+          for (int k = 0; k < N2; ++k) ln_rows(ex(set, k), PERS + (k ? PE_T1 : PE_T0), PERS + (k ? PE_T1 : PE_T0) + HID, nullptr, TAh[k], nullptr, hreg);
+          __syncthreads();
           for (int k = 0; k < N2; ++k) {
-            ln_rows(ex(set, k), PERS + (k ? PE_T1 : PE_T0), PERS + (k ? PE_T1 : PE_T0) + HID, nullptr, nullptr, nullptr, hreg);
-            const float* w3 = slot_w(10) + k * (NA * HID + 16);
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-              const int r = 2 * warp + rr, row = row0 + r;
-              float logit[NA], gn[NA];
-#pragma unroll
-              for (int q = 0; q < NA; ++q) logit[q] = warp_sum(dot4(hreg[rr], *reinterpret_cast<const float4*>(w3 + q * HID + 4 * lane))) + w3[NA * HID + q];
-              if (a.gum_next) {
-#pragma unroll
-                for (int q = 0; q < NA; ++q) gn[q] = __ldg(a.gum_next + ((long long)row * N2 + k) * NA + q);
-              } else {
-                gumbel_row(a, upd, row, k, 0, gn);
-              }
-              float mx = -3.4e38f;
-#pragma unroll
-              for (int q = 0; q < NA; ++q) { logit[q] += gn[q]; mx = fmaxf(mx, logit[q]); }
-              float den = 0.f;
-#pragma unroll
-              for (int q = 0; q < NA; ++q) { logit[q] = expf(logit[q] - mx); den += logit[q]; }
-              const float inv = 1.0f / den;
-              float pl = 0.f;
-#pragma unroll
-              for (int q = 0; q < NA; ++q) pl = lane == q ? logit[q] * inv : pl;
-              if (lane < NA) {
-                A2[r * AXLD + k * NA + lane] = pl;
-                if (rank == 0 && ag == 0) a.s.a2[(long long)row * SA + k * NA + lane] = pl;
-              }
-              if (k == 0 && lane >= SA && lane < AXLD) A2[r * AXLD + lane] = 0.f;
+            float lg = head_logits(TAh[k], slot_w(10) + k * W3P);
+            const int r = tid >> 4, c = tid & 15, row = row0 + r;
+            if (c < NA) lg += a.gum_next ? __ldg(a.gum_next + ((long long)row * N2 + k) * NA + c) : gumbel_lane(a, upd, row, k, 0, c);
+            const float pl = softmax_half(lg, c);
+            if (c < NA) {
+              A2[r * AXLD + k * NA + c] = pl;
+              if (rank == 0 && ag == 0) a.s.a2[(long long)row * SA + k * NA + c] = pl;
+            } else if (k == 0 && c - NA < AXLD - SA) {
+              A2[r * AXLD + SA + c - NA] = 0.f;
             }
           }
           // critic head: Q(state, action)
@@ -509,18 +587,22 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
         }
         // ---- round 3: target critic, first layer completed with the target actions
         ready(11);
+        TP();
         gemm(acc_ct, A2, AXLD, slot_w(11), 26, 24);
         reduce_exchange(acc_ct, slot_v(11) + V_B, ex(round & 1, 0));
         cluster_sync();
+        TP();
         float* CTh = TAh[0];
         ln_rows(ex(round & 1, 0), slot_v(11) + V_G, slot_v(11) + V_BE, nullptr, CTh, nullptr, hreg);
         ++round;
         // ---- round 4: target critic, second layer -> TD target -> critic loss -> backward through layer 3 / LayerNorm 2
         ready(12);
+        TP();
         zero_acc(acc2);
         gemm(acc2, CTh, ALD, slot_w(12), ALD, HID);
         reduce_exchange(acc2, slot_v(12) + V_B, ex(round & 1, 0));
         cluster_sync();
+        TP();
         float* DZ2 = TAh[1]; float* DZ1 = TAh[0];
         {
           ln_rows(ex(round & 1, 0), slot_v(12) + V_G, slot_v(12) + V_BE, nullptr, nullptr, nullptr, hreg);
@@ -568,11 +650,14 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
         }
         // ---- round 5: dh1 = dz2 W2 (this CTA's 16 columns) -> LayerNorm 1 backward
         ready(13);
+        TP();
         zero_acc(acc2);
         gemm_dh(acc2, DZ2, slot_w(13));
         reduce_exchange(acc2, nullptr, ex(round & 1, 0));
         dw_slice(slab + lc.w2, HID, DZ2, H1, ALD, HID);         // dW2 rows of this CTA (independent of the exchange)
+        TP();
         cluster_sync();
+        TP();
         {
           float4 dh[2];
 #pragma unroll
@@ -584,7 +669,9 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
           ++round;
         }
         dw_slice(slab + lc.w1, CI, DZ1, X, XLD, CI);            // dW1 rows of this CTA: dz1^T [state | action]
+        TP();
         cp_wait<0>();
+        TP();
         x_valid = true;
       } else if (ph == 2) {
         // ======================================================================================== phase B: actor gradients
@@ -628,74 +715,72 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
         zero_acc(acc_a); zero_acc(acc_c);
         // ---- round 1: actor layer 1; the state part of the critic's layer 1
         ready(0, true);  gemm(acc_a, X + ag * O, XLD, slot_w(0), 168, O);
+        TP();
         reduce_exchange(acc_a, slot_v(0) + V_B, ex(round & 1, 0));
         for (int i = tid; i < 2 * HID; i += THREADS) PERS[PE_AG1 + i] = slot_v(0)[V_G + i];
         ready(1);  gemm(acc_c, X, XLD, slot_w(1), 170, O);
+        TP();
         ready(2);  gemm(acc_c, X + O, XLD, slot_w(2), 170, O);
+        TP();
         cluster_sync();
+        TP();
         ln_rows(ex(round & 1, 0), PERS + PE_AG1, PERS + PE_ABE1, XH1a, H1a, rs1a, hreg);
         ++round;
         // ---- round 2: actor layer 2 -> head -> Gumbel-softmax action
         ready(3);
+        TP();
         zero_acc(acc2);
         gemm(acc2, H1a, ALD, slot_w(3), ALD, HID);
         reduce_exchange(acc2, slot_v(3) + V_B, ex(round & 1, 0));
         for (int i = tid; i < 2 * HID; i += THREADS) PERS[PE_AG2 + i] = slot_v(3)[V_G + i];
         ready(4);
-        for (int i = tid; i < NA * HID + 12; i += THREADS) PERS[PE_AW3 + i] = slot_w(4)[i];
+        TP();
+        for (int i = tid; i < NA * HID + 12; i += THREADS) {    // padded layout [16][ALD] + bias (rows 9..15 stay zero)
+          if (i < NA * HID) PERS[PE_AW3 + (i >> 7) * ALD + (i & (HID - 1))] = slot_w(4)[i];
+          else PERS[PE_AB3 + i - NA * HID] = slot_w(4)[i];
+        }
         cluster_sync();
-        ln_rows(ex(round & 1, 0), PERS + PE_AG2, PERS + PE_ABE2, XH2a, nullptr, rs2a, hreg);
+        TP();
+        ln_rows(ex(round & 1, 0), PERS + PE_AG2, PERS + PE_ABE2, XH2a, D2, rs2a, hreg);   // h2 into D2 (free until round 5)
         ++round;
-        __syncthreads();                                        // PERS (actor W3) written by all threads above
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          const int r = 2 * warp + rr, row = row0 + r;
-          float logit[NA], gn[NA];
-#pragma unroll
-          for (int q = 0; q < NA; ++q) logit[q] = warp_sum(dot4(hreg[rr], *reinterpret_cast<const float4*>(PERS + PE_AW3 + q * HID + 4 * lane))) + PERS[PE_AB3 + q];
-          if (a.gum_cur) {
-#pragma unroll
-            for (int q = 0; q < NA; ++q) gn[q] = __ldg(a.gum_cur + ((long long)row * N2 + ag) * NA + q);
-          } else {
-            gumbel_row(a, upd, row, ag, 1, gn);
+        __syncthreads();                                        // D2 and PERS (actor W3) written by all threads above
+        {
+          float lg = head_logits(D2, PERS + PE_AW3);
+          const int r = tid >> 4, c = tid & 15, row = row0 + r;
+          if (c < NA) lg += a.gum_cur ? __ldg(a.gum_cur + ((long long)row * N2 + ag) * NA + c) : gumbel_lane(a, upd, row, ag, 1, c);
+          const float pl = softmax_half(lg, c);
+          if (c < NA) {
+            MISC[MI_ANEW + r * 12 + c] = pl;
+            if (rank == 0) a.s.anew[ag][(long long)row * NA + c] = pl;
           }
-          float mx = -3.4e38f;
 #pragma unroll
-          for (int q = 0; q < NA; ++q) { logit[q] += gn[q]; mx = fmaxf(mx, logit[q]); }
-          float den = 0.f;
-#pragma unroll
-          for (int q = 0; q < NA; ++q) { logit[q] = expf(logit[q] - mx); den += logit[q]; }
-          const float inv = 1.0f / den;
-          float pl = 0.f;
-#pragma unroll
-          for (int q = 0; q < NA; ++q) pl = lane == q ? logit[q] * inv : pl;
-          if (lane < NA) {
-            MISC[MI_ANEW + r * 12 + lane] = pl;
-            if (rank == 0) a.s.anew[ag][(long long)row * NA + lane] = pl;
-          }
-          if (lane < AXLD) {                                    // the batch's actions with this agent's replaced (zero padded)
-            const int k = lane - ag * NA;
+          for (int hf = 0; hf < 2; ++hf) {                      // the batch's actions with this agent's replaced (zero padded): columns c, c + 16
+            const int col = c + 16 * hf, k = col - ag * NA;
             const bool mine = k >= 0 && k < NA;
-            const float pv_ = __shfl_sync(0x00ffffffu, pl, mine ? k : 0);
-            MISC[MI_AXA + r * AXLD + lane] = lane >= SA ? 0.f : (mine ? pv_ : X[r * XLD + SO + lane]);
+            const float pv_ = __shfl_sync(0xffffffffu, pl, (lane & 16) + (mine ? k : 0));
+            if (col < AXLD) MISC[MI_AXA + r * AXLD + col] = col >= SA ? 0.f : (mine ? pv_ : X[r * XLD + SO + col]);
           }
         }
         // ---- round 3: the updated critic's layer 1 completed with [.. actor's action ..]
         ready(5);
+        TP();
         gemm(acc_c, MISC + MI_AXA, AXLD, slot_w(5), 26, 24);
         reduce_exchange(acc_c, slot_v(5) + V_B, ex(round & 1, 0));
         for (int i = tid; i < 2 * HID; i += THREADS) PERS[PE_G1 + i] = slot_v(5)[V_G + i];
         cluster_sync();
+        TP();
         ln_rows(ex(round & 1, 0), PERS + PE_G1, PERS + PE_BE1, XH1c, D1, rs1c, hreg);
         ++round;
         // ---- round 4: critic layer 2 -> Q -> actor loss -> backward through layer 3 / LayerNorm 2
         ready(6);
+        TP();
         zero_acc(acc2);
         gemm(acc2, D1, ALD, slot_w(6), ALD, HID);
         reduce_exchange(acc2, slot_v(6) + V_B, ex(round & 1, 0));
         for (int i = tid; i < 3 * HID; i += THREADS) PERS[PE_G2 + i] = slot_v(6)[V_G + i];
         const float b3c = slot_v(6)[V_B3];
         cluster_sync();
+        TP();
         {
           ln_rows(ex(round & 1, 0), PERS + PE_G2, PERS + PE_BE2, XH2c, nullptr, rs2c, hreg);
           const float4 w3c = *reinterpret_cast<const float4*>(PERS + PE_W3 + 4 * lane);
@@ -719,10 +804,12 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
         }
         // ---- round 5: dh1 (critic) -> LayerNorm 1 backward -> gradient w.r.t. the action -> softmax -> actor layer 3
         ready(7);
+        TP();
         zero_acc(acc2);
         gemm_dh(acc2, D1, slot_w(7));
         reduce_exchange(acc2, nullptr, ex(round & 1, 0));
         cluster_sync();
+        TP();
         {
           float4 dh[2];
 #pragma unroll
@@ -748,7 +835,7 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
 #pragma unroll
             for (int k = 0; k < NA; ++k) {
               dl[k] = an[k] * (da[k] - sdot);                    // softmax backward (the Gumbel noise is a constant)
-              const float4 w3 = *reinterpret_cast<const float4*>(PERS + PE_AW3 + k * HID + 4 * lane);
+              const float4 w3 = *reinterpret_cast<const float4*>(PERS + PE_AW3 + k * ALD + 4 * lane);
               d.x = fmaf(dl[k], w3.x, d.x); d.y = fmaf(dl[k], w3.y, d.y); d.z = fmaf(dl[k], w3.z, d.z); d.w = fmaf(dl[k], w3.w, d.w);
               if (lane == 0) MISC[MI_DL + r * 12 + k] = dl[k];
             }
@@ -762,7 +849,7 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
         ln_vec_grads(slab, la.b2, D1, XH2a, PERS + PE_AG2, PERS + PE_ABE2, [&](int r, int c) {
           float s = 0.f;
 #pragma unroll
-          for (int k = 0; k < NA; ++k) s = fmaf(MISC[MI_DL + r * 12 + k], PERS[PE_AW3 + k * HID + c], s);
+          for (int k = 0; k < NA; ++k) s = fmaf(MISC[MI_DL + r * 12 + k], PERS[PE_AW3 + k * ALD + c], s);
           return s;
         });
         for (int e = tid; e < NA * CW + NA; e += THREADS) {      // dW3[k][c] = sum_r dl[r][k] * h2[r][c]; db3[k] = sum_r dl[r][k]
@@ -778,11 +865,14 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
         }
         // ---- round 6: dh1 (actor) -> LayerNorm 1 backward
         ready(8);
+        TP();
         zero_acc(acc2);
         gemm_dh(acc2, D1, slot_w(8));
         reduce_exchange(acc2, nullptr, ex(round & 1, 0));
         dw_slice(slab + la.w2, HID, D1, H1a, ALD, HID);
+        TP();
         cluster_sync();
+        TP();
         {
           float4 dh[2];
 #pragma unroll
@@ -794,7 +884,9 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
           ++round;
         }
         dw_slice(slab + la.w1, O, D2, X + ag * O, XLD, O);
+        TP();
         cp_wait<0>();
+        TP();
         x_valid = false;                                        // the next update draws new rows
       } else {
         // ======================================================================================== Adam + soft update
@@ -802,41 +894,56 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
         const NetLayout& L = critic ? lc : la;
         const float lr = critic ? a.lr_c : a.lr_a;
         const int mode = a.adam_mode[critic ? 0 : 1];
+        const int n4 = (L.total + 3) >> 2;
+        float step_size[N2], bc2s[N2];
         for (int i = 0; i < N2; ++i) {
-          const int net = critic ? N2 + i : i;
-          const long long off = a.net_off[net];
-          const float stepf = step0[net] + (float)(u + 1);
-          const float bc1 = 1.0f - powf(a.beta1, stepf), bc2s = sqrtf(1.0f - powf(a.beta2, stepf));
-          const float step_size = lr / bc1;
-          const float* gp = ca.gpart[net];
+          const float stepf = step0[critic ? N2 + i : i] + (float)(u + 1);
+          step_size[i] = lr / (1.0f - powf(a.beta1, stepf));
+          bc2s[i] = sqrtf(1.0f - powf(a.beta2, stepf));
+        }
+        // four parameters per thread and step (every vector is 16-byte aligned, every network block padded to 4 floats; the
+        // padding carries zero gradients and stays zero); both networks of the kind share the index space
+        for (int t4 = blockIdx.x * THREADS + tid; t4 < N2 * n4; t4 += n_ctas * THREADS) {
+          const int i = t4 >= n4 ? 1 : 0, i4 = t4 - i * n4, net = critic ? N2 + i : i;
+          const long long e = a.net_off[net] + 4 * i4;
+          const float* gp = ca.gpart[net] + 4 * i4;
           const long long gs = ca.gstride[net];
-          for (int idx = blockIdx.x * THREADS + tid; idx < L.total; idx += n_ctas * THREADS) {
-            float g;
-            if (mode & ADAM_FROM_G) {
-              g = __ldcg(a.G + off + idx);
-            } else {
-              g = 0.f;
-              for (int r = 0; r < NRB; ++r) g += __ldcg(gp + (long long)r * gs + idx);
-            }
-            if (mode & ADAM_WRITE_G) a.G[off + idx] = g;
-            if (mode & ADAM_APPLY) {
-              g *= a.grad_scale;
-              float m = __ldcg(a.M + off + idx), v = __ldcg(a.V + off + idx), p = __ldcg(a.P + off + idx);
-              m = m + (1.0f - a.beta1) * (g - m);
-              v = a.beta2 * v + (1.0f - a.beta2) * g * g;
-              const float denom = sqrtf(v) / bc2s + a.eps;
-              p -= step_size * (m / denom);
-              a.M[off + idx] = m; a.V[off + idx] = v; a.P[off + idx] = p;
-              const float tg = __ldcg(a.T + off + idx);
-              a.T[off + idx] = tg + a.tau * (p - tg);
+          float4 g = make_float4(0.f, 0.f, 0.f, 0.f), m4, v4, p4, t4v;
+          if (mode & ADAM_APPLY) { m4 = ldcg4(a.M + e); v4 = ldcg4(a.V + e); p4 = ldcg4(a.P + e); t4v = ldcg4(a.T + e); }
+          if (mode & ADAM_FROM_G) {
+            g = ldcg4(a.G + e);
+          } else {
+            float4 part[16];
+            for (int r0 = 0; r0 < NRB; r0 += 16) {             // the slabs' loads are issued together, added in row-block order
+#pragma unroll
+              for (int r = 0; r < 16; ++r) if (r0 + r < NRB) part[r] = ldcg4(gp + (long long)(r0 + r) * gs);
+#pragma unroll
+              for (int r = 0; r < 16; ++r) if (r0 + r < NRB) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
             }
           }
-          if (blockIdx.x == 0 && tid == 0 && a.losses) {
-            float v = 0.f;
-            const float* lp = ca.lpart + (critic ? i : N2 + i) * NRB;
-            for (int r = 0; r < NRB; ++r) v += __ldcg(lp + r);
-            a.losses[((long long)u * 2 + (critic ? 1 : 0)) * N2 + i] = v;
+          if (mode & ADAM_WRITE_G) st4(a.G + e, g);
+          if (mode & ADAM_APPLY) {
+            float gg[4] = {g.x, g.y, g.z, g.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+            float pp[4] = {p4.x, p4.y, p4.z, p4.w}, tt[4] = {t4v.x, t4v.y, t4v.z, t4v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float gk = gg[k] * a.grad_scale;
+              mm[k] = mm[k] + (1.0f - a.beta1) * (gk - mm[k]);
+              vv[k] = a.beta2 * vv[k] + (1.0f - a.beta2) * gk * gk;
+              const float denom = sqrtf(vv[k]) / bc2s[i] + a.eps;
+              pp[k] -= step_size[i] * (mm[k] / denom);
+              tt[k] = tt[k] + a.tau * (pp[k] - tt[k]);
+            }
+            st4(a.M + e, make_float4(mm[0], mm[1], mm[2], mm[3])); st4(a.V + e, make_float4(vv[0], vv[1], vv[2], vv[3]));
+            st4(a.P + e, make_float4(pp[0], pp[1], pp[2], pp[3])); st4(a.T + e, make_float4(tt[0], tt[1], tt[2], tt[3]));
           }
+        }
+        TP();
+        if (blockIdx.x == 0 && tid < N2 && a.losses) {
+          float v = 0.f;
+          const float* lp = ca.lpart + (critic ? tid : N2 + tid) * NRB;
+          for (int r = 0; r < NRB; ++r) v += __ldcg(lp + r);
+          a.losses[((long long)u * 2 + (critic ? 1 : 0)) * N2 + tid] = v;
         }
       }
       if (!(u == a.updates - 1 && ph == ca.cp_end - 1)) grid_barrier(a.s.bar, n_ctas);
@@ -890,7 +997,13 @@ int gwc_prepare(gw_learner* l) {
     return 0;
   }
   l->cluster_max_active = max_clusters;
-  return max_clusters >= clusters ? clusters * gwc::CL : 0;
+  if (max_clusters < clusters) return 0;
+  // every co-resident cluster is launched: those without a row block spread the Adam phases over more SMs
+  int launch = max_clusters;
+  if (const char* e = getenv("GW_LEARN_HELPERS")) launch = clusters + atoi(e);
+  if (launch > max_clusters) launch = max_clusters;
+  if (launch < clusters) launch = clusters;
+  return launch * gwc::CL;
 }
 
 int gwc_launch(gw_learner* l, const gwl::LearnArgs& a, int segment, cudaStream_t stream) {

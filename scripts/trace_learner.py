@@ -24,3 +24,7 @@ tot = (t[n] - t[0]) / mhz
 print(f"update: {tot:.1f} us over {n} phases (clock64 at {mhz:.0f} MHz)")
 for k in range(n):
     print(f"  phase {k:2d} {names[k]:20s} {(t[k + 1] - t[k]) / mhz:7.2f} us")
+
+if tr.learner.kernel == "cluster" and t[8]:                # built with GW_NVCC_FLAGS=-DGW_LEARN_TRACE: checkpoints inside phases A and B
+    pts = [x for x in t[8:108] if x]
+    print("checkpoints (us since phase A start):", " ".join(f"{(x - t[0]) / mhz:.1f}" for x in pts))
