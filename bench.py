@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--python-seconds", type=float, default=8.0, help="seconds per setting (FeAR off / on) of the Python reference leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-scale-points", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-5 extra (MADDPG training loop, custom_fear_10)")
+    ap.add_argument("--train-steps", type=int, default=6, help="timed vector steps of the config-5 extra at the reference learn cadence")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every step from Python instead of replaying a CUDA graph")
     ap.add_argument("--mode", default="rollout", choices=["rollout", "step"],
                     help="rollout: gw_rollout, up to --rollout-steps env steps per launch (default); step: one gw_step launch per step")
@@ -401,6 +403,51 @@ def masked_uniform_runs(a, E, dev, seeds=(0, 42, 66), steps=384):
     return out
 
 
+def train_extra(a, world, rank, dev):
+    """BASELINE.json configs[4]: the full MADDPG loop (rollout through the actor kernel, device replay ring, update kernel)
+    with custom_fear_10.yaml, a.envs environments per GPU.  Two cadences: the reference's (maddpg/agent.py:199-224 on the
+    global env count: global_envs // LEARN_STEP updates after every vector step -- the update kernel is the cost) and
+    round 1's batched one (one update every LEARN_STEP vector steps -- the rollout is the cost).  Device-timed region with a
+    barrier + synchronize on both sides, max over ranks; gradients all-reduced over NCCL when world > 1."""
+    import torch
+    import torch.distributed as dist
+    from marl_responsible_nav_b200 import maddpg
+    hp = maddpg.preset("custom_fear_10")
+    E = a.envs
+    out = {"config": f"custom_fear_10 (Level 3, FeAR weight -10, BATCH_SIZE 128, LEARN_STEP 10, MEMORY_SIZE 200000), {E} envs per GPU",
+           "envs_per_gpu": E, "global_envs": E * world}
+
+    def timed(tr, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        u0, t0 = tr.updates_done, time.perf_counter()
+        st = tr.train(k)
+        torch.cuda.synchronize()
+        el = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        el = float(el.item())
+        return {"vector_steps": k, "agent_steps_per_s": world * E * tr.env.n_learners * k / el, "updates": tr.updates_done - u0,
+                "updates_per_s": (tr.updates_done - u0) / el, "seconds": el,
+                "mean_return": st["return_sum"] / max(1, st["episodes"])}
+
+    for cadence, warm, k in (("reference", 2, a.train_steps), ("batched", 120, 600)):
+        env = maddpg.make_env(hp, E, device=dev, env_id_base=rank * E)
+        tr = maddpg.BatchedTrainer(env, hp=hp, seed=hp["SEED"], learn_cadence=cadence, global_envs=E * world)
+        tr.agent.broadcast_parameters(0)
+        tr.train(warm)
+        r = timed(tr, k)
+        r["updates_per_vector_step"] = tr.learn_schedule(0)
+        r["update_kernel"] = tr.learner.kernel if tr.learner is not None else "torch graph"
+        if world > 1:
+            r["gradient_exchange"] = "2 NCCL all-reduces per update (critics' / actors' flat gradients) between the update kernel's three segments"
+        out[cadence + "_cadence"] = r
+        del tr, env
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -513,6 +560,14 @@ def run_ours(a):
                 if world > 1:
                     break                                   # the ranks may be out of step: no further collectives in extras
 
+    # ---- BASELINE.json configs[4]: the MADDPG training loop (every N)
+    train = None
+    if not a.no_train:
+        try:
+            train = train_extra(a, world, rank, dev)
+        except Exception as exc:                            # an extra: must not cost the headline line
+            train = {"failed": repr(exc)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -543,7 +598,7 @@ def run_ours(a):
                                       if r_plan["eager_steps"] == 0 else f"{r_plan['eager_steps']} eager launches"))
                              + f"; at {E} envs one step moves {algo / 2**20:.1f} MiB ({algo / peak / 1e3:.2f} us at peak): small batches are "
                                "latency-bound (a warp's dependent chain per step), see scale_points for the step kernel at 1M envs"},
-        "scale_points": scale_points, "masked_uniform_runs": variants,
+        "scale_points": scale_points, "train": train, "masked_uniform_runs": variants,
         "workload_stats": {"episodes": stat_vec[0].item(), "mean_episode_len": stat_vec[1].item() / max(1.0, stat_vec[0].item()),
                            "learner_crashes_per_env_step": stat_vec[2].item() / (world * E * K),
                            "apples_per_env_step": stat_vec[3].item() / (world * E * K),

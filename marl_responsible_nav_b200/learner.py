@@ -68,6 +68,7 @@ class FusedLearner:
         N.check(self.lib.gw_learner_create(env._h, C.byref(cfg), C.byref(buf), C.byref(self._h)), env._h, "gw_learner_create")
         self.updates_done = 0
         self._loss_buf: Optional[torch.Tensor] = None
+        self.force_segmented = False                             # tests: take the several-rank path (three launches per update) on one rank
 
     # ---- the modules' parameters and the optimisers' moments become views of the flat vectors
     def _adopt(self, agent):
@@ -171,8 +172,9 @@ class FusedLearner:
         view = C.byref(ring._view())
         seed = int(sample_seed) & (2 ** 64 - 1)
         stream, h = self.env._stream(), self.env._h
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        if world == 1:
+        multi = dist.is_available() and dist.is_initialized()
+        world = dist.get_world_size() if multi else 1
+        if world == 1 and not self.force_segmented:
             N.check(self.lib.gw_learner_update(self._h, None, view, ring.t, seed, ring._draws + 1, updates, N.GW_LEARN_ALL, 1.0,
                                                losses.data_ptr(), stream), h, "gw_learner_update")
         else:
@@ -182,7 +184,7 @@ class FusedLearner:
                 for seg, flat in ((N.GW_LEARN_CRITIC_GRADS, g_cri), (N.GW_LEARN_ACTOR_GRADS, g_act), (N.GW_LEARN_FINISH, None)):
                     N.check(self.lib.gw_learner_update(self._h, None, view, ring.t, seed, ring._draws + 1 + u, 1, seg, scale,
                                                        lp, stream), h, "gw_learner_update")
-                    if flat is not None:
+                    if flat is not None and multi:
                         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         ring._draws += updates
         self.updates_done += updates
