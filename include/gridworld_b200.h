@@ -209,6 +209,9 @@ int gw_set_state(gw_handle* h, const void* src, int src_is_device, void* stream)
 int gw_get_stats(gw_handle* h, gw_stats* host_out, void* stream);   /* synchronises the stream */
 int gw_reset_stats(gw_handle* h, void* stream);
 int gw_launch_count(const gw_handle* h, uint64_t* kernels_launched); /* kernels launched by this handle so far */
+/* development aid: with GW_TRACE=1 in the environment gw_create allocates a per-CTA stamp buffer (16 x uint64 per CTA) that the
+ * resident step kernel fills; this copies it to the host (scripts/trace_server.py, scripts/trace_phases.py).  GW_EINVAL without it. */
+int gw_debug_trace(gw_handle* h, unsigned long long* host_out, int max_ctas);
 
 /* Operator level: C independent world updates (GWorld.UpdateGWorld with explicit actions).
  * n_agents_per_case NULL = cfg.n_agents everywhere.  apples: [C,2,2] (row,col), row<0 = absent, NULL = no apples;

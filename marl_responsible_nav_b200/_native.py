@@ -12,7 +12,7 @@ GW_OBS_F32, GW_OBS_BF16 = 0, 1
 
 EXPORTS = ["gw_abi_version", "gw_build_info", "gw_default_config", "gw_create", "gw_destroy", "gw_last_error",
            "gw_reset", "gw_step", "gw_rollout", "gw_step_host", "gw_host_call_prepare", "gw_host_call_run", "gw_host_call_reset", "gw_server_stop", "gw_server_info", "gw_sync", "gw_state_bytes", "gw_get_state", "gw_set_state", "gw_get_stats",
-           "gw_reset_stats", "gw_launch_count", "gw_update_world", "gw_fear_one_actor", "gw_fear_matrix", "gw_feal", "gw_actor_create", "gw_actor_update", "gw_actor_update_device",
+           "gw_reset_stats", "gw_launch_count", "gw_debug_trace", "gw_update_world", "gw_fear_one_actor", "gw_fear_matrix", "gw_feal", "gw_actor_create", "gw_actor_update", "gw_actor_update_device",
            "gw_actor_destroy", "gw_actor_forward", "gw_replay_sample", "gw_ln_relu_forward", "gw_ln_relu_backward", "gw_linear_backward",
            "gw_learner_layout_of", "gw_learner_create", "gw_learner_destroy", "gw_learner_update", "gw_learner_debug_ptr", "gw_learner_set_kernel", "gw_learner_kernel"]
 

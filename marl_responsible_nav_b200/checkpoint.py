@@ -75,10 +75,60 @@ def _portable_optimizer_state(opt: torch.optim.Optimizer) -> Dict:
     return {"state": state, "param_groups": groups}
 
 
+_DILL_TYPES = {"dict": dict, "list": list, "tuple": tuple, "int": int, "float": float, "bool": bool, "str": str, "bytes": bytes,
+               "NoneType": type(None), "type": type, "set": set, "frozenset": frozenset, "complex": complex, "slice": slice}
+
+
+def _dill_load_type(name):
+    """Stand-in for `dill._dill._load_type` (the reference saves with `pickle_module=dill`, which spells builtin types this
+    way): builtin value types only."""
+    if name not in _DILL_TYPES:
+        raise ValueError(f"type '{name}' is not allowed in a checkpoint")
+    return _DILL_TYPES[name]
+
+
+def _dill_create_array(f, args, state, npdict=None):
+    """Stand-in for `dill._dill._create_array`: numpy's own reconstructor, then the array state."""
+    if getattr(f, "__name__", "") != "_reconstruct" or not getattr(f, "__module__", "").startswith("numpy"):
+        raise ValueError("array constructor not allowed in a checkpoint")
+    arr = f(*args)
+    arr.__setstate__(state)
+    return arr
+
+
+def _safe_globals():
+    """The only non-tensor types the reference's checkpoint dict holds (see the module docstring): allow-listed for
+    `torch.load(weights_only=True)`, so that a `.pt` file given on the command line cannot run code on load."""
+    import collections
+    allow = [nn.MSELoss, torch.device, collections.OrderedDict, np.dtype, np.ndarray]
+    for name in ("scalar", "_reconstruct"):                           # files written under numpy 1.x name numpy.core, 2.x numpy._core
+        fn = None
+        for mod in ("numpy._core.multiarray", "numpy.core.multiarray"):
+            try:
+                fn = getattr(__import__(mod, fromlist=[name]), name)
+                break
+            except (ImportError, AttributeError):
+                continue
+        if fn is not None:
+            allow += [(fn, f"numpy.core.multiarray.{name}"), (fn, f"numpy._core.multiarray.{name}")]
+    allow += [(_dill_load_type, "dill._dill._load_type"), (_dill_create_array, "dill._dill._create_array")]
+    allow += [type(np.dtype(t)) for t in ("int64", "float64", "float32", "int32", "bool")]
+    return allow
+
+
+def _load_restricted(path: str):
+    try:
+        with torch.serialization.safe_globals(_safe_globals()):
+            return torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as exc:                                          # name the type instead of silently unpickling it
+        raise ValueError(f"{path}: cannot be read with the restricted unpickler ({type(exc).__name__}: {str(exc)[:300]}); only the "
+                         "types of the reference's MADDPG checkpoints are allowed") from exc
+
+
 def load_reference_checkpoint(path: str, device="cuda", hp: Optional[Dict] = None) -> maddpg.BatchedMADDPG:
     """A BatchedMADDPG with the networks, target networks, optimiser moments and hyper-parameters of a checkpoint written
     by the reference (or by `save_reference_checkpoint`)."""
-    ck = torch.load(path, map_location="cpu", weights_only=False)
+    ck = _load_restricted(path)
     if not isinstance(ck, dict) or "actors_state_dict" not in ck:
         raise ValueError(f"{path}: not a MADDPG checkpoint of the reference")
     if ck.get("arch", ck.get("net_config", {}).get("arch", "mlp")) != "mlp":
@@ -111,15 +161,18 @@ def load_reference_checkpoint(path: str, device="cuda", hp: Optional[Dict] = Non
                     for st in opt.state.values():
                         if torch.is_tensor(st.get("step")):
                             st["step"] = st["step"].to(device=agent.device, dtype=torch.float32)
-            except (ValueError, KeyError):                           # a fresh optimiser is a valid way to resume
-                pass
+            except (ValueError, KeyError) as exc:                    # a fresh optimiser is a valid way to resume -- but say so
+                import warnings
+                warnings.warn(f"{path}: optimiser state of '{key}' not restored ({exc}); Adam moments restart from zero")
     agent.steps = list(ck.get("steps", [0]))
     agent.scores = list(ck.get("scores", []))
     return agent
 
 
 def save_reference_checkpoint(agent: maddpg.BatchedMADDPG, path: str, steps: Optional[List[int]] = None) -> None:
-    """Write `agent` as the dict AgileRL's `MADDPG.load_checkpoint` (maddpg/agent.py:271-283) expects."""
+    """Write `agent` as the dict AgileRL's `MADDPG.load_checkpoint` expects: the reference reads it with
+    `MADDPGAgent.load_wo_memory` (maddpg/agent.py:279-283).  Its `load_checkpoint` (:268-277) additionally wants `memory.pkl`
+    and `steps.txt` next to the file -- the pickled AgileRL replay buffer and env, which this package does not produce."""
     n, hp = agent.n, agent.hp
     if getattr(agent, "learner", None) is not None:
         agent.learner.export_steps()                                 # the kernel counts Adam steps per network

@@ -75,6 +75,7 @@ extern "C" int gw_replay_sample(gw_handle* h, const gw_replay_view* ring, int64_
                                 float* reward, float* next_state, float* done, int64_t* t_out, int64_t* env_out,
                                 void* stream) {
   if (h == nullptr) return GW_EINVAL;
+  if (int rc = gw_server_stop(h)) return rc;           // a resident step kernel would hold this stream
   if (ring == nullptr || ring->struct_size != sizeof(gw_replay_view))
     return gw_fail(h, GW_EINVAL, "gw_replay_sample: ring view missing or of another size");
   const gw_replay_view& r = *ring;

@@ -168,6 +168,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 extern "C" int gw_ln_relu_forward(gw_handle* h, int64_t rows, int32_t width, const float* x, const float* gamma,
                                   const float* beta, float eps, float* y, float* mean, float* rstd, void* stream) {
   if (h == nullptr) return GW_EINVAL;
+  if (int rc = gw_server_stop(h)) return rc;           // a resident step kernel would hold this stream
   if (width != LN_W) return gw_fail(h, GW_EINVAL, "gw_ln_relu_forward: width must be 128");
   if (rows < 0 || !x || !gamma || !beta || !y || !mean || !rstd) return gw_fail(h, GW_EINVAL, "gw_ln_relu_forward: bad argument");
   if (!aligned16(x) || !aligned16(gamma) || !aligned16(beta) || !aligned16(y))
@@ -184,6 +185,7 @@ extern "C" int gw_ln_relu_backward(gw_handle* h, int64_t rows, int32_t width, co
                                    const float* mean, const float* rstd, const float* gamma, const float* beta, float* dx,
                                    float* dgamma, float* dbeta, void* stream) {
   if (h == nullptr) return GW_EINVAL;
+  if (int rc = gw_server_stop(h)) return rc;           // a resident step kernel would hold this stream
   if (width != LN_W) return gw_fail(h, GW_EINVAL, "gw_ln_relu_backward: width must be 128");
   if (rows < 1 || !dy || !x || !mean || !rstd || !gamma || !beta || !dx || !dgamma || !dbeta)
     return gw_fail(h, GW_EINVAL, "gw_ln_relu_backward: bad argument");
@@ -205,6 +207,7 @@ extern "C" int gw_linear_backward(gw_handle* h, int32_t batch, int32_t in_featur
                                   const float* x, int32_t x_row_stride, const float* w, float* dw, float* db, float* dx,
                                   void* stream) {
   if (h == nullptr) return GW_EINVAL;
+  if (int rc = gw_server_stop(h)) return rc;           // a resident step kernel would hold this stream
   if (batch < 1 || in_features < 1 || out_features < 1 || x_row_stride < in_features || !dy || !x || !w || !dw || !db)
     return gw_fail(h, GW_EINVAL, "gw_linear_backward: bad argument");
   LinBwdArgs a;
