@@ -621,10 +621,11 @@ class BatchedTrainer:
 
 
 def make_env(hp: Dict, num_envs: int, device="cuda", scenario="Level 3", obs_dtype=torch.float32, seed: Optional[int] = None,
-             env_id_base: int = 0):
-    """util.create_custom_ma_env (util.py:21-30) for a batch: WITH_FEAR / FeAR_weight / TRAIN_STEPS / SEED from the config."""
+             env_id_base: int = 0, env_kind: str = "multi"):
+    """util.create_custom_ma_env (util.py:21-30) for a batch: WITH_FEAR / FeAR_weight / TRAIN_STEPS / SEED from the config.
+    env_kind "single": the one-learner env of custom/customenv.py (what the reference's shipped checkpoints were trained on)."""
     from .batched import BatchedGridWorld
-    return BatchedGridWorld(scenario, num_envs=num_envs, device=device, env_kind="multi", fear=bool(hp["WITH_FEAR"]),
+    return BatchedGridWorld(scenario, num_envs=num_envs, device=device, env_kind=env_kind, fear=bool(hp["WITH_FEAR"]),
                             fear_weight=float(hp["FeAR_weight"]) if hp["WITH_FEAR"] else 0.0,
                             max_steps=int(hp["TRAIN_STEPS"]), auto_reset=True, obs_dtype=obs_dtype,
                             obs_layout="cnn" if hp.get("ARCH", "mlp") == "cnn" else "mlp",

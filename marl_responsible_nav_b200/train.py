@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="environments over all GPUs")
     ap.add_argument("--steps", type=int, default=1500, help="synchronous env steps (the reference: MAX_EPISODES x TRAIN_STEPS)")
     ap.add_argument("--report", type=int, default=150)
+    ap.add_argument("--env-kind", choices=("multi", "single"), default="multi", help="multi: custom/ma_customenv.py (2 learners); single: custom/customenv.py")
     ap.add_argument("--learn-cadence", choices=("reference", "batched"), default="reference",
                     help="reference: maddpg/agent.py:199-224 on the global env count (envs // LEARN_STEP updates after every "
                          "vector step); batched: --updates-per-learn updates every LEARN_STEP vector steps")
@@ -40,7 +41,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     base, n = sharding.shard_range(a.envs, rank, world)
-    env = maddpg.make_env(hp, n, device=dev, env_id_base=base)
+    env = maddpg.make_env(hp, n, device=dev, env_id_base=base, env_kind=a.env_kind)
     agent = None
     if a.load:
         from . import checkpoint
