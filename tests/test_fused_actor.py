@@ -1,5 +1,6 @@
 """GPU: the tcgen05 actor-forward kernel vs the same network evaluated by PyTorch in fp32 on the rendered observation.
-AgileRL is absent (parity unpinned); the tolerance is that of one bf16 128x128 GEMM with fp32 accumulation."""
+AgileRL is absent (parity unpinned); the tolerance is that of a bf16 GEMM chain with fp32 accumulation (3e-3 on the
+probabilities; the masked arg-max may differ only where the two best probabilities are closer than that)."""
 import pytest
 import torch
 
@@ -27,10 +28,14 @@ def test_fused_actor_matches_torch_fp32(E):
         cont, ids = fused.forward(out.obs_code, out.action_mask, training=False)
         for k in range(2):
             ref = _reference(agent.actors[k], out.obs[:, k])
-            assert torch.allclose(cont[:, k], ref, atol=2e-2), float((cont[:, k] - ref).abs().max())
+            # one bf16 GEMM chain with fp32 accumulation: measured max |dp| 0.7e-3 .. 1.3e-3 over 120 000 rows
+            # (scripts/actor_error_probe.py); the bound leaves 2.5x
+            assert torch.allclose(cont[:, k], ref, atol=3e-3), float((cont[:, k] - ref).abs().max())
             masked = ref.masked_fill(out.action_mask[:, k] == 0, -1.0)
-            agree = (masked.argmax(-1) == ids[:, k].long()).float().mean().item()
-            assert agree > 0.97, agree
+            differ = masked.argmax(-1) != ids[:, k].long()
+            assert differ.float().mean().item() < 0.005, differ.float().mean().item()
+            top2 = masked.topk(2, dim=-1).values                 # a different arg-max only where the two best are a rounding error apart
+            assert float((top2[:, 0] - top2[:, 1])[differ].max().item() if bool(differ.any()) else 0.0) < 3e-3
             assert (out.action_mask[:, k].gather(1, ids[:, k].long()[:, None]) == 1).all()     # never a masked action
         out = env.step(torch.randint(0, 9, (E, 2), generator=gen, device="cuda", dtype=torch.int8))
 

@@ -102,6 +102,23 @@ def test_rollout_gamemap_four_agents():
     _rollout_vs_oracle(2048, 25, seed=4, scenario="GameMap", n_agents=4, fear=True, auto_reset=True, max_steps=150)
 
 
+@pytest.mark.parametrize("scenario", ["Level 3", "Level 5", "GameMap"])
+@pytest.mark.parametrize("n_agents", [2, 3, 4])
+def test_rollout_every_layout_and_agent_count(scenario, n_agents):
+    """BASELINE config[3]: "all Scenarios.json layouts, 4 agents" -- every shipped layout with 2, 3 and 4 world agents
+    (2 learners + NPCs), FeAR on, against the C oracle."""
+    n_end, st = _rollout_vs_oracle(1024, 20, seed=30 + n_agents, scenario=scenario, n_agents=n_agents, fear=True, fear_weight=-5.0,
+                                   auto_reset=True, max_steps=150)
+    assert n_end > 0
+
+
+def test_rollout_oracle_diff_at_1m_envs():
+    """Config[3] size: the full 1 048 576-env batch against the C oracle (all host threads), two steps after the reset,
+    every output compared with == (1.3 GB of observations per step)."""
+    n_end, st = _rollout_vs_oracle(1 << 20, 2, seed=77, fear=True, fear_weight=-5.0, auto_reset=True, max_steps=150, threads=32)
+    assert st["env_steps"] == 2 << 20
+
+
 def test_rollout_single_env_kind():
     _rollout_vs_oracle(4096, 40, seed=5, env_kind="single", fear=True, auto_reset=True, max_steps=150)
 
