@@ -230,8 +230,18 @@ def device_timed_rollout(a, E, fear, K, W, world, rank, dev, sample_clocks=False
         return launches
 
     run(W, 0)
-    run(K, W)                                                     # the same launches as the timed region, untimed
+    launches = run(K, W)                                          # the same launches as the timed region, untimed
     env.sync()
+    # The timed launches are replayed from a CUDA graph (gw_rollout is capturable), as in device_timed: the timed region then
+    # holds the K env steps and one graph launch, not the Python / ctypes marshalling of the rollout call (~50 us, a third of
+    # a 20-step region).  --no-graph: the call itself is timed.
+    graph = None
+    if a.graph and K > 0:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            run(K, W + K)
+        graph.replay()                                            # warm-up of the graph itself
+        env.sync()
     env.reset_stats()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     flush.zero_()                                                 # L2 flush (256 MiB > 126 MB)
@@ -244,7 +254,10 @@ def device_timed_rollout(a, E, fear, K, W, world, rank, dev, sample_clocks=False
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    launches = run(K, W + K)
+    if graph is not None:
+        graph.replay()
+    else:
+        launches = run(K, W + K)
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -258,8 +271,8 @@ def device_timed_rollout(a, E, fear, K, W, world, rank, dev, sample_clocks=False
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(stat_vec, op=dist.ReduceOp.SUM)
-    plan = {"mode": "rollout", "rollout_launches": launches, "steps_per_launch": min(T, K), "graph_steps": 0, "graph_replays": 0,
-            "tail_graph_steps": 0, "eager_steps": 0}
+    plan = {"mode": "rollout", "rollout_launches": launches, "steps_per_launch": min(T, K), "graph_steps": K if graph is not None else 0,
+            "graph_replays": 1 if graph is not None else 0, "tail_graph_steps": 0, "eager_steps": 0}
     return {"ms": float(t_ms.item()), "stats": stat_vec, "env": env, "ring": rings.obs, "slots": slots, "L": L,
             "obs_bytes": obs_bytes, "clocks": clocks, "n_act": n_act, "plan": plan, "launches": launches}
 

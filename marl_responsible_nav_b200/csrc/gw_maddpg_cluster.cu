@@ -1036,6 +1036,10 @@ int gwc_launch(gw_learner* l, const gwl::LearnArgs& a, int segment, cudaStream_t
   at[1].id = cudaLaunchAttributeCooperative;
   at[1].val.cooperative = 1;
   cfg.attrs = at; cfg.numAttrs = 2;
+  // Profilers refuse the cooperative launch of a cluster kernel (ncu: LaunchFailed).  GW_LEARN_NO_COOP=1 drops the attribute:
+  // the grid (<= 33 clusters, one CTA per SM) is co-resident on an otherwise idle GPU anyway, which is all the barrier needs.
+  static const bool no_coop = getenv("GW_LEARN_NO_COOP") != nullptr;
+  if (no_coop) cfg.numAttrs = 1;
   GW_CUDA(l->h, cudaLaunchKernelEx(&cfg, gwc::gw_learn_cluster_kernel, ca));
   return GW_OK;
 }
