@@ -73,7 +73,7 @@ def _torch_update(ag, batch, g_next, g_cur):
         a_loss.backward()
         agr.append([p.grad.clone() for p in ag.actors[k].parameters()])
         ag.actor_opt[k].step()
-        losses[0, k], losses[1, k] = float(a_loss), float(c_loss)
+        losses[0, k], losses[1, k] = float(a_loss.detach()), float(c_loss.detach())
     with torch.no_grad():
         for net, tnet in zip(ag.actors + ag.critics, ag.actor_targets + ag.critic_targets):
             for p, tp in zip(net.parameters(), tnet.parameters()):
