@@ -45,6 +45,7 @@ extern "C" {
 #define GW_MAX_AGENTS 4
 #define GW_MAX_LEARNERS 2
 #define GW_N_ACTIONS 9        /* custom/custom_agent.py:140-150 */
+#define GW_MAX_BLOCKED 256
 #define GW_MAX_POLICIES 16
 #define GW_MAX_H 16
 #define GW_W 16
@@ -93,6 +94,14 @@ typedef struct gw_config {
   int64_t num_envs;                    /* E on this handle */
   int64_t env_id_base;                 /* global id of env 0 (sharding: results do not depend on the split) */
   uint64_t seed;                       /* device RNG key (Philox4x32-10) */
+  /* Restricted paths (GWorld.RestrictedPaths, custom/grid_world.py:32-86): single-cell moves `from -> to` that are refused
+   * (the agent stays, the move counts as restricted, :493-509).  A wall contributes both directions, a one-way the
+   * direction against it.  Cells as (row << 4) | col.  The reference builds these from Scenario['Map']['Walls'/'OneWays'],
+   * where JSON lists never compare equal to its tuple paths, so they are inert there; here they are enforced as the
+   * commented-out tuple conversion of LoadJsonScenario (:654-665) intends.  0 = none (every shipped scenario). */
+  int32_t n_blocked;
+  uint8_t blocked_from[GW_MAX_BLOCKED];
+  uint8_t blocked_to[GW_MAX_BLOCKED];
 } gw_config;
 
 /* Device pointers for one gw_reset / gw_step call.  NULL = not wanted / not given. */

@@ -6,6 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GW_LIB") or os.path.join(HERE, "csrc", "libgridworld_b200.so")
 
 GW_MAX_AGENTS, GW_MAX_LEARNERS, GW_N_ACTIONS, GW_MAX_POLICIES, GW_MAX_H, GW_W = 4, 2, 9, 16, 16, 16
+GW_MAX_BLOCKED = 256
 GW_OK, GW_EINVAL, GW_ENOMEM, GW_ECUDA, GW_ENODEV, GW_ESTATE = 0, -1, -2, -3, -4, -5
 GW_ENV_MULTI, GW_ENV_SINGLE = 0, 1
 GW_OBS_F32, GW_OBS_BF16 = 0, 1
@@ -66,6 +67,7 @@ class GwConfig(C.Structure):
         ("fear", C.c_int32), ("fear_radius", C.c_int32), ("fear_weight", C.c_double),
         ("max_steps", C.c_int32), ("auto_reset", C.c_int32), ("obs_dtype", C.c_int32), ("device", C.c_int32),
         ("num_envs", C.c_int64), ("env_id_base", C.c_int64), ("seed", C.c_uint64),
+        ("n_blocked", C.c_int32), ("blocked_from", C.c_uint8 * GW_MAX_BLOCKED), ("blocked_to", C.c_uint8 * GW_MAX_BLOCKED),
     ]
 
 
@@ -194,4 +196,10 @@ def build_config(scenario, num_envs=1, env_kind="multi", fear=True, fear_weight=
     cfg.obs_dtype = GW_OBS_BF16 if obs_bf16 else GW_OBS_F32
     cfg.device = int(device)
     cfg.num_envs, cfg.env_id_base, cfg.seed = int(num_envs), int(env_id_base), int(seed) & (2 ** 64 - 1)
+    blocked = list(getattr(scenario, "blocked", None) or [])
+    if len(blocked) > GW_MAX_BLOCKED:
+        raise ValueError(f"at most {GW_MAX_BLOCKED} restricted paths (walls count twice)")
+    cfg.n_blocked = len(blocked)
+    for k, (a, b) in enumerate(blocked):
+        cfg.blocked_from[k], cfg.blocked_to[k] = (int(a[0]) << 4) | int(a[1]), (int(b[0]) << 4) | int(b[1])
     return cfg

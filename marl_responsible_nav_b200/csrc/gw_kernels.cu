@@ -1830,6 +1830,11 @@ static int validate(const gw_config* c, std::string& why) {
     if (!((c->map_rows[r] >> col) & 1)) { why = "apple on an inactive cell"; return GW_EINVAL; }
   }
   if (c->env_kind == GW_ENV_SINGLE && c->apple_row[0] < 0) { why = "single env needs an apple"; return GW_EINVAL; }
+  if (c->n_blocked < 0 || c->n_blocked > GW_MAX_BLOCKED) { why = "n_blocked must be 0..256"; return GW_EINVAL; }
+  for (int k = 0; k < c->n_blocked; ++k) {
+    const int fr = c->blocked_from[k] >> 4, fc = c->blocked_from[k] & 15, tr = c->blocked_to[k] >> 4, tc = c->blocked_to[k] & 15;
+    if (fr >= c->height || tr >= c->height || std::abs(fr - tr) + std::abs(fc - tc) != 1) { why = "restricted path: cells must be adjacent and inside the grid"; return GW_EINVAL; }
+  }
   for (int i = 0; i < c->height * GW_W; ++i) {
     if (c->policy_map[i] >= c->n_policies) { why = "policy_map entry >= n_policies"; return GW_EINVAL; }
     if (c->mdr_map[i] >= GW_N_ACTIONS) { why = "mdr_map entry is not an action id"; return GW_EINVAL; }
@@ -1878,6 +1883,12 @@ static void build_next_cell(const gw_config* c, uint8_t* next) {
         const bool ok = tr >= 0 && tr < c->height && tc >= 0 && tc < c->width && ((c->map_rows[tr] >> tc) & 1);
         next[((r << 4) | col) * 4 + d] = (uint8_t)(ok ? ((tr << 4) | tc) : ((r << 4) | col));
       }
+  // restricted paths (walls / one-ways, grid_world.py:493-509): the move is refused like one into an inactive cell
+  for (int k = 0; k < c->n_blocked; ++k) {
+    const int from = c->blocked_from[k], to = c->blocked_to[k];
+    for (int d = 0; d < 4; ++d)
+      if ((from >> 4) + DR[d] == (to >> 4) && (from & 15) + DC[d] == (to & 15)) next[from * 4 + d] = (uint8_t)from;
+  }
 }
 
 // pair-mask table: the literal five-rule test (gw::pair_hit) for every relative start offset within Manhattan

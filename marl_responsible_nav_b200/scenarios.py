@@ -42,6 +42,10 @@ class Scenario:
     policies: List[Tuple[List[float], List[float]]]   # (stepWeights[3], directionWeights[4])
     mdr_action: np.ndarray                   # uint8 [H, W] Move-de-Rigueur action id per cell
     policy_keys: List[int] = field(default_factory=list)   # original JSON keys, for reporting
+    blocked: List[Tuple[Tuple[int, int], Tuple[int, int]]] = field(default_factory=list)   # restricted paths (from, to), see restricted_paths
+
+    def blocked_set(self):
+        return set(self.blocked) if self.blocked else None
 
     @property
     def shape(self) -> Tuple[int, int]:
@@ -105,8 +109,35 @@ def _ring_scenario(name: str, n_agents: int, outer_sw, inner_sw, corner_sw, rest
                     mdr_action=mdr, policy_keys=[z[0] for z in zones])
 
 
-def builtin_scenario(name: str = "Level 3", n_agents: Optional[int] = None) -> Scenario:
-    """The three layouts of custom/Scenarios.json.  `n_agents` overrides the scenario's N_Agents."""
+def restricted_paths(shape, walls=(), oneways=()) -> List[Tuple[Tuple[int, int], Tuple[int, int]]]:
+    """GWorld.RestrictedPaths (custom/grid_world.py:32-86) as (from, to) cell pairs: a wall [a, b] blocks a -> b and b -> a,
+    a one-way [a, b] blocks b -> a; entries whose cells are not inside the grid or not 4-neighbours are dropped, as there.
+    In the reference the paths only take effect when their cells are TUPLES (`[old, new] in RestrictedPaths`, :498, with
+    tuple locations); the JSON loader hands over lists, which never match (the tuple conversion is commented out, :654-665).
+    This function gives the intended, tuple-typed semantics."""
+    h, w = shape
+    out = []
+
+    def ok(a, b):
+        (x1, y1), (x2, y2) = a, b
+        if not (x1 < h and x2 < h and y1 < w and y2 < w) or min(x1, y1, x2, y2) < 0:
+            return False
+        return (x1 == x2 and abs(y1 - y2) == 1) or (y1 == y2 and abs(x1 - x2) == 1)
+
+    for wall in walls:
+        a, b = (int(wall[0][0]), int(wall[0][1])), (int(wall[1][0]), int(wall[1][1]))
+        if ok(a, b):
+            out += [(a, b), (b, a)]
+    for way in oneways:
+        a, b = (int(way[0][0]), int(way[0][1])), (int(way[1][0]), int(way[1][1]))
+        if ok(a, b):
+            out.append((b, a))
+    return out
+
+
+def builtin_scenario(name: str = "Level 3", n_agents: Optional[int] = None, walls=(), oneways=()) -> Scenario:
+    """The three layouts of custom/Scenarios.json.  `n_agents` overrides the scenario's N_Agents; `walls` / `oneways`
+    (lists of [cell, cell]) add restricted paths with the semantics of `restricted_paths`."""
     if name == "Level 3":        # 4 agents; outer ring at speed 2, inner ring at speed 1, elsewhere stay-or-one-step
         sc = _ring_scenario(name, 4, outer_sw=[0, 0, 1], inner_sw=[0, 1, 0], corner_sw=[0, 0, 1], rest_sw=[1, 1, 0])
     elif name == "Level 5":      # 3 agents; ring traffic may also stay or move one cell
@@ -122,6 +153,7 @@ def builtin_scenario(name: str = "Level 3", n_agents: Optional[int] = None) -> S
         raise KeyError(f"unknown built-in scenario {name!r} (have 'Level 3', 'Level 5', 'GameMap')")
     if n_agents is not None:
         sc.n_agents = int(n_agents)
+    sc.blocked = restricted_paths(sc.region.shape, walls, oneways)
     return sc
 
 
@@ -129,15 +161,21 @@ def _as_slice(arg) -> slice:
     return slice(arg[0], arg[1], None if arg[2] == 0 else arg[2])       # custom/grid_world.py:633-639
 
 
-def load_scenario_json(path: str, name: str = "Level 3", n_agents: Optional[int] = None) -> Scenario:
-    """Read one scenario from a file in the reference's Scenarios.json format."""
+def load_scenario_json(path: str, name: str = "Level 3", n_agents: Optional[int] = None, walls: str = "refuse") -> Scenario:
+    """Read one scenario from a file in the reference's Scenarios.json format.
+    walls: what to do with non-empty Map.Walls / Map.OneWays -- "refuse" (default: raise, the caller must choose),
+    "inert" (the reference's actual behaviour: JSON lists never equal its tuple paths, custom/grid_world.py:498, so they
+    restrict nothing) or "enforce" (the intended semantics, see `restricted_paths`)."""
     with open(path) as f:
         sc = json.load(f)[name]
     region = (np.array(sc["Map"]["Region"]) == 1).astype(np.int8)
+    blocked = []
     if sc["Map"].get("Walls") or sc["Map"].get("OneWays"):
-        # In the reference these are inert: JSON lists never compare equal to the tuple paths
-        # (custom/grid_world.py:493,498; SURVEY A.7).  Refuse rather than silently diverge.
-        raise ValueError("Walls / OneWays are not supported (they have no effect in the reference either)")
+        if walls == "enforce":
+            blocked = restricted_paths(region.shape, sc["Map"].get("Walls") or (), sc["Map"].get("OneWays") or ())
+        elif walls != "inert":
+            raise ValueError("the scenario has Walls / OneWays: pass walls='inert' (what the reference does with a JSON file: "
+                             "nothing, its list paths never match) or walls='enforce' (the intended restricted paths)")
     if sc.get("AgentLocations"):
         raise ValueError("fixed AgentLocations are not supported; all shipped scenarios spawn randomly")
     policy_index = np.zeros(region.shape, dtype=np.uint8)
@@ -165,4 +203,4 @@ def load_scenario_json(path: str, name: str = "Level 3", n_agents: Optional[int]
             mdr_of[int(key)] = int(m["mdr"])
         mdr_action = np.vectorize(lambda k: mdr_of[int(k)])(key_map).astype(np.uint8)
     return Scenario(name=name, region=region, n_agents=int(n_agents if n_agents is not None else sc["N_Agents"]),
-                    policy_index=policy_index, policies=policies, mdr_action=mdr_action, policy_keys=keys)
+                    policy_index=policy_index, policies=policies, mdr_action=mdr_action, policy_keys=keys, blocked=blocked)

@@ -79,6 +79,16 @@ typedef struct {
 
 static int cell_eq(cell_t a, cell_t b) { return a.r == b.r && a.c == b.c; }
 
+/* `[old, new] in self.RestrictedPaths` (grid_world.py:498) with the tuple-typed paths the reference intends (:654-665):
+ * a linear search of the list, as there */
+static int path_restricted(const gw_config* cfg, cell_t a, cell_t b) {
+  for (int k = 0; k < cfg->n_blocked; ++k)
+    if ((cfg->blocked_from[k] >> 4) == a.r && (cfg->blocked_from[k] & 15) == a.c && (cfg->blocked_to[k] >> 4) == b.r &&
+        (cfg->blocked_to[k] & 15) == b.c)
+      return 1;
+  return 0;
+}
+
 static void update_world(const gw_config* cfg, int n, const cell_t* loc0, const int* act, const cell_t* apples,
                          const int* apple_on, int n_eaters, update_out* out) {
   cell_t path[GW_MAX_AGENTS][MAXSTEPS + 1];
@@ -100,8 +110,10 @@ static void update_world(const gw_config* cfg, int n, const cell_t* loc0, const 
       if (cl.c < 0) cl.c = 0;
       if (cl.c > cfg->width - 1) cl.c = cfg->width - 1;
       if (!cell_eq(cl, nw)) { restr[i] = 1; nw = cl; }
-      if (cfg_active(cfg, nw.r, nw.c)) path[i][plen[i]++] = nw;                     /* :496-499 */
-      else { path[i][plen[i]++] = old; restr[i] = 1; }                              /* :512-515 */
+      if (cfg_active(cfg, nw.r, nw.c)) {                                            /* :496 */
+        if (!path_restricted(cfg, old, nw)) path[i][plen[i]++] = nw;                /* :498-499 */
+        else { path[i][plen[i]++] = old; restr[i] = 1; }                            /* :504-507: AgentPath in RestrictedPaths */
+      } else { path[i][plen[i]++] = old; restr[i] = 1; }                            /* :512-515 */
     }
     int count = n, loops = 0;                                                       /* :247-248 */
     while (count > 0 && loops < 2 * n) {                                            /* :250 */

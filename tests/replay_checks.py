@@ -88,8 +88,21 @@ def obs_f32(backend, arr):
 
 
 # ----------------------------------------------------------------------------- operator level
-def check_update_cases(make_backend):
-    g = npz("update_cases.npz")
+def wall_scenario():
+    """Level 3 with the walls / one-ways of tests/golden/wall_cases.npz (recorded from the reference run with tuple-typed
+    paths, make_wall_golden.py), enforced."""
+    from marl_responsible_nav_b200 import builtin_scenario
+    g = npz("wall_cases.npz")
+    return builtin_scenario("Level 3", walls=g["walls"].tolist(), oneways=g["oneways"].tolist())
+
+
+def _prefixed(name, prefix):
+    g = npz(name)
+    return {k[len(prefix):]: g[k] for k in g.files if k.startswith(prefix)} if prefix else g
+
+
+def check_update_cases(make_backend, fixture="update_cases.npz", prefix=""):
+    g = _prefixed(fixture, prefix)
     b = make_backend(num_envs=1, fear=False)
     pos = np.where(g["locs"] < 0, 0, g["locs"]).astype(np.int8)
     new_pos, crash, restr, caught = b.update_world(pos, g["acts"], n_agents=g["n"], apples=g["apples"])
@@ -100,8 +113,8 @@ def check_update_cases(make_backend):
     return len(g["n"])
 
 
-def check_fear_cases(make_backend):
-    g = npz("fear_cases.npz")
+def check_fear_cases(make_backend, fixture="fear_cases.npz", prefix=""):
+    g = _prefixed(fixture, prefix)
     b = make_backend(num_envs=1, fear=True)
     pos = np.where(g["locs"] < 0, 0, g["locs"]).astype(np.int8)
     resp, n_mdr, n_act, fsum = b.fear_one_actor(pos, g["acts"], g["mdr"], g["actor"], in_list=g["in_list"], n_agents=g["n"])
@@ -128,9 +141,9 @@ def check_matrix_cases(make_backend):
 
 
 # ----------------------------------------------------------------------------- multi-agent episodes
-def check_ma_episodes(make_backend, obs_bf16=False):
+def check_ma_episodes(make_backend, obs_bf16=False, fixture="ma_episodes.npz"):
     """All golden episodes of one FeAR setting run side by side, one env per episode."""
-    g = npz("ma_episodes.npz")
+    g = npz(fixture)
     total = 0
     for fear in (False, True):
         eps = np.flatnonzero(g["ep_fear"] == fear)

@@ -19,6 +19,18 @@ def test_fear_cases():
     assert RC.check_fear_cases(make) == 500
 
 
+def make_walls(**kw):
+    return c_oracle.COracle(RC.wall_scenario(), **kw)
+
+
+def test_walls_and_oneways_golden():
+    """Restricted paths with the tuple semantics the reference intends: UpdateGWorld, FeAR and whole episodes recorded by
+    running the reference with tuple-typed Walls / OneWays (tests/golden/make_wall_golden.py)."""
+    assert RC.check_update_cases(make_walls, "wall_cases.npz", "u_") == 3000
+    assert RC.check_fear_cases(make_walls, "wall_cases.npz", "f_") == 300
+    assert RC.check_ma_episodes(make_walls, fixture="wall_ma_episodes.npz") > 4000
+
+
 def test_fear_matrix_and_feal_cases():
     assert RC.check_matrix_cases(make) == 160
 

@@ -28,6 +28,17 @@ def test_fear_matrix_and_feal_golden():
     assert RC.check_matrix_cases(make) == 160
 
 
+def test_walls_and_oneways_golden():
+    """f4: restricted paths (walls both ways, one-ways against their direction) enforced by the kernels' next-cell table,
+    against what the reference computes when its paths are tuple-typed (wall_cases.npz, wall_ma_episodes.npz) and against
+    the C oracle on a device-RNG rollout."""
+    mk = lambda **kw: RC.GpuBackend(RC.wall_scenario(), **kw)
+    assert RC.check_update_cases(mk, "wall_cases.npz", "u_") == 3000
+    assert RC.check_fear_cases(mk, "wall_cases.npz", "f_") == 300
+    assert RC.check_ma_episodes(mk, fixture="wall_ma_episodes.npz") > 4000
+    _rollout_vs_oracle(2048, 25, seed=12, scenario=RC.wall_scenario(), fear=True, fear_weight=-5.0, auto_reset=True, max_steps=150)
+
+
 def test_ma_episodes_golden():
     assert RC.check_ma_episodes(make) > 1500
 

@@ -120,3 +120,41 @@ def test_policy_tables_golden(golden_dir):
     assert np.array_equal(O.generate_policy([0, 0, 1], [0, 0, 0, 1]), t["Level3_policy_base"][1])
     assert np.array_equal(O.generate_policy([0, 0, 1], None), t["Level3_policy_perturbed"][1])
     assert np.array_equal(O.generate_policy([0, 1, 0], [0, 0, 0, 1]), t["Level3_policy_base"][5])
+
+
+def test_walls_and_oneways_golden(golden_dir, level3):
+    """Restricted paths (walls / one-ways) with the tuple semantics the reference intends: the host-side path list equals
+    the RestrictedPaths GWorld built, and the Python restatement reproduces what the reference's UpdateGWorld /
+    FeAR_4_one_actor return with them (wall_cases.npz, recorded by tests/golden/make_wall_golden.py).  Without the paths
+    a good share of the cases comes out differently: the fixture does exercise them."""
+    from marl_responsible_nav_b200.scenarios import restricted_paths
+    g = _npz(golden_dir, "wall_cases.npz")
+    region = level3.region
+    blocked_list = restricted_paths(region.shape, g["walls"].tolist(), g["oneways"].tolist())
+    want = [((int(p[0][0]), int(p[0][1])), (int(p[1][0]), int(p[1][1]))) for p in g["restricted_paths"]]
+    assert blocked_list == want and len(want) == 44
+    blocked = set(blocked_list)
+    differs = 0
+    for c in range(len(g["u_n"])):
+        n = int(g["u_n"][c])
+        locs = [tuple(int(v) for v in g["u_locs"][c, i]) for i in range(n)]
+        acts = [int(a) for a in g["u_acts"][c, :n]]
+        apples = {k: tuple(int(v) for v in g["u_apples"][c, k]) for k in range(2) if g["u_apples"][c, k, 0] >= 0}
+        kw = dict(apples=apples, eaters=list(range(min(2, n)))) if apples else {}
+        new_locs, crash, restr, caught, _ = O.update_world(region, locs, acts, blocked=blocked, **kw)
+        assert new_locs == [tuple(int(v) for v in g["u_out_locs"][c, i]) for i in range(n)], c
+        assert crash == list(g["u_crash"][c, :n]) and restr == list(g["u_restr"][c, :n]), c
+        cm = np.zeros((2, 2), np.int8)
+        for idx, k in caught:
+            cm[idx, k] += 1
+        assert np.array_equal(cm, g["u_caught"][c]), c
+        differs += O.update_world(region, locs, acts, **kw)[:3] != (new_locs, crash, restr)
+    assert differs > 200, differs
+    for c in range(0, len(g["f_n"]), 3):
+        n = int(g["f_n"][c])
+        locs = [tuple(int(v) for v in g["f_locs"][c, i]) for i in range(n)]
+        lst = [(i, int(g["f_acts"][c, i])) for i in range(n) if g["f_in_list"][c, i]]
+        actor = int(g["f_actor"][c])
+        resp, n_mdr, n_act = O.fear_one_actor(region, locs, lst, [int(m) for m in g["f_mdr"][c, :n]], actor, blocked)
+        assert np.array_equal(resp[actor], g["f_resp"][c, :n]), c
+        assert np.array_equal(n_mdr[actor], g["f_n_mdr"][c, :n]) and np.array_equal(n_act[actor], g["f_n_act"][c, :n]), c
