@@ -448,13 +448,15 @@ def train_extra(a, world, rank, dev):
     for cadence, warm, k in (("reference", 2, a.train_steps), ("batched", 120, 600)):
         env = maddpg.make_env(hp, E, device=dev, env_id_base=rank * E)
         tr = maddpg.BatchedTrainer(env, hp=hp, seed=hp["SEED"], learn_cadence=cadence, global_envs=E * world)
-        tr.agent.broadcast_parameters(0)
+        exchange = tr.connect(0)
         tr.train(warm)
         r = timed(tr, k)
         r["updates_per_vector_step"] = tr.learn_schedule(0)
         r["update_kernel"] = tr.learner.kernel if tr.learner is not None else "torch graph"
         if world > 1:
-            r["gradient_exchange"] = "2 NCCL all-reduces per update (critics' / actors' flat gradients) between the update kernel's three segments"
+            r["gradient_exchange"] = ("inside the update kernel over NVLink peer memory (all-gather of the ranks' flat gradients + local sum, "
+                                      "one launch per block of updates)" if exchange == "peer" else
+                                      "2 NCCL all-reduces per update (critics' / actors' flat gradients) between the update kernel's three segments")
         out[cadence + "_cadence"] = r
         del tr, env
         torch.cuda.empty_cache()

@@ -377,6 +377,21 @@ int gw_learner_update(gw_learner* l, const gw_learn_batch* batch, const gw_repla
 #define GW_LEARN_KERNEL_CLUSTER 2
 int gw_learner_set_kernel(gw_learner* l, int32_t kind);
 int gw_learner_kernel(const gw_learner* l);
+/* Data-parallel training, gradient exchange INSIDE the update kernel (cluster kernel, GW_LEARN_ALL): one process per GPU,
+ * every rank exports a small exchange block (its flat gradient vector + arrival words, a cudaMalloc of the library's own) as
+ * a CUDA IPC handle, the host exchanges the handles (torch.distributed all_gather), every rank connects.  From then on each
+ * Adam phase of gw_learner_update writes this rank's gradient to its block, passes a barrier across ALL ranks' grids (arrival
+ * words stored over NVLink into the peers' blocks) and adds every rank's gradient in rank order with loads over NVLink: no
+ * NCCL call and no host round trip per update, `updates` per launch as on one GPU, parameters bit-identical on all ranks.
+ * Every rank must issue the same sequence of gw_learner_update calls.  A peer that does not arrive within 5 s
+ * (GW_PEER_TIMEOUT_MS) is reported by gw_learner_peer_status instead of hanging the GPU.  The segmented calls
+ * (GW_LEARN_CRITIC_GRADS ...) remain for exchanges done by the caller (NCCL: maddpg/agent.py has no counterpart, the reference
+ * trains on one device). */
+#define GW_MAX_PEERS 8
+typedef struct gw_peer_handle { uint8_t bytes[64]; } gw_peer_handle;
+int gw_learner_peer_export(gw_learner* l, gw_peer_handle* out);
+int gw_learner_peer_connect(gw_learner* l, int32_t rank, int32_t world, const gw_peer_handle* handles /* [world] */);
+int gw_learner_peer_status(gw_learner* l, int32_t* world, int32_t* timed_out);
 /* intermediate tensors of the last update, by name (tests / debugging): "a2", "q", "y", "dq", "anew", "ax", "dz2", "dh1",
  * "dz1", "adz2", "adh1", "adz1", and "<pass>.<z1|h1|st1|z2|h2|st2>" with pass in ta / ct / c / ac / c2; index = agent */
 int gw_learner_debug_ptr(gw_learner* l, const char* name, int index, float** ptr, int64_t* floats);

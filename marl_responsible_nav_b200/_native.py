@@ -15,7 +15,8 @@ EXPORTS = ["gw_abi_version", "gw_build_info", "gw_default_config", "gw_create", 
            "gw_reset", "gw_step", "gw_rollout", "gw_step_host", "gw_host_call_prepare", "gw_host_call_run", "gw_host_call_reset", "gw_server_stop", "gw_server_info", "gw_sync", "gw_state_bytes", "gw_get_state", "gw_set_state", "gw_get_stats",
            "gw_reset_stats", "gw_launch_count", "gw_debug_trace", "gw_update_world", "gw_fear_one_actor", "gw_fear_matrix", "gw_feal", "gw_actor_create", "gw_actor_update", "gw_actor_update_device",
            "gw_actor_destroy", "gw_actor_forward", "gw_replay_sample", "gw_ln_relu_forward", "gw_ln_relu_backward", "gw_linear_backward",
-           "gw_learner_layout_of", "gw_learner_create", "gw_learner_destroy", "gw_learner_update", "gw_learner_debug_ptr", "gw_learner_set_kernel", "gw_learner_kernel"]
+           "gw_learner_layout_of", "gw_learner_create", "gw_learner_destroy", "gw_learner_update", "gw_learner_debug_ptr", "gw_learner_set_kernel", "gw_learner_kernel",
+           "gw_learner_peer_export", "gw_learner_peer_connect", "gw_learner_peer_status"]
 
 
 class GwActorWeights(C.Structure):
@@ -47,6 +48,13 @@ class GwLearnerBuffers(C.Structure):
 
 class GwLearnBatch(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("state", "action", "reward", "next_state", "done", "gumbel_next", "gumbel_cur")]
+
+
+GW_MAX_PEERS = 8
+
+
+class GwPeerHandle(C.Structure):
+    _fields_ = [("bytes", C.c_uint8 * 64)]
 
 
 GW_LEARN_ALL, GW_LEARN_CRITIC_GRADS, GW_LEARN_ACTOR_GRADS, GW_LEARN_FINISH = 0, 1, 2, 3
@@ -145,6 +153,9 @@ def load():
     lib.gw_learner_destroy.argtypes = [vp]
     lib.gw_learner_update.argtypes = [vp, C.POINTER(GwLearnBatch), C.POINTER(GwReplayView), i64, C.c_uint64, C.c_uint64,
                                       C.c_int32, C.c_int32, C.c_float, vp, vp]
+    lib.gw_learner_peer_export.argtypes = [vp, C.POINTER(GwPeerHandle)]
+    lib.gw_learner_peer_connect.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(GwPeerHandle)]
+    lib.gw_learner_peer_status.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.gw_learner_set_kernel.argtypes = [vp, C.c_int32]
     lib.gw_learner_kernel.argtypes = [vp]
     lib.gw_learner_debug_ptr.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(vp), C.POINTER(i64)]

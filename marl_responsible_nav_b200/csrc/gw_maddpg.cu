@@ -851,7 +851,71 @@ extern "C" int gw_learner_create(gw_handle* h, const gw_learner_config* cfg, con
 }
 
 extern "C" int gw_learner_destroy(gw_learner* l) {
+  if (l) {
+    for (int q = 0; q < GW_MAX_PEERS; ++q) {
+      if (!l->peer_base[q]) continue;
+      if (q == l->peer_rank) cudaFree(l->peer_base[q]); else cudaIpcCloseMemHandle(l->peer_base[q]);
+    }
+  }
   delete l;
+  return GW_OK;
+}
+
+// ---- gradient exchange of a data-parallel run over NVLink peer memory (one process per GPU, CUDA IPC)
+extern "C" int gw_learner_peer_export(gw_learner* l, gw_peer_handle* out) {
+  if (!l || !out) return GW_EINVAL;
+  gw_handle* h = l->h;
+  static_assert(sizeof(gw_peer_handle) == sizeof(cudaIpcMemHandle_t), "gw_peer_handle carries a cudaIpcMemHandle_t");
+  if (gw_learner_kernel(l) != GW_LEARN_KERNEL_CLUSTER) return gw_fail(h, GW_ESTATE, "gw_learner_peer_export: the exchange lives in the cluster kernel");
+  GW_CUDA(h, cudaSetDevice(h->cfg.device));
+  if (!l->peer_base[l->peer_rank]) {
+    l->peer_flag_off = (size_t)round_up(l->lay.param_floats * 4, 256);
+    void* p = nullptr;
+    const size_t bytes = l->peer_flag_off + 8 * GW_MAX_PEERS + 256;
+    GW_CUDA(h, cudaMalloc(&p, bytes));                 // a whole allocation of its own: what CUDA IPC can share
+    GW_CUDA(h, cudaMemset(p, 0, bytes));
+    l->peer_base[l->peer_rank] = p;
+  }
+  cudaIpcMemHandle_t ipc;
+  GW_CUDA(h, cudaIpcGetMemHandle(&ipc, l->peer_base[l->peer_rank]));
+  std::memcpy(out->bytes, &ipc, sizeof(ipc));
+  return GW_OK;
+}
+
+extern "C" int gw_learner_peer_connect(gw_learner* l, int32_t rank, int32_t world, const gw_peer_handle* handles) {
+  if (!l || !handles) return GW_EINVAL;
+  gw_handle* h = l->h;
+  if (world < 2 || world > GW_MAX_PEERS || rank < 0 || rank >= world) return gw_fail(h, GW_EINVAL, "gw_learner_peer_connect: world 2..8, 0 <= rank < world");
+  if (!l->peer_base[l->peer_rank]) return gw_fail(h, GW_ESTATE, "gw_learner_peer_connect: call gw_learner_peer_export first");
+  if (l->peer_world > 1) return gw_fail(h, GW_ESTATE, "gw_learner_peer_connect: already connected");
+  GW_CUDA(h, cudaSetDevice(h->cfg.device));
+  void* own = l->peer_base[l->peer_rank];
+  l->peer_base[l->peer_rank] = nullptr;
+  l->peer_rank = rank;
+  l->peer_base[rank] = own;
+  for (int q = 0; q < world; ++q) {
+    if (q == rank) continue;
+    cudaIpcMemHandle_t ipc;
+    std::memcpy(&ipc, handles[q].bytes, sizeof(ipc));
+    void* p = nullptr;
+    GW_CUDA(h, cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+    l->peer_base[q] = p;
+  }
+  l->peer_world = world;
+  return GW_OK;
+}
+
+extern "C" int gw_learner_peer_status(gw_learner* l, int32_t* world, int32_t* timed_out) {
+  if (!l) return GW_EINVAL;
+  if (world) *world = l->peer_world;
+  if (timed_out) {
+    *timed_out = 0;
+    if (l->peer_world > 1) {
+      unsigned int e = 0;
+      GW_CUDA(l->h, cudaMemcpy(&e, static_cast<char*>(l->peer_base[l->peer_rank]) + l->peer_flag_off + 8 * GW_MAX_PEERS, 4, cudaMemcpyDeviceToHost));
+      *timed_out = (int32_t)e;
+    }
+  }
   return GW_OK;
 }
 

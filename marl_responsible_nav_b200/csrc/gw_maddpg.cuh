@@ -183,7 +183,12 @@ struct gw_learner {
   float* cluster_scratch = nullptr;          // gradient slabs of the cluster kernel (inside the caller's scratch block)
   int cluster_grid = 0;                      // CTAs of the cluster kernel, 0: shape unsupported / clusters not co-resident
   int kernel_kind = GW_LEARN_KERNEL_AUTO;
-  int cluster_max_active = -1;               // cudaOccupancyMaxActiveClusters of the cluster kernel on this device
+  int cluster_max_active = -1;
+  // gradient exchange over peer memory (gw_learner_peer_export / _connect): exchange block of every rank, mapped here
+  int peer_world = 1, peer_rank = 0;
+  void* peer_base[GW_MAX_PEERS] = {};         // [rank] = this process's own cudaMalloc block; the others cudaIpcOpenMemHandle
+  size_t peer_flag_off = 0;                   // byte offset of the arrival words (then the error word) behind the gradient vector
+  unsigned long long peer_epochs = 0;         // exchanges done so far (two per update)               // cudaOccupancyMaxActiveClusters of the cluster kernel on this device
 };
 
 // gw_maddpg_cluster.cu

@@ -64,9 +64,54 @@ struct ClusterArgs {
   float* lpart;                             // [2n][B / 16] loss partial sums (critics, then actors)
   long long gstride[2 * MAXN];
   int cp_begin, cp_end;                     // cluster-kernel phases: 0 A, 1 Adam C, 2 B, 3 Adam A
+  // data-parallel gradient exchange over NVLink peer memory (world > 1): every rank's exchange block, mapped into this process
+  int world, rank;
+  float* peer_g[GW_MAX_PEERS];              // [world] flat gradient vector of rank p (this rank's own at [rank])
+  unsigned long long* peer_flag[GW_MAX_PEERS];   // [world] rank p's arrival words: peer_flag[p][q] = last epoch rank q has published
+  unsigned long long epoch0;                // exchanges completed before this launch
+  unsigned long long timeout_ns;
+  unsigned int* peer_err;                   // set to 1 if a peer did not arrive in time (the launch then finishes without it)
 };
 
 // ------------------------------------------------------------------------------------------------ primitives
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Grid barrier that is also a barrier ACROSS the ranks of a data-parallel run: every CTA releases its writes at system scope
+// and arrives; the last CTA of this GPU publishes `epoch` in every peer's arrival row (a store over NVLink into the peer's
+// exchange block), waits until every peer has published it in ours, and only then opens the barrier for the other CTAs.
+// What any rank wrote to its exchange block before the barrier can be read by every rank after it (volatile loads: peer
+// memory is not cached here).  A peer that does not arrive within timeout_ns sets the error word instead of hanging the GPU.
+__device__ __forceinline__ void grid_barrier_peers(unsigned* bar, unsigned n_ctas, const ClusterArgs& ca, unsigned long long epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned gen = *reinterpret_cast<volatile unsigned*>(bar + 1);
+    __threadfence_system();
+    if (atomicAdd(bar, 1u) == n_ctas - 1) {
+      *reinterpret_cast<volatile unsigned*>(bar) = 0u;
+      __threadfence_system();
+      for (int p = 0; p < ca.world; ++p)
+        if (p != ca.rank) *reinterpret_cast<volatile unsigned long long*>(ca.peer_flag[p] + ca.rank) = epoch;
+      const unsigned long long t0 = global_ns();
+      for (int q = 0; q < ca.world; ++q) {
+        if (q == ca.rank) continue;
+        while (*reinterpret_cast<volatile unsigned long long*>(ca.peer_flag[ca.rank] + q) < epoch) {
+          if (global_ns() - t0 > ca.timeout_ns) { *ca.peer_err = 1u; break; }
+        }
+      }
+      __threadfence_system();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*reinterpret_cast<volatile unsigned*>(bar + 1) == gen) {}
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ float4 ldcv4(const float* p) { return __ldcv(reinterpret_cast<const float4*>(p)); }
+
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -903,23 +948,45 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
         }
         // four parameters per thread and step (every vector is 16-byte aligned, every network block padded to 4 floats; the
         // padding carries zero gradients and stays zero); both networks of the kind share the index space
+        auto local_gradient = [&](int net, int i4) {             // the row blocks' slabs, added in row-block order
+          const float* gp = ca.gpart[net] + 4 * i4;
+          const long long gs = ca.gstride[net];
+          float4 g = make_float4(0.f, 0.f, 0.f, 0.f), part[16];
+          for (int r0 = 0; r0 < NRB; r0 += 16) {                 // the loads are issued together
+#pragma unroll
+            for (int r = 0; r < 16; ++r) if (r0 + r < NRB) part[r] = ldcg4(gp + (long long)(r0 + r) * gs);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) if (r0 + r < NRB) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
+          }
+          return g;
+        };
+        const bool peers = ca.world > 1;
+        if (peers) {
+          // Several ranks, exchange inside the kernel: this rank's gradient of the kind goes to its exchange block, a barrier
+          // across all ranks' grids follows, then EVERY rank adds all ranks' gradients in rank order (an all-gather + local
+          // sum over NVLink loads: the same arithmetic everywhere, so the ranks' parameters stay bit-identical).
+          for (int t4 = blockIdx.x * THREADS + tid; t4 < N2 * n4; t4 += n_ctas * THREADS) {
+            const int i = t4 >= n4 ? 1 : 0, i4 = t4 - i * n4, net = critic ? N2 + i : i;
+            st4(ca.peer_g[ca.rank] + a.net_off[net] + 4 * i4, local_gradient(net, i4));
+          }
+          grid_barrier_peers(a.s.bar, n_ctas, ca, ca.epoch0 + 2ull * (unsigned long long)u + (critic ? 1ull : 2ull));
+        }
+        const float gscale = peers ? 1.0f / (float)ca.world : a.grad_scale;
         for (int t4 = blockIdx.x * THREADS + tid; t4 < N2 * n4; t4 += n_ctas * THREADS) {
           const int i = t4 >= n4 ? 1 : 0, i4 = t4 - i * n4, net = critic ? N2 + i : i;
           const long long e = a.net_off[net] + 4 * i4;
-          const float* gp = ca.gpart[net] + 4 * i4;
-          const long long gs = ca.gstride[net];
           float4 g = make_float4(0.f, 0.f, 0.f, 0.f), m4, v4, p4, t4v;
           if (mode & ADAM_APPLY) { m4 = ldcg4(a.M + e); v4 = ldcg4(a.V + e); p4 = ldcg4(a.P + e); t4v = ldcg4(a.T + e); }
-          if (mode & ADAM_FROM_G) {
+          if (peers) {
+            float4 part[GW_MAX_PEERS];
+#pragma unroll
+            for (int p = 0; p < GW_MAX_PEERS; ++p) if (p < ca.world) part[p] = ldcv4(ca.peer_g[p] + e);
+#pragma unroll
+            for (int p = 0; p < GW_MAX_PEERS; ++p) if (p < ca.world) { g.x += part[p].x; g.y += part[p].y; g.z += part[p].z; g.w += part[p].w; }
+          } else if (mode & ADAM_FROM_G) {
             g = ldcg4(a.G + e);
           } else {
-            float4 part[16];
-            for (int r0 = 0; r0 < NRB; r0 += 16) {             // the slabs' loads are issued together, added in row-block order
-#pragma unroll
-              for (int r = 0; r < 16; ++r) if (r0 + r < NRB) part[r] = ldcg4(gp + (long long)(r0 + r) * gs);
-#pragma unroll
-              for (int r = 0; r < 16; ++r) if (r0 + r < NRB) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
-            }
+            g = local_gradient(net, i4);
           }
           if (mode & ADAM_WRITE_G) st4(a.G + e, g);
           if (mode & ADAM_APPLY) {
@@ -927,7 +994,7 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
             float pp[4] = {p4.x, p4.y, p4.z, p4.w}, tt[4] = {t4v.x, t4v.y, t4v.z, t4v.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float gk = gg[k] * a.grad_scale;
+              const float gk = gg[k] * gscale;
               mm[k] = mm[k] + (1.0f - a.beta1) * (gk - mm[k]);
               vv[k] = a.beta2 * vv[k] + (1.0f - a.beta2) * gk * gk;
               const float denom = sqrtf(vv[k]) / bc2s[i] + a.eps;
@@ -1019,6 +1086,18 @@ int gwc_launch(gw_learner* l, const gwl::LearnArgs& a, int segment, cudaStream_t
     p += (int64_t)nrb * ca.gstride[k];
   }
   ca.lpart = p;
+  ca.world = 1; ca.rank = 0; ca.epoch0 = 0; ca.timeout_ns = 5000000000ull; ca.peer_err = nullptr;
+  for (int q = 0; q < GW_MAX_PEERS; ++q) { ca.peer_g[q] = nullptr; ca.peer_flag[q] = nullptr; }
+  if (l->peer_world > 1 && segment == GW_LEARN_ALL) {            // gradients exchanged inside the kernel over NVLink peer memory
+    ca.world = l->peer_world; ca.rank = l->peer_rank; ca.epoch0 = l->peer_epochs;
+    for (int q = 0; q < l->peer_world; ++q) {
+      ca.peer_g[q] = static_cast<float*>(l->peer_base[q]);
+      ca.peer_flag[q] = reinterpret_cast<unsigned long long*>(static_cast<char*>(l->peer_base[q]) + l->peer_flag_off);
+    }
+    ca.peer_err = reinterpret_cast<unsigned int*>(static_cast<char*>(l->peer_base[l->peer_rank]) + l->peer_flag_off + 8 * GW_MAX_PEERS);
+    if (const char* e = getenv("GW_PEER_TIMEOUT_MS")) ca.timeout_ns = 1000000ull * (unsigned long long)atoll(e);
+    l->peer_epochs += 2ull * (unsigned long long)a.updates;
+  }
   switch (segment) {
     case GW_LEARN_ALL: ca.cp_begin = 0; ca.cp_end = 4; break;
     case GW_LEARN_CRITIC_GRADS: ca.cp_begin = 0; ca.cp_end = 2; break;

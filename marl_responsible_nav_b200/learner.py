@@ -69,6 +69,7 @@ class FusedLearner:
         self.updates_done = 0
         self._loss_buf: Optional[torch.Tensor] = None
         self.force_segmented = False                             # tests: take the several-rank path (three launches per update) on one rank
+        self.peer_world = 1                                      # > 1 once connect_peers() succeeded: gradients exchanged inside the kernel
 
     # ---- the modules' parameters and the optimisers' moments become views of the flat vectors
     def _adopt(self, agent):
@@ -114,6 +115,41 @@ class FusedLearner:
     @property
     def kernel(self) -> str:
         return {v: k for k, v in self.KERNELS.items()}[self.lib.gw_learner_kernel(self._h)]
+
+    def connect_peers(self) -> bool:
+        """Data-parallel run, one process per GPU of one node: exchange the gradients INSIDE the update kernel over NVLink
+        peer memory instead of two NCCL all-reduces per update (gw_learner_peer_export / _connect: every rank's exchange
+        block is shared as a CUDA IPC handle, gathered here with torch.distributed).  Collective: every rank calls it.
+        Returns False (nothing changed, the NCCL path stays) when there is one rank, more than 8, or the cluster kernel is
+        not the active one."""
+        if not (dist.is_available() and dist.is_initialized()) or self.peer_world > 1:
+            return self.peer_world > 1
+        world, rank = dist.get_world_size(), dist.get_rank()
+        ok = 2 <= world <= N.GW_MAX_PEERS and self.kernel == "cluster"
+        mine = N.GwPeerHandle()
+        if ok:
+            N.check(self.lib.gw_learner_peer_export(self._h, C.byref(mine)), self.env._h, "gw_learner_peer_export")
+        dev = self.params.device
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)                # all ranks or none
+        if int(flag.item()) == 0:
+            return False
+        t = torch.tensor(list(bytes(mine.bytes)), dtype=torch.uint8, device=dev)
+        gathered = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        arr = (N.GwPeerHandle * world)()
+        for q, g in enumerate(gathered):
+            C.memmove(arr[q].bytes, bytes(g.cpu().tolist()), 64)
+        N.check(self.lib.gw_learner_peer_connect(self._h, rank, world, arr), self.env._h, "gw_learner_peer_connect")
+        dist.barrier()                                             # every rank has mapped every block before any update runs
+        self.peer_world = world
+        return True
+
+    def peer_timed_out(self) -> bool:
+        """True if a peer failed to arrive at an in-kernel exchange in time (the update then ran without it)."""
+        w, e = C.c_int32(), C.c_int32()
+        N.check(self.lib.gw_learner_peer_status(self._h, C.byref(w), C.byref(e)), self.env._h, "gw_learner_peer_status")
+        return bool(e.value)
 
     def export_steps(self):
         """Write the kernel's per-network Adam step counters into the torch optimisers' per-parameter `step` entries
@@ -164,9 +200,10 @@ class FusedLearner:
     # ---- `updates` whole updates in one launch, batches drawn from the ring inside the kernel
     def learn_from_ring(self, ring, updates: int, sample_seed: int) -> torch.Tensor:
         """Update u draws its batch exactly like `ring.sample_fused(seed=sample_seed)` would on its u-th call from
-        here (same Philox key and draw number) and gathers it inside the kernel.  Several ranks: every update is cut at
-        the two gradient exchanges (three launches, two NCCL all-reduces on the flat gradient vector's critic / actor
-        part).  Returns losses f32 [updates, 2, n] on the device."""
+        here (same Philox key and draw number) and gathers it inside the kernel.  Several ranks: after `connect_peers`
+        still ONE launch (the gradients are exchanged inside the kernel over NVLink peer memory); otherwise every update is
+        cut at the two gradient exchanges (three launches, two NCCL all-reduces on the flat gradient vector's critic /
+        actor part).  Returns losses f32 [updates, 2, n] on the device."""
         updates = int(updates)
         losses = self._losses(updates)
         view = C.byref(ring._view())
@@ -174,7 +211,7 @@ class FusedLearner:
         stream, h = self.env._stream(), self.env._h
         multi = dist.is_available() and dist.is_initialized()
         world = dist.get_world_size() if multi else 1
-        if world == 1 and not self.force_segmented:
+        if (world == 1 or self.peer_world == world) and not self.force_segmented:   # one launch; several ranks: in-kernel exchange
             N.check(self.lib.gw_learner_update(self._h, None, view, ring.t, seed, ring._draws + 1, updates, N.GW_LEARN_ALL, 1.0,
                                                losses.data_ptr(), stream), h, "gw_learner_update")
         else:

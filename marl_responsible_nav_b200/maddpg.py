@@ -511,14 +511,17 @@ class BatchedTrainer:
     def __init__(self, env, agent: Optional[BatchedMADDPG] = None, hp: Optional[Dict] = None,
                  updates_per_learn: int = 1, seed: int = 0, fused_actor: bool = True, fused_sampler: bool = True, fused_ops: bool = True,
                  fused_linear_bwd: bool = False, learn_cadence: str = "reference", global_envs: Optional[int] = None,
-                 fused_learner: bool = True):
+                 fused_learner: bool = True, gradient_exchange: str = "peer"):
         """learn_cadence: "reference" = the rule of maddpg/agent.py:199-224 applied to the GLOBAL env count (see
         `learn_schedule`); "batched" = one block of `updates_per_learn` updates every LEARN_STEP vector steps whatever
         E is (round 1's loop: 1 update per LEARN_STEP * E transitions, a much lower update-to-data ratio than the
         reference's).  global_envs: environments over all ranks (default: this shard x world size); the schedule and
         the BATCH_SIZE gate are computed from it so that every rank takes the same decisions.
         fused_learner: the update as ONE kernel that also draws its batches from the ring (learner.py, csrc/gw_maddpg.cu);
-        off = round 1's CUDA graph of PyTorch / library kernels (fused_sampler / fused_ops choose its pieces)."""
+        off = round 1's CUDA graph of PyTorch / library kernels (fused_sampler / fused_ops choose its pieces).
+        gradient_exchange (several ranks, fused learner): "peer" = inside the update kernel over NVLink peer memory
+        (FusedLearner.connect_peers, called by `broadcast_parameters`-time setup in `connect`), "nccl" = two all-reduces per
+        update between the kernel's three segments."""
         from .replay import ReplayRing
         self.env = env
         self.hp = dict(DEFAULT_HP if hp is None else hp)
@@ -532,6 +535,9 @@ class BatchedTrainer:
         self.agent = agent or BatchedMADDPG(env.n_learners, env.obs_len, 9, hp=self.hp, device=env.device, seed=seed)
         self.ring = ReplayRing(env.num_envs, env.n_learners, env.obs_len, self.hp["MEMORY_SIZE"], 9,
                                device=env.device, obs_dtype=env.obs_dtype)
+        if gradient_exchange not in ("peer", "nccl"):
+            raise ValueError("gradient_exchange must be 'peer' or 'nccl'")
+        self.gradient_exchange = gradient_exchange
         self.learner = None
         if fused_learner and env.device.type == "cuda":
             self.learner = self.agent.learner if self.agent.learner is not None else self.agent.attach_learner(env, seed=seed + 3)
@@ -551,6 +557,19 @@ class BatchedTrainer:
         if fused_actor and env.device.type == "cuda" and env.obs_len == self.agent.obs_dim:
             from .actor import FusedActor
             self.fused = FusedActor(env, self.agent.actors, seed=seed + 2)
+
+    def connect(self, src: int = 0) -> str:
+        """Several ranks (collective, call once after construction): rank `src`'s networks to everybody and, with
+        gradient_exchange="peer", the in-kernel gradient exchange over peer memory.  Returns what exchanges the gradients:
+        "peer", "nccl", or "none" (one rank)."""
+        self.agent.broadcast_parameters(src)
+        if self.fused is not None:
+            self.fused.update(self.agent.actors)
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return "none"
+        if self.learner is not None and self.gradient_exchange == "peer" and self.learner.connect_peers():
+            return "peer"
+        return "nccl"
 
     def _sample(self, batch_size: int) -> Dict[str, torch.Tensor]:
         """One batch for `learn`.  On the GPU: one gw_replay_sample launch (indices drawn and rows gathered by the

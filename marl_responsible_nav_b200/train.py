@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--torch-sampler", action="store_true", help="sample the replay ring with PyTorch indexing instead of gw_replay_sample")
     ap.add_argument("--torch-ops", action="store_true", help="LayerNorm + ReLU of the update by PyTorch instead of gw_ln_relu_forward / _backward")
     ap.add_argument("--torch-learner", action="store_true", help="the update as round 1's CUDA graph of PyTorch / library kernels instead of the one-kernel gw_learner_update")
+    ap.add_argument("--gradient-exchange", choices=("peer", "nccl"), default="peer",
+                    help="several GPUs: peer = inside the update kernel over NVLink peer memory; nccl = two all-reduces per update")
     ap.add_argument("--save", default=None, help="write the agents here in the reference's checkpoint format (maddpg/agent.py:255-266)")
     ap.add_argument("--load", default=None, help="resume from a checkpoint of the reference / of --save (maddpg/agent.py:268-283)")
     a = ap.parse_args()
@@ -48,8 +50,11 @@ def main():
         agent = checkpoint.load_reference_checkpoint(a.load, device=dev, hp=hp)
     trainer = maddpg.BatchedTrainer(env, agent=agent, hp=hp, updates_per_learn=a.updates_per_learn, seed=hp["SEED"],
                                     fused_actor=not a.torch_actor, fused_sampler=not a.torch_sampler, fused_ops=not a.torch_ops,
-                                    learn_cadence=a.learn_cadence, global_envs=a.envs, fused_learner=not a.torch_learner)
-    trainer.agent.broadcast_parameters(0)
+                                    learn_cadence=a.learn_cadence, global_envs=a.envs, fused_learner=not a.torch_learner,
+                                    gradient_exchange=a.gradient_exchange)
+    exchange = trainer.connect(0)
+    if rank == 0 and world > 1:
+        print(json.dumps({"gradient_exchange": exchange}), flush=True)
     done = 0
     while done < a.steps:
         k = min(a.report, a.steps - done)
