@@ -378,11 +378,11 @@ int gw_learner_update(gw_learner* l, const gw_learn_batch* batch, const gw_repla
 int gw_learner_set_kernel(gw_learner* l, int32_t kind);
 int gw_learner_kernel(const gw_learner* l);
 /* Data-parallel training, gradient exchange INSIDE the update kernel (cluster kernel, GW_LEARN_ALL): one process per GPU,
- * every rank exports a small exchange block (its flat gradient vector + arrival words, a cudaMalloc of the library's own) as
+ * every rank exports a small exchange block (one flat gradient slot per rank + arrival words, a cudaMalloc of the library's own) as
  * a CUDA IPC handle, the host exchanges the handles (torch.distributed all_gather), every rank connects.  From then on each
- * Adam phase of gw_learner_update writes this rank's gradient to its block, passes a barrier across ALL ranks' grids (arrival
- * words stored over NVLink into the peers' blocks) and adds every rank's gradient in rank order with loads over NVLink: no
- * NCCL call and no host round trip per update, `updates` per launch as on one GPU, parameters bit-identical on all ranks.
+ * Adam phase of gw_learner_update pushes this rank's gradient into its slot of EVERY rank's block (posted stores over NVLink),
+ * passes a barrier across ALL ranks' grids (arrival words stored into the peers' blocks) and adds the world's gradients from
+ * its own block in rank order: no NCCL call and no host round trip per update, `updates` per launch as on one GPU, parameters bit-identical on all ranks.
  * Every rank must issue the same sequence of gw_learner_update calls.  A peer that does not arrive within 5 s
  * (GW_PEER_TIMEOUT_MS) is reported by gw_learner_peer_status instead of hanging the GPU.  The segmented calls
  * (GW_LEARN_CRITIC_GRADS ...) remain for exchanges done by the caller (NCCL: maddpg/agent.py has no counterpart, the reference

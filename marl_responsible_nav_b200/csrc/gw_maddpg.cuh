@@ -187,7 +187,7 @@ struct gw_learner {
   // gradient exchange over peer memory (gw_learner_peer_export / _connect): exchange block of every rank, mapped here
   int peer_world = 1, peer_rank = 0;
   void* peer_base[GW_MAX_PEERS] = {};         // [rank] = this process's own cudaMalloc block; the others cudaIpcOpenMemHandle
-  size_t peer_flag_off = 0;                   // byte offset of the arrival words (then the error word) behind the gradient vector
+  size_t peer_flag_off = 0;                   // bytes of the flag-in-data slots (GW_MAX_PEERS of them); the error word follows
   unsigned long long peer_epochs = 0;         // exchanges done so far (two per update)               // cudaOccupancyMaxActiveClusters of the cluster kernel on this device
 };
 

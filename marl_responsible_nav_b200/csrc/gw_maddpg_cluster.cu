@@ -66,8 +66,8 @@ struct ClusterArgs {
   int cp_begin, cp_end;                     // cluster-kernel phases: 0 A, 1 Adam C, 2 B, 3 Adam A
   // data-parallel gradient exchange over NVLink peer memory (world > 1): every rank's exchange block, mapped into this process
   int world, rank;
-  float* peer_g[GW_MAX_PEERS];              // [world] flat gradient vector of rank p (this rank's own at [rank])
-  unsigned long long* peer_flag[GW_MAX_PEERS];   // [world] rank p's arrival words: peer_flag[p][q] = last epoch rank q has published
+  uint4* peer_ll[GW_MAX_PEERS];             // [world] rank p's exchange block: one slot of ll_stride lines per sending rank q
+  long long ll_stride;                      // lines per slot: two 16-byte lines {x, epoch, y, epoch} {z, epoch, w, epoch} per float4 of gradient
   unsigned long long epoch0;                // exchanges completed before this launch
   unsigned long long timeout_ns;
   unsigned int* peer_err;                   // set to 1 if a peer did not arrive in time (the launch then finishes without it)
@@ -79,36 +79,15 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Grid barrier that is also a barrier ACROSS the ranks of a data-parallel run: every CTA releases its writes at system scope
-// and arrives; the last CTA of this GPU publishes `epoch` in every peer's arrival row (a store over NVLink into the peer's
-// exchange block), waits until every peer has published it in ours, and only then opens the barrier for the other CTAs.
-// What any rank wrote to its exchange block before the barrier can be read by every rank after it (volatile loads: peer
-// memory is not cached here).  A peer that does not arrive within timeout_ns sets the error word instead of hanging the GPU.
-__device__ __forceinline__ void grid_barrier_peers(unsigned* bar, unsigned n_ctas, const ClusterArgs& ca, unsigned long long epoch) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned gen = *reinterpret_cast<volatile unsigned*>(bar + 1);
-    __threadfence_system();
-    if (atomicAdd(bar, 1u) == n_ctas - 1) {
-      *reinterpret_cast<volatile unsigned*>(bar) = 0u;
-      __threadfence_system();
-      for (int p = 0; p < ca.world; ++p)
-        if (p != ca.rank) *reinterpret_cast<volatile unsigned long long*>(ca.peer_flag[p] + ca.rank) = epoch;
-      const unsigned long long t0 = global_ns();
-      for (int q = 0; q < ca.world; ++q) {
-        if (q == ca.rank) continue;
-        while (*reinterpret_cast<volatile unsigned long long*>(ca.peer_flag[ca.rank] + q) < epoch) {
-          if (global_ns() - t0 > ca.timeout_ns) { *ca.peer_err = 1u; break; }
-        }
-      }
-      __threadfence_system();
-      atomicAdd(bar + 1, 1u);
-    } else {
-      while (*reinterpret_cast<volatile unsigned*>(bar + 1) == gen) {}
-    }
-    __threadfence_system();
-  }
-  __syncthreads();
+// Flag-in-data lines (the LL protocol of NCCL): a 16-byte store carries two {value, epoch} pairs, each 8-byte half validates
+// itself, so the receiver needs neither a fence nor a separate arrival word -- it polls the line until both epochs match.
+__device__ __forceinline__ void st_ll(uint4* p, float x, float y, uint32_t ep) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(__float_as_uint(x)), "r"(ep), "r"(__float_as_uint(y)), "r"(ep) : "memory");
+}
+__device__ __forceinline__ uint4 ld_ll(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
 }
 __device__ __forceinline__ float4 ldcv4(const float* p) { return __ldcv(reinterpret_cast<const float4*>(p)); }
 
@@ -961,32 +940,44 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
           return g;
         };
         const bool peers = ca.world > 1;
-        if (peers) {
-          // Several ranks, exchange inside the kernel: this rank's gradient of the kind goes to its exchange block, a barrier
-          // across all ranks' grids follows, then EVERY rank adds all ranks' gradients in rank order (an all-gather + local
-          // sum over NVLink loads: the same arithmetic everywhere, so the ranks' parameters stay bit-identical).
-          for (int t4 = blockIdx.x * THREADS + tid; t4 < N2 * n4; t4 += n_ctas * THREADS) {
-            const int i = t4 >= n4 ? 1 : 0, i4 = t4 - i * n4, net = critic ? N2 + i : i;
-            st4(ca.peer_g[ca.rank] + a.net_off[net] + 4 * i4, local_gradient(net, i4));
-          }
-          grid_barrier_peers(a.s.bar, n_ctas, ca, ca.epoch0 + 2ull * (unsigned long long)u + (critic ? 1ull : 2ull));
-        }
+        // Several ranks, exchange inside the kernel and inside this loop: the thread that owns four parameters adds its own
+        // rank's slabs, PUSHES the result as two flag-in-data lines into its slot of every other rank's exchange block (posted
+        // stores over NVLink), then polls ITS OWN block until the other ranks' lines of this exchange have arrived and adds the
+        // world's gradients in rank order -- an all-gather + local sum with the same arithmetic on every rank (parameters stay
+        // bit-identical), no barrier across GPUs, no fence, no NCCL call.  A slot is rewritten two exchanges later, which the
+        // sender reaches only through grid barriers that every reader of the old value has passed.
+        const uint32_t ep = (uint32_t)(ca.epoch0 + 2ull * (unsigned long long)u + (critic ? 1ull : 2ull));
         const float gscale = peers ? 1.0f / (float)ca.world : a.grad_scale;
         for (int t4 = blockIdx.x * THREADS + tid; t4 < N2 * n4; t4 += n_ctas * THREADS) {
           const int i = t4 >= n4 ? 1 : 0, i4 = t4 - i * n4, net = critic ? N2 + i : i;
           const long long e = a.net_off[net] + 4 * i4;
           float4 g = make_float4(0.f, 0.f, 0.f, 0.f), m4, v4, p4, t4v;
-          if (mode & ADAM_APPLY) { m4 = ldcg4(a.M + e); v4 = ldcg4(a.V + e); p4 = ldcg4(a.P + e); t4v = ldcg4(a.T + e); }
           if (peers) {
-            float4 part[GW_MAX_PEERS];
+            const float4 own = local_gradient(net, i4);
+            const long long line = (long long)ca.rank * ca.ll_stride + (e >> 1);
 #pragma unroll
-            for (int p = 0; p < GW_MAX_PEERS; ++p) if (p < ca.world) part[p] = ldcv4(ca.peer_g[p] + e);
-#pragma unroll
-            for (int p = 0; p < GW_MAX_PEERS; ++p) if (p < ca.world) { g.x += part[p].x; g.y += part[p].y; g.z += part[p].z; g.w += part[p].w; }
-          } else if (mode & ADAM_FROM_G) {
-            g = ldcg4(a.G + e);
+            for (int p = 0; p < GW_MAX_PEERS; ++p)
+              if (p < ca.world && p != ca.rank) { st_ll(ca.peer_ll[p] + line, own.x, own.y, ep); st_ll(ca.peer_ll[p] + line + 1, own.z, own.w, ep); }
+            if (mode & ADAM_APPLY) { m4 = ldcg4(a.M + e); v4 = ldcg4(a.V + e); p4 = ldcg4(a.P + e); t4v = ldcg4(a.T + e); }
+            const unsigned long long t0 = global_ns();
+            for (int q = 0; q < ca.world; ++q) {
+              float4 x = own;
+              if (q != ca.rank) {
+                const uint4* src = ca.peer_ll[ca.rank] + (long long)q * ca.ll_stride + (e >> 1);
+                uint4 l0, l1;
+                unsigned spins = 0;
+                for (;;) {
+                  l0 = ld_ll(src); l1 = ld_ll(src + 1);
+                  if (l0.y == ep && l0.w == ep && l1.y == ep && l1.w == ep) break;
+                  if ((++spins & 1023u) == 0 && global_ns() - t0 > ca.timeout_ns) { *ca.peer_err = 1u; break; }
+                }
+                x = make_float4(__uint_as_float(l0.x), __uint_as_float(l0.z), __uint_as_float(l1.x), __uint_as_float(l1.z));
+              }
+              g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+            }
           } else {
-            g = local_gradient(net, i4);
+            if (mode & ADAM_APPLY) { m4 = ldcg4(a.M + e); v4 = ldcg4(a.V + e); p4 = ldcg4(a.P + e); t4v = ldcg4(a.T + e); }
+            g = (mode & ADAM_FROM_G) ? ldcg4(a.G + e) : local_gradient(net, i4);
           }
           if (mode & ADAM_WRITE_G) st4(a.G + e, g);
           if (mode & ADAM_APPLY) {
@@ -1087,14 +1078,13 @@ int gwc_launch(gw_learner* l, const gwl::LearnArgs& a, int segment, cudaStream_t
   }
   ca.lpart = p;
   ca.world = 1; ca.rank = 0; ca.epoch0 = 0; ca.timeout_ns = 5000000000ull; ca.peer_err = nullptr;
-  for (int q = 0; q < GW_MAX_PEERS; ++q) { ca.peer_g[q] = nullptr; ca.peer_flag[q] = nullptr; }
+  for (int q = 0; q < GW_MAX_PEERS; ++q) ca.peer_ll[q] = nullptr;
+  ca.ll_stride = 0;
   if (l->peer_world > 1 && segment == GW_LEARN_ALL) {            // gradients exchanged inside the kernel over NVLink peer memory
     ca.world = l->peer_world; ca.rank = l->peer_rank; ca.epoch0 = l->peer_epochs;
-    for (int q = 0; q < l->peer_world; ++q) {
-      ca.peer_g[q] = static_cast<float*>(l->peer_base[q]);
-      ca.peer_flag[q] = reinterpret_cast<unsigned long long*>(static_cast<char*>(l->peer_base[q]) + l->peer_flag_off);
-    }
-    ca.peer_err = reinterpret_cast<unsigned int*>(static_cast<char*>(l->peer_base[l->peer_rank]) + l->peer_flag_off + 8 * GW_MAX_PEERS);
+    ca.ll_stride = (long long)(l->peer_flag_off / (GW_MAX_PEERS * sizeof(uint4)));
+    for (int q = 0; q < l->peer_world; ++q) ca.peer_ll[q] = static_cast<uint4*>(l->peer_base[q]);
+    ca.peer_err = reinterpret_cast<unsigned int*>(static_cast<char*>(l->peer_base[l->peer_rank]) + l->peer_flag_off);
     if (const char* e = getenv("GW_PEER_TIMEOUT_MS")) ca.timeout_ns = 1000000ull * (unsigned long long)atoll(e);
     l->peer_epochs += 2ull * (unsigned long long)a.updates;
   }
