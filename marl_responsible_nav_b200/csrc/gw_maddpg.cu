@@ -869,7 +869,7 @@ extern "C" int gw_learner_peer_export(gw_learner* l, gw_peer_handle* out) {
   if (gw_learner_kernel(l) != GW_LEARN_KERNEL_CLUSTER) return gw_fail(h, GW_ESTATE, "gw_learner_peer_export: the exchange lives in the cluster kernel");
   GW_CUDA(h, cudaSetDevice(h->cfg.device));
   if (!l->peer_base[l->peer_rank]) {
-    l->peer_flag_off = (size_t)round_up(l->lay.param_floats * 8, 256) * GW_MAX_PEERS;      // one slot of flag-in-data lines per rank ({value, epoch} pairs: 8 bytes per float), then the error word
+    l->peer_flag_off = (size_t)round_up(l->lay.param_floats * 8, 256) * (GW_MAX_PEERS + 1);      // one slot of flag-in-data lines per sending rank + one for returned sums ({value, epoch} pairs: 8 bytes per float), then the error word
     void* p = nullptr;
     const size_t bytes = l->peer_flag_off + 8 * GW_MAX_PEERS + 256;
     GW_CUDA(h, cudaMalloc(&p, bytes));                 // a whole allocation of its own: what CUDA IPC can share

@@ -68,6 +68,7 @@ struct ClusterArgs {
   int world, rank;
   uint4* peer_ll[GW_MAX_PEERS];             // [world] rank p's exchange block: one slot of ll_stride lines per sending rank q
   long long ll_stride;                      // lines per slot: two 16-byte lines {x, epoch, y, epoch} {z, epoch, w, epoch} per float4 of gradient
+  int reduce_scatter;                       // 0: all-gather (every rank sums everything); 1: the owner of a float4 (index mod world) sums and returns it
   unsigned long long epoch0;                // exchanges completed before this launch
   unsigned long long timeout_ns;
   unsigned int* peer_err;                   // set to 1 if a peer did not arrive in time (the launch then finishes without it)
@@ -945,7 +946,9 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
         // stores over NVLink), then polls ITS OWN block until the other ranks' lines of this exchange have arrived and adds the
         // world's gradients in rank order -- an all-gather + local sum with the same arithmetic on every rank (parameters stay
         // bit-identical), no barrier across GPUs, no fence, no NCCL call.  A slot is rewritten two exchanges later, which the
-        // sender reaches only through grid barriers that every reader of the old value has passed.
+        // sender reaches only through grid barriers that every reader of the old value has passed.  From five ranks on the
+        // owner of a float4 (its index mod world) receives the contributions, sums them in rank order and pushes the sum back
+        // (reduce-scatter + all-gather: two hops, 2 (world - 1) / world gradients of traffic per rank instead of world - 1).
         const uint32_t ep = (uint32_t)(ca.epoch0 + 2ull * (unsigned long long)u + (critic ? 1ull : 2ull));
         const float gscale = peers ? 1.0f / (float)ca.world : a.grad_scale;
         for (int t4 = blockIdx.x * THREADS + tid; t4 < N2 * n4; t4 += n_ctas * THREADS) {
@@ -954,26 +957,46 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
           float4 g = make_float4(0.f, 0.f, 0.f, 0.f), m4, v4, p4, t4v;
           if (peers) {
             const float4 own = local_gradient(net, i4);
-            const long long line = (long long)ca.rank * ca.ll_stride + (e >> 1);
-#pragma unroll
-            for (int p = 0; p < GW_MAX_PEERS; ++p)
-              if (p < ca.world && p != ca.rank) { st_ll(ca.peer_ll[p] + line, own.x, own.y, ep); st_ll(ca.peer_ll[p] + line + 1, own.z, own.w, ep); }
-            if (mode & ADAM_APPLY) { m4 = ldcg4(a.M + e); v4 = ldcg4(a.V + e); p4 = ldcg4(a.P + e); t4v = ldcg4(a.T + e); }
+            const long long line = e >> 1;
             const unsigned long long t0 = global_ns();
-            for (int q = 0; q < ca.world; ++q) {
-              float4 x = own;
-              if (q != ca.rank) {
-                const uint4* src = ca.peer_ll[ca.rank] + (long long)q * ca.ll_stride + (e >> 1);
-                uint4 l0, l1;
-                unsigned spins = 0;
-                for (;;) {
-                  l0 = ld_ll(src); l1 = ld_ll(src + 1);
-                  if (l0.y == ep && l0.w == ep && l1.y == ep && l1.w == ep) break;
-                  if ((++spins & 1023u) == 0 && global_ns() - t0 > ca.timeout_ns) { *ca.peer_err = 1u; break; }
-                }
-                x = make_float4(__uint_as_float(l0.x), __uint_as_float(l0.z), __uint_as_float(l1.x), __uint_as_float(l1.z));
+            auto poll = [&](const uint4* src) {                     // two lines of this exchange -> four values
+              uint4 l0, l1;
+              unsigned spins = 0;
+              for (;;) {
+                l0 = ld_ll(src); l1 = ld_ll(src + 1);
+                if (l0.y == ep && l0.w == ep && l1.y == ep && l1.w == ep) break;
+                if ((++spins & 1023u) == 0 && global_ns() - t0 > ca.timeout_ns) { *ca.peer_err = 1u; break; }
               }
-              g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+              return make_float4(__uint_as_float(l0.x), __uint_as_float(l0.z), __uint_as_float(l1.x), __uint_as_float(l1.z));
+            };
+            const int owner = ca.reduce_scatter ? t4 % ca.world : ca.rank;      // all-gather: every rank is the "owner" of everything
+            if (!ca.reduce_scatter) {
+#pragma unroll
+              for (int p = 0; p < GW_MAX_PEERS; ++p)
+                if (p < ca.world && p != ca.rank) {
+                  st_ll(ca.peer_ll[p] + (long long)ca.rank * ca.ll_stride + line, own.x, own.y, ep);
+                  st_ll(ca.peer_ll[p] + (long long)ca.rank * ca.ll_stride + line + 1, own.z, own.w, ep);
+                }
+            } else if (owner != ca.rank) {                          // this rank's contribution to the owner's slot
+              st_ll(ca.peer_ll[owner] + (long long)ca.rank * ca.ll_stride + line, own.x, own.y, ep);
+              st_ll(ca.peer_ll[owner] + (long long)ca.rank * ca.ll_stride + line + 1, own.z, own.w, ep);
+            }
+            if (mode & ADAM_APPLY) { m4 = ldcg4(a.M + e); v4 = ldcg4(a.V + e); p4 = ldcg4(a.P + e); t4v = ldcg4(a.T + e); }
+            if (owner == ca.rank) {
+              for (int q = 0; q < ca.world; ++q) {                  // the world's gradients in rank order
+                const float4 x = q == ca.rank ? own : poll(ca.peer_ll[ca.rank] + (long long)q * ca.ll_stride + line);
+                g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+              }
+              if (ca.reduce_scatter) {                              // the sum goes back to everybody: result slot GW_MAX_PEERS
+#pragma unroll
+                for (int p = 0; p < GW_MAX_PEERS; ++p)
+                  if (p < ca.world && p != ca.rank) {
+                    st_ll(ca.peer_ll[p] + (long long)GW_MAX_PEERS * ca.ll_stride + line, g.x, g.y, ep);
+                    st_ll(ca.peer_ll[p] + (long long)GW_MAX_PEERS * ca.ll_stride + line + 1, g.z, g.w, ep);
+                  }
+              }
+            } else {
+              g = poll(ca.peer_ll[ca.rank] + (long long)GW_MAX_PEERS * ca.ll_stride + line);
             }
           } else {
             if (mode & ADAM_APPLY) { m4 = ldcg4(a.M + e); v4 = ldcg4(a.V + e); p4 = ldcg4(a.P + e); t4v = ldcg4(a.T + e); }
@@ -1079,10 +1102,14 @@ int gwc_launch(gw_learner* l, const gwl::LearnArgs& a, int segment, cudaStream_t
   ca.lpart = p;
   ca.world = 1; ca.rank = 0; ca.epoch0 = 0; ca.timeout_ns = 5000000000ull; ca.peer_err = nullptr;
   for (int q = 0; q < GW_MAX_PEERS; ++q) ca.peer_ll[q] = nullptr;
-  ca.ll_stride = 0;
+  ca.ll_stride = 0; ca.reduce_scatter = 0;
   if (l->peer_world > 1 && segment == GW_LEARN_ALL) {            // gradients exchanged inside the kernel over NVLink peer memory
     ca.world = l->peer_world; ca.rank = l->peer_rank; ca.epoch0 = l->peer_epochs;
-    ca.ll_stride = (long long)(l->peer_flag_off / (GW_MAX_PEERS * sizeof(uint4)));
+    ca.ll_stride = (long long)(l->peer_flag_off / ((GW_MAX_PEERS + 1) * sizeof(uint4)));
+    // all-gather moves (world - 1) gradients per rank in one hop; from five ranks on the owner-sums form (two hops, a quarter
+    // of the traffic at eight ranks) is the cheaper one.  GW_PEER_PROTOCOL=ag|rs overrides (tests run both on two ranks).
+    ca.reduce_scatter = l->peer_world > 4;
+    if (const char* e = getenv("GW_PEER_PROTOCOL")) ca.reduce_scatter = e[0] == 'r';
     for (int q = 0; q < l->peer_world; ++q) ca.peer_ll[q] = static_cast<uint4*>(l->peer_base[q]);
     ca.peer_err = reinterpret_cast<unsigned int*>(static_cast<char*>(l->peer_base[l->peer_rank]) + l->peer_flag_off);
     if (const char* e = getenv("GW_PEER_TIMEOUT_MS")) ca.timeout_ns = 1000000ull * (unsigned long long)atoll(e);

@@ -37,6 +37,8 @@ def test_segmented_host_loop_equals_one_launch():
 
 def _worker(rank, world, port, out_dir, exchange="peer"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if exchange.startswith("peer-"):                   # the two forms of the in-kernel exchange: all-gather / owner sums and returns
+        os.environ["GW_PEER_PROTOCOL"] = exchange[5:]
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -45,7 +47,7 @@ def _worker(rank, world, port, out_dir, exchange="peer"):
     hp["MEMORY_SIZE"] = 8192
     base, n = sharding.shard_range(512, rank, world)
     env = maddpg.make_env(hp, n, device=dev, env_id_base=base)
-    tr = maddpg.BatchedTrainer(env, hp=hp, seed=3, global_envs=512, gradient_exchange=exchange)
+    tr = maddpg.BatchedTrainer(env, hp=hp, seed=3, global_envs=512, gradient_exchange=exchange.split("-")[0])
     how = tr.connect(0)
     tr.train(5)
     torch.cuda.synchronize()
@@ -61,21 +63,21 @@ def _worker(rank, world, port, out_dir, exchange="peer"):
 
 @pytest.mark.gpu
 def test_two_rank_training_keeps_the_networks_identical(tmp_path):
-    """Two ranks, both gradient exchanges: inside the update kernel over NVLink peer memory ("peer": one launch per block of
-    updates, no NCCL call) and with two NCCL all-reduces per update ("nccl").  Ranks stay bit-identical either way, and with
+    """Two ranks, the gradient exchanges: inside the update kernel over NVLink peer memory ("peer": one launch per block of
+    updates, no NCCL call; as all-gather and as owner-sums-and-returns) and with two NCCL all-reduces per update ("nccl").  Ranks stay bit-identical either way, and with
     two ranks the two exchanges give the SAME parameters bit for bit (a sum of two terms has one order)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     res = {}
-    for k, exchange in enumerate(("peer", "nccl")):
+    for k, exchange in enumerate(("peer-ag", "peer-rs", "nccl")):
         port = 29800 + (os.getpid() % 1000) + k
         mp.spawn(_worker, args=(2, port, str(tmp_path), exchange), nprocs=2, join=True)
         r0 = torch.load(os.path.join(str(tmp_path), f"{exchange}_rank0.pt"))
         r1 = torch.load(os.path.join(str(tmp_path), f"{exchange}_rank1.pt"))
-        assert r0["exchange"] == r1["exchange"] == exchange and not r0["timed_out"] and not r1["timed_out"]
+        assert r0["exchange"] == r1["exchange"] == exchange.split("-")[0] and not r0["timed_out"] and not r1["timed_out"]
         assert r0["finite"] and r1["finite"]
         assert r0["updates"] == r1["updates"] == 5 * (512 // 10)          # maddpg/agent.py:214-224 on the global env count
         assert all(torch.equal(a, b) for a, b in zip(r0["chk"], r0["chk"][1:]))   # both ranks' checksums, as gathered on rank 0
         assert all(torch.equal(a, b) for a, b in zip(r0["chk"], r1["chk"]))
         res[exchange] = r0["chk"][0]
-    assert torch.equal(res["peer"], res["nccl"])
+    assert torch.equal(res["peer-ag"], res["nccl"]) and torch.equal(res["peer-rs"], res["nccl"])
