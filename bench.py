@@ -30,6 +30,8 @@ ALGO_BYTES_PER_AGENT_STEP = {"f32": 668.0, "bf16": 348.0}      # SURVEY.md secti
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
 # (profiles/r1d_*_ncu_raw.csv; Level 3, f32 obs): (envs, fear) -> bytes
 NCU_DRAM_BYTES = {(4096, 1): 370.0e3 + 0.0, (1 << 20, 1): 23.2e6 + 1413.0e6, (1 << 20, 0): 19.33e6 + 1378.3e6}
+# gw_rollout_kernel<true,f32>, (envs, fear, steps per launch): one launch under ncu --set full (profiles/r2c_rollout_ncu_details.txt)
+NCU_ROLLOUT_DRAM_BYTES = {(4096, 1, 20): 553.5e3 + 55.46e6}
 
 
 def kernel_name(envs, fear, obs, mode="step"):
@@ -601,9 +603,12 @@ def run_ours(a):
         "launch_plan": r_plan,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(n_launches), "launch_per_step": per_step,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": (NCU_DRAM_BYTES.get((E, int(bool(a.fear)))) if (a.obs == "f32" and a.scenario == "Level 3" and r_plan["mode"] == "step") else None),
+                     "traffic": (None if not (a.obs == "f32" and a.scenario == "Level 3") else
+                                 NCU_DRAM_BYTES.get((E, int(bool(a.fear)))) if r_plan["mode"] == "step" else
+                                 NCU_ROLLOUT_DRAM_BYTES.get((E, int(bool(a.fear)), r_plan["steps_per_launch"]))),
                      "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1d_*_ncu_raw.csv); "
-                                       "at 4096 envs the stores are still in L2 when the kernel ends, so DRAM writes show as 0",
+                                       "at 4096 envs the stores are still in L2 when the kernel ends, so DRAM writes show as 0; gw_rollout (20 steps per launch, "
+                                       "profiles/r2c_rollout_ncu_details.txt): 56 MB of the launch's 109 MB reach DRAM before it ends, the rest is written back from L2 later",
                      "kernel": kernel_name(E, a.fear, a.obs, r_plan["mode"]),
                      "algorithmic_bytes_per_launch": algo * K / n_launches, "algorithmic_bytes_per_step": algo, "peak_source": peak_src,
                      "launch_ms": ms / n_launches,
