@@ -68,6 +68,7 @@ struct ClusterArgs {
   int world, rank;
   uint4* peer_ll[GW_MAX_PEERS];             // [world] rank p's exchange block: one slot of ll_stride lines per sending rank q
   long long ll_stride;                      // lines per slot: two 16-byte lines {x, epoch, y, epoch} {z, epoch, w, epoch} per float4 of gradient
+  int split_roles;                          // actor-side clusters next to the row-block owners (when enough clusters are resident)
   int reduce_scatter;                       // 0: all-gather (every rank sums everything); 1: the owner of a float4 (index mod world) sums and returns it
   unsigned long long epoch0;                // exchanges completed before this launch
   unsigned long long timeout_ns;
@@ -266,8 +267,16 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
   const int B = a.B, NRB = B / RR;
   // clusters beyond the 2 * B / 16 that own row blocks are helpers: they only take part in the Adam phases and the barriers
   const int cid = blockIdx.x / CL;
-  const bool worker = cid < N2 * NRB;
-  const int ag = worker ? cid / NRB : 0, rb = worker ? cid - ag * NRB : 0, row0 = rb * RR;
+  // Roles.  NW = 2 * B / 16 clusters own a row block of one agent.  When twice as many are resident and the launch runs whole
+  // updates, a second set of NW clusters owns the ACTOR side of the same row blocks: it runs the actor's forward pass (which
+  // reads nothing the critic's update writes) while the first set is in phase A, and the rest of phase B afterwards, so the
+  // actor's forward leaves the critical path.  Everything else only joins the Adam phases and the barriers.
+  const int NW = N2 * NRB;
+  const bool split = ca.cp_begin == 0 && ca.cp_end == 4 && (int)(gridDim.x / CL) >= 2 * NW && ca.split_roles;
+  const int role = cid < NW ? 0 : (split && cid < 2 * NW ? 1 : 2);      // 0: row-block owner (critic side when split), 1: actor side, 2: helper
+  const bool worker = role != 2;
+  const int wid = role == 1 ? cid - NW : cid;
+  const int ag = worker ? wid / NRB : 0, rb = worker ? wid - ag * NRB : 0, row0 = rb * RR;
   const unsigned n_ctas = gridDim.x;
   const NetLayout la = a.la, lc = a.lc;
   float* X = sm + SM_X; float* X2 = sm + SM_X2; float* EX = sm + SM_EX; float* PV = sm + SM_PV; float* RING = sm + SM_RING;
@@ -481,10 +490,10 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
 #endif
     for (int ph = ca.cp_begin; ph < ca.cp_end; ++ph) {
       if (blockIdx.x == 0 && tid == 0 && u == a.updates - 1) a.s.trace[ph] = phase_clock();
-      if (ph == 0 || ph == 2) {
-        if (!worker) { grid_barrier(a.s.bar, n_ctas); continue; }   // (phases A / B are never the last one of a launch)
-      }
-      if (ph == 0) {
+      const bool run_a = ph == 0 && role == 0;
+      const bool run_b1 = split ? (ph == 0 && role == 1) : (ph == 2 && role == 0);     // actor forward
+      const bool run_b2 = ph == 2 && (split ? role == 1 : role == 0);                  // the rest of phase B
+      if (run_a) {
         // ======================================================================================== phase A: critic gradients
         const float* Tc = a.T + a.net_off[N2 + ag];           // target critic
         const float* Pc = a.P + a.net_off[N2 + ag];           // critic
@@ -698,19 +707,22 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
         cp_wait<0>();
         TP();
         x_valid = true;
-      } else if (ph == 2) {
+      }
+      if (run_b1 || run_b2) {
         // ======================================================================================== phase B: actor gradients
         const float* Pa = a.P + a.net_off[ag];
         const float* Pc = a.P + a.net_off[N2 + ag];
         float* slab = ca.gpart[ag] + (long long)rb * ca.gstride[ag];
-        auto issue = [&](int p) {
-          float* w = slot_w(p); float* v = slot_v(p);
-          switch (p) {
+        // weight packages in the order of their use: the actor's three first (they do not depend on the critic's Adam step and
+        // may be loaded while it runs), then the updated critic's
+        auto issue = [&](int pos) {
+          float* w = slot_w(pos); float* v = slot_v(pos);
+          switch (pos) {
             case 0: load_w(w, 168, a.P, a.net_off[ag] + la.w1 + (long long)col0 * O, O, O); load_layer_vecs(v, Pa, la.b1, col0, false, 0, 0); break;
-            case 1: load_w(w, 170, a.P, a.net_off[N2 + ag] + lc.w1 + (long long)col0 * CI, CI, O); break;
-            case 2: load_w(w, 170, a.P, a.net_off[N2 + ag] + lc.w1 + (long long)col0 * CI + O, CI, SO - O); break;
-            case 3: load_w(w, ALD, a.P, a.net_off[ag] + la.w2 + (long long)col0 * HID, HID, HID); load_layer_vecs(v, Pa, la.b2, col0, false, 0, 0); break;
-            case 4: load_vec(w, Pa + la.w3, NA * HID / 4); load_vec(w + NA * HID, Pa + la.b3, 3); break;
+            case 1: load_w(w, ALD, a.P, a.net_off[ag] + la.w2 + (long long)col0 * HID, HID, HID); load_layer_vecs(v, Pa, la.b2, col0, false, 0, 0); break;
+            case 2: load_vec(w, Pa + la.w3, NA * HID / 4); load_vec(w + NA * HID, Pa + la.b3, 3); break;
+            case 3: load_w(w, 170, a.P, a.net_off[N2 + ag] + lc.w1 + (long long)col0 * CI, CI, O); break;
+            case 4: load_w(w, 170, a.P, a.net_off[N2 + ag] + lc.w1 + (long long)col0 * CI + O, CI, SO - O); break;
             case 5: load_w(w, 26, a.P, a.net_off[N2 + ag] + lc.w1 + (long long)col0 * CI + SO, CI, SA); load_layer_vecs(v, Pc, lc.b1, col0, false, 0, 0); break;
             case 6: load_w(w, ALD, a.P, a.net_off[N2 + ag] + lc.w2 + (long long)col0 * HID, HID, HID); load_layer_vecs(v, Pc, lc.b2, col0, true, lc.w3, lc.b3); break;
             case 7: load_wt(w, Pc + lc.w2, col0, HID); break;
@@ -719,74 +731,86 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
           }
           cp_commit();
         };
-        auto ready = [&](int p, bool first = false) {
+        int issue_limit = 3;                                    // the actor's packages only until the critic has been stepped
+        auto ready = [&](int pos, bool first = false) {
           if (first) cp_wait<0>(); else cp_wait<1>();
           __syncthreads();
-          issue(p + 2);
+          if (pos + 2 < issue_limit) issue(pos + 2); else cp_commit();
         };
-        if (!x_valid) stage_rows(false, u);
-        issue(0); issue(1);
-        // the critic's first-layer columns of this agent's action, transposed: W1ACT[k][o] (read after the critic's Adam step)
-        for (int e = tid; e < NA * HID; e += THREADS) {
-          const int o = e / NA, k = e - o * NA;
-          MISC[MI_W1ACT + k * HID + o] = __ldcg(Pc + lc.w1 + (long long)o * CI + SO + ag * NA + k);
-        }
         float* XH1a = pv(0); float* H1a = pv(1); float* XH2a = pv(2); float* XH1c = pv(3); float* XH2c = pv(4);
         float* D1 = pv(5); float* D2 = pv(6);                   // D1: h1 of the critic pass, then dz2 (critic), then dz2 (actor); 5, 6 = exchange
                                                                 // buffers (set 0, slots 1 / 2) that this phase's one-network rounds never use
         float* rs1a = MISC + MI_RS + 32; float* rs2a = MISC + MI_RS + 48; float* rs1c = MISC + MI_RS + 64; float* rs2c = MISC + MI_RS + 80;
         float acc_a[2][4], acc_c[2][4], acc2[2][4];
         float4 hreg[2];
-        zero_acc(acc_a); zero_acc(acc_c);
-        // ---- round 1: actor layer 1; the state part of the critic's layer 1
-        ready(0, true);  gemm(acc_a, X + ag * O, XLD, slot_w(0), 168, O);
-        TP();
-        reduce_exchange(acc_a, slot_v(0) + V_B, ex(round & 1, 0));
-        for (int i = tid; i < 2 * HID; i += THREADS) PERS[PE_AG1 + i] = slot_v(0)[V_G + i];
-        ready(1);  gemm(acc_c, X, XLD, slot_w(1), 170, O);
-        TP();
-        ready(2);  gemm(acc_c, X + O, XLD, slot_w(2), 170, O);
-        TP();
-        cluster_sync();
-        TP();
-        ln_rows(ex(round & 1, 0), PERS + PE_AG1, PERS + PE_ABE1, XH1a, H1a, rs1a, hreg);
-        ++round;
-        // ---- round 2: actor layer 2 -> head -> Gumbel-softmax action
-        ready(3);
-        TP();
-        zero_acc(acc2);
-        gemm(acc2, H1a, ALD, slot_w(3), ALD, HID);
-        reduce_exchange(acc2, slot_v(3) + V_B, ex(round & 1, 0));
-        for (int i = tid; i < 2 * HID; i += THREADS) PERS[PE_AG2 + i] = slot_v(3)[V_G + i];
-        ready(4);
-        TP();
-        for (int i = tid; i < NA * HID + 12; i += THREADS) {    // padded layout [16][ALD] + bias (rows 9..15 stay zero)
-          if (i < NA * HID) PERS[PE_AW3 + (i >> 7) * ALD + (i & (HID - 1))] = slot_w(4)[i];
-          else PERS[PE_AB3 + i - NA * HID] = slot_w(4)[i];
-        }
-        cluster_sync();
-        TP();
-        ln_rows(ex(round & 1, 0), PERS + PE_AG2, PERS + PE_ABE2, XH2a, D2, rs2a, hreg);   // h2 into D2 (free until round 5)
-        ++round;
-        __syncthreads();                                        // D2 and PERS (actor W3) written by all threads above
-        {
-          float lg = head_logits(D2, PERS + PE_AW3);
-          const int r = tid >> 4, c = tid & 15, row = row0 + r;
-          if (c < NA) lg += a.gum_cur ? __ldg(a.gum_cur + ((long long)row * N2 + ag) * NA + c) : gumbel_lane(a, upd, row, ag, 1, c);
-          const float pl = softmax_half(lg, c);
-          if (c < NA) {
-            MISC[MI_ANEW + r * 12 + c] = pl;
-            if (rank == 0) a.s.anew[ag][(long long)row * NA + c] = pl;
+        if (run_b1) {
+          // ============ the actor's forward pass (actor-side clusters run it while the critic side is in phase A)
+          if (!x_valid) stage_rows(false, u);
+          issue(0); issue(1);
+          zero_acc(acc_a);
+          // ---- round 1: actor layer 1
+          ready(0, true);  gemm(acc_a, X + ag * O, XLD, slot_w(0), 168, O);
+          TP();
+          reduce_exchange(acc_a, slot_v(0) + V_B, ex(round & 1, 0));
+          for (int i = tid; i < 2 * HID; i += THREADS) PERS[PE_AG1 + i] = slot_v(0)[V_G + i];
+          cluster_sync();
+          TP();
+          ln_rows(ex(round & 1, 0), PERS + PE_AG1, PERS + PE_ABE1, XH1a, H1a, rs1a, hreg);
+          ++round;
+          // ---- round 2: actor layer 2 -> head -> Gumbel-softmax action
+          ready(1);
+          TP();
+          zero_acc(acc2);
+          gemm(acc2, H1a, ALD, slot_w(1), ALD, HID);
+          reduce_exchange(acc2, slot_v(1) + V_B, ex(round & 1, 0));
+          for (int i = tid; i < 2 * HID; i += THREADS) PERS[PE_AG2 + i] = slot_v(1)[V_G + i];
+          ready(2);
+          TP();
+          for (int i = tid; i < NA * HID + 12; i += THREADS) {  // padded layout [16][ALD] + bias (rows 9..15 stay zero)
+            if (i < NA * HID) PERS[PE_AW3 + (i >> 7) * ALD + (i & (HID - 1))] = slot_w(2)[i];
+            else PERS[PE_AB3 + i - NA * HID] = slot_w(2)[i];
           }
+          cluster_sync();
+          TP();
+          ln_rows(ex(round & 1, 0), PERS + PE_AG2, PERS + PE_ABE2, XH2a, D2, rs2a, hreg);   // h2 into D2 (free until round 5)
+          ++round;
+          __syncthreads();                                      // D2 and PERS (actor W3) written by all threads above
+          {
+            float lg = head_logits(D2, PERS + PE_AW3);
+            const int r = tid >> 4, c = tid & 15, row = row0 + r;
+            if (c < NA) lg += a.gum_cur ? __ldg(a.gum_cur + ((long long)row * N2 + ag) * NA + c) : gumbel_lane(a, upd, row, ag, 1, c);
+            const float pl = softmax_half(lg, c);
+            if (c < NA) {
+              MISC[MI_ANEW + r * 12 + c] = pl;
+              if (rank == 0) a.s.anew[ag][(long long)row * NA + c] = pl;
+            }
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {                      // the batch's actions with this agent's replaced (zero padded): columns c, c + 16
-            const int col = c + 16 * hf, k = col - ag * NA;
-            const bool mine = k >= 0 && k < NA;
-            const float pv_ = __shfl_sync(0xffffffffu, pl, (lane & 16) + (mine ? k : 0));
-            if (col < AXLD) MISC[MI_AXA + r * AXLD + col] = col >= SA ? 0.f : (mine ? pv_ : X[r * XLD + SO + col]);
+            for (int hf = 0; hf < 2; ++hf) {                    // the batch's actions with this agent's replaced (zero padded): columns c, c + 16
+              const int col = c + 16 * hf, k = col - ag * NA;
+              const bool mine = k >= 0 && k < NA;
+              const float pv_ = __shfl_sync(0xffffffffu, pl, (lane & 16) + (mine ? k : 0));
+              if (col < AXLD) MISC[MI_AXA + r * AXLD + col] = col >= SA ? 0.f : (mine ? pv_ : X[r * XLD + SO + col]);
+            }
           }
+          cp_wait<0>();
+          __syncthreads();
+          x_valid = true;                                       // this cluster's rows are staged (its phase B continues with them)
         }
-        // ---- round 3: the updated critic's layer 1 completed with [.. actor's action ..]
+        if (run_b2) {
+        // ============ the updated critic on [state | .. actor's action ..], -Q backward to the action, the actor's backward pass
+        issue_limit = 9;
+        issue(3); issue(4);
+        // the critic's first-layer columns of this agent's action, transposed: W1ACT[k][o] (read after the critic's Adam step)
+        for (int e = tid; e < NA * HID; e += THREADS) {
+          const int o = e / NA, k = e - o * NA;
+          MISC[MI_W1ACT + k * HID + o] = __ldcg(Pc + lc.w1 + (long long)o * CI + SO + ag * NA + k);
+        }
+        zero_acc(acc_c);
+        // ---- round 3: the updated critic's layer 1 on [state | actions with the actor's]
+        ready(3, true);  gemm(acc_c, X, XLD, slot_w(3), 170, O);
+        TP();
+        ready(4);  gemm(acc_c, X + O, XLD, slot_w(4), 170, O);
+        TP();
         ready(5);
         TP();
         gemm(acc_c, MISC + MI_AXA, AXLD, slot_w(5), 26, 24);
@@ -913,7 +937,9 @@ __global__ void __launch_bounds__(THREADS, 1) gw_learn_cluster_kernel(const Clus
         cp_wait<0>();
         TP();
         x_valid = false;                                        // the next update draws new rows
-      } else {
+        }
+      }
+      if (ph == 1 || ph == 3) {
         // ======================================================================================== Adam + soft update
         const bool critic = ph == 1;
         const NetLayout& L = critic ? lc : la;
@@ -1103,6 +1129,7 @@ int gwc_launch(gw_learner* l, const gwl::LearnArgs& a, int segment, cudaStream_t
   ca.world = 1; ca.rank = 0; ca.epoch0 = 0; ca.timeout_ns = 5000000000ull; ca.peer_err = nullptr;
   for (int q = 0; q < GW_MAX_PEERS; ++q) ca.peer_ll[q] = nullptr;
   ca.ll_stride = 0; ca.reduce_scatter = 0;
+  ca.split_roles = getenv("GW_LEARN_NO_SPLIT") == nullptr;
   if (l->peer_world > 1 && segment == GW_LEARN_ALL) {            // gradients exchanged inside the kernel over NVLink peer memory
     ca.world = l->peer_world; ca.rank = l->peer_rank; ca.epoch0 = l->peer_epochs;
     ca.ll_stride = (long long)(l->peer_flag_off / ((GW_MAX_PEERS + 1) * sizeof(uint4)));
