@@ -507,12 +507,19 @@ def run_ours(a):
         # complete on return.  Default mode for this batch: the resident step kernel (no launch / stream sync per step).
         import math
 
+        # observation slots of the e2e loop: as many as action tensors, so that the (actions, slot) pairs repeat with period
+        # n_act and every pair's marshalled argument set (the library keeps 1024) is prepared in the warm-up; 64 slots x 5.2 MB
+        # still exceed L2
+        e_slots = min(slots, n_act)
+        act_views = [host_actions[i] for i in range(n_act)]
+        slot_views = [ring[i] for i in range(e_slots)]
+
         def host_loop(n, **kw):
             for t in range(n):
-                env.step_host(host_actions[t % n_act], host_rew, host_end, obs_out=ring[t % slots], **kw)   # returns with the results on the host
+                env.step_host(act_views[t % n_act], host_rew, host_end, obs_out=slot_views[t % e_slots], **kw)   # returns with the results on the host
 
         def timed_host_loop(**kw):
-            host_loop(min(256, max(10, math.lcm(n_act, slots))), **kw)      # every (actions, ring slot) pair seen once: marshalling cached
+            host_loop(min(256, max(10, math.lcm(n_act, e_slots))), **kw)    # every (actions, ring slot) pair seen once: marshalling cached
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
