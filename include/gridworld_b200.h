@@ -392,6 +392,7 @@ typedef struct gw_peer_handle { uint8_t bytes[64]; } gw_peer_handle;
 int gw_learner_peer_export(gw_learner* l, gw_peer_handle* out);
 int gw_learner_peer_connect(gw_learner* l, int32_t rank, int32_t world, const gw_peer_handle* handles /* [world] */);
 int gw_learner_peer_status(gw_learner* l, int32_t* world, int32_t* timed_out);
+int gw_learner_peer_disable(gw_learner* l);   /* exchanges are the caller's again (use when some rank failed to connect) */
 /* intermediate tensors of the last update, by name (tests / debugging): "a2", "q", "y", "dq", "anew", "ax", "dz2", "dh1",
  * "dz1", "adz2", "adh1", "adz1", and "<pass>.<z1|h1|st1|z2|h2|st2>" with pass in ta / ct / c / ac / c2; index = agent */
 int gw_learner_debug_ptr(gw_learner* l, const char* name, int index, float** ptr, int64_t* floats);

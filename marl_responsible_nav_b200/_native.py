@@ -16,7 +16,7 @@ EXPORTS = ["gw_abi_version", "gw_build_info", "gw_default_config", "gw_create", 
            "gw_reset_stats", "gw_launch_count", "gw_debug_trace", "gw_update_world", "gw_fear_one_actor", "gw_fear_matrix", "gw_feal", "gw_actor_create", "gw_actor_update", "gw_actor_update_device",
            "gw_actor_destroy", "gw_actor_forward", "gw_replay_sample", "gw_ln_relu_forward", "gw_ln_relu_backward", "gw_linear_backward",
            "gw_learner_layout_of", "gw_learner_create", "gw_learner_destroy", "gw_learner_update", "gw_learner_debug_ptr", "gw_learner_set_kernel", "gw_learner_kernel",
-           "gw_learner_peer_export", "gw_learner_peer_connect", "gw_learner_peer_status"]
+           "gw_learner_peer_export", "gw_learner_peer_connect", "gw_learner_peer_status", "gw_learner_peer_disable"]
 
 
 class GwActorWeights(C.Structure):
@@ -155,6 +155,7 @@ def load():
                                       C.c_int32, C.c_int32, C.c_float, vp, vp]
     lib.gw_learner_peer_export.argtypes = [vp, C.POINTER(GwPeerHandle)]
     lib.gw_learner_peer_connect.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(GwPeerHandle)]
+    lib.gw_learner_peer_disable.argtypes = [vp]
     lib.gw_learner_peer_status.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.gw_learner_set_kernel.argtypes = [vp, C.c_int32]
     lib.gw_learner_kernel.argtypes = [vp]

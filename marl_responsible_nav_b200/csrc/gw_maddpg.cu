@@ -905,6 +905,12 @@ extern "C" int gw_learner_peer_connect(gw_learner* l, int32_t rank, int32_t worl
   return GW_OK;
 }
 
+extern "C" int gw_learner_peer_disable(gw_learner* l) {      // back to exchanges done by the caller (a peer failed to connect)
+  if (!l) return GW_EINVAL;
+  l->peer_world = 1;
+  return GW_OK;
+}
+
 extern "C" int gw_learner_peer_status(gw_learner* l, int32_t* world, int32_t* timed_out) {
   if (!l) return GW_EINVAL;
   if (world) *world = l->peer_world;

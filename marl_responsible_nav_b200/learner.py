@@ -125,14 +125,18 @@ class FusedLearner:
         if not (dist.is_available() and dist.is_initialized()) or self.peer_world > 1:
             return self.peer_world > 1
         world, rank = dist.get_world_size(), dist.get_rank()
-        ok = 2 <= world <= N.GW_MAX_PEERS and self.kernel == "cluster"
-        mine = N.GwPeerHandle()
-        if ok:
-            N.check(self.lib.gw_learner_peer_export(self._h, C.byref(mine)), self.env._h, "gw_learner_peer_export")
         dev = self.params.device
-        flag = torch.tensor([1 if ok else 0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)                # all ranks or none
-        if int(flag.item()) == 0:
+
+        def all_ok(flag: bool) -> bool:                            # every rank or none (a rank that failed must not leave the others waiting)
+            t = torch.tensor([1 if flag else 0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return bool(int(t.item()))
+
+        mine = N.GwPeerHandle()
+        ok = 2 <= world <= N.GW_MAX_PEERS and self.kernel == "cluster"
+        if ok:
+            ok = self.lib.gw_learner_peer_export(self._h, C.byref(mine)) == 0
+        if not all_ok(ok):
             return False
         t = torch.tensor(list(bytes(mine.bytes)), dtype=torch.uint8, device=dev)
         gathered = [torch.empty_like(t) for _ in range(world)]
@@ -140,8 +144,10 @@ class FusedLearner:
         arr = (N.GwPeerHandle * world)()
         for q, g in enumerate(gathered):
             C.memmove(arr[q].bytes, bytes(g.cpu().tolist()), 64)
-        N.check(self.lib.gw_learner_peer_connect(self._h, rank, world, arr), self.env._h, "gw_learner_peer_connect")
-        dist.barrier()                                             # every rank has mapped every block before any update runs
+        ok = self.lib.gw_learner_peer_connect(self._h, rank, world, arr) == 0      # fails without peer access between the GPUs
+        if not all_ok(ok):                                         # (all_reduce: also the barrier after the mapping)
+            self.lib.gw_learner_peer_disable(self._h)
+            return False
         self.peer_world = world
         return True
 
