@@ -101,3 +101,27 @@ def test_device_side_weight_packing_equals_host_packing():
     dev_packed.update(cpu_actors)                                  # CPU parameters still take the host path
     c3, _ = dev_packed.forward(out.obs_code, out.action_mask, training=False)
     assert torch.isfinite(c3).all()
+
+
+def test_actor_noise_is_keyed_by_the_global_env_id():
+    """A rollout of 2 048 envs in one handle against the same global ids split over two handles (env_id_base 0 / 1 024): the
+    env's Philox streams AND the actor's Gumbel / exploration noise are functions of the global env id, so actions, positions
+    and rewards of the shards equal the slices of the whole (what sharding.py promises: trajectories do not depend on the
+    number of ranks)."""
+    from marl_responsible_nav_b200 import BatchedGridWorld, FusedActor, maddpg
+    E, H = 2048, 1024
+    agent = maddpg.BatchedMADDPG(2, 160, 9, device="cuda", seed=12)
+    mk = lambda n, base: BatchedGridWorld("Level 3", num_envs=n, fear=True, auto_reset=True, seed=4, env_id_base=base)
+    envs = [mk(E, 0), mk(H, 0), mk(H, H)]
+    actors = [FusedActor(e, agent.actors, seed=7) for e in envs]
+    outs = [e.reset() for e in envs]
+    for t in range(12):
+        acts = []
+        for e, f, o in zip(envs, actors, outs):
+            cont, ids = f.forward(o.obs_code, o.action_mask, training=True, expl_noise=0.1)
+            acts.append((cont.clone(), ids.clone()))
+        assert torch.equal(acts[0][0][:H], acts[1][0]) and torch.equal(acts[0][0][H:], acts[2][0]), t      # continuous actions incl. noise
+        assert torch.equal(acts[0][1][:H], acts[1][1]) and torch.equal(acts[0][1][H:], acts[2][1]), t
+        outs = [e.step(a[1]) for e, a in zip(envs, acts)]
+        assert torch.equal(outs[0].positions[:H], outs[1].positions) and torch.equal(outs[0].positions[H:], outs[2].positions), t
+        assert torch.equal(outs[0].reward[H:], outs[2].reward) and torch.equal(outs[0].fear[H:], outs[2].fear), t
