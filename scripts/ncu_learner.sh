@@ -3,7 +3,7 @@
 # profiler the cooperative launch of all 33 co-resident clusters fails (LaunchFailed), so the capture runs without the
 # cooperative attribute (GW_LEARN_NO_COOP=1) and without the helper clusters (GW_LEARN_HELPERS=0: the 16 clusters that own row blocks).
 R=${1:-r2}
-export GW_LEARN_HELPERS=0 GW_LEARN_NO_COOP=1
+export GW_LEARN_HELPERS=${GW_LEARN_HELPERS:-0} GW_LEARN_NO_COOP=1
 for K in cluster; do
   CMD="python scripts/ncu_learner_target.py $K"
   timeout 120 $CMD > gpurun_out/${R}_learner_${K}_plain.log 2>&1 &&
