@@ -68,6 +68,8 @@ class FusedLearner:
         N.check(self.lib.gw_learner_create(env._h, C.byref(cfg), C.byref(buf), C.byref(self._h)), env._h, "gw_learner_create")
         self.updates_done = 0
         self._loss_buf: Optional[torch.Tensor] = None
+        agent.learner = self                                     # the agent's parameters live in this learner's vectors from now on:
+                                                                 # `agent.learn` routes here, checkpoints export its step counters
         self.force_segmented = False                             # tests: take the several-rank path (three launches per update) on one rank
         self.peer_world = 1                                      # > 1 once connect_peers() succeeded: gradients exchanged inside the kernel
 

@@ -265,3 +265,30 @@ def test_trainer_learns_through_the_fused_kernel():
     assert torch.isfinite(tr.learner.params).all() and not torch.equal(p0, tr.learner.params)
     last = tr.losses[-1]
     assert torch.isfinite(last.critic_loss).all() and torch.isfinite(last.actor_loss).all()
+
+
+@pytest.mark.gpu
+def test_checkpoint_round_trip_through_the_learner(tmp_path):
+    """Train through the kernel, save in the reference's checkpoint format (maddpg/agent.py:255-266), load, adopt into a new
+    learner: parameters, targets, Adam moments and step counters are the kernel's, bit for bit -- and the two learners stay
+    identical when both continue on the same batches."""
+    from marl_responsible_nav_b200 import checkpoint
+    from marl_responsible_nav_b200.learner import FusedLearner
+    dev = torch.device("cuda", 0)
+    env, _, ag, la = _pair(dev, 2, 128)
+    for it in range(3):
+        batch, g_next, g_cur = _batch(dev, 128, 2, seed=70 + it)
+        la.learn(batch, g_next, g_cur)
+    env.sync()
+    path = str(tmp_path / "MADDPG.pt")
+    checkpoint.save_reference_checkpoint(ag, path, steps=[3])
+    ag2 = checkpoint.load_reference_checkpoint(path, device=dev, hp=ag.hp)
+    lb = FusedLearner(env, ag2, batch_size=128, seed=3)
+    lb.updates_done = la.updates_done
+    for x, y in ((la.params, lb.params), (la.targets, lb.targets), (la.adam_m, lb.adam_m), (la.adam_v, lb.adam_v)):
+        assert torch.equal(x, y)
+    assert lb.adam_steps.tolist() == la.adam_steps.tolist() == [3.0] * 4
+    batch, g_next, g_cur = _batch(dev, 128, 2, seed=99)
+    l1, l2 = la.learn(batch, g_next, g_cur).clone(), lb.learn(batch, g_next, g_cur).clone()
+    env.sync()
+    assert torch.equal(l1, l2) and torch.equal(la.params, lb.params) and torch.equal(la.adam_v, lb.adam_v)
