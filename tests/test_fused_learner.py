@@ -292,3 +292,30 @@ def test_checkpoint_round_trip_through_the_learner(tmp_path):
     l1, l2 = la.learn(batch, g_next, g_cur).clone(), lb.learn(batch, g_next, g_cur).clone()
     env.sync()
     assert torch.equal(l1, l2) and torch.equal(la.params, lb.params) and torch.equal(la.adam_v, lb.adam_v)
+
+
+@pytest.mark.gpu
+def test_learner_refuses_what_it_cannot_run():
+    """Error behaviour of the update entry points: integer status + message, nothing launched."""
+    from marl_responsible_nav_b200.learner import FusedLearner
+    from marl_responsible_nav_b200.replay import ReplayRing
+    dev = torch.device("cuda", 0)
+    env, _, ag, learner = _pair(dev, 2, 128)
+    batch, _, _ = _batch(dev, 128, 2, seed=1)
+    with pytest.raises(ValueError, match="shape"):
+        learner.learn({k: v[:64] for k, v in batch.items()})
+    empty = ReplayRing(32, 2, 160, capacity=320, device=dev)
+    with pytest.raises(RuntimeError, match="empty"):
+        learner.learn_from_ring(empty, 1, 5)
+    other = ReplayRing(32, 2, 144, capacity=320, device=dev)
+    other.advance()
+    with pytest.raises(RuntimeError, match="shape"):
+        learner.learn_from_ring(other, 1, 5)
+    with pytest.raises(ValueError, match="unsupported shape"):
+        FusedLearner(env, maddpg.BatchedMADDPG(2, 160, 9, hp=dict(maddpg.DEFAULT_HP, BATCH_SIZE=100), device=dev), batch_size=100)
+    _, _, _, big = _pair(dev, 2, 512, kernel="phase")           # 64 row blocks: more clusters than fit at once
+    with pytest.raises(RuntimeError, match="cluster kernel needs"):
+        big.set_kernel("cluster")
+    single = FusedLearner(env, maddpg.BatchedMADDPG(1, 160, 9, device=dev), seed=1)
+    assert single.kernel == "phase"                            # one learner: the critic's 169-float rows are not 8-byte aligned
+    assert learner.updates_done == 0 and torch.isfinite(learner.params).all()
