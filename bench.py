@@ -418,6 +418,63 @@ def masked_uniform_runs(a, E, dev, seeds=(0, 42, 66), steps=384):
     return out
 
 
+def general_layout_extra(a, dev, cpu_seconds=4.0):
+    """the GENERAL state layout (gww_*, csrc/gw_wide.cu) on a scenario the packed layout cannot hold -- the 20 x 28
+    map with 7 agents, walls and one-ways that tests/golden/make_wide_golden.py ran the reference on.  Device-timed step
+    launches (CUDA events, 32 steps after 8), FeAR on / off, at the headline batch and at a batch that fills the GPU; next to
+    it the C oracle built on gww_config, all host threads, on a bounded sample.  An extra line, never the headline."""
+    import numpy as np
+    import torch
+    from marl_responsible_nav_b200 import BatchedGridWorld, load_scenario_json
+    sc = load_scenario_json(os.path.join(ROOT, "tests", "golden", "wide_scenarios.json"), "Wide 20x28", walls="enforce")
+    H, W = sc.shape
+    algo = 64 + 64 + 2 + 8 + 8 + 16 + 4 + 1 + 4 + 18 + 2 * sc.n_agents + 2 * H * W * 4     # per env-step: state r/w, scalars, masks, positions, 2 obs rows
+    peak, _ = peaks()
+    out = {"scenario": f"{H}x{W} map, {sc.n_agents} agents, {len(sc.blocked)} restricted paths, 2 learners", "kernel": "gww_step_kernel",
+           "algorithmic_bytes_per_env_step": algo, "points": []}
+    for E, fear in ((a.envs, 1), (a.envs, 0), (65536, 1), (65536, 0)):
+        env = BatchedGridWorld(sc, num_envs=E, device=dev, fear=bool(fear), fear_weight=-5.0, seed=42, max_steps=150)
+        env.reset()
+        acts = torch.randint(0, 9, (8, E, 2), dtype=torch.int8, device=dev)
+        for t in range(8):
+            env.step(acts[t % 8])
+        env.sync()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        K = 32
+        ev0.record()
+        for t in range(K):
+            env.step(acts[t % 8])
+        ev1.record()
+        torch.cuda.synchronize()
+        per = ev0.elapsed_time(ev1) * 1e-3 / K
+        st = env.stats()
+        out["points"].append({"envs": E, "fear": bool(fear), "ms_per_step": per * 1e3, "agent_steps_per_s": E * 2 / per,
+                              "achieved_gbs": algo * E / per / 1e9, "frac_of_hbm_peak": algo * E / per / 1e9 / peak,
+                              "fear_tasks_per_env_step": st["fear_tasks"] / max(1, st["env_steps"])})
+        env.close()
+        del env, acts
+        torch.cuda.empty_cache()
+    try:
+        import c_oracle
+        threads = os.cpu_count() or 1
+        Ec = 2048
+        ora = c_oracle.COracle(sc, num_envs=Ec, threads=threads, fear=True, fear_weight=-5.0, seed=42)
+        ora.reset()
+        rng = np.random.default_rng(0)
+        la = rng.integers(0, 9, size=(Ec, 2)).astype(np.int8)
+        ora.step(la)
+        t0, n = time.perf_counter(), 0
+        while time.perf_counter() - t0 < cpu_seconds:
+            ora.step(la)
+            n += 1
+        el = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": Ec * 2 * n / el, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+                               "sample": f"{Ec} envs x {n} steps ({el:.1f} s), oracle/gw_oracle.c built with -DGWO_WIDE, FeAR on"}
+    except Exception as exc:
+        out["cpu_baseline"] = {"failed": repr(exc)}
+    return out
+
+
 def train_extra(a, world, rank, dev):
     """BASELINE.json configs[4]: the full MADDPG loop (rollout through the actor kernel, device replay ring, update kernel)
     with custom_fear_10.yaml, a.envs environments per GPU.  Two cadences: the reference's (maddpg/agent.py:199-224 on the
@@ -592,6 +649,13 @@ def run_ours(a):
         except Exception as exc:                            # an extra: must not cost the headline line
             train = {"failed": repr(exc)}
 
+    general = None
+    if world == 1 and not a.no_scale_points:
+        try:
+            general = general_layout_extra(a, dev)
+        except Exception as exc:                            # an extra: must not cost the headline line
+            general = {"failed": repr(exc)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -625,7 +689,7 @@ def run_ours(a):
                                       if r_plan["eager_steps"] == 0 else f"{r_plan['eager_steps']} eager launches"))
                              + f"; at {E} envs one step moves {algo / 2**20:.1f} MiB ({algo / peak / 1e3:.2f} us at peak): small batches are "
                                "latency-bound (a warp's dependent chain per step), see scale_points for the step kernel at 1M envs"},
-        "scale_points": scale_points, "train": train, "masked_uniform_runs": variants,
+        "scale_points": scale_points, "train": train, "masked_uniform_runs": variants, "general_layout": general,
         "workload_stats": {"episodes": stat_vec[0].item(), "mean_episode_len": stat_vec[1].item() / max(1.0, stat_vec[0].item()),
                            "learner_crashes_per_env_step": stat_vec[2].item() / (world * E * K),
                            "apples_per_env_step": stat_vec[3].item() / (world * E * K),

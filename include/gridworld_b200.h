@@ -428,6 +428,99 @@ int gw_actor_forward(gw_actor* a, int64_t num_envs, const uint64_t* obs_code, co
                      float* cont_actions, int8_t* action_ids, int training, float expl_noise, float mean_noise,
                      uint64_t seed, uint64_t step, void* stream);
 
+/* ---- GENERAL layout: grids up to 64 x 64, up to 16 world agents -------------------------------------
+ * The packed layout above (16 bytes per env, 4-bit coordinates, four 8-bit cells, a pair table over 41 offsets) is sized
+ * for the shipped scenarios: W = 16, H <= 16, <= 4 agents.  The reference itself is data-driven -- GWorld takes any map and
+ * any number of agents (custom/grid_world.py:17-31, :104-150), both env classes read the map, N_Agents, Policies, MdRs and
+ * restricted paths from the scenario dict (custom/ma_customenv.py:27-28, :338-365; custom/customenv.py:25-27, :186-240) --
+ * so a scenario file with a larger map or more agents runs there.  gww_* is the second state layout for those: the same
+ * step semantics (every rule cites the same reference lines), 64 bytes of state per env, 16-bit cells, per-cell move
+ * restrictions instead of the folded next-cell table, and the collision rules evaluated on the paths themselves (no pair
+ * table: offsets and agent counts are unbounded here).  A host binding picks the layout when it creates the world
+ * (BatchedGridWorld does: packed when the scenario fits, general otherwise).  Learners stay agents 0..n_learners-1 with
+ * n_learners <= 2 (N_INTELLIGENT_AGENTS and the apple dict are constants of the reference's env modules).
+ * gw_io / gw_stats are shared; shapes use this config's n_agents and H*W:
+ *   obs / final_obs [E, L, H*W]; npc_actions [E, n_agents]; spawn / positions [E, n_agents, 2] (int8 row, col);
+ *   info bits 8-15 as above, bits 0-3 / 4-7 crash / restricted of agents 0..3, bits 16-31 crash of agents 0..15;
+ *   obs_code is not written (the actor kernel is tied to the packed layout).
+ * Device RNG: the same Philox spec; spawn draw k uses call 0x100 + k/4, word k%4 (= the packed layout's for k < 4). */
+#define GWW_MAX_AGENTS 16
+#define GWW_MAX_DIM 64
+#define GWW_MAX_CELLS (GWW_MAX_DIM * GWW_MAX_DIM)
+#define GWW_MAX_BLOCKED 2048
+
+typedef struct gww_config {
+  int32_t struct_size;                 /* = sizeof(gww_config) */
+  int32_t abi_version;                 /* = GW_ABI_VERSION */
+  int32_t height, width;               /* 1..64 each */
+  uint64_t map_rows[GWW_MAX_DIM];      /* bit c of map_rows[r] = Region[r][c] == 1 */
+  int32_t n_agents;                    /* 1..16 */
+  int32_t n_learners;                  /* 1..2, <= n_agents */
+  int32_t env_kind;                    /* gw_env_kind */
+  int8_t apple_row[GW_MAX_LEARNERS];
+  int8_t apple_col[GW_MAX_LEARNERS];
+  uint8_t policy_map[GWW_MAX_CELLS];   /* index row * width + col (dense, unlike the packed layout's pitch of 16) */
+  uint8_t mdr_map[GWW_MAX_CELLS];
+  int32_t n_policies;
+  float step_weights[GW_MAX_POLICIES][3];
+  float dir_weights[GW_MAX_POLICIES][4];
+  double perturb_prob;
+  int32_t fear;
+  int32_t fear_radius;
+  double fear_weight;
+  int32_t max_steps;
+  int32_t auto_reset;
+  int32_t obs_dtype;
+  int32_t device;
+  int64_t num_envs;
+  int64_t env_id_base;
+  uint64_t seed;
+  int32_t n_blocked;                   /* restricted paths as above; cells as (row << 8) | col */
+  uint16_t blocked_from[GWW_MAX_BLOCKED];
+  uint16_t blocked_to[GWW_MAX_BLOCKED];
+} gww_config;
+
+typedef struct gww_env_state {         /* gww_get_state / gww_set_state: 64 bytes per env */
+  uint16_t cell[GWW_MAX_AGENTS];       /* (row << 8) | col; unused entries 0xFFFF */
+  uint32_t flags;                      /* bits 0-1 apples present, 2-3 sticky terminations, 4 sticky truncation, 5-6 previous distance valid */
+  uint32_t tick;                       /* RNG tick (resets + steps so far) */
+  int32_t episode_return[GW_MAX_LEARNERS];   /* reward units (single env: tenths) */
+  uint16_t prev_distance[GW_MAX_LEARNERS];
+  uint32_t steps;                      /* steps in the running episode */
+  uint32_t reserved[2];
+} gww_env_state;
+
+typedef struct gww_handle gww_handle;
+
+int gww_default_config(gww_config* cfg);
+int gww_create(const gww_config* cfg, gww_handle** out);
+int gww_destroy(gww_handle* h);
+const char* gww_last_error(const gww_handle* h);   /* h may be NULL (errors from gww_create) */
+int gww_reset(gww_handle* h, const uint8_t* reset_mask, const gw_io* io, void* stream);   /* as gw_reset */
+int gww_step(gww_handle* h, const gw_io* io, void* stream);                               /* as gw_step */
+int gww_sync(gww_handle* h, void* stream);
+size_t gww_state_bytes(const gww_handle* h);
+int gww_get_state(gww_handle* h, void* dst, int dst_is_device, void* stream);
+int gww_set_state(gww_handle* h, const void* src, int src_is_device, void* stream);
+int gww_get_stats(gww_handle* h, gw_stats* host_out, void* stream);
+int gww_launch_count(const gww_handle* h, uint64_t* kernels_launched);
+/* Operator level, as gw_update_world / gw_fear_one_actor / gw_fear_matrix / gw_feal with every per-agent dimension of
+ * length GWW_MAX_AGENTS: positions / new_positions [C,16,2], actions / mdr / crash / restricted / in_list / resp (one
+ * actor) / n_mdr / n_act [C,16]; matrix outputs [C,16,16]; apples / caught [C,2,2]. */
+int gww_update_world(gww_handle* h, int64_t n_cases, const int8_t* n_agents_per_case, const int8_t* positions,
+                     const int8_t* actions, const int8_t* apples, int8_t* new_positions, uint8_t* crash,
+                     uint8_t* restricted, int8_t* caught, void* stream);
+int gww_fear_one_actor(gww_handle* h, int64_t n_cases, const int8_t* n_agents_per_case, const int8_t* positions,
+                       const int8_t* actions, const int8_t* mdr, const int8_t* actor, const uint8_t* in_list,
+                       double* resp, int8_t* n_mdr, int8_t* n_act, double* fear_sum /* [C] np.sum of the matrix, nullable */,
+                       void* stream);
+int gww_fear_matrix(gww_handle* h, int64_t n_cases, const int8_t* n_agents_per_case, const int8_t* positions,
+                    const int8_t* actions, const int8_t* mdr, const uint8_t* in_list, double* resp, int8_t* n_mdr,
+                    int8_t* n_act, void* stream);
+int gww_feal(gww_handle* h, int64_t n_cases, const int8_t* n_agents_per_case, const int8_t* positions,
+             const int8_t* actions, const int8_t* mdr, const uint8_t* in_list, double* feal, int8_t* n_mdr,
+             int8_t* n_act, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

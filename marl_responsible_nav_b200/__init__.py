@@ -9,13 +9,13 @@ There is no CPU implementation in this package: constructing an environment with
 the compiled library or without a CUDA device raises.
 """
 from .scenarios import Scenario, builtin_scenario, load_scenario_json, policy_probs  # noqa: F401
-from .batched import BatchedGridWorld, StepOutput  # noqa: F401
+from .batched import BatchedGridWorld, GeneralGridWorld, StepOutput  # noqa: F401
 from .envs import CustomMAEnv, CustomEnv  # noqa: F401
 from .replay import ReplayRing  # noqa: F401
 from .actor import FusedActor  # noqa: F401
 from . import sharding  # noqa: F401
 from . import _native  # noqa: F401
 
-__all__ = ["BatchedGridWorld", "StepOutput", "CustomMAEnv", "CustomEnv", "Scenario", "builtin_scenario",
+__all__ = ["BatchedGridWorld", "GeneralGridWorld", "StepOutput", "CustomMAEnv", "CustomEnv", "Scenario", "builtin_scenario",
            "load_scenario_json", "policy_probs", "ReplayRing", "FusedActor", "sharding"]
 __version__ = "0.1.0"

@@ -47,12 +47,44 @@ def _check(t: Optional[torch.Tensor], name, dtype, shape, device):
 
 
 class BatchedGridWorld:
+    """E grid worlds on one GPU.  Two state layouts sit behind the same tensor API and are chosen here, when the world
+    is created: the PACKED layout (16 bytes per env; the shipped scenarios: W = 16, H <= 16, <= 4 agents) with every
+    kernel of the library, and the GENERAL layout (`GeneralGridWorld`, gww_* in gridworld_b200.h: grids up to 64 x 64, up
+    to 16 agents) for scenario files that do not fit.  `layout=None` picks packed whenever the scenario fits."""
+    _P, _wide, PAD = "gw_", False, N.GW_MAX_AGENTS       # C-ABI prefix, error channel, per-agent length of the operator-level arrays
+
+    def __new__(cls, scenario: Union[str, Scenario] = "Level 3", *args, layout: Optional[str] = None, **kw):
+        if cls is BatchedGridWorld:
+            if layout not in (None, "packed", "general"):
+                raise ValueError("layout must be None, 'packed' or 'general'")
+            sc = builtin_scenario(scenario) if isinstance(scenario, str) else scenario
+            if layout == "general" or (layout is None and not N.fits_packed_layout(sc, kw.get("n_agents"))):
+                return object.__new__(GeneralGridWorld)
+        return object.__new__(cls)
+
+    def _f(self, name):
+        return getattr(self.lib, self._P + name)
+
+    def _check_rc(self, rc, what):
+        if rc:
+            N.check(rc, self._h, self._P + what, wide=self._wide)
+
+    def _create_handle(self, **kw):
+        cfg = N.build_config(self.scenario, **kw)
+        probe = N.GwConfig()
+        N.check(self.lib.gw_default_config(C.byref(probe)), None, "gw_default_config")
+        if probe.struct_size != C.sizeof(N.GwConfig):
+            raise RuntimeError("gw_config layout mismatch between ctypes and the library")
+        h = C.c_void_p()
+        N.check(self.lib.gw_create(C.byref(cfg), C.byref(h)), None, "gw_create")
+        return cfg, h
+
     def __init__(self, scenario: Union[str, Scenario] = "Level 3", num_envs: int = 1, device="cuda",
                  env_kind: str = "multi", fear: bool = True, fear_weight: float = 0.0, fear_radius: int = 5,
                  n_agents: Optional[int] = None, n_learners: Optional[int] = None,
                  apples: Optional[Sequence[Tuple[int, int]]] = None, max_steps: int = 150,
                  auto_reset: bool = True, obs_dtype: torch.dtype = torch.float32, obs_layout: str = "mlp",
-                 seed: int = 0, env_id_base: int = 0, perturb_prob: float = 0.25):
+                 seed: int = 0, env_id_base: int = 0, perturb_prob: float = 0.25, layout: Optional[str] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedGridWorld needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = N.load()
@@ -79,20 +111,12 @@ class BatchedGridWorld:
             apples = MA_APPLES[:self.n_learners] if env_kind == "multi" else SINGLE_APPLE
         self.apples = tuple(tuple(a) if a is not None else None for a in apples)
 
-        cfg = N.build_config(sc, num_envs=self.num_envs, env_kind=env_kind, fear=fear, fear_weight=fear_weight,
-                             fear_radius=fear_radius, n_agents=self.n_agents, n_learners=self.n_learners,
-                             apples=self.apples, max_steps=max_steps, auto_reset=auto_reset,
-                             obs_bf16=(obs_dtype == torch.bfloat16), seed=seed, env_id_base=env_id_base,
-                             perturb_prob=perturb_prob, device=self.device.index)
-        probe = N.GwConfig()
-        N.check(self.lib.gw_default_config(C.byref(probe)), None, "gw_default_config")
-        if probe.struct_size != C.sizeof(N.GwConfig):
-            raise RuntimeError("gw_config layout mismatch between ctypes and the library")
-        self.cfg = cfg
+        self.cfg, self._h = self._create_handle(
+            num_envs=self.num_envs, env_kind=env_kind, fear=fear, fear_weight=fear_weight, fear_radius=fear_radius,
+            n_agents=self.n_agents, n_learners=self.n_learners, apples=self.apples, max_steps=max_steps, auto_reset=auto_reset,
+            obs_bf16=(obs_dtype == torch.bfloat16), seed=seed, env_id_base=env_id_base, perturb_prob=perturb_prob,
+            device=self.device.index)
         self.fear, self.fear_weight, self.auto_reset, self.max_steps = bool(fear), float(fear_weight), bool(auto_reset), int(max_steps)
-        h = C.c_void_p()
-        N.check(self.lib.gw_create(C.byref(cfg), C.byref(h)), None, "gw_create")
-        self._h = h
 
         E, L, A, dev = self.num_envs, self.n_learners, self.n_agents, self.device
         self._obs_shape = (E, L, self.obs_len)
@@ -117,7 +141,7 @@ class BatchedGridWorld:
         h = getattr(self, "_h", None)
         if h:
             self._h = None
-            self.lib.gw_destroy(h)
+            self._f("destroy")(h)
 
     def __del__(self):
         try:
@@ -211,7 +235,7 @@ class BatchedGridWorld:
         if mask is not None:
             mask = _check(mask.to(torch.uint8) if mask.dtype == torch.bool else mask, "mask", torch.uint8, (self.num_envs,), self.device)
             mptr = mask.data_ptr()
-        N.check(self.lib.gw_reset(self._h, mptr, C.byref(io), self._stream()), self._h, "gw_reset")
+        self._check_rc(self._f("reset")(self._h, mptr, C.byref(io), self._stream()), "reset")
         return StepOutput(obs=self._view(obs), action_mask=self.buf.action_mask, positions=self.buf.positions,
                           obs_code=self.buf.obs_code)
 
@@ -226,7 +250,7 @@ class BatchedGridWorld:
         obs = self._obs_arg(obs_out, "obs_out") if obs_out is not None else self.buf.obs
         fin = self._obs_arg(final_obs_out, "final_obs_out")
         io = self._io(obs, fin, actions, npc_actions, spawn, buffers=buffers)
-        N.check(self.lib.gw_step(self._h, C.byref(io), self._stream()), self._h, "gw_step")
+        self._check_rc(self._f("step")(self._h, C.byref(io), self._stream()), "step")
         b = buffers if buffers is not None else self.buf
         m = self.buf
         return StepOutput(obs=self._view(obs), action_mask=m.action_mask, positions=m.positions, reward=b.reward,
@@ -358,7 +382,7 @@ class BatchedGridWorld:
 
     def sync(self):
         """Stream synchronisation (a resident step kernel is told to leave first)."""
-        N.check(self.lib.gw_sync(self._h, self._stream()), self._h, "gw_sync")
+        self._check_rc(self._f("sync")(self._h, self._stream()), "sync")
 
     def server_info(self) -> Dict[str, int]:
         """Resident step kernel: running now, launches so far, relaunches after an idle exit, registered buffer sets."""
@@ -369,7 +393,7 @@ class BatchedGridWorld:
 
     def stats(self) -> Dict[str, float]:
         s = N.GwStats()
-        N.check(self.lib.gw_get_stats(self._h, C.byref(s), self._stream()), self._h, "gw_get_stats")
+        self._check_rc(self._f("get_stats")(self._h, C.byref(s), self._stream()), "get_stats")
         return {name: getattr(s, name) for name, _ in N.GwStats._fields_}
 
     def reset_stats(self):
@@ -377,23 +401,22 @@ class BatchedGridWorld:
 
     def launch_count(self) -> int:
         n = C.c_uint64()
-        N.check(self.lib.gw_launch_count(self._h, C.byref(n)), self._h, "gw_launch_count")
+        self._check_rc(self._f("launch_count")(self._h, C.byref(n)), "launch_count")
         return int(n.value)
 
     def state_dict(self) -> torch.Tensor:
         """Packed per-env state (16 B/env) as a uint8 CPU tensor (checkpoint / resume)."""
-        nbytes = int(self.lib.gw_state_bytes(self._h))
+        nbytes = int(self._f("state_bytes")(self._h))
         out = torch.empty(nbytes, dtype=torch.uint8)
-        N.check(self.lib.gw_get_state(self._h, C.c_void_p(out.data_ptr()), 0, self._stream()), self._h, "gw_get_state")
+        self._check_rc(self._f("get_state")(self._h, C.c_void_p(out.data_ptr()), 0, self._stream()), "get_state")
         return out
 
     def load_state_dict(self, state: torch.Tensor):
-        nbytes = int(self.lib.gw_state_bytes(self._h))
+        nbytes = int(self._f("state_bytes")(self._h))
         state = state.contiguous()
         if state.dtype != torch.uint8 or state.numel() != nbytes:
             raise ValueError(f"state must be a uint8 tensor of {nbytes} bytes")
-        N.check(self.lib.gw_set_state(self._h, C.c_void_p(state.data_ptr()), int(state.is_cuda), self._stream()),
-                self._h, "gw_set_state")
+        self._check_rc(self._f("set_state")(self._h, C.c_void_p(state.data_ptr()), int(state.is_cuda), self._stream()), "set_state")
 
     # ------------------------------------------------------------------ operator-level entry points
     def update_world(self, positions, actions, n_agents=None, apples=None):
@@ -402,13 +425,13 @@ class BatchedGridWorld:
         pos, act = self._as_i8(positions, dev), self._as_i8(actions, dev)
         Cn = pos.shape[0]
         nper, app = self._as_i8(n_agents, dev), self._as_i8(apples, dev)
-        new_pos = torch.empty((Cn, 4, 2), dtype=torch.int8, device=dev)
-        crash = torch.empty((Cn, 4), dtype=torch.uint8, device=dev)
-        restr = torch.empty((Cn, 4), dtype=torch.uint8, device=dev)
+        new_pos = torch.empty((Cn, self.PAD, 2), dtype=torch.int8, device=dev)
+        crash = torch.empty((Cn, self.PAD), dtype=torch.uint8, device=dev)
+        restr = torch.empty((Cn, self.PAD), dtype=torch.uint8, device=dev)
         caught = torch.zeros((Cn, 2, 2), dtype=torch.int8, device=dev)
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
-        N.check(self.lib.gw_update_world(self._h, Cn, p(nper), p(pos), p(act), p(app), p(new_pos), p(crash), p(restr),
-                                         p(caught), self._stream()), self._h, "gw_update_world")
+        self._check_rc(self._f("update_world")(self._h, Cn, p(nper), p(pos), p(act), p(app), p(new_pos), p(crash), p(restr),
+                                               p(caught), self._stream()), "update_world")
         return new_pos, crash, restr, caught
 
     def fear_one_actor(self, positions, actions, mdr, actor, in_list=None, n_agents=None):
@@ -418,10 +441,15 @@ class BatchedGridWorld:
         Cn = pos.shape[0]
         nper = self._as_i8(n_agents, dev)
         il = None if in_list is None else torch.as_tensor(np.asarray(in_list)).to(device=dev, dtype=torch.uint8).contiguous()
-        resp = torch.empty((Cn, 4), dtype=torch.float64, device=dev)
-        n_mdr = torch.empty((Cn, 4), dtype=torch.int8, device=dev)
-        n_act = torch.empty((Cn, 4), dtype=torch.int8, device=dev)
+        resp = torch.empty((Cn, self.PAD), dtype=torch.float64, device=dev)
+        n_mdr = torch.empty((Cn, self.PAD), dtype=torch.int8, device=dev)
+        n_act = torch.empty((Cn, self.PAD), dtype=torch.int8, device=dev)
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        if self._wide:                                             # gww_fear_one_actor also returns np.sum of the matrix (info["fear"])
+            self.last_fear_sum = torch.empty((Cn,), dtype=torch.float64, device=dev)
+            self._check_rc(self.lib.gww_fear_one_actor(self._h, Cn, p(nper), p(pos), p(act), p(md), p(ac), p(il), p(resp), p(n_mdr),
+                                                       p(n_act), p(self.last_fear_sum), self._stream()), "fear_one_actor")
+            return resp, n_mdr, n_act
         N.check(self.lib.gw_fear_one_actor(self._h, Cn, p(nper), p(pos), p(act), p(md), p(ac), p(il), p(resp), p(n_mdr),
                                            p(n_act), self._stream()), self._h, "gw_fear_one_actor")
         return resp, n_mdr, n_act
@@ -436,17 +464,46 @@ class BatchedGridWorld:
         n_mdr = torch.empty((Cn,) + tail, dtype=torch.int8, device=dev)
         n_act = torch.empty((Cn,) + tail, dtype=torch.int8, device=dev)
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
-        N.check(fn(self._h, Cn, p(nper), p(pos), p(act), p(md), p(il), p(val), p(n_mdr), p(n_act), self._stream()),
-                self._h, name)
+        self._check_rc(fn(self._h, Cn, p(nper), p(pos), p(act), p(md), p(il), p(val), p(n_mdr), p(n_act), self._stream()), name)
         return val, n_mdr, n_act
 
     def fear_matrix(self, positions, actions, mdr, in_list=None, n_agents=None):
         """Responsibility.FeAR (all actors) for C cases -> (resp f64 [C,4,4], n_mdr, n_act int8 [C,4,4])."""
-        return self._matrix_op(self.lib.gw_fear_matrix, "gw_fear_matrix", (4, 4), positions, actions, mdr, in_list, n_agents)
+        return self._matrix_op(self._f("fear_matrix"), "fear_matrix", (self.PAD, self.PAD), positions, actions, mdr, in_list, n_agents)
 
     def feal(self, positions, actions, mdr, in_list=None, n_agents=None):
         """Responsibility.FeAL for C cases -> (feal f64 [C,4], n_mdr, n_act int8 [C,4])."""
-        return self._matrix_op(self.lib.gw_feal, "gw_feal", (4,), positions, actions, mdr, in_list, n_agents)
+        return self._matrix_op(self._f("feal"), "feal", (self.PAD,), positions, actions, mdr, in_list, n_agents)
+
+
+class GeneralGridWorld(BatchedGridWorld):
+    """The GENERAL state layout (gww_* in include/gridworld_b200.h, csrc/gw_wide.cu): the same reset / step / operator-level
+    API for grids up to 64 x 64 with up to 16 agents.  What is tied to the packed layout is not offered here: the
+    multi-step rollout kernel, the resident host-driven step, `obs_code` and the fused actor (networks sized for 160 cells)."""
+    _P, _wide, PAD = "gww_", True, N.GWW_MAX_AGENTS
+
+    def _create_handle(self, **kw):
+        cfg = N.build_wide_config(self.scenario, **kw)
+        probe = N.GwwConfig()
+        N.check(self.lib.gww_default_config(C.byref(probe)), None, "gww_default_config", wide=True)
+        if probe.struct_size != C.sizeof(N.GwwConfig):
+            raise RuntimeError("gww_config layout mismatch between ctypes and the library")
+        h = C.c_void_p()
+        N.check(self.lib.gww_create(C.byref(cfg), C.byref(h)), None, "gww_create", wide=True)
+        return cfg, h
+
+    def _obs_arg(self, t, name):
+        if t is None:
+            return None
+        if t.dtype != self.obs_dtype or t.device != self.device or not t.is_contiguous() or t.numel() != self.num_envs * self.n_learners * self.obs_len:
+            raise ValueError(f"{name}: need a contiguous {self.obs_dtype} tensor with {self._obs_shape} elements on {self.device}")
+        return t
+
+    def _packed_only(self, *a, **k):
+        raise NotImplementedError("this entry point exists for the packed layout only (W = 16, H <= 16, <= 4 agents); "
+                                  "the general layout offers reset / step / state / stats and the operator-level calls")
+
+    rollout = step_host = pinned_io = server_info = reset_stats = new_rings = _packed_only
 
 
 class PinnedIO:

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libgridworld_b200.so")
-SOURCES = ["gw_kernels.cu", "gw_actor.cu", "gw_replay.cu", "gw_train_ops.cu", "gw_maddpg.cu", "gw_maddpg_cluster.cu"]
+SOURCES = ["gw_kernels.cu", "gw_actor.cu", "gw_replay.cu", "gw_train_ops.cu", "gw_maddpg.cu", "gw_maddpg_cluster.cu", "gw_wide.cu"]
 HEADERS = ["gw_device.cuh", "gw_internal.h", "gw_replay_dev.cuh", "gw_maddpg.cuh", os.path.join("..", "..", "include", "gridworld_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]

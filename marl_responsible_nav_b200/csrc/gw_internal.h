@@ -54,3 +54,6 @@ struct gw_handle {
 int gw_fail(gw_handle* h, int code, const std::string& msg);
 int gw_cuda_fail(gw_handle* h, cudaError_t e, const char* what);
 #define GW_CUDA(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return gw_cuda_fail(h, e_, #call); } while (0)
+
+// GeneratePolicy -> 31-bit cdf thresholds of the device sampler (gw_kernels.cu), shared with the general layout (gw_wide.cu)
+extern "C" void gw_policy_thresholds(const float sw[3], const float dw_in[4], bool perturbed, uint32_t thr[8]);

@@ -1873,6 +1873,11 @@ static void policy_thresholds(const float sw[3], const float dw_in[4], bool pert
   for (int k = last; k < 8; ++k) thr[k] = 0x80000000u;
 }
 
+// the same thresholds for the general layout's translation unit (gw_wide.cu)
+void gw_policy_thresholds(const float sw[3], const float dw_in[4], bool perturbed, uint32_t thr[8]) {
+  policy_thresholds(sw, dw_in, perturbed, thr);
+}
+
 // next-cell table: one move of grid_world.py:481-518 (off-grid clip or inactive target => stay)
 static void build_next_cell(const gw_config* c, uint8_t* next) {
   static const int DR[4] = {-1, 1, 0, 0}, DC[4] = {0, 0, -1, 1};     // Up, Down, Left, Right (custom_agent.py:140-150)

@@ -16,13 +16,14 @@ from marl_responsible_nav_b200.scenarios import builtin_scenario
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "libgw_oracle.so")
-_lib = None
+LIB_PATH_WIDE = os.path.join(HERE, "_build", "libgw_oracle_wide.so")     # the same source built on gww_config (general layout)
+_libs = {}
 
 
 def build(force=False):
     src, hdr = os.path.join(HERE, "gw_oracle.c"), os.path.join(HERE, "..", "include", "gridworld_b200.h")
-    stale = (not os.path.exists(LIB_PATH)
-             or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr)))
+    stale = any(not os.path.exists(lp) or os.path.getmtime(lp) < max(os.path.getmtime(src), os.path.getmtime(hdr))
+                for lp in (LIB_PATH, LIB_PATH_WIDE))
     if force or stale:
         res = subprocess.run(["make", "-C", HERE] + (["-B"] if force else []), capture_output=True, text=True)
         if res.returncode != 0:
@@ -30,13 +31,12 @@ def build(force=False):
     return LIB_PATH
 
 
-def load():
-    global _lib
-    if _lib is None:
+def load(wide=False):
+    if wide not in _libs:
         build()
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(LIB_PATH_WIDE if wide else LIB_PATH)
         vp, i64 = C.c_void_p, C.c_int64
-        lib.gwo_create.argtypes = [C.POINTER(N.GwConfig), C.POINTER(vp)]
+        lib.gwo_create.argtypes = [C.POINTER(N.GwwConfig if wide else N.GwConfig), C.POINTER(vp)]
         lib.gwo_destroy.argtypes = [vp]
         lib.gwo_reset.argtypes = [vp, vp, C.POINTER(N.GwIO)]
         lib.gwo_step.argtypes = [vp, C.POINTER(N.GwIO), C.c_int]
@@ -46,8 +46,8 @@ def load():
         lib.gwo_fear_one_actor.argtypes = [vp, i64] + [vp] * 10
         lib.gwo_fear_matrix.argtypes = [vp, i64] + [vp] * 8
         lib.gwo_feal.argtypes = [vp, i64] + [vp] * 8
-        _lib = lib
-    return _lib
+        _libs[wide] = lib
+    return _libs[wide]
 
 
 def _p(a):
@@ -59,11 +59,16 @@ def _i8(x):
 
 
 class COracle:
-    def __init__(self, scenario="Level 3", num_envs=1, threads=1, **kw):
-        self.lib = load()
+    def __init__(self, scenario="Level 3", num_envs=1, threads=1, layout=None, **kw):
+        """layout: "packed" (gw_config), "wide" (gww_config: the general layout) or None = packed when the scenario fits."""
         self.scenario = builtin_scenario(scenario) if isinstance(scenario, str) else scenario
         self.obs_bf16 = bool(kw.pop("obs_bf16", False))
-        self.cfg = N.build_config(self.scenario, num_envs=num_envs, obs_bf16=self.obs_bf16, **kw)
+        if layout is None:
+            layout = "packed" if N.fits_packed_layout(self.scenario, kw.get("n_agents")) else "wide"
+        self.wide = layout == "wide"
+        self.PAD = N.GWW_MAX_AGENTS if self.wide else N.GW_MAX_AGENTS      # per-agent dimension of the operator-level arrays
+        self.lib = load(self.wide)
+        self.cfg = (N.build_wide_config if self.wide else N.build_config)(self.scenario, num_envs=num_envs, obs_bf16=self.obs_bf16, **kw)
         self.threads = threads
         h = C.c_void_p()
         rc = self.lib.gwo_create(C.byref(self.cfg), C.byref(h))
@@ -119,16 +124,16 @@ class COracle:
         return {name: getattr(s, name) for name, _ in N.GwStats._fields_}
 
     def state(self):
-        out = np.zeros((self.E, 4), np.uint32)
+        out = np.zeros((self.E, 16 if self.wide else 4), np.uint32)
         self.lib.gwo_get_state(self._h, _p(out))
         return out
 
     def update_world(self, positions, actions, n_agents=None, apples=None):
         pos, act, nper, app = _i8(positions), _i8(actions), _i8(n_agents), _i8(apples)
         Cn = pos.shape[0]
-        new_pos = np.zeros((Cn, 4, 2), np.int8)
-        crash = np.zeros((Cn, 4), np.uint8)
-        restr = np.zeros((Cn, 4), np.uint8)
+        new_pos = np.zeros((Cn, self.PAD, 2), np.int8)
+        crash = np.zeros((Cn, self.PAD), np.uint8)
+        restr = np.zeros((Cn, self.PAD), np.uint8)
         caught = np.zeros((Cn, 2, 2), np.int8)
         rc = self.lib.gwo_update_world(self._h, Cn, _p(nper), _p(pos), _p(act), _p(app), _p(new_pos), _p(crash),
                                        _p(restr), _p(caught))
@@ -139,9 +144,9 @@ class COracle:
         pos, act, md, ac, nper = _i8(positions), _i8(actions), _i8(mdr), _i8(actor), _i8(n_agents)
         il = None if in_list is None else np.ascontiguousarray(in_list, dtype=np.uint8)
         Cn = pos.shape[0]
-        resp = np.zeros((Cn, 4))
-        n_mdr = np.zeros((Cn, 4), np.int8)
-        n_act = np.zeros((Cn, 4), np.int8)
+        resp = np.zeros((Cn, self.PAD))
+        n_mdr = np.zeros((Cn, self.PAD), np.int8)
+        n_act = np.zeros((Cn, self.PAD), np.int8)
         fsum = np.zeros(Cn)
         rc = self.lib.gwo_fear_one_actor(self._h, Cn, _p(nper), _p(pos), _p(act), _p(md), _p(ac), _p(il), _p(resp),
                                          _p(n_mdr), _p(n_act), _p(fsum))
@@ -160,7 +165,7 @@ class COracle:
         return val, n_mdr, n_act
 
     def fear_matrix(self, positions, actions, mdr, in_list=None, n_agents=None):
-        return self._matrix_call(self.lib.gwo_fear_matrix, (4, 4), positions, actions, mdr, in_list, n_agents)
+        return self._matrix_call(self.lib.gwo_fear_matrix, (self.PAD, self.PAD), positions, actions, mdr, in_list, n_agents)
 
     def feal(self, positions, actions, mdr, in_list=None, n_agents=None):
-        return self._matrix_call(self.lib.gwo_feal, (4,), positions, actions, mdr, in_list, n_agents)
+        return self._matrix_call(self.lib.gwo_feal, (self.PAD,), positions, actions, mdr, in_list, n_agents)

@@ -11,7 +11,7 @@
  * Parity pin: tests/test_c_oracle.py checks it against the golden vectors recorded from the
  * reference (the .npz files under tests/golden/) and against the Python restatement (oracle/gridworld_oracle.py).
  *
- * It shares the POD structs of include/gridworld_b200.h (gw_config, gw_io with HOST pointers) so
+ * It shares the POD structs of include/gridworld_b200.h (gw_config / gww_config, gw_io with HOST pointers) so
  * that the same inputs can be fed to both sides.  The device-RNG mode (Philox4x32-10 counters,
  * DESIGN.md "RNG") is restated here too, so full-size rollouts can be compared bit for bit.
  *
@@ -32,6 +32,26 @@
 
 #define MAXSTEPS 4 /* GWorld.MaxSteps, grid_world.py:24 */
 
+/* Two builds of this one source (oracle/Makefile): libgw_oracle.so restates the path on the packed layout's config
+ * (gw_config: W = 16, H <= 16, <= 4 agents), libgw_oracle_wide.so (-DGWO_WIDE) on the general layout's (gww_config: up to
+ * 64 x 64, up to 16 agents).  The algorithm text below is the same; only the array bounds, the cell index of the
+ * policy / MdR maps and the cell encoding of the restricted paths differ. */
+#ifdef GWO_WIDE
+typedef gww_config gwo_config;
+#define OR_A GWW_MAX_AGENTS
+#define OR_CELLS GWW_MAX_CELLS
+#define CELL_IDX(cfg, r, c) ((r) * (cfg)->width + (c))
+#define BLK_R(v) ((int)((v) >> 8))
+#define BLK_C(v) ((int)((v) & 255))
+#else
+typedef gw_config gwo_config;
+#define OR_A GW_MAX_AGENTS
+#define OR_CELLS (GW_MAX_H * GW_W)
+#define CELL_IDX(cfg, r, c) ((r) * GW_W + (c))
+#define BLK_R(v) ((int)((v) >> 4))
+#define BLK_C(v) ((int)((v) & 15))
+#endif
+
 typedef struct { int r, c; } cell_t;
 
 static const int MOVE_DR[9] = {0, -1, 1, 0, 0, -1, 1, 0, 0};   /* custom_agent.py:140-150 */
@@ -39,7 +59,7 @@ static const int MOVE_DC[9] = {0, 0, 0, -1, 1, 0, 0, -1, 1};
 static const int MOVE_LEN[9] = {1, 1, 1, 1, 1, 2, 2, 2, 2};
 
 typedef struct env_state {
-  cell_t loc[GW_MAX_AGENTS];
+  cell_t loc[OR_A];
   int apple_present[GW_MAX_LEARNERS];
   int term[GW_MAX_LEARNERS];
   int trunc;
@@ -51,10 +71,10 @@ typedef struct env_state {
 } env_state;
 
 typedef struct gwo_handle {
-  gw_config cfg;
+  gwo_config cfg;
   env_state* env;
   uint32_t thr[GW_MAX_POLICIES][2][8];
-  cell_t active[GW_MAX_H * GW_W];
+  cell_t active[OR_CELLS];
   int n_active;
   double resp_lut[10][10];
   int reset_done;
@@ -65,14 +85,14 @@ typedef struct gwo_handle {
   pthread_mutex_t stat_mu;
 } gwo_handle;
 
-static int cfg_active(const gw_config* c, int r, int col) {
+static int cfg_active(const gwo_config* c, int r, int col) {
   return r >= 0 && r < c->height && col >= 0 && col < c->width && ((c->map_rows[r] >> col) & 1);
 }
 
 /* ------------------------------------------------------------------ UpdateGWorld */
 typedef struct {
-  cell_t loc[GW_MAX_AGENTS];
-  int crash[GW_MAX_AGENTS], restr[GW_MAX_AGENTS];
+  cell_t loc[OR_A];
+  int crash[OR_A], restr[OR_A];
   int caught[2][2];
   int unresolved;
 } update_out;
@@ -81,20 +101,20 @@ static int cell_eq(cell_t a, cell_t b) { return a.r == b.r && a.c == b.c; }
 
 /* `[old, new] in self.RestrictedPaths` (grid_world.py:498) with the tuple-typed paths the reference intends (:654-665):
  * a linear search of the list, as there */
-static int path_restricted(const gw_config* cfg, cell_t a, cell_t b) {
+static int path_restricted(const gwo_config* cfg, cell_t a, cell_t b) {
   for (int k = 0; k < cfg->n_blocked; ++k)
-    if ((cfg->blocked_from[k] >> 4) == a.r && (cfg->blocked_from[k] & 15) == a.c && (cfg->blocked_to[k] >> 4) == b.r &&
-        (cfg->blocked_to[k] & 15) == b.c)
+    if (BLK_R(cfg->blocked_from[k]) == a.r && BLK_C(cfg->blocked_from[k]) == a.c && BLK_R(cfg->blocked_to[k]) == b.r &&
+        BLK_C(cfg->blocked_to[k]) == b.c)
       return 1;
   return 0;
 }
 
-static void update_world(const gw_config* cfg, int n, const cell_t* loc0, const int* act, const cell_t* apples,
+static void update_world(const gwo_config* cfg, int n, const cell_t* loc0, const int* act, const cell_t* apples,
                          const int* apple_on, int n_eaters, update_out* out) {
-  cell_t path[GW_MAX_AGENTS][MAXSTEPS + 1];
-  int plen[GW_MAX_AGENTS];
-  int crash[GW_MAX_AGENTS] = {0, 0, 0, 0}, restr[GW_MAX_AGENTS] = {0, 0, 0, 0};
-  cell_t cur[GW_MAX_AGENTS];
+  cell_t path[OR_A][MAXSTEPS + 1];
+  int plen[OR_A];
+  int crash[OR_A] = {0}, restr[OR_A] = {0};
+  cell_t cur[OR_A];
   memset(out, 0, sizeof(*out));
   for (int i = 0; i < n; ++i) { path[i][0] = loc0[i]; plen[i] = 1; }                 /* :437-439 */
   for (int step = 0; step < MAXSTEPS; ++step) {                                     /* :458 */
@@ -165,11 +185,11 @@ static void update_world(const gw_config* cfg, int n, const cell_t* loc0, const 
 static int manhattan(cell_t a, cell_t b) { return abs(a.r - b.r) + abs(a.c - b.c); }
 
 /* CountValidMovesOfAffected_tuple, Responsibility.py:20-54; agents outside `in_list` Stay (:43) */
-static int count_valid(const gw_config* cfg, int n, const cell_t* loc, const int* list_act, const int* in_list,
+static int count_valid(const gwo_config* cfg, int n, const cell_t* loc, const int* list_act, const int* in_list,
                        int affected) {
   int count = 0;
   for (int a = 0; a < GW_N_ACTIONS; ++a) {
-    int act[GW_MAX_AGENTS];
+    int act[OR_A];
     for (int i = 0; i < n; ++i) act[i] = in_list[i] ? list_act[i] : 0;
     if (in_list[affected]) act[affected] = a;                     /* SwapActionIDs4Agents, grid_world.py:709-726 */
     update_out o;
@@ -181,10 +201,10 @@ static int count_valid(const gw_config* cfg, int n, const cell_t* loc, const int
 
 static void fear_one_actor(const gwo_handle* h, int n, const cell_t* loc, const int* act, const int* in_list,
                            const int* mdr, int actor, double* resp, int* n_mdr, int* n_act) {
-  for (int j = 0; j < GW_MAX_AGENTS; ++j) { resp[j] = 0.0; n_mdr[j] = 0; n_act[j] = 0; }
+  for (int j = 0; j < OR_A; ++j) { resp[j] = 0.0; n_mdr[j] = 0; n_act[j] = 0; }
   for (int jj = 0; jj < n; ++jj) {                                /* Responsibility.py:163-198 */
     if (jj == actor) continue;
-    int la[GW_MAX_AGENTS];
+    int la[OR_A];
     for (int i = 0; i < n; ++i) la[i] = act[i];
     la[actor] = mdr[actor];
     n_mdr[jj] = count_valid(&h->cfg, n, loc, la, in_list, jj);
@@ -195,27 +215,37 @@ static void fear_one_actor(const gwo_handle* h, int n, const cell_t* loc, const 
   }
 }
 
-/* np.sum over the n x n Resp matrix (a single non-zero row) in numpy's pairwise order: numpy >= 1.22 adds an
- * array of 8 <= len <= 128 doubles with 8 interleaved accumulators r[k] += a[i+k] and combines them as
- * ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)), then the tail; shorter arrays are summed left to right. */
-static double np_sum_matrix(int n, int actor, const double* row) {
-  double a[16];
-  const int len = n * n;
-  for (int i = 0; i < len; ++i) a[i] = 0.0;
-  for (int j = 0; j < n; ++j) a[actor * n + j] = row[j];
+/* np.sum over the n x n Resp matrix (a single non-zero row) in numpy's pairwise order (numpy/_core/src/umath/
+ * loops_utils.h.src, pairwise_sum): fewer than 8 elements are added left to right; up to 128 go through 8 interleaved
+ * accumulators r[k] += a[i+k] combined as ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)), then the tail; longer arrays are split
+ * at n/2 rounded down to a multiple of 8 and the halves' sums added (n = 12..16 agents: 144..256 elements). */
+static double np_pairwise(const double* a, int len) {
   if (len < 8) {
     double res = 0.0;
     for (int i = 0; i < len; ++i) res += a[i];
     return res;
   }
-  double r[8];
-  for (int k = 0; k < 8; ++k) r[k] = a[k];
-  int i = 8;
-  for (; i < len - (len % 8); i += 8)
-    for (int k = 0; k < 8; ++k) r[k] += a[i + k];
-  double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-  for (; i < len; ++i) res += a[i];
-  return res;
+  if (len <= 128) {
+    double r[8];
+    for (int k = 0; k < 8; ++k) r[k] = a[k];
+    int i = 8;
+    for (; i < len - (len % 8); i += 8)
+      for (int k = 0; k < 8; ++k) r[k] += a[i + k];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < len; ++i) res += a[i];
+    return res;
+  }
+  int half = len / 2;
+  half -= half % 8;
+  return np_pairwise(a, half) + np_pairwise(a + half, len - half);
+}
+
+static double np_sum_matrix(int n, int actor, const double* row) {
+  double a[OR_A * OR_A];
+  const int len = n * n;
+  for (int i = 0; i < len; ++i) a[i] = 0.0;
+  for (int j = 0; j < n; ++j) a[actor * n + j] = row[j];
+  return np_pairwise(a, len);
 }
 
 /* ------------------------------------------------------------------ RNG (device-RNG mode restated) */
@@ -248,7 +278,7 @@ static void policy_thresholds(const float sw[3], const float dw_in[4], int pertu
 }
 
 static void spawn(const gwo_handle* h, int64_t e, uint32_t tick, const int8_t* spawn_in, cell_t* loc) {
-  const gw_config* c = &h->cfg;
+  const gwo_config* c = &h->cfg;
   if (spawn_in) {
     for (int i = 0; i < c->n_agents; ++i) {
       loc[i].r = spawn_in[(e * c->n_agents + i) * 2];
@@ -257,11 +287,14 @@ static void spawn(const gwo_handle* h, int64_t e, uint32_t tick, const int8_t* s
     return;
   }
   const uint64_t gid = (uint64_t)(c->env_id_base + e);
-  uint32_t w[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), tick, 0x100u};
-  philox4x32(w, (uint32_t)c->seed, (uint32_t)(c->seed >> 32));
-  int chosen[4] = {0, 0, 0, 0};
+  uint32_t w[4] = {0, 0, 0, 0};
+  int chosen[OR_A] = {0};
   for (int k = 0; k < c->n_agents; ++k) {
-    int d = (int)(((uint64_t)w[k] * (uint32_t)(h->n_active - k)) >> 32);
+    if ((k & 3) == 0) {                                /* draw k: Philox call 0x100 + k/4, word k%4 */
+      w[0] = (uint32_t)gid; w[1] = (uint32_t)(gid >> 32); w[2] = tick; w[3] = 0x100u + (uint32_t)(k >> 2);
+      philox4x32(w, (uint32_t)c->seed, (uint32_t)(c->seed >> 32));
+    }
+    int d = (int)(((uint64_t)w[k & 3] * (uint32_t)(h->n_active - k)) >> 32);
     int pos = 0;
     for (int t = 0; t < k; ++t)
       if (d >= chosen[t]) { ++d; pos = t + 1; }
@@ -280,10 +313,10 @@ static uint16_t f32_to_bf16(float f) {
 }
 
 static void write_obs(const gwo_handle* h, void* base, int64_t e, const env_state* s, int fresh) {
-  const gw_config* c = &h->cfg;
+  const gwo_config* c = &h->cfg;
   const int len = c->height * c->width;
   for (int k = 0; k < c->n_learners; ++k) {
-    float obs[GW_MAX_H * GW_W];
+    float obs[OR_CELLS];
     for (int r = 0; r < c->height; ++r)
       for (int col = 0; col < c->width; ++col) obs[r * c->width + col] = cfg_active(c, r, col) ? 0.0f : -1.0f;
     for (int i = 0; i < c->n_agents; ++i)                       /* WorldState: grid_world.py:230 / AddAgent :140 */
@@ -311,7 +344,7 @@ static void write_obs(const gwo_handle* h, void* base, int64_t e, const env_stat
 }
 
 static void write_masks(const gwo_handle* h, int8_t* dst, int64_t e, const env_state* s) {
-  const gw_config* c = &h->cfg;
+  const gwo_config* c = &h->cfg;
   if (!dst) return;
   for (int k = 0; k < c->n_learners; ++k) {                     /* ma_customenv.py:467-506: target cell only */
     int8_t* m = dst + (e * c->n_learners + k) * GW_N_ACTIONS;
@@ -322,7 +355,7 @@ static void write_masks(const gwo_handle* h, int8_t* dst, int64_t e, const env_s
 }
 
 static void fresh_env(const gwo_handle* h, env_state* s) {
-  const gw_config* c = &h->cfg;
+  const gwo_config* c = &h->cfg;
   for (int k = 0; k < GW_MAX_LEARNERS; ++k) {
     s->apple_present[k] = k < c->n_learners && c->apple_row[k] >= 0;
     s->term[k] = 0; s->pd_valid[k] = 0; s->pd[k] = 0; s->ep_ret[k] = 0;
@@ -338,8 +371,8 @@ static void fresh_env(const gwo_handle* h, env_state* s) {
 /* ------------------------------------------------------------------ public API */
 #define EXPORT __attribute__((visibility("default")))
 
-EXPORT int gwo_create(const gw_config* cfg, gwo_handle** out) {
-  if (!cfg || !out || cfg->struct_size != (int32_t)sizeof(gw_config)) return GW_EINVAL;
+EXPORT int gwo_create(const gwo_config* cfg, gwo_handle** out) {
+  if (!cfg || !out || cfg->struct_size != (int32_t)sizeof(gwo_config)) return GW_EINVAL;
   gwo_handle* h = (gwo_handle*)calloc(1, sizeof(gwo_handle));
   if (!h) return GW_ENOMEM;
   h->cfg = *cfg;
@@ -371,7 +404,7 @@ EXPORT int gwo_destroy(gwo_handle* h) {
 }
 
 static void reset_range(gwo_handle* h, const uint8_t* mask, const gw_io* io, int64_t lo, int64_t hi) {
-  const gw_config* c = &h->cfg;
+  const gwo_config* c = &h->cfg;
   for (int64_t e = lo; e < hi; ++e) {
     if (mask && !mask[e]) continue;
     env_state* s = &h->env[e];
@@ -398,16 +431,16 @@ EXPORT int gwo_reset(gwo_handle* h, const uint8_t* mask, const gw_io* io) {
 typedef struct { uint64_t episodes, len_sum, crashes, apples, unresolved, fear_nz; double return_sum, fear_sum; } stat_acc;
 
 static void step_range(gwo_handle* h, const gw_io* io, int64_t lo, int64_t hi, stat_acc* acc) {
-  const gw_config* c = &h->cfg;
+  const gwo_config* c = &h->cfg;
   const int n = c->n_agents, nl = c->n_learners;
   double pthr = c->perturb_prob * 4294967296.0;
   const uint32_t perturb_thr = pthr >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)pthr;
   for (int64_t e = lo; e < hi; ++e) {
     env_state* s = &h->env[e];
-    int act[GW_MAX_AGENTS], mdr[GW_MAX_AGENTS];
+    int act[OR_A], mdr[OR_A];
     /* setup_step, ma_customenv.py:432-452 */
     for (int i = 0; i < n; ++i) {
-      mdr[i] = c->mdr_map[s->loc[i].r * GW_W + s->loc[i].c];
+      mdr[i] = c->mdr_map[CELL_IDX(c, s->loc[i].r, s->loc[i].c)];
       if (i < nl) act[i] = io->learner_actions[e * nl + i];
       else if (io->npc_actions) act[i] = io->npc_actions[e * n + i];
       else {
@@ -418,7 +451,7 @@ static void step_range(gwo_handle* h, const gw_io* io, int64_t lo, int64_t hi, s
         uint32_t w[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), s->tick, (uint32_t)(m >> 1)};
         philox4x32(w, (uint32_t)c->seed, (uint32_t)(c->seed >> 32));
         const int pert = w[2 * (m & 1)] < perturb_thr;
-        const uint32_t* thr = h->thr[c->policy_map[s->loc[i].r * GW_W + s->loc[i].c]][pert];
+        const uint32_t* thr = h->thr[c->policy_map[CELL_IDX(c, s->loc[i].r, s->loc[i].c)]][pert];
         const uint32_t u = w[2 * (m & 1) + 1] >> 1;
         int a = 0;
         for (int k = 0; k < 8; ++k) a += (u >= thr[k]);
@@ -431,14 +464,14 @@ static void step_range(gwo_handle* h, const gw_io* io, int64_t lo, int64_t hi, s
     double fear[GW_MAX_LEARNERS] = {0.0, 0.0};
     if (c->fear) {
       for (int x = 0; x < nl; ++x) {
-        int in_list[GW_MAX_AGENTS], n_close = 0;
+        int in_list[OR_A], n_close = 0;
         for (int k = 0; k < n; ++k) {                                  /* close_agents :456-464 */
           in_list[k] = (k == x) || manhattan(s->loc[x], s->loc[k]) <= c->fear_radius;
           n_close += in_list[k];
         }
         if (c->env_kind == GW_ENV_SINGLE && n_close <= 1) { fear[x] = 0.0; continue; }   /* customenv.py:117-118 */
-        double resp[GW_MAX_AGENTS];
-        int nm[GW_MAX_AGENTS], na[GW_MAX_AGENTS];
+        double resp[OR_A];
+        int nm[OR_A], na[OR_A];
         fear_one_actor(h, n, s->loc, act, in_list, mdr, x, resp, nm, na);
         fear[x] = np_sum_matrix(n, x, resp);
       }
@@ -513,7 +546,10 @@ static void step_range(gwo_handle* h, const gw_io* io, int64_t lo, int64_t hi, s
     if (io->ended) io->ended[e] = (uint8_t)ended;
     if (io->info) {
       uint32_t bits = 0;
-      for (int i = 0; i < n; ++i) bits |= ((uint32_t)u.crash[i] << i) | ((uint32_t)u.restr[i] << (4 + i));
+      for (int i = 0; i < n && i < 4; ++i) bits |= ((uint32_t)u.crash[i] << i) | ((uint32_t)u.restr[i] << (4 + i));
+#ifdef GWO_WIDE
+      for (int i = 0; i < n; ++i) bits |= (uint32_t)u.crash[i] << (16 + i);
+#endif
       bits |= (uint32_t)crash_count << 8 | (uint32_t)apples_rewarded << 10 | (uint32_t)ended << 12 |
               (uint32_t)u.unresolved << 13 | (uint32_t)shaped[0] << 14 | (uint32_t)shaped[1] << 15;
       io->info[e] = bits;
@@ -591,6 +627,29 @@ EXPORT int gwo_get_stats(gwo_handle* h, gw_stats* out) {
   return GW_OK;
 }
 
+#ifdef GWO_WIDE
+/* gww_env_state (include/gridworld_b200.h), 64 bytes per env */
+EXPORT int gwo_get_state(gwo_handle* h, uint32_t* dst_words) {
+  if (!h || !dst_words) return GW_EINVAL;
+  gww_env_state* dst = (gww_env_state*)dst_words;
+  for (int64_t e = 0; e < h->cfg.num_envs; ++e) {
+    const env_state* s = &h->env[e];
+    gww_env_state o;
+    memset(&o, 0, sizeof(o));
+    for (int i = 0; i < OR_A; ++i)
+      o.cell[i] = i < h->cfg.n_agents ? (uint16_t)((s->loc[i].r << 8) | s->loc[i].c) : (uint16_t)0xFFFFu;
+    o.flags = (uint32_t)s->apple_present[0] | (uint32_t)s->apple_present[1] << 1;
+    if (h->cfg.env_kind == GW_ENV_MULTI) o.flags |= (uint32_t)s->term[0] << 2 | (uint32_t)s->term[1] << 3 | (uint32_t)s->trunc << 4;
+    o.flags |= (uint32_t)s->pd_valid[0] << 5 | (uint32_t)s->pd_valid[1] << 6;
+    o.tick = s->tick;
+    o.episode_return[0] = s->ep_ret[0]; o.episode_return[1] = s->ep_ret[1];
+    o.prev_distance[0] = (uint16_t)s->pd[0]; o.prev_distance[1] = (uint16_t)s->pd[1];
+    o.steps = (uint32_t)s->steps;
+    dst[e] = o;
+  }
+  return GW_OK;
+}
+#else
 /* the same 16-byte packed state as gw_get_state (csrc/gw_kernels.cu "meta word") */
 EXPORT int gwo_get_state(gwo_handle* h, uint32_t* dst) {
   if (!h || !dst) return GW_EINVAL;
@@ -608,24 +667,26 @@ EXPORT int gwo_get_state(gwo_handle* h, uint32_t* dst) {
   return GW_OK;
 }
 
+#endif
+
 EXPORT int gwo_update_world(gwo_handle* h, int64_t C, const int8_t* n_per, const int8_t* pos, const int8_t* act,
                             const int8_t* apples, int8_t* new_pos, uint8_t* crash, uint8_t* restr, int8_t* caught) {
   if (!h) return GW_EINVAL;
   for (int64_t c = 0; c < C; ++c) {
     const int n = n_per ? n_per[c] : h->cfg.n_agents;
-    cell_t loc[4], ap[2] = {{-1, -1}, {-1, -1}};
-    int a[4] = {0, 0, 0, 0}, on[2] = {0, 0};
-    for (int i = 0; i < n; ++i) { loc[i].r = pos[(c * 4 + i) * 2]; loc[i].c = pos[(c * 4 + i) * 2 + 1]; a[i] = act[c * 4 + i]; }
+    cell_t loc[OR_A], ap[2] = {{-1, -1}, {-1, -1}};
+    int a[OR_A] = {0}, on[2] = {0, 0};
+    for (int i = 0; i < n; ++i) { loc[i].r = pos[(c * OR_A + i) * 2]; loc[i].c = pos[(c * OR_A + i) * 2 + 1]; a[i] = act[c * OR_A + i]; }
     if (apples)
       for (int k = 0; k < 2; ++k)
         if (apples[(c * 2 + k) * 2] >= 0) { on[k] = 1; ap[k].r = apples[(c * 2 + k) * 2]; ap[k].c = apples[(c * 2 + k) * 2 + 1]; }
     update_out u;
     update_world(&h->cfg, n, loc, a, apples ? ap : NULL, on, n < 2 ? n : 2, &u);
-    for (int i = 0; i < 4; ++i) {
-      new_pos[(c * 4 + i) * 2] = i < n ? (int8_t)u.loc[i].r : -1;
-      new_pos[(c * 4 + i) * 2 + 1] = i < n ? (int8_t)u.loc[i].c : -1;
-      crash[c * 4 + i] = i < n ? (uint8_t)u.crash[i] : 0;
-      restr[c * 4 + i] = i < n ? (uint8_t)u.restr[i] : 0;
+    for (int i = 0; i < OR_A; ++i) {
+      new_pos[(c * OR_A + i) * 2] = i < n ? (int8_t)u.loc[i].r : -1;
+      new_pos[(c * OR_A + i) * 2 + 1] = i < n ? (int8_t)u.loc[i].c : -1;
+      crash[c * OR_A + i] = i < n ? (uint8_t)u.crash[i] : 0;
+      restr[c * OR_A + i] = i < n ? (uint8_t)u.restr[i] : 0;
     }
     if (caught)
       for (int e = 0; e < 2; ++e)
@@ -640,21 +701,21 @@ EXPORT int gwo_fear_one_actor(gwo_handle* h, int64_t C, const int8_t* n_per, con
   if (!h) return GW_EINVAL;
   for (int64_t c = 0; c < C; ++c) {
     const int n = n_per ? n_per[c] : h->cfg.n_agents;
-    cell_t loc[4];
-    int a[4] = {0, 0, 0, 0}, m[4] = {0, 0, 0, 0}, il[4] = {0, 0, 0, 0};
+    cell_t loc[OR_A];
+    int a[OR_A] = {0}, m[OR_A] = {0}, il[OR_A] = {0};
     for (int i = 0; i < n; ++i) {
-      loc[i].r = pos[(c * 4 + i) * 2]; loc[i].c = pos[(c * 4 + i) * 2 + 1];
-      a[i] = act[c * 4 + i]; m[i] = mdr[c * 4 + i];
-      il[i] = in_list ? (in_list[c * 4 + i] != 0) : 1;
+      loc[i].r = pos[(c * OR_A + i) * 2]; loc[i].c = pos[(c * OR_A + i) * 2 + 1];
+      a[i] = act[c * OR_A + i]; m[i] = mdr[c * OR_A + i];
+      il[i] = in_list ? (in_list[c * OR_A + i] != 0) : 1;
     }
     il[actor[c]] = 1;
-    double r[4];
-    int nm[4], na[4];
+    double r[OR_A];
+    int nm[OR_A], na[OR_A];
     fear_one_actor(h, n, loc, a, il, m, actor[c], r, nm, na);
-    for (int i = 0; i < 4; ++i) {
-      resp[c * 4 + i] = i < n ? r[i] : 0.0;
-      if (n_mdr) n_mdr[c * 4 + i] = (int8_t)(i < n ? nm[i] : 0);
-      if (n_act) n_act[c * 4 + i] = (int8_t)(i < n ? na[i] : 0);
+    for (int i = 0; i < OR_A; ++i) {
+      resp[c * OR_A + i] = i < n ? r[i] : 0.0;
+      if (n_mdr) n_mdr[c * OR_A + i] = (int8_t)(i < n ? nm[i] : 0);
+      if (n_act) n_act[c * OR_A + i] = (int8_t)(i < n ? na[i] : 0);
     }
     if (fear_sum) fear_sum[c] = np_sum_matrix(n, actor[c], r);
   }
@@ -667,26 +728,26 @@ EXPORT int gwo_fear_matrix(gwo_handle* h, int64_t C, const int8_t* n_per, const 
   if (!h) return GW_EINVAL;
   for (int64_t c = 0; c < C; ++c) {
     const int n = n_per ? n_per[c] : h->cfg.n_agents;
-    cell_t loc[4];
-    int a[4] = {0, 0, 0, 0}, il[4] = {0, 0, 0, 0};
+    cell_t loc[OR_A];
+    int a[OR_A] = {0}, il[OR_A] = {0};
     for (int i = 0; i < n; ++i) {
-      loc[i].r = pos[(c * 4 + i) * 2]; loc[i].c = pos[(c * 4 + i) * 2 + 1];
-      a[i] = act[c * 4 + i];
-      il[i] = in_list ? (in_list[c * 4 + i] != 0) : 1;
+      loc[i].r = pos[(c * OR_A + i) * 2]; loc[i].c = pos[(c * OR_A + i) * 2 + 1];
+      a[i] = act[c * OR_A + i];
+      il[i] = in_list ? (in_list[c * OR_A + i] != 0) : 1;
     }
-    for (int i = 0; i < 16; ++i) { resp[c * 16 + i] = 0.0; n_mdr[c * 16 + i] = 0; n_act[c * 16 + i] = 0; }
+    for (int i = 0; i < OR_A * OR_A; ++i) { resp[c * OR_A * OR_A + i] = 0.0; n_mdr[c * OR_A * OR_A + i] = 0; n_act[c * OR_A * OR_A + i] = 0; }
     for (int ii = 0; ii < n; ++ii)
       for (int jj = 0; jj < n; ++jj) {
         if (ii == jj) continue;
-        int la[4];
+        int la[OR_A];
         for (int i = 0; i < n; ++i) la[i] = a[i];
-        if (il[ii]) la[ii] = mdr[c * 4 + ii];
+        if (il[ii]) la[ii] = mdr[c * OR_A + ii];
         const int m = count_valid(&h->cfg, n, loc, la, il, jj);
         const int v = count_valid(&h->cfg, n, loc, a, il, jj);
         double r = ((double)m - (double)v) / ((double)m + 0.000001);
-        resp[c * 16 + ii * 4 + jj] = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
-        n_mdr[c * 16 + ii * 4 + jj] = (int8_t)m;
-        n_act[c * 16 + ii * 4 + jj] = (int8_t)v;
+        resp[(c * OR_A + ii) * OR_A + jj] = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+        n_mdr[(c * OR_A + ii) * OR_A + jj] = (int8_t)m;
+        n_act[(c * OR_A + ii) * OR_A + jj] = (int8_t)v;
       }
   }
   return GW_OK;
@@ -698,24 +759,24 @@ EXPORT int gwo_feal(gwo_handle* h, int64_t C, const int8_t* n_per, const int8_t*
   if (!h) return GW_EINVAL;
   for (int64_t c = 0; c < C; ++c) {
     const int n = n_per ? n_per[c] : h->cfg.n_agents;
-    cell_t loc[4];
-    int a[4] = {0, 0, 0, 0}, il[4] = {0, 0, 0, 0};
+    cell_t loc[OR_A];
+    int a[OR_A] = {0}, il[OR_A] = {0};
     for (int i = 0; i < n; ++i) {
-      loc[i].r = pos[(c * 4 + i) * 2]; loc[i].c = pos[(c * 4 + i) * 2 + 1];
-      a[i] = act[c * 4 + i];
-      il[i] = in_list ? (in_list[c * 4 + i] != 0) : 1;
+      loc[i].r = pos[(c * OR_A + i) * 2]; loc[i].c = pos[(c * OR_A + i) * 2 + 1];
+      a[i] = act[c * OR_A + i];
+      il[i] = in_list ? (in_list[c * OR_A + i] != 0) : 1;
     }
-    for (int ii = 0; ii < 4; ++ii) {
-      feal[c * 4 + ii] = 0.0; n_mdr[c * 4 + ii] = 0; n_act[c * 4 + ii] = 0;
+    for (int ii = 0; ii < OR_A; ++ii) {
+      feal[c * OR_A + ii] = 0.0; n_mdr[c * OR_A + ii] = 0; n_act[c * OR_A + ii] = 0;
       if (ii >= n) continue;
-      int la[4];
-      for (int i = 0; i < n; ++i) la[i] = (i == ii) ? a[i] : mdr[c * 4 + i];
+      int la[OR_A];
+      for (int i = 0; i < n; ++i) la[i] = (i == ii) ? a[i] : mdr[c * OR_A + i];
       const int m = count_valid(&h->cfg, n, loc, la, il, ii);
       const int v = count_valid(&h->cfg, n, loc, a, il, ii);
       double r = (double)v / ((double)m + 0.000001);
-      feal[c * 4 + ii] = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
-      n_mdr[c * 4 + ii] = (int8_t)m;
-      n_act[c * 4 + ii] = (int8_t)v;
+      feal[c * OR_A + ii] = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+      n_mdr[c * OR_A + ii] = (int8_t)m;
+      n_act[c * OR_A + ii] = (int8_t)v;
     }
   }
   return GW_OK;

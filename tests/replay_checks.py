@@ -63,14 +63,15 @@ class GpuBackend:
         return self.env.stats()
 
     def state(self):
-        return self.env.state_dict().numpy().view(np.uint32).reshape(self.E, 4)
+        return self.env.state_dict().numpy().view(np.uint32).reshape(self.E, -1)      # 4 words (packed layout) or 16 (general)
 
     def update_world(self, positions, actions, n_agents=None, apples=None):
         return tuple(t.cpu().numpy() for t in self.env.update_world(positions, actions, n_agents, apples))
 
     def fear_one_actor(self, positions, actions, mdr, actor, in_list=None, n_agents=None):
         r = self.env.fear_one_actor(positions, actions, mdr, actor, in_list, n_agents)
-        return tuple(t.cpu().numpy() for t in r) + (None,)
+        fsum = getattr(self.env, "last_fear_sum", None)                          # general layout: np.sum of the matrix as well
+        return tuple(t.cpu().numpy() for t in r) + (None if fsum is None else fsum.cpu().numpy(),)
 
     def fear_matrix(self, positions, actions, mdr, in_list=None, n_agents=None):
         return tuple(t.cpu().numpy() for t in self.env.fear_matrix(positions, actions, mdr, in_list, n_agents))
@@ -94,6 +95,13 @@ def wall_scenario():
     from marl_responsible_nav_b200 import builtin_scenario
     g = npz("wall_cases.npz")
     return builtin_scenario("Level 3", walls=g["walls"].tolist(), oneways=g["oneways"].tolist())
+
+
+def wide_scenario():
+    """The 20 x 28, 7-agent scenario of tests/golden/wide_scenarios.json (the reference's JSON format) with its walls /
+    one-ways enforced -- what make_wide_golden.py ran the reference on.  Does not fit the packed layout."""
+    from marl_responsible_nav_b200.scenarios import load_scenario_json
+    return load_scenario_json(os.path.join(GOLDEN, "wide_scenarios.json"), "Wide 20x28", walls="enforce")
 
 
 def _prefixed(name, prefix):
@@ -126,9 +134,9 @@ def check_fear_cases(make_backend, fixture="fear_cases.npz", prefix=""):
     return len(g["n"])
 
 
-def check_matrix_cases(make_backend):
+def check_matrix_cases(make_backend, fixture="matrix_cases.npz", prefix=""):
     """Responsibility.FeAR (all actors) and Responsibility.FeAL, full and partial action lists."""
-    g = npz("matrix_cases.npz")
+    g = _prefixed(fixture, prefix)
     b = make_backend(num_envs=1, fear=True)
     pos = np.where(g["locs"] < 0, 0, g["locs"]).astype(np.int8)
     resp, n_mdr, n_act = b.fear_matrix(pos, g["acts"], g["mdr"], in_list=g["in_list"], n_agents=g["n"])
@@ -145,19 +153,21 @@ def check_ma_episodes(make_backend, obs_bf16=False, fixture="ma_episodes.npz"):
     """All golden episodes of one FeAR setting run side by side, one env per episode."""
     g = npz(fixture)
     total = 0
+    H, W = g["obs"].shape[-2:]                      # 10 x 16 for the shipped scenarios; the general layout's fixtures differ
+    NA = g["all_act"].shape[1]
     for fear in (False, True):
         eps = np.flatnonzero(g["ep_fear"] == fear)
         E, T = len(eps), int(g["ep_n_steps"][eps].max())
         b = make_backend(num_envs=E, fear=fear, auto_reset=False, max_steps=0, obs_bf16=obs_bf16)
         b.reset(spawn=g["ep_spawn"][eps])
-        assert np.array_equal(obs_f32(b, b.obs).reshape(E, 2, 10, 16), g["ep_reset_obs"][eps])
+        assert np.array_equal(obs_f32(b, b.obs).reshape(E, 2, H, W), g["ep_reset_obs"][eps])
         assert np.array_equal(b.action_mask, g["ep_reset_mask"][eps])
         first, nst = g["ep_first_step"][eps], g["ep_n_steps"][eps]
         for t in range(T):
             live = np.flatnonzero(nst > t)
             idx = first[live] + t
             la = np.zeros((E, 2), np.int8)
-            npc = np.zeros((E, 4), np.int8)
+            npc = np.zeros((E, NA), np.int8)
             la[live], npc[live] = g["learner_act"][idx], g["all_act"][idx]
             b.step(la, npc_actions=npc)
             assert np.array_equal(b.positions[live], g["locs"][idx]), (fear, t)
@@ -167,29 +177,31 @@ def check_ma_episodes(make_backend, obs_bf16=False, fixture="ma_episodes.npz"):
             assert np.array_equal(b.fear[live], g["fear"][idx]), (fear, t)                   # fp64 bit-equal
             assert np.array_equal((b.info[live] >> 8) & 3, g["crash_count"][idx]), (fear, t)
             assert np.array_equal((b.info[live] >> 10) & 3, g["apples_caught"][idx]), (fear, t)
-            assert np.array_equal(obs_f32(b, b.obs)[live].reshape(-1, 2, 10, 16), g["obs"][idx]), (fear, t)
+            assert np.array_equal(obs_f32(b, b.obs)[live].reshape(-1, 2, H, W), g["obs"][idx]), (fear, t)
             assert np.array_equal(b.action_mask[live], g["mask"][idx]), (fear, t)
             total += len(live)
     return total
 
 
-def check_ma_sessions_autoreset(make_backend):
+def check_ma_sessions_autoreset(make_backend, fixture="ma_episodes.npz", max_steps=150):
     """One env per recorded session with auto-reset: episodes follow each other inside gw_step, the next
     episode's recorded spawn is offered at every step and consumed when the episode ends."""
-    g = npz("ma_episodes.npz")
+    g = npz(fixture)
+    H, W = g["obs"].shape[-2:]
+    NA = g["all_act"].shape[1]
     sessions = np.unique(g["ep_session"])
     n_steps_total = 0
     for fear in (False, True):
         sess = [s for s in sessions if bool(g["ep_fear"][g["ep_session"] == s][0]) == fear]
         E = len(sess)
         eps_of = [np.flatnonzero(g["ep_session"] == s) for s in sess]
-        b = make_backend(num_envs=E, fear=fear, auto_reset=True, max_steps=150)
+        b = make_backend(num_envs=E, fear=fear, auto_reset=True, max_steps=max_steps)
         b.reset(spawn=np.stack([g["ep_spawn"][e[0]] for e in eps_of]))
         cur_ep = [0] * E            # index into eps_of[i]
         cur_t = [0] * E
         done = [False] * E
         while not all(done):
-            la = np.zeros((E, 2), np.int8); npc = np.zeros((E, 4), np.int8); spawn = np.zeros((E, 4, 2), np.int8)
+            la = np.zeros((E, 2), np.int8); npc = np.zeros((E, NA), np.int8); spawn = np.zeros((E, NA, 2), np.int8)
             for i in range(E):
                 if done[i]:
                     spawn[i] = g["ep_spawn"][eps_of[i][0]]
@@ -211,16 +223,16 @@ def check_ma_sessions_autoreset(make_backend):
                 assert np.array_equal(b.fear[i], g["fear"][s])
                 assert bool(b.ended[i]) == bool(last), (i, cur_ep[i], cur_t[i])
                 if last:
-                    assert np.array_equal(b.final_obs[i].reshape(2, 10, 16), g["obs"][s])
+                    assert np.array_equal(b.final_obs[i].reshape(2, H, W), g["obs"][s])
                     nxt = eps_of[i][cur_ep[i] + 1] if cur_ep[i] + 1 < len(eps_of[i]) else eps_of[i][0]
-                    assert np.array_equal(b.obs[i].reshape(2, 10, 16), g["ep_reset_obs"][nxt])
+                    assert np.array_equal(b.obs[i].reshape(2, H, W), g["ep_reset_obs"][nxt])
                     assert np.array_equal(b.action_mask[i], g["ep_reset_mask"][nxt])
                     cur_ep[i] += 1
                     cur_t[i] = 0
                     if cur_ep[i] >= len(eps_of[i]):
                         done[i] = True
                 else:
-                    assert np.array_equal(b.obs[i].reshape(2, 10, 16), g["obs"][s])
+                    assert np.array_equal(b.obs[i].reshape(2, H, W), g["obs"][s])
                     assert np.array_equal(b.action_mask[i], g["mask"][s])
                     cur_t[i] += 1
                 n_steps_total += 1
@@ -231,20 +243,22 @@ def check_ma_sessions_autoreset(make_backend):
 
 
 # ----------------------------------------------------------------------------- single-agent episodes
-def check_single_episodes(make_backend):
-    g = npz("single_episodes.npz")
+def check_single_episodes(make_backend, fixture="single_episodes.npz"):
+    g = npz(fixture)
+    H, W = g["obs"].shape[-2:]
+    NA = g["all_act"].shape[1]
     total = 0
     for fear in (False, True):
         eps = np.flatnonzero(g["ep_fear"] == fear)
         E, T = len(eps), int(g["ep_n_steps"][eps].max())
         b = make_backend(num_envs=E, fear=fear, env_kind="single", auto_reset=False, max_steps=0)
         b.reset(spawn=g["ep_spawn"][eps])
-        assert np.array_equal(b.obs.reshape(E, 10, 16), g["ep_reset_obs"][eps])
+        assert np.array_equal(b.obs.reshape(E, H, W), g["ep_reset_obs"][eps])
         first, nst = g["ep_first_step"][eps], g["ep_n_steps"][eps]
         for t in range(T):
             live = np.flatnonzero(nst > t)
             idx = first[live] + t
-            la = np.zeros((E, 1), np.int8); npc = np.zeros((E, 4), np.int8)
+            la = np.zeros((E, 1), np.int8); npc = np.zeros((E, NA), np.int8)
             la[live, 0], npc[live] = g["action"][idx], g["all_act"][idx]
             b.step(la, npc_actions=npc)
             assert np.array_equal(b.positions[live], g["locs"][idx]), (fear, t)
@@ -253,6 +267,6 @@ def check_single_episodes(make_backend):
             assert np.array_equal(b.truncated[live, 0].astype(bool), g["trunc"][idx]), (fear, t)
             assert np.array_equal(b.fear[live, 0], g["fear"][idx]), (fear, t)
             assert np.array_equal(((b.info[live] >> 4) & 1).astype(bool), g["restricted"][idx]), (fear, t)
-            assert np.array_equal(b.obs[live].reshape(-1, 10, 16), g["obs"][idx]), (fear, t)
+            assert np.array_equal(b.obs[live].reshape(-1, H, W), g["obs"][idx]), (fear, t)
             total += len(live)
     return total

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     hdr = open(os.path.join(ROOT, "include", "gridworld_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(gw_[a-z_]+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"\b(gww?_[a-z_]+)\s*\(", hdr)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -50,7 +50,7 @@ def test_header_is_plain_c_and_ctypes_mirrors_match(tmp_path):
         import pytest
         pytest.skip("gcc not found")
     mirrors = {"gw_config": N.GwConfig, "gw_io": N.GwIO, "gw_stats": N.GwStats, "gw_actor_weights": N.GwActorWeights,
-               "gw_replay_view": N.GwReplayView}
+               "gw_replay_view": N.GwReplayView, "gww_config": N.GwwConfig, "gww_env_state": N.GwwEnvState}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "gridworld_b200.h")}"',
              'int main(void) {']
     for cname, cls in mirrors.items():
