@@ -19,6 +19,7 @@
 // the bytes of this phase that bound the kernel once FeAR is off).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -72,6 +73,7 @@ struct Params {
   long long E;
   gw_io io;
   const uint8_t* reset_mask;
+  int literal_fear;                        // GWW_FEAR_LITERAL=1: nine world updates per count instead of count_valid_fast (tests)
 };
 
 __device__ __constant__ int8_t MOVE_DR[9] = {0, -1, 1, 0, 0, -1, 1, 0, 0};     // custom_agent.py:140-150
@@ -168,7 +170,7 @@ __device__ void world_update(const Tab* __restrict__ T, const unsigned long long
 //  +-256 or +-1 or 0 and equal differences mean equal (drow, dcol); a row borrow cannot occur for unit moves inside the grid.)
 
 // CountValidMovesOfAffected_tuple, Responsibility.py:20-54; agents outside the list Stay (:43), the affected agent's action is
-// swapped only if it is in the list (SwapActionIDs4Agents, grid_world.py:709-726).
+// swapped only if it is in the list (SwapActionIDs4Agents, grid_world.py:709-726).  The literal form: nine world updates.
 __device__ int count_valid(const Tab* T, const unsigned long long* rows, int n, const uint16_t* loc, const uint8_t* list_act,
                            uint32_t in_list, int affected) {
   int count = 0;
@@ -181,6 +183,97 @@ __device__ int count_valid(const Tab* T, const unsigned long long* rows, int n, 
     world_update(T, rows, n, loc, act, nullptr, 0, 0, o);
     if (!((o.crash >> affected) & 1u) && !((o.restr >> affected) & 1u)) ++count;      // :46
   }
+  return count;
+}
+
+// One move of grid_world.py:481-518 from `old` with action a: the new cell, or `old` with `restricted` set.
+__device__ __forceinline__ uint16_t one_move(const Tab* T, const unsigned long long* rows, uint16_t old, int a, bool& restricted) {
+  const int r = (old >> 8) + MOVE_DR[a], c = (old & 255) + MOVE_DC[a];
+  if (r < 0 || r >= T->H || c < 0 || c >= T->W || !((rows[r] >> c) & 1ull) ||
+      ((__ldg(&T->blocked_dir[(old >> 8) * T->W + (old & 255)]) >> ((a - 1) & 3)) & 1)) { restricted = true; return old; }
+  return (uint16_t)((r << 8) | c);
+}
+
+// The same count from ONE world update.  The nine re-simulations differ only in the affected agent j's action, and j
+// influences the others only by colliding with them -- which makes the action invalid whatever follows.  So until j is hit
+// the others evolve exactly as in the world WITHOUT j: one update of that world gives their crashed sets before (Cb) and
+// after (Ca) the fix-point of every sub-step, and j's action a is valid iff none of its moves is restricted and at no
+// sub-step s the pair test hits j against some k on k's nominal path (k not crashed before s: what pass 1 sees) or against
+// k standing on its start cell (k crashed by the end of s: what the pass after k's crash sees).  Same pair rules, same
+// order of the two roles (lower index first); checked against the literal form and against the C oracle in tests/.
+__device__ int count_valid_fast(const Tab* T, const unsigned long long* rows, int n, const uint16_t* loc, const uint8_t* list_act,
+                                uint32_t in_list, int j) {
+  uint8_t act[NA];
+  uint16_t nom[NA][MAXSTEPS + 1];
+  for (int i = 0; i < n; ++i) act[i] = ((in_list >> i) & 1u) ? list_act[i] : (uint8_t)0;
+  // the world without j: nominal paths (no collisions) and the crashed sets per sub-step
+  uint32_t Cb[MAXSTEPS], Ca[MAXSTEPS], restr_others = 0;
+  for (int k = 0; k < n; ++k) {
+    nom[k][0] = loc[k];
+    for (int s = 0; s < MAXSTEPS; ++s) {
+      bool r = false;
+      nom[k][s + 1] = (k != j && act[k] != 0 && s < MOVE_LEN[act[k]]) ? one_move(T, rows, nom[k][s], act[k], r) : nom[k][s];
+      if (r) restr_others |= 1u << k;
+    }
+  }
+  uint32_t crash = 0;
+  for (int s = 0; s < MAXSTEPS; ++s) {
+    Cb[s] = crash;
+    int count = n - 1, loops = 0;
+    while (count > 0 && loops < 2 * (n - 1)) {        // the fix-point among the others (a crashed agent stands on its start cell)
+      ++loops;
+      count = 0;
+      uint32_t hit_mask = 0;
+      for (int ii = 0; ii < n - 1; ++ii) {
+        if (ii == j) continue;
+        const int qi = (s + 1) * MOVE_LEN[act[ii]], fi = qi >> 2, ci = (qi + 3) >> 2;
+        const bool xi = (crash >> ii) & 1u;
+        const int ai = xi ? loc[ii] : nom[ii][fi], bi = xi ? loc[ii] : nom[ii][ci];
+        for (int jj = ii + 1; jj < n; ++jj) {
+          if (jj == j) continue;
+          const int qj = (s + 1) * MOVE_LEN[act[jj]], fj = qj >> 2, cj = (qj + 3) >> 2;
+          const bool xj = (crash >> jj) & 1u;
+          const int aj = xj ? loc[jj] : nom[jj][fj], bj = xj ? loc[jj] : nom[jj][cj];
+          if (gw::pair_hit(ai, bi, loc[ii], qi, fi, ci, aj, bj, loc[jj], qj, fj, cj)) { ++count; hit_mask |= (1u << ii) | (1u << jj); }
+        }
+      }
+      crash |= hit_mask;
+    }
+    Ca[s] = crash;
+  }
+  // (a crashed agent's path: entries from floor(q/4) on are its start cell, so both interpolation points A and B are --
+  //  a crash at sub-step s' reverts from f(s') and f is monotone in s; before its crash the path is the nominal one)
+  const bool swap = (in_list >> j) & 1u;
+  int count = 0, last = 0;
+  for (int a = 0; a < GW_N_ACTIONS; ++a) {
+    if (!swap && a > 0) { count += last; continue; }          // j not in the list: nine identical simulations (its list action: Stay)
+    const int aj_act = swap ? a : (int)act[j];
+    const int len = MOVE_LEN[aj_act];
+    uint16_t pj[MAXSTEPS + 1];
+    pj[0] = loc[j];
+    bool bad = false;
+    for (int s = 0; s < MAXSTEPS && !bad; ++s) {
+      pj[s + 1] = (aj_act != 0 && s < len) ? one_move(T, rows, pj[s], aj_act, bad) : pj[s];
+      if (bad) break;                                         // restricted: invalid whatever the others do (:46)
+      const int qj = (s + 1) * len, fj = qj >> 2, cj = (qj + 3) >> 2;
+      const int A = pj[fj], B = pj[cj], P = loc[j];
+      for (int k = 0; k < n && !bad; ++k) {
+        if (k == j) continue;
+        const int qk = (s + 1) * MOVE_LEN[act[k]], fk = qk >> 2, ck = (qk + 3) >> 2;
+        if (!((Cb[s] >> k) & 1u)) {
+          const int ak = nom[k][fk], bk = nom[k][ck];
+          bad = j < k ? gw::pair_hit(A, B, P, qj, fj, cj, ak, bk, loc[k], qk, fk, ck) : gw::pair_hit(ak, bk, loc[k], qk, fk, ck, A, B, P, qj, fj, cj);
+        }
+        if (!bad && ((Ca[s] >> k) & 1u)) {
+          const int pk = loc[k];
+          bad = j < k ? gw::pair_hit(A, B, P, qj, fj, cj, pk, pk, pk, qk, fk, ck) : gw::pair_hit(pk, pk, pk, qk, fk, ck, A, B, P, qj, fj, cj);
+        }
+      }
+    }
+    last = bad ? 0 : 1;
+    count += last;
+  }
+  (void)restr_others;
   return count;
 }
 
@@ -412,7 +505,8 @@ __global__ void __launch_bounds__(THREADS) gww_step_kernel(Params p) {
         uint8_t la[NA];
         for (int i = 0; i < n; ++i) la[i] = s.act[q][i];
         if (v == 0) la[x] = s.mdr[q][x];
-        s.cnt[q][x][j][v] = (uint8_t)count_valid(T, s.rows, n, s.cell[q], la, in_list, j);
+        s.cnt[q][x][j][v] = (uint8_t)(p.literal_fear ? count_valid(T, s.rows, n, s.cell[q], la, in_list, j)
+                                                      : count_valid_fast(T, s.rows, n, s.cell[q], la, in_list, j));
       }
       __syncthreads();
     }
@@ -696,6 +790,8 @@ static int wide_validate(const gww_config* c, std::string& why) {
 static gww::Params wide_params(gww_handle* h, const gw_io* io) {
   gww::Params p;
   p.T = h->d_tab; p.state = h->d_state; p.stats = h->d_stats; p.E = h->cfg.num_envs; p.io = *io; p.reset_mask = nullptr;
+  const char* lit = std::getenv("GWW_FEAR_LITERAL");
+  p.literal_fear = (lit && lit[0] == '1') ? 1 : 0;
   return p;
 }
 
