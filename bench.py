@@ -421,7 +421,7 @@ def masked_uniform_runs(a, E, dev, seeds=(0, 42, 66), steps=384):
 def general_layout_extra(a, dev, cpu_seconds=4.0):
     """the GENERAL state layout (gww_*, csrc/gw_wide.cu) on a scenario the packed layout cannot hold -- the 20 x 28
     map with 7 agents, walls and one-ways that tests/golden/make_wide_golden.py ran the reference on.  Device-timed step
-    launches (CUDA events, 32 steps after 8), FeAR on / off, at the headline batch and at a batch that fills the GPU; next to
+    launches (CUDA events around a 32-step CUDA graph), FeAR on / off, at the headline batch and at a batch that fills the GPU; next to
     it the C oracle built on gww_config, all host threads, on a bounded sample.  An extra line, never the headline."""
     import numpy as np
     import torch
@@ -439,18 +439,23 @@ def general_layout_extra(a, dev, cpu_seconds=4.0):
         for t in range(8):
             env.step(acts[t % 8])
         env.sync()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         K = 32
+        g = torch.cuda.CUDAGraph()                          # the launches replayed from a CUDA graph: kernel time, not ctypes time
+        with torch.cuda.graph(g):
+            for t in range(K):
+                env.step(acts[t % 8])
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g.replay()
+        torch.cuda.synchronize()
         ev0.record()
-        for t in range(K):
-            env.step(acts[t % 8])
+        g.replay()
         ev1.record()
         torch.cuda.synchronize()
         per = ev0.elapsed_time(ev1) * 1e-3 / K
         st = env.stats()
         out["points"].append({"envs": E, "fear": bool(fear), "ms_per_step": per * 1e3, "agent_steps_per_s": E * 2 / per,
                               "achieved_gbs": algo * E / per / 1e9, "frac_of_hbm_peak": algo * E / per / 1e9 / peak,
-                              "fear_tasks_per_env_step": st["fear_tasks"] / max(1, st["env_steps"])})
+                              "fear_tasks_per_env_step": st["fear_tasks"] / float(E * (8 + 3 * K))})
         env.close()
         del env, acts
         torch.cuda.empty_cache()

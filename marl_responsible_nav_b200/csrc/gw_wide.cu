@@ -73,6 +73,7 @@ struct Params {
   long long E;
   gw_io io;
   const uint8_t* reset_mask;
+  int stage_bytes;                         // bytes of one env's observation block [L, H*W] when it can leave as ONE bulk copy (a multiple of 16), else 0
   int literal_fear;                        // GWW_FEAR_LITERAL=1: nine world updates per count instead of count_valid_fast (tests)
 };
 
@@ -104,6 +105,13 @@ __device__ void world_update(const Tab* __restrict__ T, const unsigned long long
   out.caught[0][0] = out.caught[0][1] = out.caught[1][0] = out.caught[1][1] = 0;
   out.unresolved = false;
   for (int i = 0; i < n; ++i) path[i][0] = loc0[i];                                    // :437-439
+  // pairs further apart than Manhattan distance 4 cannot share a cell within one step: no rule of the pair test can match
+  uint16_t near[NA];
+  for (int i = 0; i < n; ++i) {
+    uint32_t m = 0;
+    for (int k = i + 1; k < n; ++k) m |= (manhattan(loc0[i], loc0[k]) <= 4 ? 1u : 0u) << k;
+    near[i] = (uint16_t)m;
+  }
   for (int step = 0; step < MAXSTEPS; ++step) {                                       // :458
     for (int i = 0; i < n; ++i) cur[i] = loc0[i];                                     // :460
     for (int i = 0; i < n; ++i) {                                                     // :462-518
@@ -126,10 +134,12 @@ __device__ void world_update(const Tab* __restrict__ T, const unsigned long long
       count = 0;
       uint32_t hit_mask = 0;
       for (int ii = 0; ii < n - 1; ++ii) {                                            // :255
+        if (!near[ii]) continue;
         const int qi = (step + 1) * MOVE_LEN[act[ii]];
         const int fi = qi >> 2, ci = (qi + 3) >> 2;
         const uint16_t ai = path[ii][fi], bi = path[ii][ci], pi = loc0[ii];
-        for (int jj = ii + 1; jj < n; ++jj) {
+        for (uint32_t rest = near[ii]; rest; rest &= rest - 1u) {
+          const int jj = __ffs(rest) - 1;
           const int qj = (step + 1) * MOVE_LEN[act[jj]];
           const int fj = qj >> 2, cj = (qj + 3) >> 2;
           const uint16_t aj = path[jj][fj], bj = path[jj][cj], pj = loc0[jj];
@@ -194,6 +204,20 @@ __device__ __forceinline__ uint16_t one_move(const Tab* T, const unsigned long l
   return (uint16_t)((r << 8) | c);
 }
 
+// Agents further apart than Manhattan distance 4 cannot meet within one step (every cell of an agent's path is within 2 of
+// its start cell, and the pair rules compare cells only), so what happens to agent j depends only on the agents linked to
+// it by a chain of such near pairs: its component.
+__device__ __forceinline__ uint32_t near_component(int n, const uint16_t* loc, int j) {
+  uint32_t comp = 1u << j, frontier = comp;
+  while (frontier) {
+    const int a = __ffs(frontier) - 1;
+    frontier &= frontier - 1u;
+    for (int k = 0; k < n; ++k)
+      if (!((comp >> k) & 1u) && manhattan(loc[a], loc[k]) <= 4) { comp |= 1u << k; frontier |= 1u << k; }
+  }
+  return comp;
+}
+
 // The same count from ONE world update.  The nine re-simulations differ only in the affected agent j's action, and j
 // influences the others only by colliding with them -- which makes the action invalid whatever follows.  So until j is hit
 // the others evolve exactly as in the world WITHOUT j: one update of that world gives their crashed sets before (Cb) and
@@ -201,36 +225,39 @@ __device__ __forceinline__ uint16_t one_move(const Tab* T, const unsigned long l
 // sub-step s the pair test hits j against some k on k's nominal path (k not crashed before s: what pass 1 sees) or against
 // k standing on its start cell (k crashed by the end of s: what the pass after k's crash sees).  Same pair rules, same
 // order of the two roles (lower index first); checked against the literal form and against the C oracle in tests/.
+// `comp`: j's component (near_component); the agents outside it are left out altogether.
 __device__ int count_valid_fast(const Tab* T, const unsigned long long* rows, int n, const uint16_t* loc, const uint8_t* list_act,
-                                uint32_t in_list, int j) {
+                                uint32_t in_list, int j, uint32_t comp) {
   uint8_t act[NA];
   uint16_t nom[NA][MAXSTEPS + 1];
   for (int i = 0; i < n; ++i) act[i] = ((in_list >> i) & 1u) ? list_act[i] : (uint8_t)0;
   // the world without j: nominal paths (no collisions) and the crashed sets per sub-step
-  uint32_t Cb[MAXSTEPS], Ca[MAXSTEPS], restr_others = 0;
+  uint32_t Cb[MAXSTEPS], Ca[MAXSTEPS];
+  const uint32_t others = comp & ~(1u << j);
   for (int k = 0; k < n; ++k) {
+    if (!((others >> k) & 1u)) continue;
     nom[k][0] = loc[k];
     for (int s = 0; s < MAXSTEPS; ++s) {
       bool r = false;
-      nom[k][s + 1] = (k != j && act[k] != 0 && s < MOVE_LEN[act[k]]) ? one_move(T, rows, nom[k][s], act[k], r) : nom[k][s];
-      if (r) restr_others |= 1u << k;
+      nom[k][s + 1] = (act[k] != 0 && s < MOVE_LEN[act[k]]) ? one_move(T, rows, nom[k][s], act[k], r) : nom[k][s];
     }
   }
   uint32_t crash = 0;
+  const int n_others = __popc(others);
   for (int s = 0; s < MAXSTEPS; ++s) {
     Cb[s] = crash;
-    int count = n - 1, loops = 0;
-    while (count > 0 && loops < 2 * (n - 1)) {        // the fix-point among the others (a crashed agent stands on its start cell)
-      ++loops;
+    int count = n_others, loops = 0;
+    while (count > 0 && loops < 2 * n) {              // the fix-point among the others (a crashed agent stands on its start cell;
+      ++loops;                                        //  every pass with a hit crashes somebody new, so the cap never binds)
       count = 0;
       uint32_t hit_mask = 0;
       for (int ii = 0; ii < n - 1; ++ii) {
-        if (ii == j) continue;
+        if (!((others >> ii) & 1u)) continue;
         const int qi = (s + 1) * MOVE_LEN[act[ii]], fi = qi >> 2, ci = (qi + 3) >> 2;
         const bool xi = (crash >> ii) & 1u;
         const int ai = xi ? loc[ii] : nom[ii][fi], bi = xi ? loc[ii] : nom[ii][ci];
         for (int jj = ii + 1; jj < n; ++jj) {
-          if (jj == j) continue;
+          if (!((others >> jj) & 1u)) continue;
           const int qj = (s + 1) * MOVE_LEN[act[jj]], fj = qj >> 2, cj = (qj + 3) >> 2;
           const bool xj = (crash >> jj) & 1u;
           const int aj = xj ? loc[jj] : nom[jj][fj], bj = xj ? loc[jj] : nom[jj][cj];
@@ -258,7 +285,7 @@ __device__ int count_valid_fast(const Tab* T, const unsigned long long* rows, in
       const int qj = (s + 1) * len, fj = qj >> 2, cj = (qj + 3) >> 2;
       const int A = pj[fj], B = pj[cj], P = loc[j];
       for (int k = 0; k < n && !bad; ++k) {
-        if (k == j) continue;
+        if (!((others >> k) & 1u)) continue;
         const int qk = (s + 1) * MOVE_LEN[act[k]], fk = qk >> 2, ck = (qk + 3) >> 2;
         if (!((Cb[s] >> k) & 1u)) {
           const int ak = nom[k][fk], bk = nom[k][ck];
@@ -273,7 +300,6 @@ __device__ int count_valid_fast(const Tab* T, const unsigned long long* rows, in
     last = bad ? 0 : 1;
     count += last;
   }
-  (void)restr_others;
   return count;
 }
 
@@ -392,6 +418,72 @@ __device__ void render_rows(const Tab* T, const unsigned long long* rows, void* 
   }
 }
 
+// ---- observation blocks through shared memory: a warp keeps a copy of the constant part of one env's block (every learner's
+// row: -1 on inactive cells, 0 on active ones) in a staging area, patches the <= n + 2 special cells per row, hands the whole
+// block to the TMA engine (cp.async.bulk.global.shared::cta: whole lines, one instruction) and restores the patched cells
+// once the engine has read it.  Agents and apples stand on active cells, so restoring means writing 0.
+__device__ __forceinline__ void stage_put(uint8_t* stage, bool bf16, int idx, float v) {
+  if (bf16) reinterpret_cast<__nv_bfloat16*>(stage)[idx] = __float2bfloat16(v);
+  else reinterpret_cast<float*>(stage)[idx] = v;
+}
+__device__ void stage_init(const Tab* T, const unsigned long long* rows, uint8_t* stage, int lane) {
+  const int len = T->H * T->W;
+  for (int idx = lane; idx < len; idx += 32) {
+    const int r = idx / T->W, c = idx - r * T->W;
+    const float v = ((rows[r] >> c) & 1ull) ? 0.0f : -1.0f;
+    for (int k = 0; k < T->nl; ++k) stage_put(stage, T->obs_bf16, k * len + idx, v);
+  }
+}
+__device__ __forceinline__ void stage_store(void* gdst, const uint8_t* stage, int bytes, int lane) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+  __syncwarp();
+}
+// What a warp needs of the tables for the staged rows, loaded once per kernel.
+struct StageCtx {
+  int W, n, nl, len, bytes;
+  bool bf16, multi;
+  int apple[2];                            // packed apple cell shown in learner k's row (the single env shows apple 0), -1 = none configured
+};
+__device__ __forceinline__ StageCtx stage_ctx(const Tab* T, int bytes) {
+  StageCtx c;
+  c.W = T->W; c.n = T->n; c.nl = T->nl; c.len = T->H * T->W; c.bytes = bytes;
+  c.bf16 = T->obs_bf16 != 0; c.multi = T->kind == GW_ENV_MULTI;
+  for (int k = 0; k < 2; ++k) {
+    const int ak = c.multi ? k : 0;
+    c.apple[k] = T->apple_r[ak] >= 0 ? (T->apple_r[ak] << 8 | T->apple_c[ak]) : -1;
+  }
+  return c;
+}
+// One env's block -> obs (or final_obs) through the warp's staging area.  Lane 16 k + i owns agent i in learner k's row
+// (values of ma_customenv.py:303-322 / customenv.py:161-163, see render_rows); lane 16 k also owns k's apple when nobody stands
+// on it.  The same lanes restore the constant part (0: agents and apples stand on active cells) once the engine has read the block.
+__device__ __forceinline__ void render_staged(const StageCtx& c, uint8_t* stage, void* base, long long e, const uint16_t* cell,
+                                              uint32_t apple_bits, bool fresh, int lane) {
+  const int k = lane >> 4, i = lane & 15;
+  const bool mine = k < c.nl && i < c.n;
+  const int pc = mine ? (int)cell[i] : -2;
+  const int apple_cell = (k < c.nl && ((apple_bits >> (c.multi ? k : 0)) & 1u)) ? c.apple[k] : -1;
+  const bool on_apple = mine && pc == apple_cell;
+  const uint32_t covered = __ballot_sync(0xFFFFFFFFu, on_apple);
+  float v = fresh ? 0.5f : (float)(i + 1);
+  if (on_apple) v += 9.0f;
+  else if (c.multi && !fresh) v = (i == k) ? 1.0f : (i < 4 ? 5.0f : v);
+  const int idx = mine ? k * c.len + (pc >> 8) * c.W + (pc & 255) : -1;
+  const int aidx = (i == 0 && apple_cell >= 0 && !((covered >> (16 * k)) & 0xFFFFu)) ? k * c.len + (apple_cell >> 8) * c.W + (apple_cell & 255) : -1;
+  if (idx >= 0) stage_put(stage, c.bf16, idx, v);
+  if (aidx >= 0) stage_put(stage, c.bf16, aidx, 9.0f);
+  stage_store(reinterpret_cast<uint8_t*>(base) + e * (long long)c.bytes, stage, c.bytes, lane);
+  if (idx >= 0) stage_put(stage, c.bf16, idx, 0.0f);
+  if (aidx >= 0) stage_put(stage, c.bf16, aidx, 0.0f);
+  __syncwarp();
+}
+
 template <int TILE>
 struct Smem {
   unsigned long long rows[GWW_MAX_DIM];
@@ -401,14 +493,20 @@ struct Smem {
   uint8_t mdr[TILE][NA];
   uint16_t close[TILE][2];                 // close list of learner x (bit i = agent i in the list)
   uint8_t cnt[TILE][2][NA][2];             // valid-move counts [actor][affected][0 = MdR variant, 1 = action variant]
+  uint16_t task[TILE * 2 * (NA - 1)];      // FeAR work queue: (env in tile << 5) | (actor << 4) | affected -- only the pairs that need simulating
+  int n_tasks;
   uint8_t render[TILE];                    // bit 0 obs fresh, bit 1 write final_obs, bits 2-3 apples shown in obs, 4-5 in final_obs, 7 live
   unsigned long long stat[ST_N];
 };
 
 template <int TILE>
+__host__ __device__ constexpr size_t smem_fixed() { return (sizeof(Smem<TILE>) + 127) / 128 * 128; }
+
+template <int TILE>
 __device__ __forceinline__ void load_rows(Smem<TILE>& s, const Tab* T) {
   for (int i = threadIdx.x; i < GWW_MAX_DIM; i += blockDim.x) s.rows[i] = T->map_rows[i];
   if (threadIdx.x < ST_N) s.stat[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s.n_tasks = 0;
 }
 
 template <int TILE>
@@ -419,6 +517,10 @@ __global__ void __launch_bounds__(THREADS) gww_reset_kernel(Params p) {
   load_rows(s, T);
   __syncthreads();
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  uint8_t* const stage = p.stage_bytes ? smem_raw + smem_fixed<TILE>() + (size_t)warp * p.stage_bytes : nullptr;
+  if (stage) stage_init(T, s.rows, stage, lane);
+  const StageCtx sc = stage_ctx(T, p.stage_bytes);
+  __syncwarp();
   for (long long base = (long long)blockIdx.x * TILE; base < p.E; base += (long long)gridDim.x * TILE) {
     const long long e = base + t;
     if (t < TILE) s.render[t] = 0;
@@ -436,8 +538,11 @@ __global__ void __launch_bounds__(THREADS) gww_reset_kernel(Params p) {
     }
     __syncthreads();
     if (p.io.obs)
-      for (int q = warp; q < TILE; q += THREADS / 32)
-        if (s.render[q] & 0x80u) render_rows(T, s.rows, p.io.obs, base + q, s.cell[q], (s.render[q] >> 2) & 3u, true, lane);
+      for (int q = warp; q < TILE; q += THREADS / 32) {
+        if (!(s.render[q] & 0x80u)) continue;
+        if (stage) render_staged(sc, stage, p.io.obs, base + q, s.cell[q], (s.render[q] >> 2) & 3u, true, lane);
+        else render_rows(T, s.rows, p.io.obs, base + q, s.cell[q], (s.render[q] >> 2) & 3u, true, lane);
+      }
     __syncthreads();
   }
 }
@@ -451,6 +556,10 @@ __global__ void __launch_bounds__(THREADS) gww_step_kernel(Params p) {
   __syncthreads();
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int n = T->n, nl = T->nl;
+  uint8_t* const stage = p.stage_bytes ? smem_raw + smem_fixed<TILE>() + (size_t)warp * p.stage_bytes : nullptr;
+  if (stage) stage_init(T, s.rows, stage, lane);
+  const StageCtx sc = stage_ctx(T, p.stage_bytes);
+  __syncwarp();
   for (long long base = (long long)blockIdx.x * TILE; base < p.E; base += (long long)gridDim.x * TILE) {
     const long long e = base + t;
     const bool live = t < TILE && e < p.E;
@@ -482,39 +591,45 @@ __global__ void __launch_bounds__(THREADS) gww_step_kernel(Params p) {
         a = a < 0 ? 0 : (a > 8 ? 8 : a);
         s.act[t][i] = (uint8_t)a;
       }
-      if (FEAR)
+      if (FEAR) {
+        for (int i = 0; i < 2 * NA * 2; i += 4) *reinterpret_cast<uint32_t*>(&s.cnt[t][0][0][0] + i) = 0u;
         for (int x = 0; x < nl; ++x) {
           uint32_t m = 0;
           for (int k = 0; k < n; ++k)
             if (k == x || manhattan(st.cell[x], st.cell[k]) <= T->fear_radius) m |= 1u << k;
           s.close[t][x] = (uint16_t)m;
+          // which (actor, affected) pairs need simulating: none when the action IS the MdR (both variants alike: Resp = 0
+          // exactly), none in the single env without a close agent (customenv.py:117-118), and only the agents linked to the
+          // actor by a chain of near pairs (the others' counts cannot depend on the actor's action: Resp = 0 exactly)
+          if (s.act[t][x] == s.mdr[t][x]) continue;
+          if (T->kind == GW_ENV_SINGLE && __popc(m) <= 1) continue;
+          const uint32_t comp = p.literal_fear ? 0xFFFFu : near_component(n, st.cell, x);
+          for (int j = 0; j < n; ++j)
+            if (j != x && ((comp >> j) & 1u)) s.task[atomicAdd(&s.n_tasks, 1)] = (uint16_t)((t << 5) | (x << 4) | j);
         }
+      }
     }
     __syncthreads();
     // ---- P2: FeAR_4_one_actor's counterfactual counts (Responsibility.py:163-198), one work item = nine world updates
     if (FEAR) {
-      const int per_env = nl * n * 2;
-      const long long tile_envs = (p.E - base) < TILE ? (p.E - base) : TILE;
-      for (int it = t; it < per_env * TILE; it += THREADS) {
-        const int q = it % TILE, rest = it / TILE;
-        const int v = rest & 1, j = (rest >> 1) % n, x = (rest >> 1) / n;
-        if (q >= tile_envs || j == x) continue;
-        if (s.act[q][x] == s.mdr[q][x]) continue;                                     // both variants alike: Resp = 0 exactly
+      const int n_items = 2 * s.n_tasks;
+      for (int it = t; it < n_items; it += THREADS) {
+        const int task = s.task[it >> 1], v = it & 1;
+        const int q = task >> 5, x = (task >> 4) & 1, j = task & 15;
         const uint32_t in_list = s.close[q][x];
-        if (T->kind == GW_ENV_SINGLE && __popc(in_list) <= 1) continue;              // customenv.py:117-118
         uint8_t la[NA];
         for (int i = 0; i < n; ++i) la[i] = s.act[q][i];
         if (v == 0) la[x] = s.mdr[q][x];
         s.cnt[q][x][j][v] = (uint8_t)(p.literal_fear ? count_valid(T, s.rows, n, s.cell[q], la, in_list, j)
-                                                      : count_valid_fast(T, s.rows, n, s.cell[q], la, in_list, j));
+                                                      : count_valid_fast(T, s.rows, n, s.cell[q], la, in_list, j, near_component(n, s.cell[q], j)));
       }
       __syncthreads();
+      if (t == 0) { s.stat[ST_TASKS] += (unsigned long long)s.n_tasks; s.n_tasks = 0; }
     }
     // ---- P3: responsibility sums, the real update, rewards / flags (ma_customenv.py:254-302, customenv.py:124-158)
     uint8_t render = 0;
     if (live) {
       double fear[2] = {0.0, 0.0};
-      unsigned long long tasks = 0;
       if (FEAR)
         for (int x = 0; x < nl; ++x) {
           if (s.act[t][x] == s.mdr[t][x]) continue;
@@ -522,7 +637,6 @@ __global__ void __launch_bounds__(THREADS) gww_step_kernel(Params p) {
           double row[NA];
           for (int j = 0; j < n; ++j) row[j] = j == x ? 0.0 : resp_of(T, s.cnt[t][x][j][0], s.cnt[t][x][j][1]);
           fear[x] = np_sum_matrix(n, x, row);
-          tasks += (unsigned long long)(n - 1);
         }
       uint16_t apples[2] = {(uint16_t)((T->apple_r[0] << 8) | (T->apple_c[0] & 255)), (uint16_t)((T->apple_r[1] << 8) | (T->apple_c[1] & 255))};
       UpdateOut u;
@@ -595,7 +709,6 @@ __global__ void __launch_bounds__(THREADS) gww_step_kernel(Params p) {
       if (crash_count) atomicAdd(&s.stat[ST_CRASH], (unsigned long long)crash_count);
       if (apples_rewarded) atomicAdd(&s.stat[ST_APPLES], (unsigned long long)apples_rewarded);
       if (u.unresolved) atomicAdd(&s.stat[ST_UNRESOLVED], 1ull);
-      if (tasks) atomicAdd(&s.stat[ST_TASKS], tasks);
       if (FEAR) {
         const int nz = (fear[0] != 0.0) + (fear[1] != 0.0);
         if (nz) {
@@ -623,8 +736,13 @@ __global__ void __launch_bounds__(THREADS) gww_step_kernel(Params p) {
     for (int q = warp; q < TILE; q += THREADS / 32) {
       const uint8_t r = s.render[q];
       if (!(r & 0x80u)) continue;
-      if ((r & 2u) && p.io.final_obs) render_rows(T, s.rows, p.io.final_obs, base + q, s.cell_final[q], (r >> 4) & 3u, false, lane);
-      if (p.io.obs) render_rows(T, s.rows, p.io.obs, base + q, s.cell[q], (r >> 2) & 3u, (r & 1u) != 0, lane);
+      if (stage) {
+        if ((r & 2u) && p.io.final_obs) render_staged(sc, stage, p.io.final_obs, base + q, s.cell_final[q], (r >> 4) & 3u, false, lane);
+        if (p.io.obs) render_staged(sc, stage, p.io.obs, base + q, s.cell[q], (r >> 2) & 3u, (r & 1u) != 0, lane);
+      } else {
+        if ((r & 2u) && p.io.final_obs) render_rows(T, s.rows, p.io.final_obs, base + q, s.cell_final[q], (r >> 4) & 3u, false, lane);
+        if (p.io.obs) render_rows(T, s.rows, p.io.obs, base + q, s.cell[q], (r >> 2) & 3u, (r & 1u) != 0, lane);
+      }
     }
     __syncthreads();
   }
@@ -790,6 +908,11 @@ static int wide_validate(const gww_config* c, std::string& why) {
 static gww::Params wide_params(gww_handle* h, const gw_io* io) {
   gww::Params p;
   p.T = h->d_tab; p.state = h->d_state; p.stats = h->d_stats; p.E = h->cfg.num_envs; p.io = *io; p.reset_mask = nullptr;
+  // the observation block of one env leaves as one bulk copy when its size and the destinations allow 16-byte granules
+  const size_t block = (size_t)h->cfg.n_learners * h->cfg.height * h->cfg.width * (h->cfg.obs_dtype == GW_OBS_BF16 ? 2 : 4);
+  const bool aligned = (reinterpret_cast<uintptr_t>(io->obs) % 16 == 0) && (reinterpret_cast<uintptr_t>(io->final_obs) % 16 == 0);
+  const char* scalar = std::getenv("GWW_SCALAR_ROWS");
+  p.stage_bytes = (block % 16 == 0 && aligned && !(scalar && scalar[0] == '1')) ? (int)block : 0;
   const char* lit = std::getenv("GWW_FEAR_LITERAL");
   p.literal_fear = (lit && lit[0] == '1') ? 1 : 0;
   return p;
@@ -883,6 +1006,13 @@ int gww_create(const gww_config* cfg, gww_handle** out) {
       (e = cudaMemset(h->d_stats, 0, sizeof(unsigned long long) * gww::STAT_SLOTS * gww::ST_N)) != cudaSuccess)
     return cleanup(GW_ECUDA, std::string("initialising device tables: ") + cudaGetErrorString(e));
   delete T;
+  const int max_dyn = (int)(gww::smem_fixed<128>() + (size_t)(gww::THREADS / 32) * GW_MAX_LEARNERS * GWW_MAX_CELLS * 4);   // 150 KB at 64 x 64 fp32
+  cudaFuncSetAttribute(gww::gww_step_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+  cudaFuncSetAttribute(gww::gww_step_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+  cudaFuncSetAttribute(gww::gww_step_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+  cudaFuncSetAttribute(gww::gww_step_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+  cudaFuncSetAttribute(gww::gww_reset_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+  cudaFuncSetAttribute(gww::gww_reset_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
   *out = h;
   return GW_OK;
 }
@@ -913,8 +1043,9 @@ int gww_reset(gww_handle* h, const uint8_t* reset_mask, const gw_io* io, void* s
   gww::Params p = wide_params(h, io);
   p.reset_mask = reset_mask;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (wide_tile(h) == 32) gww::gww_reset_kernel<32><<<wide_blocks(h), gww::THREADS, sizeof(gww::Smem<32>), s>>>(p);
-  else gww::gww_reset_kernel<128><<<wide_blocks(h), gww::THREADS, sizeof(gww::Smem<128>), s>>>(p);
+  const size_t stage = (size_t)(gww::THREADS / 32) * p.stage_bytes;
+  if (wide_tile(h) == 32) gww::gww_reset_kernel<32><<<wide_blocks(h), gww::THREADS, gww::smem_fixed<32>() + stage, s>>>(p);
+  else gww::gww_reset_kernel<128><<<wide_blocks(h), gww::THREADS, gww::smem_fixed<128>() + stage, s>>>(p);
   GWW_CUDA(h, cudaGetLastError());
   h->reset_done = true;
   h->launches += 1;
@@ -929,12 +1060,13 @@ int gww_step(gww_handle* h, const gw_io* io, void* stream) {
   gww::Params p = wide_params(h, io);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const unsigned blocks = wide_blocks(h);
+  const size_t stage = (size_t)(gww::THREADS / 32) * p.stage_bytes;
   if (wide_tile(h) == 32) {
-    if (h->cfg.fear) gww::gww_step_kernel<true, 32><<<blocks, gww::THREADS, sizeof(gww::Smem<32>), s>>>(p);
-    else gww::gww_step_kernel<false, 32><<<blocks, gww::THREADS, sizeof(gww::Smem<32>), s>>>(p);
+    if (h->cfg.fear) gww::gww_step_kernel<true, 32><<<blocks, gww::THREADS, gww::smem_fixed<32>() + stage, s>>>(p);
+    else gww::gww_step_kernel<false, 32><<<blocks, gww::THREADS, gww::smem_fixed<32>() + stage, s>>>(p);
   } else {
-    if (h->cfg.fear) gww::gww_step_kernel<true, 128><<<blocks, gww::THREADS, sizeof(gww::Smem<128>), s>>>(p);
-    else gww::gww_step_kernel<false, 128><<<blocks, gww::THREADS, sizeof(gww::Smem<128>), s>>>(p);
+    if (h->cfg.fear) gww::gww_step_kernel<true, 128><<<blocks, gww::THREADS, gww::smem_fixed<128>() + stage, s>>>(p);
+    else gww::gww_step_kernel<false, 128><<<blocks, gww::THREADS, gww::smem_fixed<128>() + stage, s>>>(p);
   }
   GWW_CUDA(h, cudaGetLastError());
   h->launches += 1;

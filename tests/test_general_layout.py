@@ -206,6 +206,19 @@ def test_general_gpu_maximum_size_64x64_16_agents():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("bf16", [False, True])
+def test_general_gpu_odd_sized_map_takes_the_cell_by_cell_row_writer(bf16):
+    """7 x 9 cells: an env's observation block (2 x 63 values) is not a whole number of 16-byte granules, so it cannot leave as
+    one bulk copy; the kernel writes such rows cell by cell."""
+    from marl_responsible_nav_b200.scenarios import Scenario
+    region = np.ones((7, 9), np.int8)
+    region[3, 2:7] = 0
+    sc = Scenario("odd", region, 5, np.zeros((7, 9), np.uint8), [([1, 2, 1], [1, 1, 1, 1])], np.full((7, 9), 4, np.uint8))
+    kw = dict(num_envs=333, fear=True, fear_weight=-1.0, seed=6, max_steps=30, apples=((6, 8), (0, 0)), obs_bf16=bf16)
+    _compare_rollout(RC.GpuBackend(sc, **kw), c_oracle.COracle(sc, threads=4, **kw), steps=40, seed=8)
+
+
+@pytest.mark.gpu
 def test_general_layout_equals_packed_layout_on_level3():
     """Two independent CUDA formulations of the same step -- the packed layout's pair-mask table / bit-parallel FeAR and the
     general layout's literal paths -- produce identical rollouts on Level 3 (device RNG; 4 096 envs, FeAR on)."""
