@@ -73,6 +73,7 @@ struct Params {
   long long E;
   gw_io io;
   const uint8_t* reset_mask;
+  const uint8_t* tmpl;                     // the constant part of one env's observation block [L, H*W] in the obs dtype
   int stage_bytes;                         // bytes of one env's observation block [L, H*W] when it can leave as ONE bulk copy (a multiple of 16), else 0
   int literal_fear;                        // GWW_FEAR_LITERAL=1: nine world updates per count instead of count_valid_fast (tests)
 };
@@ -426,13 +427,9 @@ __device__ __forceinline__ void stage_put(uint8_t* stage, bool bf16, int idx, fl
   if (bf16) reinterpret_cast<__nv_bfloat16*>(stage)[idx] = __float2bfloat16(v);
   else reinterpret_cast<float*>(stage)[idx] = v;
 }
-__device__ void stage_init(const Tab* T, const unsigned long long* rows, uint8_t* stage, int lane) {
-  const int len = T->H * T->W;
-  for (int idx = lane; idx < len; idx += 32) {
-    const int r = idx / T->W, c = idx - r * T->W;
-    const float v = ((rows[r] >> c) & 1ull) ? 0.0f : -1.0f;
-    for (int k = 0; k < T->nl; ++k) stage_put(stage, T->obs_bf16, k * len + idx, v);
-  }
+// the constant part of one env's block (every learner's row: -1 on inactive cells, 0 on active ones), built by gww_create
+__device__ __forceinline__ void stage_init(const uint8_t* __restrict__ tmpl, int bytes, uint8_t* stage, int lane) {
+  for (int i = lane; i < bytes / 16; i += 32) reinterpret_cast<uint4*>(stage)[i] = __ldg(reinterpret_cast<const uint4*>(tmpl) + i);
 }
 __device__ __forceinline__ void stage_store(void* gdst, const uint8_t* stage, int bytes, int lane) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -484,26 +481,27 @@ __device__ __forceinline__ void render_staged(const StageCtx& c, uint8_t* stage,
   __syncwarp();
 }
 
-template <int TILE>
+template <int TILE, bool FEAR = true>
 struct Smem {
+  static constexpr int FT = FEAR ? TILE : 1;   // the FeAR arrays shrink to nothing without FeAR (more CTAs per SM)
   unsigned long long rows[GWW_MAX_DIM];
   uint16_t cell[TILE][NA];                 // P1-P2: pre-step cells; P3 on: what `obs` shows (post-step, or the fresh spawn)
   uint16_t cell_final[TILE][NA];           // P4: the terminal observation's cells (envs that re-spawned)
   uint8_t act[TILE][NA];
-  uint8_t mdr[TILE][NA];
-  uint16_t close[TILE][2];                 // close list of learner x (bit i = agent i in the list)
-  uint8_t cnt[TILE][2][NA][2];             // valid-move counts [actor][affected][0 = MdR variant, 1 = action variant]
-  uint16_t task[TILE * 2 * (NA - 1)];      // FeAR work queue: (env in tile << 5) | (actor << 4) | affected -- only the pairs that need simulating
+  uint8_t mdr[FT][NA];
+  uint16_t close[FT][2];                   // close list of learner x (bit i = agent i in the list)
+  uint8_t cnt[FT][2][NA][2];               // valid-move counts [actor][affected][0 = MdR variant, 1 = action variant]
+  uint16_t task[FT * 2 * (NA - 1)];        // FeAR work queue: (env in tile << 5) | (actor << 4) | affected -- only the pairs that need simulating
   int n_tasks;
   uint8_t render[TILE];                    // bit 0 obs fresh, bit 1 write final_obs, bits 2-3 apples shown in obs, 4-5 in final_obs, 7 live
   unsigned long long stat[ST_N];
 };
 
-template <int TILE>
-__host__ __device__ constexpr size_t smem_fixed() { return (sizeof(Smem<TILE>) + 127) / 128 * 128; }
+template <int TILE, bool FEAR = true>
+__host__ __device__ constexpr size_t smem_fixed() { return (sizeof(Smem<TILE, FEAR>) + 127) / 128 * 128; }
 
-template <int TILE>
-__device__ __forceinline__ void load_rows(Smem<TILE>& s, const Tab* T) {
+template <int TILE, bool FEAR>
+__device__ __forceinline__ void load_rows(Smem<TILE, FEAR>& s, const Tab* T) {
   for (int i = threadIdx.x; i < GWW_MAX_DIM; i += blockDim.x) s.rows[i] = T->map_rows[i];
   if (threadIdx.x < ST_N) s.stat[threadIdx.x] = 0;
   if (threadIdx.x == 0) s.n_tasks = 0;
@@ -512,13 +510,13 @@ __device__ __forceinline__ void load_rows(Smem<TILE>& s, const Tab* T) {
 template <int TILE>
 __global__ void __launch_bounds__(THREADS) gww_reset_kernel(Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
+  Smem<TILE, false>& s = *reinterpret_cast<Smem<TILE, false>*>(smem_raw);
   const Tab* T = p.T;
   load_rows(s, T);
   __syncthreads();
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  uint8_t* const stage = p.stage_bytes ? smem_raw + smem_fixed<TILE>() + (size_t)warp * p.stage_bytes : nullptr;
-  if (stage) stage_init(T, s.rows, stage, lane);
+  uint8_t* const stage = p.stage_bytes ? smem_raw + smem_fixed<TILE, false>() + (size_t)warp * p.stage_bytes : nullptr;
+  if (stage) stage_init(p.tmpl, p.stage_bytes, stage, lane);
   const StageCtx sc = stage_ctx(T, p.stage_bytes);
   __syncwarp();
   for (long long base = (long long)blockIdx.x * TILE; base < p.E; base += (long long)gridDim.x * TILE) {
@@ -550,14 +548,14 @@ __global__ void __launch_bounds__(THREADS) gww_reset_kernel(Params p) {
 template <bool FEAR, int TILE>
 __global__ void __launch_bounds__(THREADS) gww_step_kernel(Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
+  Smem<TILE, FEAR>& s = *reinterpret_cast<Smem<TILE, FEAR>*>(smem_raw);
   const Tab* T = p.T;
   load_rows(s, T);
   __syncthreads();
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int n = T->n, nl = T->nl;
-  uint8_t* const stage = p.stage_bytes ? smem_raw + smem_fixed<TILE>() + (size_t)warp * p.stage_bytes : nullptr;
-  if (stage) stage_init(T, s.rows, stage, lane);
+  uint8_t* const stage = p.stage_bytes ? smem_raw + smem_fixed<TILE, FEAR>() + (size_t)warp * p.stage_bytes : nullptr;
+  if (stage) stage_init(p.tmpl, p.stage_bytes, stage, lane);
   const StageCtx sc = stage_ctx(T, p.stage_bytes);
   __syncwarp();
   for (long long base = (long long)blockIdx.x * TILE; base < p.E; base += (long long)gridDim.x * TILE) {
@@ -572,7 +570,7 @@ __global__ void __launch_bounds__(THREADS) gww_step_kernel(Params p) {
       for (int i = 0; i < n; ++i) {
         const int ci = (st.cell[i] >> 8) * T->W + (st.cell[i] & 255);
         s.cell[t][i] = st.cell[i];
-        s.mdr[t][i] = __ldg(&T->mdr_map[ci]);
+        if (FEAR) s.mdr[t][i] = __ldg(&T->mdr_map[ci]);
         int a;
         if (i < nl) a = p.io.learner_actions[e * nl + i];
         else if (p.io.npc_actions) a = p.io.npc_actions[e * n + i];
@@ -857,6 +855,7 @@ struct gww_handle {
   gww::Tab* d_tab = nullptr;
   gww::EnvState* d_state = nullptr;
   unsigned long long* d_stats = nullptr;
+  uint8_t* d_tmpl = nullptr;
   bool reset_done = false;
   int sm_count = 148;
   uint64_t launches = 0, env_steps = 0;
@@ -908,6 +907,7 @@ static int wide_validate(const gww_config* c, std::string& why) {
 static gww::Params wide_params(gww_handle* h, const gw_io* io) {
   gww::Params p;
   p.T = h->d_tab; p.state = h->d_state; p.stats = h->d_stats; p.E = h->cfg.num_envs; p.io = *io; p.reset_mask = nullptr;
+  p.tmpl = h->d_tmpl;
   // the observation block of one env leaves as one bulk copy when its size and the destinations allow 16-byte granules
   const size_t block = (size_t)h->cfg.n_learners * h->cfg.height * h->cfg.width * (h->cfg.obs_dtype == GW_OBS_BF16 ? 2 : 4);
   const bool aligned = (reinterpret_cast<uintptr_t>(io->obs) % 16 == 0) && (reinterpret_cast<uintptr_t>(io->final_obs) % 16 == 0);
@@ -1005,12 +1005,28 @@ int gww_create(const gww_config* cfg, gww_handle** out) {
       (e = cudaMemset(h->d_state, 0, sizeof(gww::EnvState) * (size_t)cfg->num_envs)) != cudaSuccess ||
       (e = cudaMemset(h->d_stats, 0, sizeof(unsigned long long) * gww::STAT_SLOTS * gww::ST_N)) != cudaSuccess)
     return cleanup(GW_ECUDA, std::string("initialising device tables: ") + cudaGetErrorString(e));
+  {
+    const int len = cfg->height * cfg->width, elt = cfg->obs_dtype == GW_OBS_BF16 ? 2 : 4;
+    std::string tm((size_t)cfg->n_learners * len * elt + 16, '\0');
+    for (int k = 0; k < cfg->n_learners; ++k)
+      for (int i = 0; i < len; ++i) {
+        const bool on = (T->map_rows[i / cfg->width] >> (i % cfg->width)) & 1ull;
+        if (elt == 4) { const float v = on ? 0.0f : -1.0f; std::memcpy(&tm[((size_t)k * len + i) * 4], &v, 4); }
+        else { const uint16_t v = on ? 0x0000u : 0xBF80u; std::memcpy(&tm[((size_t)k * len + i) * 2], &v, 2); }   // bf16 -1.0
+      }
+    if ((e = cudaMalloc(&h->d_tmpl, tm.size())) != cudaSuccess || (e = cudaMemcpy(h->d_tmpl, tm.data(), tm.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return cleanup(GW_ECUDA, std::string("observation template: ") + cudaGetErrorString(e));
+  }
   delete T;
   const int max_dyn = (int)(gww::smem_fixed<128>() + (size_t)(gww::THREADS / 32) * GW_MAX_LEARNERS * GWW_MAX_CELLS * 4);   // 150 KB at 64 x 64 fp32
   cudaFuncSetAttribute(gww::gww_step_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
   cudaFuncSetAttribute(gww::gww_step_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
   cudaFuncSetAttribute(gww::gww_step_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
   cudaFuncSetAttribute(gww::gww_step_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+  // thread-per-env phases keep their paths in local memory: leave half of the SM's array to L1 (a hint; the driver raises the
+  // shared-memory share when a block needs more)
+  cudaFuncSetAttribute(gww::gww_step_kernel<false, 32>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+  cudaFuncSetAttribute(gww::gww_step_kernel<false, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
   cudaFuncSetAttribute(gww::gww_reset_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
   cudaFuncSetAttribute(gww::gww_reset_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
   *out = h;
@@ -1023,6 +1039,7 @@ int gww_destroy(gww_handle* h) {
   if (h->d_tab) cudaFree(h->d_tab);
   if (h->d_state) cudaFree(h->d_state);
   if (h->d_stats) cudaFree(h->d_stats);
+  if (h->d_tmpl) cudaFree(h->d_tmpl);
   delete h;
   return GW_OK;
 }
@@ -1044,8 +1061,8 @@ int gww_reset(gww_handle* h, const uint8_t* reset_mask, const gw_io* io, void* s
   p.reset_mask = reset_mask;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t stage = (size_t)(gww::THREADS / 32) * p.stage_bytes;
-  if (wide_tile(h) == 32) gww::gww_reset_kernel<32><<<wide_blocks(h), gww::THREADS, gww::smem_fixed<32>() + stage, s>>>(p);
-  else gww::gww_reset_kernel<128><<<wide_blocks(h), gww::THREADS, gww::smem_fixed<128>() + stage, s>>>(p);
+  if (wide_tile(h) == 32) gww::gww_reset_kernel<32><<<wide_blocks(h), gww::THREADS, gww::smem_fixed<32, false>() + stage, s>>>(p);
+  else gww::gww_reset_kernel<128><<<wide_blocks(h), gww::THREADS, gww::smem_fixed<128, false>() + stage, s>>>(p);
   GWW_CUDA(h, cudaGetLastError());
   h->reset_done = true;
   h->launches += 1;
@@ -1063,10 +1080,10 @@ int gww_step(gww_handle* h, const gw_io* io, void* stream) {
   const size_t stage = (size_t)(gww::THREADS / 32) * p.stage_bytes;
   if (wide_tile(h) == 32) {
     if (h->cfg.fear) gww::gww_step_kernel<true, 32><<<blocks, gww::THREADS, gww::smem_fixed<32>() + stage, s>>>(p);
-    else gww::gww_step_kernel<false, 32><<<blocks, gww::THREADS, gww::smem_fixed<32>() + stage, s>>>(p);
+    else gww::gww_step_kernel<false, 32><<<blocks, gww::THREADS, gww::smem_fixed<32, false>() + stage, s>>>(p);
   } else {
     if (h->cfg.fear) gww::gww_step_kernel<true, 128><<<blocks, gww::THREADS, gww::smem_fixed<128>() + stage, s>>>(p);
-    else gww::gww_step_kernel<false, 128><<<blocks, gww::THREADS, gww::smem_fixed<128>() + stage, s>>>(p);
+    else gww::gww_step_kernel<false, 128><<<blocks, gww::THREADS, gww::smem_fixed<128, false>() + stage, s>>>(p);
   }
   GWW_CUDA(h, cudaGetLastError());
   h->launches += 1;
