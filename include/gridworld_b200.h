@@ -15,6 +15,8 @@
  *                         obs flatten + reward shaping     maddpg/agent.py:89,128-131,160)
  *   gw_update_world   <- GWorld.UpdateGWorld (operator level, arbitrary positions/actions)
  *   gw_fear_one_actor <- Responsibility.FeAR_4_one_actor (operator level, arbitrary close list)
+ *   gww_*             <- the same calls for maps / agent counts beyond the shipped scenarios (GWorld is generic:
+ *                        custom/grid_world.py:17-86, :104-150; Scenario['N_Agents'], custom/ma_customenv.py:28)
  *
  * Conventions
  *   - plain C, no exceptions cross the boundary; every entry returns gw_status
@@ -28,8 +30,9 @@
  *     CUDA-graph capturable;
  *   - there is NO CPU implementation behind this interface: without a CUDA
  *     device gw_create fails with GW_ENODEV.
- *   - cells are (row, col) with row-major flat index row*W+col; W must be 16
- *     and H <= 16 in this version (all shipped scenarios are 10x16).
+ *   - cells are (row, col) with row-major flat index row*W+col.  Two state layouts: gw_* (packed: W must be 16, H <= 16,
+ *     <= 4 agents -- all shipped scenarios are 10x16 with 3..4 agents -- and every kernel of the library) and gww_* (general:
+ *     up to 64 x 64, up to 16 agents; the section at the end of this file).
  */
 #ifndef GRIDWORLD_B200_H
 #define GRIDWORLD_B200_H
@@ -503,6 +506,7 @@ size_t gww_state_bytes(const gww_handle* h);
 int gww_get_state(gww_handle* h, void* dst, int dst_is_device, void* stream);
 int gww_set_state(gww_handle* h, const void* src, int src_is_device, void* stream);
 int gww_get_stats(gww_handle* h, gw_stats* host_out, void* stream);
+int gww_reset_stats(gww_handle* h, void* stream);
 int gww_launch_count(const gww_handle* h, uint64_t* kernels_launched);
 /* Operator level, as gw_update_world / gw_fear_one_actor / gw_fear_matrix / gw_feal with every per-agent dimension of
  * length GWW_MAX_AGENTS: positions / new_positions [C,16,2], actions / mdr / crash / restricted / in_list / resp (one

@@ -18,7 +18,7 @@ EXPORTS = ["gw_abi_version", "gw_build_info", "gw_default_config", "gw_create", 
            "gw_learner_layout_of", "gw_learner_create", "gw_learner_destroy", "gw_learner_update", "gw_learner_debug_ptr", "gw_learner_set_kernel", "gw_learner_kernel",
            "gw_learner_peer_export", "gw_learner_peer_connect", "gw_learner_peer_status", "gw_learner_peer_disable",
            "gww_default_config", "gww_create", "gww_destroy", "gww_last_error", "gww_reset", "gww_step", "gww_sync",
-           "gww_state_bytes", "gww_get_state", "gww_set_state", "gww_get_stats", "gww_launch_count", "gww_update_world",
+           "gww_state_bytes", "gww_get_state", "gww_set_state", "gww_get_stats", "gww_reset_stats", "gww_launch_count", "gww_update_world",
            "gww_fear_one_actor", "gww_fear_matrix", "gww_feal"]
 
 
@@ -205,6 +205,7 @@ def load():
     lib.gww_get_state.argtypes = [vp, vp, C.c_int, vp]
     lib.gww_set_state.argtypes = [vp, vp, C.c_int, vp]
     lib.gww_get_stats.argtypes = [vp, C.POINTER(GwStats), vp]
+    lib.gww_reset_stats.argtypes = [vp, vp]
     lib.gww_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.gww_update_world.argtypes = [vp, i64] + [vp] * 8 + [vp]
     lib.gww_fear_one_actor.argtypes = [vp, i64] + [vp] * 10 + [vp]

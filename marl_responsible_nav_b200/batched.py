@@ -477,9 +477,10 @@ class BatchedGridWorld:
 
 
 class GeneralGridWorld(BatchedGridWorld):
-    """The GENERAL state layout (gww_* in include/gridworld_b200.h, csrc/gw_wide.cu): the same reset / step / operator-level
-    API for grids up to 64 x 64 with up to 16 agents.  What is tied to the packed layout is not offered here: the
-    multi-step rollout kernel, the resident host-driven step, `obs_code` and the fused actor (networks sized for 160 cells)."""
+    """The GENERAL state layout (gww_* in include/gridworld_b200.h, csrc/gw_wide.cu): the same reset / step / rollout /
+    operator-level API for grids up to 64 x 64 with up to 16 agents.  What is tied to the packed layout is not offered here: the
+    multi-step rollout KERNEL (`rollout` issues one launch per step), the resident host-driven step, `obs_code` and the fused
+    actor (networks sized for 160 cells)."""
     _P, _wide, PAD = "gww_", True, N.GWW_MAX_AGENTS
 
     def _create_handle(self, **kw):
@@ -503,7 +504,51 @@ class GeneralGridWorld(BatchedGridWorld):
         raise NotImplementedError("this entry point exists for the packed layout only (W = 16, H <= 16, <= 4 agents); "
                                   "the general layout offers reset / step / state / stats and the operator-level calls")
 
-    rollout = step_host = pinned_io = server_info = reset_stats = new_rings = _packed_only
+    step_host = pinned_io = server_info = _packed_only
+
+    def reset_stats(self):
+        self._check_rc(self.lib.gww_reset_stats(self._h, self._stream()), "reset_stats")
+
+    def rollout(self, actions: torch.Tensor, steps: int, rings, first_slot: int = 0, first_action: int = 0,
+                npc_actions: Optional[torch.Tensor] = None, spawn: Optional[torch.Tensor] = None):
+        """The same contract as BatchedGridWorld.rollout (time-major rings, step k's transition in slot (first_slot + k) % T,
+        the observation / action mask that follow it in the slot after), served by `steps` gww_step launches whose outputs
+        point straight into the ring slots -- the general layout has no multi-step kernel.  `rings.obs_code` is not written."""
+        E, L, A, dev = self.num_envs, self.n_learners, self.n_agents, self.device
+        actions = self._as_i8(actions, dev)
+        if actions.dim() != 3 or tuple(actions.shape[1:]) != (E, L):
+            raise ValueError(f"actions: expected int8 [A, {E}, {L}]")
+        n_act, T = actions.shape[0], int(rings.obs.shape[0])
+        dims = {"L": L, "O": self.obs_len, "A": A}
+        extra = {}
+        for name, t, tail in (("npc_actions", npc_actions, (A,)), ("spawn", spawn, (A, 2))):
+            if t is not None:
+                t = self._as_i8(t, dev)
+                if tuple(t.shape) != (n_act, E) + tail:
+                    raise ValueError(f"{name}: expected int8 {(n_act, E) + tail}")
+                extra[name] = t
+        fields = {}
+        for name, dtype, tail in self._RING_SPECS:
+            t = getattr(rings, name, None)
+            if t is None or name == "obs_code":
+                continue
+            if name in ("obs", "final_obs"):
+                if t.dtype != self.obs_dtype or t.device != dev or not t.is_contiguous() or t.shape[0] != T or t[0].numel() != E * L * self.obs_len:
+                    raise ValueError(f"rings.{name}: need a contiguous {self.obs_dtype} tensor [T, E, L, {self.obs_len}] on {dev}")
+            else:
+                _check(t, "rings." + name, dtype, (T, E) + tuple(dims.get(d, d) for d in tail), dev)
+            fields[name] = t
+        stream = self._stream()
+        for k in range(int(steps)):
+            slot, nxt, a = (first_slot + k) % T, (first_slot + k + 1) % T, (first_action + k) % n_act
+            io = N.GwIO()
+            io.learner_actions = actions[a].data_ptr()
+            for name, t in extra.items():
+                setattr(io, name, t[a].data_ptr())
+            for name, t in fields.items():
+                setattr(io, name, t[nxt if name in ("obs", "action_mask") else slot].data_ptr())
+            self._check_rc(self.lib.gww_step(self._h, C.byref(io), stream), "step")
+        return rings
 
 
 class PinnedIO:

@@ -1151,6 +1151,14 @@ int gww_get_stats(gww_handle* h, gw_stats* out, void* stream) {
   return GW_OK;
 }
 
+int gww_reset_stats(gww_handle* h, void* stream) {
+  if (!h) return GW_EINVAL;
+  GWW_CUDA(h, cudaSetDevice(h->cfg.device));
+  GWW_CUDA(h, cudaMemsetAsync(h->d_stats, 0, sizeof(unsigned long long) * gww::STAT_SLOTS * gww::ST_N, static_cast<cudaStream_t>(stream)));
+  h->env_steps = 0;
+  return GW_OK;
+}
+
 int gww_launch_count(const gww_handle* h, uint64_t* n) {
   if (!h || !n) return GW_EINVAL;
   *n = h->launches;

@@ -166,7 +166,7 @@ def test_general_layout_is_selected_when_the_scenario_does_not_fit():
     assert type(w) is GeneralGridWorld and w.obs_len == 560 and w.n_agents == 7
     assert type(BatchedGridWorld("Level 3", num_envs=4, layout="general")) is GeneralGridWorld
     with pytest.raises(NotImplementedError):
-        w.rollout(None, 1, None)
+        w.step_host(None, None)
     with pytest.raises(RuntimeError):                         # 5 agents do not fit the packed layout
         BatchedGridWorld("Level 3", num_envs=4, n_agents=5, layout="packed")
 
@@ -282,6 +282,31 @@ def test_general_one_update_fear_count_equals_the_literal_nine(monkeypatch):
     for t in range(3):
         chk.step(acts[t])
     assert np.array_equal(chk.fear, ora.fear) and np.array_equal(chk.positions, ora.positions)
+
+
+@pytest.mark.gpu
+def test_general_rollout_into_rings_equals_single_steps():
+    """BatchedGridWorld.rollout's contract on the general layout (one launch per step, outputs straight into the ring slots)."""
+    import torch
+    from marl_responsible_nav_b200 import BatchedGridWorld
+    kw = dict(num_envs=300, fear=True, fear_weight=-5.0, seed=13, max_steps=15)
+    a, b = BatchedGridWorld(WIDE, **kw), BatchedGridWorld(WIDE, **kw)
+    T, K = 7, 12
+    acts = torch.randint(0, 9, (5, 300, 2), dtype=torch.int8, device="cuda")
+    rings = a.new_rings(T)
+    rings.obs[2] = a.reset().obs
+    b.reset()
+    a.rollout(acts, K, rings, first_slot=2, first_action=3)
+    for k in range(K):
+        o = b.step(acts[(3 + k) % 5])
+        if k >= K - (T - 1):                                  # the newest T - 1 transitions are still in the ring
+            slot, nxt = (2 + k) % T, (3 + k) % T
+            for name in ("reward", "shaped_reward", "fear", "terminated", "truncated", "ended", "info", "positions"):
+                assert torch.equal(getattr(rings, name)[slot], getattr(o, name)), (k, name)
+            assert torch.equal(rings.obs[nxt], o.obs) and torch.equal(rings.action_mask[nxt], o.action_mask), k
+    assert a.stats()["episodes"] == b.stats()["episodes"] > 0
+    a.reset_stats()
+    assert a.stats()["episodes"] == 0 and a.stats()["env_steps"] == 0
 
 
 @pytest.mark.gpu
