@@ -506,6 +506,15 @@ class GeneralGridWorld(BatchedGridWorld):
 
     step_host = pinned_io = server_info = _packed_only
 
+    @property
+    def service_env(self) -> BatchedGridWorld:
+        """A one-env world on the packed layout and the same device: the handle that the library's replay-sampling and
+        update kernels (gw_replay_sample, gw_learner_*: they take a gw_handle for their device, stream and error state) are
+        created on when the training loop runs on a general-layout world."""
+        if getattr(self, "_service_env", None) is None:
+            self._service_env = BatchedGridWorld("Level 3", num_envs=1, device=self.device, fear=False, layout="packed")
+        return self._service_env
+
     def reset_stats(self):
         self._check_rc(self.lib.gww_reset_stats(self._h, self._stream()), "reset_stats")
 

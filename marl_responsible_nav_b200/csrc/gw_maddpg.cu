@@ -796,6 +796,7 @@ size_t smem_need(const gw_learner_config& c) {
 extern "C" int gw_learner_layout_of(const gw_learner_config* cfg, gw_learner_layout* out) {
   if (!out || out->struct_size != sizeof(gw_learner_layout)) return GW_EINVAL;
   if (int rc = check_cfg(cfg)) return rc;
+  if (smem_need(*cfg) > (size_t)227 * 1024) return GW_EINVAL;      // the critic's input row (n * (obs_len + 9) floats) must fit the tiles' shared-memory staging
   const int n = cfg->n_agents;
   const gwl::NetLayout la = gwl::make_layout(cfg->obs_len, cfg->action_dim);
   const gwl::NetLayout lc = gwl::make_layout(n * (cfg->obs_len + cfg->action_dim), 1);

@@ -48,7 +48,8 @@ class FusedLearner:
         lay.struct_size = C.sizeof(N.GwLearnerLayout)
         rc = self.lib.gw_learner_layout_of(C.byref(cfg), C.byref(lay))
         if rc != 0:
-            raise ValueError("FusedLearner: unsupported shape (1..2 agents, obs_len a multiple of 16, 9 actions, "
+            raise ValueError("FusedLearner: unsupported shape (1..2 agents, obs_len a multiple of 16 whose critic input row "
+                             "fits the kernel's shared-memory staging (about 400 cells for two learners), 9 actions, "
                              "BATCH_SIZE a multiple of 32 and <= 512)")
         self.cfg, self.layout = cfg, lay
         dev, P = env.device, int(lay.param_floats)

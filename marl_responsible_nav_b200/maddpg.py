@@ -524,6 +524,9 @@ class BatchedTrainer:
         update between the kernel's three segments."""
         from .replay import ReplayRing
         self.env = env
+        # the library's replay / update kernels hang their device, stream and error state on a packed-layout handle; a world on
+        # the general layout (larger map, more agents) lends them a one-env companion handle on the same device
+        self.svc = getattr(env, "service_env", env)
         self.hp = dict(DEFAULT_HP if hp is None else hp)
         if learn_cadence not in ("reference", "batched"):
             raise ValueError("learn_cadence must be 'reference' or 'batched'")
@@ -540,9 +543,13 @@ class BatchedTrainer:
         self.gradient_exchange = gradient_exchange
         self.learner = None
         if fused_learner and env.device.type == "cuda":
-            self.learner = self.agent.learner if self.agent.learner is not None else self.agent.attach_learner(env, seed=seed + 3)
-        elif fused_ops and env.device.type == "cuda" and self.agent.ops is None:
-            self.agent.attach_ops(env, linear_backward=fused_linear_bwd)
+            try:
+                self.learner = self.agent.learner if self.agent.learner is not None else self.agent.attach_learner(self.svc, seed=seed + 3)
+            except ValueError as exc:                          # a shape the update kernel does not hold (e.g. 560-cell observations)
+                import warnings
+                warnings.warn(f"{exc}; the update runs as the CUDA graph of PyTorch / library kernels instead")
+        if self.learner is None and fused_ops and env.device.type == "cuda" and self.agent.ops is None:
+            self.agent.attach_ops(self.svc, linear_backward=fused_linear_bwd)
         self.updates_per_learn = int(updates_per_learn)
         self.gen = torch.Generator(device=env.device).manual_seed(seed + 1 + int(getattr(env, "env_id_base", 0)))
         self.fused_sampler = bool(fused_sampler) and env.device.type == "cuda"      # csrc/gw_replay.cu
@@ -554,7 +561,7 @@ class BatchedTrainer:
         self.losses: List[LearnStats] = []
         # acting: the fused CUDA kernel (csrc/gw_actor.cu, tensor cores) or the PyTorch modules (same weights)
         self.fused = None
-        if fused_actor and env.device.type == "cuda" and env.obs_len == self.agent.obs_dim:
+        if fused_actor and env.device.type == "cuda" and env.obs_len == self.agent.obs_dim and not getattr(env, "_wide", False):
             from .actor import FusedActor
             self.fused = FusedActor(env, self.agent.actors, seed=seed + 2)
 
@@ -578,10 +585,10 @@ class BatchedTrainer:
             return self.ring.sample(batch_size, self.gen)
         dst = self.agent.static_inputs()
         if dst is not None and tuple(dst["state"].shape) == (batch_size, self.ring.L, self.ring.obs_len):
-            return self.ring.sample_fused(self.env, batch_size, seed=self.sample_seed, out=dst)
+            return self.ring.sample_fused(self.svc, batch_size, seed=self.sample_seed, out=dst)
         if self._batch is None or self._batch["state"].shape[0] != batch_size:
             self._batch = self.ring.new_batch(batch_size)
-        return self.ring.sample_fused(self.env, batch_size, seed=self.sample_seed, out=self._batch)
+        return self.ring.sample_fused(self.svc, batch_size, seed=self.sample_seed, out=self._batch)
 
     def learn_schedule(self, t: int) -> int:
         """Number of updates after vector step `t` (0-based), before the BATCH_SIZE gate.

@@ -32,6 +32,10 @@ def main():
     ap.add_argument("--torch-learner", action="store_true", help="the update as round 1's CUDA graph of PyTorch / library kernels instead of the one-kernel gw_learner_update")
     ap.add_argument("--gradient-exchange", choices=("peer", "nccl"), default="peer",
                     help="several GPUs: peer = inside the update kernel over NVLink peer memory; nccl = two all-reduces per update")
+    ap.add_argument("--scenario-json", default=None, help="a file in the reference's Scenarios.json format (any map up to 64 x 64, up to 16 agents: "
+                                                          "what does not fit the packed 10 x 16 x 4 layout runs on the general one)")
+    ap.add_argument("--scenario", default="Level 3", help="scenario name (built-in, or a key of --scenario-json)")
+    ap.add_argument("--walls", choices=("refuse", "inert", "enforce"), default="refuse", help="what to do with Walls / OneWays of --scenario-json")
     ap.add_argument("--save", default=None, help="write the agents here in the reference's checkpoint format (maddpg/agent.py:255-266)")
     ap.add_argument("--load", default=None, help="resume from a checkpoint of the reference / of --save (maddpg/agent.py:268-283)")
     a = ap.parse_args()
@@ -43,7 +47,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     base, n = sharding.shard_range(a.envs, rank, world)
-    env = maddpg.make_env(hp, n, device=dev, env_id_base=base, env_kind=a.env_kind)
+    scenario = a.scenario
+    if a.scenario_json:
+        from .scenarios import load_scenario_json
+        scenario = load_scenario_json(a.scenario_json, a.scenario, walls=a.walls)
+    env = maddpg.make_env(hp, n, device=dev, scenario=scenario, env_id_base=base, env_kind=a.env_kind)
     agent = None
     if a.load:
         from . import checkpoint

@@ -310,6 +310,30 @@ def test_general_rollout_into_rings_equals_single_steps():
 
 
 @pytest.mark.gpu
+def test_training_loop_on_the_general_layout():
+    """BatchedTrainer on the 20 x 28 x 7 world: PyTorch actors on the 560-cell observations, device replay ring written by
+    gww_step and read by gw_replay_sample, the update as the CUDA graph of PyTorch / library kernels (the one-kernel update
+    holds critic input rows up to about 800 floats; 2 x 569 here), at the batched cadence."""
+    import torch
+    from marl_responsible_nav_b200 import maddpg
+    hp = maddpg.preset("custom_fear_5")
+    hp["MEMORY_SIZE"] = 4096
+    env = maddpg.make_env(hp, 256, scenario=WIDE)
+    with pytest.warns(UserWarning, match="unsupported shape"):
+        tr = maddpg.BatchedTrainer(env, hp=hp, seed=0, learn_cadence="batched")
+    assert tr.fused is None and tr.learner is None and tr.agent.obs_dim == 560
+    p0 = [p.detach().clone() for p in tr.agent.actors[0].parameters()]
+    st = tr.train(40)
+    assert st["env_steps"] == 40 * 256 and tr.updates_done >= 3
+    assert any(not torch.equal(a, b) for a, b in zip(p0, tr.agent.actors[0].parameters()))
+    assert all(bool(torch.isfinite(l.critic_loss).all()) for l in tr.losses)
+    b = tr.ring.sample(64, tr.gen)
+    assert b["state"].shape == (64, 2, 560)
+    s, e = int(b["t"][0]) % tr.ring.T, int(b["env"][0])
+    assert torch.equal(b["reward"][0], (-5.0 * tr.ring.fear[s, e] + tr.ring.reward[s, e].double()).float())
+
+
+@pytest.mark.gpu
 def test_general_state_roundtrip_and_errors():
     from marl_responsible_nav_b200 import BatchedGridWorld
     import torch
