@@ -421,7 +421,7 @@ def masked_uniform_runs(a, E, dev, seeds=(0, 42, 66), steps=384):
 def general_layout_extra(a, dev, cpu_seconds=4.0):
     """the GENERAL state layout (gww_*, csrc/gw_wide.cu) on a scenario the packed layout cannot hold -- the 20 x 28
     map with 7 agents, walls and one-ways that tests/golden/make_wide_golden.py ran the reference on.  Device-timed step
-    launches (CUDA events around a 32-step CUDA graph), FeAR on / off, at the headline batch and at a batch that fills the GPU; next to
+    launches (CUDA events around a 32-step CUDA graph), FeAR on / off, at the headline batch, at 65 536 and at 524 288 envs; next to
     it the C oracle built on gww_config, all host threads, on a bounded sample.  An extra line, never the headline."""
     import numpy as np
     import torch
@@ -432,7 +432,7 @@ def general_layout_extra(a, dev, cpu_seconds=4.0):
     peak, _ = peaks()
     out = {"scenario": f"{H}x{W} map, {sc.n_agents} agents, {len(sc.blocked)} restricted paths, 2 learners", "kernel": "gww_step_kernel",
            "algorithmic_bytes_per_env_step": algo, "points": []}
-    for E, fear in ((a.envs, 1), (a.envs, 0), (65536, 1), (65536, 0)):
+    for E, fear in ((a.envs, 1), (a.envs, 0), (65536, 1), (65536, 0), (524288, 1), (524288, 0)):
         env = BatchedGridWorld(sc, num_envs=E, device=dev, fear=bool(fear), fear_weight=-5.0, seed=42, max_steps=150)
         env.reset()
         acts = torch.randint(0, 9, (8, E, 2), dtype=torch.int8, device=dev)

@@ -205,6 +205,66 @@ __device__ __forceinline__ uint16_t one_move(const Tab* T, const unsigned long l
   return (uint16_t)((r << 8) | c);
 }
 
+// UpdateGWorld in trajectory form (what the env step runs; the literal form above stays for the operator-level calls and as
+// the cross-check).  A crash reverts the path from floor(q/4) on and stops the agent (grid_world.py:200-208, :470), and
+// floor(q/4) only grows, so at any sub-step an agent is either on its nominal trajectory -- start cell, cell after the
+// first move, cell after the second -- or, once crashed, on its start cell with BOTH interpolation points there.  So three
+// cells and a crashed bit per agent replace the path lists; a second move is attempted (and can count as restricted) only
+// by an agent that did not crash in sub-step 0.  The fix-point cap of 2N passes never binds: two crashed agents stand on
+// distinct start cells and cannot hit each other, so every pass with a hit crashes somebody new.
+__device__ void world_update_fast(const Tab* __restrict__ T, const unsigned long long* rows, int n, const uint16_t* loc0,
+                                  const uint8_t* act, const uint16_t* apples, int apple_on, int n_eaters, UpdateOut& out) {
+  uint16_t p1[NA], p2[NA], near[NA];
+  uint32_t r2 = 0, crash = 0, restr = 0;
+  out.caught[0][0] = out.caught[0][1] = out.caught[1][0] = out.caught[1][1] = 0;
+  out.unresolved = false;
+  for (int i = 0; i < n; ++i) {
+    const int a = act[i];
+    bool ra = false, rb = false;
+    p1[i] = a != 0 ? one_move(T, rows, loc0[i], a, ra) : loc0[i];
+    p2[i] = MOVE_LEN[a] == 2 ? one_move(T, rows, p1[i], a, rb) : p1[i];
+    restr |= (ra ? 1u : 0u) << i;
+    r2 |= (rb ? 1u : 0u) << i;
+    uint32_t m = 0;
+    for (int k = i + 1; k < n; ++k) m |= (manhattan(loc0[i], loc0[k]) <= 4 ? 1u : 0u) << k;
+    near[i] = (uint16_t)m;
+  }
+  for (int step = 0; step < MAXSTEPS; ++step) {
+    if (step == 1) restr |= r2 & ~crash;
+    int count = n;
+    while (count > 0) {
+      count = 0;
+      uint32_t hit_mask = 0;
+      for (int ii = 0; ii < n - 1; ++ii) {
+        if (!near[ii]) continue;
+        const int qi = (step + 1) * MOVE_LEN[act[ii]], fi = qi >> 2, ci = (qi + 3) >> 2;
+        const bool xi = (crash >> ii) & 1u;
+        const int pi = loc0[ii];
+        const int ai = (xi || fi == 0) ? pi : (fi == 1 ? p1[ii] : p2[ii]), bi = xi ? pi : (ci == 1 ? p1[ii] : p2[ii]);
+        for (uint32_t rest = near[ii]; rest; rest &= rest - 1u) {
+          const int jj = __ffs(rest) - 1;
+          const int qj = (step + 1) * MOVE_LEN[act[jj]], fj = qj >> 2, cj = (qj + 3) >> 2;
+          const bool xj = (crash >> jj) & 1u;
+          const int pj = loc0[jj];
+          const int aj = (xj || fj == 0) ? pj : (fj == 1 ? p1[jj] : p2[jj]), bj = xj ? pj : (cj == 1 ? p1[jj] : p2[jj]);
+          if (gw::pair_hit(ai, bi, pi, qi, fi, ci, aj, bj, pj, qj, fj, cj)) { ++count; hit_mask |= (1u << ii) | (1u << jj); }
+        }
+      }
+      crash |= hit_mask;
+    }
+    if (apples)                                                                       // :531-540 (a lone agent's `cur` stays its start cell)
+      for (int e = 0; e < n_eaters; ++e) {
+        const int q = (step + 1) * MOVE_LEN[act[e]], f = q >> 2;
+        const uint16_t cur = (n < 2 || ((crash >> e) & 1u) || f == 0) ? loc0[e] : (f == 1 ? p1[e] : p2[e]);
+        for (int k = 0; k < 2; ++k)
+          if (((apple_on >> k) & 1) && cur == apples[k]) out.caught[e][k] += 1;
+      }
+  }
+  for (int i = 0; i < n; ++i)                                                         // :552: floor(4 len / 4) = len
+    out.loc[i] = (n < 2 || ((crash >> i) & 1u)) ? loc0[i] : (MOVE_LEN[act[i]] == 1 ? p1[i] : p2[i]);
+  out.crash = crash; out.restr = restr;
+}
+
 // Agents further apart than Manhattan distance 4 cannot meet within one step (every cell of an agent's path is within 2 of
 // its start cell, and the pair rules compare cells only), so what happens to agent j depends only on the agents linked to
 // it by a chain of such near pairs: its component.
@@ -638,7 +698,8 @@ __global__ void __launch_bounds__(THREADS) gww_step_kernel(Params p) {
         }
       uint16_t apples[2] = {(uint16_t)((T->apple_r[0] << 8) | (T->apple_c[0] & 255)), (uint16_t)((T->apple_r[1] << 8) | (T->apple_c[1] & 255))};
       UpdateOut u;
-      world_update(T, s.rows, n, st.cell, s.act[t], apples, (int)(st.flags & 3u), nl, u);
+      if (p.literal_fear) world_update(T, s.rows, n, st.cell, s.act[t], apples, (int)(st.flags & 3u), nl, u);
+      else world_update_fast(T, s.rows, n, st.cell, s.act[t], apples, (int)(st.flags & 3u), nl, u);
       for (int i = 0; i < n; ++i) st.cell[i] = u.loc[i];
       double reward[2] = {0.0, 0.0};
       int term_now[2] = {0, 0}, trunc_now = 0, apples_rewarded = 0, crash_count = 0, shaped[2] = {0, 0};
