@@ -295,8 +295,8 @@ __device__ int count_valid_fast(const Tab* T, const unsigned long long* rows, in
   // the world without j: nominal paths (no collisions) and the crashed sets per sub-step
   uint32_t Cb[MAXSTEPS], Ca[MAXSTEPS];
   const uint32_t others = comp & ~(1u << j);
-  for (int k = 0; k < n; ++k) {
-    if (!((others >> k) & 1u)) continue;
+  for (uint32_t rest = others; rest; rest &= rest - 1u) {
+    const int k = __ffs(rest) - 1;
     nom[k][0] = loc[k];
     for (int s = 0; s < MAXSTEPS; ++s) {
       bool r = false;
@@ -312,13 +312,13 @@ __device__ int count_valid_fast(const Tab* T, const unsigned long long* rows, in
       ++loops;                                        //  every pass with a hit crashes somebody new, so the cap never binds)
       count = 0;
       uint32_t hit_mask = 0;
-      for (int ii = 0; ii < n - 1; ++ii) {
-        if (!((others >> ii) & 1u)) continue;
+      for (uint32_t ri = others; ri; ri &= ri - 1u) {
+        const int ii = __ffs(ri) - 1;
         const int qi = (s + 1) * MOVE_LEN[act[ii]], fi = qi >> 2, ci = (qi + 3) >> 2;
         const bool xi = (crash >> ii) & 1u;
         const int ai = xi ? loc[ii] : nom[ii][fi], bi = xi ? loc[ii] : nom[ii][ci];
-        for (int jj = ii + 1; jj < n; ++jj) {
-          if (!((others >> jj) & 1u)) continue;
+        for (uint32_t rj = ri & (ri - 1u); rj; rj &= rj - 1u) {
+          const int jj = __ffs(rj) - 1;
           const int qj = (s + 1) * MOVE_LEN[act[jj]], fj = qj >> 2, cj = (qj + 3) >> 2;
           const bool xj = (crash >> jj) & 1u;
           const int aj = xj ? loc[jj] : nom[jj][fj], bj = xj ? loc[jj] : nom[jj][cj];
@@ -345,8 +345,8 @@ __device__ int count_valid_fast(const Tab* T, const unsigned long long* rows, in
       if (bad) break;                                         // restricted: invalid whatever the others do (:46)
       const int qj = (s + 1) * len, fj = qj >> 2, cj = (qj + 3) >> 2;
       const int A = pj[fj], B = pj[cj], P = loc[j];
-      for (int k = 0; k < n && !bad; ++k) {
-        if (!((others >> k) & 1u)) continue;
+      for (uint32_t rk = others; rk && !bad; rk &= rk - 1u) {
+        const int k = __ffs(rk) - 1;
         const int qk = (s + 1) * MOVE_LEN[act[k]], fk = qk >> 2, ck = (qk + 3) >> 2;
         if (!((Cb[s] >> k) & 1u)) {
           const int ak = nom[k][fk], bk = nom[k][ck];
@@ -551,6 +551,7 @@ struct Smem {
   uint8_t mdr[FT][NA];
   uint16_t close[FT][2];                   // close list of learner x (bit i = agent i in the list)
   uint8_t cnt[FT][2][NA][2];               // valid-move counts [actor][affected][0 = MdR variant, 1 = action variant]
+  uint16_t task_comp[FT * 2 * (NA - 1)];   // the queued pair's near component (actor and affected agent share it)
   uint16_t task[FT * 2 * (NA - 1)];        // FeAR work queue: (env in tile << 5) | (actor << 4) | affected -- only the pairs that need simulating
   int n_tasks;
   uint8_t render[TILE];                    // bit 0 obs fresh, bit 1 write final_obs, bits 2-3 apples shown in obs, 4-5 in final_obs, 7 live
@@ -663,7 +664,11 @@ __global__ void __launch_bounds__(THREADS) gww_step_kernel(Params p) {
           if (T->kind == GW_ENV_SINGLE && __popc(m) <= 1) continue;
           const uint32_t comp = p.literal_fear ? 0xFFFFu : near_component(n, st.cell, x);
           for (int j = 0; j < n; ++j)
-            if (j != x && ((comp >> j) & 1u)) s.task[atomicAdd(&s.n_tasks, 1)] = (uint16_t)((t << 5) | (x << 4) | j);
+            if (j != x && ((comp >> j) & 1u)) {
+              const int slot = atomicAdd(&s.n_tasks, 1);
+              s.task[slot] = (uint16_t)((t << 5) | (x << 4) | j);
+              s.task_comp[slot] = (uint16_t)comp;
+            }
         }
       }
     }
@@ -679,7 +684,7 @@ __global__ void __launch_bounds__(THREADS) gww_step_kernel(Params p) {
         for (int i = 0; i < n; ++i) la[i] = s.act[q][i];
         if (v == 0) la[x] = s.mdr[q][x];
         s.cnt[q][x][j][v] = (uint8_t)(p.literal_fear ? count_valid(T, s.rows, n, s.cell[q], la, in_list, j)
-                                                      : count_valid_fast(T, s.rows, n, s.cell[q], la, in_list, j, near_component(n, s.cell[q], j)));
+                                                      : count_valid_fast(T, s.rows, n, s.cell[q], la, in_list, j, s.task_comp[it >> 1]));
       }
       __syncthreads();
       if (t == 0) { s.stat[ST_TASKS] += (unsigned long long)s.n_tasks; s.n_tasks = 0; }
