@@ -252,8 +252,11 @@ def test_errors_are_loud():
     env.reset()
     with pytest.raises(ValueError):
         env.step(torch.zeros((7, 2), dtype=torch.int8, device="cuda"))
-    with pytest.raises(RuntimeError, match="n_agents"):
-        BatchedGridWorld("Level 3", num_envs=8, n_agents=7)
+    with pytest.raises(RuntimeError, match="n_agents"):                  # the packed layout holds up to 4 agents ...
+        BatchedGridWorld("Level 3", num_envs=8, n_agents=7, layout="packed")
+    assert type(BatchedGridWorld("Level 3", num_envs=8, n_agents=7)).__name__ == "GeneralGridWorld"   # ... seven take the general one ...
+    with pytest.raises(RuntimeError, match="n_agents"):                  # ... which holds up to 16
+        BatchedGridWorld("Level 3", num_envs=8, n_agents=17)
 
 
 def test_step_host_matches_device_step():
