@@ -933,9 +933,121 @@ struct RollParams {
 // below -- inputs that the host rewrites between two calls are loaded past the L1 (ordinary L2-level loads after the
 // system-scope acquire fence that follows the doorbell: `ld.volatile` reads of host memory are served one PCIe round
 // trip after the other, ~50 ns per request, measured 50-100 us per step at 4096 envs).
-template <bool FEAR, int OBS, bool SERVER, bool ROLL = false>
+// ---- FeAR of one step for the warp's four envs (ma_customenv.py:245-252, Responsibility.py:135-210).  Inputs are per lane
+// what the step computed before the world update: the env's packed cells, the trajectories played / the learners' MdR
+// trajectories (effw), which learners deviate from their MdR (neqb), the near pairs (near6) and this lane's pair geometry
+// (didx).  Nothing here depends on the update itself, which is what lets gw_rollout's helper warps run it beside the update.
+struct FearOut { double f0, f1; uint32_t tasks; };
+__device__ __forceinline__ FearOut fear_block(const StepParams& p, Smem<32>& s, int lane, int gsh, int r, int n, int nl, bool own,
+                                              uint32_t cells, uint32_t effw, uint32_t neqb, uint32_t near6, uint32_t didx) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  double fear0 = 0.0, fear1 = 0.0;
+  uint32_t tm = 0;                                               // bit 4x + j: task (actor x, affected j)
+  {
+    const int xx = r >> 2, kk = r & 3;                             // close_agents :456-464 for both actors at once
+    const bool cl = xx < nl && kk < n &&
+                    (kk == xx || manhattan((cells >> (8 * xx)) & 0xFFu, (cells >> (8 * kk)) & 0xFFu) <= p.fear_radius);
+    const uint32_t closeb = (__ballot_sync(FULL, cl) >> gsh) & 0xFFu;
+#pragma unroll
+    for (int x = 0; x < GW_MAX_LEARNERS; ++x) {
+      if (x >= nl) break;
+      if (((neqb >> x) & 1u) == 0) continue;                                            // action == MdR: Resp = 0 exactly
+      const uint32_t js = reach_mask(s.sim, near6, x) & ~(1u << x) & ((1u << n) - 1u);
+      if (js == 0) continue;
+      if (((effw >> (16 + 4 * x)) & 0xFu) == ((effw >> (4 * x)) & 0xFu)) continue;      // same trajectory: counts equal
+      tm |= js << (4 * x);
+    }
+    if (!own) tm = 0;
+    // Work items (task, variant) of the warp's four envs are dealt to its 32 lanes, whichever env they belong to: a
+    // lane fetches the env's words from that group's first lane, counts (count_valid_moves: no per-action loop), and
+    // the counts travel back as warp-wide sums per group.  One round unless the four envs hold more than 16 tasks.
+    uint32_t cw0 = 0, cw1 = 0;
+    const int n_it = 2 * __popc(tm);
+    const int c0 = __shfl_sync(FULL, n_it, 0), c1 = __shfl_sync(FULL, n_it, 8), c2 = __shfl_sync(FULL, n_it, 16),
+              c3 = __shfl_sync(FULL, n_it, 24);
+    const int total = c0 + c1 + c2 + c3;
+    if (total > 0) {                                               // warp-uniform
+      const uint32_t my_lo = gather_lanes<4, 8>(FULL, didx, gsh), my_hi = gather_lanes<2, 8>(FULL, didx, gsh + 4);
+      const uint32_t my_misc = closeb | (tm << 8) | (near6 << 16);
+      uint32_t f0 = 0, f1 = 0;                                     // this lane's contributions (to the env of its item)
+      int item_g = 0;
+      for (int base = 0; base < total; base += 32) {
+        const int it = base + lane;
+        const int gq = (it >= c0) + (it >= c0 + c1) + (it >= c0 + c1 + c2);
+        const int local = it - (gq > 0 ? c0 : 0) - (gq > 1 ? c1 : 0) - (gq > 2 ? c2 : 0);
+        const int src = 8 * gq;
+        const uint32_t cells_g = __shfl_sync(FULL, cells, src), effw_g = __shfl_sync(FULL, effw, src),
+                       misc_g = __shfl_sync(FULL, my_misc, src), lo_g = __shfl_sync(FULL, my_lo, src),
+                       hi_g = __shfl_sync(FULL, my_hi, src);
+        if (it < total) {
+          const uint32_t v = (uint32_t)local & 1u;
+          uint32_t mm = (misc_g >> 8) & 0xFFu;
+          for (int q = 0; q < (local >> 1); ++q) mm &= mm - 1u;
+          const uint32_t bit = (uint32_t)__ffs(mm) - 1u, x = bit >> 2, j = bit & 3u;
+          const uint32_t close = (misc_g >> (4 * x)) & 0xFu;
+          const uint32_t keep = ((close & 1u) ? 0xFu : 0u) | ((close & 2u) ? 0xF0u : 0u) | ((close & 4u) ? 0xF00u : 0u) |
+                                ((close & 8u) ? 0xF000u : 0u);
+          uint32_t eo = effw_g & keep;                             // agents outside the close list Stay (defaultAction='stay')
+          if (v == 0) eo = (eo & ~(0xFu << (4 * x))) | (((effw_g >> (16 + 4 * x)) & 0xFu) << (4 * x));   // actor plays its MdR (:169-172)
+          PairGeom g;
+          g.near6 = (misc_g >> 16) & 0x3Fu;
+          g.didx_lo = lo_g;
+          g.didx_hi = hi_g;
+          const uint32_t cnt = count_valid_moves(s.sim, cells_g, eo, g, (int)j, ((close >> j) & 1u) != 0);
+          const uint32_t jslot = j - (j > x ? 1u : 0u);
+          const uint32_t field = cnt << (4 * (jslot * 2 + v));
+          if (x == 0) f0 += field; else f1 += field;
+          item_g = gq;
+        }
+        // the sums of this round go back to their groups (4-bit fields, at most 9 each: no carry)
+        uint32_t cw0r = 0, cw1r = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t s0 = __reduce_add_sync(FULL, (it < total && item_g == q) ? f0 : 0u);
+          const uint32_t s1 = __reduce_add_sync(FULL, (it < total && item_g == q) ? f1 : 0u);
+          if ((lane >> 3) == q) { cw0r = s0; cw1r = s1; }
+        }
+        cw0 += cw0r; cw1 += cw1r;
+        f0 = f1 = 0;
+      }
+#pragma unroll
+      for (int x = 0; x < GW_MAX_LEARNERS; ++x) {
+        const uint32_t tb = (tm >> (4 * x)) & 0xFu;
+        if (tb == 0) continue;
+        const uint32_t c = x == 0 ? cw0 : cw1;
+        double rs[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int js = 0; js < 3; ++js) {
+          const int j = js + (js >= x ? 1 : 0);
+          if ((tb >> j) & 1u) rs[js] = s.small.resp_lut[(c >> (8 * js)) & 0xFu][(c >> (8 * js + 4)) & 0xFu];
+        }
+        const double f = fear_sum3(n, rs[0], rs[1], rs[2]);
+        if (x == 0) fear0 = f; else fear1 = f;
+      }
+      
+    }
+  }
+  FearOut o;
+  o.f0 = fear0; o.f1 = fear1; o.tasks = (uint32_t)__popc(tm);
+  return o;
+}
+
+// gw_rollout with FeAR, split form: warp w of the CTA's first eight steps its four envs, warp w + 8 computes their FeAR beside
+// it.  The pair talk through a per-warp mailbox in shared memory and two mbarriers (inputs written / results written).
+struct SplitBox {
+  uint32_t in[8][4][32];                   // per lane of the main warp: cells, effw, neqb | near6 << 2 | own << 8, didx
+  double fear[8][4][2];                    // per env of the warp: info["fear"] of learner 0 / 1
+  uint32_t tasks[8][4];
+  unsigned long long full[8], done[8];
+};
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <bool FEAR, int OBS, bool SERVER, bool ROLL = false, bool SPLIT = false>
 __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& s, uint8_t* stage, bool& tables_pending,
-                                                 const RollParams* rp = nullptr) {
+                                                 const RollParams* rp = nullptr, SplitBox* box = nullptr) {
+  uint32_t split_phase = 0;
   constexpr int TILE = 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = tid & 7, gsh = lane & 24;
   constexpr unsigned FULL = 0xFFFFFFFFu;     // every shuffle / ballot below is executed by the whole converged warp: a
@@ -1092,6 +1204,14 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
         }
       }
       const uint32_t near6 = (__ballot_sync(FULL, near) >> gsh) & 0x3Fu;
+      if (SPLIT) {                                                     // everything FeAR needs is known: hand it to the helper warp
+        box->in[warp][0][lane] = cells;
+        box->in[warp][1][lane] = effw;
+        box->in[warp][2][lane] = neqb | (near6 << 2) | (own ? 0x100u : 0u);
+        box->in[warp][3][lane] = didx;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&box->full[warp]));
+      }
       uint32_t cm = 0;
       {
         uint32_t nn = 0, nr = 0, rn = 0;
@@ -1212,89 +1332,16 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
       // ---- FeAR (ma_customenv.py:245-252, Responsibility.py:135-210): the env's own 8 lanes count its tasks
       double fear0 = 0.0, fear1 = 0.0;
       if (FEAR) {
-        const int xx = r >> 2, kk = r & 3;                             // close_agents :456-464 for both actors at once
-        const bool cl = xx < nl && kk < n &&
-                        (kk == xx || manhattan((cells >> (8 * xx)) & 0xFFu, (cells >> (8 * kk)) & 0xFFu) <= p.fear_radius);
-        const uint32_t closeb = (__ballot_sync(FULL, cl) >> gsh) & 0xFFu;
-        uint32_t tm = 0;                                               // bit 4x + j: task (actor x, affected j)
-#pragma unroll
-        for (int x = 0; x < GW_MAX_LEARNERS; ++x) {
-          if (x >= nl) break;
-          if (((neqb >> x) & 1u) == 0) continue;                                            // action == MdR: Resp = 0 exactly
-          const uint32_t js = reach_mask(s.sim, near6, x) & ~(1u << x) & ((1u << n) - 1u);
-          if (js == 0) continue;
-          if (((effw >> (16 + 4 * x)) & 0xFu) == ((effw >> (4 * x)) & 0xFu)) continue;      // same trajectory: counts equal
-          tm |= js << (4 * x);
+        FearOut fo;
+        if (SPLIT) {                                                   // computed by this warp's helper warp meanwhile (gw_rollout_split_kernel)
+          mbar_wait(smem_u32(&box->done[warp]), split_phase);
+          split_phase ^= 1u;
+          fo.f0 = box->fear[warp][lane >> 3][0]; fo.f1 = box->fear[warp][lane >> 3][1]; fo.tasks = box->tasks[warp][lane >> 3];
+        } else {
+          fo = fear_block(p, s, lane, gsh, r, n, nl, own, cells, effw, neqb, near6, didx);
         }
-        if (!own) tm = 0;
-        // Work items (task, variant) of the warp's four envs are dealt to its 32 lanes, whichever env they belong to: a
-        // lane fetches the env's words from that group's first lane, counts (count_valid_moves: no per-action loop), and
-        // the counts travel back as warp-wide sums per group.  One round unless the four envs hold more than 16 tasks.
-        uint32_t cw0 = 0, cw1 = 0;
-        const int n_it = 2 * __popc(tm);
-        const int c0 = __shfl_sync(FULL, n_it, 0), c1 = __shfl_sync(FULL, n_it, 8), c2 = __shfl_sync(FULL, n_it, 16),
-                  c3 = __shfl_sync(FULL, n_it, 24);
-        const int total = c0 + c1 + c2 + c3;
-        if (total > 0) {                                               // warp-uniform
-          const uint32_t my_lo = gather_lanes<4, 8>(FULL, didx, gsh), my_hi = gather_lanes<2, 8>(FULL, didx, gsh + 4);
-          const uint32_t my_misc = closeb | (tm << 8) | (near6 << 16);
-          uint32_t f0 = 0, f1 = 0;                                     // this lane's contributions (to the env of its item)
-          int item_g = 0;
-          for (int base = 0; base < total; base += 32) {
-            const int it = base + lane;
-            const int gq = (it >= c0) + (it >= c0 + c1) + (it >= c0 + c1 + c2);
-            const int local = it - (gq > 0 ? c0 : 0) - (gq > 1 ? c1 : 0) - (gq > 2 ? c2 : 0);
-            const int src = 8 * gq;
-            const uint32_t cells_g = __shfl_sync(FULL, cells, src), effw_g = __shfl_sync(FULL, effw, src),
-                           misc_g = __shfl_sync(FULL, my_misc, src), lo_g = __shfl_sync(FULL, my_lo, src),
-                           hi_g = __shfl_sync(FULL, my_hi, src);
-            if (it < total) {
-              const uint32_t v = (uint32_t)local & 1u;
-              uint32_t mm = (misc_g >> 8) & 0xFFu;
-              for (int q = 0; q < (local >> 1); ++q) mm &= mm - 1u;
-              const uint32_t bit = (uint32_t)__ffs(mm) - 1u, x = bit >> 2, j = bit & 3u;
-              const uint32_t close = (misc_g >> (4 * x)) & 0xFu;
-              const uint32_t keep = ((close & 1u) ? 0xFu : 0u) | ((close & 2u) ? 0xF0u : 0u) | ((close & 4u) ? 0xF00u : 0u) |
-                                    ((close & 8u) ? 0xF000u : 0u);
-              uint32_t eo = effw_g & keep;                             // agents outside the close list Stay (defaultAction='stay')
-              if (v == 0) eo = (eo & ~(0xFu << (4 * x))) | (((effw_g >> (16 + 4 * x)) & 0xFu) << (4 * x));   // actor plays its MdR (:169-172)
-              PairGeom g;
-              g.near6 = (misc_g >> 16) & 0x3Fu;
-              g.didx_lo = lo_g;
-              g.didx_hi = hi_g;
-              const uint32_t cnt = count_valid_moves(s.sim, cells_g, eo, g, (int)j, ((close >> j) & 1u) != 0);
-              const uint32_t jslot = j - (j > x ? 1u : 0u);
-              const uint32_t field = cnt << (4 * (jslot * 2 + v));
-              if (x == 0) f0 += field; else f1 += field;
-              item_g = gq;
-            }
-            // the sums of this round go back to their groups (4-bit fields, at most 9 each: no carry)
-            uint32_t cw0r = 0, cw1r = 0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t s0 = __reduce_add_sync(FULL, (it < total && item_g == q) ? f0 : 0u);
-              const uint32_t s1 = __reduce_add_sync(FULL, (it < total && item_g == q) ? f1 : 0u);
-              if ((lane >> 3) == q) { cw0r = s0; cw1r = s1; }
-            }
-            cw0 += cw0r; cw1 += cw1r;
-            f0 = f1 = 0;
-          }
-#pragma unroll
-          for (int x = 0; x < GW_MAX_LEARNERS; ++x) {
-            const uint32_t tb = (tm >> (4 * x)) & 0xFu;
-            if (tb == 0) continue;
-            const uint32_t c = x == 0 ? cw0 : cw1;
-            double rs[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-            for (int js = 0; js < 3; ++js) {
-              const int j = js + (js >= x ? 1 : 0);
-              if ((tb >> j) & 1u) rs[js] = s.small.resp_lut[(c >> (8 * js)) & 0xFu][(c >> (8 * js + 4)) & 0xFu];
-            }
-            const double f = fear_sum3(n, rs[0], rs[1], rs[2]);
-            if (x == 0) fear0 = f; else fear1 = f;
-          }
-          if (r == 0) { v_tasks = (uint32_t)__popc(tm); v_nz = (fear0 != 0.0) + (fear1 != 0.0); v_fear = fear0 + fear1; }
-        }
+        fear0 = fo.f0; fear1 = fo.f1;
+        if (r == 0) { v_tasks = fo.tasks; v_nz = (fear0 != 0.0) + (fear1 != 0.0); v_fear = fear0 + fear1; }
       }
       if (r < nl && own) {
         const double f = (r == 0) ? fear0 : fear1;
@@ -1427,6 +1474,53 @@ __global__ void __launch_bounds__(256, 2) gw_rollout_kernel(StepParams p, RollPa
   bool tables_pending = true;
   small_step_tiles<FEAR, OBS, false, true>(p, s, stage, tables_pending, &rp);
   if (tables_pending) tables_wait(s);
+}
+
+// The FeAR half of gw_rollout_split_kernel: warp w + 8 serves warp w -- the same tiles, the same number of steps, one
+// mailbox hand-over each way per step.
+__device__ void fear_helper_tiles(const StepParams& p, Smem<32>& s, const RollParams& rp, SplitBox* box) {
+  const int tid = (int)threadIdx.x - 256, warp = tid >> 5, lane = tid & 31, r = tid & 7, gsh = lane & 24;
+  const long long n_tiles = (p.E + 31) / 32;
+  tables_wait(s);
+  uint32_t phase = 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    for (int k_step = 0; k_step < rp.steps; ++k_step) {
+      mbar_wait(smem_u32(&box->full[warp]), phase);
+      phase ^= 1u;
+      const uint32_t cells = box->in[warp][0][lane], effw = box->in[warp][1][lane], misc = box->in[warp][2][lane],
+                     didx = box->in[warp][3][lane];
+      const FearOut fo = fear_block(p, s, lane, gsh, r, p.n, p.nl, (misc & 0x100u) != 0, cells, effw, misc & 3u, (misc >> 2) & 0x3Fu, didx);
+      if (r == 0) {
+        box->fear[warp][lane >> 3][0] = fo.f0;
+        box->fear[warp][lane >> 3][1] = fo.f1;
+        box->tasks[warp][lane >> 3] = fo.tasks;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&box->done[warp]));
+    }
+}
+
+// gw_rollout with FeAR on sixteen warps: the step's dependent chain is what bounds small batches (a warp issues one
+// instruction every ~6 cycles and a step is ~2 000 of them), and a quarter of it is FeAR, which needs nothing of the world
+// update it sits behind.  Warps 0-7 run the step as in gw_rollout_kernel and post FeAR's inputs as soon as they are known;
+// warps 8-15 compute it meanwhile; the step picks the values up where it used to compute them.
+template <int OBS>
+__global__ void __launch_bounds__(512, 1) gw_rollout_split_kernel(StepParams p, RollParams rp) {
+  constexpr int TILE = 32;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
+  uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
+  __shared__ SplitBox box;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(&box.full[i]), 1); mbar_init(smem_u32(&box.done[i]), 1); }
+  load_tables<TILE>(s, stage, p, 32, p.nl * p.H * GW_W * (OBS == GW_OBS_F32 ? 4 : 2));      // (fences the mbarrier inits, __syncthreads)
+  if (threadIdx.x < 256) {
+    bool tables_pending = true;
+    small_step_tiles<true, OBS, false, true, true>(p, s, stage, tables_pending, &rp, &box);
+    if (tables_pending) tables_wait(s);
+  } else {
+    fear_helper_tiles(p, s, rp, &box);
+  }
 }
 
 // ------------------------------------------------------------------ resident step server (gw_step_host, mode 2)
@@ -2480,7 +2574,8 @@ int gw_step(gw_handle* h, const gw_io* io, void* stream) {
 }  // extern "C"
 
 template <typename K>
-static void launch_rollout_k(K kernel, const gw::StepParams& p, const gw::RollParams& rp, unsigned blocks, size_t smem, cudaStream_t s) {
+static void launch_rollout_k(K kernel, const gw::StepParams& p, const gw::RollParams& rp, unsigned blocks, size_t smem, cudaStream_t s,
+                             int threads = 256) {
   static thread_local const void* raised_fn = nullptr;
   static thread_local size_t raised = 0;
   if (raised_fn != (const void*)kernel || raised < smem) {
@@ -2488,7 +2583,7 @@ static void launch_rollout_k(K kernel, const gw::StepParams& p, const gw::RollPa
     raised_fn = (const void*)kernel;
     raised = smem;
   }
-  kernel<<<blocks, 256, smem, s>>>(p, rp);
+  kernel<<<blocks, threads, smem, s>>>(p, rp);
 }
 
 extern "C" {
@@ -2520,7 +2615,11 @@ int gw_rollout(gw_handle* h, const gw_io* rings, const gw_rollout_plan* plan, vo
   const size_t smem = gw::smem_fixed_bytes<32>() + (size_t)8 * 4 * gw::stage_row_bytes(c);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool f32 = c.obs_dtype == GW_OBS_F32;
-  if (c.fear) {
+  static const bool split = [] { const char* e = std::getenv("GW_ROLL_SPLIT"); return !(e && e[0] == '0'); }();
+  if (c.fear && split && blocks <= 2u * (unsigned)h->sm_count) {        // latency regime: FeAR on helper warps beside the step
+    if (f32) launch_rollout_k(gw::gw_rollout_split_kernel<GW_OBS_F32>, p, rp, blocks, smem, s, 512);
+    else launch_rollout_k(gw::gw_rollout_split_kernel<GW_OBS_BF16>, p, rp, blocks, smem, s, 512);
+  } else if (c.fear) {
     if (f32) launch_rollout_k(gw::gw_rollout_kernel<true, GW_OBS_F32>, p, rp, blocks, smem, s);
     else launch_rollout_k(gw::gw_rollout_kernel<true, GW_OBS_BF16>, p, rp, blocks, smem, s);
   } else {
