@@ -27,6 +27,7 @@
 #include <string>
 
 #include <cuda_bf16.h>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "gw_device.cuh"
@@ -1044,10 +1045,24 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// The step's own 256 threads: with helper warps in the CTA (SPLIT) a CTA-wide barrier would wait for them too.
+template <bool SPLIT>
+__device__ __forceinline__ void main_sync() {
+  if (SPLIT) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else __syncthreads();
+}
+// the main warps tell their helpers to leave (gw_*_split_kernel, at the end of the kernel)
+__device__ __forceinline__ void split_post_exit(SplitBox* box) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  box->in[warp][2][lane] = 0x200u;
+  __syncwarp();
+  if (lane == 0) mbar_arrive(smem_u32(&box->full[warp]));
+}
+
 template <bool FEAR, int OBS, bool SERVER, bool ROLL = false, bool SPLIT = false>
 __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& s, uint8_t* stage, bool& tables_pending,
-                                                 const RollParams* rp = nullptr, SplitBox* box = nullptr) {
-  uint32_t split_phase = 0;
+                                                 const RollParams* rp = nullptr, SplitBox* box = nullptr, uint32_t* split_phase_io = nullptr) {
+  uint32_t split_phase = SPLIT ? *split_phase_io : 0u;              // parity of the helper's "results written" barrier: lives across calls
   constexpr int TILE = 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = tid & 7, gsh = lane & 24;
   constexpr unsigned FULL = 0xFFFFFFFFu;     // every shuffle / ballot below is executed by the whole converged warp: a
@@ -1075,7 +1090,7 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
     const bool own = el < tile_envs;
     if (SERVER && tile != (long long)blockIdx.x) {                      // the previous tile's result copies have read the staging
       if (tid == 0) bulk_wait_read<0>();
-      __syncthreads();
+      main_sync<SPLIT>();
     }
 
     // ================================================================= loads and RNG (no table needed)
@@ -1140,7 +1155,7 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
         npc_a = (uint32_t)min(max((int)(SERVER ? __ldcg(p.io.npc_actions + ea * n + r) : p.io.npc_actions[ea * n + r]), 0), 8);
     }
     if (SERVER && act_staged) {
-      __syncthreads();
+      main_sync<SPLIT>();
 #pragma unroll
       for (int k = 0; k < GW_MAX_LEARNERS; ++k)
         if (k < nl && own) la |= (uint32_t)min(max((int)act_s[el * nl + k], 0), 8) << (4 * k);
@@ -1356,7 +1371,7 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
     trace_stamp(p, 2);
     if (SERVER) {
       fence_proxy_async_smem();
-      __syncthreads();
+      main_sync<SPLIT>();
       if (warp == 0) {
         const int nr = tile_envs * nl;
         if (p.io.reward) server_flush(p.io.reward + tile_base * nl, out_rew, nr * 4, lane);
@@ -1443,8 +1458,8 @@ __device__ __forceinline__ void small_step_tiles(const StepParams& p, Smem<32>& 
     }
     }                                                                  // steps of this tile
   }
+  if (SPLIT) *split_phase_io = split_phase;
 }
-
 template <bool FEAR, int OBS>
 __global__ void __launch_bounds__(256, 2) gw_step_small_kernel(StepParams p) {
   constexpr int TILE = 32;
@@ -1476,28 +1491,31 @@ __global__ void __launch_bounds__(256, 2) gw_rollout_kernel(StepParams p, RollPa
   if (tables_pending) tables_wait(s);
 }
 
-// The FeAR half of gw_rollout_split_kernel: warp w + 8 serves warp w -- the same tiles, the same number of steps, one
-// mailbox hand-over each way per step.
-__device__ void fear_helper_tiles(const StepParams& p, Smem<32>& s, const RollParams& rp, SplitBox* box) {
+// The FeAR half of the *_split_kernel's: warp w + 8 serves warp w, one mailbox hand-over each way per step, until the main
+// warp posts the exit word.
+__device__ void fear_helper_loop(const StepParams& p, Smem<32>& s, SplitBox* box) {
   const int tid = (int)threadIdx.x - 256, warp = tid >> 5, lane = tid & 31, r = tid & 7, gsh = lane & 24;
-  const long long n_tiles = (p.E + 31) / 32;
   tables_wait(s);
   uint32_t phase = 0;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-    for (int k_step = 0; k_step < rp.steps; ++k_step) {
-      mbar_wait(smem_u32(&box->full[warp]), phase);
-      phase ^= 1u;
-      const uint32_t cells = box->in[warp][0][lane], effw = box->in[warp][1][lane], misc = box->in[warp][2][lane],
-                     didx = box->in[warp][3][lane];
-      const FearOut fo = fear_block(p, s, lane, gsh, r, p.n, p.nl, (misc & 0x100u) != 0, cells, effw, misc & 3u, (misc >> 2) & 0x3Fu, didx);
-      if (r == 0) {
-        box->fear[warp][lane >> 3][0] = fo.f0;
-        box->fear[warp][lane >> 3][1] = fo.f1;
-        box->tasks[warp][lane >> 3] = fo.tasks;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&box->done[warp]));
+  for (;;) {
+    mbar_wait(smem_u32(&box->full[warp]), phase);
+    phase ^= 1u;
+    const uint32_t misc = box->in[warp][2][lane];
+    if (misc & 0x200u) break;
+    const uint32_t cells = box->in[warp][0][lane], effw = box->in[warp][1][lane], didx = box->in[warp][3][lane];
+    const FearOut fo = fear_block(p, s, lane, gsh, r, p.n, p.nl, (misc & 0x100u) != 0, cells, effw, misc & 3u, (misc >> 2) & 0x3Fu, didx);
+    if (r == 0) {
+      box->fear[warp][lane >> 3][0] = fo.f0;
+      box->fear[warp][lane >> 3][1] = fo.f1;
+      box->tasks[warp][lane >> 3] = fo.tasks;
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&box->done[warp]));
+  }
+}
+__device__ __forceinline__ void split_init(SplitBox* box) {          // before load_tables (which fences the inits and syncs the CTA)
+  if (threadIdx.x == 0)
+    for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(&box->full[i]), 1); mbar_init(smem_u32(&box->done[i]), 1); }
 }
 
 // gw_rollout with FeAR on sixteen warps: the step's dependent chain is what bounds small batches (a warp issues one
@@ -1511,15 +1529,38 @@ __global__ void __launch_bounds__(512, 1) gw_rollout_split_kernel(StepParams p, 
   Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
   uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
   __shared__ SplitBox box;
-  if (threadIdx.x == 0)
-    for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(&box.full[i]), 1); mbar_init(smem_u32(&box.done[i]), 1); }
-  load_tables<TILE>(s, stage, p, 32, p.nl * p.H * GW_W * (OBS == GW_OBS_F32 ? 4 : 2));      // (fences the mbarrier inits, __syncthreads)
+  split_init(&box);
+  load_tables<TILE>(s, stage, p, 32, p.nl * p.H * GW_W * (OBS == GW_OBS_F32 ? 4 : 2));
   if (threadIdx.x < 256) {
     bool tables_pending = true;
-    small_step_tiles<true, OBS, false, true, true>(p, s, stage, tables_pending, &rp, &box);
+    uint32_t phase = 0;
+    small_step_tiles<true, OBS, false, true, true>(p, s, stage, tables_pending, &rp, &box, &phase);
     if (tables_pending) tables_wait(s);
+    split_post_exit(&box);
   } else {
-    fear_helper_tiles(p, s, rp, &box);
+    fear_helper_loop(p, s, &box);
+  }
+}
+
+// One gw_step launch per step, the same way (up to one tile per SM; the 256-thread kernel above runs two CTAs per SM).
+template <int OBS>
+__global__ void __launch_bounds__(512, 1) gw_step_small_split_kernel(StepParams p) {
+  constexpr int TILE = 32;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
+  uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
+  __shared__ SplitBox box;
+  split_init(&box);
+  load_tables<TILE>(s, stage, p, 32, p.nl * p.H * GW_W * (OBS == GW_OBS_F32 ? 4 : 2));
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x < 256) {
+    bool tables_pending = true;
+    uint32_t phase = 0;
+    small_step_tiles<true, OBS, false, false, true>(p, s, stage, tables_pending, nullptr, &box, &phase);
+    if (tables_pending) tables_wait(s);
+    split_post_exit(&box);
+  } else {
+    fear_helper_loop(p, s, &box);
   }
 }
 
@@ -1554,16 +1595,24 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-template <bool FEAR, int OBS>
-__global__ void __launch_bounds__(256, 2) gw_step_server_kernel(StepParams p, ServerParams sp) {
+template <bool FEAR, int OBS, bool SPLIT = false>
+__global__ void __launch_bounds__(SPLIT ? 512 : 256, SPLIT ? 1 : 2) gw_step_server_kernel(StepParams p, ServerParams sp) {
   constexpr int TILE = 32;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem<TILE>& s = *reinterpret_cast<Smem<TILE>*>(smem_raw);
   uint8_t* stage = smem_raw + smem_fixed_bytes<TILE>();
   __shared__ unsigned long long cmd_s;
   __shared__ __align__(16) unsigned long long io_s[(sizeof(gw_io) + 7) / 8];
+  __shared__ typename std::conditional<SPLIT, SplitBox, int>::type box_s;     // the mailboxes exist in the split kernel only
+  SplitBox* const box = reinterpret_cast<SplitBox*>(&box_s);
+  uint32_t split_phase = 0;
+  if (SPLIT) split_init(box);
   load_tables<TILE>(s, stage, p, 32, p.nl * p.H * GW_W * (OBS == GW_OBS_F32 ? 4 : 2));
   tables_wait(s);
+  if (SPLIT && threadIdx.x >= 256) {                                   // FeAR helper warps: served through the mailboxes until told to leave
+    fear_helper_loop(p, s, box);
+    return;
+  }
   unsigned int seq = sp.first_seq, rounds = 0;
 #ifdef GW_ENABLE_TRACE
   unsigned long long tr_acc[5] = {0, 0, 0, 0, 0}, tr_t = 0;   // thread 0: time in wait / table entry / step / drain / arrive
@@ -1604,21 +1653,21 @@ __global__ void __launch_bounds__(256, 2) gw_step_server_kernel(StepParams p, Se
       }
       cmd_s = w;
     }
-    __syncthreads();
+    main_sync<SPLIT>();
     const unsigned long long w = cmd_s;
     if (((w >> 16) & 0xFFu) != SRV_OP_STEP) break;
     SRV_TRACE(0);
     if (threadIdx.x < (int)((sizeof(gw_io) + 7) / 8))
       io_s[threadIdx.x] = __ldcv(reinterpret_cast<const unsigned long long*>(sp.io_table + (w & 0xFFFFu)) + threadIdx.x);
-    __syncthreads();
+    main_sync<SPLIT>();
     StepParams q = p;
     q.io = *reinterpret_cast<const gw_io*>(io_s);
     bool tables_pending = false;
     SRV_TRACE(1);
-    small_step_tiles<FEAR, OBS, true>(q, s, stage, tables_pending);
+    small_step_tiles<FEAR, OBS, true, false, SPLIT>(q, s, stage, tables_pending, nullptr, box, &split_phase);
     SRV_TRACE(2);
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // this thread's observation rows have landed
-    __syncthreads();
+    main_sync<SPLIT>();
     SRV_TRACE(3);
     if (threadIdx.x == 0) {
       // Release at GPU scope per CTA (cumulative over what the barrier ordered before it), one system-scope fence by the
@@ -1640,6 +1689,7 @@ __global__ void __launch_bounds__(256, 2) gw_step_server_kernel(StepParams p, Se
     p.trace[(size_t)blockIdx.x * 16 + 5] = rounds;
   }
 #endif
+  if (SPLIT) split_post_exit(box);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     asm volatile("fence.acq_rel.sys;" ::: "memory");
     st_volatile_u32(sp.host_resp + 1, sp.generation);
@@ -2284,6 +2334,12 @@ static void launch_k(K kernel, const gw::StepParams& p, unsigned blocks, int thr
 
 // Programmatic dependent launch is opt-in (GW_PDL=1): measured on B200 it saves 0.4 us per step at 4096 envs but costs
 // 7 us at 65536 envs, where the early-launched CTAs of the next grid unbalance the SMs (profiles/README.md).
+// FeAR on helper warps (the *_split_kernel's): on unless GW_SPLIT=0; they hold one 512-thread CTA per SM
+static bool use_split() {
+  static const bool on = [] { const char* e = std::getenv("GW_SPLIT"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 static bool use_pdl() {
   static const bool v = [] { const char* s = std::getenv("GW_PDL"); return s && std::atoi(s) != 0; }();
   return v;
@@ -2311,7 +2367,10 @@ static void launch_step_small(const gw_config& c, gw::StepParams& p, unsigned bl
   const bool f32 = c.obs_dtype == GW_OBS_F32;
   const size_t smem = gw::smem_fixed_bytes<32>() + (size_t)8 * 4 * gw::stage_row_bytes(c);
   const bool pdl = p.pdl_early != 0 || use_pdl();
-  if (c.fear) {
+  if (c.fear && use_split() && (int)blocks <= sm_count) {               // one tile per SM: FeAR on helper warps beside the step
+    if (f32) launch_k(gw::gw_step_small_split_kernel<GW_OBS_F32>, p, blocks, 512, smem, s, pdl);
+    else launch_k(gw::gw_step_small_split_kernel<GW_OBS_BF16>, p, blocks, 512, smem, s, pdl);
+  } else if (c.fear) {
     if (f32) launch_k(gw::gw_step_small_kernel<true, GW_OBS_F32>, p, blocks, 256, smem, s, pdl);
     else launch_k(gw::gw_step_small_kernel<true, GW_OBS_BF16>, p, blocks, 256, smem, s, pdl);
   } else {
@@ -2390,10 +2449,12 @@ static int server_stop(gw_handle* h) {
 }
 
 template <typename K>
-static void launch_server_k(K kernel, const gw::StepParams& p, const gw::ServerParams& sp, unsigned blocks, size_t smem, cudaStream_t s) {
+static void launch_server_k(K kernel, const gw::StepParams& p, const gw::ServerParams& sp, unsigned blocks, size_t smem, cudaStream_t s,
+                            int threads = 256) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kernel<<<blocks, 256, smem, s>>>(p, sp);
+  kernel<<<blocks, threads, smem, s>>>(p, sp);
 }
+
 
 static int server_start(gw_handle* h, cudaStream_t s, unsigned int first_seq) {
   gw_server& v = h->srv;
@@ -2412,7 +2473,10 @@ static int server_start(gw_handle* h, cudaStream_t s, unsigned int first_seq) {
   const unsigned blocks = (unsigned)(n_tiles < resident ? n_tiles : resident);
   const size_t smem = gw::smem_fixed_bytes<32>() + (size_t)8 * 4 * gw::stage_row_bytes(c);
   const bool f32 = c.obs_dtype == GW_OBS_F32;
-  if (c.fear) {
+  if (c.fear && use_split() && n_tiles <= (long long)h->sm_count) {      // one tile per SM: FeAR on helper warps beside the step
+    if (f32) launch_server_k(gw::gw_step_server_kernel<true, GW_OBS_F32, true>, p, sp, blocks, smem, s, 512);
+    else launch_server_k(gw::gw_step_server_kernel<true, GW_OBS_BF16, true>, p, sp, blocks, smem, s, 512);
+  } else if (c.fear) {
     if (f32) launch_server_k(gw::gw_step_server_kernel<true, GW_OBS_F32>, p, sp, blocks, smem, s);
     else launch_server_k(gw::gw_step_server_kernel<true, GW_OBS_BF16>, p, sp, blocks, smem, s);
   } else {
@@ -2615,8 +2679,7 @@ int gw_rollout(gw_handle* h, const gw_io* rings, const gw_rollout_plan* plan, vo
   const size_t smem = gw::smem_fixed_bytes<32>() + (size_t)8 * 4 * gw::stage_row_bytes(c);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool f32 = c.obs_dtype == GW_OBS_F32;
-  static const bool split = [] { const char* e = std::getenv("GW_ROLL_SPLIT"); return !(e && e[0] == '0'); }();
-  if (c.fear && split && blocks <= 2u * (unsigned)h->sm_count) {        // latency regime: FeAR on helper warps beside the step
+  if (c.fear && use_split() && blocks <= (unsigned)h->sm_count) {       // one tile per SM: FeAR on helper warps beside the step
     if (f32) launch_rollout_k(gw::gw_rollout_split_kernel<GW_OBS_F32>, p, rp, blocks, smem, s, 512);
     else launch_rollout_k(gw::gw_rollout_split_kernel<GW_OBS_BF16>, p, rp, blocks, smem, s, 512);
   } else if (c.fear) {
