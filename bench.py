@@ -37,10 +37,11 @@ NCU_ROLLOUT_DRAM_BYTES = {(4096, 1, 20): 553.5e3 + 55.46e6}
 def kernel_name(envs, fear, obs, mode="step"):
     """The kernel gw_step picks for this batch (csrc/gw_kernels.cu: pick_small / pick_tile); gw_rollout has one."""
     f = "true" if fear else "false"
+    split = fear and envs <= 32 * 148 and os.environ.get("GW_SPLIT", "1") != "0"     # one tile per SM: FeAR on helper warps
     if mode == "rollout":
-        return f"gw_rollout_kernel<{f},{obs}>"
+        return f"gw_rollout_split_kernel<{obs}>" if split else f"gw_rollout_kernel<{f},{obs}>"
     if envs <= 6144:
-        return f"gw_step_small_kernel<{f},{obs}>"
+        return f"gw_step_small_split_kernel<{obs}>" if split else f"gw_step_small_kernel<{f},{obs}>"
     tile = 32 if envs <= 24576 else (128 if envs <= 196608 else 256)
     return f"gw_step_kernel<256,{tile},{f},{obs}>"
 METRIC = "agent-steps/sec (batched envs, device-timed) at 1/2/4/8 B200 vs CPU ref"
