@@ -31,7 +31,7 @@ ALGO_BYTES_PER_AGENT_STEP = {"f32": 668.0, "bf16": 348.0}      # SURVEY.md secti
 # (profiles/r1d_*_ncu_raw.csv; Level 3, f32 obs): (envs, fear) -> bytes
 NCU_DRAM_BYTES = {(4096, 1): 370.0e3 + 0.0, (1 << 20, 1): 23.2e6 + 1413.0e6, (1 << 20, 0): 19.33e6 + 1378.3e6}
 # gw_rollout_kernel<true,f32>, (envs, fear, steps per launch): one launch under ncu --set full (profiles/r2c_rollout_ncu_details.txt)
-NCU_ROLLOUT_DRAM_BYTES = {(4096, 1, 20): 553.5e3 + 55.46e6}
+NCU_ROLLOUT_DRAM_BYTES = {(4096, 1, 20): 550.4e3 + 53.71e6}      # gw_rollout_split_kernel, profiles/r2r_rollout_split_ncu_details.txt
 
 
 def kernel_name(envs, fear, obs, mode="step"):
@@ -685,7 +685,7 @@ def run_ours(a):
                                  NCU_ROLLOUT_DRAM_BYTES.get((E, int(bool(a.fear)), r_plan["steps_per_launch"]))),
                      "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1d_*_ncu_raw.csv); "
                                        "at 4096 envs the stores are still in L2 when the kernel ends, so DRAM writes show as 0; gw_rollout (20 steps per launch, "
-                                       "profiles/r2c_rollout_ncu_details.txt): 56 MB of the launch's 109 MB reach DRAM before it ends, the rest is written back from L2 later",
+                                       "profiles/r2r_rollout_split_ncu_details.txt): 54 MB of the launch's 109 MB reach DRAM before it ends, the rest is written back from L2 later",
                      "kernel": kernel_name(E, a.fear, a.obs, r_plan["mode"]),
                      "algorithmic_bytes_per_launch": algo * K / n_launches, "algorithmic_bytes_per_step": algo, "peak_source": peak_src,
                      "launch_ms": ms / n_launches,
