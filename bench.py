@@ -31,7 +31,7 @@ ALGO_BYTES_PER_AGENT_STEP = {"f32": 668.0, "bf16": 348.0}      # SURVEY.md secti
 # (profiles/r1d_*_ncu_raw.csv; Level 3, f32 obs): (envs, fear) -> bytes
 NCU_DRAM_BYTES = {(4096, 1): 370.0e3 + 0.0, (1 << 20, 1): 23.2e6 + 1413.0e6, (1 << 20, 0): 19.33e6 + 1378.3e6}
 # gw_rollout_kernel<true,f32>, (envs, fear, steps per launch): one launch under ncu --set full (profiles/r2c_rollout_ncu_details.txt)
-NCU_ROLLOUT_DRAM_BYTES = {(4096, 1, 20): 550.4e3 + 53.71e6}      # gw_rollout_split_kernel, profiles/r2r_rollout_split_ncu_details.txt
+NCU_ROLLOUT_DRAM_BYTES = {(4096, 1, 20): 551.2e3 + 53.04e6}      # gw_rollout_split_kernel, profiles/r2r_rollout_split_ncu_details.txt
 
 
 def kernel_name(envs, fear, obs, mode="step"):
