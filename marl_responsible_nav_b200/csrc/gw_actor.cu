@@ -99,7 +99,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
-constexpr int THREADS = 512;
+// CTA size.  (1 024 threads for the two-tile kernel -- 16 warps per tile in flight, 64 registers -- measured 15 % slower
+// at 1 M envs: the phases only one column group runs, operand build and head, do not get shorter.)
+__host__ __device__ constexpr int threads_of(int /*groups*/) { return 512; }
 
 // GROUPS = 1: the CTA's 16 warps work on one tile (four column groups in the epilogues) -- shortest path for one tile,
 // used while the batch does not fill the machine.  GROUPS = 2: two groups of 8 warps work on two tiles out of phase (two
@@ -109,13 +111,15 @@ constexpr int THREADS = 512;
 // operand)] [w1: 128 x cells bf16] [Fixed<GROUPS>]
 template <int GROUPS>
 struct Fixed {
-  static constexpr int NGRP = THREADS / GROUPS / 128;         // column groups of the epilogues (warps sharing a TMEM lane quarter)
+  static constexpr int NGRP = threads_of(GROUPS) / GROUPS / 128;         // column groups of the epilogues (warps sharing a TMEM lane quarter)
   alignas(1024) uint8_t w2[HID * HID * 2];
   alignas(128) uint8_t w3[16 * HID * 2];             // W3 padded to 16 outputs, bf16, UMMA layout
   float b3[NACT];
   alignas(16) float c1[HID], ln1_g[HID], ln1_b[HID], b2[HID], ln2_g[HID], ln2_b[HID];
   alignas(8) float2 part[GROUPS][NGRP][ROWS];       // LayerNorm partial (sum, sum of squares) per column group and row
-  uint32_t rnd[GROUPS][ROWS][29];                   // Philox words of the head's noise
+  float noise[GROUPS][2][ROWS][19];                 // the head's noise per row: 9 Gumbel values, 9 standard normals (odd stride: no bank
+                                                    // conflicts), double-buffered over consecutive tiles like maskbits
+  uint16_t maskbits[GROUPS][2][ROWS];               // action-mask bits per row, double-buffered over consecutive tiles
   alignas(8) unsigned long long bar[GROUPS], bar_w; // MMA completion per group; arrival of W1 / W2
   uint32_t tmem_base;
 };
@@ -126,9 +130,12 @@ __device__ __forceinline__ float gumbel_from(uint32_t w) {
   const float u = fmaxf(((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f), 1e-20f);
   return -__logf(-__logf(u) + 1e-20f);
 }
-__device__ __forceinline__ float gauss_from(uint32_t a, uint32_t b) {          // Box-Muller
+__device__ __forceinline__ float2 gauss_pair_from(uint32_t a, uint32_t b) {     // Box-Muller, both outputs
   const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  return sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307f * u2);
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float sn, cs;
+  __sincosf(6.283185307f * u2, &sn, &cs);
+  return make_float2(r * cs, r * sn);
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -155,6 +162,136 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Packed fp32 pairs (sm_100: add / fma on two floats in a 64-bit register pair -> FADD2 / FFMA2): the LayerNorm epilogues
+// are the kernel's CUDA-core work, this halves their arithmetic instructions.
+__device__ __forceinline__ uint64_t pack2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) { return pack2(__float_as_uint(lo), __float_as_uint(hi)); }
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  uint32_t a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+  lo = __uint_as_float(a); hi = __uint_as_float(b);
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// (lo, hi) -> max(., 0) -> bf16 pair, lo in the low half: ReLU rides on the conversion
+__device__ __forceinline__ uint32_t relu_bf16x2(uint64_t v) {
+  uint32_t a, b, d;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(b)), "f"(__uint_as_float(a)));
+  return d;
+}
+
+// One LayerNorm + ReLU epilogue of this thread's CPG columns of its row: TMEM accumulator (+ bias) -> statistics (partial
+// sums of the column groups joined through shared memory) -> normalise, affine, ReLU, bf16 -> the next layer's A operand.
+// Rows without an env are processed like any other (their accumulator rows are finite: zero operand rows + bias) and
+// their results are never read: a row of A only reaches the same row of D.
+// tcgen05.ld without the wait, and the wait with the registers as in/out operands (what follows depends on it): a
+// chunk's load is in flight while the previous chunk is processed
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+
+// One LayerNorm + ReLU epilogue of this thread's CPG columns of its row: TMEM accumulator (+ bias) -> statistics (partial
+// sums of the column groups joined through shared memory; `sync` joins the warps that share the rows) -> second pass over
+// the accumulator (re-read from TMEM: keeping the row in registers across the barrier spills at 128 registers per
+// thread and measured 40 % slower) -> normalise, affine, ReLU, bf16 -> the next layer's A operand.
+// Rows without an env are processed like any other (their accumulator rows are finite: zero operand rows + bias) and
+// their results are never read: a row of A only reaches the same row of D.
+template <int CPG, int NGRP, class Sync>
+__device__ __forceinline__ void ln_relu_epilogue(uint32_t taddr, const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                 const float* __restrict__ beta, float2 (*part)[ROWS], int cg, int m,
+                                                 uint8_t* a_tile, int col0, bool on, Sync&& sync) {
+  static_assert(CPG % 32 == 0, "two chunks of 16 columns in flight");
+  if (on) {
+    uint64_t sa2 = 0ull, sb2 = 0ull, qa2 = 0ull, qb2 = 0ull;     // (0.f, 0.f): two chains each for the sum and the sum of squares
+    uint32_t ra[16], rb[16];
+    auto stats = [&](const uint32_t (&r)[16], int c0) {
+#pragma unroll
+      for (int u = 0; u < 16; u += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(&bias[c0 + u]);
+        const uint64_t x0 = add2(pack2(r[u], r[u + 1]), pack2f(b4.x, b4.y));
+        const uint64_t x1 = add2(pack2(r[u + 2], r[u + 3]), pack2f(b4.z, b4.w));
+        sa2 = add2(sa2, x0); qa2 = fma2(x0, x0, qa2);
+        sb2 = add2(sb2, x1); qb2 = fma2(x1, x1, qb2);
+      }
+    };
+    tmem_ld16_issue(taddr, ra);
+#pragma unroll
+    for (int c0 = 0; c0 < CPG; c0 += 32) {
+      tmem_wait16(ra);
+      tmem_ld16_issue(taddr + (uint32_t)(c0 + 16), rb);
+      stats(ra, c0);
+      tmem_wait16(rb);
+      if (c0 + 32 < CPG) tmem_ld16_issue(taddr + (uint32_t)(c0 + 32), ra);
+      stats(rb, c0 + 16);
+    }
+    float s0, s1, q0, q1;
+    unpack2(add2(sa2, sb2), s0, s1); unpack2(add2(qa2, qb2), q0, q1);
+    part[cg][m] = make_float2(s0 + s1, q0 + q1);
+  }
+  sync();                                                // partial sums of the column groups
+  if (on) {
+    uint32_t ra[16], rb[16];
+    tmem_ld16_issue(taddr, ra);                          // in flight while the statistics are joined
+    float su = 0.f, sq = 0.f;
+#pragma unroll
+    for (int g = 0; g < NGRP; ++g) { const float2 pp = part[g][m]; su += pp.x; sq += pp.y; }
+    const float mu = su * (1.0f / HID);
+    const float rs = rsqrtf(fmaxf(sq * (1.0f / HID) - mu * mu, 0.f) + 1e-5f);
+    const float nmr = -mu * rs;
+    const uint64_t rs2 = pack2f(rs, rs), nmr2 = pack2f(nmr, nmr);
+    auto norm = [&](const uint32_t (&r)[16], int c0) {
+#pragma unroll
+      for (int u = 0; u < 16; u += 8) {                  // one 16-byte core-matrix row per 8 columns
+        const int c8 = c0 + u;
+        const float4 i0 = *reinterpret_cast<const float4*>(&bias[c8]), i1 = *reinterpret_cast<const float4*>(&bias[c8 + 4]);
+        const float4 g0 = *reinterpret_cast<const float4*>(&gamma[c8]), g1 = *reinterpret_cast<const float4*>(&gamma[c8 + 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&beta[c8]), b1 = *reinterpret_cast<const float4*>(&beta[c8 + 4]);
+        const uint64_t x0 = add2(pack2(r[u], r[u + 1]), pack2f(i0.x, i0.y)), x1 = add2(pack2(r[u + 2], r[u + 3]), pack2f(i0.z, i0.w));
+        const uint64_t x2 = add2(pack2(r[u + 4], r[u + 5]), pack2f(i1.x, i1.y)), x3 = add2(pack2(r[u + 6], r[u + 7]), pack2f(i1.z, i1.w));
+        // (x - mu) * rs as one fma, then the affine part; ReLU inside the conversion
+        const uint32_t p0 = relu_bf16x2(fma2(fma2(x0, rs2, nmr2), pack2f(g0.x, g0.y), pack2f(b0.x, b0.y)));
+        const uint32_t p1 = relu_bf16x2(fma2(fma2(x1, rs2, nmr2), pack2f(g0.z, g0.w), pack2f(b0.z, b0.w)));
+        const uint32_t p2 = relu_bf16x2(fma2(fma2(x2, rs2, nmr2), pack2f(g1.x, g1.y), pack2f(b1.x, b1.y)));
+        const uint32_t p3 = relu_bf16x2(fma2(fma2(x3, rs2, nmr2), pack2f(g1.z, g1.w), pack2f(b1.z, b1.w)));
+        *reinterpret_cast<uint4*>(a_tile + umma_off(m, col0 + c8)) = make_uint4(p0, p1, p2, p3);
+      }
+    };
+#pragma unroll
+    for (int c0 = 0; c0 < CPG; c0 += 32) {
+      tmem_wait16(ra);
+      tmem_ld16_issue(taddr + (uint32_t)(c0 + 16), rb);
+      norm(ra, c0);
+      tmem_wait16(rb);
+      if (c0 + 32 < CPG) tmem_ld16_issue(taddr + (uint32_t)(c0 + 32), ra);
+      norm(rb, c0 + 16);
+    }
+  }
+}
+
 __device__ __forceinline__ void mma_k16(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, int k_steps, uint32_t idesc = IDESC,
                                         uint32_t b_rows = 128u) {
   const uint32_t b_lbo = b_rows * 16u;                     // bytes between K-adjacent core matrices of B
@@ -170,8 +307,8 @@ __device__ __forceinline__ void mma_k16(uint32_t tmem_d, uint32_t a_addr, uint32
 }
 
 template <int GROUPS>
-__global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
-  constexpr int TPG = THREADS / GROUPS, NGRP = Fixed<GROUPS>::NGRP, CPG = HID / NGRP;
+__global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(FwdArgs a) {
+  constexpr int THREADS = threads_of(GROUPS), TPG = THREADS / GROUPS, NGRP = Fixed<GROUPS>::NGRP, CPG = HID / NGRP;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int cells = a.cpo;                                 // K of layer 1: a multiple of 16 (H x 16)
   const uint32_t op_bytes = (uint32_t)ROWS * cells * 2;
@@ -184,6 +321,8 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
     if (GROUPS == 1) __syncthreads();
     else asm volatile("bar.sync %0, %1;" ::"r"(1 + gi), "n"(TPG) : "memory");
   };
+  // barrier of the NGRP warps that share this thread's rows (same TMEM lane quarter of the same group)
+  auto rows_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(3 + gi * 4 + (warp & 3)), "n"(NGRP * 32) : "memory"); };
   const int k = blockIdx.y;                               // learner
   const ActorParams& P = a.params[k];
   const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.bar[gi]), bar_w = (uint32_t)__cvta_generic_to_shared(&s.bar_w);
@@ -233,13 +372,34 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
   const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
   const bool quarter_on = q * 32 < RT;                     // warp-uniform: a half-full tile fills lane quarters 0 and 1
   const long long n_tiles = (a.E + RT - 1) / RT;
-  for (long long tile = (long long)blockIdx.x * GROUPS + gi; tile < n_tiles; tile += (long long)gridDim.x * GROUPS) {
+  const long long tile0 = (long long)blockIdx.x * GROUPS + gi, tile_step = (long long)gridDim.x * GROUPS;
+  // Column group OPG builds the next tile's layer-1 operand and starts layer 1 while column group 0 is still in the head
+  // of the previous tile; the row's obs_code is fetched one tile ahead (its DRAM latency hides behind the tile in flight)
+  constexpr int OPG = NGRP - 1;
+  auto op_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(11 + gi), "n"(128) : "memory"); };
+  unsigned long long code_next = 0ull;
+  if (cg == OPG && quarter_on && m < RT && tile0 < n_tiles && tile0 * RT + m < a.E) code_next = a.obs_code[tile0 * RT + m];
+  int par = 0;                                             // tile parity of this group (maskbits / noise buffer)
+  for (long long tile = tile0; tile < n_tiles; tile += tile_step, par ^= 1) {
     const long long e = tile * RT + m;
     const bool live = quarter_on && m < RT && e < a.E;
 
     // ---- layer-1 operand: the row's special cells (delta against the template, which is 0 on every active cell)
-    if (cg == 0 && live) {
-      const unsigned long long code = a.obs_code[e];
+    if (cg == OPG) {
+    const unsigned long long code = code_next;
+    if (quarter_on && m < RT) {
+      const long long en = e + tile_step * RT;
+      if (tile + tile_step < n_tiles && en < a.E) code_next = a.obs_code[en];
+    }
+    // ... and the row's action mask for the head (9 bytes -> 9 bits)
+    if (live && a.action_mask) {
+      const int8_t* mk = a.action_mask + (e * a.nl + k) * NACT;
+      uint32_t bits = 0u;
+#pragma unroll
+      for (int o = 0; o < NACT; ++o) bits |= (mk[o] != 0 ? 1u : 0u) << o;
+      s.maskbits[gi][par][m] = (uint16_t)bits;
+    }
+    if (live) {
       const uint32_t cellsw = (uint32_t)code, apples = (uint32_t)(code >> 32) & 3u;
       const bool fresh = (code >> 34) & 1ull;
       const bool apple_on = (a.kind == GW_ENV_MULTI) ? ((apples >> k) & 1u) : (apples & 1u);
@@ -260,81 +420,52 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // operand -> visible to the tensor-core proxy
     asm volatile("tcgen05.fence::before_thread_sync;");
-    group_sync();
+    op_sync();                                                       // the four warps of this column group
     asm volatile("tcgen05.fence::after_thread_sync;");
 
     // ---- layer 1 on the tensor cores: D0[128x128] (TMEM columns 0..127) = A[128 x cells] * W1^T
-    if (lt == 0) {
+    if (lt == OPG * 128) {
       if (w_pending) mbar_wait(bar_w, 0u);
       mma_k16(tmem, a_addr, w1_addr, cells / 16);
       // completion of all prior MMAs arrives on the mbarrier (implies tcgen05.fence::before_thread_sync)
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
     }
+    }
     w_pending = false;
-    // ---- meanwhile: the random words of the head (9 Gumbel uniforms + 9 x 2 Box-Muller uniforms per row, a pure function
-    // of seed / env / learner / step), 512 / RT threads per row
+    // ---- meanwhile: the head's noise (9 Gumbel values + 5 Box-Muller pairs per row, a pure function of seed / env /
+    // learner / step), TPG / RT threads per row; Philox call c of a row yields: c = 0, 1: Gumbel 4c..4c+3; c = 2: Gumbel 8
+    // and normals 0, 1; c = 3: normals 2..5; c = 4: normals 6..8
     if (a.gumbel | a.explore) {
       const int tpr = TPG / RT, rr = lt / tpr;
       const long long er = tile * RT + rr;
-      const int n_calls = a.explore ? 7 : 3;
+      const int n_calls = a.explore ? 5 : 3;
       if (er < a.E)
         for (int c = lt % tpr; c < n_calls; c += tpr) {
           const unsigned long long ge = (unsigned long long)(a.env_id_base + er);
           uint32_t w[4] = {(uint32_t)ge, (uint32_t)(ge >> 32) ^ ((uint32_t)k << 24) ^ ((uint32_t)c << 28),
                            a.step_lo, a.step_hi ^ 0xAC70u};
           gw::philox4x32(w, a.seed_lo, a.seed_hi);
+          float* nz = s.noise[gi][par][rr];
+          if (c < 2) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) s.rnd[gi][rr][4 * c + u] = w[u];
+            for (int u = 0; u < 4; ++u) nz[4 * c + u] = gumbel_from(w[u]);
+          } else if (c == 2) {
+            nz[8] = gumbel_from(w[0]);
+            if (a.explore) { const float2 g = gauss_pair_from(w[2], w[3]); nz[9] = g.x; nz[10] = g.y; }
+          } else {
+            const float2 g0 = gauss_pair_from(w[0], w[1]), g1 = gauss_pair_from(w[2], w[3]);
+            nz[4 * c - 1] = g0.x; nz[4 * c] = g0.y; nz[4 * c + 1] = g1.x;
+            if (c == 3) nz[4 * c + 2] = g1.y;
+          }
         }
     }
-    float acc[CPG];
-    float mu_p = 0.f, sq_p = 0.f;
     mbar_wait(bar, phase);
     phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    // ---- LayerNorm 1 + ReLU -> operand of layer 2 (this thread: 32 columns of its row)
-    if (quarter_on) {
-#pragma unroll
-      for (int c0 = 0; c0 < CPG; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + (uint32_t)(col0 + c0), r);
-#pragma unroll
-        for (int u = 0; u < 32; ++u) {
-          acc[c0 + u] = __uint_as_float(r[u]) + s.c1[col0 + c0 + u];
-          mu_p += acc[c0 + u];
-          sq_p = fmaf(acc[c0 + u], acc[c0 + u], sq_p);
-        }
-      }
-      s.part[gi][cg][m] = make_float2(mu_p, sq_p);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    group_sync();                                       // partial sums of the four column groups; layer 1 has read its operand
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    if (quarter_on) {
-      float su = 0.f, sq = 0.f;
-#pragma unroll
-      for (int g = 0; g < NGRP; ++g) { const float2 pp = s.part[gi][g][m]; su += pp.x; sq += pp.y; }
-      const float mu = su * (1.0f / HID);
-      const float rs = rsqrtf(fmaxf(sq * (1.0f / HID) - mu * mu, 0.f) + 1e-5f);
-      const float nmr = -mu * rs;
-#pragma unroll
-      for (int c8 = 0; c8 < CPG; c8 += 8) {                // one 16-byte core-matrix row per 8 columns
-        const float4 g0 = *reinterpret_cast<const float4*>(&s.ln1_g[col0 + c8]), g1 = *reinterpret_cast<const float4*>(&s.ln1_g[col0 + c8 + 4]);
-        const float4 b0 = *reinterpret_cast<const float4*>(&s.ln1_b[col0 + c8]), b1 = *reinterpret_cast<const float4*>(&s.ln1_b[col0 + c8 + 4]);
-        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        uint32_t pk[4];
-#pragma unroll
-        for (int u = 0; u < 8; u += 2) {
-          // (acc - mu) * rs as one fma, then the affine part, ReLU; rows without an env produce zeros
-          const float x0 = live ? fmaxf(fmaf(fmaf(acc[c8 + u], rs, nmr), gg[u], bb[u]), 0.f) : 0.f;
-          const float x1 = live ? fmaxf(fmaf(fmaf(acc[c8 + u + 1], rs, nmr), gg[u + 1], bb[u + 1]), 0.f) : 0.f;
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);          // one cvt for the pair
-          pk[u >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-        }
-        *reinterpret_cast<uint4*>(a_tile + umma_off(m, col0 + c8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
-    }
+    // ---- LayerNorm 1 + ReLU -> operand of layer 2 (this thread: CPG columns of its row)
+    ln_relu_epilogue<CPG, NGRP>(lane_addr + (uint32_t)col0, &s.c1[col0], &s.ln1_g[col0], &s.ln1_b[col0], s.part[gi], cg, m,
+                                a_tile, col0, quarter_on, rows_sync);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;");
     group_sync();
@@ -346,53 +477,13 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
       mma_k16(tmem + (uint32_t)HID, a_addr, w2_addr, HID / 16);
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
     }
-    mu_p = 0.f; sq_p = 0.f;
     mbar_wait(bar, phase);
     phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;");
 
     // ---- LayerNorm 2 + ReLU -> operand of layer 3 (again this thread's columns of its row, again in the operand tile)
-    if (quarter_on) {
-#pragma unroll
-      for (int c0 = 0; c0 < CPG; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + (uint32_t)(HID + col0 + c0), r);
-#pragma unroll
-        for (int u = 0; u < 32; ++u) {
-          acc[c0 + u] = __uint_as_float(r[u]) + s.b2[col0 + c0 + u];
-          mu_p += acc[c0 + u];
-          sq_p = fmaf(acc[c0 + u], acc[c0 + u], sq_p);
-        }
-      }
-      s.part[gi][cg][m] = make_float2(mu_p, sq_p);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    group_sync();                                       // partial sums of the column groups; layer 2 has read its operand
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    if (quarter_on) {
-      float su = 0.f, sq = 0.f;
-#pragma unroll
-      for (int g = 0; g < NGRP; ++g) { const float2 pp = s.part[gi][g][m]; su += pp.x; sq += pp.y; }
-      const float mu = su * (1.0f / HID);
-      const float rs = rsqrtf(fmaxf(sq * (1.0f / HID) - mu * mu, 0.f) + 1e-5f);
-      const float nmr = -mu * rs;
-#pragma unroll
-      for (int c8 = 0; c8 < CPG; c8 += 8) {                // one 16-byte core-matrix row per 8 columns
-        const float4 g0 = *reinterpret_cast<const float4*>(&s.ln2_g[col0 + c8]), g1 = *reinterpret_cast<const float4*>(&s.ln2_g[col0 + c8 + 4]);
-        const float4 b0 = *reinterpret_cast<const float4*>(&s.ln2_b[col0 + c8]), b1 = *reinterpret_cast<const float4*>(&s.ln2_b[col0 + c8 + 4]);
-        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        uint32_t pk[4];
-#pragma unroll
-        for (int u = 0; u < 8; u += 2) {
-          // (acc - mu) * rs as one fma, then the affine part, ReLU; rows without an env produce zeros
-          const float x0 = live ? fmaxf(fmaf(fmaf(acc[c8 + u], rs, nmr), gg[u], bb[u]), 0.f) : 0.f;
-          const float x1 = live ? fmaxf(fmaf(fmaf(acc[c8 + u + 1], rs, nmr), gg[u + 1], bb[u + 1]), 0.f) : 0.f;
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);          // one cvt for the pair
-          pk[u >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-        }
-        *reinterpret_cast<uint4*>(a_tile + umma_off(m, col0 + c8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
-    }
+    ln_relu_epilogue<CPG, NGRP>(lane_addr + (uint32_t)(HID + col0), &s.b2[col0], &s.ln2_g[col0], &s.ln2_b[col0], s.part[gi], cg, m,
+                                a_tile, col0, quarter_on, rows_sync);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;");
     group_sync();
@@ -423,7 +514,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
       // included) + Gaussian exploration noise (training), both from the Philox words drawn above
       if (a.gumbel) {
 #pragma unroll
-        for (int o = 0; o < NACT; ++o) logit[o] += gumbel_from(s.rnd[gi][m][o]);
+        for (int o = 0; o < NACT; ++o) logit[o] += s.noise[gi][par][m][o];
       }
       float mx = logit[0];
 #pragma unroll
@@ -434,23 +525,21 @@ __global__ void __launch_bounds__(THREADS, 1) actor_forward_kernel(FwdArgs a) {
       const float inv = 1.0f / den;
       int best = 0;
       float best_v = -1e30f;
-      const int8_t* mk = a.action_mask ? a.action_mask + (e * a.nl + k) * NACT : nullptr;
+      const uint32_t mbits = a.action_mask ? (uint32_t)s.maskbits[gi][par][m] : 0x1FFu;
       float* out = a.cont + (e * a.nl + k) * NACT;
 #pragma unroll
       for (int o = 0; o < NACT; ++o) {
         float v = pr[o] * inv;
-        if (a.explore) {
-          const float g = gauss_from(s.rnd[gi][m][9 + 2 * o], s.rnd[gi][m][10 + 2 * o]);
-          v = fminf(fmaxf(v + a.mean_noise + a.expl_noise * g, 0.f), 1.f);
-        }
+        if (a.explore) v = fminf(fmaxf(v + a.mean_noise + a.expl_noise * s.noise[gi][par][m][9 + o], 0.f), 1.f);
         out[o] = v;
-        const bool ok = mk == nullptr || mk[o] != 0;
+        const bool ok = (mbits >> o) & 1u;
         if (ok && v > best_v) { best_v = v; best = o; }
       }
       a.ids[e * a.nl + k] = (int8_t)best;
     }
-    // part / rnd / the operand tile are rewritten by the next tile only behind barriers that every warp reaches
-    // after it is done with them
+    // Column group 0 joins the next tile at its noise phase, the others are already there (column group OPG has built
+    // the operand and started layer 1).  maskbits / noise of this tile are rewritten two tiles on, the operand tile and
+    // part only behind barriers that every warp reaches after it is done with them.
   }
   if (w_pending && tid == 0) mbar_wait(bar_w, 0u);         // a CTA whose first group has no tile must not exit with the copies in flight
 
@@ -642,10 +731,10 @@ int gw_actor_forward(gw_actor* a, int64_t num_envs, const uint64_t* obs_code, co
   if (two && gwa::smem_bytes<2>(f.cpo) <= (size_t)227 * 1024) {
     const long long pairs = (tiles + 1) / 2;
     dim3 grid((unsigned)(pairs < cap ? pairs : cap), (unsigned)h->cfg.n_learners);
-    gwa::actor_forward_kernel<2><<<grid, gwa::THREADS, gwa::smem_bytes<2>(f.cpo), static_cast<cudaStream_t>(stream)>>>(f);
+    gwa::actor_forward_kernel<2><<<grid, gwa::threads_of(2), gwa::smem_bytes<2>(f.cpo), static_cast<cudaStream_t>(stream)>>>(f);
   } else {
     dim3 grid((unsigned)(tiles < cap ? tiles : cap), (unsigned)h->cfg.n_learners);
-    gwa::actor_forward_kernel<1><<<grid, gwa::THREADS, gwa::smem_bytes<1>(f.cpo), static_cast<cudaStream_t>(stream)>>>(f);
+    gwa::actor_forward_kernel<1><<<grid, gwa::threads_of(1), gwa::smem_bytes<1>(f.cpo), static_cast<cudaStream_t>(stream)>>>(f);
   }
   GW_CUDA(h, cudaGetLastError());
   h->launches += 1;
