@@ -11,14 +11,20 @@
 //            tcgen05.mma (M=128, N=128, K=16, bf16 -> fp32) against W1 (bf16, UMMA layout, one TMA bulk copy) accumulate
 //            in TMEM columns 0..127.
 //   LN 1     warps that share a TMEM lane quarter (a warp's lanes are those of its id mod 4) split the 128 columns
-//            (tcgen05.ld, thread = row): + c1, LayerNorm (partial sums joined through shared memory), ReLU, bf16 into the
-//            A operand of layer 2 (UMMA K-major core matrices; it reuses the space of the layer-1 operand).
+//            (tcgen05.ld, thread = row) and make two passes over the accumulator, both in packed fp32 pairs (FADD2 /
+//            FFMA2): + c1 and the statistics (partial sums joined through shared memory by the warps that share the rows),
+//            then + c1 again, normalise, affine, ReLU inside the bf16 conversion, into the A operand of layer 2 (UMMA
+//            K-major core matrices; it reuses the space of the layer-1 operand).  A chunk's TMEM load is in flight while
+//            the previous chunk is processed.
 //   layer 2  [128 x 128] x W2^T: 8 tcgen05.mma into TMEM columns 128..255.
 //   LN 2     the same column split: + b2, LayerNorm, ReLU, bf16 into the A operand of layer 3 (same space again).
 //   layer 3  [128 x 128] x W3p^T with W3 padded from 9 to 16 outputs: 8 tcgen05.mma with N = 16 into TMEM columns 0..15;
 //            the operand tile is cleared for the next tile once they have completed.
 //   head     the first column group reads the 9 logits of its row (+ b3) and finishes Gumbel softmax / exploration noise /
-//            clip / mask / arg-max.  The Philox words of the noise are drawn by all threads while layer 1 runs.
+//            clip / mask / arg-max.  The noise (9 Gumbel values, 9 normals from 5 Box-Muller pairs: 5 Philox calls per
+//            row) is drawn and transformed by all threads while layer 1 runs; the last column group builds the next
+//            tile's operand (obs_code fetched one tile ahead), packs its action mask into 9 bits and starts its layer 1
+//            while the first one is still in the head.
 // Small batches use half-full tiles (64 rows) so that the grid covers the machine; large ones keep two tiles in flight per
 // CTA (two 8-warp groups out of phase, see Fixed<GROUPS>).
 // sm_100a only (tcgen05 / TMEM); descriptors follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
@@ -126,13 +132,15 @@ struct Fixed {
 template <int GROUPS>
 __host__ __device__ inline size_t smem_bytes(int cells) { return (size_t)(GROUPS + 1) * ROWS * cells * 2 + sizeof(Fixed<GROUPS>) + 1024; }
 
+// uniform in (0, 1) from the top 23 bits of a word, without an integer-to-float conversion: [1, 2) - (1 - 2^-24)
+__device__ __forceinline__ float unit_from(uint32_t w) { return __uint_as_float(0x3F800000u | (w >> 9)) - 0.99999994f; }
 __device__ __forceinline__ float gumbel_from(uint32_t w) {
-  const float u = fmaxf(((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f), 1e-20f);
-  return -__logf(-__logf(u) + 1e-20f);
+  return -__logf(-__logf(unit_from(w)) + 1e-20f);
 }
 __device__ __forceinline__ float2 gauss_pair_from(uint32_t a, uint32_t b) {     // Box-Muller, both outputs
-  const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float r = sqrtf(-2.0f * __logf(u1));
+  const float u1 = unit_from(a), u2 = unit_from(b);
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));      // noise: MUFU.SQRT is plenty
   float sn, cs;
   __sincosf(6.283185307f * u2, &sn, &cs);
   return make_float2(r * cs, r * sn);
@@ -308,7 +316,8 @@ __device__ __forceinline__ void mma_k16(uint32_t tmem_d, uint32_t a_addr, uint32
 
 template <int GROUPS>
 __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(FwdArgs a) {
-  constexpr int THREADS = threads_of(GROUPS), TPG = THREADS / GROUPS, NGRP = Fixed<GROUPS>::NGRP, CPG = HID / NGRP;
+  constexpr int THREADS = threads_of(GROUPS), TPG = THREADS / GROUPS, TSH = TPG == 512 ? 2 : 1,   // log2(TPG / ROWS)
+                 NGRP = Fixed<GROUPS>::NGRP, CPG = HID / NGRP;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int cells = a.cpo;                                 // K of layer 1: a multiple of 16 (H x 16)
   const uint32_t op_bytes = (uint32_t)ROWS * cells * 2;
@@ -436,11 +445,11 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
     // learner / step), TPG / RT threads per row; Philox call c of a row yields: c = 0, 1: Gumbel 4c..4c+3; c = 2: Gumbel 8
     // and normals 0, 1; c = 3: normals 2..5; c = 4: normals 6..8
     if (a.gumbel | a.explore) {
-      const int tpr = TPG / RT, rr = lt / tpr;
+      const int tsh = RT == ROWS ? TSH : TSH + 1, tpr = 1 << tsh, rr = lt >> tsh;   // RT is ROWS or ROWS / 2: no division
       const long long er = tile * RT + rr;
       const int n_calls = a.explore ? 5 : 3;
       if (er < a.E)
-        for (int c = lt % tpr; c < n_calls; c += tpr) {
+        for (int c = lt & (tpr - 1); c < n_calls; c += tpr) {
           const unsigned long long ge = (unsigned long long)(a.env_id_base + er);
           uint32_t w[4] = {(uint32_t)ge, (uint32_t)(ge >> 32) ^ ((uint32_t)k << 24) ^ ((uint32_t)c << 28),
                            a.step_lo, a.step_hi ^ 0xAC70u};
@@ -511,7 +520,7 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
     asm volatile("tcgen05.fence::after_thread_sync;");
     if (live && cg == 0) {
       // GumbelSoftmax head (the reference's output activation draws fresh Gumbel noise on EVERY forward, evaluation
-      // included) + Gaussian exploration noise (training), both from the Philox words drawn above
+      // included) + Gaussian exploration noise (training), both drawn above
       if (a.gumbel) {
 #pragma unroll
         for (int o = 0; o < NACT; ++o) logit[o] += s.noise[gi][par][m][o];
