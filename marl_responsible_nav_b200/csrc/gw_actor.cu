@@ -43,12 +43,17 @@
 namespace gwa {
 
 constexpr int HID = 128, NACT = GW_N_ACTIONS, ROWS = 128, MAX_CELLS = GW_MAX_H * GW_W;
+// Layers 1 and 2 carry their bias through the GEMM: one more K step (16 columns) whose first two columns of A are 1.0 and
+// whose first two columns of W hold the bias split into a bf16 head and a bf16 remainder (hi + lo = the fp32 value to
+// 2^-17): the LayerNorm epilogues read the accumulator as it is, no bias vector in shared memory.
+constexpr int KB = 16;
+constexpr uint32_t ONES2 = 0x3F803F80u;             // bf16 (1.0, 1.0)
 
 struct ActorParams {                     // device-resident, per learner
-  alignas(16) __nv_bfloat16 w1_umma[HID * MAX_CELLS];   // W1 [out n][in cell] in the canonical K-major core-matrix layout
+  alignas(16) __nv_bfloat16 w1_umma[HID * (MAX_CELLS + KB)];   // W1 [out n][in cell] in the canonical K-major core-matrix layout; columns cells, cells + 1: c1 (hi, lo)
   float c1[HID];                         // b1 + W1 * template row (fp32)
   float ln1_g[HID], ln1_b[HID];
-  alignas(16) __nv_bfloat16 w2_umma[HID * HID];   // W2 [out n][in k] in the canonical K-major core-matrix layout
+  alignas(16) __nv_bfloat16 w2_umma[HID * (HID + KB)];   // W2 [out n][in k] in the canonical K-major core-matrix layout; columns 128, 129: b2 (hi, lo)
   float b2[HID], ln2_g[HID], ln2_b[HID];
   alignas(16) __nv_bfloat16 w3_umma[16 * HID];   // W3 [out o, padded to 16][in j] in the canonical K-major core-matrix layout
   float b3[NACT];
@@ -118,10 +123,10 @@ __host__ __device__ constexpr int threads_of(int /*groups*/) { return 512; }
 template <int GROUPS>
 struct Fixed {
   static constexpr int NGRP = threads_of(GROUPS) / GROUPS / 128;         // column groups of the epilogues (warps sharing a TMEM lane quarter)
-  alignas(1024) uint8_t w2[HID * HID * 2];
+  alignas(1024) uint8_t w2[HID * (HID + KB) * 2];
   alignas(128) uint8_t w3[16 * HID * 2];             // W3 padded to 16 outputs, bf16, UMMA layout
   float b3[NACT];
-  alignas(16) float c1[HID], ln1_g[HID], ln1_b[HID], b2[HID], ln2_g[HID], ln2_b[HID];
+  alignas(16) float ln1_g[HID], ln1_b[HID], ln2_g[HID], ln2_b[HID];
   alignas(8) float2 part[GROUPS][NGRP][ROWS];       // LayerNorm partial (sum, sum of squares) per column group and row
   float noise[GROUPS][2][ROWS][19];                 // the head's noise per row: 9 Gumbel values, 9 standard normals (odd stride: no bank
                                                     // conflicts), double-buffered over consecutive tiles like maskbits
@@ -129,8 +134,10 @@ struct Fixed {
   alignas(8) unsigned long long bar[GROUPS], bar_w; // MMA completion per group; arrival of W1 / W2
   uint32_t tmem_base;
 };
+// K extent of an operand tile: layer 1 needs cells + KB columns, layer 2 (same space) HID + KB
+__host__ __device__ inline int op_k(int cells) { return (cells > HID ? cells : HID) + KB; }
 template <int GROUPS>
-__host__ __device__ inline size_t smem_bytes(int cells) { return (size_t)(GROUPS + 1) * ROWS * cells * 2 + sizeof(Fixed<GROUPS>) + 1024; }
+__host__ __device__ inline size_t smem_bytes(int cells) { return (size_t)(GROUPS + 1) * ROWS * op_k(cells) * 2 + sizeof(Fixed<GROUPS>) + 1024; }
 
 // uniform in (0, 1) from the top 23 bits of a word, without an integer-to-float conversion: [1, 2) - (1 - 2^-24)
 __device__ __forceinline__ float unit_from(uint32_t w) { return __uint_as_float(0x3F800000u | (w >> 9)) - 0.99999994f; }
@@ -201,10 +208,6 @@ __device__ __forceinline__ uint32_t relu_bf16x2(uint64_t v) {
   return d;
 }
 
-// One LayerNorm + ReLU epilogue of this thread's CPG columns of its row: TMEM accumulator (+ bias) -> statistics (partial
-// sums of the column groups joined through shared memory) -> normalise, affine, ReLU, bf16 -> the next layer's A operand.
-// Rows without an env are processed like any other (their accumulator rows are finite: zero operand rows + bias) and
-// their results are never read: a row of A only reaches the same row of D.
 // tcgen05.ld without the wait, and the wait with the registers as in/out operands (what follows depends on it): a
 // chunk's load is in flight while the previous chunk is processed
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
@@ -222,26 +225,25 @@ __device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
                :: "memory");
 }
 
-// One LayerNorm + ReLU epilogue of this thread's CPG columns of its row: TMEM accumulator (+ bias) -> statistics (partial
-// sums of the column groups joined through shared memory; `sync` joins the warps that share the rows) -> second pass over
-// the accumulator (re-read from TMEM: keeping the row in registers across the barrier spills at 128 registers per
-// thread and measured 40 % slower) -> normalise, affine, ReLU, bf16 -> the next layer's A operand.
-// Rows without an env are processed like any other (their accumulator rows are finite: zero operand rows + bias) and
-// their results are never read: a row of A only reaches the same row of D.
+// One LayerNorm + ReLU epilogue of this thread's CPG columns of its row: TMEM accumulator (the layer's bias is already in
+// it, see KB) -> statistics (partial sums of the column groups joined through shared memory; `sync` joins the warps that
+// share the rows) -> second pass over the accumulator (re-read from TMEM: keeping the row in registers across the barrier
+// spills at 128 registers per thread and measured 40 % slower) -> normalise, affine, ReLU, bf16 -> the next layer's A
+// operand; ONES: this thread also sets the next layer's bias columns (K = 128, 129) of its row to 1.0.
+// Rows without an env are processed like any other (their accumulator rows are zero: zero operand rows) and their
+// results are never read: a row of A only reaches the same row of D.
 template <int CPG, int NGRP, class Sync>
-__device__ __forceinline__ void ln_relu_epilogue(uint32_t taddr, const float* __restrict__ bias, const float* __restrict__ gamma,
-                                                 const float* __restrict__ beta, float2 (*part)[ROWS], int cg, int m,
-                                                 uint8_t* a_tile, int col0, bool on, Sync&& sync) {
+__device__ __forceinline__ void ln_relu_epilogue(uint32_t taddr, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                 float2 (*part)[ROWS], int cg, int m, uint8_t* a_tile, int col0, bool on,
+                                                 bool ones, Sync&& sync) {
   static_assert(CPG % 32 == 0, "two chunks of 16 columns in flight");
   if (on) {
     uint64_t sa2 = 0ull, sb2 = 0ull, qa2 = 0ull, qb2 = 0ull;     // (0.f, 0.f): two chains each for the sum and the sum of squares
     uint32_t ra[16], rb[16];
-    auto stats = [&](const uint32_t (&r)[16], int c0) {
+    auto stats = [&](const uint32_t (&r)[16]) {
 #pragma unroll
       for (int u = 0; u < 16; u += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(&bias[c0 + u]);
-        const uint64_t x0 = add2(pack2(r[u], r[u + 1]), pack2f(b4.x, b4.y));
-        const uint64_t x1 = add2(pack2(r[u + 2], r[u + 3]), pack2f(b4.z, b4.w));
+        const uint64_t x0 = pack2(r[u], r[u + 1]), x1 = pack2(r[u + 2], r[u + 3]);
         sa2 = add2(sa2, x0); qa2 = fma2(x0, x0, qa2);
         sb2 = add2(sb2, x1); qb2 = fma2(x1, x1, qb2);
       }
@@ -251,10 +253,10 @@ __device__ __forceinline__ void ln_relu_epilogue(uint32_t taddr, const float* __
     for (int c0 = 0; c0 < CPG; c0 += 32) {
       tmem_wait16(ra);
       tmem_ld16_issue(taddr + (uint32_t)(c0 + 16), rb);
-      stats(ra, c0);
+      stats(ra);
       tmem_wait16(rb);
       if (c0 + 32 < CPG) tmem_ld16_issue(taddr + (uint32_t)(c0 + 32), ra);
-      stats(rb, c0 + 16);
+      stats(rb);
     }
     float s0, s1, q0, q1;
     unpack2(add2(sa2, sb2), s0, s1); unpack2(add2(qa2, qb2), q0, q1);
@@ -264,6 +266,10 @@ __device__ __forceinline__ void ln_relu_epilogue(uint32_t taddr, const float* __
   if (on) {
     uint32_t ra[16], rb[16];
     tmem_ld16_issue(taddr, ra);                          // in flight while the statistics are joined
+    if (ones) {                                          // K = 128..143 of the row: (1, 1, 0, ...) over what layer 1 had there
+      *reinterpret_cast<uint4*>(a_tile + umma_off(m, HID)) = make_uint4(ONES2, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(a_tile + umma_off(m, HID + 8)) = make_uint4(0u, 0u, 0u, 0u);
+    }
     float su = 0.f, sq = 0.f;
 #pragma unroll
     for (int g = 0; g < NGRP; ++g) { const float2 pp = part[g][m]; su += pp.x; sq += pp.y; }
@@ -275,16 +281,13 @@ __device__ __forceinline__ void ln_relu_epilogue(uint32_t taddr, const float* __
 #pragma unroll
       for (int u = 0; u < 16; u += 8) {                  // one 16-byte core-matrix row per 8 columns
         const int c8 = c0 + u;
-        const float4 i0 = *reinterpret_cast<const float4*>(&bias[c8]), i1 = *reinterpret_cast<const float4*>(&bias[c8 + 4]);
         const float4 g0 = *reinterpret_cast<const float4*>(&gamma[c8]), g1 = *reinterpret_cast<const float4*>(&gamma[c8 + 4]);
         const float4 b0 = *reinterpret_cast<const float4*>(&beta[c8]), b1 = *reinterpret_cast<const float4*>(&beta[c8 + 4]);
-        const uint64_t x0 = add2(pack2(r[u], r[u + 1]), pack2f(i0.x, i0.y)), x1 = add2(pack2(r[u + 2], r[u + 3]), pack2f(i0.z, i0.w));
-        const uint64_t x2 = add2(pack2(r[u + 4], r[u + 5]), pack2f(i1.x, i1.y)), x3 = add2(pack2(r[u + 6], r[u + 7]), pack2f(i1.z, i1.w));
         // (x - mu) * rs as one fma, then the affine part; ReLU inside the conversion
-        const uint32_t p0 = relu_bf16x2(fma2(fma2(x0, rs2, nmr2), pack2f(g0.x, g0.y), pack2f(b0.x, b0.y)));
-        const uint32_t p1 = relu_bf16x2(fma2(fma2(x1, rs2, nmr2), pack2f(g0.z, g0.w), pack2f(b0.z, b0.w)));
-        const uint32_t p2 = relu_bf16x2(fma2(fma2(x2, rs2, nmr2), pack2f(g1.x, g1.y), pack2f(b1.x, b1.y)));
-        const uint32_t p3 = relu_bf16x2(fma2(fma2(x3, rs2, nmr2), pack2f(g1.z, g1.w), pack2f(b1.z, b1.w)));
+        const uint32_t p0 = relu_bf16x2(fma2(fma2(pack2(r[u], r[u + 1]), rs2, nmr2), pack2f(g0.x, g0.y), pack2f(b0.x, b0.y)));
+        const uint32_t p1 = relu_bf16x2(fma2(fma2(pack2(r[u + 2], r[u + 3]), rs2, nmr2), pack2f(g0.z, g0.w), pack2f(b0.z, b0.w)));
+        const uint32_t p2 = relu_bf16x2(fma2(fma2(pack2(r[u + 4], r[u + 5]), rs2, nmr2), pack2f(g1.x, g1.y), pack2f(b1.x, b1.y)));
+        const uint32_t p3 = relu_bf16x2(fma2(fma2(pack2(r[u + 6], r[u + 7]), rs2, nmr2), pack2f(g1.z, g1.w), pack2f(b1.z, b1.w)));
         *reinterpret_cast<uint4*>(a_tile + umma_off(m, col0 + c8)) = make_uint4(p0, p1, p2, p3);
       }
     };
@@ -320,7 +323,8 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
                  NGRP = Fixed<GROUPS>::NGRP, CPG = HID / NGRP;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int cells = a.cpo;                                 // K of layer 1: a multiple of 16 (H x 16)
-  const uint32_t op_bytes = (uint32_t)ROWS * cells * 2;
+  const uint32_t op_bytes = (uint32_t)ROWS * op_k(cells) * 2;     // operand tile incl. the bias K step
+  const uint32_t w1_bytes = (uint32_t)ROWS * (cells + KB) * 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gi = tid / TPG, lt = tid % TPG;                // group, thread within the group
   uint8_t* const a_tile = smem_raw + (size_t)gi * op_bytes;
@@ -347,11 +351,11 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
     for (int g = 0; g < GROUPS; ++g) mbar_init((uint32_t)__cvta_generic_to_shared(&s.bar[g]), 1);
     mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(op_bytes + (uint32_t)(HID * HID * 2 + 16 * HID * 2)) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(w1_bytes + (uint32_t)(HID * (HID + KB) * 2 + 16 * HID * 2)) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"((uint32_t)__cvta_generic_to_shared(w1_tile)), "l"(P.w1_umma), "r"(op_bytes), "r"(bar_w) : "memory");
+                 ::"r"((uint32_t)__cvta_generic_to_shared(w1_tile)), "l"(P.w1_umma), "r"(w1_bytes), "r"(bar_w) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"((uint32_t)__cvta_generic_to_shared(s.w2)), "l"(P.w2_umma), "n"(HID * HID * 2), "r"(bar_w) : "memory");
+                 ::"r"((uint32_t)__cvta_generic_to_shared(s.w2)), "l"(P.w2_umma), "n"(HID * (HID + KB) * 2), "r"(bar_w) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"((uint32_t)__cvta_generic_to_shared(s.w3)), "l"(P.w3_umma), "n"(16 * HID * 2), "r"(bar_w) : "memory");
   }
@@ -359,8 +363,8 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
     for (int i = lt; i < (int)(op_bytes / 16); i += TPG) reinterpret_cast<uint4*>(a_tile)[i] = make_uint4(0, 0, 0, 0);
     if (tid < NACT) s.b3[tid] = P.b3[tid];
     if (tid < HID) {
-      s.c1[tid] = P.c1[tid]; s.ln1_g[tid] = P.ln1_g[tid]; s.ln1_b[tid] = P.ln1_b[tid];
-      s.b2[tid] = P.b2[tid]; s.ln2_g[tid] = P.ln2_g[tid]; s.ln2_b[tid] = P.ln2_b[tid];
+      s.ln1_g[tid] = P.ln1_g[tid]; s.ln1_b[tid] = P.ln1_b[tid];
+      s.ln2_g[tid] = P.ln2_g[tid]; s.ln2_b[tid] = P.ln2_b[tid];
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
@@ -426,6 +430,7 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
         if (i < a.n && (int)c < cells) *reinterpret_cast<__nv_bfloat16*>(a_tile + umma_off(m, (int)c)) = __float2bfloat16(here ? v + 9.0f : v);
       }
       if (apple_on && !covered && (int)apple < cells) *reinterpret_cast<__nv_bfloat16*>(a_tile + umma_off(m, (int)apple)) = __float2bfloat16(9.0f);
+      *reinterpret_cast<uint32_t*>(a_tile + umma_off(m, cells)) = ONES2;       // the bias columns: c1 = hi + lo
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // operand -> visible to the tensor-core proxy
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -435,7 +440,7 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
     // ---- layer 1 on the tensor cores: D0[128x128] (TMEM columns 0..127) = A[128 x cells] * W1^T
     if (lt == OPG * 128) {
       if (w_pending) mbar_wait(bar_w, 0u);
-      mma_k16(tmem, a_addr, w1_addr, cells / 16);
+      mma_k16(tmem, a_addr, w1_addr, cells / 16 + 1);
       // completion of all prior MMAs arrives on the mbarrier (implies tcgen05.fence::before_thread_sync)
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
     }
@@ -473,8 +478,8 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
     asm volatile("tcgen05.fence::after_thread_sync;");
 
     // ---- LayerNorm 1 + ReLU -> operand of layer 2 (this thread: CPG columns of its row)
-    ln_relu_epilogue<CPG, NGRP>(lane_addr + (uint32_t)col0, &s.c1[col0], &s.ln1_g[col0], &s.ln1_b[col0], s.part[gi], cg, m,
-                                a_tile, col0, quarter_on, rows_sync);
+    ln_relu_epilogue<CPG, NGRP>(lane_addr + (uint32_t)col0, &s.ln1_g[col0], &s.ln1_b[col0], s.part[gi], cg, m,
+                                a_tile, col0, quarter_on, cg == 0, rows_sync);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;");
     group_sync();
@@ -483,7 +488,7 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
     // ---- layer 2: D1[128x128] (TMEM columns 128..255) = A2[128x128] * W2^T.  (Rows RT..127 of a half-full tile hold
     // whatever the layer-1 operand held there -- zeros: they only reach accumulator rows nobody reads.)
     if (lt == 0) {
-      mma_k16(tmem + (uint32_t)HID, a_addr, w2_addr, HID / 16);
+      mma_k16(tmem + (uint32_t)HID, a_addr, w2_addr, HID / 16 + 1);
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
     }
     mbar_wait(bar, phase);
@@ -491,8 +496,8 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
     asm volatile("tcgen05.fence::after_thread_sync;");
 
     // ---- LayerNorm 2 + ReLU -> operand of layer 3 (again this thread's columns of its row, again in the operand tile)
-    ln_relu_epilogue<CPG, NGRP>(lane_addr + (uint32_t)(HID + col0), &s.b2[col0], &s.ln2_g[col0], &s.ln2_b[col0], s.part[gi], cg, m,
-                                a_tile, col0, quarter_on, rows_sync);
+    ln_relu_epilogue<CPG, NGRP>(lane_addr + (uint32_t)(HID + col0), &s.ln2_g[col0], &s.ln2_b[col0], s.part[gi], cg, m,
+                                a_tile, col0, quarter_on, false, rows_sync);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;");
     group_sync();
@@ -556,6 +561,13 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_all), "n"(GROUPS * 2 * HID));
 }
 
+// bias of output n as the two bf16 columns k0, k0 + 1 of a packed weight matrix: head + remainder
+__host__ __device__ inline void put_bias(__nv_bfloat16* w_umma, int n, int k0, float b) {
+  const __nv_bfloat16 hi = __float2bfloat16(b);
+  w_umma[umma_off(n, k0) / 2] = hi;
+  w_umma[umma_off(n, k0 + 1) / 2] = __float2bfloat16(b - __bfloat162float(hi));
+}
+
 // Weights straight from the trainer's device tensors (torch layout, fp32) into the kernel's packed form: the same
 // arithmetic as pack_weights below (c1 accumulated in double, in cell order), without the trip through the host.
 struct PackArgs {
@@ -584,6 +596,8 @@ __global__ void __launch_bounds__(256) actor_pack_kernel(PackArgs a) {
     for (int cell = 0; cell < cpo; ++cell)
       if (!((a.map_rows[cell >> 4] >> (cell & 15)) & 1)) acc -= (double)W.w1[j * cpo + cell];   // template value -1 on inactive cells
     P.c1[j] = (float)acc;
+    put_bias(P.w1_umma, j, cpo, (float)acc);
+    put_bias(P.w2_umma, j, HID, W.b2[j]);
     P.ln1_g[j] = W.ln1_g[j]; P.ln1_b[j] = W.ln1_b[j];
     P.b2[j] = W.b2[j]; P.ln2_g[j] = W.ln2_g[j]; P.ln2_b[j] = W.ln2_b[j];
     if (j < NACT) P.b3[j] = W.b3[j];
@@ -617,6 +631,8 @@ static int pack_weights(gw_handle* h, const gw_actor_weights* w, int nl, std::ve
         if (!active) acc -= (double)W.w1[j * cpo + cell];              // template value -1 on inactive cells, 0 elsewhere
       }
       P.c1[j] = (float)acc;
+      gwa::put_bias(P.w1_umma, j, cpo, (float)acc);
+      gwa::put_bias(P.w2_umma, j, gwa::HID, W.b2[j]);
       P.ln1_g[j] = W.ln1_g[j]; P.ln1_b[j] = W.ln1_b[j];
       P.b2[j] = W.b2[j]; P.ln2_g[j] = W.ln2_g[j]; P.ln2_b[j] = W.ln2_b[j];
     }
