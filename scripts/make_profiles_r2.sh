@@ -19,3 +19,9 @@ timeout 300 python -m marl_responsible_nav_b200.train --config custom_fear_10 --
 timeout 300 python scripts/bench_rollout.py > gpurun_out/${R}_rollout.log 2>&1
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > gpurun_out/${R}_gpu.txt; nproc >> gpurun_out/${R}_gpu.txt
 ls gpurun_out | grep ${R}_ | wc -l
+# actor kernel alone (CUDA events) and under ncu --set full at 1 M envs x 2 learners (after the plain run has exited 0)
+timeout 200 python scripts/time_actor.py > gpurun_out/${R}_time_actor.log 2>&1
+CMD="python scripts/bench_actor_only.py"
+$CMD > gpurun_out/${R}_actor_plain.log 2>&1 &&
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:actor_forward -s 3 -c 1 -f -o gpurun_out/${R}_actor $CMD > gpurun_out/${R}_actor_ncu.log 2>&1
+ls gpurun_out | grep ${R}_ | wc -l
