@@ -134,8 +134,8 @@ struct Fixed {
   alignas(8) unsigned long long bar[GROUPS], bar_w; // MMA completion per group; arrival of W1 / W2
   uint32_t tmem_base;
 };
-// K extent of an operand tile: layer 1 needs cells + KB columns, layer 2 (same space) HID + KB
-__host__ __device__ inline int op_k(int cells) { return (cells > HID ? cells : HID) + KB; }
+// K extent of the layer-1 operand tile (the only operand in shared memory): cells + the bias K step
+__host__ __device__ inline int op_k(int cells) { return cells + KB; }
 template <int GROUPS>
 __host__ __device__ inline size_t smem_bytes(int cells) { return (size_t)(GROUPS + 1) * ROWS * op_k(cells) * 2 + sizeof(Fixed<GROUPS>) + 1024; }
 
@@ -225,16 +225,26 @@ __device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
                :: "memory");
 }
 
+// 8 packed bf16 pairs (16 K columns of this thread's row) into a TMEM-resident A operand: lane = row, one 32-bit
+// column per pair
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // One LayerNorm + ReLU epilogue of this thread's CPG columns of its row: TMEM accumulator (the layer's bias is already in
 // it, see KB) -> statistics (partial sums of the column groups joined through shared memory; `sync` joins the warps that
 // share the rows) -> second pass over the accumulator (re-read from TMEM: keeping the row in registers across the barrier
 // spills at 128 registers per thread and measured 40 % slower) -> normalise, affine, ReLU, bf16 -> the next layer's A
-// operand; ONES: this thread also sets the next layer's bias columns (K = 128, 129) of its row to 1.0.
+// operand, which lives in TMEM (bf16 pairs, `a_taddr` = its first column in this warp's lane quarter): no shared-memory
+// store, no shared-memory read by the MMA; ONES: this thread also sets the next layer's bias columns (K = 128..143:
+// 1, 1, 0 ...) of its row.
 // Rows without an env are processed like any other (their accumulator rows are zero: zero operand rows) and their
 // results are never read: a row of A only reaches the same row of D.
 template <int CPG, int NGRP, class Sync>
 __device__ __forceinline__ void ln_relu_epilogue(uint32_t taddr, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                 float2 (*part)[ROWS], int cg, int m, uint8_t* a_tile, int col0, bool on,
+                                                 float2 (*part)[ROWS], int cg, int m, uint32_t a_taddr, int col0, bool on,
                                                  bool ones, Sync&& sync) {
   static_assert(CPG % 32 == 0, "two chunks of 16 columns in flight");
   if (on) {
@@ -266,9 +276,9 @@ __device__ __forceinline__ void ln_relu_epilogue(uint32_t taddr, const float* __
   if (on) {
     uint32_t ra[16], rb[16];
     tmem_ld16_issue(taddr, ra);                          // in flight while the statistics are joined
-    if (ones) {                                          // K = 128..143 of the row: (1, 1, 0, ...) over what layer 1 had there
-      *reinterpret_cast<uint4*>(a_tile + umma_off(m, HID)) = make_uint4(ONES2, 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(a_tile + umma_off(m, HID + 8)) = make_uint4(0u, 0u, 0u, 0u);
+    if (ones) {                                          // K = 128..143 of the row: (1, 1, 0, ...)
+      const uint32_t o8[8] = {ONES2, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      tmem_st8(a_taddr + (uint32_t)(HID / 2), o8);
     }
     float su = 0.f, sq = 0.f;
 #pragma unroll
@@ -278,8 +288,9 @@ __device__ __forceinline__ void ln_relu_epilogue(uint32_t taddr, const float* __
     const float nmr = -mu * rs;
     const uint64_t rs2 = pack2f(rs, rs), nmr2 = pack2f(nmr, nmr);
     auto norm = [&](const uint32_t (&r)[16], int c0) {
+      uint32_t pk[8];
 #pragma unroll
-      for (int u = 0; u < 16; u += 8) {                  // one 16-byte core-matrix row per 8 columns
+      for (int u = 0; u < 16; u += 8) {
         const int c8 = c0 + u;
         const float4 g0 = *reinterpret_cast<const float4*>(&gamma[c8]), g1 = *reinterpret_cast<const float4*>(&gamma[c8 + 4]);
         const float4 b0 = *reinterpret_cast<const float4*>(&beta[c8]), b1 = *reinterpret_cast<const float4*>(&beta[c8 + 4]);
@@ -288,8 +299,9 @@ __device__ __forceinline__ void ln_relu_epilogue(uint32_t taddr, const float* __
         const uint32_t p1 = relu_bf16x2(fma2(fma2(pack2(r[u + 2], r[u + 3]), rs2, nmr2), pack2f(g0.z, g0.w), pack2f(b0.z, b0.w)));
         const uint32_t p2 = relu_bf16x2(fma2(fma2(pack2(r[u + 4], r[u + 5]), rs2, nmr2), pack2f(g1.x, g1.y), pack2f(b1.x, b1.y)));
         const uint32_t p3 = relu_bf16x2(fma2(fma2(pack2(r[u + 6], r[u + 7]), rs2, nmr2), pack2f(g1.z, g1.w), pack2f(b1.z, b1.w)));
-        *reinterpret_cast<uint4*>(a_tile + umma_off(m, col0 + c8)) = make_uint4(p0, p1, p2, p3);
+        pk[u / 2] = p0; pk[u / 2 + 1] = p1; pk[u / 2 + 2] = p2; pk[u / 2 + 3] = p3;
       }
+      tmem_st8(a_taddr + (uint32_t)((col0 + c0) / 2), pk);
     };
 #pragma unroll
     for (int c0 = 0; c0 < CPG; c0 += 32) {
@@ -300,6 +312,23 @@ __device__ __forceinline__ void ln_relu_epilogue(uint32_t taddr, const float* __
       if (c0 + 32 < CPG) tmem_ld16_issue(taddr + (uint32_t)(c0 + 32), ra);
       norm(rb, c0 + 16);
     }
+    tmem_st_wait();
+  }
+}
+
+// k_steps MMAs of K = 16 with the A operand in TMEM (bf16 pairs, 8 columns per K step, lane = row) and B in shared memory
+__device__ __forceinline__ void mma_k16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_addr, int k_steps, uint32_t idesc = IDESC,
+                                           uint32_t b_rows = 128u) {
+  const uint32_t b_lbo = b_rows * 16u;
+  for (int kk = 0; kk < k_steps; ++kk) {
+    const uint64_t db = smem_desc(b_addr + kk * 2 * b_lbo, b_lbo);
+    const uint32_t acc = kk > 0 ? 1u : 0u;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a + (uint32_t)(kk * 8)),
+        "l"(db), "r"(idesc), "r"(acc), "r"(0u)
+        : "memory");
   }
 }
 
@@ -393,6 +422,8 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
   unsigned long long code_next = 0ull;
   if (cg == OPG && quarter_on && m < RT && tile0 < n_tiles && tile0 * RT + m < a.E) code_next = a.obs_code[tile0 * RT + m];
   int par = 0;                                             // tile parity of this group (maskbits / noise buffer)
+  uint32_t prev_cells = 0u;                                // the cells this row's thread set in the operand of the previous tile
+  bool prev_live = false;
   for (long long tile = tile0; tile < n_tiles; tile += tile_step, par ^= 1) {
     const long long e = tile * RT + m;
     const bool live = quarter_on && m < RT && e < a.E;
@@ -412,11 +443,23 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
       for (int o = 0; o < NACT; ++o) bits |= (mk[o] != 0 ? 1u : 0u) << o;
       s.maskbits[gi][par][m] = (uint16_t)bits;
     }
+    // The operand tile belongs to layer 1 alone (the operands of layers 2 and 3 live in TMEM): instead of clearing it,
+    // the row's thread takes back the few cells it set for the previous tile (layer 1 of that tile completed long ago)
+    const uint32_t apple = (a.kind == GW_ENV_MULTI) ? (a.apple_cells >> (8 * k)) & 0xFFu : a.apple_cells & 0xFFu;
+    if (prev_live) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t c = (prev_cells >> (8 * i)) & 0xFFu;
+        if (i < a.n && (int)c < cells) *reinterpret_cast<uint16_t*>(a_tile + umma_off(m, (int)c)) = 0;
+      }
+      if ((int)apple < cells) *reinterpret_cast<uint16_t*>(a_tile + umma_off(m, (int)apple)) = 0;
+    }
+    prev_live = live;
+    prev_cells = (uint32_t)code;
     if (live) {
       const uint32_t cellsw = (uint32_t)code, apples = (uint32_t)(code >> 32) & 3u;
       const bool fresh = (code >> 34) & 1ull;
       const bool apple_on = (a.kind == GW_ENV_MULTI) ? ((apples >> k) & 1u) : (apples & 1u);
-      const uint32_t apple = (a.kind == GW_ENV_MULTI) ? (a.apple_cells >> (8 * k)) & 0xFFu : a.apple_cells & 0xFFu;
       bool covered = false;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -479,40 +522,37 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
 
     // ---- LayerNorm 1 + ReLU -> operand of layer 2 (this thread: CPG columns of its row)
     ln_relu_epilogue<CPG, NGRP>(lane_addr + (uint32_t)col0, &s.ln1_g[col0], &s.ln1_b[col0], s.part[gi], cg, m,
-                                a_tile, col0, quarter_on, cg == 0, rows_sync);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                                lane_addr + (uint32_t)HID, col0, quarter_on, cg == 0, rows_sync);
     asm volatile("tcgen05.fence::before_thread_sync;");
     group_sync();
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    // ---- layer 2: D1[128x128] (TMEM columns 128..255) = A2[128x128] * W2^T.  (Rows RT..127 of a half-full tile hold
-    // whatever the layer-1 operand held there -- zeros: they only reach accumulator rows nobody reads.)
+    // ---- layer 2: D[128x128] (TMEM columns 0..127 again: LayerNorm 1 has consumed the layer-1 accumulator) =
+    // A2[128 x 144] (TMEM columns 128..199) * W2^T.  (Rows RT..127 of a half-full tile hold whatever TMEM held there: they
+    // only reach accumulator rows nobody reads.)
     if (lt == 0) {
-      mma_k16(tmem + (uint32_t)HID, a_addr, w2_addr, HID / 16 + 1);
+      mma_k16_ts(tmem, tmem + (uint32_t)HID, w2_addr, HID / 16 + 1);
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
     }
     mbar_wait(bar, phase);
     phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    // ---- LayerNorm 2 + ReLU -> operand of layer 3 (again this thread's columns of its row, again in the operand tile)
-    ln_relu_epilogue<CPG, NGRP>(lane_addr + (uint32_t)(HID + col0), &s.ln2_g[col0], &s.ln2_b[col0], s.part[gi], cg, m,
-                                a_tile, col0, quarter_on, false, rows_sync);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // ---- LayerNorm 2 + ReLU -> operand of layer 3 (again this thread's columns of its row, again TMEM columns 128..191)
+    ln_relu_epilogue<CPG, NGRP>(lane_addr + (uint32_t)col0, &s.ln2_g[col0], &s.ln2_b[col0], s.part[gi], cg, m,
+                                lane_addr + (uint32_t)HID, col0, quarter_on, false, rows_sync);
     asm volatile("tcgen05.fence::before_thread_sync;");
     group_sync();
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    // ---- layer 3: D[128 x 16] (TMEM columns 0..15; the layer-1 accumulator is long consumed) = A3[128x128] * W3p^T
+    // ---- layer 3: D[128 x 16] (TMEM columns 0..15; LayerNorm 2 has consumed the accumulator) = A3[128x128] * W3p^T
     if (lt == 0) {
-      mma_k16(tmem, a_addr, w3_addr, HID / 16, IDESC_N16, 16u);
+      mma_k16_ts(tmem, tmem + (uint32_t)HID, w3_addr, HID / 16, IDESC_N16, 16u);
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
     }
     mbar_wait(bar, phase);
     phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;");
-    // layer 3 has read its operand: back to the all-zero layer-1 operand for the next tile
-    for (int i = lt; i < (int)(op_bytes / 16); i += TPG) reinterpret_cast<uint4*>(a_tile)[i] = make_uint4(0, 0, 0, 0);
     float logit[NACT];
     if (quarter_on && cg == 0) {
       uint32_t r[16];
@@ -521,7 +561,7 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
       for (int o = 0; o < NACT; ++o) logit[o] = __uint_as_float(r[o]) + s.b3[o];
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-    group_sync();                                       // operand tile cleared, accumulators read: the next tile may start
+    group_sync();                                       // logits read: the next tile's layer 1 may overwrite them
     asm volatile("tcgen05.fence::after_thread_sync;");
     if (live && cg == 0) {
       // GumbelSoftmax head (the reference's output activation draws fresh Gumbel noise on EVERY forward, evaluation
