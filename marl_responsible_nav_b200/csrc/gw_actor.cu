@@ -6,20 +6,21 @@
 // One CTA = 512 threads on tiles of up to 128 rows (envs) of one learner; all three layers run on the tensor cores:
 //   layer 1  An observation is the constant map template plus <= 5 special cells, so W1*obs + b1 = c1 + W1 * delta with
 //            c1 = b1 + W1 * template (fp32, exact) and delta non-zero in <= 5 cells.  The A operand is an all-zero
-//            [128 x cells] bf16 tile in which each row's thread drops its <= 5 values (0.5, 1..5, 9.5, 10..14: exact in
-//            bf16) -- built from the 8-byte obs_code gw_step wrote; the 640-byte observation is never read.  cells / 16
-//            tcgen05.mma (M=128, N=128, K=16, bf16 -> fp32) against W1 (bf16, UMMA layout, one TMA bulk copy) accumulate
-//            in TMEM columns 0..127.
+//            [128 x (cells + 16)] bf16 tile in shared memory in which each row's thread drops its <= 5 values (0.5, 1..5,
+//            9.5, 10..14: exact in bf16) -- built from the 8-byte obs_code gw_step wrote; the 640-byte observation is
+//            never read -- and takes them back one tile later.  cells / 16 + 1 tcgen05.mma (M=128, N=128, K=16, bf16 ->
+//            fp32) against W1 (bf16, UMMA layout, one TMA bulk copy) accumulate in TMEM columns 0..127; the last K step
+//            carries the bias: A columns of 1.0 against W1 columns holding c1 as a bf16 head + a bf16 remainder.
 //   LN 1     warps that share a TMEM lane quarter (a warp's lanes are those of its id mod 4) split the 128 columns
 //            (tcgen05.ld, thread = row) and make two passes over the accumulator, both in packed fp32 pairs (FADD2 /
-//            FFMA2): + c1 and the statistics (partial sums joined through shared memory by the warps that share the rows),
-//            then + c1 again, normalise, affine, ReLU inside the bf16 conversion, into the A operand of layer 2 (UMMA
-//            K-major core matrices; it reuses the space of the layer-1 operand).  A chunk's TMEM load is in flight while
-//            the previous chunk is processed.
-//   layer 2  [128 x 128] x W2^T: 8 tcgen05.mma into TMEM columns 128..255.
-//   LN 2     the same column split: + b2, LayerNorm, ReLU, bf16 into the A operand of layer 3 (same space again).
-//   layer 3  [128 x 128] x W3p^T with W3 padded from 9 to 16 outputs: 8 tcgen05.mma with N = 16 into TMEM columns 0..15;
-//            the operand tile is cleared for the next tile once they have completed.
+//            FFMA2): the statistics (partial sums joined through shared memory by the warps that share the rows), then
+//            normalise, affine, ReLU inside the bf16 conversion, and tcgen05.st of the bf16 pairs into TMEM columns
+//            128..199: the A operand of layer 2 lives in tensor memory (lane = row, one 32-bit column per K pair), its
+//            bias K step (1, 1, 0 ...) included.  A chunk's TMEM load is in flight while the previous one is processed.
+//   layer 2  A2[128 x 144] (TMEM) x W2^T (shared memory): 9 tcgen05.mma with the A operand in TMEM, into columns 0..127
+//            again (LayerNorm 1 has consumed the layer-1 accumulator).
+//   LN 2     the same epilogue: LayerNorm, ReLU, bf16 pairs into TMEM columns 128..191 = the A operand of layer 3.
+//   layer 3  A3[128 x 128] (TMEM) x W3p^T with W3 padded from 9 to 16 outputs: 8 tcgen05.mma with N = 16 into columns 0..15.
 //   head     the first column group reads the 9 logits of its row (+ b3) and finishes Gumbel softmax / exploration noise /
 //            clip / mask / arg-max.  The noise (9 Gumbel values, 9 normals from 5 Box-Muller pairs: 5 Philox calls per
 //            row) is drawn and transformed by all threads while layer 1 runs; the last column group builds the next
@@ -118,8 +119,9 @@ __host__ __device__ constexpr int threads_of(int /*groups*/) { return 512; }
 // used while the batch does not fill the machine.  GROUPS = 2: two groups of 8 warps work on two tiles out of phase (two
 // column groups each, own operand tile, own TMEM columns, own barriers), sharing W1 / W2: while one group waits for its
 // MMAs or barriers the other one has the issue slots.
-// Dynamic shared memory: [GROUPS x a_tile: 128 x cells bf16 (layer-1 operand; its first 32 KB double as the layer-2
-// operand)] [w1: 128 x cells bf16] [Fixed<GROUPS>]
+// Dynamic shared memory: [GROUPS x a_tile: 128 x (cells + 16) bf16, the layer-1 operand] [w1: 128 x (cells + 16) bf16]
+// [Fixed<GROUPS>].  TMEM per group (256 columns): 0..127 the accumulator of layer 1, then of layer 2 (layer 3: 0..15);
+// 128..199 the A operand of layer 2 (144 K values as bf16 pairs), then 128..191 that of layer 3.
 template <int GROUPS>
 struct Fixed {
   static constexpr int NGRP = threads_of(GROUPS) / GROUPS / 128;         // column groups of the epilogues (warps sharing a TMEM lane quarter)
@@ -370,7 +372,19 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
   const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.bar[gi]), bar_w = (uint32_t)__cvta_generic_to_shared(&s.bar_w);
   const int RT = a.rows_per_tile;
 
-  // ---- one-time setup: 256 TMEM columns per group (two 128x128 fp32 accumulators), mbarriers, W1 / W2 by TMA, the small vectors
+  const int q = warp & 3, cg = (lt >> 5) >> 2;             // TMEM lane quarter (warp id mod 4: TPG is a multiple of 128), column group
+  const int m = q * 32 + lane;                             // this thread's row of the tile
+  const bool quarter_on = q * 32 < RT;                     // warp-uniform: a half-full tile fills lane quarters 0 and 1
+  const long long n_tiles = (a.E + RT - 1) / RT;
+  const long long tile0 = (long long)blockIdx.x * GROUPS + gi, tile_step = (long long)gridDim.x * GROUPS;
+  // Column group OPG builds the next tile's layer-1 operand and starts layer 1 while column group 0 is still in the head
+  // of the previous tile; the row's obs_code is fetched one tile ahead (its DRAM latency hides behind the tile in flight;
+  // the first one is issued before the one-time setup)
+  constexpr int OPG = NGRP - 1;
+  unsigned long long code_next = 0ull;
+  if (cg == OPG && quarter_on && m < RT && tile0 < n_tiles && tile0 * RT + m < a.E) code_next = a.obs_code[tile0 * RT + m];
+
+  // ---- one-time setup: 256 TMEM columns per group (accumulator + the operands of layers 2 and 3), mbarriers, W1 / W2 by TMA, the small vectors
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      (uint32_t)__cvta_generic_to_shared(&s.tmem_base)), "n"(GROUPS * 2 * HID));
@@ -408,19 +422,9 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
   uint32_t phase = 0;
   bool w_pending = true;
 
-  const int q = warp & 3, cg = (lt >> 5) >> 2;             // TMEM lane quarter (warp id mod 4: TPG is a multiple of 128), column group
-  const int m = q * 32 + lane;                             // this thread's row of the tile
   const int col0 = cg * CPG;
   const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-  const bool quarter_on = q * 32 < RT;                     // warp-uniform: a half-full tile fills lane quarters 0 and 1
-  const long long n_tiles = (a.E + RT - 1) / RT;
-  const long long tile0 = (long long)blockIdx.x * GROUPS + gi, tile_step = (long long)gridDim.x * GROUPS;
-  // Column group OPG builds the next tile's layer-1 operand and starts layer 1 while column group 0 is still in the head
-  // of the previous tile; the row's obs_code is fetched one tile ahead (its DRAM latency hides behind the tile in flight)
-  constexpr int OPG = NGRP - 1;
   auto op_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(11 + gi), "n"(128) : "memory"); };
-  unsigned long long code_next = 0ull;
-  if (cg == OPG && quarter_on && m < RT && tile0 < n_tiles && tile0 * RT + m < a.E) code_next = a.obs_code[tile0 * RT + m];
   int par = 0;                                             // tile parity of this group (maskbits / noise buffer)
   uint32_t prev_cells = 0u;                                // the cells this row's thread set in the operand of the previous tile
   bool prev_live = false;
@@ -493,11 +497,21 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
     // learner / step), TPG / RT threads per row; Philox call c of a row yields: c = 0, 1: Gumbel 4c..4c+3; c = 2: Gumbel 8
     // and normals 0, 1; c = 3: normals 2..5; c = 4: normals 6..8
     if (a.gumbel | a.explore) {
-      const int tsh = RT == ROWS ? TSH : TSH + 1, tpr = 1 << tsh, rr = lt >> tsh;   // RT is ROWS or ROWS / 2: no division
+      // RT is ROWS or ROWS / 2: no runtime division.  One tile per CTA (latency regime): the column group that builds the
+      // operand waits for obs_code and the weights first, so the other three share the rows (3 or 6 threads per row)
+      int tpr, rr, c_first;
+      if (GROUPS == 1) {
+        if (RT == ROWS) { tpr = 3; rr = lt / 3; c_first = lt - rr * 3; }
+        else { tpr = 6; rr = lt / 6; c_first = lt - rr * 6; }
+        if (cg == OPG) c_first = 8;                        // no call
+      } else {
+        const int tsh = RT == ROWS ? TSH : TSH + 1;
+        tpr = 1 << tsh; rr = lt >> tsh; c_first = lt & (tpr - 1);
+      }
       const long long er = tile * RT + rr;
       const int n_calls = a.explore ? 5 : 3;
       if (er < a.E)
-        for (int c = lt & (tpr - 1); c < n_calls; c += tpr) {
+        for (int c = c_first; c < n_calls; c += tpr) {
           const unsigned long long ge = (unsigned long long)(a.env_id_base + er);
           uint32_t w[4] = {(uint32_t)ge, (uint32_t)(ge >> 32) ^ ((uint32_t)k << 24) ^ ((uint32_t)c << 28),
                            a.step_lo, a.step_hi ^ 0xAC70u};
@@ -786,13 +800,15 @@ int gw_actor_forward(gw_actor* a, int64_t num_envs, const uint64_t* obs_code, co
   f.step_lo = (uint32_t)step; f.step_hi = (uint32_t)(step >> 32);
   const int nl = h->cfg.n_learners > 0 ? h->cfg.n_learners : 1;
   // half-full tiles while full ones would leave SMs without a CTA (latency regime)
-  f.rows_per_tile = ((num_envs + gwa::ROWS - 1) / gwa::ROWS) * nl < (long long)h->sm_count ? gwa::ROWS / 2 : gwa::ROWS;
+  // (half tiles only while ALL of them fit in one wave: two half tiles in sequence on one SM are slower than one full tile)
+  f.rows_per_tile = ((num_envs + gwa::ROWS / 2 - 1) / (gwa::ROWS / 2)) * nl <= (long long)h->sm_count ? gwa::ROWS / 2 : gwa::ROWS;
   const long long tiles = (num_envs + f.rows_per_tile - 1) / f.rows_per_tile;
   const long long cap = (long long)h->sm_count / nl > 0 ? (long long)h->sm_count / nl : 1;   // one 512-thread CTA per SM over all learners
-  // two tiles in flight per CTA once every SM has at least two tiles to work on (and the second operand tile fits)
+  // two tiles in flight per CTA as soon as some CTA would otherwise run two tiles one after the other (and the second
+  // operand tile fits): 16 384 envs x 2 learners 14.5 -> 12.5 us
   static const int groups_env = [] { const char* v = std::getenv("GW_ACTOR_GROUPS"); return v ? std::atoi(v) : 0; }();
   const bool two = groups_env ? groups_env == 2
-                              : (tiles >= 2 * cap && gwa::smem_bytes<2>(f.cpo) <= (size_t)227 * 1024);
+                              : (tiles > cap && gwa::smem_bytes<2>(f.cpo) <= (size_t)227 * 1024);
   if (two && gwa::smem_bytes<2>(f.cpo) <= (size_t)227 * 1024) {
     const long long pairs = (tiles + 1) / 2;
     dim3 grid((unsigned)(pairs < cap ? pairs : cap), (unsigned)h->cfg.n_learners);
