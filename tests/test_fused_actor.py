@@ -12,7 +12,7 @@ def _reference(actor, obs):
     return torch.softmax(logits, dim=-1)
 
 
-@pytest.mark.parametrize("E", [100, 4096, 20000])
+@pytest.mark.parametrize("E", [100, 4096, 20000, 200000])      # 200 000: ~10 tiles per warp group, one after the other
 def test_fused_actor_matches_torch_fp32(E):
     from marl_responsible_nav_b200 import BatchedGridWorld, FusedActor, maddpg
     env = BatchedGridWorld("Level 3", num_envs=E, fear=False, auto_reset=True, seed=5)
