@@ -48,6 +48,7 @@ constexpr int HID = 128, NACT = GW_N_ACTIONS, ROWS = 128, MAX_CELLS = GW_MAX_H *
 // whose first two columns of W hold the bias split into a bf16 head and a bf16 remainder (hi + lo = the fp32 value to
 // 2^-17): the LayerNorm epilogues read the accumulator as it is, no bias vector in shared memory.
 constexpr int KB = 16;
+constexpr int D3_COL = 200;                        // TMEM column (within a group's 256) of the layer-3 accumulator
 constexpr uint32_t ONES2 = 0x3F803F80u;             // bf16 (1.0, 1.0)
 
 struct ActorParams {                     // device-resident, per learner
@@ -133,7 +134,7 @@ struct Fixed {
   float noise[GROUPS][2][ROWS][19];                 // the head's noise per row: 9 Gumbel values, 9 standard normals (odd stride: no bank
                                                     // conflicts), double-buffered over consecutive tiles like maskbits
   uint16_t maskbits[GROUPS][2][ROWS];               // action-mask bits per row, double-buffered over consecutive tiles
-  alignas(8) unsigned long long bar[GROUPS], bar_w; // MMA completion per group; arrival of W1 / W2
+  alignas(8) unsigned long long bar[GROUPS], bar1[GROUPS], bar_w; // completion of layers 2 / 3 and of layer 1 per group; arrival of W1 / W2
   uint32_t tmem_base;
 };
 // K extent of the layer-1 operand tile (the only operand in shared memory): cells + the bias K step
@@ -369,7 +370,8 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
   auto rows_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(3 + gi * 4 + (warp & 3)), "n"(NGRP * 32) : "memory"); };
   const int k = blockIdx.y;                               // learner
   const ActorParams& P = a.params[k];
-  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.bar[gi]), bar_w = (uint32_t)__cvta_generic_to_shared(&s.bar_w);
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.bar[gi]), bar1 = (uint32_t)__cvta_generic_to_shared(&s.bar1[gi]),
+                 bar_w = (uint32_t)__cvta_generic_to_shared(&s.bar_w);
   const int RT = a.rows_per_tile;
 
   const int q = warp & 3, cg = (lt >> 5) >> 2;             // TMEM lane quarter (warp id mod 4: TPG is a multiple of 128), column group
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int g = 0; g < GROUPS; ++g) mbar_init((uint32_t)__cvta_generic_to_shared(&s.bar[g]), 1);
+    for (int g = 0; g < GROUPS; ++g) { mbar_init((uint32_t)__cvta_generic_to_shared(&s.bar[g]), 1); mbar_init((uint32_t)__cvta_generic_to_shared(&s.bar1[g]), 1); }
     mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(w1_bytes + (uint32_t)(HID * (HID + KB) * 2 + 16 * HID * 2)) : "memory");
@@ -428,12 +430,15 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
   int par = 0;                                             // tile parity of this group (maskbits / noise buffer)
   uint32_t prev_cells = 0u;                                // the cells this row's thread set in the operand of the previous tile
   bool prev_live = false;
-  for (long long tile = tile0; tile < n_tiles; tile += tile_step, par ^= 1) {
+  // ---- start of a tile (column group OPG only): the layer-1 operand -- the row's special cells, delta against the
+  // template, which is 0 on every active cell --, the row's action mask for the head, and layer 1 on the tensor cores.
+  // Called for the first tile before the loop and for tile t+1 between LayerNorm 2 and layer 3 of tile t: layer 1 of the
+  // next tile runs under layer 3, the head and the noise phase, and is long complete when LayerNorm 1 asks for it.
+  auto start_tile = [&](long long tile, int par) {
+    if (cg != OPG) return;
     const long long e = tile * RT + m;
     const bool live = quarter_on && m < RT && e < a.E;
-
-    // ---- layer-1 operand: the row's special cells (delta against the template, which is 0 on every active cell)
-    if (cg == OPG) {
+    {
     const unsigned long long code = code_next;
     if (quarter_on && m < RT) {
       const long long en = e + tile_step * RT;
@@ -489,11 +494,18 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
       if (w_pending) mbar_wait(bar_w, 0u);
       mma_k16(tmem, a_addr, w1_addr, cells / 16 + 1);
       // completion of all prior MMAs arrives on the mbarrier (implies tcgen05.fence::before_thread_sync)
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar1) : "memory");
     }
     }
+  };
+  if (tile0 < n_tiles) start_tile(tile0, 0);
+  uint32_t phase1 = 0;
+  for (long long tile = tile0; tile < n_tiles; tile += tile_step, par ^= 1) {
+    const long long e = tile * RT + m;
+    const bool live = quarter_on && m < RT && e < a.E;
+
     w_pending = false;
-    // ---- meanwhile: the head's noise (9 Gumbel values + 5 Box-Muller pairs per row, a pure function of seed / env /
+    // ---- while layer 1 may still run: the head's noise (9 Gumbel values + 5 Box-Muller pairs per row, a pure function of seed / env /
     // learner / step), TPG / RT threads per row; Philox call c of a row yields: c = 0, 1: Gumbel 4c..4c+3; c = 2: Gumbel 8
     // and normals 0, 1; c = 3: normals 2..5; c = 4: normals 6..8
     if (a.gumbel | a.explore) {
@@ -530,8 +542,8 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
           }
         }
     }
-    mbar_wait(bar, phase);
-    phase ^= 1u;
+    mbar_wait(bar1, phase1);                            // layer 1 of this tile (issued one tile ago)
+    phase1 ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;");
 
     // ---- LayerNorm 1 + ReLU -> operand of layer 2 (this thread: CPG columns of its row)
@@ -559,9 +571,12 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
     group_sync();
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    // ---- layer 3: D[128 x 16] (TMEM columns 0..15; LayerNorm 2 has consumed the accumulator) = A3[128x128] * W3p^T
+    // ---- the next tile starts here: its layer 1 may overwrite columns 0..127 (LayerNorm 2 has consumed them)
+    if (tile + tile_step < n_tiles) start_tile(tile + tile_step, par ^ 1);
+
+    // ---- layer 3: D[128 x 16] (TMEM columns 200..215, clear of both the accumulator and the operands) = A3[128x128] * W3p^T
     if (lt == 0) {
-      mma_k16_ts(tmem, tmem + (uint32_t)HID, w3_addr, HID / 16, IDESC_N16, 16u);
+      mma_k16_ts(tmem + (uint32_t)D3_COL, tmem + (uint32_t)HID, w3_addr, HID / 16, IDESC_N16, 16u);
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
     }
     mbar_wait(bar, phase);
@@ -570,13 +585,10 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
     float logit[NACT];
     if (quarter_on && cg == 0) {
       uint32_t r[16];
-      tmem_ld16(lane_addr, r);
+      tmem_ld16(lane_addr + (uint32_t)D3_COL, r);
 #pragma unroll
       for (int o = 0; o < NACT; ++o) logit[o] = __uint_as_float(r[o]) + s.b3[o];
     }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    group_sync();                                       // logits read: the next tile's layer 1 may overwrite them
-    asm volatile("tcgen05.fence::after_thread_sync;");
     if (live && cg == 0) {
       // GumbelSoftmax head (the reference's output activation draws fresh Gumbel noise on EVERY forward, evaluation
       // included) + Gaussian exploration noise (training), both drawn above
@@ -605,9 +617,9 @@ __global__ void __launch_bounds__(threads_of(GROUPS), 1) actor_forward_kernel(Fw
       }
       a.ids[e * a.nl + k] = (int8_t)best;
     }
-    // Column group 0 joins the next tile at its noise phase, the others are already there (column group OPG has built
-    // the operand and started layer 1).  maskbits / noise of this tile are rewritten two tiles on, the operand tile and
-    // part only behind barriers that every warp reaches after it is done with them.
+    // No barrier at the end of a tile: column group 0 joins the next one at its noise phase, the others are already
+    // there.  maskbits / noise of this tile are rewritten two tiles on and the logit columns by the next tile's layer 3,
+    // the operand tile and part only behind barriers that every warp reaches after it is done with them.
   }
   if (w_pending && tid == 0) mbar_wait(bar_w, 0u);         // a CTA whose first group has no tile must not exit with the copies in flight
 
