@@ -1,4 +1,4 @@
-"""Time gw_actor_forward alone (CUDA events, 50 launches after warm-up) at several batch sizes.
+"""Time gw_actor_forward alone (CUDA events, 50 graph-replayed launches after warm-up) at several batch sizes.
 GW_ACTOR_LN_RELOAD / GW_ACTOR_GROUPS select the kernel variant (read once per process)."""
 import json, os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
@@ -14,10 +14,17 @@ for E in [int(x) for x in (sys.argv[1:] or ["4096", "65536", "1048576"])]:
         for _ in range(5):
             fused.forward(out.obs_code, out.action_mask, training=training)
         torch.cuda.synchronize()
+        # 50 launches replayed from a CUDA graph: at small batches the eager call rate (~9 us per Python / ctypes call) would
+        # be what is measured
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(50):
+                fused.forward(out.obs_code, out.action_mask, training=training)
+        g.replay()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(50):
-            fused.forward(out.obs_code, out.action_mask, training=training)
+        g.replay()
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 50 * 1e3
