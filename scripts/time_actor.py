@@ -1,5 +1,5 @@
 """Time gw_actor_forward alone (CUDA events, 50 graph-replayed launches after warm-up) at several batch sizes.
-GW_ACTOR_LN_RELOAD / GW_ACTOR_GROUPS select the kernel variant (read once per process)."""
+GW_ACTOR_GROUPS=1|2 forces a regime (read once per process)."""
 import json, os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import torch
@@ -29,6 +29,5 @@ for E in [int(x) for x in (sys.argv[1:] or ["4096", "65536", "1048576"])]:
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 50 * 1e3
         rows = E * 2
-        print(json.dumps({"envs": E, "training": training, "reload": os.environ.get("GW_ACTOR_LN_RELOAD", "default"),
-                          "actor_kernel_us": us, "tflops": rows * 76032 / us / 1e6}), flush=True)
+        print(json.dumps({"envs": E, "training": training, "actor_kernel_us": us, "tflops": rows * 76032 / us / 1e6}), flush=True)
     del env, fused, agent
